@@ -1,0 +1,279 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes bindings for oracle/liboracle.so (the C restatement)
+and oracle/_ref/libcolate_ref.so (the unmodified reference behind oracle/ref_probe.cpp).
+
+Importable only from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product package never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+NBINS, MAX_BLOCKS = 185, 500
+
+_p = np.ctypeslib.ndpointer
+_f64 = _p(dtype=np.float64, flags="C_CONTIGUOUS")
+_i64 = _p(dtype=np.int64, flags="C_CONTIGUOUS")
+_i32 = _p(dtype=np.int32, flags="C_CONTIGUOUS")
+_u32 = _p(dtype=np.uint32, flags="C_CONTIGUOUS")
+_f32 = _p(dtype=np.float32, flags="C_CONTIGUOUS")
+_u8 = _p(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+
+def build(ref: bool = True):
+    """make -C oracle (liboracle.so; plus _ref/ when /root/reference is present)."""
+    subprocess.run(["make", "-s", "-C", HERE, "liboracle.so"] + (["ref"] if ref else []), check=True)
+
+
+class MT(C.Structure):
+    _fields_ = [("mt", C.c_uint32 * 624), ("pos", C.c_uint32)]
+
+    def words(self):
+        return np.frombuffer(self, dtype=np.uint32, count=625).copy()
+
+
+class GenomeC(C.Structure):
+    _fields_ = [("n", C.c_int64), ("chrom", C.c_void_p), ("bp", C.c_void_p), ("anc", C.c_void_p),
+                ("der", C.c_void_p), ("aaf", C.c_void_p), ("daf", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build(ref=False)
+        L = C.CDLL(path)
+        L.oracle_mt_seed.argtypes = [C.POINTER(MT), C.c_uint32]
+        L.oracle_mt_next.argtypes = [C.POINTER(MT)]
+        L.oracle_mt_next.restype = C.c_uint32
+        L.oracle_mt_words.argtypes = [C.c_uint32, C.c_long, C.c_int, _u32]
+        L.oracle_uniform_real_n.argtypes = [C.c_uint32, C.c_long, C.c_int, _f64]
+        L.oracle_uniform_int_n.argtypes = [C.c_uint32, C.c_long, C.c_int, C.c_int, _i32]
+        L.oracle_age_bins.argtypes = [_f64]
+        L.oracle_bin_of_double_age.argtypes = [C.c_double]
+        L.oracle_bin_of_float_age.argtypes = [C.c_float]
+        L.oracle_site_meta.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_char_p]
+        L.oracle_site_meta.restype = C.c_uint32
+        L.oracle_stage1.argtypes = [C.c_int, _i64, _i32, _f32, _f32, _u32,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.POINTER(GenomeC), C.POINTER(GenomeC), C.POINTER(MT),
+                                    _f64, _f64, _f64, _f64, _i64, _i64, _i64, _i64, C.POINTER(C.c_int64)]
+        L.oracle_draw_block_weights.argtypes = [C.POINTER(MT), C.c_int, C.c_int, _i32]
+        L.oracle_stage2.argtypes = [C.c_int, C.c_int, _i32, _f64, _f64, _f64, _f64, C.c_double, _f64, _f64]
+        L.oracle_age_generations.argtypes = [C.c_char_p, C.c_char_p, C.c_float, C.c_int, C.POINTER(C.c_double)]
+        L.oracle_age_generations.restype = C.c_double
+        L.oracle_epochs_from_bins.argtypes = [C.c_char_p, C.c_double, C.c_double, _f64, C.c_int, C.POINTER(C.c_int)]
+        L.oracle_epochs_from_coal_line.argtypes = [C.c_char_p, C.c_double, _f64, C.c_int]
+        L.oracle_estep.argtypes = [C.c_int, C.c_int, _f64, _f64, C.c_double, _f64, _f64]
+        L.oracle_estep.restype = C.c_double
+        L.oracle_em_run.argtypes = [C.c_int, _f64, _f64, _f64, _f64, C.c_int, _f64, C.POINTER(C.c_double)]
+        L.oracle_write_coal.argtypes = [C.c_char_p, C.c_int, C.c_int, _f64, _f64, C.c_int, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _genome_c(g):
+    arrs = [np.ascontiguousarray(x) for x in (g.chrom, g.bp, g.anc, g.der, g.aaf, g.daf)]
+    gc = GenomeC(g.n, *[a.ctypes.data for a in arrs])
+    gc._keep = arrs
+    return gc
+
+
+def age_bins():
+    out = np.zeros(NBINS)
+    lib().oracle_age_bins(out)
+    return out
+
+
+def mt_seed(seed: int) -> MT:
+    g = MT()
+    lib().oracle_mt_seed(C.byref(g), seed & 0xFFFFFFFF)
+    return g
+
+
+def stage1(sites, target, reference, seed=1, tmask=None, rmask=None, rng: MT | None = None):
+    """Oracle stage i on parsed arrays.  tmask/rmask: list of bytes (upper-cased mask sequence
+    per chromosome) or None.  Returns dict with num_blocks, the four [nb,185] fp64 block
+    vectors, the integer tallies, n_used and the generator state after the stage."""
+    L = lib()
+    rng = rng or mt_seed(seed)
+    n_chr = len(sites.chr_names)
+    z = lambda dt=np.float64: np.zeros((MAX_BLOCKS, NBINS), dtype=dt)
+    S, N, SE, NE = z(), z(), z(), z()
+    nS, nN, nE = z(np.int64), z(np.int64), z(np.int64)
+    nU = np.zeros(MAX_BLOCKS, dtype=np.int64)
+    tot = C.c_int64(0)
+
+    def mk(mask):
+        if mask is None:
+            return None, None, None
+        bufs = [C.create_string_buffer(m, len(m)) for m in mask]
+        ptrs = (C.c_char_p * n_chr)(*[C.cast(b, C.c_char_p) for b in bufs])
+        lens = (C.c_int64 * n_chr)(*[len(m) for m in mask])
+        return bufs, ptrs, lens
+
+    tb, tp, tl = mk(tmask)
+    rb, rp, rl = mk(rmask)
+    gt, gr = _genome_c(target), _genome_c(reference)
+    nb = L.oracle_stage1(n_chr, np.ascontiguousarray(sites.site_off, dtype=np.int64),
+                         np.ascontiguousarray(sites.pos), np.ascontiguousarray(sites.age_begin),
+                         np.ascontiguousarray(sites.age_end), np.ascontiguousarray(sites.meta()),
+                         C.cast(tp, C.c_void_p) if tp else None, C.cast(tl, C.c_void_p) if tl else None,
+                         C.cast(rp, C.c_void_p) if rp else None, C.cast(rl, C.c_void_p) if rl else None,
+                         C.byref(gt), C.byref(gr), C.byref(rng), S, N, SE, NE, nS, nN, nE, nU, C.byref(tot))
+    if nb < 0:
+        return {"num_blocks": nb}
+    return {"num_blocks": nb, "shared": S[:nb].copy(), "notshared": N[:nb].copy(), "shared_emp": SE[:nb].copy(),
+            "notshared_emp": NE[:nb].copy(), "n_shared": nS[:nb].copy(), "n_notshared": nN[:nb].copy(),
+            "n_emp": nE[:nb].copy(), "n_used": nU[:nb].copy(), "n_used_total": tot.value, "rng": rng}
+
+
+def draw_block_weights(rng: MT, R: int, num_blocks: int):
+    w = np.zeros((R, num_blocks), dtype=np.int32)
+    lib().oracle_draw_block_weights(C.byref(rng), R, num_blocks, w)
+    return w
+
+
+def stage2(weights, blk, age: float = 0.0):
+    R, nb = weights.shape
+    counts = np.zeros((R, 2, NBINS))
+    lib().oracle_stage2(R, nb, np.ascontiguousarray(weights), np.ascontiguousarray(blk["shared"]),
+                        np.ascontiguousarray(blk["notshared"]), np.ascontiguousarray(blk["shared_emp"]),
+                        np.ascontiguousarray(blk["notshared_emp"]), age, age_bins(), counts)
+    return counts
+
+
+def ages(target_age=None, reference_age=None, years_per_gen=None):
+    ypg = C.c_double(0)
+    a = lib().oracle_age_generations(target_age.encode() if target_age else None,
+                                     reference_age.encode() if reference_age else None,
+                                     years_per_gen if years_per_gen is not None else 0.0,
+                                     1 if years_per_gen is not None else 0, C.byref(ypg))
+    return a, ypg.value
+
+
+def epochs_from_bins(bins: str, age: float = 0.0, years_per_gen: float = 28.0):
+    ep = np.zeros(1024)
+    null = C.c_int(0)
+    n = lib().oracle_epochs_from_bins(bins.encode(), age, years_per_gen, ep, 1024, C.byref(null))
+    if n < 0:
+        raise ValueError("bad --bins")
+    return ep[:n].copy(), null.value
+
+
+def epochs_from_coal_line(line: str, age: float = 0.0):
+    ep = np.zeros(1024)
+    n = lib().oracle_epochs_from_coal_line(line.encode(), age, ep, 1024)
+    if n < 0:
+        raise ValueError("bad --coal epoch line")
+    return ep[:n].copy()
+
+
+def estep(shared: bool, epochs, rates, t: float):
+    E = len(epochs)
+    num, den = np.zeros(E), np.zeros(E)
+    ll = lib().oracle_estep(1 if shared else 0, E, np.ascontiguousarray(epochs, dtype=np.float64),
+                            np.ascontiguousarray(rates, dtype=np.float64), t, num, den)
+    return ll, num, den
+
+
+def em_run(epochs, rates_init, counts, max_iter=100000):
+    E = len(epochs)
+    out = np.zeros(E)
+    ll = C.c_double(0)
+    it = lib().oracle_em_run(E, np.ascontiguousarray(epochs, dtype=np.float64),
+                             np.ascontiguousarray(rates_init, dtype=np.float64), age_bins(),
+                             np.ascontiguousarray(counts, dtype=np.float64), max_iter, out, C.byref(ll))
+    return out, it, ll.value
+
+
+def write_coal(path, epochs, rates, is_ancient=False, ep_null=0):
+    rates = np.ascontiguousarray(rates, dtype=np.float64).copy()
+    R, E = rates.shape
+    rc = lib().oracle_write_coal(path.encode(), R, E, np.ascontiguousarray(epochs, dtype=np.float64), rates,
+                                 1 if is_ancient else 0, ep_null)
+    if rc:
+        raise OSError(path)
+    return rates
+
+
+# ---------------------------------------------------------------- compiled reference
+_ref = None
+
+
+def ref_available() -> bool:
+    return os.path.exists(os.path.join(HERE, "_ref", "libcolate_ref.so"))
+
+
+def ref_cli() -> str | None:
+    p = os.path.join(HERE, "_ref", "Colate")
+    return p if os.path.exists(p) else None
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        L = C.CDLL(os.path.join(HERE, "_ref", "libcolate_ref.so"))
+        L.ref_parse_tmptmp.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_char_p, C.c_char_p,
+                                       C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_double, C.c_double, C.c_int,
+                                       _f64, _f64, _f64, _f64, _f64, _u32, _u32]
+        for nm in ("ref_em_shared", "ref_em_notshared"):
+            f = getattr(L, nm)
+            f.argtypes = [C.c_int, _f64, _f64, C.c_double, C.c_double, _f64, _f64]
+            f.restype = C.c_double
+        for nm in ("ref_em_simplified_shared", "ref_em_simplified_notshared"):
+            f = getattr(L, nm)
+            f.argtypes = [C.c_int, _f64, _f64, C.c_double, _f64, _f64]
+            f.restype = C.c_double
+        L.ref_uniform_real.argtypes = [C.c_int, C.c_long, C.c_int, _f64]
+        L.ref_uniform_int.argtypes = [C.c_int, C.c_long, C.c_int, C.c_int, _i32]
+        L.ref_mt_words.argtypes = [C.c_int, C.c_long, C.c_int, _u32]
+        L.ref_bin_of_float_age.argtypes = [C.c_float]
+        L.ref_bin_of_double_age.argtypes = [C.c_double]
+        _ref = L
+    return _ref
+
+
+def ref_parse_tmptmp(dirname, chr_names, prefix, target, reference, seed=1, tmask=None, rmask=None):
+    """Runs the reference's parse_tmptmp on files written by colate_b200.synth.write_dataset."""
+    L = ref()
+    n = len(chr_names)
+    arr = lambda xs: (C.c_char_p * n)(*[x.encode() for x in xs])
+    names = arr(chr_names)
+    muts = arr([os.path.join(dirname, f"{prefix}_chr{c}.mut") for c in chr_names])
+    tm = arr([os.path.join(dirname, f"{tmask}_chr{c}.fa") for c in chr_names]) if tmask else None
+    rm = arr([os.path.join(dirname, f"{rmask}_chr{c}.fa") for c in chr_names]) if rmask else None
+    z = lambda: np.zeros((MAX_BLOCKS, NBINS))
+    S, N, SE, NE = z(), z(), z(), z()
+    rest = np.zeros(2)
+    mt = np.zeros(625, dtype=np.uint32)
+    nxt = np.zeros(8, dtype=np.uint32)
+    nb = L.ref_parse_tmptmp(n, names, muts, os.path.join(dirname, target + ".colate.in").encode(),
+                            os.path.join(dirname, reference + ".colate.in").encode(), tm, rm, 0.0, 0.0, seed,
+                            S, N, SE, NE, rest, mt, nxt)
+    return {"num_blocks": nb, "shared": S[:nb].copy(), "notshared": N[:nb].copy(), "shared_emp": SE[:nb].copy(),
+            "notshared_emp": NE[:nb].copy(), "emp_rest": rest, "mt": mt, "next_words": nxt}
+
+
+def ref_estep(shared: bool, epochs, rates, t: float):
+    E = len(epochs)
+    num, den = np.zeros(E), np.zeros(E)
+    f = ref().ref_em_shared if shared else ref().ref_em_notshared
+    ll = f(E, np.ascontiguousarray(epochs, dtype=np.float64), np.ascontiguousarray(rates, dtype=np.float64), t, t, num, den)
+    return ll, num, den
+
+
+def ref_estep_simplified(shared: bool, epochs, rates, t: float):
+    E = len(epochs)
+    num, den = np.zeros(E), np.zeros(E)
+    f = ref().ref_em_simplified_shared if shared else ref().ref_em_simplified_notshared
+    ll = f(E, np.ascontiguousarray(epochs, dtype=np.float64), np.ascontiguousarray(rates, dtype=np.float64), t, num, den)
+    return ll, num, den
