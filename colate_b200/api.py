@@ -1,0 +1,287 @@
+"""Host-side mirror of the reference's `mut()` driver (include/coal/coal.cpp:3071-3863) on top
+of the C-ABI.  Names follow the reference: sites = rows of the .mut files, genomes = .colate.in
+record streams, blocks = 30 Mb genomic blocks, replicates = block-bootstrap replicates.
+
+Everything that computes goes through libcolate_b200.so (CUDA); this module only marshals
+arrays and mirrors the control flow of mut().
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import MAX_BLOCKS, MT_WORDS, NBINS, check, lib, ptr
+
+
+def age_bins() -> np.ndarray:
+    """age_bin[], coal.cpp:3129-3137."""
+    out = np.zeros(NBINS)
+    lib().colate_age_bins(out)
+    return out
+
+
+def mt_seed(seed: int) -> np.ndarray:
+    """std::mt19937::seed(seed) as a 624-word state window (coal.cpp:3157-3162)."""
+    w = np.zeros(MT_WORDS, dtype=np.uint32)
+    lib().colate_mt_seed(seed & 0xFFFFFFFF, w)
+    return w
+
+
+def draw_block_weights(mt_state: np.ndarray, R: int, num_blocks: int) -> np.ndarray:
+    """Block multiplicities per replicate (coal.cpp:3350-3357); advances mt_state in place."""
+    w = np.zeros((R, num_blocks), dtype=np.int32)
+    lib().colate_draw_block_weights(mt_state, R, num_blocks, w)
+    return w
+
+
+def ages(target_age: str | None = None, reference_age: str | None = None, years_per_gen: float | None = None):
+    """(age in generations, years_per_gen), coal.cpp:3105-3118."""
+    ypg = C.c_double(0)
+    a = lib().colate_age_generations(target_age.encode() if target_age is not None else None,
+                                     reference_age.encode() if reference_age is not None else None,
+                                     0 if years_per_gen is None else 1, 0.0 if years_per_gen is None else years_per_gen,
+                                     C.byref(ypg))
+    return a, ypg.value
+
+
+def epochs_from_bins(bins: str, age: float = 0.0, years_per_gen: float = 28.0):
+    """Epoch grid of --bins x,y,step (coal.cpp:3553-3630) -> (epochs, ep_null)."""
+    ep = np.zeros(4096)
+    null = C.c_int(0)
+    n = check(lib().colate_epochs_from_bins(bins.encode(), age, years_per_gen, ep, 4096, C.byref(null)))
+    return ep[:n].copy(), null.value
+
+
+def epochs_from_coal_file(path: str, age: float = 0.0):
+    ep, r = np.zeros(4096), np.zeros(4096)
+    n = check(lib().colate_epochs_from_coal_file(path.encode(), age, ep, r, 4096))
+    return ep[:n].copy(), r[:n].copy()
+
+
+def chr_ranges(n_chr: int, rec_chrom: np.ndarray):
+    """Record range per --chr entry, emulating the chromosome seek (coal.cpp:2125-2145)."""
+    rec_chrom = np.ascontiguousarray(rec_chrom, dtype=np.int32)
+    first = np.zeros(n_chr, dtype=np.int64)
+    end = np.zeros(n_chr, dtype=np.int64)
+    check(lib().colate_chr_ranges(n_chr, rec_chrom.shape[0], rec_chrom, first, end))
+    return first, end
+
+
+def read_mut(path: str):
+    """Relate .mut[.gz] -> (pos, age_begin, age_end, meta) (mutations.cpp:56-283)."""
+    n = check(lib().colate_read_mut(path.encode(), 0, None, None, None, None))
+    pos = np.zeros(n, np.int32); ab = np.zeros(n, np.float32); ae = np.zeros(n, np.float32); meta = np.zeros(n, np.uint32)
+    check(lib().colate_read_mut(path.encode(), n, ptr(pos), ptr(ab), ptr(ae), ptr(meta)))
+    return pos, ab, ae, meta
+
+
+def read_colate_in(path: str, chr_names):
+    """.colate.in -> (rec_chrom, bp, aaf, daf, alleles) (coal.cpp:2505-2514)."""
+    names = (C.c_char_p * len(chr_names))(*[s.encode() for s in chr_names])
+    n = check(lib().colate_read_colate_in(path.encode(), len(chr_names), names, 0, None, None, None, None, None))
+    rc = np.zeros(n, np.int32); bp = np.zeros(n, np.int32); aaf = np.zeros(n, np.int32); daf = np.zeros(n, np.int32)
+    al = np.zeros(n, np.uint16)
+    check(lib().colate_read_colate_in(path.encode(), len(chr_names), names, n, ptr(rc), ptr(bp), ptr(aaf), ptr(daf), ptr(al)))
+    return rc, bp, aaf, daf, al
+
+
+def mask_bits_from_fasta(path: str, pos: np.ndarray, row0: int, bits: np.ndarray):
+    """fasta mask at the site positions -> pass bits of rows [row0, row0+len(pos)) (data.cpp:213-237, coal.cpp:2169-2174)."""
+    pos = np.ascontiguousarray(pos, dtype=np.int32)
+    check(lib().colate_mask_bits_from_fasta(path.encode(), pos.shape[0], ptr(pos), row0, ptr(bits)))
+
+
+def mask_bits_from_seq(seqs, site_off, pos) -> np.ndarray:
+    """Same as mask_bits_from_fasta for in-memory (already upper-cased) per-chromosome sequences."""
+    n = int(site_off[-1])
+    ok = np.ones(n, dtype=bool)
+    for c, s in enumerate(seqs):
+        lo, hi = int(site_off[c]), int(site_off[c + 1])
+        p = pos[lo:hi].astype(np.int64)
+        arr = np.frombuffer(s, dtype=np.uint8)
+        inside = (p >= 0) & (p < arr.shape[0])
+        okc = np.ones(hi - lo, dtype=bool)
+        okc[inside] = arr[p[inside] - 1] == ord("P")
+        ok[lo:hi] = okc
+    pad = (-n) % 32
+    by = np.packbits(np.concatenate([ok, np.zeros(pad, dtype=bool)]), bitorder="little")
+    return np.ascontiguousarray(by).view("<u4").astype(np.uint32).reshape(-1)
+
+
+@dataclass
+class Stage1Result:
+    num_blocks: int
+    block_stats: np.ndarray     # [num_blocks, 4, 185] fp64: shared, notshared, shared_emp, notshared_emp
+    block_tallies: np.ndarray   # [num_blocks, 3, 185] int64: samples->shared, samples->notshared, rows->emp
+    n_used: int
+    mt_state: np.ndarray        # state window after the stage
+
+
+class Handle:
+    """One GPU.  Mirrors the data flow of mut(): readers -> parse_tmptmp -> bootstrap -> EM."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        check(lib().colate_create(device, C.byref(h)))
+        self._h = h
+        self.n_chr = 0
+        self.n_site = 0
+
+    def close(self):
+        if self._h:
+            lib().colate_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self) -> int:
+        return lib().colate_stream(self._h)
+
+    # ---- inputs
+    def set_sites(self, site_off, pos, age_begin, age_end, meta):
+        site_off = np.ascontiguousarray(site_off, dtype=np.int64)
+        self.n_chr = site_off.shape[0] - 1
+        self.n_site = int(site_off[-1])
+        a = [np.ascontiguousarray(x, dtype=dt) for x, dt in ((pos, np.int32), (age_begin, np.float32), (age_end, np.float32), (meta, np.uint32))]
+        check(lib().colate_set_sites(self._h, self.n_chr, ptr(site_off), *[ptr(x) for x in a], 0))
+
+    def set_sites_device(self, n_chr, n_site, site_off_ptr, pos_ptr, ab_ptr, ae_ptr, meta_ptr):
+        """Device pointers (e.g. torch tensors' data_ptr()); site_off_ptr is a device pointer too."""
+        self.n_chr, self.n_site = n_chr, n_site
+        check(lib().colate_set_sites(self._h, n_chr, C.c_void_p(site_off_ptr), C.c_void_p(pos_ptr), C.c_void_p(ab_ptr),
+                                     C.c_void_p(ae_ptr), C.c_void_p(meta_ptr), 1))
+
+    def set_genome(self, slot, rec_chrom, bp, aaf, daf, alleles):
+        first, end = chr_ranges(self.n_chr, rec_chrom)
+        a = [np.ascontiguousarray(x, dtype=dt) for x, dt in ((bp, np.int32), (aaf, np.int32), (daf, np.int32), (alleles, np.uint16))]
+        check(lib().colate_set_genome(self._h, slot, a[0].shape[0], ptr(first), ptr(end), *[ptr(x) for x in a], 0))
+        return first, end
+
+    def set_genome_device(self, slot, n_rec, first_ptr, end_ptr, bp_ptr, aaf_ptr, daf_ptr, alleles_ptr):
+        check(lib().colate_set_genome(self._h, slot, n_rec, C.c_void_p(first_ptr), C.c_void_p(end_ptr), C.c_void_p(bp_ptr),
+                                      C.c_void_p(aaf_ptr), C.c_void_p(daf_ptr), C.c_void_p(alleles_ptr), 1))
+
+    def set_mask(self, slot, pass_bits):
+        if pass_bits is None:
+            check(lib().colate_set_mask(self._h, slot, None, 0))
+        else:
+            pass_bits = np.ascontiguousarray(pass_bits, dtype=np.uint32)
+            assert pass_bits.shape[0] == (self.n_site + 31) // 32
+            check(lib().colate_set_mask(self._h, slot, ptr(pass_bits), 0))
+
+    # ---- stage i
+    def stage1_flags(self, target_slot=0, reference_slot=1):
+        used = np.zeros(self.n_chr, dtype=np.int64)
+        blocks = np.zeros(self.n_chr, dtype=np.int32)
+        check(lib().colate_stage1_flags(self._h, target_slot, reference_slot, ptr(used), ptr(blocks)))
+        return used, blocks
+
+    def stage1_sample(self, mt_state, used_rank_base=0, block_base=0, n_blocks=None, want_state=True):
+        nb = MAX_BLOCKS if n_blocks is None else n_blocks
+        stats = np.zeros((nb, 4, NBINS))
+        tallies = np.zeros((nb, 3, NBINS), dtype=np.int64)
+        mt_state = np.ascontiguousarray(mt_state, dtype=np.uint32)
+        out_state = np.zeros(MT_WORDS, dtype=np.uint32) if want_state else None
+        check(lib().colate_stage1_sample(self._h, ptr(mt_state), used_rank_base, block_base, ptr(stats), ptr(tallies),
+                                         ptr(out_state)))
+        return stats, tallies, out_state
+
+    def stage1(self, mt_state, target_slot=0, reference_slot=1) -> Stage1Result:
+        """parse_tmptmp (coal.cpp:2072) on one GPU."""
+        stats = np.zeros((MAX_BLOCKS, 4, NBINS))
+        tallies = np.zeros((MAX_BLOCKS, 3, NBINS), dtype=np.int64)
+        nb, nu = C.c_int(0), C.c_int64(0)
+        mt_state = np.ascontiguousarray(mt_state, dtype=np.uint32)
+        out_state = np.zeros(MT_WORDS, dtype=np.uint32)
+        check(lib().colate_stage1(self._h, target_slot, reference_slot, ptr(mt_state), C.byref(nb), ptr(stats), ptr(tallies),
+                                  C.byref(nu), ptr(out_state)))
+        return Stage1Result(nb.value, stats[:nb.value].copy(), tallies[:nb.value].copy(), nu.value, out_state)
+
+    def stage1_timing(self) -> dict:
+        t = _lib.Stage1Timing()
+        check(lib().colate_last_stage1_timing(self._h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in t._fields_}
+
+    # ---- stage ii / iii
+    def stage2_bootstrap(self, block_weights, block_stats, age=0.0, fetch=True):
+        w = np.ascontiguousarray(block_weights, dtype=np.int32)
+        R, nb = w.shape
+        bs = np.ascontiguousarray(block_stats, dtype=np.float64)
+        assert bs.shape == (nb, 4, NBINS)
+        counts = np.zeros((R, 2, NBINS)) if fetch else None
+        check(lib().colate_stage2_bootstrap(self._h, R, nb, ptr(w), ptr(bs), age, ptr(counts)))
+        return counts
+
+    def stage3_em(self, R, epochs, rates_init, counts=None, max_iter=100000):
+        ep = np.ascontiguousarray(epochs, dtype=np.float64)
+        ri = np.ascontiguousarray(rates_init, dtype=np.float64)
+        E = ep.shape[0]
+        cn = None if counts is None else np.ascontiguousarray(counts, dtype=np.float64)
+        rates = np.zeros((R, E)); iters = np.zeros(R, dtype=np.int32); ll = np.zeros(R)
+        check(lib().colate_stage3_em(self._h, R, E, ptr(ep), ptr(ri), ptr(cn), max_iter, ptr(rates), ptr(iters), ptr(ll)))
+        return rates, iters, ll
+
+    def estep(self, shared: bool, epochs, rates, t):
+        ep = np.ascontiguousarray(epochs, dtype=np.float64)
+        r = np.ascontiguousarray(rates, dtype=np.float64)
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        E, n = ep.shape[0], t.shape[0]
+        num, den, ll = np.zeros((n, E)), np.zeros((n, E)), np.zeros(n)
+        check(lib().colate_estep(self._h, 1 if shared else 0, E, ptr(ep), ptr(r), n, ptr(t), ptr(num), ptr(den), ptr(ll)))
+        return ll, num, den
+
+    def mt_stream(self, mt_state, word0, n_words, log2_chunk_sites=3):
+        """Test hook: engine words [word0, word0+n) generated by the device path (+ window after)."""
+        out = np.zeros(n_words + MT_WORDS, dtype=np.uint32)
+        check(lib().colate_test_mt_stream(self._h, np.ascontiguousarray(mt_state, dtype=np.uint32), word0, n_words,
+                                          log2_chunk_sites, out))
+        return out[:n_words], out[n_words:]
+
+    # ---- convenience: load a synth.Sites / synth.Genome pair
+    def load(self, sites, target, reference, tmask=None, rmask=None):
+        self.set_sites(sites.site_off, sites.pos, sites.age_begin, sites.age_end, sites.meta())
+        for slot, g in ((0, target), (1, reference)):
+            self.set_genome(slot, g.chrom, g.bp, g.aaf, g.daf, g.anc.astype(np.uint16) | (g.der.astype(np.uint16) << 8))
+        self.set_mask(0, None if tmask is None else mask_bits_from_seq(tmask, sites.site_off, sites.pos))
+        self.set_mask(1, None if rmask is None else mask_bits_from_seq(rmask, sites.site_off, sites.pos))
+
+
+def mut(handle: Handle, seed: int, bins: str | None = "3,7,0.2", num_bootstraps: int = 1, target_age=None,
+        reference_age=None, years_per_gen=None, coal_file: str | None = None, max_iter: int = 100000):
+    """mut() (coal.cpp:3071-3863) after the readers: stage i -> ii -> iii on one GPU.
+    Returns dict(epochs, rates[R,E], iters[R], ep_null, is_ancient, num_blocks, stage1=Stage1Result, counts)."""
+    age, ypg = ages(target_age, reference_age, years_per_gen)
+    state = mt_seed(seed)
+    s1 = handle.stage1(state)
+    w = draw_block_weights(s1.mt_state, num_bootstraps, s1.num_blocks)
+    counts = handle.stage2_bootstrap(w, s1.block_stats, age)
+    if coal_file is not None:
+        epochs, rates_init = epochs_from_coal_file(coal_file, age)
+        ep_null = 0
+    else:
+        epochs, ep_null = epochs_from_bins(bins, age, ypg)
+        rates_init = np.full(epochs.shape[0], 1.0 / 20000.0)
+    rates, iters, ll = handle.stage3_em(num_bootstraps, epochs, rates_init, None, max_iter)
+    return dict(epochs=epochs, rates=rates, iters=iters, ll=ll, ep_null=ep_null, is_ancient=age > 0.0,
+                num_blocks=s1.num_blocks, stage1=s1, counts=counts, weights=w)
+
+
+def write_coal(path: str, epochs, rates, is_ancient=False, ep_null=0):
+    r = np.ascontiguousarray(rates, dtype=np.float64).copy()
+    check(lib().colate_write_coal(path.encode(), r.shape[0], r.shape[1], np.ascontiguousarray(epochs, dtype=np.float64), r,
+                                  1 if is_ancient else 0, ep_null))
+    return r
+
+
+def write_bin(path: str, epochs, rates, iters):
+    r = np.ascontiguousarray(rates, dtype=np.float64)
+    check(lib().colate_write_bin(path.encode(), r.shape[0], r.shape[1], np.ascontiguousarray(epochs, dtype=np.float64), r,
+                                 np.ascontiguousarray(iters, dtype=np.int32)))

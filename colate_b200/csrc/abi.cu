@@ -1,0 +1,347 @@
+// C-ABI glue (include/colate_b200.h): handle management, uploads, stage drivers.
+#include "device.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+using namespace colate;
+
+namespace {
+
+int copy_in(void* dst, const void* src, size_t bytes, int location, cudaStream_t s)
+{
+  if (bytes == 0) return 0;
+  CK(cudaMemcpyAsync(dst, src, bytes, location ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  return 0;
+}
+
+int ensure_tables(colate_handle* h)
+{
+  if (h->thr_ready) return 0;
+  double thr[NTHR], ab[NBINS];
+  if (!bin_thresholds(thr)) return fail(COLATE_ERR_ARG, "host libm log() is not monotone around an age-bin threshold");
+  colate_age_bins(ab);
+  CK(h->thr10.ensure(sizeof thr));
+  CK(h->d_agebin.ensure(sizeof ab));
+  CK(cudaMemcpyAsync(h->thr10.p, thr, sizeof thr, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_agebin.p, ab, sizeof ab, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->thr_ready = true;
+  return 0;
+}
+
+int pick_chunk_log2(int64_t n_used)
+{
+  if (const char* e = getenv("COLATE_CHUNK_LOG2")) return std::max(0, std::min(30, atoi(e)));
+  int64_t per = n_used / 296;  // aim at >= 2 generator chunks per SM
+  int k = 0;
+  while ((int64_t(2) << k) <= per) k++;
+  return std::max(3, std::min(k, 24));
+}
+
+}  // namespace
+
+extern "C" {
+
+int colate_create(int device, colate_handle** out)
+{
+  if (!out) return fail(COLATE_ERR_ARG, "out is null");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(COLATE_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(COLATE_ERR_ARG, "device index out of range");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(COLATE_ERR_CUDA, "device is not sm_100 (kernels are built for sm_100a only)");
+  colate_handle* h = new colate_handle();
+  h->device = device;
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
+  *out = h;
+  return 0;
+}
+
+void colate_destroy(colate_handle* h)
+{
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  DevBuf* bufs[] = {&h->site_off, &h->pos, &h->ab, &h->ae, &h->meta, &h->candR, &h->candT, &h->use, &h->word_rank, &h->scan_tmp,
+                    &h->chr_used, &h->chr_blocks, &h->chr_block_base, &h->misc, &h->u_ab, &h->u_ae, &h->u_fd, &h->u_fa, &h->u_dafr,
+                    &h->u_nr, &h->u_blk, &h->blk_rank_start, &h->tile_start, &h->partial_f, &h->partial_n, &h->out_f, &h->out_n,
+                    &h->windows, &h->rng_stream, &h->poly, &h->thr10, &h->d_counts, &h->d_blockstats, &h->d_weights, &h->d_epochs,
+                    &h->d_rates, &h->d_iters, &h->d_ll, &h->d_agebin, &h->d_tmp};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& g : h->genomes) {
+    DevBuf* gb[] = {&g.bp, &g.aaf, &g.daf, &g.alleles, &g.chr_first, &g.chr_end, &g.mask_bits, &g.j_aaf, &g.j_daf, &g.j_prevbp, &g.j_flag};
+    for (DevBuf* b : gb) b->release();
+  }
+  for (auto& ev : h->ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+void* colate_stream(colate_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int colate_set_sites(colate_handle* h, int n_chr, const int64_t* site_off, const int32_t* pos, const float* age_begin,
+                     const float* age_end, const uint32_t* meta, int location)
+{
+  if (!h || n_chr <= 0 || !site_off) return fail(COLATE_ERR_ARG, "colate_set_sites: bad arguments");
+  CK(cudaSetDevice(h->device));
+  std::vector<int64_t> off(n_chr + 1);
+  if (location) CK(cudaMemcpy(off.data(), site_off, (n_chr + 1) * 8, cudaMemcpyDeviceToHost));
+  else memcpy(off.data(), site_off, (n_chr + 1) * 8);
+  if (off[0] != 0) return fail(COLATE_ERR_ARG, "site_off[0] must be 0");
+  for (int c = 0; c < n_chr; c++) if (off[c + 1] < off[c]) return fail(COLATE_ERR_ARG, "site_off must be non-decreasing");
+  const int64_t n = off[n_chr];
+  if (n >= (int64_t(1) << 31)) return fail(COLATE_ERR_ARG, "more than 2^31 rows per handle");
+  CK(h->site_off.ensure((n_chr + 1) * 8)); CK(h->pos.ensure(n * 4 + 4)); CK(h->ab.ensure(n * 4 + 4));
+  CK(h->ae.ensure(n * 4 + 4)); CK(h->meta.ensure(n * 4 + 4));
+  CK(cudaMemcpyAsync(h->site_off.p, off.data(), (n_chr + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+  int rc;
+  if ((rc = copy_in(h->pos.p, pos, n * 4, location, h->stream))) return rc;
+  if ((rc = copy_in(h->ab.p, age_begin, n * 4, location, h->stream))) return rc;
+  if ((rc = copy_in(h->ae.p, age_end, n * 4, location, h->stream))) return rc;
+  if ((rc = copy_in(h->meta.p, meta, n * 4, location, h->stream))) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  h->n_chr = n_chr;
+  h->n_site = n;
+  h->h_site_off = off;
+  h->sites_set = true;
+  h->flags_done = false;
+  for (auto& g : h->genomes) { g.joined = false; g.has_mask = false; }
+  return 0;
+}
+
+int colate_set_genome(colate_handle* h, int slot, int64_t n_rec, const int64_t* chr_first, const int64_t* chr_end,
+                      const int32_t* bp, const int32_t* aaf, const int32_t* daf, const uint16_t* alleles, int location)
+{
+  if (!h || slot < 0 || slot >= COLATE_MAX_GENOMES || n_rec < 0) return fail(COLATE_ERR_ARG, "colate_set_genome: bad arguments");
+  if (!h->sites_set) return fail(COLATE_ERR_STATE, "colate_set_genome: call colate_set_sites first");
+  CK(cudaSetDevice(h->device));
+  GenomeDev& g = h->genomes[slot];
+  const int nc = h->n_chr;
+  CK(g.bp.ensure(n_rec * 4 + 4)); CK(g.aaf.ensure(n_rec * 4 + 4)); CK(g.daf.ensure(n_rec * 4 + 4)); CK(g.alleles.ensure(n_rec * 2 + 4));
+  CK(g.chr_first.ensure(nc * 8)); CK(g.chr_end.ensure(nc * 8));
+  int rc;
+  if ((rc = copy_in(g.chr_first.p, chr_first, nc * 8, location, h->stream))) return rc;
+  if ((rc = copy_in(g.chr_end.p, chr_end, nc * 8, location, h->stream))) return rc;
+  if ((rc = copy_in(g.bp.p, bp, n_rec * 4, location, h->stream))) return rc;
+  if ((rc = copy_in(g.aaf.p, aaf, n_rec * 4, location, h->stream))) return rc;
+  if ((rc = copy_in(g.daf.p, daf, n_rec * 4, location, h->stream))) return rc;
+  if ((rc = copy_in(g.alleles.p, alleles, n_rec * 2, location, h->stream))) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  g.n_rec = n_rec;
+  g.set = true;
+  g.joined = false;
+  h->flags_done = false;
+  return 0;
+}
+
+int colate_set_mask(colate_handle* h, int slot, const uint32_t* pass_bits, int location)
+{
+  if (!h || slot < 0 || slot >= COLATE_MAX_GENOMES) return fail(COLATE_ERR_ARG, "colate_set_mask: bad arguments");
+  if (!h->sites_set) return fail(COLATE_ERR_STATE, "colate_set_mask: call colate_set_sites first");
+  CK(cudaSetDevice(h->device));
+  GenomeDev& g = h->genomes[slot];
+  h->flags_done = false;
+  if (!pass_bits) { g.has_mask = false; return 0; }
+  const int64_t nw = (h->n_site + 31) / 32;
+  CK(g.mask_bits.ensure(nw * 4 + 4));
+  int rc;
+  if ((rc = copy_in(g.mask_bits.p, pass_bits, nw * 4, location, h->stream))) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  g.has_mask = true;
+  return 0;
+}
+
+int colate_stage1_flags(colate_handle* h, int target_slot, int reference_slot, int64_t* n_used_chr, int32_t* n_blocks_chr)
+{
+  if (!h || target_slot < 0 || target_slot >= COLATE_MAX_GENOMES || reference_slot < 0 || reference_slot >= COLATE_MAX_GENOMES)
+    return fail(COLATE_ERR_ARG, "colate_stage1_flags: bad arguments");
+  if (!h->sites_set || !h->genomes[target_slot].set || !h->genomes[reference_slot].set)
+    return fail(COLATE_ERR_STATE, "colate_stage1_flags: sites / genomes not set");
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_tables(h);
+  if (rc) return rc;
+  cudaStream_t s = h->stream;
+  CK(cudaEventRecord(h->ev[0], s));
+  if ((rc = run_join(h, reference_slot))) return rc;
+  if ((rc = run_join(h, target_slot))) return rc;
+  CK(cudaEventRecord(h->ev[1], s));
+  if ((rc = run_flags(h, target_slot, reference_slot))) return rc;
+  CK(cudaEventRecord(h->ev[2], s));
+  h->h_chr_used.resize(h->n_chr);
+  h->h_chr_blocks.resize(h->n_chr);
+  int64_t misc[8];
+  CK(cudaMemcpyAsync(h->h_chr_used.data(), h->chr_used.p, h->n_chr * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h->h_chr_blocks.data(), h->chr_blocks.p, h->n_chr * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(misc, h->misc.p, 64, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  h->n_used = misc[0];
+  h->n_blocks_local = (int)misc[1];
+  h->tgt_slot = target_slot;
+  h->ref_slot = reference_slot;
+  h->flags_done = true;
+  if (n_used_chr) memcpy(n_used_chr, h->h_chr_used.data(), h->n_chr * 8);
+  if (n_blocks_chr) memcpy(n_blocks_chr, h->h_chr_blocks.data(), h->n_chr * 4);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->timing.join_ms = ms;
+  cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->timing.flags_ms = ms;
+  h->timing.n_site = h->n_site;
+  h->timing.n_used = h->n_used;
+  return 0;
+}
+
+int colate_stage1_sample(colate_handle* h, const uint32_t* mt_state, int64_t used_rank_base, int block_base,
+                         double* block_stats, int64_t* block_tallies, uint32_t* mt_state_out)
+{
+  if (!h || !mt_state || used_rank_base < 0 || block_base < 0) return fail(COLATE_ERR_ARG, "colate_stage1_sample: bad arguments");
+  if (!h->flags_done) return fail(COLATE_ERR_STATE, "colate_stage1_sample: call colate_stage1_flags first");
+  if (block_base + h->n_blocks_local > MAX_BLOCKS) return fail(COLATE_ERR_BLOCKS, "more than 500 genomic blocks");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int64_t nu = h->n_used;
+  const int nb = h->n_blocks_local;
+  uint32_t* stream_local = nullptr;
+  uint32_t win_after[COLATE_MT_WORDS];
+  CK(cudaEventRecord(h->ev[6], s));
+  int rc = run_mt_stream(h, mt_state, 200 * used_rank_base, 200 * nu, pick_chunk_log2(nu), &stream_local, nullptr);
+  if (rc) return rc;
+  CK(cudaEventRecord(h->ev[7], s));
+  if ((rc = run_sample(h, stream_local, block_base))) return rc;
+  int64_t misc[8];
+  CK(cudaMemcpyAsync(misc, h->misc.p, 64, cudaMemcpyDeviceToHost, s));
+  if (block_stats && nb > 0) CK(cudaMemcpyAsync(block_stats, h->out_f.p, (size_t)nb * 4 * NBINS * 8, cudaMemcpyDeviceToHost, s));
+  if (block_tallies && nb > 0) CK(cudaMemcpyAsync(block_tallies, h->out_n.p, (size_t)nb * 3 * NBINS * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (misc[3]) return fail(COLATE_ERR_AGE_RANGE, "a used row has an age bin >= 185 (age_end beyond ~9.3e6 generations)");
+  if (mt_state_out) {
+    if ((rc = mt_window_after(h, win_after))) return rc;
+    memcpy(mt_state_out, win_after, sizeof win_after);
+  }
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]); h->timing.rng_ms = ms;
+  cudaEventElapsedTime(&ms, h->ev[7], h->ev[4]); h->timing.sample_ms = ms;   // compact + tiles + k_sample
+  cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->timing.reduce_ms = ms;
+  h->timing.rng_words = 200 * nu;
+  h->timing.total_ms = h->timing.join_ms + h->timing.flags_ms + h->timing.rng_ms + h->timing.sample_ms + h->timing.reduce_ms;
+  return 0;
+}
+
+
+int colate_stage1(colate_handle* h, int target_slot, int reference_slot, const uint32_t* mt_state, int* num_blocks,
+                  double* block_stats, int64_t* block_tallies, int64_t* n_used_total, uint32_t* mt_state_out)
+{
+  int rc = colate_stage1_flags(h, target_slot, reference_slot, nullptr, nullptr);
+  if (rc) return rc;
+  if (h->n_blocks_local > MAX_BLOCKS) return fail(COLATE_ERR_BLOCKS, "more than 500 genomic blocks");
+  rc = colate_stage1_sample(h, mt_state, 0, 0, block_stats, block_tallies, mt_state_out);
+  if (rc) return rc;
+  if (num_blocks) *num_blocks = h->n_blocks_local;
+  if (n_used_total) *n_used_total = h->n_used;
+  return 0;
+}
+
+int colate_last_stage1_timing(colate_handle* h, colate_stage1_timing* out)
+{
+  if (!h || !out) return fail(COLATE_ERR_ARG, "null");
+  *out = h->timing;
+  return 0;
+}
+
+int colate_stage2_bootstrap(colate_handle* h, int R, int num_blocks, const int32_t* block_weights,
+                            const double* block_stats, double age, double* counts)
+{
+  if (!h || R <= 0 || num_blocks <= 0 || num_blocks > MAX_BLOCKS || !block_weights || !block_stats)
+    return fail(COLATE_ERR_ARG, "colate_stage2_bootstrap: bad arguments");
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_tables(h);
+  if (rc) return rc;
+  double ab[NBINS];
+  colate_age_bins(ab);
+  if (!(age >= 0) || !(age < ab[NBINS - 1])) return fail(COLATE_ERR_ARG, "age outside the age grid");
+  cudaStream_t s = h->stream;
+  CK(h->d_weights.ensure((size_t)R * num_blocks * 4));
+  CK(h->d_blockstats.ensure((size_t)num_blocks * 4 * NBINS * 8));
+  CK(h->d_counts.ensure((size_t)R * 2 * NBINS * 8));
+  CK(cudaMemcpyAsync(h->d_weights.p, block_weights, (size_t)R * num_blocks * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->d_blockstats.p, block_stats, (size_t)num_blocks * 4 * NBINS * 8, cudaMemcpyHostToDevice, s));
+  if ((rc = run_bootstrap(h, R, num_blocks, age))) return rc;
+  if (counts) CK(cudaMemcpyAsync(counts, h->d_counts.p, (size_t)R * 2 * NBINS * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  h->counts_R = R;
+  return 0;
+}
+
+int colate_stage3_em(colate_handle* h, int R, int E, const double* epochs, const double* rates_init, const double* counts,
+                     int max_iter, double* rates, int32_t* iters, double* final_ll)
+{
+  if (!h || R <= 0 || E < 2 || E > 1024 || !epochs || !rates_init || max_iter < 0)
+    return fail(COLATE_ERR_ARG, "colate_stage3_em: bad arguments");
+  if (!counts && h->counts_R != R) return fail(COLATE_ERR_STATE, "colate_stage3_em: no device-resident counts for this R");
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_tables(h);
+  if (rc) return rc;
+  cudaStream_t s = h->stream;
+  CK(h->d_epochs.ensure((size_t)E * 8));
+  CK(h->d_rates.ensure((size_t)(R + 1) * E * 8));
+  CK(h->d_iters.ensure((size_t)R * 4));
+  CK(h->d_ll.ensure((size_t)R * 8));
+  CK(cudaMemcpyAsync(h->d_epochs.p, epochs, (size_t)E * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->d_rates.p, rates_init, (size_t)E * 8, cudaMemcpyHostToDevice, s));
+  if (counts) {
+    CK(h->d_counts.ensure((size_t)R * 2 * NBINS * 8));
+    CK(cudaMemcpyAsync(h->d_counts.p, counts, (size_t)R * 2 * NBINS * 8, cudaMemcpyHostToDevice, s));
+    h->counts_R = R;
+  }
+  if ((rc = run_em(h, R, E, max_iter))) return rc;
+  if (rates) CK(cudaMemcpyAsync(rates, h->d_rates.as<double>() + E, (size_t)R * E * 8, cudaMemcpyDeviceToHost, s));
+  if (iters) CK(cudaMemcpyAsync(iters, h->d_iters.p, (size_t)R * 4, cudaMemcpyDeviceToHost, s));
+  if (final_ll) CK(cudaMemcpyAsync(final_ll, h->d_ll.p, (size_t)R * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int colate_estep(colate_handle* h, int shared, int E, const double* epochs, const double* rates, int n_t, const double* t,
+                 double* num, double* denom, double* logl)
+{
+  if (!h || E < 2 || E > 1024 || n_t <= 0 || !epochs || !rates || !t) return fail(COLATE_ERR_ARG, "colate_estep: bad arguments");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  CK(h->d_epochs.ensure((size_t)E * 8));
+  CK(h->d_rates.ensure((size_t)E * 8));
+  const size_t tot = (size_t)n_t * (2 + 2 * (size_t)E);
+  CK(h->d_tmp.ensure(tot * 8));
+  CK(cudaMemcpyAsync(h->d_epochs.p, epochs, (size_t)E * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->d_rates.p, rates, (size_t)E * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->d_tmp.p, t, (size_t)n_t * 8, cudaMemcpyHostToDevice, s));
+  int rc = run_estep(h, shared, E, n_t);
+  if (rc) return rc;
+  double* base = h->d_tmp.as<double>();
+  if (num) CK(cudaMemcpyAsync(num, base + n_t, (size_t)n_t * E * 8, cudaMemcpyDeviceToHost, s));
+  if (denom) CK(cudaMemcpyAsync(denom, base + n_t + (size_t)n_t * E, (size_t)n_t * E * 8, cudaMemcpyDeviceToHost, s));
+  if (logl) CK(cudaMemcpyAsync(logl, base + n_t + 2 * (size_t)n_t * E, (size_t)n_t * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// test hook: raw engine words [word0, word0+n) of the stream behind `mt_state`, via the device path
+int colate_test_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int64_t n_words, int log2_chunk_sites,
+                          uint32_t* out)
+{
+  if (!h || !mt_state || word0 < 0 || n_words < 0) return fail(COLATE_ERR_ARG, "colate_test_mt_stream: bad arguments");
+  CK(cudaSetDevice(h->device));
+  uint32_t* p = nullptr;
+  int rc = run_mt_stream(h, mt_state, word0, n_words, log2_chunk_sites, &p, out ? out + n_words : nullptr);
+  if (rc) return rc;
+  if (n_words > 0) CK(cudaMemcpyAsync(out, p, (size_t)n_words * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+}  // extern "C"

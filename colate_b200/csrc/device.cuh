@@ -1,0 +1,101 @@
+// Device-side shared declarations: handle layout, buffers, launch helpers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+
+namespace colate {
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(COLATE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));      \
+  } while (0)
+
+// growable device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes)
+  {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return (T*)p; }
+};
+
+// one .colate.in file on the device, plus its join onto the site axis
+struct GenomeDev {
+  bool set = false, joined = false, has_mask = false;
+  int64_t n_rec = 0;
+  DevBuf bp, aaf, daf, alleles, chr_first, chr_end, mask_bits;
+  // join (site-aligned): counts of the record at the row's position, position of the record
+  // before it (-1: that record is the first one the reader holds on this chromosome),
+  // flag bit0 = a record sits at the row's position, bit1 = its alleles equal the row's
+  DevBuf j_aaf, j_daf, j_prevbp, j_flag;
+};
+
+struct Stage1Dims {
+  int64_t n_used = 0;
+  int n_blocks = 0;
+};
+
+}  // namespace colate
+
+struct colate_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  // sites
+  bool sites_set = false;
+  int n_chr = 0;
+  int64_t n_site = 0;
+  std::vector<int64_t> h_site_off;
+  colate::DevBuf site_off, pos, ab, ae, meta;
+  colate::GenomeDev genomes[COLATE_MAX_GENOMES];
+  // stage-1 scratch
+  bool flags_done = false;
+  int tgt_slot = -1, ref_slot = -1;
+  colate::DevBuf candR, candT, use, word_rank, scan_tmp;
+  colate::DevBuf chr_used, chr_blocks, chr_block_base, misc;  // misc: small device scalars
+  colate::DevBuf u_ab, u_ae, u_fd, u_fa, u_dafr, u_nr, u_blk; // compacted used rows
+  colate::DevBuf blk_rank_start, tile_start, partial_f, partial_n, out_f, out_n;
+  colate::DevBuf windows, rng_stream, poly, thr10;
+  std::vector<int64_t> h_chr_used;
+  std::vector<int32_t> h_chr_blocks;
+  int64_t n_used = 0;
+  int n_blocks_local = 0;
+  int64_t mt_total_local = 0;
+  bool thr_ready = false;
+  colate_stage1_timing timing = {};
+  // stage 2/3
+  colate::DevBuf d_counts, d_blockstats, d_weights, d_epochs, d_rates, d_iters, d_ll, d_agebin, d_tmp;
+  int counts_R = 0;
+};
+
+namespace colate {
+// kernels_sites.cu
+int run_join(colate_handle* h, int slot);
+int run_flags(colate_handle* h, int tslot, int rslot);
+int run_sample(colate_handle* h, const uint32_t* stream_local, int block_base_unused);
+// kernels_mt.cu
+int run_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int64_t n_words, int log2_chunk_sites,
+                  uint32_t** stream_at_word0, uint32_t* window_after /* host, may be null */);
+int mt_window_after(colate_handle* h, uint32_t* window_after);
+// kernels_em.cu
+int run_bootstrap(colate_handle* h, int R, int num_blocks, double age);
+int run_em(colate_handle* h, int R, int E, int max_iter);
+int run_estep(colate_handle* h, int shared, int E, int n_t);
+}  // namespace colate

@@ -1,0 +1,413 @@
+// Host-side pieces of the path that are not kernels: error plumbing, the age grid and the
+// exact bin thresholds, the per-row filter, the chromosome seek emulation, ages / epoch
+// grid, and the readers / writers of the reference's file formats.
+#include "internal.h"
+
+#include <zlib.h>
+
+#include <cmath>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace colate {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+// max(0,(int)round(log(x10)*C)+1), coal.cpp:2253/2265/2284; (int) as cvttsd2si
+int bin_of_x10_host(double x10)
+{
+  double r = std::round(std::log(x10) * 10.0);
+  int v = (r > -2147483649.0 && r < 2147483648.0) ? (int)r : INT_MIN;
+  v = (int)((unsigned)v + 1u);
+  return v > 0 ? v : 0;
+}
+
+static inline double from_bits(uint64_t b) { double d; memcpy(&d, &b, 8); return d; }
+static inline uint64_t to_bits(double d) { uint64_t b; memcpy(&b, &d, 8); return b; }
+
+bool bin_thresholds(double* thr10)
+{
+  bool monotone = true;
+  thr10[0] = 0.0;
+  for (int k = 1; k <= NBINS; k++) {
+    // positive doubles order like their bit patterns
+    uint64_t lo = to_bits(1e-3), hi = to_bits(1e12);   // f(lo) < k <= f(hi)
+    while (hi - lo > 1) {
+      uint64_t mid = lo + (hi - lo) / 2;
+      if (bin_of_x10_host(from_bits(mid)) >= k) hi = mid; else lo = mid;
+    }
+    thr10[k] = from_bits(hi);
+    for (int d = 1; d <= 16; d++) {
+      if (bin_of_x10_host(from_bits(hi - d)) >= k) monotone = false;
+      if (bin_of_x10_host(from_bits(hi + d)) < k) monotone = false;
+    }
+  }
+  return monotone;
+}
+
+// ---- gz/plain file slurp (igzstream semantics: gzopen reads plain files transparently) ----
+static bool slurp(const std::string& path, std::vector<char>& buf)
+{
+  gzFile f = gzopen(path.c_str(), "rb");
+  if (!f) return false;
+  gzbuffer(f, 1 << 20);
+  buf.clear();
+  size_t cap = 1 << 22;
+  buf.resize(cap);
+  size_t n = 0;
+  for (;;) {
+    if (n == cap) { cap *= 2; buf.resize(cap); }
+    int got = gzread(f, buf.data() + n, (unsigned)std::min<size_t>(cap - n, 1u << 30));
+    if (got < 0) { gzclose(f); return false; }
+    if (got == 0) break;
+    n += (size_t)got;
+  }
+  gzclose(f);
+  buf.resize(n);
+  return true;
+}
+
+static bool slurp_or_gz(const std::string& path, std::vector<char>& buf)
+{
+  // Mutations::Read(filename) / fasta::Read: try <path>, then <path>.gz
+  FILE* probe = fopen(path.c_str(), "rb");
+  if (probe) { fclose(probe); return slurp(path, buf); }
+  return slurp(path + ".gz", buf);
+}
+
+}  // namespace colate
+
+using namespace colate;
+
+extern "C" {
+
+const char* colate_last_error(void) { return g_err.c_str(); }
+const char* colate_version(void) { return "colate_b200 0.1 (sm_100a)"; }
+
+void colate_age_bins(double* age_bin)
+{
+  double C = 10;
+  age_bin[0] = 0.0;
+  for (int bin = 0; bin < NBINS - 1; bin++) age_bin[bin + 1] = std::exp(bin / C) / 10.0;
+}
+
+int colate_test_bin_thresholds(double* thr10) { return bin_thresholds(thr10) ? 0 : 1; }
+
+uint32_t colate_site_meta(int flipped, int n_branch, float age_begin, float age_end, const char* mutation_type)
+{
+  if (!(flipped == 0 && n_branch == 1 && age_begin < age_end && age_end >= 0)) return 0;
+  const char* slash = strchr(mutation_type, '/');
+  size_t n = strlen(mutation_type);
+  size_t la = slash ? (size_t)(slash - mutation_type) : n;
+  size_t ld = slash ? n - la - 1 : 0;
+  if (la != 1 || ld != 1) return 0;  // empty, or not one of the single-letter codes
+  char a = mutation_type[0], d = mutation_type[2];
+  if (!(a == 'A' || a == 'C' || a == 'G' || a == 'T' || a == '0')) return 0;
+  if (!(d == 'A' || d == 'C' || d == 'G' || d == 'T' || d == '1')) return 0;
+  return 1u | ((uint32_t)(unsigned char)a << 8) | ((uint32_t)(unsigned char)d << 16);
+}
+
+int colate_chr_ranges(int n_chr, int64_t n_rec, const int32_t* rec_chrom, int64_t* chr_first, int64_t* chr_end)
+{
+  int64_t cur = -1, next = 0;  // cur: record currently held by the reader (-1: none yet)
+  for (int c = 0; c < n_chr; c++) {
+    while (!(cur >= 0 && rec_chrom[cur] == c)) {
+      if (next >= n_rec) break;          // fread fails: the reader keeps its last record
+      cur = next++;
+    }
+    if (cur >= 0 && rec_chrom[cur] == c) {
+      int64_t e = cur + 1;
+      while (e < n_rec && rec_chrom[e] == c) e++;
+      chr_first[c] = cur;
+      chr_end[c] = e;
+      // whatever part of the run the row loop leaves unread is skipped by the next seek
+      cur = e - 1;
+      next = e;
+    } else {
+      chr_first[c] = -1;
+      chr_end[c] = -1;
+    }
+  }
+  return 0;
+}
+
+double colate_age_generations(const char* target_age, const char* reference_age, int has_years_per_gen,
+                              float years_per_gen, double* years_per_gen_out)
+{
+  // coal.cpp:3105-3118: std::stof of the two strings, float flag for years_per_gen
+  double ta = 0, ra = 0;
+  if (target_age) ta = strtof(target_age, nullptr);
+  if (reference_age) ra = strtof(reference_age, nullptr);
+  double ypg = 28.0;
+  if (has_years_per_gen) ypg = years_per_gen;
+  if (years_per_gen_out) *years_per_gen_out = ypg;
+  return std::max(ta, ra) / ypg;
+}
+
+int colate_epochs_from_bins(const char* bins, double age, double years_per_gen, double* epochs, int cap, int* ep_null)
+{
+  // coal.cpp:3553-3630
+  const double log_10 = std::log(10);
+  double log_age = std::log(age * years_per_gen) / log_10;
+  std::string s(bins);
+  double v[3];
+  size_t i = 0;
+  for (int t = 0; t < 3; t++) {
+    if (t > 0 && i >= s.size()) return fail(COLATE_ERR_ARG, "Error: epochs format is wrong. Specify x,y,stepsize.");
+    std::string tok;
+    while (i < s.size() && s[i] != ',') tok += s[i++];
+    i++;
+    char* end = nullptr;
+    v[t] = strtof(tok.c_str(), &end);
+    if (end == tok.c_str()) return fail(COLATE_ERR_ARG, "--bins: not a number: '" + tok + "'");
+  }
+  const double lower = v[0], upper = v[1], step = v[2];
+  if (!(step > 0)) return fail(COLATE_ERR_ARG, "--bins: stepsize must be positive");
+  int ne = 0;
+  *ep_null = 0;
+  epochs[ne++] = 0.0;
+  if (log_age < lower && age != 0.0) { epochs[ne++] = age; log_age = -1; }
+  double boundary = lower;
+  while (boundary < upper) {
+    if (ne + 3 > cap) return fail(COLATE_ERR_ARG, "--bins: too many epochs");
+    if (boundary > log_age && log_age != -1) {
+      epochs[ne++] = age;
+      if (boundary - log_age < 0.25 * step) boundary += step;
+      log_age = -1;
+    } else {
+      if (log_age != -1) (*ep_null)++;
+      epochs[ne++] = std::exp(log_10 * boundary) / years_per_gen;
+    }
+    boundary += step;
+  }
+  epochs[ne++] = std::exp(log_10 * upper) / years_per_gen;
+  epochs[ne] = std::max(1e8, 10 * epochs[ne - 1]) / years_per_gen;
+  ne++;
+  return ne;
+}
+
+int colate_epochs_from_coal_file(const char* path, double age, double* epochs, double* rates_init, int cap)
+{
+  // coal.cpp:3508-3549 (epoch line) and 3638-3646 (initial rates)
+  std::vector<char> buf;
+  if (!slurp(path, buf)) return fail(COLATE_ERR_IO, std::string("cannot read ") + path);
+  std::string all(buf.begin(), buf.end());
+  size_t l1 = all.find('\n');
+  if (l1 == std::string::npos) return fail(COLATE_ERR_IO, "--coal: missing epoch line");
+  size_t l2 = all.find('\n', l1 + 1);
+  std::string line = all.substr(l1 + 1, (l2 == std::string::npos ? all.size() : l2) - l1 - 1);
+  int ne = 0, ep = 0;
+  std::string tmp;
+  auto push = [&](const std::string& tok) -> bool {
+    char* end = nullptr;
+    float f = strtof(tok.c_str(), &end);
+    if (end == tok.c_str()) return false;
+    if (ne + 2 > cap) return false;
+    if (ep == 1 && age < f && age != 0.0) { epochs[ne++] = age; ep++; }
+    if (ep != 1 || age == 0.0) { epochs[ne++] = f; ep++; }
+    return true;
+  };
+  for (size_t i = 0; i < line.size(); i++) {
+    if (line[i] == ' ' || line[i] == '\t') {
+      if (!push(tmp)) return fail(COLATE_ERR_IO, "--coal: malformed epoch line");
+      tmp.clear();
+    } else tmp += line[i];
+  }
+  if (!tmp.empty() && !push(tmp)) return fail(COLATE_ERR_IO, "--coal: malformed epoch line");
+  if (ne < 2 || epochs[0] != 0) return fail(COLATE_ERR_IO, "--coal: first epoch must be 0");
+  for (int e = 1; e < ne; e++)
+    if (!(epochs[e] > epochs[e - 1])) return fail(COLATE_ERR_IO, "--coal: epochs must increase");
+  // `is >> dummy >> dummy` then one rate per epoch
+  const char* p = (l2 == std::string::npos) ? "" : all.c_str() + l2 + 1;
+  char* end = nullptr;
+  for (int k = 0; k < 2; k++) { strtod(p, &end); if (end == p) return fail(COLATE_ERR_IO, "--coal: missing rates"); p = end; }
+  for (int e = 0; e < ne; e++) {
+    double r = strtod(p, &end);
+    if (end == p) return fail(COLATE_ERR_IO, "--coal: missing rates");
+    rates_init[e] = r;
+    p = end;
+  }
+  return ne;
+}
+
+// ---- readers ------------------------------------------------------------------------------
+int64_t colate_read_mut(const char* path, int64_t cap, int32_t* pos, float* age_begin, float* age_end, uint32_t* meta)
+{
+  std::vector<char> buf;
+  if (!slurp_or_gz(path, buf)) return fail(COLATE_ERR_IO, std::string("Error while reading ") + path + "(.gz).");
+  buf.push_back('\n');
+  buf.push_back('\0');
+  const char* p = buf.data();
+  const char* endp = buf.data() + buf.size() - 1;
+  // header line
+  const char* nl = (const char*)memchr(p, '\n', endp - p);
+  if (!nl) return 0;
+  p = nl + 1;
+  int64_t n = 0;
+  while (p < endp) {
+    nl = (const char*)memchr(p, '\n', endp - p);
+    if (!nl) break;
+    if (nl == p) {  // std::getline returns an empty line; the reference would fault on it
+      if (nl + 1 >= endp) break;
+      return fail(COLATE_ERR_IO, std::string("empty line in ") + path);
+    }
+    if (pos) {
+      if (n >= cap) return fail(COLATE_ERR_ARG, "colate_read_mut: capacity too small");
+      // snp;pos;dist;rs-id;tree;branches;is_not_mapping;is_flipped;age_begin;age_end;type;...
+      const char* f[11];
+      const char* q = p;
+      int nf = 0;
+      f[nf++] = q;
+      while (q < nl && nf < 11) { if (*q == ';') f[nf++] = q + 1; q++; }
+      if (nf < 10) return fail(COLATE_ERR_IO, std::string("Error reading following line in mut file: ") + std::string(p, nl));
+      pos[n] = (int32_t)strtol(f[1], nullptr, 10);
+      int nb = 0;
+      for (const char* b = f[5]; b < f[6] - 1;) {
+        while (b < f[6] - 1 && *b == ' ') b++;
+        if (b < f[6] - 1) { nb++; while (b < f[6] - 1 && *b != ' ') b++; }
+      }
+      int flipped = strtol(f[7], nullptr, 10) != 0;
+      float ab = strtof(f[8], nullptr), ae = strtof(f[9], nullptr);
+      age_begin[n] = ab;
+      age_end[n] = ae;
+      char mt[16] = "NA";
+      if (nf >= 11) {
+        // mutation type runs to the next ';' or the end of the line (mutations.cpp:216-223)
+        const char* e = f[10];
+        size_t k = 0;
+        while (e < nl && *e != ';' && k + 1 < sizeof mt) mt[k++] = *e++;
+        mt[k] = 0;
+        if (e < nl && *e != ';') { mt[0] = 'N'; mt[1] = 'N'; mt[2] = 0; }  // longer than any valid code
+      }
+      meta[n] = colate_site_meta(flipped, nb, ab, ae, mt);
+    }
+    n++;
+    p = nl + 1;
+  }
+  return n;
+}
+
+int64_t colate_read_colate_in(const char* path, int n_chr, const char* const* chr_names, int64_t cap,
+                              int32_t* rec_chrom, int32_t* bp, int32_t* aaf, int32_t* daf, uint16_t* alleles)
+{
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(COLATE_ERR_IO, std::string("Failed to open ") + path);
+  fseek(f, 0, SEEK_END);
+  long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::vector<char> buf((size_t)sz);
+  if (sz > 0 && fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); return fail(COLATE_ERR_IO, "short read"); }
+  fclose(f);
+  std::vector<std::string> names(chr_names, chr_names + n_chr);
+  int64_t n = 0;
+  size_t o = 0;
+  int last_id = -1;
+  std::string last_name;
+  while (o + 4 <= (size_t)sz) {
+    int32_t l;
+    memcpy(&l, buf.data() + o, 4);
+    if (l < 0 || l >= 1024 || o + 4 + (size_t)l + 14 > (size_t)sz) break;  // truncated tail
+    if (bp) {
+      if (n >= cap) return fail(COLATE_ERR_ARG, "colate_read_colate_in: capacity too small");
+      const char* nm = buf.data() + o + 4;
+      int id;
+      if (last_id >= 0 && last_name.size() == (size_t)l && memcmp(last_name.data(), nm, l) == 0) id = last_id;
+      else {
+        id = n_chr;
+        for (int c = 0; c < n_chr; c++)
+          if (names[c].size() == (size_t)l && memcmp(names[c].data(), nm, l) == 0) { id = c; break; }
+        last_id = id;
+        last_name.assign(nm, l);
+      }
+      const char* r = nm + l;
+      rec_chrom[n] = id;
+      memcpy(&bp[n], r, 4);
+      alleles[n] = (uint16_t)((unsigned char)r[4] | ((unsigned char)r[5] << 8));
+      memcpy(&aaf[n], r + 6, 4);
+      memcpy(&daf[n], r + 10, 4);
+    }
+    n++;
+    o += 4 + (size_t)l + 14;
+  }
+  return n;
+}
+
+int colate_mask_bits_from_fasta(const char* path, int64_t n, const int32_t* pos, int64_t row0, uint32_t* pass_bits)
+{
+  std::vector<char> buf;
+  if (!slurp_or_gz(path, buf)) return fail(COLATE_ERR_IO, std::string("Error while opening file ") + path + ".");
+  // data.cpp:213-237: drop the first line, concatenate the rest upper-cased
+  size_t i = 0;
+  while (i < buf.size() && buf[i] != '\n') i++;
+  i++;
+  size_t len = 0;
+  for (; i < buf.size(); i++) {
+    char c = buf[i];
+    if (c == '\n') continue;
+    if (c >= 'a' && c <= 'z') c -= 32;
+    buf[len++] = c;
+  }
+  for (int64_t k = 0; k < n; k++) {
+    int32_t b = pos[k];
+    bool pass = true;
+    if ((uint64_t)(int64_t)b < (uint64_t)len) {       // int vs size_t compare, coal.cpp:2169
+      if (b >= 1 && buf[b - 1] != 'P') pass = false;
+    }
+    int64_t m = row0 + k;
+    if (pass) pass_bits[m >> 5] |= (1u << (m & 31));
+    else pass_bits[m >> 5] &= ~(1u << (m & 31));
+  }
+  return 0;
+}
+
+// ---- writers ------------------------------------------------------------------------------
+int colate_write_coal(const char* path, int R, int E, const double* epochs, double* rates, int is_ancient, int ep_null)
+{
+  // coal.cpp:3660-3672, 3830-3844; operator<<(double) with default flags == "%g"
+  FILE* f = fopen(path, "w");
+  if (!f) return fail(COLATE_ERR_IO, std::string("cannot write ") + path);
+  fprintf(f, "0\n");
+  if (is_ancient) {
+    fprintf(f, "0 ");
+    for (int e = ep_null + 1; e < E; e++) fprintf(f, "%g ", epochs[e]);
+  } else {
+    for (int e = 0; e < E; e++) fprintf(f, "%g ", epochs[e]);
+  }
+  fprintf(f, "\n");
+  for (int i = 0; i < R; i++) {
+    double* r = rates + (size_t)i * E;
+    fprintf(f, "0 %d ", i);
+    if (is_ancient) {
+      for (int j = 0; j <= ep_null && j < E; j++) r[j] = 0;
+      for (int e = ep_null; e < E; e++) fprintf(f, "%g ", r[e]);
+    } else {
+      for (int e = 0; e < E; e++) fprintf(f, "%g ", r[e]);
+    }
+    fprintf(f, "\n");
+  }
+  fclose(f);
+  return 0;
+}
+
+int colate_write_bin(const char* path, int R, int E, const double* epochs, const double* rates, const int32_t* iters)
+{
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(COLATE_ERR_IO, std::string("cannot write ") + path);
+  const char magic[8] = {'C', 'O', 'L', 'A', 'T', 'E', 'B', '1'};
+  int32_t hdr[2] = {R, E};
+  fwrite(magic, 1, 8, f);
+  fwrite(hdr, 4, 2, f);
+  fwrite(epochs, 8, (size_t)E, f);
+  fwrite(rates, 8, (size_t)R * E, f);
+  fwrite(iters, 4, (size_t)R, f);
+  fclose(f);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,44 @@
+// Internal declarations shared by the host translation units and the CUDA ones.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <string>
+
+#include "../../include/colate_b200.h"
+
+namespace colate {
+
+constexpr int NBINS = COLATE_NUM_AGE_BINS;
+constexpr int MAX_BLOCKS = COLATE_MAX_BLOCKS;
+constexpr int NTHR = NBINS + 1;  // thr10[1..185]; index 0 unused
+
+// error plumbing (thread-local message behind colate_last_error())
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+// host_mt.cpp
+uint32_t mt_temper(uint32_t z);
+uint32_t mt_untemper(uint32_t y);
+void mt_seed_window(uint32_t seed, uint32_t* w);
+void mt_generate_window(uint32_t* w, int64_t n, uint32_t* out);
+void draw_block_weights(uint32_t* w, int R, int num_blocks, int32_t* weights);
+const uint32_t* jump_poly(int q);  // t^(200*2^q) mod p(t), 624 x u32
+void jump_window_host(const uint32_t* w, int q, uint32_t* out);
+
+// host_misc.cpp
+// thr10[k], k = 1..185: smallest double x with max(0,(int)round(log(x)*10)+1) >= k
+// (coal.cpp:2253, 2265, 2284), found by bisection against this host's libm.
+// Returns false if log() is not monotone in a +-16 ulp neighbourhood of a threshold.
+bool bin_thresholds(double* thr10 /*[NTHR]*/);
+int bin_of_x10_host(double x10);
+
+}  // namespace colate
+
+extern "C" {
+// test hooks, not part of the public ABI
+int colate_test_charpoly_terms(int* out, int cap);
+int colate_test_jump_window_host(const uint32_t* w, int q, uint32_t* out);
+int colate_test_bin_thresholds(double* thr10);
+int colate_test_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int64_t n_words,
+                          int log2_chunk_sites, uint32_t* out);
+}

@@ -1,0 +1,226 @@
+// The reference's std::mt19937 stream (coal.cpp:3157-3162, consumed at coal.cpp:2262, 2282)
+// generated on the device, bit for bit, in parallel.
+//
+// The stream is cut into chunks of S = 200 * 2^k words (2^k used rows).  The 624-word state
+// window in front of every chunk is reached by jump-ahead: x[J+j] = XOR_{i: g_i=1} x[i+j] with
+// g = t^J mod p(t), p the characteristic polynomial of MT19937 (host_mt.cpp).  Chunk windows
+// are filled by a binary tree of jumps (chunk d from chunk d - lowbit(d)), so only the
+// polynomials t^(S*2^l) are needed; each chunk is then generated sequentially by one CTA
+// (the recurrence exposes 227-wide parallelism per step) and written tempered to HBM.
+#include "device.cuh"
+
+#include <map>
+#include <mutex>
+
+namespace colate {
+
+constexpr int MT_N = 624;
+constexpr int XLEN = 19937 + MT_N;       // base sequence needed by one jump
+constexpr int JUMP_THREADS = 640;
+constexpr int MAX_TAPS = 19968;
+
+__device__ __forceinline__ uint32_t mt_mix_dev(uint32_t a, uint32_t b, uint32_t c)
+{
+  uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+  return c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+__device__ __forceinline__ uint32_t mt_temper_dev(uint32_t z)
+{
+  z ^= (z >> 11);
+  z ^= (z << 7) & 0x9d2c5680u;
+  z ^= (z << 15) & 0xefc60000u;
+  z ^= (z >> 18);
+  return z;
+}
+
+// windows[d] <- jump(windows[src]) for d = (2*blockIdx+1) << level, src = d - (1<<level);
+// level < 0: in-place jump of windows[0].
+__global__ void __launch_bounds__(JUMP_THREADS)
+k_jump(uint32_t* __restrict__ windows, const uint16_t* __restrict__ taps, int n_taps, int level, int n_chunks)
+{
+  extern __shared__ __align__(16) uint32_t sm[];
+  uint32_t* X = sm;                                   // XLEN words (+ pad)
+  uint16_t* T = (uint16_t*)(sm + ((XLEN + 3) & ~3));  // tap offsets
+  const int tid = threadIdx.x;
+  int d, src;
+  if (level < 0) { d = 0; src = 0; }
+  else {
+    d = (2 * blockIdx.x + 1) << level;
+    if (d >= n_chunks) return;
+    src = d - (1 << level);
+  }
+  for (int i = tid; i < MT_N; i += blockDim.x) X[i] = windows[(size_t)src * MT_N + i];
+  for (int i = tid; i < n_taps; i += blockDim.x) T[i] = taps[i];
+  __syncthreads();
+  for (int base = MT_N; base < XLEN; base += 227) {
+    int n = base + tid;
+    if (tid < 227 && n < XLEN) X[n] = mt_mix_dev(X[n - 624], X[n - 623], X[n - 227]);
+    __syncthreads();
+  }
+  if (tid < MT_N) {
+    uint32_t acc = 0;
+    const uint32_t* Xt = X + tid;
+    int i = 0;
+    for (; i + 8 <= n_taps; i += 8) {
+      uint4 t4 = *(const uint4*)(T + i);  // 8 taps, same address for the whole CTA
+      acc ^= Xt[t4.x & 0xffff] ^ Xt[t4.x >> 16] ^ Xt[t4.y & 0xffff] ^ Xt[t4.y >> 16] ^
+             Xt[t4.z & 0xffff] ^ Xt[t4.z >> 16] ^ Xt[t4.w & 0xffff] ^ Xt[t4.w >> 16];
+    }
+    for (; i < n_taps; i++) acc ^= Xt[T[i]];
+    windows[(size_t)d * MT_N + tid] = acc;
+  }
+}
+
+// chunk c: sequential generation from its window, tempered words to stream[c*chunk_words ...)
+__global__ void __launch_bounds__(256)
+k_gen(const uint32_t* __restrict__ windows, int64_t chunk_words, int64_t total_words, uint32_t* __restrict__ stream)
+{
+  __shared__ uint32_t bufA[MT_N + 1], bufB[MT_N + 1];
+  const int tid = threadIdx.x;
+  const int64_t start = (int64_t)blockIdx.x * chunk_words;
+  if (start >= total_words) return;
+  const int64_t end = min(start + chunk_words, total_words);
+  for (int i = tid; i < MT_N; i += blockDim.x) bufA[i] = windows[(size_t)blockIdx.x * MT_N + i];
+  __syncthreads();
+  uint32_t* cur = bufA;
+  uint32_t* nxt = bufB;
+  for (int64_t o = start; o < end; o += MT_N) {
+    const int64_t rem = end - o;
+    uint32_t* out = stream + o;
+    if (tid < 227) {
+      uint32_t v = mt_mix_dev(cur[tid], cur[tid + 1], cur[tid + 397]);
+      nxt[tid] = v;
+      if (tid < rem) out[tid] = mt_temper_dev(v);
+    }
+    __syncthreads();
+    if (tid < 227) {
+      int k = tid + 227;
+      uint32_t v = mt_mix_dev(cur[k], cur[k + 1], nxt[tid]);
+      nxt[k] = v;
+      if (k < rem) out[k] = mt_temper_dev(v);
+    }
+    __syncthreads();
+    if (tid < 170) {
+      int k = tid + 454;
+      uint32_t b = (k == 623) ? nxt[0] : cur[k + 1];
+      uint32_t v = mt_mix_dev(cur[k], b, nxt[k - 227]);
+      nxt[k] = v;
+      if (k < rem) out[k] = mt_temper_dev(v);
+    }
+    __syncthreads();
+    uint32_t* t = cur; cur = nxt; nxt = t;
+  }
+}
+
+// ---- tap lists per polynomial, cached per device -------------------------------------------
+struct TapList { uint16_t* d = nullptr; int n = 0; };
+static std::mutex g_mu;
+static std::map<std::pair<int, int>, TapList> g_taps;  // (device, q) -> taps
+
+static int get_taps(int device, int q, cudaStream_t s, TapList* out)
+{
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_taps.find({device, q});
+  if (it != g_taps.end()) { *out = it->second; return 0; }
+  const uint32_t* g = jump_poly(q);
+  if (!g) return fail(COLATE_ERR_ARG, "jump polynomial unavailable");
+  std::vector<uint16_t> taps;
+  taps.reserve(10500);
+  for (int i = 0; i < 19937; i++) if ((g[i >> 5] >> (i & 31)) & 1u) taps.push_back((uint16_t)i);
+  TapList tl;
+  tl.n = (int)taps.size();
+  size_t bytes = ((taps.size() + 15) & ~(size_t)15) * 2 + 32;
+  CK(cudaMalloc(&tl.d, bytes));
+  CK(cudaMemsetAsync(tl.d, 0, bytes, s));
+  CK(cudaMemcpyAsync(tl.d, taps.data(), taps.size() * 2, cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));  // taps is a local
+  g_taps[{device, q}] = tl;
+  *out = tl;
+  return 0;
+}
+
+static int launch_jump(colate_handle* h, int q, int level, int n_chunks, int grid)
+{
+  TapList tl;
+  int rc = get_taps(h->device, q, h->stream, &tl);
+  if (rc) return rc;
+  const size_t smem = (size_t)((XLEN + 3) & ~3) * 4 + (size_t)((tl.n + 15) & ~15) * 2 + 32;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(k_jump, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * ((XLEN + 3) & ~3) + 2 * MAX_TAPS + 64));
+    attr_set = true;
+  }
+  k_jump<<<grid, JUMP_THREADS, smem, h->stream>>>(h->windows.as<uint32_t>(), tl.d, tl.n, level, n_chunks);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// Generates engine words [word0, word0+n_words) of the stream that starts at state window
+// `mt_state`.  *stream_at_word0 points at word0 inside the handle's stream buffer (16-byte
+// aligned when word0 is a multiple of 4).  window_after (host, optional) = state window after
+// word0+n_words outputs.
+int run_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int64_t n_words, int k,
+                  uint32_t** stream_at_word0, uint32_t* window_after)
+{
+  if (k < 0 || k > 40) return fail(COLATE_ERR_ARG, "bad chunk size");
+  const int64_t S = (int64_t)200 << k;
+  const int64_t c0 = word0 / S;
+  const int64_t last = n_words > 0 ? word0 + n_words - 1 : word0;
+  const int64_t M64 = last / S - c0 + 1;
+  if (M64 > (1 << 24)) return fail(COLATE_ERR_ARG, "too many generator chunks");
+  const int M = (int)M64;
+  const int64_t total_local = word0 + n_words - c0 * S;  // words from the start of chunk c0
+  cudaStream_t s = h->stream;
+  CK(h->windows.ensure((size_t)M * MT_N * 4));
+  CK(h->rng_stream.ensure((size_t)std::max<int64_t>(total_local, 4) * 4 + 64));
+  CK(cudaMemcpyAsync(h->windows.p, mt_state, MT_N * 4, cudaMemcpyHostToDevice, s));
+  // reach chunk c0: one in-place jump per set bit of c0
+  for (int b = 62; b >= 0; b--) {
+    if (!((c0 >> b) & 1)) continue;
+    if (k + b > 48) return fail(COLATE_ERR_ARG, "generator offset too large");
+    int rc = launch_jump(h, k + b, -1, 1, 1);
+    if (rc) return rc;
+  }
+  // tree over the chunks of this call
+  int K = 0;
+  while ((1 << K) < M) K++;
+  for (int l = K - 1; l >= 0; l--) {
+    if (M <= (1 << l)) continue;
+    int grid = (M - (1 << l) + (2 << l) - 1) / (2 << l);
+    int rc = launch_jump(h, k + l, l, M, grid);
+    if (rc) return rc;
+  }
+  if (total_local > 0) {
+    k_gen<<<M, 256, 0, s>>>(h->windows.as<uint32_t>(), S, total_local, h->rng_stream.as<uint32_t>());
+    CK(cudaGetLastError());
+  }
+  *stream_at_word0 = h->rng_stream.as<uint32_t>() + (word0 - c0 * S);
+  h->mt_total_local = total_local;
+  if (window_after) return mt_window_after(h, window_after);
+  return 0;
+}
+
+// State window after the last word produced by the latest run_mt_stream() call, composed on
+// the host from the chunk-0 window and the tail of the stream (tempering is invertible):
+// y[i] = window(c0)[i] for i < 624, y[624+n] = untemper(stream[n]); answer = y[T .. T+624).
+int mt_window_after(colate_handle* h, uint32_t* window_after)
+{
+  cudaStream_t s = h->stream;
+  const int64_t T = h->mt_total_local;
+  uint32_t w0[MT_N];
+  std::vector<uint32_t> tail((size_t)std::min<int64_t>(T, MT_N));
+  CK(cudaMemcpyAsync(w0, h->windows.p, MT_N * 4, cudaMemcpyDeviceToHost, s));
+  if (!tail.empty())
+    CK(cudaMemcpyAsync(tail.data(), h->rng_stream.as<uint32_t>() + (T - (int64_t)tail.size()), tail.size() * 4,
+                       cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  for (int j = 0; j < MT_N; j++) {
+    int64_t i = T + j;  // index into y
+    if (i < MT_N) window_after[j] = w0[i];
+    else window_after[j] = mt_untemper(tail[(size_t)(i - MT_N - (T - (int64_t)tail.size()))]);
+  }
+  return 0;
+}
+
+}  // namespace colate

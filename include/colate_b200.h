@@ -1,0 +1,177 @@
+/* colate_b200.h -- C ABI of the B200-native `Colate --mode mut` (tmp/tmp) hot path.
+ *
+ * The reference (leospeidel/Colate) has no FFI: mut() calls plain C++ functions of the
+ * same translation unit.  This header defines the seam between them; every entry point
+ * cites the reference interface it replaces (paths relative to /root/reference/).
+ * INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions: extern "C", plain pointers and sizes.  All functions return 0 on success
+ * and a negative colate_status on error (message: colate_last_error()).  Host buffers are
+ * caller-owned; device buffers are owned by the handle.  Calls are synchronous from the
+ * caller's view and not re-entrant on one handle.  One handle = one GPU (one process per
+ * GPU under torch.distributed / NCCL, or one host thread per handle).
+ * There is no CPU fallback: every compute entry point fails with COLATE_ERR_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef COLATE_B200_H
+#define COLATE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COLATE_NUM_AGE_BINS 185      /* (int)(log(1e8)*10)+1, coal.cpp:3126-3127 */
+#define COLATE_MAX_BLOCKS 500        /* coal.cpp:3140 */
+#define COLATE_BLOCK_BASES 30000000  /* coal.cpp:3139 */
+#define COLATE_NUM_SAMPLES 100       /* coal.cpp:2085 */
+#define COLATE_MT_WORDS 624
+
+typedef enum {
+  COLATE_OK = 0,
+  COLATE_ERR_ARG = -1,        /* bad argument / inconsistent sizes                        */
+  COLATE_ERR_AGE_RANGE = -2,  /* a used row has age bin >= 185: the reference writes out of */
+                              /* bounds there (coal.cpp:2269) / rejection-samples (2289)   */
+  COLATE_ERR_BLOCKS = -3,     /* more than 500 genomic blocks (reference overruns, 3140)   */
+  COLATE_ERR_CUDA = -4,       /* CUDA runtime error or no usable device                    */
+  COLATE_ERR_IO = -5,         /* unreadable / malformed input file                         */
+  COLATE_ERR_ORDER = -6,      /* positions not ascending / duplicate chromosome names      */
+  COLATE_ERR_STATE = -7       /* call sequence violated (e.g. stage1 before set_sites)     */
+} colate_status;
+
+typedef struct colate_handle colate_handle;
+
+const char* colate_last_error(void);
+const char* colate_version(void);
+
+/* ---- handle -------------------------------------------------------------------------- */
+int colate_create(int device, colate_handle** out);
+void colate_destroy(colate_handle* h);
+/* cudaStream_t the handle launches on (as void*), for event timing by the caller. */
+void* colate_stream(colate_handle* h);
+
+/* ---- inputs: what parse_tmptmp (coal.cpp:2072) obtains from its readers -------------- */
+
+/* Rows of the per-chromosome .mut files in --chr order (Mutations::Read,
+ * include/src/mutations.cpp:56-283; consumed at coal.cpp:2148-2176).
+ *   site_off[n_chr+1]  row range of each chromosome
+ *   pos, age_begin, age_end   SNPInfo::pos / age_begin / age_end (float32 as in mutations.hpp:21)
+ *   meta  bit0 = row passes coal.cpp:2150 + 2166 + 2175-2176 (everything that depends on the
+ *         row alone), byte1 = ancestral char, byte2 = derived char  (colate_site_meta())
+ * location: 0 = host pointers (copied host->device), 1 = device pointers (copied d2d). */
+int colate_set_sites(colate_handle* h, int n_chr, const int64_t* site_off, const int32_t* pos,
+                     const float* age_begin, const float* age_end, const uint32_t* meta, int location);
+
+/* Records of one .colate.in file in file order (record layout coal.cpp:2505-2514; read at
+ * coal.cpp:2126-2133, 2185-2192, 2205-2212) into genome slot `slot` (0..COLATE_MAX_GENOMES-1).
+ *   chr_first[c], chr_end[c]  record range the reference's sequential reader can reach while
+ *       it is on chromosome c (chr_first = the record pre-loaded by the chromosome seek,
+ *       coal.cpp:2125-2145; -1/-1 if the chromosome is never reached): colate_chr_ranges()
+ *   alleles = ancestral | derived << 8 */
+#define COLATE_MAX_GENOMES 64
+int colate_set_genome(colate_handle* h, int slot, int64_t n_rec, const int64_t* chr_first,
+                      const int64_t* chr_end, const int32_t* bp, const int32_t* aaf, const int32_t* daf,
+                      const uint16_t* alleles, int location);
+
+/* P/N mask of genome `slot` evaluated at the site positions (fasta::Read,
+ * include/src/data.cpp:213-237; test at coal.cpp:2169-2174): bit m of pass_bits = row m is
+ * NOT rejected by the mask (positions at or beyond the mask end pass).  NULL clears it. */
+int colate_set_mask(colate_handle* h, int slot, const uint32_t* pass_bits, int location);
+
+/* ---- stage i: parse_tmptmp, coal.cpp:2071-2321 (called at coal.cpp:3317) ------------- */
+
+/* Stage i, part A: per-row use flags (A.2 filter, both stream lookups with the sequential
+ * reader's look-ahead rule, coal.cpp:2181-2219).  Outputs (host):
+ *   n_used_chr[n_chr]    rows reaching coal.cpp:2222 per chromosome
+ *   n_blocks_chr[n_chr]  genomic blocks the chromosome occupies (coal.cpp:2227-2234, 2306-2310) */
+int colate_stage1_flags(colate_handle* h, int target_slot, int reference_slot,
+                        int64_t* n_used_chr, int32_t* n_blocks_chr);
+
+/* Stage i, part B: Monte-Carlo age binning (coal.cpp:2236-2297) of the rows flagged by part A.
+ *   mt_state[624]   std::mt19937 state window: the 624 untempered words preceding the next
+ *                   output (for a freshly seeded engine: its seed array; colate_mt_seed()).
+ *   used_rank_base  used rows that precede this handle's first row in the global row order
+ *                   (0 on one GPU; multi-GPU: exclusive sum of the other ranks' n_used) --
+ *                   row r of this handle consumes generator words [200*(base+r), +200)
+ *   block_base      global index of this handle's first genomic block
+ * Outputs (host, caller-allocated):
+ *   block_stats[n_blocks][4][185] fp64: age_shared_count, age_notshared_count, and row 0 of
+ *       age_shared_emp / age_notshared_emp, for blocks block_base .. block_base+n_blocks-1
+ *   block_tallies[n_blocks][3][185] int64: samples added to shared / notshared, rows added to emp
+ *   mt_state_out[624]  state window after 200*(used_rank_base+n_used) words (may alias mt_state)
+ * Returns COLATE_ERR_AGE_RANGE if a used row's age bin reaches 185. */
+int colate_stage1_sample(colate_handle* h, const uint32_t* mt_state, int64_t used_rank_base,
+                         int block_base, double* block_stats, int64_t* block_tallies,
+                         uint32_t* mt_state_out);
+
+/* Convenience: parts A+B on one GPU.  *num_blocks = return value of parse_tmptmp. */
+int colate_stage1(colate_handle* h, int target_slot, int reference_slot, const uint32_t* mt_state,
+                  int* num_blocks, double* block_stats, int64_t* block_tallies,
+                  int64_t* n_used_total, uint32_t* mt_state_out);
+
+/* ---- stage ii: block bootstrap + F redistribution, coal.cpp:3344-3451 ---------------- */
+/* block_weights[R][num_blocks]: multiplicity of each block per replicate, drawn by the host
+ * with the reference's generator (colate_draw_block_weights(), coal.cpp:3350-3357).
+ * counts[R][2][185]: age_shared_count / age_notshared_count per replicate (host). The
+ * counts also stay resident on the device for colate_stage3_em(). */
+int colate_stage2_bootstrap(colate_handle* h, int R, int num_blocks, const int32_t* block_weights,
+                            const double* block_stats, double age, double* counts);
+
+/* ---- stage iii: EM, coal.cpp:3675-3827 + coal_EM (coal_EM.hpp:38-58, coal_EM.cpp:5-468) - */
+/* counts: [R][2][185] host pointer, or NULL to use the device-resident result of the last
+ * colate_stage2_bootstrap().  rates[R][E], iters[R] (the `iter` printed at coal.cpp:3823),
+ * final_ll[R]. */
+int colate_stage3_em(colate_handle* h, int R, int E, const double* epochs, const double* rates_init,
+                     const double* counts, int max_iter, double* rates, int32_t* iters, double* final_ll);
+
+/* One E-step call: coal_EM(epochs, rates).EM_shared / EM_notshared(t, t, num, denom)
+ * (coal_EM.cpp:153, 297) evaluated on the device for n_t ages.  num/denom: [n_t][E]. */
+int colate_estep(colate_handle* h, int shared, int E, const double* epochs, const double* rates,
+                 int n_t, const double* t, double* num, double* denom, double* logl);
+
+/* ---- timing of the last stage-1 call (CUDA events on the handle's stream), ms -------- */
+typedef struct {
+  float join_ms, flags_ms, rng_ms, sample_ms, reduce_ms, total_ms;
+  int64_t n_site, n_used, rng_words;
+} colate_stage1_timing;
+int colate_last_stage1_timing(colate_handle* h, colate_stage1_timing* out);
+
+/* ---- host-side pieces of the path (no GPU needed) ------------------------------------ */
+/* std::mt19937::seed(seed) -> state window (coal.cpp:3157-3162). */
+void colate_mt_seed(uint32_t seed, uint32_t* mt_state);
+/* Next n raw engine outputs from a state window; advances the window. */
+void colate_mt_generate(uint32_t* mt_state, int64_t n, uint32_t* out);
+/* Block multiplicities for R replicates (coal.cpp:3350-3357; std::uniform_int_distribution
+ * <int>(0,num_blocks-1) of libstdc++); advances the state window. */
+void colate_draw_block_weights(uint32_t* mt_state, int R, int num_blocks, int32_t* block_weights);
+/* age grid, coal.cpp:3129-3137 */
+void colate_age_bins(double* age_bin);
+/* packed site word from a parsed .mut row (coal.cpp:2150-2176 minus the masks). */
+uint32_t colate_site_meta(int flipped, int n_branch, float age_begin, float age_end, const char* mutation_type);
+/* record ranges per --chr entry, emulating the chromosome seek of coal.cpp:2125-2145.
+ * rec_chrom[k] = index of record k's chromosome name in the --chr list (or >= n_chr). */
+int colate_chr_ranges(int n_chr, int64_t n_rec, const int32_t* rec_chrom, int64_t* chr_first, int64_t* chr_end);
+/* ages and epoch grid, coal.cpp:3105-3120, 3503-3632.  Returns num_epochs or <0. */
+double colate_age_generations(const char* target_age, const char* reference_age, int has_years_per_gen,
+                              float years_per_gen, double* years_per_gen_out);
+int colate_epochs_from_bins(const char* bins, double age, double years_per_gen, double* epochs, int cap, int* ep_null);
+int colate_epochs_from_coal_file(const char* path, double age, double* epochs, double* rates_init, int cap);
+
+/* ---- readers / writers (host) --------------------------------------------------------- */
+/* Relate .mut[.gz] (mutations.cpp:56-283).  Two-call pattern: n = colate_read_mut(path, 0, ...NULL)
+ * returns the row count; then call again with arrays of that capacity. */
+int64_t colate_read_mut(const char* path, int64_t cap, int32_t* pos, float* age_begin, float* age_end, uint32_t* meta);
+/* .colate.in (coal.cpp:2505-2514).  rec_chrom[k] = index of the record's name in chr_names. */
+int64_t colate_read_colate_in(const char* path, int n_chr, const char* const* chr_names, int64_t cap,
+                              int32_t* rec_chrom, int32_t* bp, int32_t* aaf, int32_t* daf, uint16_t* alleles);
+/* fasta mask (data.cpp:213-237) evaluated at positions -> pass bits for rows [row0, row0+n). */
+int colate_mask_bits_from_fasta(const char* path, int64_t n, const int32_t* pos, int64_t row0, uint32_t* pass_bits);
+/* <out>.coal (coal.cpp:3660-3672, 3830-3844) and the raw fp64 side output <out>.bin. */
+int colate_write_coal(const char* path, int R, int E, const double* epochs, double* rates, int is_ancient, int ep_null);
+int colate_write_bin(const char* path, int R, int E, const double* epochs, const double* rates, const int32_t* iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COLATE_B200_H */

@@ -1,0 +1,99 @@
+"""GPU parity: stage i (parse_tmptmp, coal.cpp:2071-2321) through the C-ABI vs the oracle."""
+import numpy as np
+import pytest
+
+from colate_b200 import api, synth
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare_stage1(o, s1, rel=1e-12):
+    assert s1.num_blocks == o["num_blocks"]
+    assert s1.n_used == o["n_used_total"]
+    # integer tallies: bit-exact
+    assert np.array_equal(s1.block_tallies[:, 0], o["n_shared"])
+    assert np.array_equal(s1.block_tallies[:, 1], o["n_notshared"])
+    assert np.array_equal(s1.block_tallies[:, 2], o["n_emp"])
+    # fp64 sums: same addends, different (fixed) association -> <= 1e-12 relative to the block mass
+    for v, k in enumerate(("shared", "notshared", "shared_emp", "notshared_emp")):
+        ref = o[k]
+        got = s1.block_stats[:, v]
+        scale = np.maximum(np.abs(ref).sum(axis=1, keepdims=True), 1e-300)
+        assert np.max(np.abs(got - ref) / scale) <= rel, k
+        assert np.array_equal(got == 0, ref == 0), k
+    # generator state after the stage: identical subsequent stream
+    a = np.zeros(64, np.uint32); b = np.array([po.lib().oracle_mt_next(o["rng"]) for _ in range(64)], np.uint32)
+    st = s1.mt_state.copy()
+    api.lib().colate_mt_generate(st, 64, a)
+    assert np.array_equal(a, b)
+
+
+def test_mt_stream_matches_std_mt19937(handle):
+    st = api.mt_seed(1)
+    for word0, n, k in ((0, 5000, 3), (1600, 40000, 3), (200 * 12345, 30000, 4), (0, 700000, 7), (200 * 1000003, 4000, 5), (400, 0, 3)):
+        got, after = handle.mt_stream(st, word0, n, k)
+        want = np.zeros(n + 50, np.uint32)
+        po.lib().oracle_mt_words(1, word0, n + 50, want)
+        assert np.array_equal(got, want[:n]), (word0, n, k)
+        nxt = np.zeros(50, np.uint32)
+        api.lib().colate_mt_generate(after, 50, nxt)
+        assert np.array_equal(nxt, want[n:]), (word0, n, k)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("masks", [False, True])
+def test_stage1_small_weird(handle, seed, masks):
+    sites = synth.make_sites(seed, [4000, 3000, 5000], [2.5e8, 1.2e8, 0.9e8], weird=0.1)
+    gt = synth.make_genome(seed + 100, sites, 0.7, weird=0.1)
+    gr = synth.make_genome(seed + 200, sites, 0.6, weird=0.1)
+    tm = rm = None
+    if masks:
+        tm = [synth.make_mask(seed * 10 + c, int(L) if c != 1 else int(L) // 2, 0.3) for c, L in enumerate(sites.chrom_len)]
+        rm = [synth.make_mask(seed * 20 + c, int(L), 0.2) for c, L in enumerate(sites.chrom_len)]
+    o = po.stage1(sites, gt, gr, seed=seed, tmask=tm, rmask=rm)
+    handle.load(sites, gt, gr, tm, rm)
+    s1 = handle.stage1(api.mt_seed(seed))
+    _compare_stage1(o, s1)
+
+
+def test_stage1_config1_shape(handle):
+    """chr1-shaped input at 1/5 scale (200 k rows; the oracle finishes in a second)."""
+    sites = synth.make_sites(1, [200000], [2.49e8])
+    gt = synth.make_genome(101, sites, 0.7)
+    gr = synth.make_genome(201, sites, 0.7)
+    o = po.stage1(sites, gt, gr, seed=1)
+    handle.load(sites, gt, gr)
+    s1 = handle.stage1(api.mt_seed(1))
+    _compare_stage1(o, s1)
+    assert s1.n_used > 50000
+
+
+def test_stage1_edge_cases(handle):
+    # empty chromosome in the middle, chromosome without records, genome with a single record
+    sites = synth.make_sites(5, [300, 0, 200, 100], [1e8, 1e8, 4e7, 9e7])
+    gt = synth.make_genome(6, sites, 0.9)
+    gr = synth.make_genome(7, sites, 0.9)
+    keep = gr.chrom != 2
+    gr = synth.Genome(gr.chrom[keep], gr.bp[keep], gr.anc[keep], gr.der[keep], gr.aaf[keep], gr.daf[keep])
+    o = po.stage1(sites, gt, gr, seed=9)
+    handle.load(sites, gt, gr)
+    _compare_stage1(o, handle.stage1(api.mt_seed(9)))
+    one = synth.Genome(gt.chrom[:1], gt.bp[:1], gt.anc[:1], gt.der[:1], gt.aaf[:1], gt.daf[:1])
+    o = po.stage1(sites, one, gr, seed=9)
+    handle.load(sites, one, gr)
+    s1 = handle.stage1(api.mt_seed(9))
+    assert s1.n_used == 0 == o["n_used_total"]
+    _compare_stage1(o, s1)
+
+
+def test_stage1_age_range_error(handle):
+    sites = synth.make_sites(1, [500], [1e8])
+    sites.age_end[:] = 2e7  # bin >= 185: the reference writes out of bounds here
+    gt = synth.make_genome(2, sites, 1.0)
+    gr = synth.make_genome(3, sites, 1.0)
+    assert po.stage1(sites, gt, gr, seed=1)["num_blocks"] == -2
+    handle.load(sites, gt, gr)
+    with pytest.raises(api._lib.ColateError) as e:
+        handle.stage1(api.mt_seed(1))
+    assert e.value.code == -2
