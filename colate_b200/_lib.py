@@ -30,9 +30,9 @@ VP = C.c_void_p
 
 
 class Stage1Timing(C.Structure):
-    _fields_ = [("join_ms", C.c_float), ("flags_ms", C.c_float), ("rng_ms", C.c_float), ("sample_ms", C.c_float),
-                ("reduce_ms", C.c_float), ("total_ms", C.c_float), ("n_site", C.c_int64), ("n_used", C.c_int64),
-                ("rng_words", C.c_int64)]
+    _fields_ = [("join_ms", C.c_float), ("flags_ms", C.c_float), ("rng_ms", C.c_float), ("compact_ms", C.c_float),
+                ("sample_ms", C.c_float), ("reduce_ms", C.c_float), ("total_ms", C.c_float), ("n_site", C.c_int64),
+                ("n_used", C.c_int64), ("rng_words", C.c_int64)]
 
 
 class ColateError(RuntimeError):
@@ -58,6 +58,8 @@ SIGNATURES = {
     "colate_stage3_em": (C.c_int, [VP, C.c_int, C.c_int, VP, VP, VP, C.c_int, VP, VP, VP]),
     "colate_estep": (C.c_int, [VP, C.c_int, C.c_int, VP, VP, C.c_int, VP, VP, VP, VP]),
     "colate_last_stage1_timing": (C.c_int, [VP, C.POINTER(Stage1Timing)]),
+    "colate_set_option": (C.c_int, [VP, C.c_char_p, C.c_int64]),
+    "colate_launch_count": (C.c_int64, [VP]),
     "colate_mt_seed": (None, [C.c_uint32, u32]),
     "colate_mt_generate": (None, [u32, C.c_int64, u32]),
     "colate_draw_block_weights": (None, [u32, C.c_int, C.c_int, i32]),

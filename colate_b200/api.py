@@ -205,6 +205,12 @@ class Handle:
                                   C.byref(nu), ptr(out_state)))
         return Stage1Result(nb.value, stats[:nb.value].copy(), tallies[:nb.value].copy(), nu.value, out_state)
 
+    def set_option(self, key: str, value: int):
+        check(lib().colate_set_option(self._h, key.encode(), value))
+
+    def launch_count(self) -> int:
+        return lib().colate_launch_count(self._h)
+
     def stage1_timing(self) -> dict:
         t = _lib.Stage1Timing()
         check(lib().colate_last_stage1_timing(self._h, C.byref(t)))

@@ -169,12 +169,13 @@ int colate_stage1_flags(colate_handle* h, int target_slot, int reference_slot, i
   int rc = ensure_tables(h);
   if (rc) return rc;
   cudaStream_t s = h->stream;
+  if (h->opt_rejoin) for (auto& g : h->genomes) g.joined = false;
   CK(cudaEventRecord(h->ev[0], s));
   if ((rc = run_join(h, reference_slot))) return rc;
   if ((rc = run_join(h, target_slot))) return rc;
   CK(cudaEventRecord(h->ev[1], s));
   if ((rc = run_flags(h, target_slot, reference_slot))) return rc;
-  CK(cudaEventRecord(h->ev[2], s));
+  CK(cudaEventRecord(h->ev[3], s));
   h->h_chr_used.resize(h->n_chr);
   h->h_chr_blocks.resize(h->n_chr);
   int64_t misc[8];
@@ -191,7 +192,7 @@ int colate_stage1_flags(colate_handle* h, int target_slot, int reference_slot, i
   if (n_blocks_chr) memcpy(n_blocks_chr, h->h_chr_blocks.data(), h->n_chr * 4);
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->timing.join_ms = ms;
-  cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->timing.flags_ms = ms;
+  cudaEventElapsedTime(&ms, h->ev[1], h->ev[3]); h->timing.flags_ms = ms;
   h->timing.n_site = h->n_site;
   h->timing.n_used = h->n_used;
   return 0;
@@ -226,10 +227,12 @@ int colate_stage1_sample(colate_handle* h, const uint32_t* mt_state, int64_t use
   }
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]); h->timing.rng_ms = ms;
-  cudaEventElapsedTime(&ms, h->ev[7], h->ev[4]); h->timing.sample_ms = ms;   // compact + tiles + k_sample
+  cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->timing.compact_ms = ms;
+  cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); h->timing.sample_ms = ms;   // k_sample alone
   cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->timing.reduce_ms = ms;
   h->timing.rng_words = 200 * nu;
-  h->timing.total_ms = h->timing.join_ms + h->timing.flags_ms + h->timing.rng_ms + h->timing.sample_ms + h->timing.reduce_ms;
+  h->timing.total_ms = h->timing.join_ms + h->timing.flags_ms + h->timing.rng_ms + h->timing.compact_ms + h->timing.sample_ms +
+                       h->timing.reduce_ms;
   return 0;
 }
 
@@ -246,6 +249,15 @@ int colate_stage1(colate_handle* h, int target_slot, int reference_slot, const u
   if (n_used_total) *n_used_total = h->n_used;
   return 0;
 }
+
+int colate_set_option(colate_handle* h, const char* key, int64_t value)
+{
+  if (!h || !key) return fail(COLATE_ERR_ARG, "null");
+  if (!strcmp(key, "rejoin")) { h->opt_rejoin = value != 0; return 0; }
+  return fail(COLATE_ERR_ARG, std::string("unknown option ") + key);
+}
+
+int64_t colate_launch_count(colate_handle* h) { return h ? h->launches : 0; }
 
 int colate_last_stage1_timing(colate_handle* h, colate_stage1_timing* out)
 {

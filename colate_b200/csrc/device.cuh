@@ -83,6 +83,8 @@ struct colate_handle {
   // stage 2/3
   colate::DevBuf d_counts, d_blockstats, d_weights, d_epochs, d_rates, d_iters, d_ll, d_agebin, d_tmp;
   int counts_R = 0;
+  int64_t launches = 0;
+  bool opt_rejoin = false;
 };
 
 namespace colate {

@@ -328,6 +328,7 @@ int run_bootstrap(colate_handle* h, int R, int num_blocks, double age)
 {
   k_bootstrap<<<R, 256, 0, h->stream>>>(num_blocks, h->d_weights.as<int32_t>(), h->d_blockstats.as<double>(), age,
                                         h->d_agebin.as<double>(), h->d_counts.as<double>());
+  h->launches += 1;
   CK(cudaGetLastError());
   return 0;
 }
@@ -339,6 +340,7 @@ int run_em(colate_handle* h, int R, int E, int max_iter)
   k_em<<<R, EM_THREADS, smem, h->stream>>>(E, h->d_epochs.as<double>(), h->d_rates.as<double>() /*init*/,
                                            h->d_agebin.as<double>(), h->d_counts.as<double>(), max_iter,
                                            h->d_rates.as<double>() + E, h->d_iters.as<int32_t>(), h->d_ll.as<double>());
+  h->launches += 1;
   CK(cudaGetLastError());
   return 0;
 }

@@ -152,6 +152,7 @@ static int launch_jump(colate_handle* h, int q, int level, int n_chunks, int gri
     attr_set = true;
   }
   k_jump<<<grid, JUMP_THREADS, smem, h->stream>>>(h->windows.as<uint32_t>(), tl.d, tl.n, level, n_chunks);
+  h->launches += 1;
   CK(cudaGetLastError());
   return 0;
 }
@@ -193,6 +194,7 @@ int run_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int
   }
   if (total_local > 0) {
     k_gen<<<M, 256, 0, s>>>(h->windows.as<uint32_t>(), S, total_local, h->rng_stream.as<uint32_t>());
+    h->launches += 1;
     CK(cudaGetLastError());
   }
   *stream_at_word0 = h->rng_stream.as<uint32_t>() + (word0 - c0 * S);

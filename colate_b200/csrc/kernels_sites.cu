@@ -429,6 +429,7 @@ int run_join(colate_handle* h, int slot)
                                         g.aaf.as<int32_t>(), g.daf.as<int32_t>(), g.alleles.as<uint16_t>(),
                                         g.j_aaf.as<int32_t>(), g.j_daf.as<int32_t>(), g.j_prevbp.as<int32_t>(), g.j_flag.as<uint8_t>());
     CK(cudaGetLastError());
+    h->launches += 1;
   }
   g.joined = true;
   return 0;
@@ -462,11 +463,13 @@ int run_flags(colate_handle* h, int tslot, int rslot)
     k_popc_blocksum<<<nsb, SCAN_THREADS, 0, s>>>(h->use.as<uint32_t>(), nw, h->scan_tmp.as<uint32_t>());
     k_scan_sums<<<1, 32, 0, s>>>(h->scan_tmp.as<uint32_t>(), nsb, total);
     k_word_rank<<<nsb, SCAN_THREADS, 0, s>>>(h->use.as<uint32_t>(), nw, h->scan_tmp.as<uint32_t>(), total, h->word_rank.as<uint32_t>());
+    h->launches += 6;
   } else {
     CK(cudaMemsetAsync(h->word_rank.p, 0, 8, s));
   }
   k_chr<<<1, 32, 0, s>>>(h->n_chr, h->site_off.as<int64_t>(), h->pos.as<int32_t>(), h->use.as<uint32_t>(), h->word_rank.as<uint32_t>(),
                          h->chr_used.as<int64_t>(), h->chr_blocks.as<int32_t>(), h->chr_block_base.as<int32_t>(), h->misc.as<int64_t>());
+  h->launches += 1;
   CK(cudaGetLastError());
   return 0;
 }
@@ -486,6 +489,8 @@ int run_sample(colate_handle* h, const uint32_t* stream_local, int)
   const int max_tiles = (int)(nu / TILE_SITES) + nb + 1;
   CK(h->partial_f.ensure((size_t)max_tiles * 4 * NBINS * 8)); CK(h->partial_n.ensure((size_t)max_tiles * 3 * NBINS * 4));
   CK(h->out_f.ensure((size_t)MAX_BLOCKS * 4 * NBINS * 8)); CK(h->out_n.ensure((size_t)MAX_BLOCKS * 3 * NBINS * 8));
+  CK(cudaEventRecord(h->ev[2], s));
+  h->launches += (n > 0 ? 1 : 0) + 2 + (nb > 0 ? 1 : 0);
   if (n > 0)
     k_compact<<<grid_for(n, 256), 256, 0, s>>>(n, h->n_chr, h->site_off.as<int64_t>(), h->pos.as<int32_t>(), h->ab.as<float>(),
                                                h->ae.as<float>(), h->use.as<uint32_t>(), h->word_rank.as<uint32_t>(),

@@ -132,10 +132,22 @@ int colate_estep(colate_handle* h, int shared, int E, const double* epochs, cons
 
 /* ---- timing of the last stage-1 call (CUDA events on the handle's stream), ms -------- */
 typedef struct {
-  float join_ms, flags_ms, rng_ms, sample_ms, reduce_ms, total_ms;
+  float join_ms;     /* k_join x2 (skipped when the join of a genome is still cached)            */
+  float flags_ms;    /* row filter, both stream lookups, used-row ranks                        */
+  float rng_ms;      /* MT19937 jump-ahead tree + stream generation                            */
+  float compact_ms;  /* used rows -> dense records, tile table                                 */
+  float sample_ms;   /* k_sample alone: the per-mutation Monte-Carlo binning kernel            */
+  float reduce_ms;   /* per-block fixed-order reduction                                        */
+  float total_ms;
   int64_t n_site, n_used, rng_words;
 } colate_stage1_timing;
 int colate_last_stage1_timing(colate_handle* h, colate_stage1_timing* out);
+
+/* Options: "rejoin" = 1 drops the cached record->row join of every genome before each
+ * colate_stage1_flags() (benchmarks time the join as part of the pass). */
+int colate_set_option(colate_handle* h, const char* key, int64_t value);
+/* Kernels launched on this handle since creation (for launch accounting). */
+int64_t colate_launch_count(colate_handle* h);
 
 /* ---- host-side pieces of the path (no GPU needed) ------------------------------------ */
 /* std::mt19937::seed(seed) -> state window (coal.cpp:3157-3162). */
