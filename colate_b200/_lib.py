@@ -57,6 +57,7 @@ SIGNATURES = {
     "colate_stage2_bootstrap": (C.c_int, [VP, C.c_int, C.c_int, VP, VP, C.c_double, VP]),
     "colate_stage3_em": (C.c_int, [VP, C.c_int, C.c_int, VP, VP, VP, C.c_int, VP, VP, VP]),
     "colate_estep": (C.c_int, [VP, C.c_int, C.c_int, VP, VP, C.c_int, VP, VP, VP, VP]),
+    "colate_libm_exact": (C.c_int, []),
     "colate_last_stage1_timing": (C.c_int, [VP, C.POINTER(Stage1Timing)]),
     "colate_set_option": (C.c_int, [VP, C.c_char_p, C.c_int64]),
     "colate_launch_count": (C.c_int64, [VP]),
@@ -80,6 +81,7 @@ TEST_HOOKS = {
     "colate_test_charpoly_terms": (C.c_int, [i32, C.c_int]),
     "colate_test_jump_window_host": (C.c_int, [u32, C.c_int, u32]),
     "colate_test_bin_thresholds": (C.c_int, [f64]),
+    "colate_test_libm": (C.c_int, [VP, C.c_int, C.c_int, f64, f64]),
     "colate_test_mt_stream": (C.c_int, [VP, u32, C.c_int64, C.c_int64, C.c_int, u32]),
 }
 

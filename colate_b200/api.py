@@ -16,6 +16,11 @@ from . import _lib
 from ._lib import MAX_BLOCKS, MT_WORDS, NBINS, check, lib, ptr
 
 
+def libm_exact() -> bool:
+    """True if the host libm matches the device exp/log/log1p bit for bit (glibc 2.39, FMA variants)."""
+    return bool(lib().colate_libm_exact())
+
+
 def age_bins() -> np.ndarray:
     """age_bin[], coal.cpp:3129-3137."""
     out = np.zeros(NBINS)
@@ -243,6 +248,13 @@ class Handle:
         num, den, ll = np.zeros((n, E)), np.zeros((n, E)), np.zeros(n)
         check(lib().colate_estep(self._h, 1 if shared else 0, E, ptr(ep), ptr(r), n, ptr(t), ptr(num), ptr(den), ptr(ll)))
         return ll, num, den
+
+    def libm(self, which: str, x):
+        """Test hook: the device's glibc-exact exp / log / log1p on an array."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros_like(x)
+        check(lib().colate_test_libm(self._h, {"exp": 0, "log": 1, "log1p": 2}[which], x.shape[0], x, y))
+        return y
 
     def mt_stream(self, mt_state, word0, n_words, log2_chunk_sites=3):
         """Test hook: engine words [word0, word0+n) generated by the device path (+ window after)."""

@@ -1,7 +1,9 @@
 // C-ABI glue (include/colate_b200.h): handle management, uploads, stage drivers.
 #include "device.cuh"
+#include "glibc_math.cuh"
 
 #include <algorithm>
+#include <random>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -30,6 +32,28 @@ int ensure_tables(colate_handle* h)
   CK(cudaStreamSynchronize(h->stream));
   h->thr_ready = true;
   return 0;
+}
+
+// Does this host's libm compute exp/log/log1p exactly like the glibc_math.cuh port (i.e. is it
+// glibc 2.39 with the FMA variants selected)?  If so the device EM is bit-identical to the
+// reference run on this host; if not it is bit-identical to the reference on a glibc-2.39/FMA host.
+int libm_self_check()
+{
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  glm::Tables T{glm::hEXP_TAB, glm::hLOG_TAB};
+  std::mt19937_64 g(12345);
+  std::uniform_real_distribution<double> U(0, 1);
+  auto same = [](double a, double b) { return (std::isnan(a) && std::isnan(b)) || !memcmp(&a, &b, 8); };
+  int ok = 1;
+  for (int i = 0; i < 200000 && ok; i++) {
+    double x = (i & 1) ? -U(g) * 760 : (U(g) - 0.5) * 40;
+    double y = std::exp((U(g) - 0.5) * ((i & 2) ? 1400 : 1));
+    double z = (i & 1) ? -std::exp(-U(g) * 700) : std::exp(-U(g) * 700);
+    if (!same(std::exp(x), glm::exp(x, T)) || !same(std::log(y), glm::log(y, T)) || !same(std::log1p(z), glm::log1p(z))) ok = 0;
+  }
+  cached = ok;
+  return ok;
 }
 
 int pick_chunk_log2(int64_t n_used)
@@ -340,6 +364,15 @@ int colate_estep(colate_handle* h, int shared, int E, const double* epochs, cons
   if (logl) CK(cudaMemcpyAsync(logl, base + n_t + 2 * (size_t)n_t * E, (size_t)n_t * 8, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   return 0;
+}
+
+int colate_libm_exact(void) { return libm_self_check(); }
+
+int colate_test_libm(colate_handle* h, int which, int n, const double* x, double* y)
+{
+  if (!h || n <= 0 || !x || !y) return fail(COLATE_ERR_ARG, "colate_test_libm: bad arguments");
+  CK(cudaSetDevice(h->device));
+  return run_libm(h, which, n, x, y);
 }
 
 // test hook: raw engine words [word0, word0+n) of the stream behind `mt_state`, via the device path

@@ -81,7 +81,8 @@ struct colate_handle {
   bool thr_ready = false;
   colate_stage1_timing timing = {};
   // stage 2/3
-  colate::DevBuf d_counts, d_blockstats, d_weights, d_epochs, d_rates, d_iters, d_ll, d_agebin, d_tmp;
+  colate::DevBuf d_counts, d_blockstats, d_weights, d_epochs, d_rates, d_iters, d_ll, d_agebin, d_tmp, d_scratch, d_prof, libm_tab;
+  int libm_exact = -1;  // host libm == glibc_math.cuh port on the self-check sample (1/0), -1 unknown
   int counts_R = 0;
   int64_t launches = 0;
   bool opt_rejoin = false;
@@ -100,4 +101,5 @@ int mt_window_after(colate_handle* h, uint32_t* window_after);
 int run_bootstrap(colate_handle* h, int R, int num_blocks, double age);
 int run_em(colate_handle* h, int R, int E, int max_iter);
 int run_estep(colate_handle* h, int shared, int E, int n_t);
+int run_libm(colate_handle* h, int which, int n, const double* x_host, double* y_host);
 }  // namespace colate

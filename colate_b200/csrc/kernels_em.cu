@@ -2,16 +2,20 @@
 // 185-bin age histograms: coal.cpp:3675-3827 driving coal_EM, coal_EM.cpp:5-468) kernels.
 //
 // Everything here is IEEE fp64 in the reference's operation order (the file is compiled with
-// --fmad=false; products and sums are never contracted).  exp/log/log1p are CUDA's, which
-// differ from glibc's in the last ulp: stage ii is bit-exact with the reference, stage iii
-// agrees to ~1e-13 relative per iteration (north-star tolerance 1e-9 on the rates).
+// --fmad=false; products and sums are never contracted), exp/log/log1p are glibc's algorithms
+// (glibc_math.cuh) and every sum over age bins runs in the reference's order, so both stages
+// reproduce the reference bit for bit on a host whose libm selects the FMA variants.
+#include <cooperative_groups.h>
+
 #include "device.cuh"
+#include "glibc_math.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace colate {
 
-constexpr int EM_THREADS = 384;          // warps 0-5: shared tasks, warps 6-11: not-shared tasks
-constexpr int EM_WARPS = EM_THREADS / 32;
-constexpr int EM_HALF = EM_THREADS / 2;  // 192 >= NBINS
+constexpr int EM_THREADS = 512;
+constexpr int EM_TASKS = 384;  // 2 x 185 (bin, shared / not shared) padded; task = 2*bin + type
 
 // ---- stage ii ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -67,25 +71,26 @@ __device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0
 __device__ __forceinline__ bool bad(double x) { return !(fabs(x) < __longlong_as_double(0x7ff0000000000000ull)); }
 
 // coal_EM::logsumexp, coal_EM.cpp:5-31
-__device__ __forceinline__ double lse(double a, double b)
+__device__ __forceinline__ double lse(double a, double b, const glm::Tables& T)
 {
   if (bad(a)) return bad(b) ? neg_inf() : b;
   if (bad(b)) return a;
-  if (a > b) return a + log1p(exp(b - a));
-  return b + log1p(exp(a - b));
+  if (a > b) return a + glm::log1p(glm::exp(b - a, T));
+  return b + glm::log1p(glm::exp(a - b, T));
 }
 // coal_EM::logminusexp, coal_EM.cpp:33-58
-__device__ __forceinline__ double lme(double a, double b)
+__device__ __forceinline__ double lme(double a, double b, const glm::Tables& T)
 {
   if (bad(a)) return neg_inf();
   if (bad(b)) return a;
   if (a < b) return neg_inf();
-  return a + log1p(-exp(b - a));
+  return a + glm::log1p(-glm::exp(b - a, T));
 }
 
 struct EmCtx {
   int E;
   const double *ep, *rate, *A, *B, *Lam;
+  glm::Tables T;
 };
 
 // cumulative hazard of the plain epoch grid (coal_EM.cpp:100-103); serial by construction
@@ -97,18 +102,19 @@ __device__ void em_cumhaz(int E, const double* ep, const double* rate, double* L
 }
 
 // coal_EM ctor -> get_AB, coal_EM.cpp:105-149, entry i
-__device__ void em_AB(int E, const double* ep, const double* rate, const double* Lam, int i, double* A, double* B)
+__device__ void em_AB(int E, const double* ep, const double* rate, const double* Lam, int i, double* A, double* B,
+                      const glm::Tables& T)
 {
   const double r = rate[i];
   if (i < E - 1) {
     const double tb = ep[i], te = ep[i + 1], inv = 1.0 / r;
     if (r > 0 && te != 0 && te - tb > 0) {
-      A[i] = lme(-Lam[i], -Lam[i + 1]);
-      double b = (tb + inv) - (te + inv) * exp(-Lam[i + 1] + Lam[i]);
-      B[i] = log(b) - Lam[i];
+      A[i] = lme(-Lam[i], -Lam[i + 1], T);
+      double b = (tb + inv) - (te + inv) * glm::exp(-Lam[i + 1] + Lam[i], T);
+      B[i] = glm::log(b, T) - Lam[i];
     } else { A[i] = neg_inf(); B[i] = neg_inf(); }
   } else {
-    if (r > 0) { A[i] = -Lam[i]; B[i] = log(ep[i] + 1.0 / r) - Lam[i]; }
+    if (r > 0) { A[i] = -Lam[i]; B[i] = glm::log(ep[i] + 1.0 / r, T) - Lam[i]; }
     else { A[i] = neg_inf(); B[i] = neg_inf(); }
   }
 }
@@ -120,27 +126,30 @@ __device__ __forceinline__ int tint_k(int E, const double* ep, double t)
   return E;
 }
 
-// EM_shared(t, t, ...), coal_EM.cpp:153-295.  emit(e, num_e, denom_e) is called for every
-// epoch in order (so callers can reduce across a warp); returns the log normaliser.
-template <class Emit>
-__device__ double task_shared(const EmCtx& c, double t, int k, bool active, Emit emit)
+// The epoch that contains t, EM_shared: log-domain num / denom (coal_EM.cpp:198-210)
+__device__ __forceinline__ void shared_special(const EmCtx& c, double t, int et, double& num_t, double& den_t)
 {
-  const int E = c.E, et = k - 1;
-  double num_t = 0, den_t = 0, nc = 1.0;
+  const double r = c.rate[et];
+  const double c0 = c.Lam[et];
+  const double c1 = c0 + r * (t - c.ep[et]);
+  if (r > 0) {
+    const double inv = 1.0 / r, tb = c.ep[et];
+    num_t = lme(-c0, -c1, c.T);
+    den_t = glm::log((tb + inv) / inv - (t + inv) / inv * glm::exp(-c1 + c0, c.T), c.T) + glm::log(inv, c.T) - c0;
+  } else { num_t = neg_inf(); den_t = neg_inf(); }
+}
+
+// EM_shared(t, t, ...) after the normaliser is known (coal_EM.cpp:263-292).  pl = state of the
+// running logsumexp over A[0..et-1] (1.0 = the reference's "nothing yet" sentinel, coal_EM.cpp:254).
+// emit(e, num_e, denom_e) for every epoch in order; returns the log normaliser.
+template <class Emit>
+__device__ double task_shared(const EmCtx& c, int et, bool active, double pl, double num_t, double den_t, Emit emit)
+{
+  const int E = c.E;
+  double nc = 0.0;
   bool good = false;
   if (active) {
-    const double r = c.rate[et];
-    const double c0 = c.Lam[et];
-    const double c1 = c0 + r * (t - c.ep[et]);
-    if (r > 0) {
-      const double inv = 1.0 / r, tb = c.ep[et];
-      num_t = lme(-c0, -c1);
-      den_t = log((tb + inv) / inv - (t + inv) / inv * exp(-c1 + c0)) + log(inv) - c0;
-    } else { num_t = neg_inf(); den_t = neg_inf(); }
-    for (int e = 0; e <= et; e++) {
-      const double v = (e < et) ? c.A[e] : num_t;
-      if (nc == 1.0) nc = v; else nc = lse(nc, v);
-    }
+    nc = (pl == 1.0) ? num_t : lse(pl, num_t, c.T);
     good = !bad(nc);
   }
   double integ = 1.0;
@@ -149,14 +158,14 @@ __device__ double task_shared(const EmCtx& c, double t, int k, bool active, Emit
     double ne = 0.0, de = 0.0;
     if (good) {
       if (e < lim) {
-        ne = exp(((e < et) ? c.A[e] : num_t) - nc);
+        ne = glm::exp(((e < et) ? c.A[e] : num_t) - nc, c.T);
         if (integ > 0.0) integ -= ne; else integ = 0.0;
-        de = exp(((e < et) ? c.B[e] : den_t) - nc);
+        de = glm::exp(((e < et) ? c.B[e] : den_t) - nc, c.T);
         de += -c.ep[e] * ne + (c.ep[e + 1] - c.ep[e]) * integ;
         if (de < 0.0) de = 0.0;
       } else if (e == E - 1 && et == E - 1) {
-        ne = exp(num_t - nc);
-        de = exp(den_t - nc);
+        ne = glm::exp(num_t - nc, c.T);
+        de = glm::exp(den_t - nc, c.T);
         de -= c.ep[e] * ne;
         if (de < 0.0) de = 0.0;
       }
@@ -164,6 +173,18 @@ __device__ double task_shared(const EmCtx& c, double t, int k, bool active, Emit
     emit(e, ne, de);
   }
   return good ? nc : 0.0;
+}
+
+// running logsumexp state after A[0..j-1] for j = 0..E (coal_EM.cpp:254-258), shared by all bins
+__device__ void shared_prefix_chain(const EmCtx& c, double* PL)
+{
+  double nc = 1.0;
+  PL[0] = nc;
+  for (int e = 0; e < c.E; e++) {
+    const double v = c.A[e];
+    if (nc == 1.0) nc = v; else nc = lse(nc, v, c.T);
+    PL[e + 1] = nc;
+  }
 }
 
 // EM_notshared(t, t, ...), coal_EM.cpp:297-468 (327-357, 435-466)
@@ -180,14 +201,14 @@ __device__ double task_notshared(const EmCtx& c, double t, int k, bool active, E
     if (et != E - 1) {
       const double c3 = c2 + r * (c.ep[k] - t);
       if (r > 0) {
-        num_t = lme(-c2, -c3);
-        den_t = log((t + inv) - (c.ep[k] + inv) * exp(-c3 + c2)) - c2;
+        num_t = lme(-c2, -c3, c.T);
+        den_t = glm::log((t + inv) - (c.ep[k] + inv) * glm::exp(-c3 + c2, c.T), c.T) - c2;
         nc = num_t;
       } else { num_t = neg_inf(); den_t = neg_inf(); nc = neg_inf(); }
-      for (int e = et + 1; e < E; e++) nc = lse(nc, c.A[e]);
+      for (int e = et + 1; e < E; e++) nc = lse(nc, c.A[e], c.T);
     } else {
       num_t = -c2;
-      den_t = log(t + inv) - c2;
+      den_t = glm::log(t + inv, c.T) - c2;
       nc = num_t;
     }
     good = !bad(nc);
@@ -201,13 +222,13 @@ __device__ double task_notshared(const EmCtx& c, double t, int k, bool active, E
       } else {
         const double ln = (e == et) ? num_t : c.A[e];
         const double ld = (e == et) ? den_t : c.B[e];
-        ne = exp(ln - nc);
+        ne = glm::exp(ln - nc, c.T);
         if (e < E - 1) {
           if (integ > 0.0) integ -= ne; else integ = 0.0;
-          de = exp(ld - nc);
+          de = glm::exp(ld - nc, c.T);
           de += -c.ep[e] * ne + (c.ep[e + 1] - c.ep[e]) * integ;
         } else {
-          de = exp(ld - nc);
+          de = glm::exp(ld - nc, c.T);
           de -= c.ep[e] * ne;
         }
         if (de < 0.0) de = 0.0;
@@ -218,112 +239,201 @@ __device__ double task_notshared(const EmCtx& c, double t, int k, bool active, E
   return good ? nc : 0.0;
 }
 
-__device__ __forceinline__ double warp_sum(double v)
-{
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// ---- stage iii: one CTA per bootstrap replicate, EM to convergence -------------------------
+// ---- stage iii: EM to convergence ----------------------------------------------------------
+// One thread-block cluster per bootstrap replicate (cluster size 1 when there are enough
+// replicates to fill the GPU, up to 8 SMs per replicate when there are few).  Per iteration:
+//   A  cumulative hazard (serial), per-epoch A_ep / B_ep
+//   B  the sequential logsumexp folds: one prefix chain for all "shared" tasks, one suffix chain
+//      per bin for the "not shared" tasks (these folds bound the iteration latency)
+//   C  per (bin, type) task: posterior mass / exposure per epoch -> scratch M[which][e][task]
+//      (tasks are dealt round-robin to the CTAs of the cluster)
+//   D  cluster barrier; every CTA then sums M over the tasks IN THE REFERENCE'S ORDER
+//      (coal.cpp:3704-3733) and applies the M-step redundantly, so no broadcast is needed.
 __global__ void __launch_bounds__(EM_THREADS)
 k_em(int E, const double* __restrict__ epochs, const double* __restrict__ rates_init,
      const double* __restrict__ age_bin_g, const double* __restrict__ counts, int max_iter,
-     double* __restrict__ rates_out, int32_t* __restrict__ iters_out, double* __restrict__ ll_out)
+     const uint64_t* __restrict__ exp_tab_g, const uint64_t* __restrict__ log_tab_g, double* scratch,
+     double* __restrict__ rates_out, int32_t* __restrict__ iters_out, double* __restrict__ ll_out, long long* prof_g)
 {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+  const int rep = blockIdx.x / csize;
+
   extern __shared__ double sm[];
-  double* ep = sm;                 // [E]
-  double* rate = ep + E;           // [E]
-  double* Lam = rate + E;          // [E]
-  double* A = Lam + E;             // [E]
-  double* B = A + E;               // [E]
-  double* wn = B + E;              // [EM_WARPS][E]
-  double* wd = wn + EM_WARPS * E;  // [EM_WARPS][E]
-  double* wl = wd + EM_WARPS * E;  // [EM_WARPS]
-  double* tn = wl + EM_WARPS;      // [E]
-  double* td = tn + E;             // [E]
+  double* ep = sm;                  // [E]
+  double* rate = ep + E;            // [E]
+  double* Lam = rate + E;           // [E]
+  double* A = Lam + E;              // [E]
+  double* B = A + E;                // [E]
+  double* PL = B + E;               // [E+1]
+  double* tn = PL + E + 1;          // [E]
+  double* td = tn + E;              // [E]
+  double* q = td + E;               // [E]
+  double* numt = q + E;             // [NBINS] shared tasks: special-epoch log num
+  double* dent = numt + NBINS;      // [NBINS]
+  uint64_t* etab = (uint64_t*)(dent + NBINS);  // [256]
+  uint64_t* ltab = etab + 256;                 // [256]
   __shared__ int stop_flag;
   __shared__ double ll_s, prev_s;
+  __shared__ unsigned char act[EM_TASKS];
 
-  const int rep = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool is_shared = tid < EM_HALF;
-  const int bin = is_shared ? tid : tid - EM_HALF;
+  const int tid = threadIdx.x;
   for (int e = tid; e < E; e += blockDim.x) { ep[e] = epochs[e]; rate[e] = rates_init[e]; }
+  for (int i = tid; i < 256; i += blockDim.x) { etab[i] = exp_tab_g[i]; ltab[i] = log_tab_g[i]; }
   if (tid == 0) { stop_flag = 0; ll_s = neg_inf(); }
-  __syncthreads();
+  // task of this thread: threads 0..383 <-> task = tid; bin = task >> 1, type = task & 1 (0 shared)
+  const int task = tid, bin = tid >> 1;
+  const bool is_task = tid < 2 * NBINS;
+  const bool is_shared = (tid & 1) == 0;
   double t = 0.0, cnt = 0.0;
-  int k = 1;
-  if (bin < NBINS) {
+  if (is_task) {
     t = age_bin_g[bin];
-    k = tint_k(E, ep, t);
     cnt = counts[(size_t)rep * 2 * NBINS + (is_shared ? 0 : NBINS) + bin];
   }
-  const bool active = bin < NBINS && cnt > 0;  // coal.cpp:3706, 3719
-  EmCtx c{E, ep, rate, A, B, Lam};
+  const bool active = is_task && cnt > 0;  // coal.cpp:3706, 3719
+  if (tid < EM_TASKS) act[tid] = active ? 1 : 0;
+  __syncthreads();
+  const int k = is_task ? tint_k(E, ep, t) : 1;
+  const int et = k - 1;
+  const bool mine = active && ((task % csize) == crank);  // tasks dealt round-robin over the cluster
+  EmCtx c{E, ep, rate, A, B, Lam, glm::Tables{etab, ltab}};
+  // scratch of this replicate: [buf][task][RS], row = {count*num[e] (E), count*denom[e] (E), count*logl}
+  const int RS = 2 * E + 2;
+  double* Mrep = scratch + (size_t)rep * 2 * EM_TASKS * RS;
+  long long* prof = prof_g ? prof_g + (size_t)blockIdx.x * 8 : nullptr;
+  long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (is_task && !active)  // rows of inactive tasks stay 0 so that the sums below need no test
+    for (int b2 = 0; b2 < 2; b2++)
+      for (int e = 0; e < RS; e++) Mrep[((size_t)b2 * EM_TASKS + task) * RS + e] = 0.0;
 
   int iter = 0;
   for (; iter < max_iter; iter++) {
+    double* M = Mrep + (size_t)(iter & 1) * EM_TASKS * RS;
+    double* Mt = M + (size_t)task * RS;
+    long long t0 = prof ? clock64() : 0, t1;
     if (tid == 0) em_cumhaz(E, ep, rate, Lam);
     __syncthreads();
-    for (int e = tid; e < E; e += blockDim.x) em_AB(E, ep, rate, Lam, e, A, B);
+    for (int e = tid; e < E; e += blockDim.x) em_AB(E, ep, rate, Lam, e, A, B, c.T);
     __syncthreads();
+    if (prof) { t1 = clock64(); tp[0] += t1 - t0; t0 = t1; }
+    // folds and special epochs
+    double my_logl = 0.0;
+    if (tid == EM_THREADS - 1) shared_prefix_chain(c, PL);
     auto emit = [&](int e, double ne, double de) {
-      double a = warp_sum(cnt * ne), b = warp_sum(cnt * de);
-      if (lane == 0) { wn[warp * E + e] = a; wd[warp * E + e] = b; }
+      Mt[e] = cnt * ne;
+      Mt[E + e] = cnt * de;
     };
-    double logl = is_shared ? task_shared(c, t, k, active, emit) : task_notshared(c, t, k, active, emit);
-    double l = warp_sum(active ? cnt * logl : 0.0);
-    if (lane == 0) wl[warp] = l;
+    if (mine && !is_shared) my_logl = cnt * task_notshared(c, t, k, true, emit);
+    if (mine && is_shared) shared_special(c, t, et, numt[bin], dent[bin]);
     __syncthreads();
-    for (int e = tid; e < E; e += blockDim.x) {
-      double a = 0.0, b = 0.0;
-      for (int w = 0; w < EM_WARPS; w++) { a += wn[w * E + e]; b += wd[w * E + e]; }
-      tn[e] = a; td[e] = b;
+    if (prof) { t1 = clock64(); tp[1] += t1 - t0; t0 = t1; }
+    if (mine && is_shared) my_logl = cnt * task_shared(c, et, true, PL[et], numt[bin], dent[bin], emit);
+    if (mine) Mt[2 * E] = my_logl;
+    __threadfence();
+    if (prof) { t1 = clock64(); tp[2] += t1 - t0; t0 = t1; }
+    cluster.sync();
+    if (prof) { t1 = clock64(); tp[3] += t1 - t0; t0 = t1; }
+    // sums over the tasks in the reference's order (bin ascending, shared before not shared,
+    // coal.cpp:3704-3733): thread = column of M, ten loads in flight per step
+    if (tid <= 2 * E) {
+      const double* col = M + tid;
+      double acc = 0.0;
+      constexpr int U = 10;  // 2 * NBINS = 370 = 37 * 10
+      double v[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) v[u] = __ldcg(col + (size_t)u * RS);
+      for (int j = 0; j < 2 * NBINS; j += U) {
+        double w[U];
+        if (j + U < 2 * NBINS) {
+#pragma unroll
+          for (int u = 0; u < U; u++) w[u] = __ldcg(col + (size_t)(j + U + u) * RS);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) acc += v[u];
+#pragma unroll
+        for (int u = 0; u < U; u++) v[u] = w[u];
+      }
+      if (tid < E) tn[tid] = acc;
+      else if (tid < 2 * E) td[tid - E] = acc;
+      else { prev_s = ll_s; ll_s = acc; }
     }
     __syncthreads();
+    if (prof) { t1 = clock64(); tp[4] += t1 - t0; t0 = t1; }
+    for (int e = tid; e < E; e += blockDim.x) q[e] = tn[e] / td[e];
+    __syncthreads();
     if (tid == 0) {
-      double ll = 0.0;
-      for (int w = 0; w < EM_WARPS; w++) ll += wl[w];
       for (int e = 0; e < E; e++) {  // M-step, coal.cpp:3771-3815 (regularise == 2)
         if (tn[e] == 0) rate[e] = (e > 0) ? rate[e - 1] : 0.0;
         else if (td[e] == 0) { }
-        else { double r = tn[e] / td[e]; rate[e] = (r < 5e-9) ? 5e-9 : r; }
+        else { double r = q[e]; rate[e] = (r < 5e-9) ? 5e-9 : r; }
       }
-      prev_s = ll_s;
-      ll_s = ll;
-      if ((ll / prev_s > 1.0 - 1e-7) && (iter > 1000)) stop_flag = 1;  // coal.cpp:3822
+      if ((ll_s / prev_s > 1.0 - 1e-7) && (iter > 1000)) stop_flag = 1;  // coal.cpp:3822
     }
     __syncthreads();
+    if (prof) { t1 = clock64(); tp[5] += t1 - t0; t0 = t1; }
     if (stop_flag) break;
   }
-  for (int e = tid; e < E; e += blockDim.x) rates_out[(size_t)rep * E + e] = rate[e];
-  if (tid == 0) { iters_out[rep] = iter; ll_out[rep] = ll_s; }
+  if (prof && tid == 0) for (int i = 0; i < 8; i++) prof[i] = tp[i];
+  if (prof && tid == EM_THREADS - 1) prof[6] = tp[1];
+  if (crank == 0) {
+    for (int e = tid; e < E; e += blockDim.x) rates_out[(size_t)rep * E + e] = rate[e];
+    if (tid == 0) { iters_out[rep] = iter; ll_out[rep] = ll_s; }
+  }
 }
 
 // E-step probe: one thread per age, plain stores
 __global__ void k_estep(int shared, int E, const double* __restrict__ epochs, const double* __restrict__ rates,
-                        int n_t, const double* __restrict__ tt, double* __restrict__ num, double* __restrict__ denom,
+                        int n_t, const double* __restrict__ tt, const uint64_t* __restrict__ exp_tab_g,
+                        const uint64_t* __restrict__ log_tab_g, double* __restrict__ num, double* __restrict__ denom,
                         double* __restrict__ logl)
 {
   extern __shared__ double sm[];
-  double* ep = sm; double* rate = ep + E; double* Lam = rate + E; double* A = Lam + E; double* B = A + E;
+  double* ep = sm; double* rate = ep + E; double* Lam = rate + E; double* A = Lam + E; double* B = A + E; double* PL = B + E;
+  EmCtx c{E, ep, rate, A, B, Lam, glm::Tables{exp_tab_g, log_tab_g}};
   for (int e = threadIdx.x; e < E; e += blockDim.x) { ep[e] = epochs[e]; rate[e] = rates[e]; }
   __syncthreads();
   if (threadIdx.x == 0) em_cumhaz(E, ep, rate, Lam);
   __syncthreads();
-  for (int e = threadIdx.x; e < E; e += blockDim.x) em_AB(E, ep, rate, Lam, e, A, B);
+  for (int e = threadIdx.x; e < E; e += blockDim.x) em_AB(E, ep, rate, Lam, e, A, B, c.T);
   __syncthreads();
-  EmCtx c{E, ep, rate, A, B, Lam};
+  if (threadIdx.x == 0) shared_prefix_chain(c, PL);
+  __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_t; i += gridDim.x * blockDim.x) {
     const double t = tt[i];
     const int k = tint_k(E, ep, t);
     double* n = num + (size_t)i * E;
     double* d = denom + (size_t)i * E;
     auto emit = [&](int e, double ne, double de) { n[e] = ne; d[e] = de; };
-    logl[i] = shared ? task_shared(c, t, k, true, emit) : task_notshared(c, t, k, true, emit);
+    if (shared) {
+      double num_t, den_t;
+      shared_special(c, t, k - 1, num_t, den_t);
+      logl[i] = task_shared(c, k - 1, true, PL[k - 1], num_t, den_t, emit);
+    } else {
+      logl[i] = task_notshared(c, t, k, true, emit);
+    }
   }
 }
 
+// test hook: which = 0 exp, 1 log, 2 log1p
+__global__ void k_libm(int which, int n, const double* __restrict__ x, const uint64_t* __restrict__ exp_tab_g,
+                       const uint64_t* __restrict__ log_tab_g, double* __restrict__ y)
+{
+  glm::Tables T{exp_tab_g, log_tab_g};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    y[i] = which == 0 ? glm::exp(x[i], T) : which == 1 ? glm::log(x[i], T) : glm::log1p(x[i]);
+}
+
 // ---- launchers -------------------------------------------------------------------------------
+int ensure_libm_tables(colate_handle* h)
+{
+  if (h->libm_tab.p) return 0;
+  CK(h->libm_tab.ensure(512 * 8));
+  CK(cudaMemcpyAsync(h->libm_tab.p, glm::hEXP_TAB, 256 * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->libm_tab.as<uint64_t>() + 256, glm::hLOG_TAB, 256 * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int run_bootstrap(colate_handle* h, int R, int num_blocks, double age)
 {
   k_bootstrap<<<R, 256, 0, h->stream>>>(num_blocks, h->d_weights.as<int32_t>(), h->d_blockstats.as<double>(), age,
@@ -335,24 +445,71 @@ int run_bootstrap(colate_handle* h, int R, int num_blocks, double age)
 
 int run_em(colate_handle* h, int R, int E, int max_iter)
 {
-  const size_t smem = sizeof(double) * ((size_t)5 * E + 2 * EM_WARPS * E + EM_WARPS + 2 * E);
+  int rc = ensure_libm_tables(h);
+  if (rc) return rc;
+  int csize = 1;
+  if (const char* e = getenv("COLATE_EM_CLUSTER")) csize = atoi(e);
+  else { while (csize < 8 && R * csize * 2 <= 148) csize *= 2; }
+  if (csize != 1 && csize != 2 && csize != 4 && csize != 8) csize = 1;
+  const size_t smem = sizeof(double) * ((size_t)9 * E + 1 + 2 * NBINS) + 512 * 8;
   CK(cudaFuncSetAttribute(k_em, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
-  k_em<<<R, EM_THREADS, smem, h->stream>>>(E, h->d_epochs.as<double>(), h->d_rates.as<double>() /*init*/,
-                                           h->d_agebin.as<double>(), h->d_counts.as<double>(), max_iter,
-                                           h->d_rates.as<double>() + E, h->d_iters.as<int32_t>(), h->d_ll.as<double>());
+  CK(h->d_scratch.ensure((size_t)R * 2 * (2 * E + 2) * EM_TASKS * 8 + 1024));
+  long long* prof = nullptr;
+  if (getenv("COLATE_EM_PROF")) {
+    CK(h->d_prof.ensure((size_t)R * csize * 8 * 8));
+    CK(cudaMemsetAsync(h->d_prof.p, 0, (size_t)R * csize * 8 * 8, h->stream));
+    prof = h->d_prof.as<long long>();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(R * csize);
+  cfg.blockDim = dim3(EM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const uint64_t* tabs = h->libm_tab.as<uint64_t>();
+  CK(cudaLaunchKernelEx(&cfg, k_em, E, (const double*)h->d_epochs.as<double>(), (const double*)h->d_rates.as<double>(),
+                        (const double*)h->d_agebin.as<double>(), (const double*)h->d_counts.as<double>(), max_iter, tabs, tabs + 256,
+                        h->d_scratch.as<double>(), h->d_rates.as<double>() + E, h->d_iters.as<int32_t>(), h->d_ll.as<double>(), prof));
   h->launches += 1;
   CK(cudaGetLastError());
+  if (prof) {
+    std::vector<long long> hp(8);
+    CK(cudaMemcpyAsync(hp.data(), prof, 64, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    fprintf(stderr, "[k_em prof, CTA 0, cycles] AB %lld | folds+notshared %lld (tid511: %lld) | shared %lld | cluster.sync %lld | column sums %lld | M-step %lld (csize %d)\n",
+            hp[0], hp[1], hp[6], hp[2], hp[3], hp[4], hp[5], csize);
+  }
   return 0;
 }
 
 int run_estep(colate_handle* h, int shared, int E, int n_t)
 {
-  const size_t smem = sizeof(double) * 5 * E;
+  int rc = ensure_libm_tables(h);
+  if (rc) return rc;
+  const size_t smem = sizeof(double) * (6 * E + 1);
   double* base = h->d_tmp.as<double>();  // [t: n_t][num: n_t*E][denom: n_t*E][logl: n_t]
-  k_estep<<<(n_t + 127) / 128, 128, smem, h->stream>>>(shared, E, h->d_epochs.as<double>(), h->d_rates.as<double>(), n_t, base,
-                                                       base + n_t, base + n_t + (size_t)n_t * E,
-                                                       base + n_t + 2 * (size_t)n_t * E);
+  const uint64_t* tabs = h->libm_tab.as<uint64_t>();
+  k_estep<<<1, 256, smem, h->stream>>>(shared, E, h->d_epochs.as<double>(), h->d_rates.as<double>(), n_t, base, tabs, tabs + 256,
+                                       base + n_t, base + n_t + (size_t)n_t * E, base + n_t + 2 * (size_t)n_t * E);
   CK(cudaGetLastError());
+  return 0;
+}
+
+int run_libm(colate_handle* h, int which, int n, const double* x_host, double* y_host)
+{
+  int rc = ensure_libm_tables(h);
+  if (rc) return rc;
+  CK(h->d_tmp.ensure((size_t)n * 16));
+  double* d = h->d_tmp.as<double>();
+  const uint64_t* tabs = h->libm_tab.as<uint64_t>();
+  CK(cudaMemcpyAsync(d, x_host, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+  k_libm<<<296, 256, 0, h->stream>>>(which, n, d, tabs, tabs + 256, d + n);
+  CK(cudaMemcpyAsync(y_host, d + n, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 

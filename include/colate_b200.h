@@ -130,6 +130,11 @@ int colate_stage3_em(colate_handle* h, int R, int E, const double* epochs, const
 int colate_estep(colate_handle* h, int shared, int E, const double* epochs, const double* rates,
                  int n_t, const double* t, double* num, double* denom, double* logl);
 
+/* 1 if this host's libm evaluates exp/log/log1p bit-identically to the device implementation
+ * (glibc 2.39, FMA variants): then colate_stage3_em() reproduces the reference run on this host
+ * bit for bit.  0: the device still follows glibc 2.39/FMA; the host's libm differs. */
+int colate_libm_exact(void);
+
 /* ---- timing of the last stage-1 call (CUDA events on the handle's stream), ms -------- */
 typedef struct {
   float join_ms;     /* k_join x2 (skipped when the join of a genome is still cached)            */

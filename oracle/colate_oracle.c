@@ -693,3 +693,9 @@ int oracle_write_coal(const char* path, int R, int E, const double* epochs, doub
   fclose(f);
   return 0;
 }
+
+/* the host libm itself, for pinning the device's glibc-exact exp/log/log1p (which = 0,1,2) */
+void oracle_libm(int which, int n, const double* x, double* y)
+{
+  for (int i = 0; i < n; i++) y[i] = which == 0 ? exp(x[i]) : which == 1 ? log(x[i]) : log1p(x[i]);
+}

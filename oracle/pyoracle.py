@@ -75,6 +75,7 @@ def lib():
         L.oracle_estep.argtypes = [C.c_int, C.c_int, _f64, _f64, C.c_double, _f64, _f64]
         L.oracle_estep.restype = C.c_double
         L.oracle_em_run.argtypes = [C.c_int, _f64, _f64, _f64, _f64, C.c_int, _f64, C.POINTER(C.c_double)]
+        L.oracle_libm.argtypes = [C.c_int, C.c_int, _f64, _f64]
         L.oracle_write_coal.argtypes = [C.c_char_p, C.c_int, C.c_int, _f64, _f64, C.c_int, C.c_int]
         _lib = L
     return _lib
@@ -193,6 +194,13 @@ def em_run(epochs, rates_init, counts, max_iter=100000):
                              np.ascontiguousarray(rates_init, dtype=np.float64), age_bins(),
                              np.ascontiguousarray(counts, dtype=np.float64), max_iter, out, C.byref(ll))
     return out, it, ll.value
+
+
+def libm(which: str, x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.zeros_like(x)
+    lib().oracle_libm({"exp": 0, "log": 1, "log1p": 2}[which], x.shape[0], x, y)
+    return y
 
 
 def write_coal(path, epochs, rates, is_ancient=False, ep_null=0):

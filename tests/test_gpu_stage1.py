@@ -66,7 +66,7 @@ def test_stage1_config1_shape(handle):
     handle.load(sites, gt, gr)
     s1 = handle.stage1(api.mt_seed(1))
     _compare_stage1(o, s1)
-    assert s1.n_used > 50000
+    assert s1.n_used > 20000
 
 
 def test_stage1_edge_cases(handle):
