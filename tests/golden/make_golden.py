@@ -1,0 +1,118 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/*.npz|*.coal from the UNMODIFIED reference compiled by oracle/Makefile
+(oracle/_ref/libcolate_ref.so = the reference's own parse_tmptmp / coal_EM behind oracle/ref_probe.cpp,
+oracle/_ref/Colate = its CLI).  Run in the build container (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference ships no golden vectors for this path; these fixtures are its outputs
+on small seeded inputs and pin both the oracle (CPU tests) and the CUDA path (GPU tests)."""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from colate_b200 import synth  # noqa: E402
+from oracle import pyoracle as po  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def dataset(seed, rows, lens, weird, pt=0.7, pr=0.7):
+    sites = synth.make_sites(seed, rows, lens, weird=weird)
+    gt = synth.make_genome(seed + 100, sites, pt, weird=weird)
+    gr = synth.make_genome(seed + 200, sites, pr, weird=weird)
+    return sites, gt, gr
+
+
+def pack(sites, gt, gr):
+    d = dict(chr_names=np.array(sites.chr_names), site_off=sites.site_off, pos=sites.pos, age_begin=sites.age_begin,
+             age_end=sites.age_end, flipped=sites.flipped, n_branch=sites.n_branch, anc=sites.anc, der=sites.der, odd=sites.odd,
+             chrom_len=np.array(sites.chrom_len, dtype=np.int64))
+    for nm, g in (("t", gt), ("r", gr)):
+        for k in ("chrom", "bp", "anc", "der", "aaf", "daf"):
+            d[f"{nm}_{k}"] = getattr(g, k)
+    return d
+
+
+def main():
+    assert po.ref_available() and po.ref_cli(), "build oracle/_ref first (make -C oracle ref)"
+    # ---- stage i: parse_tmptmp on weird rows, with and without masks
+    seed = 11
+    sites, gt, gr = dataset(seed, [1500, 900, 1200], [2.4e8, 6.1e7, 1.3e8], weird=0.12)
+    masks = {"tm": [synth.make_mask(seed * 10 + c, int(L) if c != 1 else int(L) // 2, 0.3, lower=(c == 2)) for c, L in enumerate(sites.chrom_len)],
+             "rm": [synth.make_mask(seed * 20 + c, int(L), 0.2) for c, L in enumerate(sites.chrom_len)]}
+    d = tempfile.mkdtemp()
+    synth.write_dataset(d, sites, {"t": gt, "r": gr}, masks)
+    out = pack(sites, gt, gr)
+    # masks are stored as pass bits at the site positions (the full sequences are ~400 MB)
+    from colate_b200 import api
+    up = lambda ms: [bytes(m).upper() for m in ms]
+    out["tmask_bits"] = api.mask_bits_from_seq(up(masks["tm"]), sites.site_off, sites.pos)
+    out["rmask_bits"] = api.mask_bits_from_seq(up(masks["rm"]), sites.site_off, sites.pos)
+    for tag, tm, rm in (("nomask", None, None), ("mask", "tm", "rm")):
+        r = po.ref_parse_tmptmp(d, sites.chr_names, "syn", "t", "r", seed=seed, tmask=tm, rmask=rm)
+        assert r["emp_rest"].sum() == 0
+        for k in ("num_blocks", "shared", "notshared", "shared_emp", "notshared_emp", "mt", "next_words"):
+            out[f"ref_{tag}_{k}"] = np.asarray(r[k])
+    out["seed"] = seed
+    np.savez_compressed(os.path.join(OUT, "stage1_small.npz"), **out)
+
+    # ---- whole path: reference CLI .coal for three flag sets + E-step vectors
+    seed = 1
+    sites, gt, gr = dataset(seed, [30000, 20000], [2.5e8, 1.2e8], weird=0.02)
+    d = tempfile.mkdtemp()
+    synth.write_dataset(d, sites, {"t": gt, "r": gr})
+    cli = pack(sites, gt, gr)
+    cases = {"bins02_R1": ["--bins", "3,7,0.2"], "bins02_R3": ["--bins", "3,7,0.2", "--num_bootstraps", "3"],
+             "ancient": ["--bins", "3,7,0.2", "--target_age", "7000", "--reference_age", "0", "--years_per_gen", "28"],
+             "bins01_R1": ["--bins", "3,7,0.1"]}
+    for name, extra in cases.items():
+        cmd = [po.ref_cli(), "--mode", "mut", "--mut", d + "/syn", "--chr", d + "/chr.txt", "--target_tmp", d + "/t.colate.in",
+               "--reference_tmp", d + "/r.colate.in", "--seed", str(seed), "-o", d + "/" + name] + extra
+        pr = subprocess.run(cmd, capture_output=True, text=True)
+        assert pr.returncode == 0, pr.stderr
+        txt = open(d + "/" + name + ".coal").read()
+        open(os.path.join(OUT, f"cli_{name}.coal"), "w").write(txt)
+        nb = [ln for ln in pr.stderr.split("\n") if ln.startswith("Number of blocks")]
+        cli[f"{name}_num_blocks"] = int(nb[0].split(":")[1])
+        cli[f"{name}_args"] = np.array(extra)
+    cli["seed"] = seed
+    np.savez_compressed(os.path.join(OUT, "cli_small.npz"), **cli)
+
+    # ---- E-step known answers from the reference's coal_EM (the object its unit test exercises)
+    ab = po.age_bins()
+    rng = np.random.default_rng(0)
+    est = {}
+    for tag, bins, age in (("b02", "3,7,0.2", 0.0), ("b01", "3,7,0.1", 0.0), ("anc", "3,7,0.2", 250.0)):
+        ep, null = po.epochs_from_bins(bins, age, 28.0)
+        E = len(ep)
+        rates = np.stack([np.full(E, 1 / 20000.), np.exp(rng.uniform(np.log(1e-7), np.log(1e-2), E)), np.full(E, 1e-7), np.full(E, 1e-1)])
+        rates[1, 2] = 0.0
+        num = np.zeros((4, 2, 185, E)); den = np.zeros_like(num); ll = np.zeros((4, 2, 185))
+        for i in range(4):
+            for s in (0, 1):
+                for b in range(185):
+                    ll[i, s, b], num[i, s, b], den[i, s, b] = po.ref_estep(s == 0, ep, rates[i], ab[b])
+        est.update({f"{tag}_epochs": ep, f"{tag}_ep_null": null, f"{tag}_rates": rates, f"{tag}_num": num, f"{tag}_den": den, f"{tag}_ll": ll})
+    np.savez_compressed(os.path.join(OUT, "estep_ref.npz"), **est)
+
+    # ---- <random>: libstdc++ outputs
+    w = np.zeros(4000, np.uint32); po.ref().ref_mt_words(1, 0, 4000, w)
+    w2 = np.zeros(1000, np.uint32); po.ref().ref_mt_words(123456789, 10**6, 1000, w2)
+    u = np.zeros(2000); po.ref().ref_uniform_real(7, 3, 2000, u)
+    ints = {}
+    for nb in (1, 9, 105, 500):
+        a = np.zeros(3000, np.int32); po.ref().ref_uniform_int(3, 11, nb, 3000, a); ints[f"int_{nb}"] = a
+    np.savez_compressed(os.path.join(OUT, "random_ref.npz"), words_seed1=w, words_seed123456789_skip1e6=w2, real_seed7_skip3=u, **ints)
+    print("golden fixtures written to", OUT)
+    for f in sorted(os.listdir(OUT)):
+        print("  ", f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

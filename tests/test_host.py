@@ -1,0 +1,232 @@
+"""CPU: host side of the product (readers, seek emulation, RNG, epoch grid, writers, CLI) and the C ABI surface.
+No compute entry point is exercised here -- those need a GPU and fail loudly without one."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from colate_b200 import _lib, api, synth
+from oracle import pyoracle as po
+from helpers import GOLDEN, dataset_from, load, same
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "colate_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(colate_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    L = C.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/colate_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert b"sm_100a" in api.lib().colate_version()
+
+
+def test_no_cpu_fallback(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_lib.ColateError) as e:
+        api.Handle(0)
+    assert e.value.code == -4 and "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_touch_the_oracle():
+    for dp, _, files in os.walk(os.path.join(ROOT, "colate_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert "pyoracle" not in txt and "liboracle" not in txt and "oracle/" not in txt.replace("oracle/_ref", ""), os.path.join(dp, f)
+
+
+def test_mt19937_window_generator(built):
+    z = load("random_ref.npz")
+    w = api.mt_seed(1)
+    out = np.zeros(4000, np.uint32)
+    api.lib().colate_mt_generate(w, 4000, out)
+    assert same(out, z["words_seed1"])
+    w = api.mt_seed(123456789)
+    burn = np.zeros(10**6, np.uint32); api.lib().colate_mt_generate(w, 10**6, burn)
+    out = np.zeros(1000, np.uint32); api.lib().colate_mt_generate(w, 1000, out)
+    assert same(out, z["words_seed123456789_skip1e6"])
+    # odd chunk sizes keep the window consistent
+    w = api.mt_seed(1)
+    parts = []
+    for n in (1, 5, 623, 624, 625, 7, 1248, 867):
+        o = np.zeros(n, np.uint32); api.lib().colate_mt_generate(w, n, o); parts.append(o)
+    assert same(np.concatenate(parts), z["words_seed1"][:sum(len(p) for p in parts)])
+
+
+def test_characteristic_polynomial_and_jumps(built):
+    terms = np.zeros(1000, np.int32)
+    n = api.lib().colate_test_charpoly_terms(terms, 1000)
+    assert n == 134 and terms[0] == 0                       # 135 terms with the leading t^19937
+    for q in (0, 3, 9, 17, 20):
+        w = api.mt_seed(77)
+        jw = np.zeros(624, np.uint32)
+        assert api.lib().colate_test_jump_window_host(w, q, jw) == 0
+        a = np.zeros(700, np.uint32); api.lib().colate_mt_generate(jw, 700, a)
+        b = np.zeros(700, np.uint32); po.lib().oracle_mt_words(77, 200 << q, 700, b)
+        assert same(a, b), q
+
+
+def test_block_weights_match_libstdcxx_uniform_int(built):
+    for R, nb, burn in ((1, 9, 0), (5, 9, 777), (1000, 105, 200 * 31), (3, 1, 5), (4, 500, 0)):
+        w = api.mt_seed(11)
+        tmp = np.zeros(max(burn, 1), np.uint32); api.lib().colate_mt_generate(w, burn, tmp)
+        W = api.draw_block_weights(w, R, nb)
+        g = po.mt_seed(11)
+        for _ in range(burn):
+            po.lib().oracle_mt_next(g)
+        assert same(W, po.draw_block_weights(g, R, nb))
+        assert (W.sum(axis=1) == nb).all()
+        nxt = np.zeros(8, np.uint32); api.lib().colate_mt_generate(w, 8, nxt)
+        assert same(nxt, np.array([po.lib().oracle_mt_next(g) for _ in range(8)], np.uint32))
+
+
+def test_bin_thresholds_reproduce_the_bin_index(built):
+    thr = np.zeros(186)
+    assert api.lib().colate_test_bin_thresholds(thr) == 0    # host log() monotone around every threshold
+    rng = np.random.default_rng(0)
+    a = np.concatenate([np.exp(rng.uniform(np.log(1e-4), np.log(9e6), 200000)), thr[1:] / 10, np.nextafter(thr[1:] / 10, 0), [0.0]])
+    x10 = 10 * a
+    want = np.array([po.lib().oracle_bin_of_double_age(v) for v in a])
+    got = np.searchsorted(thr[1:], x10, side="right")
+    assert same(got, want)
+
+
+def test_libm_port_is_this_hosts_libm(built):
+    assert api.libm_exact()
+
+
+def test_ages_epochs_and_age_bins_match_oracle(built):
+    assert same(api.age_bins(), po.age_bins())
+    for ta, ra, ypg in ((None, None, None), ("7000", "0", 28.0), ("1e4", "23000", 29.5), ("0", "500", None)):
+        assert api.ages(ta, ra, ypg) == po.ages(ta, ra, ypg)
+        age, y = api.ages(ta, ra, ypg)
+        for bins in ("3,7,0.2", "3,7,0.1", "2.5,6.5,0.25", "4,7,0.3"):
+            e1, n1 = api.epochs_from_bins(bins, age, y)
+            e2, n2 = po.epochs_from_bins(bins, age, y)
+            assert same(e1, e2) and n1 == n2
+    with pytest.raises(_lib.ColateError):
+        api.epochs_from_bins("3,7")
+
+
+def test_coal_file_roundtrip(built):
+    ep, _ = api.epochs_from_bins("3,7,0.2")
+    ep = ep[1:]          # [0, 0, ...] of a non-ancient run trips the reference's own assert (coal.cpp:3546-3549) when fed back
+    rates = np.abs(np.random.default_rng(1).normal(1e-4, 3e-5, (2, len(ep))))
+    with tempfile.TemporaryDirectory() as d:
+        api.write_coal(os.path.join(d, "a.coal"), ep, rates)
+        po.write_coal(os.path.join(d, "b.coal"), ep, rates)
+        assert open(os.path.join(d, "a.coal")).read() == open(os.path.join(d, "b.coal")).read()
+        with pytest.raises(_lib.ColateError):
+            api.write_coal(os.path.join(d, "bad.coal"), np.concatenate([[0.0], ep]), np.ones((1, len(ep) + 1)))
+            api.epochs_from_coal_file(os.path.join(d, "bad.coal"))
+        e2, r2 = api.epochs_from_coal_file(os.path.join(d, "a.coal"))
+        # --coal goes through stof (float) for the epochs and operator>> (double) for the rates, like the reference
+        line = open(os.path.join(d, "a.coal")).read().split("\n")[1]
+        assert same(e2, po.epochs_from_coal_line(line))
+        assert np.allclose(r2, rates[0], rtol=1e-5)
+        api.write_bin(os.path.join(d, "a.bin"), ep, rates, np.array([1001, 1274], np.int32))
+        raw = open(os.path.join(d, "a.bin"), "rb").read()
+        assert raw[:8] == b"COLATEB1" and np.frombuffer(raw[8:16], np.int32).tolist() == [2, len(ep)]
+        assert same(np.frombuffer(raw[16 + 8 * len(ep):16 + 8 * len(ep) * 3], np.float64).reshape(2, -1), rates)
+
+
+def _brute_chr_ranges(n_chr, chrom):
+    cur, nxt, n = -1, 0, len(chrom)
+    first, end = [], []
+    for c in range(n_chr):
+        while not (cur >= 0 and chrom[cur] == c):
+            if nxt >= n:
+                break
+            cur = nxt; nxt += 1
+        if cur >= 0 and chrom[cur] == c:
+            e = cur + 1
+            while e < n and chrom[e] == c:
+                e += 1
+            first.append(cur); end.append(e); cur, nxt = e - 1, e
+        else:
+            first.append(-1); end.append(-1)
+    return np.array(first), np.array(end)
+
+
+def test_chr_ranges_emulate_the_sequential_seek(built):
+    rng = np.random.default_rng(2)
+    cases = [np.array([0, 0, 1, 1, 2]), np.array([1, 1, 2, 2]), np.array([2, 0, 0, 1]), np.array([], dtype=np.int32),
+             np.array([0, 0, 3, 3, 1, 0, 2]), np.array([1]), np.array([5, 5, 5])]
+    cases += [np.sort(rng.integers(0, 4, 30)) for _ in range(5)] + [rng.integers(0, 5, 25) for _ in range(20)]
+    for ch in cases:
+        f, e = api.chr_ranges(3, ch.astype(np.int32))
+        bf, be = _brute_chr_ranges(3, ch)
+        assert same(f, bf) and same(e, be), ch
+
+
+def test_readers_roundtrip_against_written_files(built):
+    z = load("stage1_small.npz")
+    sites, gt, gr = dataset_from(z)
+    with tempfile.TemporaryDirectory() as d:
+        synth.write_dataset(d, sites, {"t": gt, "r": gr})
+        metas = sites.meta()
+        for c, nm in enumerate(sites.chr_names):
+            lo, hi = int(sites.site_off[c]), int(sites.site_off[c + 1])
+            pos, ab, ae, meta = api.read_mut(os.path.join(d, f"syn_chr{nm}.mut"))
+            assert same(pos, sites.pos[lo:hi]) and same(ab, sites.age_begin[lo:hi]) and same(ae, sites.age_end[lo:hi])
+            assert same(meta, metas[lo:hi])
+        subprocess.run(["gzip", "-k", os.path.join(d, "syn_chr1.mut")], check=True)
+        os.remove(os.path.join(d, "syn_chr1.mut"))                      # Mutations::Read falls back to <file>.gz
+        pos, _, _, _ = api.read_mut(os.path.join(d, "syn_chr1.mut"))
+        assert same(pos, sites.pos[:int(sites.site_off[1])])
+        for nm, g in (("t", gt), ("r", gr)):
+            rc, bp, aaf, daf, al = api.read_colate_in(os.path.join(d, nm + ".colate.in"), sites.chr_names)
+            assert same(rc, g.chrom) and same(bp, g.bp) and same(aaf, g.aaf) and same(daf, g.daf)
+            assert same(al, g.anc.astype(np.uint16) | (g.der.astype(np.uint16) << 8))
+        with pytest.raises(_lib.ColateError):
+            api.read_mut(os.path.join(d, "missing.mut"))
+        # site meta from the row filter == the oracle's restatement, row by row
+        for i in range(0, sites.n, 7):
+            mt = {0: chr(sites.anc[i]) + "/" + chr(sites.der[i]), 1: chr(sites.anc[i]) + "T/" + chr(sites.der[i]), 2: "NA"}[int(sites.odd[i])]
+            a = api.lib().colate_site_meta(int(sites.flipped[i]), int(sites.n_branch[i]), float(sites.age_begin[i]), float(sites.age_end[i]), mt.encode())
+            b = po.lib().oracle_site_meta(int(sites.flipped[i]), int(sites.n_branch[i]), float(sites.age_begin[i]), float(sites.age_end[i]), mt.encode())
+            assert a == b == metas[i]
+
+
+def test_mask_bits_from_fasta(built):
+    sites = synth.make_sites(3, [400, 300], [3e5, 2e5])
+    masks = [synth.make_mask(1, 300000, 0.4, 50, 500), synth.make_mask(2, 100000, 0.3, 50, 500, lower=True)]   # 2nd: short + lower case
+    want = api.mask_bits_from_seq([m.upper() for m in masks], sites.site_off, sites.pos)
+    bits = np.zeros((sites.n + 31) // 32, np.uint32)
+    with tempfile.TemporaryDirectory() as d:
+        for c, m in enumerate(masks):
+            p = os.path.join(d, f"m_chr{c + 1}.fa")
+            synth.write_mask(p, m, width=61)
+            lo, hi = int(sites.site_off[c]), int(sites.site_off[c + 1])
+            api.mask_bits_from_fasta(p, sites.pos[lo:hi], lo, bits)
+    assert same(bits, want)
+    beyond = sites.pos[int(sites.site_off[1]):] >= 100000
+    idx = np.arange(int(sites.site_off[1]), sites.n)[beyond]
+    assert ((bits[idx >> 5] >> (idx & 31)) & 1).all()                  # rows beyond the mask end pass (coal.cpp:2169)
+
+
+def test_cli_surface(built):
+    cli = os.path.join(ROOT, "colate_b200", "bin", "Colate")
+    assert os.path.exists(cli)
+    r = subprocess.run([cli, "--mode", "mut", "--num_bootstrapz", "3"], capture_output=True, text=True)
+    assert r.returncode != 0 and "does not exist" in r.stderr            # cxxopts rejects unknown options
+    r = subprocess.run([cli, "--mode", "mut"], capture_output=True, text=True)
+    assert r.returncode == 0 and "Not enough arguments supplied." in r.stdout
+    r = subprocess.run([cli, "--mode", "nonsense"], capture_output=True, text=True)
+    assert "Invalid or missing mode." in r.stdout
+    import torch
+    if not torch.cuda.is_available():
+        with tempfile.TemporaryDirectory() as d:
+            r = subprocess.run([cli, "--mode", "mut", "--mut", d + "/x", "--target_tmp", "a", "--reference_tmp", "b", "--bins", "3,7,0.2",
+                                "--num_bootstrap", "2", "-o", d + "/o"], capture_output=True, text=True)
+            assert r.returncode != 0 and "no CPU fallback" in r.stderr
