@@ -27,6 +27,13 @@ int ensure_tables(colate_handle* h)
   colate_age_bins(ab);
   CK(h->thr10.ensure(sizeof thr));
   CK(h->d_agebin.ensure(sizeof ab));
+  static double thrA[NBINS + 2];
+  static uint16_t lut[LUT_N];
+  if (!age_thresholds(thrA, lut)) return fail(COLATE_ERR_ARG, "host libm log() is not monotone around an age-bin threshold");
+  CK(h->thrA.ensure(sizeof thrA));
+  CK(h->lut.ensure(sizeof lut + 16));
+  CK(cudaMemcpyAsync(h->thrA.p, thrA, sizeof thrA, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->lut.p, lut, sizeof lut, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->thr10.p, thr, sizeof thr, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_agebin.p, ab, sizeof ab, cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -83,6 +90,7 @@ int colate_create(int device, colate_handle** out)
   if (prop.major < 10) return fail(COLATE_ERR_CUDA, "device is not sm_100 (kernels are built for sm_100a only)");
   colate_handle* h = new colate_handle();
   h->device = device;
+  h->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
   *out = h;
@@ -95,8 +103,8 @@ void colate_destroy(colate_handle* h)
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   DevBuf* bufs[] = {&h->site_off, &h->pos, &h->ab, &h->ae, &h->meta, &h->candR, &h->candT, &h->use, &h->word_rank, &h->scan_tmp,
-                    &h->chr_used, &h->chr_blocks, &h->chr_block_base, &h->misc, &h->u_ab, &h->u_ae, &h->u_fd, &h->u_fa, &h->u_dafr,
-                    &h->u_nr, &h->u_blk, &h->blk_rank_start, &h->tile_start, &h->partial_f, &h->partial_n, &h->out_f, &h->out_n,
+                    &h->chr_used, &h->chr_blocks, &h->chr_block_base, &h->misc, &h->u_hdr, &h->u_eb2, &h->u_ews, &h->u_ewn, &h->u_cnt,
+                    &h->u_blk, &h->blk_rank_start, &h->out_f, &h->out_n, &h->thrA, &h->lut, &h->d_scratch, &h->d_prof, &h->libm_tab,
                     &h->windows, &h->rng_stream, &h->poly, &h->thr10, &h->d_counts, &h->d_blockstats, &h->d_weights, &h->d_epochs,
                     &h->d_rates, &h->d_iters, &h->d_ll, &h->d_agebin, &h->d_tmp};
   for (DevBuf* b : bufs) b->release();

@@ -70,9 +70,10 @@ struct colate_handle {
   int tgt_slot = -1, ref_slot = -1;
   colate::DevBuf candR, candT, use, word_rank, scan_tmp;
   colate::DevBuf chr_used, chr_blocks, chr_block_base, misc;  // misc: small device scalars
-  colate::DevBuf u_ab, u_ae, u_fd, u_fa, u_dafr, u_nr, u_blk; // compacted used rows
-  colate::DevBuf blk_rank_start, tile_start, partial_f, partial_n, out_f, out_n;
-  colate::DevBuf windows, rng_stream, poly, thr10;
+  colate::DevBuf u_hdr, u_eb2, u_ews, u_ewn, u_blk, u_cnt;   // compacted used rows, per-row sample counts
+  colate::DevBuf blk_rank_start, out_f, out_n;
+  colate::DevBuf windows, rng_stream, poly, thr10, thrA, lut;
+  int sm_count = 148;
   std::vector<int64_t> h_chr_used;
   std::vector<int32_t> h_chr_blocks;
   int64_t n_used = 0;

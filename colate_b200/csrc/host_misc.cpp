@@ -51,6 +51,38 @@ bool bin_thresholds(double* thr10)
   return monotone;
 }
 
+bool age_thresholds(double* thrA, uint16_t* lut)
+{
+  bool monotone = true;
+  thrA[0] = 0.0;
+  for (int k = 1; k <= NBINS; k++) {
+    uint64_t lo = to_bits(1e-4), hi = to_bits(1e11);
+    while (hi - lo > 1) {
+      uint64_t mid = lo + (hi - lo) / 2;
+      if (bin_of_x10_host(10 * from_bits(mid)) >= k) hi = mid; else lo = mid;
+    }
+    thrA[k] = from_bits(hi);
+    for (int d = 1; d <= 16; d++) {
+      if (bin_of_x10_host(10 * from_bits(hi - d)) >= k) monotone = false;
+      if (bin_of_x10_host(10 * from_bits(hi + d)) < k) monotone = false;
+    }
+  }
+  thrA[NBINS + 1] = HUGE_VAL;
+  for (int c = 0; c < LUT_N; c++) {
+    const double edge = from_bits((uint64_t)(uint32_t)((c + LUT_BASE) << 14) << 32);
+    int k = 0;
+    while (k < NBINS && edge >= thrA[k + 1]) k++;
+    // at most one threshold inside a cell (cells are 2^-6 wide in log2, bins e^0.1); bit 7 says
+    // whether there is one (then the device compares against thrA[k+1]), the first and last
+    // cells are clamp targets and always compare
+    const double next = from_bits((uint64_t)(uint32_t)((c + 1 + LUT_BASE) << 14) << 32);
+    if (k + 2 <= NBINS && next > thrA[k + 2]) monotone = false;
+    const bool inside = (k < NBINS && next > thrA[k + 1]) || c == 0 || c == LUT_N - 1;
+    lut[c] = (uint16_t)(k | (inside ? 0x8000 : 0));
+  }
+  return monotone;
+}
+
 // ---- gz/plain file slurp (igzstream semantics: gzopen reads plain files transparently) ----
 static bool slurp(const std::string& path, std::vector<char>& buf)
 {

@@ -11,6 +11,9 @@ namespace colate {
 constexpr int NBINS = COLATE_NUM_AGE_BINS;
 constexpr int MAX_BLOCKS = COLATE_MAX_BLOCKS;
 constexpr int NTHR = NBINS + 1;  // thr10[1..185]; index 0 unused
+// age -> bin lookup: cell = (high word of the double >> 14) - LUT_BASE, cells from 2^-4 to 2^24
+constexpr int LUT_BASE = 0x3FB00000 >> 14;
+constexpr int LUT_N = (0x41700000 >> 14) - LUT_BASE;
 
 // error plumbing (thread-local message behind colate_last_error())
 void set_error(const std::string& msg);
@@ -30,6 +33,9 @@ void jump_window_host(const uint32_t* w, int q, uint32_t* out);
 // (coal.cpp:2253, 2265, 2284), found by bisection against this host's libm.
 // Returns false if log() is not monotone in a +-16 ulp neighbourhood of a threshold.
 bool bin_thresholds(double* thr10 /*[NTHR]*/);
+// thrA[k], k = 1..185: smallest age a with bin(a) >= k where bin(a) = max(0,(int)round(log(10*a)*10)+1);
+// thrA[186] = +inf; lut[cell] = bin at the lower edge of the cell
+bool age_thresholds(double* thrA /*[NBINS+2]*/, uint16_t* lut /*[LUT_N]*/);
 int bin_of_x10_host(double x10);
 
 }  // namespace colate

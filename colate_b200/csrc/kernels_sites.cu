@@ -9,11 +9,10 @@
 //               per-warp shared-memory histograms (no atomics), one partial per tile
 //   k_reduce    fixed-order sum of the tile partials of each genomic block
 #include "device.cuh"
+#include "exact_sum.cuh"
 
 namespace colate {
 
-constexpr int TILE_SITES = 1024;  // used rows per sampling tile
-constexpr int SAMPLE_WARPS = 8;
 constexpr int SCAN_ITEMS = 8;     // bitmap words per thread in the rank scan
 constexpr int SCAN_THREADS = 256;
 
@@ -201,7 +200,10 @@ __global__ void k_chr(int n_chr, const int64_t* __restrict__ site_off, const int
   misc[1] = base;
 }
 
-// used rows -> dense records in rank order
+// used rows -> dense records in rank order:
+//   hdr[r]  = {age_end - age_begin, age_begin, weight into shared, weight into notshared} (fp64 x4)
+//   e_b2/e_ws/e_wn[r] = bin and weights of the row's single "emp" contribution (255 = none)
+//   u_blk[r] = genomic block (index local to this handle)
 __global__ void k_compact(int64_t n_site, int n_chr, const int64_t* __restrict__ site_off, const int32_t* __restrict__ pos,
                           const float* __restrict__ ab, const float* __restrict__ ae,
                           const uint32_t* __restrict__ use, const uint32_t* __restrict__ word_rank,
@@ -209,9 +211,8 @@ __global__ void k_compact(int64_t n_site, int n_chr, const int64_t* __restrict__
                           const int32_t* __restrict__ t_aaf, const int32_t* __restrict__ t_daf,
                           const int32_t* __restrict__ r_aaf, const int32_t* __restrict__ r_daf,
                           const double* __restrict__ thr10,
-                          float* __restrict__ u_ab, float* __restrict__ u_ae, float* __restrict__ u_fd, float* __restrict__ u_fa,
-                          int32_t* __restrict__ u_dafr, int32_t* __restrict__ u_nr, int32_t* __restrict__ u_blk,
-                          int64_t* __restrict__ misc)
+                          double4* __restrict__ hdr, uint8_t* __restrict__ e_b2, double* __restrict__ e_ws,
+                          double* __restrict__ e_wn, int32_t* __restrict__ u_blk, int64_t* __restrict__ misc)
 {
   int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= n_site) return;
@@ -219,32 +220,41 @@ __global__ void k_compact(int64_t n_site, int n_chr, const int64_t* __restrict__
   int64_t r = rank_of(use, word_rank, m);
   int c = chr_of(site_off, n_chr, m);
   // pseudo-genotype, coal.cpp:2236-2242: float /= double, then round half away
-  int32_t dt = t_daf[m], at = t_aaf[m];
-  double half_n = (double)(dt + at) / 2.0;
+  const int32_t dt = t_daf[m], at = t_aaf[m];
+  const double half_n = (double)(dt + at) / 2.0;
   float fd = __double2float_rn(__ddiv_rn((double)(float)dt, half_n));
   float fa = __double2float_rn(__ddiv_rn((double)(float)at, half_n));
   fd = roundf(fd);
   fa = roundf(fa);
   float b = ab[m];
   if (b < 0.0f) b = 0.0f;  // coal.cpp:2225 with ref_age == 0 (coal.cpp:2075)
-  float e = ae[m];
-  u_ab[r] = b;
-  u_ae[r] = e;
-  u_fd[r] = fd;
-  u_fa[r] = fa;
-  u_dafr[r] = r_daf[m];
-  u_nr[r] = r_daf[m] + r_aaf[m];
+  const float e = ae[m];
+  const int32_t dafr = r_daf[m], nr = r_daf[m] + r_aaf[m];
+  const double abd = (double)b;
+  // float * int -> float, then / double (coal.cpp:2255-2256, 2269, 2291-2292)
+  const double num_s = (double)__fmul_rn(fd, __int2float_rn(dafr));
+  const double num_n = (double)__fmul_rn(fa, __int2float_rn(dafr));
+  const double den = __dmul_rn((double)nr, 100.0);
+  hdr[r] = make_double4(__dsub_rn((double)e, abd), abd, __ddiv_rn(num_s, den), __ddiv_rn(num_n, den));
+  uint8_t b2 = 255;
+  double ws = 0.0, wn = 0.0;
+  if (abd <= 0.0) {  // coal.cpp:2247-2256 with age == 0
+    const double x10 = (double)__fmul_rn(10.0f, e);
+    int lo = 0, hi = NBINS;  // number of thresholds <= x10
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (x10 >= thr10[mid]) lo = mid; else hi = mid - 1; }
+    if (lo < NBINS) { b2 = (uint8_t)lo; ws = __ddiv_rn(num_s, (double)nr); wn = __ddiv_rn(num_n, (double)nr); }
+  }
+  e_b2[r] = b2; e_ws[r] = ws; e_wn[r] = wn;
   u_blk[r] = chr_block_base[c] + (pos[m] - 1) / COLATE_BLOCK_BASES;
   // the reference writes out of bounds / rejection-samples once a bin index reaches 185
   if (__dmul_rn(10.0, (double)e) >= thr10[NBINS]) misc[3] = 1;
 }
 
-// rank range of every genomic block and the tile table
-__global__ void k_tiles(const int32_t* __restrict__ u_blk, int64_t* __restrict__ misc,
-                        int64_t* __restrict__ blk_rank_start, int32_t* __restrict__ tile_start)
+// rank range of every genomic block
+__global__ void k_block_ranges(const int32_t* __restrict__ u_blk, const int64_t* __restrict__ misc, int64_t* __restrict__ blk_rank_start)
 {
-  int64_t n_used = misc[0];
-  int n_blocks = (int)misc[1];
+  const int64_t n_used = misc[0];
+  const int n_blocks = (int)misc[1];
   for (int b = threadIdx.x; b <= n_blocks; b += blockDim.x) {
     int64_t lo = 0, hi = n_used;  // first rank with u_blk >= b
     while (lo < hi) {
@@ -253,16 +263,37 @@ __global__ void k_tiles(const int32_t* __restrict__ u_blk, int64_t* __restrict__
     }
     blk_rank_start[b] = lo;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
-    for (int b = 0; b < n_blocks; b++) {
-      tile_start[b] = t;
-      t += (int)((blk_rank_start[b + 1] - blk_rank_start[b] + TILE_SITES - 1) / TILE_SITES);
-    }
-    tile_start[n_blocks] = t;
-    misc[2] = t;
-  }
+}
+
+// ---- mbarrier / bulk-copy (TMA) helpers ------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk async copy (TMA engine, SASS UBLKCP), completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -276,140 +307,262 @@ __device__ __forceinline__ double u01(uint32_t x1, uint32_t x2)
   return u >= 1.0 ? 0x1.fffffffffffffp-1 : u;
 }
 
-// max(0,(int)round(log(x10)*10)+1) (coal.cpp:2253/2265/2284) without evaluating log in fp64:
-// a float estimate picks the bin, the exact host-computed thresholds settle it.
-__device__ __forceinline__ int bin_of_x10(double x10, const double* thr)
+// max(0,(int)round(log(10*a)*10)+1) (coal.cpp:2265/2284) without evaluating log: the top 17 bits
+// of a select a cell of width 2^-6 in log2 (narrower than an age bin, e^0.1), a table gives the
+// bin at the cell's lower edge and one exact threshold (host-computed against libm) settles it.
+__device__ __forceinline__ int bin_of_age(double a, const uint16_t* lut, const double* thrA)
 {
-  float lf = __log2f((float)x10) * 6.931471805599453f;
-  int k = __float2int_rn(lf);
-  k = max(0, min(k + 1, NBINS));
-  while (k < NBINS && x10 >= thr[k + 1]) k++;
-  while (k > 0 && x10 < thr[k]) k--;
+  int cell = (__double2hiint(a) >> 14) - LUT_BASE;
+  cell = max(0, min(cell, LUT_N - 1));
+  int k = lut[cell];           // bit 15: an age-bin threshold lies inside this cell (1 cell in 9)
+  if (k & 0x8000) { k &= 0xff; k += (a >= thrA[k + 1]) ? 1 : 0; }
   return k;
 }
 
-struct WarpHist {
-  double hS[NBINS], hN[NBINS], eS[NBINS], eN[NBINS];
-  uint32_t cS[NBINS], cN[NBINS], cE[NBINS];
-  uint32_t pad;
+constexpr int SW = 8;                 // consumer warps = used rows per pipeline stage
+constexpr int SAMPLE_STAGES = 4;
+constexpr int ROW_BYTES = 192;        // per-row sample counts, one byte per age bin (185 used)
+struct __align__(16) SampleStage {
+  uint4 words[SW][50];                // 200 engine words per used row
+  double4 hdr[SW];
 };
 
-__global__ void __launch_bounds__(SAMPLE_WARPS * 32)
-k_sample(const int64_t* misc_in, const int64_t* __restrict__ blk_rank_start,
-         const int32_t* __restrict__ tile_start, const double* __restrict__ thr10_g,
-         const float* __restrict__ u_ab, const float* __restrict__ u_ae, const float* __restrict__ u_fd,
-         const float* __restrict__ u_fa, const int32_t* __restrict__ u_dafr, const int32_t* __restrict__ u_nr,
-         const uint32_t* __restrict__ stream, double* __restrict__ partial_f, uint32_t* __restrict__ partial_n,
-         int64_t* misc)
+// THE per-mutation kernel.  Streams the reference's generator output (800 B per used row) and
+// the row headers from HBM through a TMA bulk-copy ring in shared memory; each consumer warp
+// takes one row per stage: 100 uniform ages -> exact bin index -> per-row counts per bin
+// (byte-packed shared-memory counters) -> one 192-byte count row back to HBM.  (MATCH.ANY was
+// measured at ~33 cycles per warp instruction per SM on B200 -- the ADU pipe -- and capped this
+// kernel at 30 % of HBM peak; a shared-memory atomic add costs ~5.)
+__global__ void __launch_bounds__((SW + 1) * 32)
+k_sample(int64_t n_used, const uint32_t* __restrict__ stream, const double4* __restrict__ hdr_g,
+         const double* __restrict__ thrA_g, const uint16_t* __restrict__ lut_g, uint8_t* __restrict__ cnt, int64_t* misc)
 {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  WarpHist* hist = (WarpHist*)smem_raw;
-  double* thr = (double*)(smem_raw + sizeof(WarpHist) * SAMPLE_WARPS);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SampleStage* st = (SampleStage*)smem_raw;
+  uint64_t* full = (uint64_t*)(smem_raw + sizeof(SampleStage) * SAMPLE_STAGES);
+  uint64_t* empty = full + SAMPLE_STAGES;
+  double* thrA = (double*)(empty + SAMPLE_STAGES);                 // [NBINS + 2]
+  uint16_t* lut = (uint16_t*)(thrA + NBINS + 2);                     // [LUT_N]
+  uint64_t* rows = (uint64_t*)(lut + ((LUT_N + 15) & ~15));         // [SW][4][ROW_BYTES / 8]: per-warp count rows
 
-  const int n_tiles = (int)misc_in[2];
-  const int n_blocks = (int)misc_in[1];
-  const int tile = blockIdx.x;
-  if (tile >= n_tiles) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  for (int i = threadIdx.x; i < NTHR; i += blockDim.x) thr[i] = thr10_g[i];
-  {
-    uint32_t* z = (uint32_t*)&hist[warp];
-    for (int i = lane; i < (int)(sizeof(WarpHist) / 4); i += 32) z[i] = 0;
+  const int64_t n_stage = (n_used + SW - 1) / SW;
+  for (int i = threadIdx.x; i < NBINS + 2; i += blockDim.x) thrA[i] = thrA_g[i];
+  for (int i = threadIdx.x; i < LUT_N; i += blockDim.x) lut[i] = lut_g[i];
+  for (int i = threadIdx.x; i < SW * 4 * ROW_BYTES / 8; i += blockDim.x) rows[i] = 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SAMPLE_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], SW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // genomic block of this tile: last b with tile_start[b] <= tile
-  int lo = 0, hi = n_blocks;
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (tile_start[mid] <= tile) lo = mid; else hi = mid;
-  }
-  const int blk = lo;
-  const int64_t r0 = blk_rank_start[blk] + (int64_t)(tile - tile_start[blk]) * TILE_SITES;
-  const int64_t r1 = min(r0 + TILE_SITES, blk_rank_start[blk + 1]);
   __syncthreads();
 
-  WarpHist& H = hist[warp];
-  bool overflow = false;
-  for (int64_t r = r0 + warp; r < r1; r += SAMPLE_WARPS) {
-    const float abf = u_ab[r], aef = u_ae[r], fd = u_fd[r], fa = u_fa[r];
-    const int32_t dafr = u_dafr[r], nr = u_nr[r];
-    const double abd = (double)abf;
-    const double len = __dsub_rn((double)aef, abd);
-    const bool emp = abd <= 0.0;  // coal.cpp:2247 with age == 0
-    const double num_s = (double)__fmul_rn(fd, __int2float_rn(dafr));
-    const double num_n = (double)__fmul_rn(fa, __int2float_rn(dafr));
-    const double den = __dmul_rn((double)nr, 100.0);
-    const double wS = __ddiv_rn(num_s, den), wN = __ddiv_rn(num_n, den);
-
-    if (emp && lane == 0) {  // coal.cpp:2250-2256
-      int b2 = bin_of_x10((double)__fmul_rn(10.0f, aef), thr);
-      if (b2 < NBINS) {
-        H.eS[b2] += __ddiv_rn(num_s, (double)nr);
-        H.eN[b2] += __ddiv_rn(num_n, (double)nr);
-        H.cE[b2] += 1;
+  if (warp == SW) {  // producer warp: one lane drives the TMA ring
+    if (lane == 0) {
+      int it = 0;
+      for (int64_t sid = blockIdx.x; sid < n_stage; sid += gridDim.x, it++) {
+        const int slot = it % SAMPLE_STAGES;
+        mbar_wait(&empty[slot], ((it / SAMPLE_STAGES) & 1) ^ 1);
+        const int64_t r0 = sid * SW;
+        const int nrow = (int)min((int64_t)SW, n_used - r0);
+        mbar_expect_tx(&full[slot], (uint32_t)nrow * (800 + 32));
+        bulk_g2s(&st[slot].words[0][0], stream + 200 * r0, (uint32_t)nrow * 800, &full[slot]);
+        bulk_g2s(&st[slot].hdr[0], hdr_g + r0, (uint32_t)nrow * 32, &full[slot]);
       }
     }
-    // 200 engine words of this row: 50 x 16 B; lane l takes chunks l and 32+l
-    const uint4* sp = (const uint4*)(stream + 200 * r);
-    uint4 q0 = __ldg(sp + lane);
-    uint4 q1 = make_uint4(0, 0, 0, 0);
-    const bool has1 = lane < 18;
-    if (has1) q1 = __ldg(sp + 32 + lane);
-    int bins[4];
-    {
-      double a;
-      a = __dadd_rn(__dmul_rn(u01(q0.x, q0.y), len), abd); bins[0] = bin_of_x10(__dmul_rn(10.0, a), thr);
-      a = __dadd_rn(__dmul_rn(u01(q0.z, q0.w), len), abd); bins[1] = bin_of_x10(__dmul_rn(10.0, a), thr);
-      a = __dadd_rn(__dmul_rn(u01(q1.x, q1.y), len), abd); bins[2] = has1 ? bin_of_x10(__dmul_rn(10.0, a), thr) : 0xffff;
-      a = __dadd_rn(__dmul_rn(u01(q1.z, q1.w), len), abd); bins[3] = has1 ? bin_of_x10(__dmul_rn(10.0, a), thr) : 0xffff;
-    }
+    return;
+  }
+
+  uint64_t* myrows = rows + (size_t)warp * 4 * (ROW_BYTES / 8);       // four copies: lanes spread over them
+  uint32_t* myrow = (uint32_t*)(myrows + (size_t)(lane & 3) * (ROW_BYTES / 8));
+  bool overflow = false;
+  int it = 0;
+  for (int64_t sid = blockIdx.x; sid < n_stage; sid += gridDim.x, it++) {
+    const int slot = it % SAMPLE_STAGES;
+    mbar_wait(&full[slot], (it / SAMPLE_STAGES) & 1);
+    const int64_t r = sid * SW + warp;
+    if (r < n_used) {
+      const double4 h = st[slot].hdr[warp];
+      const double len = h.x, abd = h.y;
+      const uint4 q0 = st[slot].words[warp][lane];
+      const bool has1 = lane < 18;
+      const uint4 q1 = has1 ? st[slot].words[warp][32 + lane] : make_uint4(0, 0, 0, 0);
+      int bins[4];
+      // sampled_age = U * (age_end - age_begin) + age_begin, product and sum rounded separately
+      bins[0] = bin_of_age(__dadd_rn(__dmul_rn(u01(q0.x, q0.y), len), abd), lut, thrA);
+      bins[1] = bin_of_age(__dadd_rn(__dmul_rn(u01(q0.z, q0.w), len), abd), lut, thrA);
+      bins[2] = has1 ? bin_of_age(__dadd_rn(__dmul_rn(u01(q1.x, q1.y), len), abd), lut, thrA) : 0xffff;
+      bins[3] = has1 ? bin_of_age(__dadd_rn(__dmul_rn(u01(q1.z, q1.w), len), abd), lut, thrA) : 0xffff;
+      // per-row counts: one byte per age bin, four bins per 32-bit word; shared-memory atomics
+      // resolve lanes that hit the same bin (at most 100 per byte: no carry into the next bin)
 #pragma unroll
-    for (int s = 0; s < 4; s++) {
-      const int b = bins[s];
-      const unsigned peers = __match_any_sync(0xffffffffu, b);
-      if (b < NBINS) {
-        if (lane == __ffs(peers) - 1) {
-          const int cnt = __popc(peers);
-          const double c = (double)cnt;
-          H.hN[b] += __dmul_rn(c, wN);
-          H.cN[b] += cnt;
-          if (!emp) { H.hS[b] += __dmul_rn(c, wS); H.cS[b] += cnt; }
-        }
-      } else if (b == NBINS) overflow = true;
+      for (int s = 0; s < 4; s++) {
+        const int b = bins[s];
+        if (b < NBINS) atomicAdd(&myrow[b >> 2], 1u << (8 * (b & 3)));
+        else if (b == NBINS) overflow = true;
+      }
       __syncwarp();
+      if (lane < ROW_BYTES / 8) {
+        uint64_t* rw = myrows;
+        // byte-wise sum of the four copies (at most 100 per byte: no carries)
+        const uint64_t v = rw[lane] + rw[ROW_BYTES / 8 + lane] + rw[2 * (ROW_BYTES / 8) + lane] + rw[3 * (ROW_BYTES / 8) + lane];
+        rw[lane] = 0; rw[ROW_BYTES / 8 + lane] = 0; rw[2 * (ROW_BYTES / 8) + lane] = 0; rw[3 * (ROW_BYTES / 8) + lane] = 0;
+        ((uint64_t*)(cnt + (size_t)r * ROW_BYTES))[lane] = v;
+      }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[slot]);
   }
   if (overflow) misc[3] = 1;
+}
+
+constexpr int RP_SITES = 32;   // rows per replay stage
+constexpr int RP_STAGES = 4;
+constexpr int RP_GROUP = 8;    // rows collapsed into one exact update
+constexpr int RP_THREADS = 224;  // 6 consumer warps (192 >= 185 bins) + 1 producer warp
+struct __align__(16) ReplayStage {
+  uint8_t cnt[RP_SITES][ROW_BYTES];
+  double4 hdr[RP_SITES];
+};
+
+// Exact replay: for every genomic block and both histograms, thread = age bin walks the block's
+// used rows IN ORDER and adds the row's weight once per sample that fell into the bin, with the
+// reference's rounding (exact_sum.cuh), so age_shared_count / age_notshared_count come out bit
+// for bit as the sequential loop of coal.cpp:2259-2295 leaves them.  blockIdx.y: 0 shared, 1 not shared.
+__global__ void __launch_bounds__(RP_THREADS)
+k_replay(const int64_t* __restrict__ blk_rank_start, const uint8_t* __restrict__ cnt, const double4* __restrict__ hdr_g,
+         double* __restrict__ out_f, int64_t* __restrict__ out_n, long long* prof)
+{
+  __shared__ ReplayStage st[RP_STAGES];
+  __shared__ __align__(8) uint64_t full[RP_STAGES], empty[RP_STAGES];
+  const int blk = blockIdx.x, which = blockIdx.y;
+  const int64_t r0 = blk_rank_start[blk], r1 = blk_rank_start[blk + 1];
+  const int n_stage = (int)((r1 - r0 + RP_SITES - 1) / RP_SITES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RP_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 6); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
-  // fixed-order sum over the warps of the tile
-  double* pf = partial_f + (size_t)tile * 4 * NBINS;
-  uint32_t* pn = partial_n + (size_t)tile * 3 * NBINS;
-  for (int i = threadIdx.x; i < NBINS; i += blockDim.x) {
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    uint32_t c0 = 0, c1 = 0, c2 = 0;
-    for (int w = 0; w < SAMPLE_WARPS; w++) {
-      s0 += hist[w].hS[i]; s1 += hist[w].hN[i]; s2 += hist[w].eS[i]; s3 += hist[w].eN[i];
-      c0 += hist[w].cS[i]; c1 += hist[w].cN[i]; c2 += hist[w].cE[i];
+  long long tw = 0, tstart = clock64();
+  if (warp == 6) {
+    if (lane == 0) {
+      for (int it = 0; it < n_stage; it++) {
+        const int slot = it % RP_STAGES;
+        long long a0 = clock64();
+        mbar_wait(&empty[slot], ((it / RP_STAGES) & 1) ^ 1);
+        tw += clock64() - a0;
+        const int64_t s0 = r0 + (int64_t)it * RP_SITES;
+        const int nrow = (int)min((int64_t)RP_SITES, r1 - s0);
+        mbar_expect_tx(&full[slot], (uint32_t)nrow * (ROW_BYTES + 32));
+        bulk_g2s(&st[slot].cnt[0][0], cnt + (size_t)s0 * ROW_BYTES, (uint32_t)nrow * ROW_BYTES, &full[slot]);
+        bulk_g2s(&st[slot].hdr[0], hdr_g + s0, (uint32_t)nrow * 32, &full[slot]);
+      }
+      if (prof) { prof[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + 6] = tw; }
     }
-    pf[i] = s0; pf[NBINS + i] = s1; pf[2 * NBINS + i] = s2; pf[3 * NBINS + i] = s3;
-    pn[i] = c0; pn[NBINS + i] = c1; pn[2 * NBINS + i] = c2;
+    return;
+  }
+  const int bin = threadIdx.x;  // 0..191
+  double acc = 0.0;
+  int64_t tally = 0;
+  int n_any = 0, n_fb = 0;
+  for (int it = 0; it < n_stage; it++) {
+    const int slot = it % RP_STAGES;
+    long long a0 = clock64();
+    mbar_wait(&full[slot], (it / RP_STAGES) & 1);
+    tw += clock64() - a0;
+    const int nrow = (int)min((int64_t)RP_SITES, r1 - (r0 + (int64_t)it * RP_SITES));
+    const uint8_t* cp = &st[slot].cnt[0][0] + bin;
+    const double* hp = (const double*)&st[slot].hdr[0];
+    // Groups of RP_GROUP rows.  While acc stays inside one binade [2^E, 2^(E+1)) every rounded
+    // addition of w moves it by d(w) = w rounded to a multiple of ulp(acc) -- a function of w and
+    // E only -- and all these moves are exact, so the group collapses to acc += sum(c * d(w)):
+    // no serial dependency per row.  A group that leaves the binade, meets a rounding tie or has
+    // acc outside the normal range is redone row by row with exact_sum.cuh.
+    for (int g0 = 0; g0 < nrow; g0 += RP_GROUP) {
+      int cs[RP_GROUP];
+      double ws[RP_GROUP];
+      int any = 0;
+#pragma unroll
+      for (int i = 0; i < RP_GROUP; i++) {
+        const int sidx = min(g0 + i, RP_SITES - 1);
+        const int c = (g0 + i < nrow) ? cp[sidx * ROW_BYTES] : 0;
+        const double w = hp[4 * sidx + 2 + which];
+        const long long yb = __double_as_longlong(hp[4 * sidx + 1]);
+        const int ct = ((which == 1) | (yb > 0)) ? c : 0;  // rows with age_begin <= 0 add nothing to shared
+        tally += ct;
+        cs[i] = (__double_as_longlong(w) << 1) != 0 ? ct : 0;  // x + 0.0 == x: c no-op additions
+        ws[i] = w;
+        any |= cs[i];
+      }
+      if (__any_sync(0xffffffffu, any != 0)) {
+        n_any++;
+        const int E = __double2hiint(acc) >> 20;                         // biased exponent (acc >= 0)
+        const double M = __hiloint2double((E << 20) | 0x80000, 0);       // 1.5 * 2^E: ulp(M) == ulp(acc)
+        const double hu = __hiloint2double((E - 53) << 20, 0);           // ulp(acc) / 2
+        const double wmax = __hiloint2double((E - 1) << 20, 0);          // w must stay below 2^(E-1)
+        double tot = 0.0;
+        int bad = (E <= 54) | (E >= 0x7fe);
+#pragma unroll
+        for (int i = 0; i < RP_GROUP; i++) {
+          const double d = __dsub_rn(__dadd_rn(ws[i], M), M);
+          const double err = __dsub_rn(ws[i], d);
+          bad |= (cs[i] != 0) & ((fabs(err) == hu) | !(ws[i] < wmax) | (ws[i] < 0.0));
+          tot = __fma_rn((double)cs[i], d, tot);
+        }
+        const double accn = __dadd_rn(acc, tot);
+        bad |= (__double2hiint(accn) >> 20) != E;
+        bad &= (any != 0);
+        if (__any_sync(0xffffffffu, bad)) {
+          n_fb++;
+          if (bad) {
+#pragma unroll 1
+            for (int i = 0; i < RP_GROUP; i++)
+              if (cs[i]) acc = exsum::add_repeated(acc, ws[i], cs[i]);
+          } else if (any) acc = accn;
+        } else if (any) acc = accn;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[slot]);
+  }
+  if (prof && lane == 0) {
+    long long* p = prof + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
+    p[warp] = tw;
+    if (warp == 0) { p[7] = clock64() - tstart; p[8] = n_stage; }
+    if (warp == 3) { p[9] = n_any; p[10] = n_fb; }
+    if (warp == 1) { p[11] = n_any; p[12] = n_fb; }
+  }
+  if (bin < NBINS) {
+    out_f[((size_t)blk * 4 + which) * NBINS + bin] = acc;
+    out_n[((size_t)blk * 3 + which) * NBINS + bin] = tally;
   }
 }
 
-__global__ void k_reduce(const int32_t* __restrict__ tile_start, const double* __restrict__ partial_f,
-                         const uint32_t* __restrict__ partial_n, double* __restrict__ out_f, int64_t* __restrict__ out_n)
+// age_shared_emp / age_notshared_emp row 0 (coal.cpp:2250-2256): one addition per row with
+// age_begin <= 0, in row order, thread = age bin.
+__global__ void __launch_bounds__(192)
+k_emp(const int64_t* __restrict__ blk_rank_start, const uint8_t* __restrict__ e_b2, const double* __restrict__ e_ws,
+      const double* __restrict__ e_wn, double* __restrict__ out_f, int64_t* __restrict__ out_n)
 {
-  const int blk = blockIdx.x;
-  const int t0 = tile_start[blk], t1 = tile_start[blk + 1];
-  for (int i = threadIdx.x; i < 4 * NBINS; i += blockDim.x) {
-    double s = 0;
-    for (int t = t0; t < t1; t++) s += partial_f[(size_t)t * 4 * NBINS + i];
-    out_f[(size_t)blk * 4 * NBINS + i] = s;
+  constexpr int CH = 512;
+  __shared__ uint8_t sb[CH];
+  __shared__ double sws[CH], swn[CH];
+  const int blk = blockIdx.x, bin = threadIdx.x;
+  const int64_t r0 = blk_rank_start[blk], r1 = blk_rank_start[blk + 1];
+  double as = 0.0, an = 0.0;
+  int64_t n = 0;
+  for (int64_t c0 = r0; c0 < r1; c0 += CH) {
+    const int m = (int)min((int64_t)CH, r1 - c0);
+    for (int i = threadIdx.x; i < m; i += blockDim.x) { sb[i] = e_b2[c0 + i]; sws[i] = e_ws[c0 + i]; swn[i] = e_wn[c0 + i]; }
+    __syncthreads();
+    for (int i = 0; i < m; i++)
+      if (sb[i] == bin) { as = __dadd_rn(as, sws[i]); an = __dadd_rn(an, swn[i]); n++; }
+    __syncthreads();
   }
-  for (int i = threadIdx.x; i < 3 * NBINS; i += blockDim.x) {
-    int64_t s = 0;
-    for (int t = t0; t < t1; t++) s += partial_n[(size_t)t * 3 * NBINS + i];
-    out_n[(size_t)blk * 3 * NBINS + i] = s;
+  if (bin < NBINS) {
+    out_f[((size_t)blk * 4 + 2) * NBINS + bin] = as;
+    out_f[((size_t)blk * 4 + 3) * NBINS + bin] = an;
+    out_n[((size_t)blk * 3 + 2) * NBINS + bin] = n;
   }
 }
 
@@ -474,7 +627,7 @@ int run_flags(colate_handle* h, int tslot, int rslot)
   return 0;
 }
 
-// compaction + tile table + sampling + per-block reduction; needs h->n_used / n_blocks_local
+// compaction + sampling + exact per-block replay; needs h->n_used / n_blocks_local
 int run_sample(colate_handle* h, const uint32_t* stream_local, int)
 {
   const int64_t n = h->n_site, nu = h->n_used;
@@ -483,37 +636,59 @@ int run_sample(colate_handle* h, const uint32_t* stream_local, int)
   GenomeDev& R = h->genomes[h->ref_slot];
   cudaStream_t s = h->stream;
   const size_t un = (size_t)std::max<int64_t>(nu, 1);
-  CK(h->u_ab.ensure(un * 4)); CK(h->u_ae.ensure(un * 4)); CK(h->u_fd.ensure(un * 4)); CK(h->u_fa.ensure(un * 4));
-  CK(h->u_dafr.ensure(un * 4)); CK(h->u_nr.ensure(un * 4)); CK(h->u_blk.ensure(un * 4));
-  CK(h->blk_rank_start.ensure((MAX_BLOCKS + 2) * 8)); CK(h->tile_start.ensure((MAX_BLOCKS + 2) * 4));
-  const int max_tiles = (int)(nu / TILE_SITES) + nb + 1;
-  CK(h->partial_f.ensure((size_t)max_tiles * 4 * NBINS * 8)); CK(h->partial_n.ensure((size_t)max_tiles * 3 * NBINS * 4));
+  CK(h->u_hdr.ensure(un * 32 + 64)); CK(h->u_eb2.ensure(un + 64)); CK(h->u_ews.ensure(un * 8 + 64)); CK(h->u_ewn.ensure(un * 8 + 64));
+  CK(h->u_blk.ensure(un * 4 + 64)); CK(h->u_cnt.ensure(un * ROW_BYTES + 64));
+  CK(h->blk_rank_start.ensure((MAX_BLOCKS + 2) * 8));
   CK(h->out_f.ensure((size_t)MAX_BLOCKS * 4 * NBINS * 8)); CK(h->out_n.ensure((size_t)MAX_BLOCKS * 3 * NBINS * 8));
   CK(cudaEventRecord(h->ev[2], s));
-  h->launches += (n > 0 ? 1 : 0) + 2 + (nb > 0 ? 1 : 0);
-  if (n > 0)
+  if (n > 0) {
     k_compact<<<grid_for(n, 256), 256, 0, s>>>(n, h->n_chr, h->site_off.as<int64_t>(), h->pos.as<int32_t>(), h->ab.as<float>(),
                                                h->ae.as<float>(), h->use.as<uint32_t>(), h->word_rank.as<uint32_t>(),
                                                h->chr_block_base.as<int32_t>(), T.j_aaf.as<int32_t>(), T.j_daf.as<int32_t>(),
                                                R.j_aaf.as<int32_t>(), R.j_daf.as<int32_t>(), h->thr10.as<double>(),
-                                               h->u_ab.as<float>(), h->u_ae.as<float>(), h->u_fd.as<float>(), h->u_fa.as<float>(),
-                                               h->u_dafr.as<int32_t>(), h->u_nr.as<int32_t>(), h->u_blk.as<int32_t>(), h->misc.as<int64_t>());
-  k_tiles<<<1, 512, 0, s>>>(h->u_blk.as<int32_t>(), h->misc.as<int64_t>(), h->blk_rank_start.as<int64_t>(), h->tile_start.as<int32_t>());
-  CK(cudaEventRecord(h->ev[3], s));
-  const size_t smem = sizeof(WarpHist) * SAMPLE_WARPS + NTHR * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+                                               h->u_hdr.as<double4>(), h->u_eb2.as<uint8_t>(), h->u_ews.as<double>(),
+                                               h->u_ewn.as<double>(), h->u_blk.as<int32_t>(), h->misc.as<int64_t>());
+    h->launches += 1;
   }
-  k_sample<<<max_tiles, SAMPLE_WARPS * 32, smem, s>>>(h->misc.as<int64_t>(), h->blk_rank_start.as<int64_t>(), h->tile_start.as<int32_t>(),
-                                                      h->thr10.as<double>(), h->u_ab.as<float>(), h->u_ae.as<float>(), h->u_fd.as<float>(),
-                                                      h->u_fa.as<float>(), h->u_dafr.as<int32_t>(), h->u_nr.as<int32_t>(), stream_local,
-                                                      h->partial_f.as<double>(), h->partial_n.as<uint32_t>(), h->misc.as<int64_t>());
+  k_block_ranges<<<1, 512, 0, s>>>(h->u_blk.as<int32_t>(), h->misc.as<int64_t>(), h->blk_rank_start.as<int64_t>());
+  h->launches += 1;
+  CK(cudaEventRecord(h->ev[3], s));
+  if (nu > 0) {
+    const size_t smem = sizeof(SampleStage) * SAMPLE_STAGES + 2 * SAMPLE_STAGES * 8 + (NBINS + 2) * 8 + 2 * ((LUT_N + 15) & ~15) +
+                        (size_t)SW * 4 * ROW_BYTES;
+    CK(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t n_stage = (nu + SW - 1) / SW;
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / (smem + 1024)));
+    if (const char* e = getenv("COLATE_SAMPLE_CTAS_PER_SM")) per_sm = std::max(1, atoi(e));
+    const int grid = (int)std::min<int64_t>(n_stage, (int64_t)h->sm_count * per_sm);
+    k_sample<<<grid, (SW + 1) * 32, smem, s>>>(nu, stream_local, h->u_hdr.as<double4>(), h->thrA.as<double>(), h->lut.as<uint16_t>(),
+                                                h->u_cnt.as<uint8_t>(), h->misc.as<int64_t>());
+    h->launches += 1;
+  }
   CK(cudaEventRecord(h->ev[4], s));
-  if (nb > 0)
-    k_reduce<<<nb, 256, 0, s>>>(h->tile_start.as<int32_t>(), h->partial_f.as<double>(), h->partial_n.as<uint32_t>(),
-                                h->out_f.as<double>(), h->out_n.as<int64_t>());
+  if (nb > 0) {
+    long long* prof = nullptr;
+    if (getenv("COLATE_REPLAY_PROF")) {
+      CK(h->d_prof.ensure((size_t)nb * 2 * 16 * 8));
+      CK(cudaMemsetAsync(h->d_prof.p, 0, (size_t)nb * 2 * 16 * 8, s));
+      prof = h->d_prof.as<long long>();
+    }
+    k_replay<<<dim3(nb, 2), RP_THREADS, 0, s>>>(h->blk_rank_start.as<int64_t>(), h->u_cnt.as<uint8_t>(), h->u_hdr.as<double4>(),
+                                                h->out_f.as<double>(), h->out_n.as<int64_t>(), prof);
+    if (prof) {
+      std::vector<long long> hp((size_t)nb * 2 * 16);
+      CK(cudaMemcpyAsync(hp.data(), prof, hp.size() * 8, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      for (int i : {0, 1, nb / 2, nb + nb / 2}) {
+        long long* p = hp.data() + (size_t)i * 16;
+        fprintf(stderr, "[k_replay prof cta %d] stages %lld total %lld cyc | full-wait per warp: %lld %lld %lld %lld %lld %lld | producer empty-wait %lld | warp3 groups %lld fallbacks %lld | warp1 groups %lld fallbacks %lld\n", i,
+                p[8], p[7], p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[9], p[10], p[11], p[12]);
+      }
+    }
+    k_emp<<<nb, 192, 0, s>>>(h->blk_rank_start.as<int64_t>(), h->u_eb2.as<uint8_t>(), h->u_ews.as<double>(), h->u_ewn.as<double>(),
+                             h->out_f.as<double>(), h->out_n.as<int64_t>());
+    h->launches += 2;
+  }
   CK(cudaEventRecord(h->ev[5], s));
   CK(cudaGetLastError());
   return 0;
