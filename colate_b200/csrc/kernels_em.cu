@@ -14,7 +14,7 @@ namespace cg = cooperative_groups;
 
 namespace colate {
 
-constexpr int EM_THREADS = 512;
+constexpr int EM_THREADS = 416;  // 12 task warps + 1 warp for the prefix chain
 constexpr int EM_TASKS = 384;  // 2 x 185 (bin, shared / not shared) padded; task = 2*bin + type
 
 // ---- stage ii ------------------------------------------------------------------------------
@@ -75,8 +75,8 @@ __device__ __forceinline__ double lse(double a, double b, const glm::Tables& T)
 {
   if (bad(a)) return bad(b) ? neg_inf() : b;
   if (bad(b)) return a;
-  if (a > b) return a + glm::log1p(glm::exp(b - a, T));
-  return b + glm::log1p(glm::exp(a - b, T));
+  const double hi = (a > b) ? a : b, lo = (a > b) ? b : a;   // same value as the two-branch form
+  return hi + glm::log1p(glm::exp(lo - hi, T));
 }
 // coal_EM::logminusexp, coal_EM.cpp:33-58
 __device__ __forceinline__ double lme(double a, double b, const glm::Tables& T)
@@ -242,14 +242,18 @@ __device__ double task_notshared(const EmCtx& c, double t, int k, bool active, E
 // ---- stage iii: EM to convergence ----------------------------------------------------------
 // One thread-block cluster per bootstrap replicate (cluster size 1 when there are enough
 // replicates to fill the GPU, up to 8 SMs per replicate when there are few).  Per iteration:
-//   A  cumulative hazard (serial), per-epoch A_ep / B_ep
-//   B  the sequential logsumexp folds: one prefix chain for all "shared" tasks, one suffix chain
-//      per bin for the "not shared" tasks (these folds bound the iteration latency)
-//   C  per (bin, type) task: posterior mass / exposure per epoch -> scratch M[which][e][task]
+//   A  cumulative hazard (every thread sums the per-epoch products in order), A_ep / B_ep
+//   B  the sequential logsumexp folds: one prefix chain for all "shared" tasks (its own warp,
+//      published entry by entry), one suffix chain per bin for the "not shared" tasks -- these
+//      folds bound the iteration latency; shared tasks start as soon as their prefix is ready
+//   C  per (bin, type) task: posterior mass / exposure per epoch -> scratch M[task][column]
 //      (tasks are dealt round-robin to the CTAs of the cluster)
 //   D  cluster barrier; every CTA then sums M over the tasks IN THE REFERENCE'S ORDER
-//      (coal.cpp:3704-3733) and applies the M-step redundantly, so no broadcast is needed.
-__global__ void __launch_bounds__(EM_THREADS)
+//      (coal.cpp:3704-3733; chunks staged through shared memory) and applies the M-step
+//      redundantly, so no broadcast is needed.
+constexpr int EM_STAGE_DOUBLES = 3328;  // per staging buffer of the column sums (26 KB)
+
+__global__ void __launch_bounds__(EM_THREADS, 2)
 k_em(int E, const double* __restrict__ epochs, const double* __restrict__ rates_init,
      const double* __restrict__ age_bin_g, const double* __restrict__ counts, int max_iter,
      const uint64_t* __restrict__ exp_tab_g, const uint64_t* __restrict__ log_tab_g, double* scratch,
@@ -268,30 +272,31 @@ k_em(int E, const double* __restrict__ epochs, const double* __restrict__ rates_
   double* PL = B + E;               // [E+1]
   double* tn = PL + E + 1;          // [E]
   double* td = tn + E;              // [E]
-  double* q = td + E;               // [E]
-  double* numt = q + E;             // [NBINS] shared tasks: special-epoch log num
-  double* dent = numt + NBINS;      // [NBINS]
-  uint64_t* etab = (uint64_t*)(dent + NBINS);  // [256]
-  uint64_t* ltab = etab + 256;                 // [256]
+  double* cand = td + E;            // [E]
+  double* prod = cand + E;          // [E]
+  double* stage = prod + E;         // [2][EM_STAGE_DOUBLES]
+  uint64_t* etab = (uint64_t*)(stage + 2 * EM_STAGE_DOUBLES);  // [256]
+  uint64_t* ltab = etab + 256;                                  // [256]
   __shared__ int stop_flag;
-  __shared__ double ll_s, prev_s;
-  __shared__ unsigned char act[EM_TASKS];
+  __shared__ volatile int pl_ready;
+  __shared__ double ll_s, prev_s, ll_new;
 
   const int tid = threadIdx.x;
   for (int e = tid; e < E; e += blockDim.x) { ep[e] = epochs[e]; rate[e] = rates_init[e]; }
   for (int i = tid; i < 256; i += blockDim.x) { etab[i] = exp_tab_g[i]; ltab[i] = log_tab_g[i]; }
-  if (tid == 0) { stop_flag = 0; ll_s = neg_inf(); }
-  // task of this thread: threads 0..383 <-> task = tid; bin = task >> 1, type = task & 1 (0 shared)
-  const int task = tid, bin = tid >> 1;
-  const bool is_task = tid < 2 * NBINS;
-  const bool is_shared = (tid & 1) == 0;
+  if (tid == 0) { stop_flag = 0; ll_s = neg_inf(); pl_ready = 0; PL[0] = 1.0; }
+  // threads 0..191: shared task of bin tid; 192..383: not-shared task of bin tid-192;
+  // warp 12: the prefix chain.  Row of a task in M (= the reference's summation order): 2*bin + type.
+  const bool is_shared = tid < 192;
+  const int bin = is_shared ? tid : tid - 192;
+  const bool is_task = tid < 384 && bin < NBINS;
+  const int task = 2 * bin + (is_shared ? 0 : 1);
   double t = 0.0, cnt = 0.0;
   if (is_task) {
     t = age_bin_g[bin];
     cnt = counts[(size_t)rep * 2 * NBINS + (is_shared ? 0 : NBINS) + bin];
   }
   const bool active = is_task && cnt > 0;  // coal.cpp:3706, 3719
-  if (tid < EM_TASKS) act[tid] = active ? 1 : 0;
   __syncthreads();
   const int k = is_task ? tint_k(E, ep, t) : 1;
   const int et = k - 1;
@@ -299,10 +304,11 @@ k_em(int E, const double* __restrict__ epochs, const double* __restrict__ rates_
   EmCtx c{E, ep, rate, A, B, Lam, glm::Tables{etab, ltab}};
   // scratch of this replicate: [buf][task][RS], row = {count*num[e] (E), count*denom[e] (E), count*logl}
   const int RS = 2 * E + 2;
+  const int TJ = max(1, EM_STAGE_DOUBLES / RS);  // tasks per staged chunk
   double* Mrep = scratch + (size_t)rep * 2 * EM_TASKS * RS;
   long long* prof = prof_g ? prof_g + (size_t)blockIdx.x * 8 : nullptr;
   long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (is_task && !active)  // rows of inactive tasks stay 0 so that the sums below need no test
+  if (is_task && !active)  // rows of inactive tasks stay 0: x + 0.0 == x, so the sums need no test
     for (int b2 = 0; b2 < 2; b2++)
       for (int e = 0; e < RS; e++) Mrep[((size_t)b2 * EM_TASKS + task) * RS + e] = 0.0;
 
@@ -311,70 +317,133 @@ k_em(int E, const double* __restrict__ epochs, const double* __restrict__ rates_
     double* M = Mrep + (size_t)(iter & 1) * EM_TASKS * RS;
     double* Mt = M + (size_t)task * RS;
     long long t0 = prof ? clock64() : 0, t1;
-    if (tid == 0) em_cumhaz(E, ep, rate, Lam);
+    // cumulative hazard, coal_EM.cpp:100-103: products in parallel, then every thread that needs
+    // Lam[e] adds them up in index order (same additions as the serial loop)
+    for (int e = tid + 1; e < E; e += blockDim.x) prod[e] = rate[e - 1] * (ep[e] - ep[e - 1]);
+    __syncthreads();
+    for (int e = tid; e < E; e += blockDim.x) {
+      double l = 0.0;
+      for (int i = 1; i <= e; i++) l = l + prod[i];
+      Lam[e] = l;
+    }
     __syncthreads();
     for (int e = tid; e < E; e += blockDim.x) em_AB(E, ep, rate, Lam, e, A, B, c.T);
     __syncthreads();
     if (prof) { t1 = clock64(); tp[0] += t1 - t0; t0 = t1; }
-    // folds and special epochs
+    // folds, special epochs and per-task E-step
     double my_logl = 0.0;
-    if (tid == EM_THREADS - 1) shared_prefix_chain(c, PL);
     auto emit = [&](int e, double ne, double de) {
       Mt[e] = cnt * ne;
       Mt[E + e] = cnt * de;
     };
-    if (mine && !is_shared) my_logl = cnt * task_notshared(c, t, k, true, emit);
-    if (mine && is_shared) shared_special(c, t, et, numt[bin], dent[bin]);
-    __syncthreads();
-    if (prof) { t1 = clock64(); tp[1] += t1 - t0; t0 = t1; }
-    if (mine && is_shared) my_logl = cnt * task_shared(c, et, true, PL[et], numt[bin], dent[bin], emit);
+    if (tid == 384) {  // prefix chain of the shared tasks (coal_EM.cpp:254-258), published entry by entry
+      double nc = 1.0;
+      PL[0] = nc;
+      for (int e = 0; e < E; e++) {
+        const double v = A[e];
+        if (nc == 1.0) nc = v; else nc = lse(nc, v, c.T);
+        PL[e + 1] = nc;
+        __threadfence_block();
+        pl_ready = e + 1;
+      }
+    } else if (mine && !is_shared) {
+      my_logl = cnt * task_notshared(c, t, k, true, emit);
+    } else if (mine && is_shared) {
+      double num_t, den_t;
+      shared_special(c, t, et, num_t, den_t);
+      while (pl_ready < et) { }
+      const double pl = ((volatile double*)PL)[et];
+      my_logl = cnt * task_shared(c, et, true, pl, num_t, den_t, emit);
+    }
     if (mine) Mt[2 * E] = my_logl;
     __threadfence();
-    if (prof) { t1 = clock64(); tp[2] += t1 - t0; t0 = t1; }
+    if (prof) { t1 = clock64(); tp[1] += t1 - t0; t0 = t1; }
     cluster.sync();
+    if (tid == 0) pl_ready = 0;
     if (prof) { t1 = clock64(); tp[3] += t1 - t0; t0 = t1; }
-    // sums over the tasks in the reference's order (bin ascending, shared before not shared,
-    // coal.cpp:3704-3733): thread = column of M, ten loads in flight per step
-    if (tid <= 2 * E) {
-      const double* col = M + tid;
-      double acc = 0.0;
-      constexpr int U = 10;  // 2 * NBINS = 370 = 37 * 10
-      double v[U];
-#pragma unroll
-      for (int u = 0; u < U; u++) v[u] = __ldcg(col + (size_t)u * RS);
-      for (int j = 0; j < 2 * NBINS; j += U) {
-        double w[U];
-        if (j + U < 2 * NBINS) {
-#pragma unroll
-          for (int u = 0; u < U; u++) w[u] = __ldcg(col + (size_t)(j + U + u) * RS);
+    // sums over the tasks in the reference's order (bin ascending, shared before not shared)
+    const int n_task = 2 * NBINS;
+    if (csize > 1) {
+      // cluster: CTA r sums columns [r*CW, (r+1)*CW) of M over all tasks (one gather into shared
+      // memory, thread = column) and stores the results into every CTA's tn / td / ll through
+      // distributed shared memory
+      const int ncol = 2 * E + 1;
+      const int CW = (ncol + csize - 1) / csize;
+      const int cbeg = crank * CW, cend = min(ncol, cbeg + CW);
+      const int CB = (2 * EM_STAGE_DOUBLES) / n_task;   // columns that fit the staging buffer at once
+      for (int c0 = cbeg; c0 < cend; c0 += CB) {
+        const int cw = min(CB, cend - c0);
+        for (int i = tid; i < n_task * cw; i += blockDim.x) {
+          const int j = i / cw, cc = i - j * cw;
+          stage[i] = __ldcg(M + (size_t)j * RS + c0 + cc);
         }
+        __syncthreads();
+        if (tid < cw) {
+          double acc = 0.0;
+#pragma unroll 10
+          for (int j = 0; j < n_task; j++) acc += stage[j * cw + tid];
+          const int col = c0 + tid;
+          for (int r = 0; r < csize; r++) {
+            if (col < E) cluster.map_shared_rank(tn, r)[col] = acc;
+            else if (col < 2 * E) cluster.map_shared_rank(td, r)[col - E] = acc;
+            else cluster.map_shared_rank(&ll_new, r)[0] = acc;
+          }
+        }
+        __syncthreads();
+      }
+      cluster.sync();
+      if (tid == 0) { prev_s = ll_s; ll_s = ll_new; }
+    } else {
+      // single CTA: chunks of TJ rows of M are staged through shared memory (double-buffered), thread = column
+      double acc = 0.0;
+      int buf = 0;
+      for (int i = tid; i < min(TJ, n_task) * RS; i += blockDim.x) stage[i] = __ldcg(M + i);
+      __syncthreads();
+      for (int j0 = 0; j0 < n_task; j0 += TJ) {
+        const int nj = min(TJ, n_task - j0);
+        const int j1 = j0 + TJ, nn = (j1 < n_task) ? min(TJ, n_task - j1) : 0;
+        double pre[9];
+        const double* src = M + (size_t)j1 * RS;
 #pragma unroll
-        for (int u = 0; u < U; u++) acc += v[u];
+        for (int u = 0; u < 9; u++) { const int i = tid + u * EM_THREADS; pre[u] = (i < nn * RS) ? __ldcg(src + i) : 0.0; }
+        if (tid <= 2 * E) {
+          const double* col = stage + (size_t)buf * EM_STAGE_DOUBLES + tid;
+          for (int j = 0; j < nj; j++) acc += col[(size_t)j * RS];
+        }
+        double* dst = stage + (size_t)(buf ^ 1) * EM_STAGE_DOUBLES;
 #pragma unroll
-        for (int u = 0; u < U; u++) v[u] = w[u];
+        for (int u = 0; u < 9; u++) { const int i = tid + u * EM_THREADS; if (i < nn * RS) dst[i] = pre[u]; }
+        __syncthreads();
+        buf ^= 1;
       }
       if (tid < E) tn[tid] = acc;
       else if (tid < 2 * E) td[tid - E] = acc;
-      else { prev_s = ll_s; ll_s = acc; }
+      else if (tid == 2 * E) { prev_s = ll_s; ll_s = acc; }
     }
     __syncthreads();
     if (prof) { t1 = clock64(); tp[4] += t1 - t0; t0 = t1; }
-    for (int e = tid; e < E; e += blockDim.x) q[e] = tn[e] / td[e];
-    __syncthreads();
-    if (tid == 0) {
-      for (int e = 0; e < E; e++) {  // M-step, coal.cpp:3771-3815 (regularise == 2)
-        if (tn[e] == 0) rate[e] = (e > 0) ? rate[e - 1] : 0.0;
-        else if (td[e] == 0) { }
-        else { double r = q[e]; rate[e] = (r < 5e-9) ? 5e-9 : r; }
-      }
-      if ((ll_s / prev_s > 1.0 - 1e-7) && (iter > 1000)) stop_flag = 1;  // coal.cpp:3822
+    // M-step, coal.cpp:3771-3815 (regularise == 2): rate[e] = num/denom floored at 5e-9; num == 0 ->
+    // copy the (already updated) rate of the previous epoch, or 0 for epoch 0; denom == 0 -> keep
+    for (int e = tid; e < E; e += blockDim.x) {
+      const double n_ = tn[e], d_ = td[e];
+      double r = rate[e];
+      if (n_ != 0 && d_ != 0) { r = n_ / d_; r = (r < 5e-9) ? 5e-9 : r; }
+      cand[e] = r;
     }
+    __syncthreads();
+    for (int e = tid; e < E; e += blockDim.x) {
+      int s = e;
+      while (s >= 0 && tn[s] == 0) s--;          // nearest epoch at or below e with a non-zero numerator
+      rate[e] = (s >= 0) ? cand[s] : 0.0;
+    }
+    if (tid == 0 && (ll_s / prev_s > 1.0 - 1e-7) && (iter > 1000)) stop_flag = 1;  // coal.cpp:3822
     __syncthreads();
     if (prof) { t1 = clock64(); tp[5] += t1 - t0; t0 = t1; }
     if (stop_flag) break;
   }
-  if (prof && tid == 0) for (int i = 0; i < 8; i++) prof[i] = tp[i];
-  if (prof && tid == EM_THREADS - 1) prof[6] = tp[1];
+  if (prof && tid == 0) for (int i = 0; i < 6; i++) prof[i] = tp[i];
+  if (prof && tid == 384) prof[6] = tp[1];
+  if (prof && tid == 192 + 8 * crank + 1) prof[7] = tp[1];
   if (crank == 0) {
     for (int e = tid; e < E; e += blockDim.x) rates_out[(size_t)rep * E + e] = rate[e];
     if (tid == 0) { iters_out[rep] = iter; ll_out[rep] = ll_s; }
@@ -451,7 +520,7 @@ int run_em(colate_handle* h, int R, int E, int max_iter)
   if (const char* e = getenv("COLATE_EM_CLUSTER")) csize = atoi(e);
   else { while (csize < 8 && R * csize * 2 <= 148) csize *= 2; }
   if (csize != 1 && csize != 2 && csize != 4 && csize != 8) csize = 1;
-  const size_t smem = sizeof(double) * ((size_t)9 * E + 1 + 2 * NBINS) + 512 * 8;
+  const size_t smem = sizeof(double) * ((size_t)10 * E + 1 + 2 * EM_STAGE_DOUBLES) + 512 * 8;
   CK(cudaFuncSetAttribute(k_em, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
   CK(h->d_scratch.ensure((size_t)R * 2 * (2 * E + 2) * EM_TASKS * 8 + 1024));
   long long* prof = nullptr;
@@ -480,8 +549,8 @@ int run_em(colate_handle* h, int R, int E, int max_iter)
     std::vector<long long> hp(8);
     CK(cudaMemcpyAsync(hp.data(), prof, 64, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    fprintf(stderr, "[k_em prof, CTA 0, cycles] AB %lld | folds+notshared %lld (tid511: %lld) | shared %lld | cluster.sync %lld | column sums %lld | M-step %lld (csize %d)\n",
-            hp[0], hp[1], hp[6], hp[2], hp[3], hp[4], hp[5], csize);
+    fprintf(stderr, "[k_em prof, CTA 0 thread 0, cycles] AB %lld | folds + tasks %lld (prefix-chain thread %lld, a not-shared task %lld) | cluster.sync %lld | column sums %lld | M-step %lld (csize %d)\n",
+            hp[0], hp[1], hp[6], hp[7], hp[3], hp[4], hp[5], csize);
   }
   return 0;
 }

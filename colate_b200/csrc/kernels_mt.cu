@@ -34,19 +34,25 @@ __device__ __forceinline__ uint32_t mt_temper_dev(uint32_t z)
   return z;
 }
 
-// windows[d] <- jump(windows[src]) for d = (2*blockIdx+1) << level, src = d - (1<<level);
-// level < 0: in-place jump of windows[0].
+// windows[d] <- jump(windows[src]) for d = (2*j+1) << level, src = d - (1<<level), j = blockIdx.x / P;
+// level < 0: single jump windows[aux_dst] <- jump(windows[aux_src]).
+// A jump is split over P CTAs (P = 1, 2, 4, 8): CTA p computes outputs [p*624/P, (p+1)*624/P); inside
+// the CTA the taps are split over T = P groups of threads whose partial XORs are combined in shared
+// memory.  (One CTA per jump is bound by a single SM's shared-memory bandwidth: 624 x ~10^4 loads.)
 __global__ void __launch_bounds__(JUMP_THREADS)
-k_jump(uint32_t* __restrict__ windows, const uint16_t* __restrict__ taps, int n_taps, int level, int n_chunks)
+k_jump(uint32_t* __restrict__ windows, const uint16_t* __restrict__ taps, int n_taps, int level, int n_chunks, int P,
+       int aux_src, int aux_dst)
 {
   extern __shared__ __align__(16) uint32_t sm[];
   uint32_t* X = sm;                                   // XLEN words (+ pad)
   uint16_t* T = (uint16_t*)(sm + ((XLEN + 3) & ~3));  // tap offsets
+  uint32_t* red = (uint32_t*)(T + ((MAX_TAPS + 15) & ~15));  // [8][78] partial results
   const int tid = threadIdx.x;
+  const int j = blockIdx.x / P, p = blockIdx.x % P;
   int d, src;
-  if (level < 0) { d = 0; src = 0; }
+  if (level < 0) { d = aux_dst; src = aux_src; }
   else {
-    d = (2 * blockIdx.x + 1) << level;
+    d = (2 * j + 1) << level;
     if (d >= n_chunks) return;
     src = d - (1 << level);
   }
@@ -58,17 +64,27 @@ k_jump(uint32_t* __restrict__ windows, const uint16_t* __restrict__ taps, int n_
     if (tid < 227 && n < XLEN) X[n] = mt_mix_dev(X[n - 624], X[n - 623], X[n - 227]);
     __syncthreads();
   }
+  const int nout = MT_N / P;          // outputs of this CTA
+  const int part = tid / nout;        // tap group of this thread (0..P-1); threads >= 624 idle
+  const int jl = tid - part * nout;
+  uint32_t acc = 0;
   if (tid < MT_N) {
-    uint32_t acc = 0;
-    const uint32_t* Xt = X + tid;
-    int i = 0;
-    for (; i + 8 <= n_taps; i += 8) {
-      uint4 t4 = *(const uint4*)(T + i);  // 8 taps, same address for the whole CTA
+    const int per = (((n_taps + P - 1) / P) + 7) & ~7;   // taps per group, multiple of 8 (16-byte loads)
+    const int t0 = part * per, t1 = min(n_taps, t0 + per);
+    const uint32_t* Xt = X + p * nout + jl;
+    int i = t0;
+    for (; i + 8 <= t1; i += 8) {
+      uint4 t4 = *(const uint4*)(T + i);  // 8 taps, same address for the whole group
       acc ^= Xt[t4.x & 0xffff] ^ Xt[t4.x >> 16] ^ Xt[t4.y & 0xffff] ^ Xt[t4.y >> 16] ^
              Xt[t4.z & 0xffff] ^ Xt[t4.z >> 16] ^ Xt[t4.w & 0xffff] ^ Xt[t4.w >> 16];
     }
-    for (; i < n_taps; i++) acc ^= Xt[T[i]];
-    windows[(size_t)d * MT_N + tid] = acc;
+    for (; i < t1; i++) acc ^= Xt[T[i]];
+    if (part > 0) red[(part - 1) * nout + jl] = acc;
+  }
+  __syncthreads();
+  if (tid < nout) {
+    for (int q = 1; q < P; q++) acc ^= red[(q - 1) * nout + tid];
+    windows[(size_t)d * MT_N + p * nout + tid] = acc;
   }
 }
 
@@ -140,18 +156,16 @@ static int get_taps(int device, int q, cudaStream_t s, TapList* out)
   return 0;
 }
 
-static int launch_jump(colate_handle* h, int q, int level, int n_chunks, int grid)
+static int launch_jump(colate_handle* h, int q, int level, int n_chunks, int n_jumps, int aux_src, int aux_dst)
 {
   TapList tl;
   int rc = get_taps(h->device, q, h->stream, &tl);
   if (rc) return rc;
-  const size_t smem = (size_t)((XLEN + 3) & ~3) * 4 + (size_t)((tl.n + 15) & ~15) * 2 + 32;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(k_jump, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * ((XLEN + 3) & ~3) + 2 * MAX_TAPS + 64));
-    attr_set = true;
-  }
-  k_jump<<<grid, JUMP_THREADS, smem, h->stream>>>(h->windows.as<uint32_t>(), tl.d, tl.n, level, n_chunks);
+  int P = 8;
+  while (P > 1 && n_jumps * P > 2 * h->sm_count) P >>= 1;   // fill the GPU, then stop splitting
+  const size_t smem = (size_t)((XLEN + 3) & ~3) * 4 + (size_t)((MAX_TAPS + 15) & ~15) * 2 + (size_t)7 * 312 * 4 + 64;
+  CK(cudaFuncSetAttribute(k_jump, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_jump<<<n_jumps * P, JUMP_THREADS, smem, h->stream>>>(h->windows.as<uint32_t>(), tl.d, tl.n, level, n_chunks, P, aux_src, aux_dst);
   h->launches += 1;
   CK(cudaGetLastError());
   return 0;
@@ -173,23 +187,28 @@ int run_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int
   const int M = (int)M64;
   const int64_t total_local = word0 + n_words - c0 * S;  // words from the start of chunk c0
   cudaStream_t s = h->stream;
-  CK(h->windows.ensure((size_t)M * MT_N * 4));
+  CK(h->windows.ensure((size_t)(M + 1) * MT_N * 4));  // + one scratch window for the offset jumps
   CK(h->rng_stream.ensure((size_t)std::max<int64_t>(total_local, 4) * 4 + 64));
   CK(cudaMemcpyAsync(h->windows.p, mt_state, MT_N * 4, cudaMemcpyHostToDevice, s));
-  // reach chunk c0: one in-place jump per set bit of c0
+  // reach chunk c0: one jump per set bit of c0, ping-ponging between window 0 and the scratch window
+  int cur = 0;
   for (int b = 62; b >= 0; b--) {
     if (!((c0 >> b) & 1)) continue;
     if (k + b > 48) return fail(COLATE_ERR_ARG, "generator offset too large");
-    int rc = launch_jump(h, k + b, -1, 1, 1);
+    const int nxt = cur == 0 ? M : 0;
+    int rc = launch_jump(h, k + b, -1, 1, 1, cur, nxt);
     if (rc) return rc;
+    cur = nxt;
   }
+  if (cur != 0)
+    CK(cudaMemcpyAsync(h->windows.p, h->windows.as<uint32_t>() + (size_t)M * MT_N, MT_N * 4, cudaMemcpyDeviceToDevice, s));
   // tree over the chunks of this call
   int K = 0;
   while ((1 << K) < M) K++;
   for (int l = K - 1; l >= 0; l--) {
     if (M <= (1 << l)) continue;
-    int grid = (M - (1 << l) + (2 << l) - 1) / (2 << l);
-    int rc = launch_jump(h, k + l, l, M, grid);
+    int n_jumps = (M - (1 << l) + (2 << l) - 1) / (2 << l);
+    int rc = launch_jump(h, k + l, l, M, n_jumps, 0, 0);
     if (rc) return rc;
   }
   if (total_local > 0) {
