@@ -1,0 +1,141 @@
+"""Multi-GPU driver of the path: one process per GPU (torch.distributed, NCCL over NVLink; gloo in
+CPU tests), mirroring SURVEY.md 8(e).
+
+  sites      sharded by chromosome: rank r owns a contiguous range of the --chr list.  The only
+             exchanges are (1) an all-gather of two integers per rank (used rows, genomic blocks:
+             they give every rank its offset into the reference's generator stream and its first
+             block) and (2) one all-reduce of the zero-padded [500, 4, 185] block histograms
+             (adding zeros is exact, so the result is bit-identical to a single-GPU run);
+  replicates sharded round-robin for the bootstrap + EM; every rank draws the full weight table from
+             the same generator state (it is the reference's stream), results are all-gathered;
+  pairs      independent: no collective (bench.py --gpus N).
+
+The compute backend is anything with the four stage methods of `api.Handle`; tests inject a
+CPU stand-in to exercise this host logic under gloo with world_size 2.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import api
+from ._lib import MAX_BLOCKS, NBINS
+
+
+def split_chromosomes(rows_per_chr, world: int):
+    """Contiguous ranges [lo, hi) of the --chr list per rank, balanced by row count."""
+    rows = np.asarray(rows_per_chr, dtype=np.int64)
+    n = rows.shape[0]
+    cum = np.concatenate([[0], np.cumsum(rows)])
+    total = cum[-1]
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r / world
+        c = int(np.searchsorted(cum, target, side="left"))
+        c = max(bounds[-1], min(n, c))
+        bounds.append(c)
+    bounds.append(n)
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+class CudaBackend:
+    """The product path: api.Handle on this rank's GPU."""
+
+    def __init__(self, handle: api.Handle):
+        self.h = handle
+
+    def flags(self):
+        return self.h.stage1_flags()
+
+    def sample(self, mt_state, used_rank_base, block_base, n_blocks):
+        return self.h.stage1_sample(mt_state, used_rank_base, block_base, n_blocks)
+
+    def bootstrap(self, weights, block_stats, age):
+        self.h.stage2_bootstrap(weights, block_stats, age, fetch=False)
+        return None
+
+    def em(self, R, epochs, rates_init, counts, max_iter):
+        return self.h.stage3_em(R, epochs, rates_init, counts, max_iter)
+
+
+@dataclass
+class DistResult:
+    num_blocks: int
+    n_used: int
+    block_stats: np.ndarray      # [num_blocks, 4, 185], identical on every rank
+    block_tallies: np.ndarray    # [num_blocks, 3, 185]
+    mt_state: np.ndarray         # generator state after stage i, identical on every rank
+    rates: np.ndarray | None     # [R, E] on every rank
+    iters: np.ndarray | None
+    epochs: np.ndarray | None
+    ep_null: int = 0
+
+
+def _dist():
+    import torch
+    import torch.distributed as dist
+    return torch, dist
+
+
+def stage1_sharded(backend, seed_state: np.ndarray, device="cuda"):
+    """Stage i with the sites sharded by chromosome.  Every rank returns the full block histograms."""
+    torch, dist = _dist()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    used_chr, blocks_chr = backend.flags()
+    mine = torch.tensor([int(np.sum(used_chr)), int(np.sum(blocks_chr))], dtype=torch.int64, device=device)
+    allv = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    allv = np.stack([v.cpu().numpy() for v in allv])           # [world, 2]
+    used_base = int(allv[:rank, 0].sum())
+    block_base = int(allv[:rank, 1].sum())
+    n_used, num_blocks = int(allv[:, 0].sum()), int(allv[:, 1].sum())
+    if num_blocks > MAX_BLOCKS:
+        raise api._lib.ColateError(-3, "more than 500 genomic blocks")
+    n_local = int(allv[rank, 1])
+    stats, tallies, state_after = backend.sample(seed_state, used_base, block_base, n_local)
+    pad = torch.zeros((MAX_BLOCKS, 4, NBINS), dtype=torch.float64, device=device)
+    pad_n = torch.zeros((MAX_BLOCKS, 3, NBINS), dtype=torch.int64, device=device)
+    if n_local:
+        pad[block_base:block_base + n_local] = torch.from_numpy(np.ascontiguousarray(stats[:n_local])).to(device)
+        pad_n[block_base:block_base + n_local] = torch.from_numpy(np.ascontiguousarray(tallies[:n_local])).to(device)
+    dist.all_reduce(pad, op=dist.ReduceOp.SUM)                 # disjoint supports: x + 0.0 == x
+    dist.all_reduce(pad_n, op=dist.ReduceOp.SUM)
+    # the generator state after the last used row lives on the last rank
+    st = torch.from_numpy(state_after.astype(np.int64)).to(device)
+    dist.broadcast(st, src=world - 1)
+    return DistResult(num_blocks, n_used, pad[:num_blocks].cpu().numpy(), pad_n[:num_blocks].cpu().numpy(),
+                      st.cpu().numpy().astype(np.uint32), None, None, None)
+
+
+def em_sharded(backend, res: DistResult, num_bootstraps: int, epochs, rates_init, age=0.0, max_iter=100000, device="cuda"):
+    """Stages ii + iii with the replicates dealt round-robin to the ranks; all-gathers the rates."""
+    torch, dist = _dist()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    state = res.mt_state.copy()
+    w = api.draw_block_weights(state, num_bootstraps, res.num_blocks)   # same table on every rank
+    mine = np.arange(rank, num_bootstraps, world)
+    E = len(epochs)
+    rates = torch.zeros((num_bootstraps, E), dtype=torch.float64, device=device)
+    iters = torch.zeros(num_bootstraps, dtype=torch.int64, device=device)
+    if mine.shape[0]:
+        counts = backend.bootstrap(np.ascontiguousarray(w[mine]), res.block_stats, age)
+        r, it, _ = backend.em(mine.shape[0], epochs, rates_init, counts, max_iter)
+        idx = torch.from_numpy(mine).to(device)
+        rates[idx] = torch.from_numpy(np.ascontiguousarray(r)).to(device)
+        iters[idx] = torch.from_numpy(np.asarray(it, dtype=np.int64)).to(device)
+    dist.all_reduce(rates, op=dist.ReduceOp.SUM)               # disjoint supports again
+    dist.all_reduce(iters, op=dist.ReduceOp.SUM)
+    res.rates, res.iters, res.epochs = rates.cpu().numpy(), iters.cpu().numpy().astype(np.int32), np.asarray(epochs)
+    return res
+
+
+def mut_sharded(backend, seed: int, bins: str = "3,7,0.2", num_bootstraps: int = 1, target_age=None, reference_age=None,
+                years_per_gen=None, max_iter=100000, device="cuda") -> DistResult:
+    """mut() (coal.cpp:3071-3863) across the ranks of the default process group."""
+    age, ypg = api.ages(target_age, reference_age, years_per_gen)
+    res = stage1_sharded(backend, api.mt_seed(seed), device)
+    epochs, ep_null = api.epochs_from_bins(bins, age, ypg)
+    res = em_sharded(backend, res, num_bootstraps, epochs, np.full(len(epochs), 1.0 / 20000.0), age, max_iter, device)
+    res.ep_null = ep_null
+    return res

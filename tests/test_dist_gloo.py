@@ -1,0 +1,143 @@
+"""CPU: the multi-GPU host logic (colate_b200/dist.py) under gloo with world_size 2.  The compute
+backend is replaced by an oracle-backed stand-in (test infrastructure), so what is tested is the
+sharding: chromosome split, generator-stream offsets, block bases, zero-padded all-reduce,
+replicate assignment and gathers.  The result must be bit-identical to the single-process run."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleBackend:
+    """Stand-in for api.Handle on one rank: same stage contract, computed by the CPU oracle."""
+
+    def __init__(self, sites, gt, gr, chr_lo, chr_hi):
+        from colate_b200 import synth
+        lo, hi = int(sites.site_off[chr_lo]), int(sites.site_off[chr_hi])
+        off = sites.site_off[chr_lo:chr_hi + 1] - sites.site_off[chr_lo]
+        self.sites = synth.Sites(sites.chr_names[chr_lo:chr_hi], off, sites.pos[lo:hi], sites.age_begin[lo:hi], sites.age_end[lo:hi],
+                                 sites.flipped[lo:hi], sites.n_branch[lo:hi], sites.anc[lo:hi], sites.der[lo:hi], sites.odd[lo:hi],
+                                 sites.chrom_len[chr_lo:chr_hi])
+
+        def sub(g):  # records of the rank's chromosomes, renumbered (the seek only ever looks at listed names)
+            ch = g.chrom.astype(np.int64) - chr_lo
+            ch = np.where((ch >= 0) & (ch < chr_hi - chr_lo), ch, chr_hi - chr_lo + 5)
+            return synth.Genome(ch.astype(np.int32), g.bp, g.anc, g.der, g.aaf, g.daf)
+        self.gt, self.gr = sub(gt), sub(gr)
+        self._counts = None
+
+    def flags(self):
+        from oracle import pyoracle as po
+        used, blocks = [], []
+        for c in range(len(self.sites.chr_names)):
+            o = OracleBackend._one(self, c)
+            used.append(o["n_used_total"]); blocks.append(o["num_blocks"])
+        return np.array(used, np.int64), np.array(blocks, np.int32)
+
+    def _one(self, c):
+        from colate_b200 import synth
+        from oracle import pyoracle as po
+        s = self.sites
+        lo, hi = int(s.site_off[c]), int(s.site_off[c + 1])
+        one = synth.Sites([s.chr_names[c]], np.array([0, hi - lo]), s.pos[lo:hi], s.age_begin[lo:hi], s.age_end[lo:hi], s.flipped[lo:hi],
+                          s.n_branch[lo:hi], s.anc[lo:hi], s.der[lo:hi], s.odd[lo:hi], [s.chrom_len[c]])
+
+        def sub(g):
+            ch = np.where(g.chrom == c, 0, 7).astype(np.int32)
+            return synth.Genome(ch, g.bp, g.anc, g.der, g.aaf, g.daf)
+        return po.stage1(one, sub(self.gt), sub(self.gr), seed=1)
+
+    def sample(self, mt_state, used_rank_base, block_base, n_blocks):
+        from colate_b200 import api
+        from oracle import pyoracle as po
+        # an oracle generator positioned at this rank's offset in the reference's stream
+        g = po.mt_seed(self._seed)
+        for _ in range(200 * used_rank_base):
+            po.lib().oracle_mt_next(g)
+        o = po.stage1(self.sites, self.gt, self.gr, rng=g)
+        nb = o["num_blocks"]
+        stats = np.stack([o["shared"], o["notshared"], o["shared_emp"], o["notshared_emp"]], axis=1)
+        tallies = np.stack([o["n_shared"], o["n_notshared"], o["n_emp"]], axis=1)
+        after = api.mt_seed(self._seed)
+        burn = np.zeros(max(1, 200 * (used_rank_base + o["n_used_total"])), np.uint32)
+        api.lib().colate_mt_generate(after, 200 * (used_rank_base + o["n_used_total"]), burn)
+        assert nb == n_blocks
+        return stats, tallies, after
+
+    def bootstrap(self, weights, block_stats, age):
+        from oracle import pyoracle as po
+        blk = {k: np.ascontiguousarray(block_stats[:, i]) for i, k in enumerate(("shared", "notshared", "shared_emp", "notshared_emp"))}
+        return po.stage2(np.ascontiguousarray(weights), blk, age)
+
+    def em(self, R, epochs, rates_init, counts, max_iter):
+        from oracle import pyoracle as po
+        out = [po.em_run(epochs, rates_init, counts[r], max_iter) for r in range(R)]
+        return np.stack([o[0] for o in out]), np.array([o[1] for o in out]), np.array([o[2] for o in out])
+
+
+def _worker(rank, world, port, seed, R, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from colate_b200 import dist as cdist, synth
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sites = synth.make_sites(seed, [900, 600, 1400, 700, 1100], [2.4e8, 5e7, 1.3e8, 6.1e7, 9e7], weird=0.05)
+    gt = synth.make_genome(seed + 100, sites, 0.8)
+    gr = synth.make_genome(seed + 200, sites, 0.8)
+    parts = cdist.split_chromosomes(np.diff(sites.site_off), world)
+    be = OracleBackend(sites, gt, gr, *parts[rank])
+    be._seed = seed
+    res = cdist.mut_sharded(be, seed, bins="3,7,0.2", num_bootstraps=R, max_iter=30, device="cpu")
+    q.put((rank, res.num_blocks, res.n_used, res.block_stats, res.block_tallies, res.mt_state, res.rates, res.iters))
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+@pytest.mark.parametrize("R", [1, 5])
+def test_chromosome_and_replicate_sharding_world2(built, R):
+    from colate_b200 import synth
+    from oracle import pyoracle as po
+    seed, world = 4, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, seed, R, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=150) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    # single-process run of the whole thing
+    sites = synth.make_sites(seed, [900, 600, 1400, 700, 1100], [2.4e8, 5e7, 1.3e8, 6.1e7, 9e7], weird=0.05)
+    gt = synth.make_genome(seed + 100, sites, 0.8)
+    gr = synth.make_genome(seed + 200, sites, 0.8)
+    o = po.stage1(sites, gt, gr, seed=seed)
+    w = po.draw_block_weights(o["rng"], R, o["num_blocks"])
+    counts = po.stage2(w, o, 0.0)
+    ep, _ = po.epochs_from_bins("3,7,0.2")
+    want = np.stack([po.em_run(ep, np.full(len(ep), 1 / 20000.), counts[r], 30)[0] for r in range(R)])
+    ref_stats = np.stack([o["shared"], o["notshared"], o["shared_emp"], o["notshared_emp"]], axis=1)
+    for rank, nb, nu, stats, tallies, st, rates, iters in outs:
+        assert nb == o["num_blocks"] and nu == o["n_used_total"]
+        assert np.array_equal(stats, ref_stats)                       # bit-identical to one process
+        assert np.array_equal(tallies[:, 1], o["n_notshared"])
+        assert np.array_equal(rates, want) and (iters == 30).all()
+    assert np.array_equal(outs[0][5], outs[1][5])                     # same generator state everywhere
+
+
+def test_split_chromosomes():
+    from colate_b200.dist import split_chromosomes
+    assert split_chromosomes([10, 10, 10, 10], 2) == [(0, 2), (2, 4)]
+    assert split_chromosomes([5], 4) == [(0, 0), (0, 0), (0, 0), (0, 1)] or sum(h - l for l, h in split_chromosomes([5], 4)) == 1
+    for w in (1, 2, 3, 8):
+        parts = split_chromosomes([249, 243, 198, 191, 180, 171, 159, 146, 141, 135, 135, 133, 115, 107, 102, 90, 81, 78, 59, 63, 48, 51], w)
+        assert parts[0][0] == 0 and parts[-1][1] == 22 and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
