@@ -31,7 +31,7 @@ VP = C.c_void_p
 
 class Stage1Timing(C.Structure):
     _fields_ = [("join_ms", C.c_float), ("flags_ms", C.c_float), ("rng_ms", C.c_float), ("compact_ms", C.c_float),
-                ("sample_ms", C.c_float), ("reduce_ms", C.c_float), ("total_ms", C.c_float), ("n_site", C.c_int64),
+                ("sample_ms", C.c_float), ("replay_ms", C.c_float), ("total_ms", C.c_float), ("n_site", C.c_int64),
                 ("n_used", C.c_int64), ("rng_words", C.c_int64)]
 
 

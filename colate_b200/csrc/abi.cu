@@ -263,10 +263,10 @@ int colate_stage1_sample(colate_handle* h, const uint32_t* mt_state, int64_t use
   cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]); h->timing.rng_ms = ms;
   cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->timing.compact_ms = ms;
   cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); h->timing.sample_ms = ms;   // k_sample alone
-  cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->timing.reduce_ms = ms;
+  cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->timing.replay_ms = ms;
   h->timing.rng_words = 200 * nu;
   h->timing.total_ms = h->timing.join_ms + h->timing.flags_ms + h->timing.rng_ms + h->timing.compact_ms + h->timing.sample_ms +
-                       h->timing.reduce_ms;
+                       h->timing.replay_ms;
   return 0;
 }
 

@@ -142,7 +142,7 @@ typedef struct {
   float rng_ms;      /* MT19937 jump-ahead tree + stream generation                            */
   float compact_ms;  /* used rows -> dense records, tile table                                 */
   float sample_ms;   /* k_sample alone: the per-mutation Monte-Carlo binning kernel            */
-  float reduce_ms;   /* per-block fixed-order reduction                                        */
+  float replay_ms;   /* k_replay + k_emp: exact per-block histograms in the reference's addition order */
   float total_ms;
   int64_t n_site, n_used, rng_words;
 } colate_stage1_timing;
