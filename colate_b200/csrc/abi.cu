@@ -27,12 +27,12 @@ int ensure_tables(colate_handle* h)
   colate_age_bins(ab);
   CK(h->thr10.ensure(sizeof thr));
   CK(h->d_agebin.ensure(sizeof ab));
-  static double thrA[NBINS + 2];
+  static double thrA[NBINS + 2], thrP[192];
   static uint16_t lut[LUT_N];
-  if (!age_thresholds(thrA, lut)) return fail(COLATE_ERR_ARG, "host libm log() is not monotone around an age-bin threshold");
-  CK(h->thrA.ensure(sizeof thrA));
+  if (!age_thresholds(thrA, thrP, lut)) return fail(COLATE_ERR_ARG, "host libm log() is not monotone around an age-bin threshold");
+  CK(h->thrA.ensure(sizeof thrP));
   CK(h->lut.ensure(sizeof lut + 16));
-  CK(cudaMemcpyAsync(h->thrA.p, thrA, sizeof thrA, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->thrA.p, thrP, sizeof thrP, cudaMemcpyHostToDevice, h->stream));  // slot-indexed thresholds
   CK(cudaMemcpyAsync(h->lut.p, lut, sizeof lut, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->thr10.p, thr, sizeof thr, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_agebin.p, ab, sizeof ab, cudaMemcpyHostToDevice, h->stream));

@@ -51,7 +51,7 @@ bool bin_thresholds(double* thr10)
   return monotone;
 }
 
-bool age_thresholds(double* thrA, uint16_t* lut)
+bool age_thresholds(double* thrA, double* thrP, uint16_t* lut)
 {
   bool monotone = true;
   thrA[0] = 0.0;
@@ -68,17 +68,19 @@ bool age_thresholds(double* thrA, uint16_t* lut)
     }
   }
   thrA[NBINS + 1] = HUGE_VAL;
+  for (int p = 0; p < 192; p++) thrP[p] = HUGE_VAL;
+  for (int k = 0; k <= NBINS; k++) thrP[slot_of_bin(k)] = thrA[k + 1];
   for (int c = 0; c < LUT_N; c++) {
-    const double edge = from_bits((uint64_t)(uint32_t)((c + LUT_BASE) << 14) << 32);
+    const double edge = from_bits((uint64_t)(uint32_t)((c + LUT_BASE) << LUT_SHIFT) << 32);
     int k = 0;
     while (k < NBINS && edge >= thrA[k + 1]) k++;
-    // at most one threshold inside a cell (cells are 2^-6 wide in log2, bins e^0.1); bit 7 says
-    // whether there is one (then the device compares against thrA[k+1]), the first and last
-    // cells are clamp targets and always compare
-    const double next = from_bits((uint64_t)(uint32_t)((c + 1 + LUT_BASE) << 14) << 32);
+    // at most one threshold inside a cell (a cell is at most a factor 1 + 1/32 wide, a bin e^0.1);
+    // bit 15 says whether there is one (then the device compares against thrP[slot]), the first
+    // and last cells are clamp targets and always compare
+    const double next = from_bits((uint64_t)(uint32_t)((c + 1 + LUT_BASE) << LUT_SHIFT) << 32);
     if (k + 2 <= NBINS && next > thrA[k + 2]) monotone = false;
     const bool inside = (k < NBINS && next > thrA[k + 1]) || c == 0 || c == LUT_N - 1;
-    lut[c] = (uint16_t)(k | (inside ? 0x8000 : 0));
+    lut[c] = (uint16_t)(slot_of_bin(k) | (inside ? 0x8000 : 0));
   }
   return monotone;
 }

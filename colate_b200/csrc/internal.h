@@ -11,9 +11,21 @@ namespace colate {
 constexpr int NBINS = COLATE_NUM_AGE_BINS;
 constexpr int MAX_BLOCKS = COLATE_MAX_BLOCKS;
 constexpr int NTHR = NBINS + 1;  // thr10[1..185]; index 0 unused
-// age -> bin lookup: cell = (high word of the double >> 14) - LUT_BASE, cells from 2^-4 to 2^24
-constexpr int LUT_BASE = 0x3FB00000 >> 14;
-constexpr int LUT_N = (0x41700000 >> 14) - LUT_BASE;
+// age -> bin lookup: cell = (high word of the double >> LUT_SHIFT) - LUT_BASE, 32 cells per octave
+// from 2^-4 to 2^24 (a row's age interval then spans at most ~32 32-bit words of the table:
+// no shared-memory bank conflicts between the lanes of a warp)
+constexpr int LUT_SHIFT = 15;
+constexpr int LUT_BASE = 0x3FB00000 >> LUT_SHIFT;
+constexpr int LUT_N = (0x41700000 >> LUT_SHIFT) - LUT_BASE;
+// Per-row sample counts travel as one byte per age bin, bins interleaved over 47 32-bit words:
+// bin k lives in byte k / 47 of word k % 47, so the neighbouring bins one row's samples fall into
+// hit different words (shared-memory atomics on one word serialise).  slot = byte offset in the row.
+constexpr int ROW_WORDS = 47;
+constexpr int ROW_SLOTS = 4 * ROW_WORDS;  // 188 >= NBINS + 1 (bin 185 = "age out of range")
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+constexpr int slot_of_bin(int k) { return 4 * (k % ROW_WORDS) + k / ROW_WORDS; }
 
 // error plumbing (thread-local message behind colate_last_error())
 void set_error(const std::string& msg);
@@ -34,8 +46,9 @@ void jump_window_host(const uint32_t* w, int q, uint32_t* out);
 // Returns false if log() is not monotone in a +-16 ulp neighbourhood of a threshold.
 bool bin_thresholds(double* thr10 /*[NTHR]*/);
 // thrA[k], k = 1..185: smallest age a with bin(a) >= k where bin(a) = max(0,(int)round(log(10*a)*10)+1);
-// thrA[186] = +inf; lut[cell] = bin at the lower edge of the cell
-bool age_thresholds(double* thrA /*[NBINS+2]*/, uint16_t* lut /*[LUT_N]*/);
+// thrA[186] = +inf.  thrP[slot_of_bin(k)] = thrA[k+1] (the threshold that ends bin k, indexed by count slot);
+// lut[cell] = slot_of_bin(bin at the lower edge of the cell) | 0x8000 if a threshold lies inside the cell
+bool age_thresholds(double* thrA /*[NBINS+2]*/, double* thrP /*[192]*/, uint16_t* lut /*[LUT_N]*/);
 int bin_of_x10_host(double x10);
 
 }  // namespace colate

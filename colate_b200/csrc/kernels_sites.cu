@@ -201,7 +201,7 @@ __global__ void k_chr(int n_chr, const int64_t* __restrict__ site_off, const int
 }
 
 // used rows -> dense records in rank order:
-//   hdr[r]  = {age_end - age_begin, age_begin, weight into shared, weight into notshared} (fp64 x4)
+//   hdr[r]  = {(age_end - age_begin) * 2^-64, age_begin, weight into shared, weight into notshared} (fp64 x4)
 //   e_b2/e_ws/e_wn[r] = bin and weights of the row's single "emp" contribution (255 = none)
 //   u_blk[r] = genomic block (index local to this handle)
 __global__ void k_compact(int64_t n_site, int n_chr, const int64_t* __restrict__ site_off, const int32_t* __restrict__ pos,
@@ -235,7 +235,9 @@ __global__ void k_compact(int64_t n_site, int n_chr, const int64_t* __restrict__
   const double num_s = (double)__fmul_rn(fd, __int2float_rn(dafr));
   const double num_n = (double)__fmul_rn(fa, __int2float_rn(dafr));
   const double den = __dmul_rn((double)nr, 100.0);
-  hdr[r] = make_double4(__dsub_rn((double)e, abd), abd, __ddiv_rn(num_s, den), __ddiv_rn(num_n, den));
+  // .x = (age_end - age_begin) * 2^-64: the sampling kernel multiplies it with the 64-bit integer
+  // x2:x1 converted once (exact power-of-two scaling, same rounding as U * (age_end - age_begin))
+  hdr[r] = make_double4(__dmul_rn(__dsub_rn((double)e, abd), 0x1p-64), abd, __ddiv_rn(num_s, den), __ddiv_rn(num_n, den));
   uint8_t b2 = 255;
   double ws = 0.0, wn = 0.0;
   if (abd <= 0.0) {  // coal.cpp:2247-2256 with age == 0
@@ -298,30 +300,44 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 // ------------------------------------------------------------------------------------------
 // uniform_real_distribution<double>(0,1) from two engine words, bit-exact with libstdc++'s
-// generate_canonical<double,53>: (x1 + x2*2^32) / 2^64, rounded once, clamped below 1.
-__device__ __forceinline__ double u01(uint32_t x1, uint32_t x2)
+// generate_canonical<double,53>: (x1 + x2*2^32) / 2^64 rounded once and clamped below 1.  Here the
+// 64-bit integer x2:x1 is converted with one round-to-nearest I2F (the same single rounding), the
+// clamp becomes a min with 2^64 - 2^11, and the factor 2^-64 is folded into the row's length.
+__device__ __forceinline__ double u64_scaled(uint32_t x1, uint32_t x2)
 {
-  double d1 = __hiloint2double(0x3F300000, (int)x1) - 0x1p-12;  // x1 * 2^-64, exact
-  double d2 = __hiloint2double(0x41300000, (int)x2) - 0x1p20;   // x2 * 2^-32, exact
-  double u = __dadd_rn(d2, d1);
-  return u >= 1.0 ? 0x1.fffffffffffffp-1 : u;
+  const double v = __ull2double_rn(((unsigned long long)x2 << 32) | x1);
+  // v == 2^64 (x2:x1 >= 2^64 - 2^10) -> the double just below: bit pattern minus one
+  const int hi = __double2hiint(v);
+  const bool top = hi == 0x43f00000;
+  return __hiloint2double(top ? 0x43efffff : hi, top ? -1 : __double2loint(v));
 }
 
 // max(0,(int)round(log(10*a)*10)+1) (coal.cpp:2265/2284) without evaluating log: the top 17 bits
 // of a select a cell of width 2^-6 in log2 (narrower than an age bin, e^0.1), a table gives the
 // bin at the cell's lower edge and one exact threshold (host-computed against libm) settles it.
-__device__ __forceinline__ int bin_of_age(double a, const uint16_t* lut, const double* thrA)
+// Returns the count slot (internal.h: slot_of_bin) of the sample's age bin.
+__device__ __forceinline__ int slot_of_age(double a, const uint16_t* lut, const double* thrP)
 {
-  int cell = (__double2hiint(a) >> 14) - LUT_BASE;
+  int cell = (__double2hiint(a) >> LUT_SHIFT) - LUT_BASE;
   cell = max(0, min(cell, LUT_N - 1));
-  int k = lut[cell];           // bit 15: an age-bin threshold lies inside this cell (1 cell in 9)
-  if (k & 0x8000) { k &= 0xff; k += (a >= thrA[k + 1]) ? 1 : 0; }
-  return k;
+  int p = lut[cell];           // bit 15: an age-bin threshold lies inside this cell (about 1 cell in 5)
+  if (p & 0x8000) {
+    p &= 0xff;
+    if (a >= thrP[p]) { p += 4; if (p >= ROW_SLOTS) p -= ROW_SLOTS - 1; }   // slot of the next bin
+  }
+  return p;
 }
 
 constexpr int SW = 8;                 // consumer warps = used rows per pipeline stage
 constexpr int SAMPLE_STAGES = 4;
 constexpr int ROW_BYTES = 192;        // per-row sample counts, one byte per age bin (185 used)
+#ifndef ROW_COPIES
+#define ROW_COPIES 2
+#endif
+#ifndef ROW_STRIDE64_
+#define ROW_STRIDE64_ 24
+#endif
+constexpr int ROW_STRIDE64 = ROW_STRIDE64_;      // 64-bit words between the two shared-memory copies of a row (208 B: staggers the banks)
 struct __align__(16) SampleStage {
   uint4 words[SW][50];                // 200 engine words per used row
   double4 hdr[SW];
@@ -341,15 +357,15 @@ k_sample(int64_t n_used, const uint32_t* __restrict__ stream, const double4* __r
   SampleStage* st = (SampleStage*)smem_raw;
   uint64_t* full = (uint64_t*)(smem_raw + sizeof(SampleStage) * SAMPLE_STAGES);
   uint64_t* empty = full + SAMPLE_STAGES;
-  double* thrA = (double*)(empty + SAMPLE_STAGES);                 // [NBINS + 2]
-  uint16_t* lut = (uint16_t*)(thrA + NBINS + 2);                     // [LUT_N]
-  uint64_t* rows = (uint64_t*)(lut + ((LUT_N + 15) & ~15));         // [SW][4][ROW_BYTES / 8]: per-warp count rows
+  double* thrA = (double*)(empty + SAMPLE_STAGES);                 // [192] thresholds by count slot
+  uint16_t* lut = (uint16_t*)(thrA + 192);                     // [LUT_N]
+  uint64_t* rows = (uint64_t*)(lut + ((LUT_N + 15) & ~15));         // [SW][ROW_COPIES][ROW_STRIDE64]: per-warp count rows
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_stage = (n_used + SW - 1) / SW;
-  for (int i = threadIdx.x; i < NBINS + 2; i += blockDim.x) thrA[i] = thrA_g[i];
+  for (int i = threadIdx.x; i < 192; i += blockDim.x) thrA[i] = thrA_g[i];
   for (int i = threadIdx.x; i < LUT_N; i += blockDim.x) lut[i] = lut_g[i];
-  for (int i = threadIdx.x; i < SW * 4 * ROW_BYTES / 8; i += blockDim.x) rows[i] = 0;
+  for (int i = threadIdx.x; i < SW * ROW_COPIES * ROW_STRIDE64; i += blockDim.x) rows[i] = 0;
   if (threadIdx.x == 0) {
     for (int i = 0; i < SAMPLE_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], SW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -372,9 +388,8 @@ k_sample(int64_t n_used, const uint32_t* __restrict__ stream, const double4* __r
     return;
   }
 
-  uint64_t* myrows = rows + (size_t)warp * 4 * (ROW_BYTES / 8);       // four copies: lanes spread over them
-  uint32_t* myrow = (uint32_t*)(myrows + (size_t)(lane & 3) * (ROW_BYTES / 8));
-  bool overflow = false;
+  uint64_t* myrows = rows + (size_t)warp * ROW_COPIES * ROW_STRIDE64;           // two copies (odd / even lanes), bank-staggered
+  uint32_t* myrow = (uint32_t*)(myrows + (size_t)(lane & (ROW_COPIES - 1)) * ROW_STRIDE64);
   int it = 0;
   for (int64_t sid = blockIdx.x; sid < n_stage; sid += gridDim.x, it++) {
     const int slot = it % SAMPLE_STAGES;
@@ -382,37 +397,37 @@ k_sample(int64_t n_used, const uint32_t* __restrict__ stream, const double4* __r
     const int64_t r = sid * SW + warp;
     if (r < n_used) {
       const double4 h = st[slot].hdr[warp];
-      const double len = h.x, abd = h.y;
+      const double lenp = h.x, abd = h.y;
       const uint4 q0 = st[slot].words[warp][lane];
       const bool has1 = lane < 18;
-      const uint4 q1 = has1 ? st[slot].words[warp][32 + lane] : make_uint4(0, 0, 0, 0);
-      int bins[4];
+      uint4 q1 = q0;
+      if (has1) q1 = st[slot].words[warp][32 + lane];
       // sampled_age = U * (age_end - age_begin) + age_begin, product and sum rounded separately
-      bins[0] = bin_of_age(__dadd_rn(__dmul_rn(u01(q0.x, q0.y), len), abd), lut, thrA);
-      bins[1] = bin_of_age(__dadd_rn(__dmul_rn(u01(q0.z, q0.w), len), abd), lut, thrA);
-      bins[2] = has1 ? bin_of_age(__dadd_rn(__dmul_rn(u01(q1.x, q1.y), len), abd), lut, thrA) : 0xffff;
-      bins[3] = has1 ? bin_of_age(__dadd_rn(__dmul_rn(u01(q1.z, q1.w), len), abd), lut, thrA) : 0xffff;
-      // per-row counts: one byte per age bin, four bins per 32-bit word; shared-memory atomics
-      // resolve lanes that hit the same bin (at most 100 per byte: no carry into the next bin)
-#pragma unroll
-      for (int s = 0; s < 4; s++) {
-        const int b = bins[s];
-        if (b < NBINS) atomicAdd(&myrow[b >> 2], 1u << (8 * (b & 3)));
-        else if (b == NBINS) overflow = true;
+      const int b0 = slot_of_age(__dadd_rn(__dmul_rn(u64_scaled(q0.x, q0.y), lenp), abd), lut, thrA);
+      const int b1 = slot_of_age(__dadd_rn(__dmul_rn(u64_scaled(q0.z, q0.w), lenp), abd), lut, thrA);
+      // per-row counts: one byte per age bin at its count slot (neighbouring bins in different words);
+      // shared-memory atomics resolve lanes that hit the same word (at most 100 per byte: no carry).
+      // Bin 185 (age out of range) is counted like any other and reported by k_replay.
+      atomicAdd(&myrow[b0 >> 2], 1u << (8 * (b0 & 3)));
+      atomicAdd(&myrow[b1 >> 2], 1u << (8 * (b1 & 3)));
+      if (has1) {
+        const int b2 = slot_of_age(__dadd_rn(__dmul_rn(u64_scaled(q1.x, q1.y), lenp), abd), lut, thrA);
+        const int b3 = slot_of_age(__dadd_rn(__dmul_rn(u64_scaled(q1.z, q1.w), lenp), abd), lut, thrA);
+        atomicAdd(&myrow[b2 >> 2], 1u << (8 * (b2 & 3)));
+        atomicAdd(&myrow[b3 >> 2], 1u << (8 * (b3 & 3)));
       }
       __syncwarp();
       if (lane < ROW_BYTES / 8) {
         uint64_t* rw = myrows;
-        // byte-wise sum of the four copies (at most 100 per byte: no carries)
-        const uint64_t v = rw[lane] + rw[ROW_BYTES / 8 + lane] + rw[2 * (ROW_BYTES / 8) + lane] + rw[3 * (ROW_BYTES / 8) + lane];
-        rw[lane] = 0; rw[ROW_BYTES / 8 + lane] = 0; rw[2 * (ROW_BYTES / 8) + lane] = 0; rw[3 * (ROW_BYTES / 8) + lane] = 0;
+        uint64_t v = 0;                                          // byte-wise sum of the copies
+#pragma unroll
+        for (int c = 0; c < ROW_COPIES; c++) { v += rw[c * ROW_STRIDE64 + lane]; rw[c * ROW_STRIDE64 + lane] = 0; }
         ((uint64_t*)(cnt + (size_t)r * ROW_BYTES))[lane] = v;
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[slot]);
   }
-  if (overflow) misc[3] = 1;
 }
 
 constexpr int RP_SITES = 32;   // rows per replay stage
@@ -430,7 +445,7 @@ struct __align__(16) ReplayStage {
 // for bit as the sequential loop of coal.cpp:2259-2295 leaves them.  blockIdx.y: 0 shared, 1 not shared.
 __global__ void __launch_bounds__(RP_THREADS)
 k_replay(const int64_t* __restrict__ blk_rank_start, const uint8_t* __restrict__ cnt, const double4* __restrict__ hdr_g,
-         double* __restrict__ out_f, int64_t* __restrict__ out_n, long long* prof)
+         double* __restrict__ out_f, int64_t* __restrict__ out_n, int64_t* misc, long long* prof)
 {
   __shared__ ReplayStage st[RP_STAGES];
   __shared__ __align__(8) uint64_t full[RP_STAGES], empty[RP_STAGES];
@@ -471,7 +486,7 @@ k_replay(const int64_t* __restrict__ blk_rank_start, const uint8_t* __restrict__
     mbar_wait(&full[slot], (it / RP_STAGES) & 1);
     tw += clock64() - a0;
     const int nrow = (int)min((int64_t)RP_SITES, r1 - (r0 + (int64_t)it * RP_SITES));
-    const uint8_t* cp = &st[slot].cnt[0][0] + bin;
+    const uint8_t* cp = &st[slot].cnt[0][0] + (bin < ROW_SLOTS ? slot_of_bin(bin) : bin);  // interleaved count slots
     const double* hp = (const double*)&st[slot].hdr[0];
     // Groups of RP_GROUP rows.  While acc stays inside one binade [2^E, 2^(E+1)) every rounded
     // addition of w moves it by d(w) = w rounded to a multiple of ulp(acc) -- a function of w and
@@ -491,6 +506,7 @@ k_replay(const int64_t* __restrict__ blk_rank_start, const uint8_t* __restrict__
         const int ct = ((which == 1) | (yb > 0)) ? c : 0;  // rows with age_begin <= 0 add nothing to shared
         tally += ct;
         cs[i] = (__double_as_longlong(w) << 1) != 0 ? ct : 0;  // x + 0.0 == x: c no-op additions
+        if (bin == NBINS && c) misc[3] = 1;  // a sample fell into bin 185: the reference is out of bounds there
         ws[i] = w;
         any |= cs[i];
       }
@@ -654,8 +670,8 @@ int run_sample(colate_handle* h, const uint32_t* stream_local, int)
   h->launches += 1;
   CK(cudaEventRecord(h->ev[3], s));
   if (nu > 0) {
-    const size_t smem = sizeof(SampleStage) * SAMPLE_STAGES + 2 * SAMPLE_STAGES * 8 + (NBINS + 2) * 8 + 2 * ((LUT_N + 15) & ~15) +
-                        (size_t)SW * 4 * ROW_BYTES;
+    const size_t smem = sizeof(SampleStage) * SAMPLE_STAGES + 2 * SAMPLE_STAGES * 8 + 192 * 8 + 2 * ((LUT_N + 15) & ~15) +
+                        (size_t)SW * ROW_COPIES * ROW_STRIDE64 * 8;
     CK(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_stage = (nu + SW - 1) / SW;
     int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / (smem + 1024)));
@@ -674,7 +690,7 @@ int run_sample(colate_handle* h, const uint32_t* stream_local, int)
       prof = h->d_prof.as<long long>();
     }
     k_replay<<<dim3(nb, 2), RP_THREADS, 0, s>>>(h->blk_rank_start.as<int64_t>(), h->u_cnt.as<uint8_t>(), h->u_hdr.as<double4>(),
-                                                h->out_f.as<double>(), h->out_n.as<int64_t>(), prof);
+                                                h->out_f.as<double>(), h->out_n.as<int64_t>(), h->misc.as<int64_t>(), prof);
     if (prof) {
       std::vector<long long> hp((size_t)nb * 2 * 16);
       CK(cudaMemcpyAsync(hp.data(), prof, hp.size() * 8, cudaMemcpyDeviceToHost, s));
