@@ -347,10 +347,14 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     sample_bytes = 800.0 * n_used
+    # DRAM traffic of one k_sample launch from the ncu --set full capture of this workload
+    # (profiles/r01_ncu_k_sample_full.md: dram__bytes_read.sum + dram__bytes_write.sum = 1.2273 GB at
+    # 1,209,943 used rows); it scales with the used rows (832 B read + 192 B written each)
+    traffic = 1.2273e9 * n_used / 1209943.0
     ach = sample_bytes / (t_stage1["sample_ms"] * 1e-3) / 1e9
     stage_bytes = 40.0 * rows + 800.0 * n_used
     roofline = {"bound": "hbm", "kernel": "k_sample (per-mutation Monte-Carlo age binning)", "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": "ncu --set full, profiles/r01_ncu_k_sample_full.md", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": sample_bytes, "launch_ms": t_stage1["sample_ms"],
                 "stage1_all_kernels": {"bytes": stage_bytes, "ms": t_stage1["total_ms"],
                                        "gbs": stage_bytes / (t_stage1["total_ms"] * 1e-3) / 1e9,
