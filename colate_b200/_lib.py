@@ -81,6 +81,7 @@ TEST_HOOKS = {
     "colate_test_charpoly_terms": (C.c_int, [i32, C.c_int]),
     "colate_test_jump_window_host": (C.c_int, [u32, C.c_int, u32]),
     "colate_test_bin_thresholds": (C.c_int, [f64]),
+    "colate_test_add_repeated": (C.c_double, [C.c_double, C.c_double, C.c_int]),
     "colate_test_libm": (C.c_int, [VP, C.c_int, C.c_int, f64, f64]),
     "colate_test_mt_stream": (C.c_int, [VP, u32, C.c_int64, C.c_int64, C.c_int, u32]),
 }

@@ -2,6 +2,7 @@
 // exact bin thresholds, the per-row filter, the chromosome seek emulation, ages / epoch
 // grid, and the readers / writers of the reference's file formats.
 #include "internal.h"
+#include "exact_sum.cuh"
 
 #include <zlib.h>
 
@@ -132,6 +133,7 @@ void colate_age_bins(double* age_bin)
 }
 
 int colate_test_bin_thresholds(double* thr10) { return bin_thresholds(thr10) ? 0 : 1; }
+double colate_test_add_repeated(double acc, double w, int c) { return exsum::add_repeated(acc, w, c); }
 
 uint32_t colate_site_meta(int flipped, int n_branch, float age_begin, float age_end, const char* mutation_type)
 {

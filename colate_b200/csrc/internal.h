@@ -58,6 +58,7 @@ extern "C" {
 int colate_test_charpoly_terms(int* out, int cap);
 int colate_test_jump_window_host(const uint32_t* w, int q, uint32_t* out);
 int colate_test_bin_thresholds(double* thr10);
+double colate_test_add_repeated(double acc, double w, int c);
 int colate_test_libm(colate_handle* h, int which, int n, const double* x, double* y);
 int colate_test_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int64_t n_words,
                           int log2_chunk_sites, uint32_t* out);

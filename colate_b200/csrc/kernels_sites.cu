@@ -201,7 +201,7 @@ __global__ void k_chr(int n_chr, const int64_t* __restrict__ site_off, const int
 }
 
 // used rows -> dense records in rank order:
-//   hdr[r]  = {(age_end - age_begin) * 2^-64, age_begin, weight into shared, weight into notshared} (fp64 x4)
+//   hdr[r]  = {(age_end - age_begin) * 2^-64, age_begin, weight into shared (-0.0: none), weight into notshared} (fp64 x4)
 //   e_b2/e_ws/e_wn[r] = bin and weights of the row's single "emp" contribution (255 = none)
 //   u_blk[r] = genomic block (index local to this handle)
 __global__ void k_compact(int64_t n_site, int n_chr, const int64_t* __restrict__ site_off, const int32_t* __restrict__ pos,
@@ -237,7 +237,9 @@ __global__ void k_compact(int64_t n_site, int n_chr, const int64_t* __restrict__
   const double den = __dmul_rn((double)nr, 100.0);
   // .x = (age_end - age_begin) * 2^-64: the sampling kernel multiplies it with the 64-bit integer
   // x2:x1 converted once (exact power-of-two scaling, same rounding as U * (age_end - age_begin))
-  hdr[r] = make_double4(__dmul_rn(__dsub_rn((double)e, abd), 0x1p-64), abd, __ddiv_rn(num_s, den), __ddiv_rn(num_n, den));
+  // .z is -0.0 for rows with age_begin <= 0: they add nothing to the shared histogram (coal.cpp:2259)
+  hdr[r] = make_double4(__dmul_rn(__dsub_rn((double)e, abd), 0x1p-64), abd, abd > 0.0 ? __ddiv_rn(num_s, den) : -0.0,
+                        __ddiv_rn(num_n, den));
   uint8_t b2 = 255;
   double ws = 0.0, wn = 0.0;
   if (abd <= 0.0) {  // coal.cpp:2247-2256 with age == 0
@@ -290,6 +292,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one lane waits (suspended by the hardware, woken by the phase change), the warp follows: keeps
+// 20-odd idle warps from hammering the barrier unit while a few warps work
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane)
+{
+  if (lane == 0) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(100000u) : "memory");
+  }
+  __syncwarp();
 }
 // global -> shared bulk async copy (TMA engine, SASS UBLKCP), completion counted on `bar`
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
@@ -430,128 +447,147 @@ k_sample(int64_t n_used, const uint32_t* __restrict__ stream, const double4* __r
   }
 }
 
-constexpr int RP_SITES = 32;   // rows per replay stage
+constexpr int RP_SITES = 32;    // rows per replay stage
 constexpr int RP_STAGES = 4;
-constexpr int RP_GROUP = 8;    // rows collapsed into one exact update
-constexpr int RP_THREADS = 224;  // 6 consumer warps (192 >= 185 bins) + 1 producer warp
+constexpr int RP_ROWS = 8;      // rows collapsed into one exact update
+constexpr int RP_RANGES = 6;    // consumer warps: 32-bin ranges (192 >= 185 bins)
+constexpr int RP_THREADS = (RP_RANGES + 1) * 32;   // + 1 producer warp
 struct __align__(16) ReplayStage {
   uint8_t cnt[RP_SITES][ROW_BYTES];
   double4 hdr[RP_SITES];
 };
 
+// one collapsed step of the slow path: acc + c * d(w) when that is what c rounded additions give
+__device__ __forceinline__ double replay_row(double acc, double w, int c)
+{
+  const int E = __double2hiint(acc) >> 20;
+  const double M = __hiloint2double((E << 20) | 0x80000, 0);
+  const double d = __dsub_rn(__dadd_rn(w, M), M);
+  const double err = __dsub_rn(w, d);
+  const double t = __fma_rn((double)c, d, acc);
+  const bool ok = (E > 54) & (E < 0x7fe) & (fabs(err) != __hiloint2double((E - 53) << 20, 0)) &
+                  (__double2hiint(w) < ((E - 1) << 20)) & ((__double2hiint(t) >> 20) == E);
+  return ok ? t : exsum::add_repeated(acc, w, c);
+}
+
 // Exact replay: for every genomic block and both histograms, thread = age bin walks the block's
 // used rows IN ORDER and adds the row's weight once per sample that fell into the bin, with the
-// reference's rounding (exact_sum.cuh), so age_shared_count / age_notshared_count come out bit
-// for bit as the sequential loop of coal.cpp:2259-2295 leaves them.  blockIdx.y: 0 shared, 1 not shared.
-__global__ void __launch_bounds__(RP_THREADS)
-k_replay(const int64_t* __restrict__ blk_rank_start, const uint8_t* __restrict__ cnt, const double4* __restrict__ hdr_g,
-         double* __restrict__ out_f, int64_t* __restrict__ out_n, int64_t* misc, long long* prof)
+// reference's rounding, so age_shared_count / age_notshared_count come out bit for bit as the
+// sequential loop of coal.cpp:2259-2295 leaves them.
+//
+// While the sum stays inside one binade [2^E, 2^(E+1)) every rounded addition of w moves it by
+// d(w) = w rounded to a multiple of ulp(acc) -- a function of w and E only -- and all these moves
+// are exact, so a run of RP_ROWS rows collapses to acc += sum(count * d(w)): no serial dependency
+// per row.  A run that leaves the binade, meets a rounding tie or a weight too large for the
+// shortcut is redone row by row (replay_row / exact_sum.cuh).
+// blockIdx.y: 0 shared, 1 not shared.  hdr.z carries -0.0 for rows that add nothing to shared.
+template <int WHICH>
+__device__ __forceinline__ void replay_body(ReplayStage* st, uint64_t* full, uint64_t* empty,
+                                            const int64_t* __restrict__ blk_rank_start, const uint8_t* __restrict__ cnt,
+                                            const double4* __restrict__ hdr_g, double* __restrict__ out_f,
+                                            int64_t* __restrict__ out_n, int64_t* misc)
 {
-  __shared__ ReplayStage st[RP_STAGES];
-  __shared__ __align__(8) uint64_t full[RP_STAGES], empty[RP_STAGES];
-  const int blk = blockIdx.x, which = blockIdx.y;
+  const int blk = blockIdx.x;
   const int64_t r0 = blk_rank_start[blk], r1 = blk_rank_start[blk + 1];
   const int n_stage = (int)((r1 - r0 + RP_SITES - 1) / RP_SITES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < RP_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 6); }
+    for (int i = 0; i < RP_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], RP_RANGES); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  long long tw = 0, tstart = clock64();
-  if (warp == 6) {
+  if (warp == RP_RANGES) {
     if (lane == 0) {
       for (int it = 0; it < n_stage; it++) {
         const int slot = it % RP_STAGES;
-        long long a0 = clock64();
         mbar_wait(&empty[slot], ((it / RP_STAGES) & 1) ^ 1);
-        tw += clock64() - a0;
         const int64_t s0 = r0 + (int64_t)it * RP_SITES;
         const int nrow = (int)min((int64_t)RP_SITES, r1 - s0);
         mbar_expect_tx(&full[slot], (uint32_t)nrow * (ROW_BYTES + 32));
         bulk_g2s(&st[slot].cnt[0][0], cnt + (size_t)s0 * ROW_BYTES, (uint32_t)nrow * ROW_BYTES, &full[slot]);
         bulk_g2s(&st[slot].hdr[0], hdr_g + s0, (uint32_t)nrow * 32, &full[slot]);
       }
-      if (prof) { prof[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + 6] = tw; }
     }
     return;
   }
-  const int bin = threadIdx.x;  // 0..191
+  const int bin = threadIdx.x;                                    // 0..191
+  const int cslot = bin < ROW_SLOTS ? slot_of_bin(bin) : bin;     // interleaved count slots (bytes 188..191 stay 0)
   double acc = 0.0;
-  int64_t tally = 0;
-  int n_any = 0, n_fb = 0;
+  uint32_t tally = 0;
+  bool overflow = false;
   for (int it = 0; it < n_stage; it++) {
     const int slot = it % RP_STAGES;
-    long long a0 = clock64();
     mbar_wait(&full[slot], (it / RP_STAGES) & 1);
-    tw += clock64() - a0;
     const int nrow = (int)min((int64_t)RP_SITES, r1 - (r0 + (int64_t)it * RP_SITES));
-    const uint8_t* cp = &st[slot].cnt[0][0] + (bin < ROW_SLOTS ? slot_of_bin(bin) : bin);  // interleaved count slots
-    const double* hp = (const double*)&st[slot].hdr[0];
-    // Groups of RP_GROUP rows.  While acc stays inside one binade [2^E, 2^(E+1)) every rounded
-    // addition of w moves it by d(w) = w rounded to a multiple of ulp(acc) -- a function of w and
-    // E only -- and all these moves are exact, so the group collapses to acc += sum(c * d(w)):
-    // no serial dependency per row.  A group that leaves the binade, meets a rounding tie or has
-    // acc outside the normal range is redone row by row with exact_sum.cuh.
-    for (int g0 = 0; g0 < nrow; g0 += RP_GROUP) {
-      int cs[RP_GROUP];
-      double ws[RP_GROUP];
-      int any = 0;
-#pragma unroll
-      for (int i = 0; i < RP_GROUP; i++) {
-        const int sidx = min(g0 + i, RP_SITES - 1);
-        const int c = (g0 + i < nrow) ? cp[sidx * ROW_BYTES] : 0;
-        const double w = hp[4 * sidx + 2 + which];
-        const long long yb = __double_as_longlong(hp[4 * sidx + 1]);
-        const int ct = ((which == 1) | (yb > 0)) ? c : 0;  // rows with age_begin <= 0 add nothing to shared
-        tally += ct;
-        cs[i] = (__double_as_longlong(w) << 1) != 0 ? ct : 0;  // x + 0.0 == x: c no-op additions
-        if (bin == NBINS && c) misc[3] = 1;  // a sample fell into bin 185: the reference is out of bounds there
-        ws[i] = w;
-        any |= cs[i];
-      }
-      if (__any_sync(0xffffffffu, any != 0)) {
-        n_any++;
-        const int E = __double2hiint(acc) >> 20;                         // biased exponent (acc >= 0)
-        const double M = __hiloint2double((E << 20) | 0x80000, 0);       // 1.5 * 2^E: ulp(M) == ulp(acc)
-        const double hu = __hiloint2double((E - 53) << 20, 0);           // ulp(acc) / 2
-        const double wmax = __hiloint2double((E - 1) << 20, 0);          // w must stay below 2^(E-1)
-        double tot = 0.0;
-        int bad = (E <= 54) | (E >= 0x7fe);
-#pragma unroll
-        for (int i = 0; i < RP_GROUP; i++) {
-          const double d = __dsub_rn(__dadd_rn(ws[i], M), M);
-          const double err = __dsub_rn(ws[i], d);
-          bad |= (cs[i] != 0) & ((fabs(err) == hu) | !(ws[i] < wmax) | (ws[i] < 0.0));
-          tot = __fma_rn((double)cs[i], d, tot);
-        }
-        const double accn = __dadd_rn(acc, tot);
-        bad |= (__double2hiint(accn) >> 20) != E;
-        bad &= (any != 0);
-        if (__any_sync(0xffffffffu, bad)) {
-          n_fb++;
-          if (bad) {
+    const uint8_t* cp = &st[slot].cnt[0][0] + cslot;
+    const double* hp = (const double*)&st[slot].hdr[0] + 2 + WHICH;
+    // rows that exist and add to this histogram (-0.0 weight: nothing to add), one bit per row
+    uint32_t live = nrow >= 32 ? 0xffffffffu : (1u << nrow) - 1u;
+    if (WHICH == 0) live &= __ballot_sync(0xffffffffu, ((const int*)(hp + 4 * lane))[1] >= 0);
 #pragma unroll 1
-            for (int i = 0; i < RP_GROUP; i++)
-              if (cs[i]) acc = exsum::add_repeated(acc, ws[i], cs[i]);
-          } else if (any) acc = accn;
-        } else if (any) acc = accn;
+    for (int g0 = 0; g0 < nrow; g0 += RP_ROWS) {
+      // this bin's counts in the run's rows, one byte each (<= 100)
+      uint32_t cs_lo = 0, cs_hi = 0;
+#pragma unroll
+      for (int i = 0; i < RP_ROWS; i++) {
+        const uint32_t c = cp[(g0 + i) * ROW_BYTES];
+        if (i < 4) cs_lo |= c << (8 * i); else cs_hi |= c << (8 * (i - 4));
       }
+      const uint32_t lv = live >> g0;
+      cs_lo &= (((lv & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu;        // bit i -> byte i
+      cs_hi &= ((((lv >> 4) & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu;
+      if (WHICH == 1) overflow |= (bin == NBINS) & ((cs_lo | cs_hi) != 0);   // a sample in bin 185: out of bounds in the reference
+      tally += __dp4a(cs_lo, 0x01010101u, __dp4a(cs_hi, 0x01010101u, 0u));
+      const bool any = (cs_lo | cs_hi) != 0;
+      if (!__any_sync(0xffffffffu, any)) continue;
+      const int E = __double2hiint(acc) >> 20;                         // biased exponent (acc >= 0)
+      const double M = __hiloint2double((E << 20) | 0x80000, 0);       // 1.5 * 2^E: ulp(M) == ulp(acc)
+      const double hu = __hiloint2double((E - 53) << 20, 0);           // ulp(acc) / 2
+      const int wmax_hi = (E - 1) << 20;                               // w must stay below 2^(E-1)
+      bool bad = (E <= 54) | (E >= 0x7fe);
+      double t0 = 0.0, t1 = 0.0;                                       // exact sums: any order
+#pragma unroll
+      for (int i = 0; i < RP_ROWS; i++) {
+        const int c = ((i < 4 ? cs_lo : cs_hi) >> (8 * (i & 3))) & 0xff;
+        const double w = hp[4 * (g0 + i)];
+        const double d = __dsub_rn(__dadd_rn(w, M), M);
+        const double err = __dsub_rn(w, d);
+        bad |= (c != 0) & ((fabs(err) == hu) | (__double2hiint(w) >= wmax_hi));
+        if (i & 1) t1 = __fma_rn((double)c, d, t1); else t0 = __fma_rn((double)c, d, t0);
+      }
+      const double accn = __dadd_rn(acc, __dadd_rn(t0, t1));
+      bad |= (__double2hiint(accn) >> 20) != E;
+      bad &= any;
+      if (__any_sync(0xffffffffu, bad)) {
+        if (bad) {
+#pragma unroll 1
+          for (int r = g0; r < min(nrow, g0 + RP_ROWS); r++) {
+            const double w = hp[4 * r];
+            const int c = cp[r * ROW_BYTES];
+            if (c != 0 && (__double_as_longlong(w) << 1) != 0 && __double2hiint(w) >= 0)   // x + 0.0 == x
+              acc = replay_row(acc, w, c);
+          }
+        } else if (any) acc = accn;
+      } else if (any) acc = accn;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[slot]);
   }
-  if (prof && lane == 0) {
-    long long* p = prof + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
-    p[warp] = tw;
-    if (warp == 0) { p[7] = clock64() - tstart; p[8] = n_stage; }
-    if (warp == 3) { p[9] = n_any; p[10] = n_fb; }
-    if (warp == 1) { p[11] = n_any; p[12] = n_fb; }
-  }
+  if (overflow) misc[3] = 1;
   if (bin < NBINS) {
-    out_f[((size_t)blk * 4 + which) * NBINS + bin] = acc;
-    out_n[((size_t)blk * 3 + which) * NBINS + bin] = tally;
+    out_f[((size_t)blk * 4 + WHICH) * NBINS + bin] = acc;
+    out_n[((size_t)blk * 3 + WHICH) * NBINS + bin] = tally;
   }
+}
+
+__global__ void __launch_bounds__(RP_THREADS)
+k_replay(const int64_t* __restrict__ blk_rank_start, const uint8_t* __restrict__ cnt, const double4* __restrict__ hdr_g,
+         double* __restrict__ out_f, int64_t* __restrict__ out_n, int64_t* misc)
+{
+  __shared__ ReplayStage st[RP_STAGES];
+  __shared__ __align__(8) uint64_t full[RP_STAGES], empty[RP_STAGES];
+  if (blockIdx.y == 0) replay_body<0>(st, full, empty, blk_rank_start, cnt, hdr_g, out_f, out_n, misc);
+  else replay_body<1>(st, full, empty, blk_rank_start, cnt, hdr_g, out_f, out_n, misc);
 }
 
 // age_shared_emp / age_notshared_emp row 0 (coal.cpp:2250-2256): one addition per row with
@@ -683,24 +719,8 @@ int run_sample(colate_handle* h, const uint32_t* stream_local, int)
   }
   CK(cudaEventRecord(h->ev[4], s));
   if (nb > 0) {
-    long long* prof = nullptr;
-    if (getenv("COLATE_REPLAY_PROF")) {
-      CK(h->d_prof.ensure((size_t)nb * 2 * 16 * 8));
-      CK(cudaMemsetAsync(h->d_prof.p, 0, (size_t)nb * 2 * 16 * 8, s));
-      prof = h->d_prof.as<long long>();
-    }
     k_replay<<<dim3(nb, 2), RP_THREADS, 0, s>>>(h->blk_rank_start.as<int64_t>(), h->u_cnt.as<uint8_t>(), h->u_hdr.as<double4>(),
-                                                h->out_f.as<double>(), h->out_n.as<int64_t>(), h->misc.as<int64_t>(), prof);
-    if (prof) {
-      std::vector<long long> hp((size_t)nb * 2 * 16);
-      CK(cudaMemcpyAsync(hp.data(), prof, hp.size() * 8, cudaMemcpyDeviceToHost, s));
-      CK(cudaStreamSynchronize(s));
-      for (int i : {0, 1, nb / 2, nb + nb / 2}) {
-        long long* p = hp.data() + (size_t)i * 16;
-        fprintf(stderr, "[k_replay prof cta %d] stages %lld total %lld cyc | full-wait per warp: %lld %lld %lld %lld %lld %lld | producer empty-wait %lld | warp3 groups %lld fallbacks %lld | warp1 groups %lld fallbacks %lld\n", i,
-                p[8], p[7], p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[9], p[10], p[11], p[12]);
-      }
-    }
+                                                h->out_f.as<double>(), h->out_n.as<int64_t>(), h->misc.as<int64_t>());
     k_emp<<<nb, 192, 0, s>>>(h->blk_rank_start.as<int64_t>(), h->u_eb2.as<uint8_t>(), h->u_ews.as<double>(), h->u_ewn.as<double>(),
                              h->out_f.as<double>(), h->out_n.as<int64_t>());
     h->launches += 2;

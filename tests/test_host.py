@@ -101,6 +101,32 @@ def test_bin_thresholds_reproduce_the_bin_index(built):
     assert same(got, want)
 
 
+def test_repeated_rounded_addition_matches_the_plain_loop(built):
+    """exact_sum.cuh (k_replay's slow path): acc += w, c times, each addition rounded (coal.cpp:2269, 2291-2292)."""
+    f = api.lib().colate_test_add_repeated
+    rng = np.random.default_rng(5)
+
+    def plain(acc, w, c):
+        acc = np.float64(acc)
+        for _ in range(c):
+            acc = np.float64(acc + np.float64(w))
+        return float(acc)
+
+    cases = []
+    for _ in range(4000):
+        w = float(rng.integers(0, 3) * rng.integers(0, 40) / (rng.integers(1, 60) * 100.0))   # weights like num / (reads * 100)
+        acc = float(rng.choice([0.0, w, rng.uniform(0, 1e-3), rng.uniform(0, 4), np.exp(rng.uniform(-5, 12))]))
+        cases.append((acc, w, int(rng.integers(1, 101))))
+    for e in range(-6, 14):       # sums that step over a power of two, with and without landing on it
+        top = 2.0 ** e
+        for w in (top / 64, top / 64 * (1 + 2.0 ** -30), 0.3 * top, top / 3, top * 2.0 ** -52, top * 2.0 ** -53, top * 1.5 * 2.0 ** -53):
+            for back in (1, 2, 7, 63, 64, 65):
+                cases.append((float(np.float64(top) - np.float64(back) * np.float64(w)), float(w), 100))
+                cases.append((float(np.nextafter(top, 0)), float(w), 37))
+    for acc, w, c in cases:
+        assert f(acc, w, c) == plain(acc, w, c), (acc, w, c)
+
+
 def test_libm_port_is_this_hosts_libm(built):
     assert api.libm_exact()
 
