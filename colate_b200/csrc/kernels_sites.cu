@@ -580,25 +580,17 @@ __device__ __forceinline__ void replay_body(ReplayStage* st, uint64_t* full, uin
   }
 }
 
-__global__ void __launch_bounds__(RP_THREADS)
-k_replay(const int64_t* __restrict__ blk_rank_start, const uint8_t* __restrict__ cnt, const double4* __restrict__ hdr_g,
-         double* __restrict__ out_f, int64_t* __restrict__ out_n, int64_t* misc)
-{
-  __shared__ ReplayStage st[RP_STAGES];
-  __shared__ __align__(8) uint64_t full[RP_STAGES], empty[RP_STAGES];
-  if (blockIdx.y == 0) replay_body<0>(st, full, empty, blk_rank_start, cnt, hdr_g, out_f, out_n, misc);
-  else replay_body<1>(st, full, empty, blk_rank_start, cnt, hdr_g, out_f, out_n, misc);
-}
-
 // age_shared_emp / age_notshared_emp row 0 (coal.cpp:2250-2256): one addition per row with
-// age_begin <= 0, in row order, thread = age bin.
-__global__ void __launch_bounds__(192)
-k_emp(const int64_t* __restrict__ blk_rank_start, const uint8_t* __restrict__ e_b2, const double* __restrict__ e_ws,
-      const double* __restrict__ e_wn, double* __restrict__ out_f, int64_t* __restrict__ out_n)
+// age_begin <= 0, in row order, thread = age bin.  Runs as the blockIdx.y == 2 slice of k_replay's
+// grid (same launch, other SMs); `scratch` is the CTA's stage storage.
+__device__ __forceinline__ void emp_body(unsigned char* scratch, const int64_t* __restrict__ blk_rank_start,
+                                         const uint8_t* __restrict__ e_b2, const double* __restrict__ e_ws,
+                                         const double* __restrict__ e_wn, double* __restrict__ out_f, int64_t* __restrict__ out_n)
 {
   constexpr int CH = 512;
-  __shared__ uint8_t sb[CH];
-  __shared__ double sws[CH], swn[CH];
+  double* sws = (double*)scratch;
+  double* swn = sws + CH;
+  uint8_t* sb = (uint8_t*)(swn + CH);
   const int blk = blockIdx.x, bin = threadIdx.x;
   const int64_t r0 = blk_rank_start[blk], r1 = blk_rank_start[blk + 1];
   double as = 0.0, an = 0.0;
@@ -616,6 +608,19 @@ k_emp(const int64_t* __restrict__ blk_rank_start, const uint8_t* __restrict__ e_
     out_f[((size_t)blk * 4 + 3) * NBINS + bin] = an;
     out_n[((size_t)blk * 3 + 2) * NBINS + bin] = n;
   }
+}
+
+__global__ void __launch_bounds__(RP_THREADS)
+k_replay(const int64_t* __restrict__ blk_rank_start, const uint8_t* __restrict__ cnt, const double4* __restrict__ hdr_g,
+         const uint8_t* __restrict__ e_b2, const double* __restrict__ e_ws, const double* __restrict__ e_wn,
+         double* __restrict__ out_f, int64_t* __restrict__ out_n, int64_t* misc)
+{
+  __shared__ ReplayStage st[RP_STAGES];
+  __shared__ __align__(8) uint64_t full[RP_STAGES], empty[RP_STAGES];
+  static_assert(sizeof(ReplayStage) * RP_STAGES >= 512 * 17, "emp_body scratch");
+  if (blockIdx.y == 0) replay_body<0>(st, full, empty, blk_rank_start, cnt, hdr_g, out_f, out_n, misc);
+  else if (blockIdx.y == 1) replay_body<1>(st, full, empty, blk_rank_start, cnt, hdr_g, out_f, out_n, misc);
+  else emp_body((unsigned char*)st, blk_rank_start, e_b2, e_ws, e_wn, out_f, out_n);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -719,11 +724,10 @@ int run_sample(colate_handle* h, const uint32_t* stream_local, int)
   }
   CK(cudaEventRecord(h->ev[4], s));
   if (nb > 0) {
-    k_replay<<<dim3(nb, 2), RP_THREADS, 0, s>>>(h->blk_rank_start.as<int64_t>(), h->u_cnt.as<uint8_t>(), h->u_hdr.as<double4>(),
+    k_replay<<<dim3(nb, 3), RP_THREADS, 0, s>>>(h->blk_rank_start.as<int64_t>(), h->u_cnt.as<uint8_t>(), h->u_hdr.as<double4>(),
+                                                h->u_eb2.as<uint8_t>(), h->u_ews.as<double>(), h->u_ewn.as<double>(),
                                                 h->out_f.as<double>(), h->out_n.as<int64_t>(), h->misc.as<int64_t>());
-    k_emp<<<nb, 192, 0, s>>>(h->blk_rank_start.as<int64_t>(), h->u_eb2.as<uint8_t>(), h->u_ews.as<double>(), h->u_ewn.as<double>(),
-                             h->out_f.as<double>(), h->out_n.as<int64_t>());
-    h->launches += 2;
+    h->launches += 1;
   }
   CK(cudaEventRecord(h->ev[5], s));
   CK(cudaGetLastError());
