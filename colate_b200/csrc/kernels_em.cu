@@ -583,6 +583,309 @@ k_em(int E, const double* __restrict__ epochs, const double* __restrict__ rates_
   }
 }
 
+// ---- stage iii, latency mode: ONE replicate spread over a cluster of 8 CTAs ------------------
+// Used when there are too few replicates to fill the GPU (config 2: R = 1).  The per-iteration
+// latency floor is the two sequential logsumexp folds of the E-step (coal_EM.cpp:254-258 and
+// 327-357: ~42 dependent exp + log1p pairs), so everything else is arranged around them:
+//   * CTA r owns the age bins = r (mod csize), both task types; slot = 2 * (bin / csize) + type
+//   * A_ep / B_ep and the fold-free part of every head (special epoch) run side by side
+//   * folds: the not-shared tasks two per warp (adjacent bins: nearly identical branch decisions,
+//     so the lanes rarely diverge), the shared tasks' common prefix chain on its own warp, which
+//     afterwards finishes the 24 shared heads (one logsumexp each) on its lanes
+//   * the two exp() per (task, epoch) are spread over the whole CTA, the serial `integ` recursion
+//     is reduced to one subtraction per epoch, and the rows go out with coalesced stores
+//   * cluster barrier; CTA r gathers columns [r*CW, (r+1)*CW) of all rows from L2 (batched loads),
+//     sums them IN THE REFERENCE'S ORDER (coal.cpp:3704-3733) and writes the totals into every
+//     CTA's shared memory through DSMEM; cluster barrier; redundant M-step.
+// Same operations and operand order as task_shared / task_notshared.
+constexpr int EMS_THREADS = 640;
+constexpr int EMS_FOLD_WARPS = 12;
+constexpr int EMS_TLMAX = 96;
+
+__global__ void __launch_bounds__(EMS_THREADS, 1)
+k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ rates_init,
+           const double* __restrict__ age_bin_g, const double* __restrict__ counts, int max_iter,
+           const uint64_t* __restrict__ exp_tab_g, const uint64_t* __restrict__ log_tab_g, double* scratch,
+           double* __restrict__ rates_out, int32_t* __restrict__ iters_out, double* __restrict__ ll_out, long long* prof_g)
+{
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+  const int rep = blockIdx.x / csize;
+  const int n_task = 2 * NBINS, ncol = 2 * E + 1, RS = 2 * E + 2;
+  const int CW = (ncol + csize - 1) / csize;               // columns summed by one CTA
+  const int nbl = (NBINS + csize - 1) / csize;             // bins of one CTA
+  const int ntl = 2 * nbl;                                 // its task slots
+
+  extern __shared__ double sm[];
+  double* ep = sm;                  // [E]
+  double* rate = ep + E;            // [E]
+  double* Lam = rate + E;           // [E]
+  double* A = Lam + E;              // [E]
+  double* B = A + E;                // [E]
+  double* PL = B + E;               // [E+1]
+  double* tn = PL + E + 1;          // [E]
+  double* td = tn + E;              // [E]
+  double* cand = td + E;            // [E]
+  double* prod = cand + E;          // [E]
+  double* raw = prod + E;           // [ntl][E][2]  exp() of the two log-domain terms
+  double* colbuf = raw + (size_t)ntl * E * 2;              // [n_task][cw] gathered columns; before that [ntl][E] integ
+  uint64_t* etab = (uint64_t*)(colbuf + (size_t)n_task * CW);  // [256]
+  uint64_t* ltab = etab + 256;                                  // [256]
+  __shared__ int stop_flag;
+  __shared__ double ll_s, prev_s, ll_new;
+  __shared__ double h_t[EMS_TLMAX], h_cnt[EMS_TLMAX], h_nc[EMS_TLMAX], h_numt[EMS_TLMAX], h_dent[EMS_TLMAX], h_logl[EMS_TLMAX];
+  __shared__ int h_et[EMS_TLMAX], h_good[EMS_TLMAX];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int e = tid; e < E; e += blockDim.x) { ep[e] = epochs[e]; rate[e] = rates_init[e]; }
+  for (int i = tid; i < 256; i += blockDim.x) { etab[i] = exp_tab_g[i]; ltab[i] = log_tab_g[i]; }
+  if (tid == 0) { stop_flag = 0; ll_s = neg_inf(); }
+  __syncthreads();
+  double* Mrep = scratch + (size_t)rep * 2 * EM_TASKS * RS;
+  if (tid < ntl) {
+    const int b = (tid >> 1) * csize + crank, type = tid & 1;
+    double t = 0.0, cnt = 0.0;
+    if (b < NBINS) { t = age_bin_g[b]; cnt = counts[(size_t)rep * 2 * NBINS + (type ? NBINS : 0) + b]; }
+    h_t[tid] = t;
+    h_cnt[tid] = cnt > 0 ? cnt : 0.0;                      // coal.cpp:3706, 3719: only bins with a positive count
+    h_et[tid] = tint_k(E, ep, t) - 1;
+    h_good[tid] = 0; h_nc[tid] = 0.0; h_numt[tid] = 0.0; h_dent[tid] = 0.0; h_logl[tid] = 0.0;
+    if (b < NBINS && !(cnt > 0))    // rows of inactive tasks stay 0: x + 0.0 == x, so the sums need no test
+      for (int b2 = 0; b2 < 2; b2++)
+        for (int e = 0; e < RS; e++) Mrep[((size_t)b2 * EM_TASKS + 2 * b + type) * RS + e] = 0.0;
+  }
+  EmCtx c{E, ep, rate, A, B, Lam, glm::Tables{etab, ltab}};
+  long long* prof = prof_g ? prof_g + (size_t)blockIdx.x * 8 : nullptr;
+  long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  __syncthreads();
+
+  int iter = 0;
+  for (; iter < max_iter; iter++) {
+    double* M = Mrep + (size_t)(iter & 1) * EM_TASKS * RS;
+    long long t0 = prof ? clock64() : 0, t1;
+    // cumulative hazard, coal_EM.cpp:100-103: products in parallel, then every thread that needs
+    // Lam[e] adds them up in index order (same additions as the serial loop)
+    for (int e = tid + 1; e < E; e += blockDim.x) prod[e] = rate[e - 1] * (ep[e] - ep[e - 1]);
+    __syncthreads();
+    for (int e = tid; e < E; e += blockDim.x) {
+      double l = 0.0;
+      for (int i = 1; i <= e; i++) l = l + prod[i];
+      Lam[e] = l;
+    }
+    __syncthreads();
+    // A_ep / B_ep (threads 0..E-1) next to the fold-free part of the heads (one thread per slot, from warp 2 on)
+    if (tid < E) em_AB(E, ep, rate, Lam, tid, A, B, c.T);
+    else if (tid >= 64 && tid < 64 + ntl && h_cnt[tid - 64] > 0) {
+      const int l = tid - 64, et = h_et[l], k = et + 1;
+      const double t = h_t[l];
+      double num_t, den_t;
+      if ((l & 1) == 0) {
+        shared_special(c, t, et, num_t, den_t);
+      } else {                                             // EM_notshared, coal_EM.cpp:327-357, up to the fold
+        const double r = rate[et], inv = 1.0 / r;
+        const double c1 = Lam[et] + r * (t - ep[et]);
+        const double c2 = c1 + r * (t - t);
+        if (et != E - 1) {
+          const double c3 = c2 + r * (ep[k] - t);
+          if (r > 0) {
+            num_t = lme(-c2, -c3, c.T);
+            den_t = glm::log((t + inv) - (ep[k] + inv) * glm::exp(-c3 + c2, c.T), c.T) - c2;
+          } else { num_t = neg_inf(); den_t = neg_inf(); }
+        } else {
+          num_t = -c2;
+          den_t = glm::log(t + inv, c.T) - c2;
+        }
+      }
+      h_numt[l] = num_t; h_dent[l] = den_t;
+    }
+    __syncthreads();
+    if (prof) { t1 = clock64(); tp[0] += t1 - t0; t0 = t1; }
+    // the folds
+    if (warp < EMS_FOLD_WARPS) {
+      const int fpw = (nbl + EMS_FOLD_WARPS - 1) / EMS_FOLD_WARPS;   // not-shared folds per warp, adjacent bins together
+      const int f = warp * fpw + lane, l = 2 * f + 1;
+      if (lane < fpw && f < nbl && h_cnt[l] > 0) {
+        double nc = h_numt[l];
+        const int et = h_et[l];
+        if (et != E - 1) for (int e = et + 1; e < E; e++) nc = lse(nc, A[e], c.T);
+        const bool good = !bad(nc);
+        h_nc[l] = nc; h_good[l] = good ? 1 : 0; h_logl[l] = h_cnt[l] * (good ? nc : 0.0);
+      }
+    } else if (warp == EMS_FOLD_WARPS) {
+      if (lane == 0) {
+        if (prof && iter == 500 && crank == 0) {   // per-step cycles of the prefix chain, one iteration
+          double nc = 1.0;
+          PL[0] = nc;
+          for (int e = 0; e < E; e++) {
+            const double v = A[e];
+            if (nc == 1.0) nc = v;
+            else {
+              const double hi = (nc > v) ? nc : v, lo = (nc > v) ? v : nc;
+              const long long q0 = clock64();
+              const double x = glm::exp(lo - hi, c.T);
+              const long long q1 = clock64();
+              const double y = glm::log1p(x);
+              const long long q2 = clock64();
+              nc = hi + y;
+              if (e < 56) prof_g[8 * gridDim.x + e] = (q1 - q0) * 100000 + (q2 - q1) + (long long)(x * 1000) * 10000000000ll;
+            }
+            PL[e + 1] = nc;
+          }
+        } else shared_prefix_chain(c, PL);
+      }
+      __syncwarp();
+      for (int j = lane; j < nbl; j += 32) {
+        const int l = 2 * j;
+        if (h_cnt[l] > 0) {
+          const double pl = PL[h_et[l]], num_t = h_numt[l];
+          const double nc = (pl == 1.0) ? num_t : lse(pl, num_t, c.T);
+          const bool good = !bad(nc);
+          h_nc[l] = nc; h_good[l] = good ? 1 : 0; h_logl[l] = h_cnt[l] * (good ? nc : 0.0);
+        }
+      }
+    }
+    __syncthreads();
+    if (prof) { t1 = clock64(); tp[1] += t1 - t0; t0 = t1; }
+    // exp() of the two log-domain terms of every (slot, epoch) pair
+    for (int i = tid; i < ntl * E; i += blockDim.x) {
+      const int l = i / E, e = i - l * E;
+      double xn, xd;
+      if (h_good[l] && task_raw_args((l & 1) == 0, c, h_et[l], e, h_numt[l], h_dent[l], h_nc[l], xn, xd)) {
+        raw[2 * i] = glm::exp(xn, c.T);
+        raw[2 * i + 1] = glm::exp(xd, c.T);
+      }
+    }
+    __syncthreads();
+    if (prof) { t1 = clock64(); tp[2] += t1 - t0; t0 = t1; }
+    // the serial part of a task: integ after epoch e (coal_EM.cpp:266-271, 437-446)
+    double* __restrict__ integ_s = colbuf;
+    if (tid < ntl && h_good[tid]) {
+      const int et = h_et[tid];
+      const int lo = (tid & 1) ? et : 0;
+      const int hi = (tid & 1) ? E - 1 : ((E - 1 < et + 1) ? E - 1 : et + 1);
+      double integ = 1.0;
+      const double* __restrict__ rw = raw + (size_t)tid * E * 2;
+      double* __restrict__ out = integ_s + tid * E;
+#pragma unroll 4
+      for (int e = 0; e < E; e++) {
+        const double ne = (e >= lo && e < hi) ? rw[2 * e] : 0.0;   // x - 0.0 == x outside the task's range
+        if (e >= lo && e < hi) { if (integ > 0.0) integ -= ne; else integ = 0.0; }
+        out[e] = integ;
+      }
+    }
+    __syncthreads();
+    // rows -> the replicate's scratch in L2: {count*num[e] (E), count*denom[e] (E), count*logl}
+    for (int i = tid; i < ntl * E; i += blockDim.x) {
+      const int l = i / E, e = i - l * E;
+      const double cnt = h_cnt[l];
+      if (cnt > 0) {
+        const int et = h_et[l];
+        double ne = 0.0, de = 0.0;
+        if (h_good[l]) {
+          const double integ = integ_s[i];
+          if ((l & 1) == 0) {
+            const int lim = (E - 1 < et + 1) ? E - 1 : et + 1;
+            if (e < lim) {
+              ne = raw[2 * i];
+              de = raw[2 * i + 1];
+              de += -ep[e] * ne + (ep[e + 1] - ep[e]) * integ;
+              if (de < 0.0) de = 0.0;
+            } else if (e == E - 1 && et == E - 1) {
+              ne = raw[2 * i];
+              de = raw[2 * i + 1];
+              de -= ep[e] * ne;
+              if (de < 0.0) de = 0.0;
+            }
+          } else {
+            if (e < et) {
+              de = ep[e + 1] - ep[e];
+            } else {
+              ne = raw[2 * i];
+              if (e < E - 1) {
+                de = raw[2 * i + 1];
+                de += -ep[e] * ne + (ep[e + 1] - ep[e]) * integ;
+              } else {
+                de = raw[2 * i + 1];
+                de -= ep[e] * ne;
+              }
+              if (de < 0.0) de = 0.0;
+            }
+          }
+        }
+        double* Mrow = M + (size_t)(2 * ((l >> 1) * csize + crank) + (l & 1)) * RS;
+        Mrow[e] = cnt * ne;
+        Mrow[E + e] = cnt * de;
+      }
+    }
+    if (tid < ntl && h_cnt[tid] > 0) M[(size_t)(2 * ((tid >> 1) * csize + crank) + (tid & 1)) * RS + 2 * E] = h_logl[tid];
+    if (prof) { t1 = clock64(); tp[6] += t1 - t0; t0 = t1; }
+    cluster.sync();   // release / acquire at cluster scope: the rows are visible to the gathering CTAs (read with ld.cg)
+    if (prof) { t1 = clock64(); tp[3] += t1 - t0; t0 = t1; }
+    // sums over the tasks in the reference's order (bin ascending, shared before not shared)
+    {
+      const int cbeg = crank * CW, cw = max(0, min(ncol, cbeg + CW) - cbeg);
+      constexpr int GB = 8;                                // loads in flight per thread
+      for (int i0 = 0; i0 < n_task * cw; i0 += GB * EMS_THREADS) {
+        double pre[GB];
+#pragma unroll
+        for (int u = 0; u < GB; u++) {
+          const int i = i0 + u * EMS_THREADS + tid;
+          const int j = i / cw, cc = i - j * cw;
+          pre[u] = (i < n_task * cw) ? __ldcg(M + (size_t)j * RS + cbeg + cc) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < GB; u++) {
+          const int i = i0 + u * EMS_THREADS + tid;
+          if (i < n_task * cw) colbuf[i] = pre[u];
+        }
+      }
+      __syncthreads();
+      if (prof) { t1 = clock64(); tp[7] += t1 - t0; t0 = t1; }
+      if (tid < cw) {
+        double acc = 0.0;
+#pragma unroll 10
+        for (int j = 0; j < n_task; j++) acc += colbuf[j * cw + tid];
+        prod[tid] = acc;                                   // prod[] is free until the next iteration
+      }
+      __syncthreads();
+      for (int i = tid; i < cw * csize; i += blockDim.x) { // totals -> every CTA's tn / td / ll (DSMEM)
+        const int r = i / cw, cc = i - r * cw, col = cbeg + cc;
+        const double acc = prod[cc];
+        if (col < E) cluster.map_shared_rank(tn, r)[col] = acc;
+        else if (col < 2 * E) cluster.map_shared_rank(td, r)[col - E] = acc;
+        else cluster.map_shared_rank(&ll_new, r)[0] = acc;
+      }
+      cluster.sync();
+      if (tid == 0) { prev_s = ll_s; ll_s = ll_new; }
+    }
+    __syncthreads();
+    if (prof) { t1 = clock64(); tp[4] += t1 - t0; t0 = t1; }
+    // M-step, coal.cpp:3771-3815 (regularise == 2): rate[e] = num/denom floored at 5e-9; num == 0 ->
+    // copy the (already updated) rate of the previous epoch, or 0 for epoch 0; denom == 0 -> keep
+    for (int e = tid; e < E; e += blockDim.x) {
+      const double n_ = tn[e], d_ = td[e];
+      double r = rate[e];
+      if (n_ != 0 && d_ != 0) { r = n_ / d_; r = (r < 5e-9) ? 5e-9 : r; }
+      cand[e] = r;
+    }
+    __syncthreads();
+    for (int e = tid; e < E; e += blockDim.x) {
+      int s = e;
+      while (s >= 0 && tn[s] == 0) s--;          // nearest epoch at or below e with a non-zero numerator
+      rate[e] = (s >= 0) ? cand[s] : 0.0;
+    }
+    if (tid == 0 && (ll_s / prev_s > 1.0 - 1e-7) && (iter > 1000)) stop_flag = 1;  // coal.cpp:3822
+    __syncthreads();
+    if (prof) { t1 = clock64(); tp[5] += t1 - t0; t0 = t1; }
+    if (stop_flag) break;
+  }
+  if (prof && tid == 0) for (int i = 0; i < 8; i++) prof[i] = tp[i];
+  if (crank == 0) {
+    for (int e = tid; e < E; e += blockDim.x) rates_out[(size_t)rep * E + e] = rate[e];
+    if (tid == 0) { iters_out[rep] = iter; ll_out[rep] = ll_s; }
+  }
+}
+
 // E-step probe: one thread per age, plain stores
 __global__ void k_estep(int shared, int E, const double* __restrict__ epochs, const double* __restrict__ rates,
                         int n_t, const double* __restrict__ tt, const uint64_t* __restrict__ exp_tab_g,
@@ -651,20 +954,31 @@ int run_em(colate_handle* h, int R, int E, int max_iter)
   if (rc) return rc;
   int csize = 1;
   if (const char* e = getenv("COLATE_EM_CLUSTER")) csize = atoi(e);
-  else { while (csize < 8 && R * csize * 2 <= 148) csize *= 2; }
-  if (csize != 1 && csize != 2 && csize != 4 && csize != 8) csize = 1;
-  const size_t smem = sizeof(double) * ((size_t)10 * E + 1 + 2 * EM_STAGE_DOUBLES) + 512 * 8;
-  CK(cudaFuncSetAttribute(k_em, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+  else {
+    while (csize < 8 && R * csize * 2 <= 148) csize *= 2;
+    if (csize == 8 && R * 16 * 2 <= 148) csize = 16;   // non-portable cluster size: one GPC (16-20 SMs) per replicate
+  }
+  if (csize != 1 && csize != 2 && csize != 4 && csize != 8 && csize != 16) csize = 1;
+  // latency mode: one replicate over a cluster of 8 (k_em_split) when its per-CTA tables fit
+  const int nbl = (NBINS + csize - 1) / csize, ntl = 2 * nbl, CW = (2 * E + 1 + csize - 1) / csize;
+  const size_t smem_split = sizeof(double) * ((size_t)10 * E + 1 + (size_t)ntl * E * 2 + (size_t)2 * NBINS * CW) + 512 * 8;
+  const bool split = csize >= 8 && ntl <= EMS_TLMAX && smem_split <= 200 * 1024 && !getenv("COLATE_EM_NOSPLIT");
+  const size_t smem = split ? smem_split : sizeof(double) * ((size_t)10 * E + 1 + 2 * EM_STAGE_DOUBLES) + 512 * 8;
+  if (split) {
+    CK(cudaFuncSetAttribute(k_em_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (csize > 8) CK(cudaFuncSetAttribute(k_em_split, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  }
+  else CK(cudaFuncSetAttribute(k_em, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
   CK(h->d_scratch.ensure((size_t)R * 2 * (2 * E + 2) * EM_TASKS * 8 + 1024));
   long long* prof = nullptr;
   if (getenv("COLATE_EM_PROF")) {
-    CK(h->d_prof.ensure((size_t)R * csize * 8 * 8));
-    CK(cudaMemsetAsync(h->d_prof.p, 0, (size_t)R * csize * 8 * 8, h->stream));
+    CK(h->d_prof.ensure((size_t)R * csize * 8 * 8 + 64 * 8));
+    CK(cudaMemsetAsync(h->d_prof.p, 0, (size_t)R * csize * 8 * 8 + 64 * 8, h->stream));
     prof = h->d_prof.as<long long>();
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(R * csize);
-  cfg.blockDim = dim3(EM_THREADS);
+  cfg.blockDim = dim3(split ? EMS_THREADS : EM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = h->stream;
   cudaLaunchAttribute at[1];
@@ -673,17 +987,31 @@ int run_em(colate_handle* h, int R, int E, int max_iter)
   cfg.attrs = at;
   cfg.numAttrs = 1;
   const uint64_t* tabs = h->libm_tab.as<uint64_t>();
-  CK(cudaLaunchKernelEx(&cfg, k_em, E, (const double*)h->d_epochs.as<double>(), (const double*)h->d_rates.as<double>(),
+  CK(cudaLaunchKernelEx(&cfg, split ? k_em_split : k_em, E, (const double*)h->d_epochs.as<double>(), (const double*)h->d_rates.as<double>(),
                         (const double*)h->d_agebin.as<double>(), (const double*)h->d_counts.as<double>(), max_iter, tabs, tabs + 256,
                         h->d_scratch.as<double>(), h->d_rates.as<double>() + E, h->d_iters.as<int32_t>(), h->d_ll.as<double>(), prof));
   h->launches += 1;
   CK(cudaGetLastError());
   if (prof) {
-    std::vector<long long> hp(8);
-    CK(cudaMemcpyAsync(hp.data(), prof, 64, cudaMemcpyDeviceToHost, h->stream));
+    std::vector<long long> hp(8 * csize);
+    CK(cudaMemcpyAsync(hp.data(), prof, 64 * csize, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    fprintf(stderr, "[k_em prof, CTA 0 thread 0, cycles] AB %lld | folds + tasks %lld (prefix-chain thread %lld, a not-shared task %lld) | cluster.sync %lld | column sums %lld | M-step %lld (csize %d)\n",
-            hp[0], hp[1], hp[6], hp[7], hp[3], hp[4], hp[5], csize);
+    if (split) {
+      std::vector<long long> st(56);
+      CK(cudaMemcpy(st.data(), prof + 8 * (size_t)R * csize, 56 * 8, cudaMemcpyDeviceToHost));
+      fprintf(stderr, "[k_em_split prof] prefix-chain cycles per step at iteration 500:");
+      for (int e = 0; e < std::min(E, 56); e++) fprintf(stderr, " [x=.%03lld exp %lld log1p %lld]", st[e] / 10000000000ll, (st[e] / 100000) % 100000, st[e] % 100000);
+      fprintf(stderr, "\n");
+    }
+    for (int r = 0; r < csize; r++) {
+      const long long* q = hp.data() + 8 * r;
+      if (split)
+        fprintf(stderr, "[k_em_split prof, replicate 0 CTA %d thread 0, cycles] AB + head preludes %lld | folds %lld | raw exps %lld | integ + rows out + fence %lld | cluster.sync %lld | gather %lld | sums + broadcast + sync %lld | M-step %lld\n",
+                r, q[0], q[1], q[2], q[6], q[3], q[7], q[4] - q[7], q[5]);
+      else
+        fprintf(stderr, "[k_em prof, replicate 0 CTA %d thread 0, cycles] AB %lld | folds + tasks %lld (prefix-chain thread %lld, a not-shared task %lld) | cluster.sync %lld | column sums %lld | M-step %lld (csize %d)\n",
+                r, q[0], q[1], q[6], q[7], q[3], q[4], q[5], csize);
+    }
   }
   return 0;
 }
