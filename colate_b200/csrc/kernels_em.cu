@@ -71,12 +71,26 @@ __device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0
 __device__ __forceinline__ bool bad(double x) { return !(fabs(x) < __longlong_as_double(0x7ff0000000000000ull)); }
 
 // coal_EM::logsumexp, coal_EM.cpp:5-31
-__device__ __forceinline__ double lse(double a, double b, const glm::Tables& T)
+__device__ __noinline__ double lse_generic(double a, double b, const glm::Tables& T)
 {
   if (bad(a)) return bad(b) ? neg_inf() : b;
   if (bad(b)) return a;
   const double hi = (a > b) ? a : b, lo = (a > b) ? b : a;   // same value as the two-branch form
   return hi + glm::log1p(glm::exp(lo - hi, T));
+}
+// The same, arranged for the sequential folds (their latency bounds an EM iteration): the common
+// case -- finite operands, exp() on its main path, log1p() on its k = 0 path, i.e. terms between
+// e^-20 and 0.414 of the running sum -- as straight-line code with one rare-case branch at the end.
+// Same operations as the generic path takes for those operands.
+__device__ __forceinline__ double lse(double a, double b, const glm::Tables& T)
+{
+  const double hi = (a > b) ? a : b, lo = (a > b) ? b : a;
+  const double d = lo - hi;
+  const double x = glm::exp_main(d, T);
+  const double y = glm::log1p_k0(x);
+  const bool ok = !bad(a) & !bad(b) & glm::exp_is_main(d) & glm::log1p_is_k0(x);
+  if (ok) return hi + y;
+  return lse_generic(a, b, T);
 }
 // coal_EM::logminusexp, coal_EM.cpp:33-58
 __device__ __forceinline__ double lme(double a, double b, const glm::Tables& T)
@@ -117,6 +131,27 @@ __device__ void em_AB(int E, const double* ep, const double* rate, const double*
     if (r > 0) { A[i] = -Lam[i]; B[i] = glm::log(ep[i] + 1.0 / r, T) - Lam[i]; }
     else { A[i] = neg_inf(); B[i] = neg_inf(); }
   }
+}
+
+// the two halves of em_AB, for callers that need A_ep before B_ep
+__device__ __forceinline__ void em_A(int E, const double* ep, const double* rate, const double* Lam, int i, double* A, const glm::Tables& T)
+{
+  const double r = rate[i];
+  if (i < E - 1) {
+    const double tb = ep[i], te = ep[i + 1];
+    A[i] = (r > 0 && te != 0 && te - tb > 0) ? lme(-Lam[i], -Lam[i + 1], T) : neg_inf();
+  } else A[i] = (r > 0) ? -Lam[i] : neg_inf();
+}
+__device__ __forceinline__ void em_B(int E, const double* ep, const double* rate, const double* Lam, int i, double* B, const glm::Tables& T)
+{
+  const double r = rate[i];
+  if (i < E - 1) {
+    const double tb = ep[i], te = ep[i + 1], inv = 1.0 / r;
+    if (r > 0 && te != 0 && te - tb > 0) {
+      double b = (tb + inv) - (te + inv) * glm::exp(-Lam[i + 1] + Lam[i], T);
+      B[i] = glm::log(b, T) - Lam[i];
+    } else B[i] = neg_inf();
+  } else B[i] = (r > 0) ? glm::log(ep[i] + 1.0 / r, T) - Lam[i] : neg_inf();
 }
 
 // get_tint with age_begin == age_end (coal_EM.cpp:60-95): grid points before the copies of t
@@ -602,6 +637,9 @@ constexpr int EMS_THREADS = 640;
 constexpr int EMS_FOLD_WARPS = 12;
 constexpr int EMS_TLMAX = 96;
 
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
 __global__ void __launch_bounds__(EMS_THREADS, 1)
 k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ rates_init,
            const double* __restrict__ age_bin_g, const double* __restrict__ counts, int max_iter,
@@ -655,8 +693,8 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
         for (int e = 0; e < RS; e++) Mrep[((size_t)b2 * EM_TASKS + 2 * b + type) * RS + e] = 0.0;
   }
   EmCtx c{E, ep, rate, A, B, Lam, glm::Tables{etab, ltab}};
-  long long* prof = prof_g ? prof_g + (size_t)blockIdx.x * 8 : nullptr;
-  long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long* prof = prof_g ? prof_g + (size_t)blockIdx.x * 16 : nullptr;
+  long long tp[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   __syncthreads();
 
   int iter = 0;
@@ -673,34 +711,24 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
       Lam[e] = l;
     }
     __syncthreads();
-    // A_ep / B_ep (threads 0..E-1) next to the fold-free part of the heads (one thread per slot, from warp 2 on)
-    if (tid < E) em_AB(E, ep, rate, Lam, tid, A, B, c.T);
-    else if (tid >= 64 && tid < 64 + ntl && h_cnt[tid - 64] > 0) {
-      const int l = tid - 64, et = h_et[l], k = et + 1;
-      const double t = h_t[l];
-      double num_t, den_t;
-      if ((l & 1) == 0) {
-        shared_special(c, t, et, num_t, den_t);
-      } else {                                             // EM_notshared, coal_EM.cpp:327-357, up to the fold
-        const double r = rate[et], inv = 1.0 / r;
-        const double c1 = Lam[et] + r * (t - ep[et]);
-        const double c2 = c1 + r * (t - t);
-        if (et != E - 1) {
-          const double c3 = c2 + r * (ep[k] - t);
-          if (r > 0) {
-            num_t = lme(-c2, -c3, c.T);
-            den_t = glm::log((t + inv) - (ep[k] + inv) * glm::exp(-c3 + c2, c.T), c.T) - c2;
-          } else { num_t = neg_inf(); den_t = neg_inf(); }
-        } else {
-          num_t = -c2;
-          den_t = glm::log(t + inv, c.T) - c2;
-        }
-      }
-      h_numt[l] = num_t; h_dent[l] = den_t;
+    // what the folds need: A_ep (threads 0..E-1) and the not-shared tasks' own first term (one thread per bin, from warp 2 on)
+    if (tid < E) em_A(E, ep, rate, Lam, tid, A, c.T);
+    else if (tid >= 64 && tid < 64 + nbl && h_cnt[2 * (tid - 64) + 1] > 0) {   // EM_notshared, coal_EM.cpp:327-357, num part
+      const int l = 2 * (tid - 64) + 1, et = h_et[l], k = et + 1;
+      const double t = h_t[l], r = rate[et];
+      const double c1 = Lam[et] + r * (t - ep[et]);
+      const double c2 = c1 + r * (t - t);
+      double num_t;
+      if (et != E - 1) {
+        const double c3 = c2 + r * (ep[k] - t);
+        num_t = (r > 0) ? lme(-c2, -c3, c.T) : neg_inf();
+      } else num_t = -c2;
+      h_numt[l] = num_t;
     }
     __syncthreads();
     if (prof) { t1 = clock64(); tp[0] += t1 - t0; t0 = t1; }
-    // the folds
+    // the folds; the warps without one fill in what only the later phases need (B_ep, the denominator
+    // terms of the not-shared heads, the special epoch of the shared heads)
     if (warp < EMS_FOLD_WARPS) {
       const int fpw = (nbl + EMS_FOLD_WARPS - 1) / EMS_FOLD_WARPS;   // not-shared folds per warp, adjacent bins together
       const int f = warp * fpw + lane, l = 2 * f + 1;
@@ -712,28 +740,8 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
         h_nc[l] = nc; h_good[l] = good ? 1 : 0; h_logl[l] = h_cnt[l] * (good ? nc : 0.0);
       }
     } else if (warp == EMS_FOLD_WARPS) {
-      if (lane == 0) {
-        if (prof && iter == 500 && crank == 0) {   // per-step cycles of the prefix chain, one iteration
-          double nc = 1.0;
-          PL[0] = nc;
-          for (int e = 0; e < E; e++) {
-            const double v = A[e];
-            if (nc == 1.0) nc = v;
-            else {
-              const double hi = (nc > v) ? nc : v, lo = (nc > v) ? v : nc;
-              const long long q0 = clock64();
-              const double x = glm::exp(lo - hi, c.T);
-              const long long q1 = clock64();
-              const double y = glm::log1p(x);
-              const long long q2 = clock64();
-              nc = hi + y;
-              if (e < 56) prof_g[8 * gridDim.x + e] = (q1 - q0) * 100000 + (q2 - q1) + (long long)(x * 1000) * 10000000000ll;
-            }
-            PL[e + 1] = nc;
-          }
-        } else shared_prefix_chain(c, PL);
-      }
-      __syncwarp();
+      if (lane == 0) shared_prefix_chain(c, PL);
+      named_bar_sync(1, EMS_THREADS - EMS_FOLD_WARPS * 32);           // the shared heads' special epochs are in
       for (int j = lane; j < nbl; j += 32) {
         const int l = 2 * j;
         if (h_cnt[l] > 0) {
@@ -743,6 +751,32 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
           h_nc[l] = nc; h_good[l] = good ? 1 : 0; h_logl[l] = h_cnt[l] * (good ? nc : 0.0);
         }
       }
+    } else {
+      const int q = tid - (EMS_FOLD_WARPS + 1) * 32;
+      if (q < E) em_B(E, ep, rate, Lam, q, B, c.T);
+      else if (q < E + nbl) {                                        // EM_notshared, coal_EM.cpp:327-357, denom part
+        const int l = 2 * (q - E) + 1;
+        if (h_cnt[l] > 0) {
+          const int et = h_et[l], k = et + 1;
+          const double t = h_t[l], r = rate[et], inv = 1.0 / r;
+          const double c1 = Lam[et] + r * (t - ep[et]);
+          const double c2 = c1 + r * (t - t);
+          double den_t;
+          if (et != E - 1) {
+            const double c3 = c2 + r * (ep[k] - t);
+            den_t = (r > 0) ? glm::log((t + inv) - (ep[k] + inv) * glm::exp(-c3 + c2, c.T), c.T) - c2 : neg_inf();
+          } else den_t = glm::log(t + inv, c.T) - c2;
+          h_dent[l] = den_t;
+        }
+      } else if (q < E + 2 * nbl) {
+        const int l = 2 * (q - E - nbl);
+        if (h_cnt[l] > 0) {
+          double num_t, den_t;
+          shared_special(c, h_t[l], h_et[l], num_t, den_t);
+          h_numt[l] = num_t; h_dent[l] = den_t;
+        }
+      }
+      named_bar_arrive(1, EMS_THREADS - EMS_FOLD_WARPS * 32);
     }
     __syncthreads();
     if (prof) { t1 = clock64(); tp[1] += t1 - t0; t0 = t1; }
@@ -766,14 +800,20 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
       double integ = 1.0;
       const double* __restrict__ rw = raw + (size_t)tid * E * 2;
       double* __restrict__ out = integ_s + tid * E;
-#pragma unroll 4
-      for (int e = 0; e < E; e++) {
-        const double ne = (e >= lo && e < hi) ? rw[2 * e] : 0.0;   // x - 0.0 == x outside the task's range
-        if (e >= lo && e < hi) { if (integ > 0.0) integ -= ne; else integ = 0.0; }
-        out[e] = integ;
+      for (int e0 = 0; e0 < E; e0 += 8) {   // loads of a chunk first: only the subtractions are serial
+        double nb[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) nb[u] = (e0 + u >= lo && e0 + u < hi) ? rw[2 * (e0 + u)] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int e = e0 + u;
+          if (e >= lo && e < hi) { if (integ > 0.0) integ -= nb[u]; else integ = 0.0; }
+          if (e < E) out[e] = integ;
+        }
       }
     }
     __syncthreads();
+    if (prof) { t1 = clock64(); tp[8] += t1 - t0; t0 = t1; }
     // rows -> the replicate's scratch in L2: {count*num[e] (E), count*denom[e] (E), count*logl}
     for (int i = tid; i < ntl * E; i += blockDim.x) {
       const int l = i / E, e = i - l * E;
@@ -879,7 +919,7 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
     if (prof) { t1 = clock64(); tp[5] += t1 - t0; t0 = t1; }
     if (stop_flag) break;
   }
-  if (prof && tid == 0) for (int i = 0; i < 8; i++) prof[i] = tp[i];
+  if (prof && tid == 0) for (int i = 0; i < 16; i++) prof[i] = tp[i];
   if (crank == 0) {
     for (int e = tid; e < E; e += blockDim.x) rates_out[(size_t)rep * E + e] = rate[e];
     if (tid == 0) { iters_out[rep] = iter; ll_out[rep] = ll_s; }
@@ -962,7 +1002,7 @@ int run_em(colate_handle* h, int R, int E, int max_iter)
   // latency mode: one replicate over a cluster of 8 (k_em_split) when its per-CTA tables fit
   const int nbl = (NBINS + csize - 1) / csize, ntl = 2 * nbl, CW = (2 * E + 1 + csize - 1) / csize;
   const size_t smem_split = sizeof(double) * ((size_t)10 * E + 1 + (size_t)ntl * E * 2 + (size_t)2 * NBINS * CW) + 512 * 8;
-  const bool split = csize >= 8 && ntl <= EMS_TLMAX && smem_split <= 200 * 1024 && !getenv("COLATE_EM_NOSPLIT");
+  const bool split = csize >= 8 && ntl <= EMS_TLMAX && E + 2 * nbl <= EMS_THREADS - (EMS_FOLD_WARPS + 1) * 32 && smem_split <= 200 * 1024 && !getenv("COLATE_EM_NOSPLIT");
   const size_t smem = split ? smem_split : sizeof(double) * ((size_t)10 * E + 1 + 2 * EM_STAGE_DOUBLES) + 512 * 8;
   if (split) {
     CK(cudaFuncSetAttribute(k_em_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -972,8 +1012,8 @@ int run_em(colate_handle* h, int R, int E, int max_iter)
   CK(h->d_scratch.ensure((size_t)R * 2 * (2 * E + 2) * EM_TASKS * 8 + 1024));
   long long* prof = nullptr;
   if (getenv("COLATE_EM_PROF")) {
-    CK(h->d_prof.ensure((size_t)R * csize * 8 * 8 + 64 * 8));
-    CK(cudaMemsetAsync(h->d_prof.p, 0, (size_t)R * csize * 8 * 8 + 64 * 8, h->stream));
+    CK(h->d_prof.ensure((size_t)R * csize * 16 * 8));
+    CK(cudaMemsetAsync(h->d_prof.p, 0, (size_t)R * csize * 16 * 8, h->stream));
     prof = h->d_prof.as<long long>();
   }
   cudaLaunchConfig_t cfg = {};
@@ -993,21 +1033,15 @@ int run_em(colate_handle* h, int R, int E, int max_iter)
   h->launches += 1;
   CK(cudaGetLastError());
   if (prof) {
-    std::vector<long long> hp(8 * csize);
-    CK(cudaMemcpyAsync(hp.data(), prof, 64 * csize, cudaMemcpyDeviceToHost, h->stream));
+    const int ps = split ? 16 : 8;
+    std::vector<long long> hp((size_t)ps * csize);
+    CK(cudaMemcpyAsync(hp.data(), prof, (size_t)ps * 8 * csize, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (split) {
-      std::vector<long long> st(56);
-      CK(cudaMemcpy(st.data(), prof + 8 * (size_t)R * csize, 56 * 8, cudaMemcpyDeviceToHost));
-      fprintf(stderr, "[k_em_split prof] prefix-chain cycles per step at iteration 500:");
-      for (int e = 0; e < std::min(E, 56); e++) fprintf(stderr, " [x=.%03lld exp %lld log1p %lld]", st[e] / 10000000000ll, (st[e] / 100000) % 100000, st[e] % 100000);
-      fprintf(stderr, "\n");
-    }
     for (int r = 0; r < csize; r++) {
-      const long long* q = hp.data() + 8 * r;
+      const long long* q = hp.data() + (size_t)ps * r;
       if (split)
-        fprintf(stderr, "[k_em_split prof, replicate 0 CTA %d thread 0, cycles] AB + head preludes %lld | folds %lld | raw exps %lld | integ + rows out + fence %lld | cluster.sync %lld | gather %lld | sums + broadcast + sync %lld | M-step %lld\n",
-                r, q[0], q[1], q[2], q[6], q[3], q[7], q[4] - q[7], q[5]);
+        fprintf(stderr, "[k_em_split prof, replicate 0 CTA %d thread 0, cycles] A + first terms %lld | folds %lld | raw exps %lld | integ %lld | rows out %lld | cluster.sync %lld | gather %lld | sums + broadcast + sync %lld | M-step %lld\n",
+                r, q[0], q[1], q[2], q[8], q[6], q[3], q[7], q[4] - q[7], q[5]);
       else
         fprintf(stderr, "[k_em prof, replicate 0 CTA %d thread 0, cycles] AB %lld | folds + tasks %lld (prefix-chain thread %lld, a not-shared task %lld) | cluster.sync %lld | column sums %lld | M-step %lld (csize %d)\n",
                 r, q[0], q[1], q[6], q[7], q[3], q[4], q[5], csize);
