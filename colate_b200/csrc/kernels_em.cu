@@ -93,12 +93,28 @@ __device__ __forceinline__ double lse(double a, double b, const glm::Tables& T)
   return lse_generic(a, b, T);
 }
 // coal_EM::logminusexp, coal_EM.cpp:33-58
-__device__ __forceinline__ double lme(double a, double b, const glm::Tables& T)
+__device__ __noinline__ double lme_generic(double a, double b, const glm::Tables& T)
 {
   if (bad(a)) return neg_inf();
   if (bad(b)) return a;
   if (a < b) return neg_inf();
   return a + glm::log1p(-glm::exp(b - a, T));
+}
+__device__ __forceinline__ double lme(double a, double b, const glm::Tables& T)   // straight-line common case, as lse()
+{
+  const double d = b - a;
+  const double x = -glm::exp_main(d, T);
+  const double y = glm::log1p_k0(x);
+  const bool ok = !bad(a) & !bad(b) & !(a < b) & glm::exp_is_main(d) & glm::log1p_is_k0(x);
+  if (ok) return a + y;
+  return lme_generic(a, b, T);
+}
+// exp() with its main path first (one rare-case branch)
+__device__ __forceinline__ double exp_fast(double x, const glm::Tables& T)
+{
+  const double y = glm::exp_main(x, T);
+  if (glm::exp_is_main(x)) return y;
+  return glm::exp(x, T);
 }
 
 struct EmCtx {
@@ -785,8 +801,8 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
       const int l = i / E, e = i - l * E;
       double xn, xd;
       if (h_good[l] && task_raw_args((l & 1) == 0, c, h_et[l], e, h_numt[l], h_dent[l], h_nc[l], xn, xd)) {
-        raw[2 * i] = glm::exp(xn, c.T);
-        raw[2 * i + 1] = glm::exp(xd, c.T);
+        raw[2 * i] = exp_fast(xn, c.T);
+        raw[2 * i + 1] = exp_fast(xd, c.T);
       }
     }
     __syncthreads();
@@ -800,14 +816,15 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
       double integ = 1.0;
       const double* __restrict__ rw = raw + (size_t)tid * E * 2;
       double* __restrict__ out = integ_s + tid * E;
-      for (int e0 = 0; e0 < E; e0 += 8) {   // loads of a chunk first: only the subtractions are serial
+      for (int e0 = 0; e0 < E; e0 += 8) {   // branch-free steps, loads of a chunk first: only the subtractions are serial
         double nb[8];
 #pragma unroll
         for (int u = 0; u < 8; u++) nb[u] = (e0 + u >= lo && e0 + u < hi) ? rw[2 * (e0 + u)] : 0.0;
 #pragma unroll
         for (int u = 0; u < 8; u++) {
           const int e = e0 + u;
-          if (e >= lo && e < hi) { if (integ > 0.0) integ -= nb[u]; else integ = 0.0; }
+          const double stepped = (integ > 0.0) ? integ - nb[u] : 0.0;
+          integ = (e >= lo && e < hi) ? stepped : integ;
           if (e < E) out[e] = integ;
         }
       }
