@@ -682,7 +682,8 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
   double* cand = td + E;            // [E]
   double* prod = cand + E;          // [E]
   double* raw = prod + E;           // [ntl][E][2]  exp() of the two log-domain terms
-  double* colbuf = raw + (size_t)ntl * E * 2;              // [n_task][cw] gathered columns; before that [ntl][E] integ
+  double* integ_s = raw + (size_t)ntl * E * 2;             // [ntl][E]     integ after epoch e
+  double* colbuf = integ_s + (size_t)ntl * E;              // [n_task][CW] columns [crank*CW, ..) of every task's row, pushed by the owners
   uint64_t* etab = (uint64_t*)(colbuf + (size_t)n_task * CW);  // [256]
   uint64_t* ltab = etab + 256;                                  // [256]
   __shared__ int stop_flag;
@@ -695,7 +696,6 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
   for (int i = tid; i < 256; i += blockDim.x) { etab[i] = exp_tab_g[i]; ltab[i] = log_tab_g[i]; }
   if (tid == 0) { stop_flag = 0; ll_s = neg_inf(); }
   __syncthreads();
-  double* Mrep = scratch + (size_t)rep * 2 * EM_TASKS * RS;
   if (tid < ntl) {
     const int b = (tid >> 1) * csize + crank, type = tid & 1;
     double t = 0.0, cnt = 0.0;
@@ -704,18 +704,15 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
     h_cnt[tid] = cnt > 0 ? cnt : 0.0;                      // coal.cpp:3706, 3719: only bins with a positive count
     h_et[tid] = tint_k(E, ep, t) - 1;
     h_good[tid] = 0; h_nc[tid] = 0.0; h_numt[tid] = 0.0; h_dent[tid] = 0.0; h_logl[tid] = 0.0;
-    if (b < NBINS && !(cnt > 0))    // rows of inactive tasks stay 0: x + 0.0 == x, so the sums need no test
-      for (int b2 = 0; b2 < 2; b2++)
-        for (int e = 0; e < RS; e++) Mrep[((size_t)b2 * EM_TASKS + 2 * b + type) * RS + e] = 0.0;
   }
+  for (int i = tid; i < n_task * CW; i += blockDim.x) colbuf[i] = 0.0;   // rows of inactive tasks stay 0: x + 0.0 == x
   EmCtx c{E, ep, rate, A, B, Lam, glm::Tables{etab, ltab}};
   long long* prof = prof_g ? prof_g + (size_t)blockIdx.x * 16 : nullptr;
   long long tp[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  __syncthreads();
+  cluster.sync();   // every column buffer is zeroed before the first remote row arrives
 
   int iter = 0;
   for (; iter < max_iter; iter++) {
-    double* M = Mrep + (size_t)(iter & 1) * EM_TASKS * RS;
     long long t0 = prof ? clock64() : 0, t1;
     // cumulative hazard, coal_EM.cpp:100-103: products in parallel, then every thread that needs
     // Lam[e] adds them up in index order (same additions as the serial loop)
@@ -798,17 +795,22 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
     if (prof) { t1 = clock64(); tp[1] += t1 - t0; t0 = t1; }
     // exp() of the two log-domain terms of every (slot, epoch) pair
     for (int i = tid; i < ntl * E; i += blockDim.x) {
-      const int l = i / E, e = i - l * E;
-      double xn, xd;
-      if (h_good[l] && task_raw_args((l & 1) == 0, c, h_et[l], e, h_numt[l], h_dent[l], h_nc[l], xn, xd)) {
-        raw[2 * i] = exp_fast(xn, c.T);
-        raw[2 * i + 1] = exp_fast(xd, c.T);
+      const int l = i / E, e = i - l * E, et = h_et[l];
+      const bool sh = (l & 1) == 0;
+      const int lim = (E - 1 < et + 1) ? E - 1 : et + 1;
+      const bool need = h_good[l] && (sh ? (e < lim || (e == E - 1 && et == E - 1)) : (e >= et));
+      const bool own = sh ? !(e < et) : (e == et);           // the task's own special-epoch terms instead of A_ep / B_ep
+      if (need) {
+        const double nc = h_nc[l];
+        const double xn = (own ? h_numt[l] : A[e]) - nc, xd = (own ? h_dent[l] : B[e]) - nc;
+        const double yn = glm::exp_main(xn, c.T), yd = glm::exp_main(xd, c.T);
+        if (glm::exp_is_main(xn) & glm::exp_is_main(xd)) { raw[2 * i] = yn; raw[2 * i + 1] = yd; }
+        else { raw[2 * i] = glm::exp(xn, c.T); raw[2 * i + 1] = glm::exp(xd, c.T); }
       }
     }
     __syncthreads();
     if (prof) { t1 = clock64(); tp[2] += t1 - t0; t0 = t1; }
     // the serial part of a task: integ after epoch e (coal_EM.cpp:266-271, 437-446)
-    double* __restrict__ integ_s = colbuf;
     if (tid < ntl && h_good[tid]) {
       const int et = h_et[tid];
       const int lo = (tid & 1) ? et : 0;
@@ -816,22 +818,23 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
       double integ = 1.0;
       const double* __restrict__ rw = raw + (size_t)tid * E * 2;
       double* __restrict__ out = integ_s + tid * E;
-      for (int e0 = 0; e0 < E; e0 += 8) {   // branch-free steps, loads of a chunk first: only the subtractions are serial
+      // Branch-free steps, loads of a chunk first.  Outside [lo, hi) the step subtracts 0.0: before lo
+      // integ is still 1.0, and from hi on the value is not used.
+      for (int e0 = 0; e0 < E; e0 += 8) {
         double nb[8];
 #pragma unroll
         for (int u = 0; u < 8; u++) nb[u] = (e0 + u >= lo && e0 + u < hi) ? rw[2 * (e0 + u)] : 0.0;
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-          const int e = e0 + u;
-          const double stepped = (integ > 0.0) ? integ - nb[u] : 0.0;
-          integ = (e >= lo && e < hi) ? stepped : integ;
-          if (e < E) out[e] = integ;
+          integ = (integ > 0.0) ? integ - nb[u] : 0.0;
+          if (e0 + u < E) out[e0 + u] = integ;
         }
       }
     }
     __syncthreads();
     if (prof) { t1 = clock64(); tp[8] += t1 - t0; t0 = t1; }
-    // rows -> the replicate's scratch in L2: {count*num[e] (E), count*denom[e] (E), count*logl}
+    // rows {count*num[e] (E), count*denom[e] (E), count*logl} -> pushed through distributed shared
+    // memory into the column buffers of the CTAs that sum them
     for (int i = tid; i < ntl * E; i += blockDim.x) {
       const int l = i / E, e = i - l * E;
       const double cnt = h_cnt[l];
@@ -869,39 +872,27 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
             }
           }
         }
-        double* Mrow = M + (size_t)(2 * ((l >> 1) * csize + crank) + (l & 1)) * RS;
-        Mrow[e] = cnt * ne;
-        Mrow[E + e] = cnt * de;
+        const int tk = 2 * ((l >> 1) * csize + crank) + (l & 1);   // row of the task
+        const int r1 = e / CW, r2 = (E + e) / CW;
+        cluster.map_shared_rank(colbuf, r1)[tk * CW + (e - r1 * CW)] = cnt * ne;
+        cluster.map_shared_rank(colbuf, r2)[tk * CW + (E + e - r2 * CW)] = cnt * de;
       }
     }
-    if (tid < ntl && h_cnt[tid] > 0) M[(size_t)(2 * ((tid >> 1) * csize + crank) + (tid & 1)) * RS + 2 * E] = h_logl[tid];
+    if (tid < ntl && h_cnt[tid] > 0) {
+      const int tk = 2 * ((tid >> 1) * csize + crank) + (tid & 1), r = (2 * E) / CW;
+      cluster.map_shared_rank(colbuf, r)[tk * CW + (2 * E - r * CW)] = h_logl[tid];
+    }
     if (prof) { t1 = clock64(); tp[6] += t1 - t0; t0 = t1; }
-    cluster.sync();   // release / acquire at cluster scope: the rows are visible to the gathering CTAs (read with ld.cg)
+    cluster.sync();   // release / acquire at cluster scope: the pushed rows are in place
     if (prof) { t1 = clock64(); tp[3] += t1 - t0; t0 = t1; }
     // sums over the tasks in the reference's order (bin ascending, shared before not shared)
     {
       const int cbeg = crank * CW, cw = max(0, min(ncol, cbeg + CW) - cbeg);
-      constexpr int GB = 8;                                // loads in flight per thread
-      for (int i0 = 0; i0 < n_task * cw; i0 += GB * EMS_THREADS) {
-        double pre[GB];
-#pragma unroll
-        for (int u = 0; u < GB; u++) {
-          const int i = i0 + u * EMS_THREADS + tid;
-          const int j = i / cw, cc = i - j * cw;
-          pre[u] = (i < n_task * cw) ? __ldcg(M + (size_t)j * RS + cbeg + cc) : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < GB; u++) {
-          const int i = i0 + u * EMS_THREADS + tid;
-          if (i < n_task * cw) colbuf[i] = pre[u];
-        }
-      }
-      __syncthreads();
       if (prof) { t1 = clock64(); tp[7] += t1 - t0; t0 = t1; }
       if (tid < cw) {
         double acc = 0.0;
 #pragma unroll 10
-        for (int j = 0; j < n_task; j++) acc += colbuf[j * cw + tid];
+        for (int j = 0; j < n_task; j++) acc += colbuf[j * CW + tid];
         prod[tid] = acc;                                   // prod[] is free until the next iteration
       }
       __syncthreads();
@@ -1018,7 +1009,7 @@ int run_em(colate_handle* h, int R, int E, int max_iter)
   if (csize != 1 && csize != 2 && csize != 4 && csize != 8 && csize != 16) csize = 1;
   // latency mode: one replicate over a cluster of 8 (k_em_split) when its per-CTA tables fit
   const int nbl = (NBINS + csize - 1) / csize, ntl = 2 * nbl, CW = (2 * E + 1 + csize - 1) / csize;
-  const size_t smem_split = sizeof(double) * ((size_t)10 * E + 1 + (size_t)ntl * E * 2 + (size_t)2 * NBINS * CW) + 512 * 8;
+  const size_t smem_split = sizeof(double) * ((size_t)10 * E + 1 + (size_t)ntl * E * 3 + (size_t)2 * NBINS * CW) + 512 * 8;
   const bool split = csize >= 8 && ntl <= EMS_TLMAX && E + 2 * nbl <= EMS_THREADS - (EMS_FOLD_WARPS + 1) * 32 && smem_split <= 200 * 1024 && !getenv("COLATE_EM_NOSPLIT");
   const size_t smem = split ? smem_split : sizeof(double) * ((size_t)10 * E + 1 + 2 * EM_STAGE_DOUBLES) + 512 * 8;
   if (split) {
