@@ -645,14 +645,48 @@ k_em(int E, const double* __restrict__ epochs, const double* __restrict__ rates_
 //     afterwards finishes the 24 shared heads (one logsumexp each) on its lanes
 //   * the two exp() per (task, epoch) are spread over the whole CTA, the serial `integ` recursion
 //     is reduced to one subtraction per epoch, and the rows go out with coalesced stores
-//   * cluster barrier; CTA r gathers columns [r*CW, (r+1)*CW) of all rows from L2 (batched loads),
-//     sums them IN THE REFERENCE'S ORDER (coal.cpp:3704-3733) and writes the totals into every
-//     CTA's shared memory through DSMEM; cluster barrier; redundant M-step.
+//   * rows are pushed with st.async into the column buffers of the CTAs that sum them (CTA r sums
+//     columns [r*CW, (r+1)*CW) IN THE REFERENCE'S ORDER, coal.cpp:3704-3733) and the totals are
+//     broadcast the same way; each destination counts the arriving bytes on an mbarrier
+//     (complete_tx), so nobody waits on a cluster-wide barrier; redundant M-step.
 // Same operations and operand order as task_shared / task_notshared.
 constexpr int EMS_THREADS = 640;
 constexpr int EMS_FOLD_WARPS = 12;
 constexpr int EMS_TLMAX = 96;
 
+// distributed-shared-memory plumbing of k_em_split: remote stores that count their bytes on an mbarrier of
+// the destination CTA (st.async ... complete_tx), so a consumer waits for exactly the data it needs
+// instead of a cluster-wide barrier
+__device__ __forceinline__ uint32_t em_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t em_mapa(uint32_t saddr, int rank)
+{
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void em_st_async(uint32_t raddr, double v, uint32_t rbar)
+{
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(raddr),
+               "l"(__double_as_longlong(v)), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void em_mbar_init(uint64_t* bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(em_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void em_mbar_arm(uint64_t* bar, uint32_t bytes)   // this phase completes once `bytes` have landed
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(em_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void em_mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(em_smem_u32(bar)), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -688,14 +722,24 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
   uint64_t* ltab = etab + 256;                                  // [256]
   __shared__ int stop_flag;
   __shared__ double ll_s, prev_s, ll_new;
+  __shared__ __align__(8) uint64_t bar_rows, bar_tot;      // bytes of pushed rows / of broadcast totals that have landed here
   __shared__ double h_t[EMS_TLMAX], h_cnt[EMS_TLMAX], h_nc[EMS_TLMAX], h_numt[EMS_TLMAX], h_dent[EMS_TLMAX], h_logl[EMS_TLMAX];
   __shared__ int h_et[EMS_TLMAX], h_good[EMS_TLMAX];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int e = tid; e < E; e += blockDim.x) { ep[e] = epochs[e]; rate[e] = rates_init[e]; }
   for (int i = tid; i < 256; i += blockDim.x) { etab[i] = exp_tab_g[i]; ltab[i] = log_tab_g[i]; }
-  if (tid == 0) { stop_flag = 0; ll_s = neg_inf(); }
-  __syncthreads();
+  if (tid == 0) {
+    stop_flag = 0; ll_s = neg_inf();
+    em_mbar_init(&bar_rows, 1); em_mbar_init(&bar_tot, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // tasks with a positive count anywhere in the cluster: each pushes one value per column
+  const int n_active = __syncthreads_count(tid < n_task && counts[(size_t)rep * 2 * NBINS + tid] > 0);
+  const int my_cw = max(0, min(ncol, crank * CW + CW) - crank * CW);
+  const uint32_t bytes_rows = (uint32_t)n_active * my_cw * 8, bytes_tot = (uint32_t)ncol * 8;
+  const uint32_t colbuf_s = em_smem_u32(colbuf), tn_s = em_smem_u32(tn), td_s = em_smem_u32(td), ll_sa = em_smem_u32(&ll_new);
+  const uint32_t bar_rows_s = em_smem_u32(&bar_rows), bar_tot_s = em_smem_u32(&bar_tot);
   if (tid < ntl) {
     const int b = (tid >> 1) * csize + crank, type = tid & 1;
     double t = 0.0, cnt = 0.0;
@@ -709,11 +753,12 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
   EmCtx c{E, ep, rate, A, B, Lam, glm::Tables{etab, ltab}};
   long long* prof = prof_g ? prof_g + (size_t)blockIdx.x * 16 : nullptr;
   long long tp[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  cluster.sync();   // every column buffer is zeroed before the first remote row arrives
+  cluster.sync();   // every column buffer is zeroed and every mbarrier initialised before the first remote row arrives
 
   int iter = 0;
   for (; iter < max_iter; iter++) {
     long long t0 = prof ? clock64() : 0, t1;
+    if (tid == 0) { em_mbar_arm(&bar_rows, bytes_rows); em_mbar_arm(&bar_tot, bytes_tot); }   // this iteration's phases
     // cumulative hazard, coal_EM.cpp:100-103: products in parallel, then every thread that needs
     // Lam[e] adds them up in index order (same additions as the serial loop)
     for (int e = tid + 1; e < E; e += blockDim.x) prod[e] = rate[e - 1] * (ep[e] - ep[e - 1]);
@@ -874,16 +919,17 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
         }
         const int tk = 2 * ((l >> 1) * csize + crank) + (l & 1);   // row of the task
         const int r1 = e / CW, r2 = (E + e) / CW;
-        cluster.map_shared_rank(colbuf, r1)[tk * CW + (e - r1 * CW)] = cnt * ne;
-        cluster.map_shared_rank(colbuf, r2)[tk * CW + (E + e - r2 * CW)] = cnt * de;
+        em_st_async(em_mapa(colbuf_s, r1) + 8u * (tk * CW + (e - r1 * CW)), cnt * ne, em_mapa(bar_rows_s, r1));
+        em_st_async(em_mapa(colbuf_s, r2) + 8u * (tk * CW + (E + e - r2 * CW)), cnt * de, em_mapa(bar_rows_s, r2));
       }
     }
     if (tid < ntl && h_cnt[tid] > 0) {
       const int tk = 2 * ((tid >> 1) * csize + crank) + (tid & 1), r = (2 * E) / CW;
-      cluster.map_shared_rank(colbuf, r)[tk * CW + (2 * E - r * CW)] = h_logl[tid];
+      em_st_async(em_mapa(colbuf_s, r) + 8u * (tk * CW + (2 * E - r * CW)), h_logl[tid], em_mapa(bar_rows_s, r));
     }
     if (prof) { t1 = clock64(); tp[6] += t1 - t0; t0 = t1; }
-    cluster.sync();   // release / acquire at cluster scope: the pushed rows are in place
+    if (warp == 0) em_mbar_wait(&bar_rows, iter & 1);        // all rows of this iteration have landed in colbuf
+    __syncthreads();
     if (prof) { t1 = clock64(); tp[3] += t1 - t0; t0 = t1; }
     // sums over the tasks in the reference's order (bin ascending, shared before not shared)
     {
@@ -899,11 +945,11 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
       for (int i = tid; i < cw * csize; i += blockDim.x) { // totals -> every CTA's tn / td / ll (DSMEM)
         const int r = i / cw, cc = i - r * cw, col = cbeg + cc;
         const double acc = prod[cc];
-        if (col < E) cluster.map_shared_rank(tn, r)[col] = acc;
-        else if (col < 2 * E) cluster.map_shared_rank(td, r)[col - E] = acc;
-        else cluster.map_shared_rank(&ll_new, r)[0] = acc;
+        const uint32_t dst = col < E ? tn_s + 8u * col : col < 2 * E ? td_s + 8u * (col - E) : ll_sa;
+        em_st_async(em_mapa(dst, r), acc, em_mapa(bar_tot_s, r));
       }
-      cluster.sync();
+      if (warp == 0) em_mbar_wait(&bar_tot, iter & 1);       // the totals of all columns have landed here
+      __syncthreads();
       if (tid == 0) { prev_s = ll_s; ll_s = ll_new; }
     }
     __syncthreads();
@@ -928,6 +974,7 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
     if (stop_flag) break;
   }
   if (prof && tid == 0) for (int i = 0; i < 16; i++) prof[i] = tp[i];
+  cluster.sync();   // nobody leaves while a peer may still address its shared memory
   if (crank == 0) {
     for (int e = tid; e < E; e += blockDim.x) rates_out[(size_t)rep * E + e] = rate[e];
     if (tid == 0) { iters_out[rep] = iter; ll_out[rep] = ll_s; }
