@@ -84,10 +84,10 @@ __device__ __noinline__ double lse_generic(double a, double b, const glm::Tables
 // Same operations as the generic path takes for those operands.
 __device__ __forceinline__ double lse(double a, double b, const glm::Tables& T)
 {
-  const double hi = (a > b) ? a : b, lo = (a > b) ? b : a;
-  const double d = lo - hi;
+  const double d = -fabs(a - b);                 // == lo - hi exactly (for a != b), without waiting for the select
   const double x = glm::exp_main(d, T);
   const double y = glm::log1p_k0(x);
+  const double hi = (a > b) ? a : b;
   const bool ok = !bad(a) & !bad(b) & glm::exp_is_main(d) & glm::log1p_is_k0(x);
   if (ok) return hi + y;
   return lse_generic(a, b, T);
@@ -793,12 +793,29 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
       if (lane < fpw && f < nbl && h_cnt[l] > 0) {
         double nc = h_numt[l];
         const int et = h_et[l];
-        if (et != E - 1) for (int e = et + 1; e < E; e++) nc = lse(nc, A[e], c.T);
+        if (et != E - 1) {
+          double v = A[et + 1];
+          for (int e = et + 1; e < E; e++) {               // next term loaded before the step that hides its latency
+            const double vn = A[min(e + 1, E - 1)];
+            nc = lse(nc, v, c.T);
+            v = vn;
+          }
+        }
         const bool good = !bad(nc);
         h_nc[l] = nc; h_good[l] = good ? 1 : 0; h_logl[l] = h_cnt[l] * (good ? nc : 0.0);
       }
     } else if (warp == EMS_FOLD_WARPS) {
-      if (lane == 0) shared_prefix_chain(c, PL);
+      if (lane == 0) {                                     // shared_prefix_chain with the next term prefetched
+        double nc = A[0], v = A[min(1, E - 1)];
+        PL[0] = 1.0;
+        PL[1] = nc;
+        for (int e = 1; e < E; e++) {
+          const double vn = A[min(e + 1, E - 1)];
+          if (nc == 1.0) nc = v; else nc = lse(nc, v, c.T);
+          PL[e + 1] = nc;
+          v = vn;
+        }
+      }
       named_bar_sync(1, EMS_THREADS - EMS_FOLD_WARPS * 32);           // the shared heads' special epochs are in
       for (int j = lane; j < nbl; j += 32) {
         const int l = 2 * j;
@@ -838,25 +855,27 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
     }
     __syncthreads();
     if (prof) { t1 = clock64(); tp[1] += t1 - t0; t0 = t1; }
-    // exp() of the two log-domain terms of every (slot, epoch) pair
-    for (int i = tid; i < ntl * E; i += blockDim.x) {
+    // exp() of the two log-domain terms of every (slot, epoch) pair: first the numerator terms (the
+    // integ recursion needs them), then the denominator terms while the first warp(s) run the recursion
+    auto raw_term = [&](int i, int which) {
       const int l = i / E, e = i - l * E, et = h_et[l];
       const bool sh = (l & 1) == 0;
       const int lim = (E - 1 < et + 1) ? E - 1 : et + 1;
       const bool need = h_good[l] && (sh ? (e < lim || (e == E - 1 && et == E - 1)) : (e >= et));
       const bool own = sh ? !(e < et) : (e == et);           // the task's own special-epoch terms instead of A_ep / B_ep
       if (need) {
-        const double nc = h_nc[l];
-        const double xn = (own ? h_numt[l] : A[e]) - nc, xd = (own ? h_dent[l] : B[e]) - nc;
-        const double yn = glm::exp_main(xn, c.T), yd = glm::exp_main(xd, c.T);
-        if (glm::exp_is_main(xn) & glm::exp_is_main(xd)) { raw[2 * i] = yn; raw[2 * i + 1] = yd; }
-        else { raw[2 * i] = glm::exp(xn, c.T); raw[2 * i + 1] = glm::exp(xd, c.T); }
+        const double x = (which == 0 ? (own ? h_numt[l] : A[e]) : (own ? h_dent[l] : B[e])) - h_nc[l];
+        raw[2 * i + which] = exp_fast(x, c.T);
       }
-    }
+    };
+    for (int i = tid; i < ntl * E; i += blockDim.x) raw_term(i, 0);
     __syncthreads();
     if (prof) { t1 = clock64(); tp[2] += t1 - t0; t0 = t1; }
-    // the serial part of a task: integ after epoch e (coal_EM.cpp:266-271, 437-446)
-    if (tid < ntl && h_good[tid]) {
+    const int iw = ((ntl + 31) >> 5) * 32;                   // threads reserved for the recursion (one per slot)
+    if (tid >= iw) {
+      for (int i = tid - iw; i < ntl * E; i += blockDim.x - iw) raw_term(i, 1);
+    } else if (tid < ntl && h_good[tid]) {
+      // the serial part of a task: integ after epoch e (coal_EM.cpp:266-271, 437-446)
       const int et = h_et[tid];
       const int lo = (tid & 1) ? et : 0;
       const int hi = (tid & 1) ? E - 1 : ((E - 1 < et + 1) ? E - 1 : et + 1);

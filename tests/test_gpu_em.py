@@ -111,9 +111,9 @@ def test_em_rates_and_iterations(handle, bins, age, R):
         assert _same(rates[r], ro) and _same(ll[r], llo)               # ... is met with 0 ulp
 
 
-@pytest.mark.parametrize("cluster", ["1", "2", "4", "8"])
+@pytest.mark.parametrize("cluster", ["1", "2", "4", "8", "16"])
 def test_em_cluster_sizes_bit_identical(handle, cluster, monkeypatch):
-    """A replicate spread over 1, 2, 4 or 8 SMs (thread-block cluster) gives the same bits."""
+    """A replicate spread over 1, 2, 4, 8 or 16 SMs (thread-block cluster) gives the same bits."""
     monkeypatch.setenv("COLATE_EM_CLUSTER", cluster)
     o = _block_stats()
     counts = po.stage2(np.ones((1, o["num_blocks"]), np.int32), o, 0.0)
