@@ -93,3 +93,55 @@ def test_stage1_age_range_error(handle):
     with pytest.raises(api._lib.ColateError) as e:
         handle.stage1(api.mt_seed(1))
     assert e.value.code == -2
+
+
+def test_config2_whole_genome_full_size(handle):
+    """BASELINE.json configs[1] at its full size (22 autosomes, 10,000,000 rows, two ~1x genomes):
+    every block histogram, tally and the generator state bit-exact against the oracle, then the
+    whole path (stage ii + EM to convergence, E = 43) against the oracle's rates."""
+    sites = synth.make_sites(1, synth.rows_for_genome(10_000_000), synth.AUTOSOME_LEN)
+    gt = synth.make_genome(101, sites, 0.7)
+    gr = synth.make_genome(201, sites, 0.7)
+    o = po.stage1(sites, gt, gr, seed=1)
+    handle.load(sites, gt, gr)
+    s1 = handle.stage1(api.mt_seed(1))
+    _compare_stage1(o, s1)
+    assert s1.n_used > 1_000_000 and s1.num_blocks > 100
+    # one tally per sample: 100 draws per used row end up in the not-shared histogram
+    assert int(s1.block_tallies[:, 1].sum()) == 100 * s1.n_used
+    w = api.draw_block_weights(s1.mt_state, 1, s1.num_blocks)
+    counts = handle.stage2_bootstrap(w, s1.block_stats, 0.0)
+    assert np.array_equal(counts, po.stage2(w, o, 0.0))
+    ep, _ = po.epochs_from_bins("3,7,0.1", 0.0, 28.0)
+    init = np.full(len(ep), 1 / 20000.)
+    rates, iters, ll = handle.stage3_em(1, ep, init)          # counts: the device-resident result of stage ii
+    ro, it, llo = po.em_run(ep, init, counts[0])
+    assert iters[0] == it and np.array_equal(rates[0], ro) and ll[0] == llo
+
+
+def test_config4_adna_masks(handle):
+    """BASELINE.json configs[3] shape (aDNA-like: ~0.5x coverage, mostly single reads, P/N masks with
+    40 % / 20 % N in runs, target 7000 years old) on chromosomes 1-3 at the whole-genome row density."""
+    lens = synth.AUTOSOME_LEN[:3]
+    rows = [int(10_000_000 * L / sum(synth.AUTOSOME_LEN)) for L in lens]
+    sites = synth.make_sites(4, rows, lens)
+    gt = synth.make_genome(104, sites, 0.35, mean_extra_reads=0.1)
+    gr = synth.make_genome(204, sites, 0.35, mean_extra_reads=0.1)
+    tm = [synth.make_mask(40 + c, int(L), 0.4) for c, L in enumerate(lens)]
+    rm = [synth.make_mask(50 + c, int(L), 0.2) for c, L in enumerate(lens)]
+    o = po.stage1(sites, gt, gr, seed=1, tmask=tm, rmask=rm)
+    handle.load(sites, gt, gr, tm, rm)
+    s1 = handle.stage1(api.mt_seed(1))
+    _compare_stage1(o, s1)
+    assert s1.n_used > 10_000
+    age = 7000.0 / 28.0   # --target_age 7000 --years_per_gen 28 (coal.cpp:3110-3118)
+    w = api.draw_block_weights(s1.mt_state, 2, s1.num_blocks)
+    counts = handle.stage2_bootstrap(w, s1.block_stats, age)
+    assert np.array_equal(counts, po.stage2(w, o, age))
+    ep, ep_null = po.epochs_from_bins("3,7,0.1", age, 28.0)
+    assert ep_null > 0
+    init = np.full(len(ep), 1 / 20000.)
+    rates, iters, ll = handle.stage3_em(2, ep, init)
+    for r in range(2):
+        ro, it, llo = po.em_run(ep, init, counts[r])
+        assert iters[r] == it and np.array_equal(rates[r], ro) and ll[r] == llo
