@@ -1,0 +1,55 @@
+"""All-pairs driver (BASELINE.json configs[4]: N genomes -> every ordered pair target=i, reference=j, i<j).
+
+The reference is run once per pair (`Colate --mode mut --target_tmp i --reference_tmp j --seed S`); the
+estimator is asymmetric in target / reference (coal.cpp:2198, 2236-2242).  On the device the pairs share
+almost everything:
+  * the mutation SoA is uploaded once, every genome is joined against it once (k_join; the joined
+    columns are cached per genome slot) -- only the per-pair passes (flags, generator stream, sampling,
+    exact replay, stage ii) run per pair;
+  * the EM of ALL pairs runs as one launch in throughput mode (one CTA per pair, 2 CTAs/SM), ~0.3 ms per
+    pair instead of the ~21 ms the latency-mode EM needs for a single pair.
+Results per pair are what `api.mut()` returns for that pair alone (same seed): bit-identical.
+"""
+from __future__ import annotations
+
+import itertools
+import time
+
+import numpy as np
+
+from . import api
+
+
+def all_pairs(handle: api.Handle, n_genomes: int, seed: int, bins: str = "3,7,0.1", pairs=None, target_age=None,
+              reference_age=None, years_per_gen=None, max_iter: int = 100000, em_batch: int = 2048):
+    """Genomes must already sit in slots 0..n_genomes-1 of `handle` (set_sites + set_genome / set_mask).
+    Returns dict(pairs[P,2], epochs[E], rates[P,E], iters[P], ll[P], num_blocks[P], n_used[P], seconds=dict)."""
+    if pairs is None:
+        pairs = list(itertools.combinations(range(n_genomes), 2))
+    pairs = [(int(i), int(j)) for i, j in pairs]
+    for i, j in pairs:
+        if not (0 <= i < n_genomes and 0 <= j < n_genomes and i != j):
+            raise ValueError(f"bad pair ({i}, {j})")
+    age, ypg = api.ages(target_age, reference_age, years_per_gen)
+    epochs, ep_null = api.epochs_from_bins(bins, age, ypg)
+    init = np.full(epochs.shape[0], 1.0 / 20000.0)
+    P = len(pairs)
+    counts = np.zeros((P, 2, api.NBINS))
+    nb = np.zeros(P, dtype=np.int32)
+    nu = np.zeros(P, dtype=np.int64)
+    t0 = time.perf_counter()
+    for p, (i, j) in enumerate(pairs):
+        s1 = handle.stage1(api.mt_seed(seed), target_slot=i, reference_slot=j)      # the reference reseeds per run
+        w = api.draw_block_weights(s1.mt_state, 1, s1.num_blocks)
+        counts[p] = handle.stage2_bootstrap(w, s1.block_stats, age)[0]
+        nb[p], nu[p] = s1.num_blocks, s1.n_used
+    t1 = time.perf_counter()
+    rates = np.zeros((P, epochs.shape[0]))
+    iters = np.zeros(P, dtype=np.int32)
+    ll = np.zeros(P)
+    for b0 in range(0, P, em_batch):                        # every pair is one "replicate" of one EM launch
+        b1 = min(P, b0 + em_batch)
+        rates[b0:b1], iters[b0:b1], ll[b0:b1] = handle.stage3_em(b1 - b0, epochs, init, counts[b0:b1], max_iter)
+    t2 = time.perf_counter()
+    return dict(pairs=np.array(pairs, dtype=np.int32).reshape(P, 2), epochs=epochs, ep_null=ep_null, rates=rates, iters=iters,
+                ll=ll, num_blocks=nb, n_used=nu, counts=counts, seconds=dict(stage12=t1 - t0, em=t2 - t1))

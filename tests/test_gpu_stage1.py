@@ -145,3 +145,29 @@ def test_config4_adna_masks(handle):
     for r in range(2):
         ro, it, llo = po.em_run(ep, init, counts[r])
         assert iters[r] == it and np.array_equal(rates[r], ro) and ll[r] == llo
+
+
+def test_config5_all_pairs_small(handle):
+    """BASELINE.json configs[4] (all pairs of N genomes over one mutation set) at small scale: every
+    ordered pair (target=i, reference=j), i<j, through the batched driver == that pair run alone == oracle."""
+    from colate_b200 import pairs as pairs_mod
+    sites = synth.make_sites(11, [30000, 20000], [2.4e8, 1.3e8])
+    genomes = [synth.make_genome(300 + g, sites, 0.7) for g in range(5)]
+    handle.set_sites(sites.site_off, sites.pos, sites.age_begin, sites.age_end, sites.meta())
+    for g, G in enumerate(genomes):
+        handle.set_genome(g, G.chrom, G.bp, G.aaf, G.daf, G.anc.astype(np.uint16) | (G.der.astype(np.uint16) << 8))
+        handle.set_mask(g, None)
+    res = pairs_mod.all_pairs(handle, len(genomes), seed=3, bins="3,7,0.2", max_iter=60)
+    assert res["pairs"].shape == (10, 2)
+    ep, _ = po.epochs_from_bins("3,7,0.2", 0.0, 28.0)
+    init = np.full(len(ep), 1 / 20000.)
+    for p, (i, j) in enumerate(res["pairs"]):
+        o = po.stage1(sites, genomes[i], genomes[j], seed=3)
+        assert res["num_blocks"][p] == o["num_blocks"] and res["n_used"][p] == o["n_used_total"]
+        w = po.draw_block_weights(o["rng"], 1, o["num_blocks"])
+        assert np.array_equal(res["counts"][p], po.stage2(w, o, 0.0)[0]), (i, j)
+        ro, it, llo = po.em_run(ep, init, res["counts"][p], max_iter=60)
+        assert res["iters"][p] == it and np.array_equal(res["rates"][p], ro) and res["ll"][p] == llo, (i, j)
+    # asymmetric in target / reference: the swapped pair is a different estimate
+    swapped = pairs_mod.all_pairs(handle, len(genomes), seed=3, bins="3,7,0.2", pairs=[(1, 0)], max_iter=60)
+    assert not np.array_equal(swapped["rates"][0], res["rates"][0])
