@@ -70,6 +70,11 @@ SIGNATURES = {
     "colate_age_generations": (C.c_double, [C.c_char_p, C.c_char_p, C.c_int, C.c_float, C.POINTER(C.c_double)]),
     "colate_epochs_from_bins": (C.c_int, [C.c_char_p, C.c_double, C.c_double, f64, C.c_int, C.POINTER(C.c_int)]),
     "colate_epochs_from_coal_file": (C.c_int, [C.c_char_p, C.c_double, f64, f64, C.c_int]),
+    "colate_ingest_begin": (C.c_int, [VP, C.c_int, C.c_int64]),
+    "colate_ingest_mut_text": (C.c_int64, [VP, VP, C.c_int64, C.c_int]),
+    "colate_ingest_end": (C.c_int, [VP]),
+    "colate_ingest_fetch": (C.c_int, [VP, C.c_int64, C.c_int64, VP, VP, VP, VP]),
+    "colate_ingest_stats": (C.c_int, [VP, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "colate_read_mut": (C.c_int64, [C.c_char_p, C.c_int64, VP, VP, VP, VP]),
     "colate_read_colate_in": (C.c_int64, [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.c_int64, VP, VP, VP, VP, VP]),
     "colate_mask_bits_from_fasta": (C.c_int, [C.c_char_p, C.c_int64, VP, C.c_int64, VP]),

@@ -182,6 +182,32 @@ class Handle:
             assert pass_bits.shape[0] == (self.n_site + 31) // 32
             check(lib().colate_set_mask(self._h, slot, ptr(pass_bits), 0))
 
+    def ingest_mut(self, texts, row_capacity=None):
+        """GPU-side ingest of Relate .mut text (one bytes object per --chr entry, in order) straight into the
+        handle's site arrays: replaces read_mut() + set_sites().  Returns rows per chromosome."""
+        if row_capacity is None:
+            row_capacity = sum(t.count(b"\n") + 1 for t in texts)
+        check(lib().colate_ingest_begin(self._h, len(texts), row_capacity))
+        rows = []
+        for t in texts:
+            buf = np.frombuffer(t, dtype=np.uint8) if len(t) else np.zeros(1, np.uint8)
+            rows.append(check(lib().colate_ingest_mut_text(self._h, C.c_void_p(buf.ctypes.data), len(t), 0)))
+        check(lib().colate_ingest_end(self._h))
+        self.n_chr = len(texts)
+        self.n_site = int(sum(rows))
+        return rows
+
+    def ingest_fetch(self, row0=0, n_rows=None):
+        n = self.n_site - row0 if n_rows is None else n_rows
+        pos = np.zeros(n, np.int32); ab = np.zeros(n, np.float32); ae = np.zeros(n, np.float32); meta = np.zeros(n, np.uint32)
+        check(lib().colate_ingest_fetch(self._h, row0, n, ptr(pos), ptr(ab), ptr(ae), ptr(meta)))
+        return pos, ab, ae, meta
+
+    def ingest_stats(self):
+        ms, fb = C.c_double(0), C.c_int64(0)
+        check(lib().colate_ingest_stats(self._h, C.byref(ms), C.byref(fb)))
+        return dict(kernel_ms=ms.value, host_fallback_rows=fb.value)
+
     # ---- stage i
     def stage1_flags(self, target_slot=0, reference_slot=1):
         used = np.zeros(self.n_chr, dtype=np.int64)

@@ -6,6 +6,7 @@
 #include <sys/time.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -43,7 +44,7 @@ void help()
   std::cout << "Usage:\n  Colate --mode mut --mut <prefix> --target_tmp <t.colate.in> --reference_tmp <r.colate.in> --bins x,y,step\n"
                "         [--chr <file>] [--target_mask <prefix>] [--reference_mask <prefix>] [--target_age <years>]\n"
                "         [--reference_age <years>] [--years_per_gen <float>] [--coal <file>] [--seed <int>]\n"
-               "         [--num_bootstraps <int>] [--device <int>] -o <output prefix>\n"
+               "         [--num_bootstraps <int>] [--device <int>] [--host_parse] -o <output prefix>\n"
             << std::endl;
 }
 
@@ -61,7 +62,7 @@ bool parse(int argc, char** argv, Options& o)
     } else if (a == "-o") key = "output";
     else if (a == "-i") key = "input";
     else { std::cerr << "Option '" << a << "' does not exist" << std::endl; return false; }
-    if (key == "help" || key == "strandfilter") { o.kv[key] = "1"; continue; }
+    if (key == "help" || key == "strandfilter" || key == "host_parse") { o.kv[key] = "1"; continue; }   // host_parse: addition of this build
     if (!val.count(key)) {  // cxxopts::option_not_exists_exception in the reference (cxxopts.hpp:1180-1185)
       std::cerr << "Option '" << key << "' does not exist" << std::endl;
       return false;
@@ -156,24 +157,55 @@ int run_mut(const Options& options)
       std::set<std::string> uniq(name_chr.begin(), name_chr.end());
       if ((int)uniq.size() != n_chr) { std::cerr << "Duplicate chromosome names in --chr" << std::endl; return 1; }
     }
-    // readers -> SoA
+    // readers -> SoA.  Plain-text .mut files are parsed on the GPU (colate_ingest_*: the bytes go to the device,
+    // one thread per row); if any file only exists as .gz the host reader (zlib) takes over for all of them.
     std::vector<int64_t> site_off(n_chr + 1, 0);
     std::vector<int32_t> pos;
-    std::vector<float> ab, ae;
-    std::vector<uint32_t> meta;
-    for (int c = 0; c < n_chr; c++) {
-      std::cerr << "parsing CHR: " << c + 1 << " / " << n_chr << std::endl;
-      int64_t n = colate_read_mut(f_mut[c].c_str(), 0, nullptr, nullptr, nullptr, nullptr);
-      if (n < 0) { std::cerr << colate_last_error() << std::endl; exit(1); }
-      size_t o = pos.size();
-      pos.resize(o + n); ab.resize(o + n); ae.resize(o + n); meta.resize(o + n);
-      if (colate_read_mut(f_mut[c].c_str(), n, pos.data() + o, ab.data() + o, ae.data() + o, meta.data() + o) < 0) {
-        std::cerr << colate_last_error() << std::endl;
-        exit(1);
-      }
-      site_off[c + 1] = (int64_t)pos.size();
+    std::vector<std::vector<char>> texts(n_chr);
+    bool all_plain = !options.count("host_parse");
+    for (int c = 0; c < n_chr && all_plain; c++) {
+      FILE* f = fopen(f_mut[c].c_str(), "rb");
+      if (!f) { all_plain = false; break; }
+      fseek(f, 0, SEEK_END);
+      const long sz = ftell(f);
+      fseek(f, 0, SEEK_SET);
+      texts[c].resize((size_t)std::max(sz, 0L));
+      if (sz > 0 && fread(texts[c].data(), 1, (size_t)sz, f) != (size_t)sz) all_plain = false;
+      fclose(f);
     }
-    if (colate_set_sites(h, n_chr, site_off.data(), pos.data(), ab.data(), ae.data(), meta.data(), 0)) return die("colate_set_sites");
+    if (all_plain) {
+      int64_t cap = 0;
+      for (auto& t : texts) cap += (int64_t)std::count(t.begin(), t.end(), '\n') + 1;
+      if (colate_ingest_begin(h, n_chr, cap)) return die("colate_ingest_begin");
+      for (int c = 0; c < n_chr; c++) {
+        std::cerr << "parsing CHR: " << c + 1 << " / " << n_chr << std::endl;
+        const int64_t n = colate_ingest_mut_text(h, texts[c].data(), (int64_t)texts[c].size(), 0);
+        if (n < 0) { std::cerr << colate_last_error() << std::endl; exit(1); }
+        site_off[c + 1] = site_off[c] + n;
+        std::vector<char>().swap(texts[c]);
+      }
+      if (colate_ingest_end(h)) return die("colate_ingest_end");
+      if (options.count("target_mask") || options.count("reference_mask")) {   // the mask gather runs on host positions
+        pos.resize((size_t)site_off[n_chr]);
+        if (colate_ingest_fetch(h, 0, site_off[n_chr], pos.data(), nullptr, nullptr, nullptr)) return die("colate_ingest_fetch");
+      }
+    } else {
+      std::vector<float> ab, ae;
+      std::vector<uint32_t> meta;
+      for (int c = 0; c < n_chr; c++) {
+        std::cerr << "parsing CHR: " << c + 1 << " / " << n_chr << std::endl;
+        int64_t n = colate_read_mut(f_mut[c].c_str(), 0, nullptr, nullptr, nullptr, nullptr);
+        if (n < 0) { std::cerr << colate_last_error() << std::endl; exit(1); }
+        size_t o = pos.size();
+        pos.resize(o + n); ab.resize(o + n); ae.resize(o + n); meta.resize(o + n);
+        if (colate_read_mut(f_mut[c].c_str(), n, pos.data() + o, ab.data() + o, ae.data() + o, meta.data() + o) < 0) {
+          std::cerr << colate_last_error() << std::endl;
+          exit(1);
+        }
+        site_off[c + 1] = (int64_t)pos.size();
+      }
+      if (colate_set_sites(h, n_chr, site_off.data(), pos.data(), ab.data(), ae.data(), meta.data(), 0)) return die("colate_set_sites");
+    }
     std::vector<const char*> names;
     for (auto& s : name_chr) names.push_back(s.c_str());
     const std::string files[2] = {options.get("target_tmp"), options.get("reference_tmp")};
@@ -191,7 +223,7 @@ int run_mut(const Options& options)
     const std::vector<std::string>* masks[2] = {&f_tmask, &f_rmask};
     for (int g = 0; g < 2; g++) {
       if (masks[g]->empty()) continue;
-      std::vector<uint32_t> bits((pos.size() + 31) / 32 + 1, 0);
+      std::vector<uint32_t> bits(((size_t)site_off[n_chr] + 31) / 32 + 1, 0);
       for (int c = 0; c < n_chr; c++) {
         if (colate_mask_bits_from_fasta((*masks[g])[c].c_str(), site_off[c + 1] - site_off[c], pos.data() + site_off[c], site_off[c], bits.data())) {
           std::cerr << colate_last_error() << std::endl;

@@ -87,6 +87,13 @@ struct colate_handle {
   int counts_R = 0;
   int64_t launches = 0;
   bool opt_rejoin = false;
+  // GPU-side .mut ingest (kernels_ingest.cu)
+  bool ing_active = false;
+  int ing_nchr = 0;
+  int64_t ing_cap = 0, ing_fallback_rows = 0;
+  double ing_ms = 0.0;
+  std::vector<int64_t> ing_off;
+  colate::DevBuf ing_text, ing_tile_cnt, ing_tile_off, ing_nl, ing_status, ing_fb;
 };
 
 namespace colate {

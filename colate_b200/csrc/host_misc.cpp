@@ -116,6 +116,39 @@ static bool slurp_or_gz(const std::string& path, std::vector<char>& buf)
   return slurp(path + ".gz", buf);
 }
 
+// one data line of a .mut file, [p, nl) with *nl == '\n' (mutations.cpp:70-250; the columns the path uses)
+bool parse_mut_line_host(const char* p, const char* nl, int32_t* pos, float* age_begin, float* age_end, uint32_t* meta)
+{
+  // snp;pos;dist;rs-id;tree;branches;is_not_mapping;is_flipped;age_begin;age_end;type;...
+  const char* f[11];
+  const char* q = p;
+  int nf = 0;
+  f[nf++] = q;
+  while (q < nl && nf < 11) { if (*q == ';') f[nf++] = q + 1; q++; }
+  if (nf < 10) return false;
+  *pos = (int32_t)strtol(f[1], nullptr, 10);
+  int nb = 0;
+  for (const char* b = f[5]; b < f[6] - 1;) {
+    while (b < f[6] - 1 && *b == ' ') b++;
+    if (b < f[6] - 1) { nb++; while (b < f[6] - 1 && *b != ' ') b++; }
+  }
+  int flipped = strtol(f[7], nullptr, 10) != 0;
+  float ab = strtof(f[8], nullptr), ae = strtof(f[9], nullptr);
+  *age_begin = ab;
+  *age_end = ae;
+  char mt[16] = "NA";
+  if (nf >= 11) {
+    // mutation type runs to the next ';' or the end of the line (mutations.cpp:216-223)
+    const char* e = f[10];
+    size_t k = 0;
+    while (e < nl && *e != ';' && k + 1 < sizeof mt) mt[k++] = *e++;
+    mt[k] = 0;
+    if (e < nl && *e != ';') { mt[0] = 'N'; mt[1] = 'N'; mt[2] = 0; }  // longer than any valid code
+  }
+  *meta = colate_site_meta(flipped, nb, ab, ae, mt);
+  return true;
+}
+
 }  // namespace colate
 
 using namespace colate;
@@ -295,33 +328,8 @@ int64_t colate_read_mut(const char* path, int64_t cap, int32_t* pos, float* age_
     }
     if (pos) {
       if (n >= cap) return fail(COLATE_ERR_ARG, "colate_read_mut: capacity too small");
-      // snp;pos;dist;rs-id;tree;branches;is_not_mapping;is_flipped;age_begin;age_end;type;...
-      const char* f[11];
-      const char* q = p;
-      int nf = 0;
-      f[nf++] = q;
-      while (q < nl && nf < 11) { if (*q == ';') f[nf++] = q + 1; q++; }
-      if (nf < 10) return fail(COLATE_ERR_IO, std::string("Error reading following line in mut file: ") + std::string(p, nl));
-      pos[n] = (int32_t)strtol(f[1], nullptr, 10);
-      int nb = 0;
-      for (const char* b = f[5]; b < f[6] - 1;) {
-        while (b < f[6] - 1 && *b == ' ') b++;
-        if (b < f[6] - 1) { nb++; while (b < f[6] - 1 && *b != ' ') b++; }
-      }
-      int flipped = strtol(f[7], nullptr, 10) != 0;
-      float ab = strtof(f[8], nullptr), ae = strtof(f[9], nullptr);
-      age_begin[n] = ab;
-      age_end[n] = ae;
-      char mt[16] = "NA";
-      if (nf >= 11) {
-        // mutation type runs to the next ';' or the end of the line (mutations.cpp:216-223)
-        const char* e = f[10];
-        size_t k = 0;
-        while (e < nl && *e != ';' && k + 1 < sizeof mt) mt[k++] = *e++;
-        mt[k] = 0;
-        if (e < nl && *e != ';') { mt[0] = 'N'; mt[1] = 'N'; mt[2] = 0; }  // longer than any valid code
-      }
-      meta[n] = colate_site_meta(flipped, nb, ab, ae, mt);
+      if (!parse_mut_line_host(p, nl, &pos[n], &age_begin[n], &age_end[n], &meta[n]))
+        return fail(COLATE_ERR_IO, std::string("Error reading following line in mut file: ") + std::string(p, nl));
     }
     n++;
     p = nl + 1;

@@ -50,6 +50,7 @@ bool bin_thresholds(double* thr10 /*[NTHR]*/);
 // lut[cell] = slot_of_bin(bin at the lower edge of the cell) | 0x8000 if a threshold lies inside the cell
 bool age_thresholds(double* thrA /*[NBINS+2]*/, double* thrP /*[192]*/, uint16_t* lut /*[LUT_N]*/);
 int bin_of_x10_host(double x10);
+bool parse_mut_line_host(const char* p, const char* nl, int32_t* pos, float* age_begin, float* age_end, uint32_t* meta);
 
 }  // namespace colate
 

@@ -346,7 +346,10 @@ __device__ __forceinline__ int slot_of_age(double a, const uint16_t* lut, const 
 }
 
 constexpr int SW = 8;                 // consumer warps = used rows per pipeline stage
-constexpr int SAMPLE_STAGES = 4;
+#ifndef SAMPLE_STAGES_
+#define SAMPLE_STAGES_ 4
+#endif
+constexpr int SAMPLE_STAGES = SAMPLE_STAGES_;
 constexpr int ROW_BYTES = 192;        // per-row sample counts, one byte per age bin (185 used)
 #ifndef ROW_COPIES
 #define ROW_COPIES 2

@@ -175,6 +175,24 @@ double colate_age_generations(const char* target_age, const char* reference_age,
 int colate_epochs_from_bins(const char* bins, double age, double years_per_gen, double* epochs, int cap, int* ep_null);
 int colate_epochs_from_coal_file(const char* path, double age, double* epochs, double* rates_init, int cap);
 
+/* ---- GPU-side ingest of Relate .mut text --------------------------------
+ * Replaces Mutations::Read (include/src/mutations.cpp:56-283) + colate_set_sites for plain-text input:
+ * the file's bytes (host or device, `location` as above) are split into lines and parsed on the
+ * device, one thread per row, straight into the handle's site arrays.  Integers as std::stoi, ages
+ * as std::stof (correctly rounded decimal -> float; the rare rows the device cannot convert with
+ * that guarantee are re-parsed on the host with strtof).  Result == colate_read_mut() row for row.
+ *   colate_ingest_begin(h, n_chr, row_capacity)     row_capacity >= total data rows of all files
+ *   colate_ingest_mut_text(h, text, n_bytes, loc)   once per --chr entry, in order; returns its rows
+ *   colate_ingest_end(h)                            == colate_set_sites() on what was ingested
+ *   colate_ingest_fetch(...)                        host copies of ingested rows (masks, tests)
+ *   colate_ingest_stats(...)                        device time of the parse kernels, host-parsed rows */
+int colate_ingest_begin(colate_handle* h, int n_chr, int64_t row_capacity);
+int64_t colate_ingest_mut_text(colate_handle* h, const char* text, int64_t n_bytes, int location);
+int colate_ingest_end(colate_handle* h);
+int colate_ingest_fetch(colate_handle* h, int64_t row0, int64_t n_rows, int32_t* pos, float* age_begin, float* age_end,
+                        uint32_t* meta);
+int colate_ingest_stats(colate_handle* h, double* kernel_ms, int64_t* host_fallback_rows);
+
 /* ---- readers / writers (host) --------------------------------------------------------- */
 /* Relate .mut[.gz] (mutations.cpp:56-283).  Two-call pattern: n = colate_read_mut(path, 0, ...NULL)
  * returns the row count; then call again with arrays of that capacity. */
