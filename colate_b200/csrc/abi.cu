@@ -114,6 +114,7 @@ void colate_destroy(colate_handle* h)
     DevBuf* gb[] = {&g.bp, &g.aaf, &g.daf, &g.alleles, &g.chr_first, &g.chr_end, &g.mask_bits, &g.j_aaf, &g.j_daf, &g.j_prevbp, &g.j_flag};
     for (DevBuf* b : gb) b->release();
   }
+  for (int k = 0; k < 2; k++) if (h->ing_bounce[k]) { cudaFreeHost(h->ing_bounce[k]); cudaEventDestroy(h->ing_bounce_ev[k]); }
   for (auto& ev : h->ev) cudaEventDestroy(ev);
   cudaStreamDestroy(h->stream);
   delete h;

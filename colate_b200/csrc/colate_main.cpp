@@ -3,6 +3,7 @@
 // flow of mut() (include/coal/coal.cpp:3071-3863); all computation goes through the C ABI
 // (include/colate_b200.h) onto the GPU.  There is no CPU fallback.
 #include <sys/resource.h>
+#include <sys/stat.h>
 #include <sys/time.h>
 #include <unistd.h>
 
@@ -19,6 +20,7 @@
 #include <set>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/colate_b200.h"
@@ -84,6 +86,14 @@ int die(const std::string& what)
 
 bool file_exists(const std::string& p) { std::ifstream f(p); return f.good(); }
 
+// COLATE_TIMING=1: wall-clock phases on stderr
+struct Phases {
+  bool on = getenv("COLATE_TIMING") != nullptr;
+  double t0 = now(), last = t0;
+  static double now() { timeval tv; gettimeofday(&tv, nullptr); return tv.tv_sec + 1e-6 * tv.tv_usec; }
+  void tick(const char* what) { if (!on) return; const double t = now(); fprintf(stderr, "[timing] %-28s %8.3f s (total %.3f)\n", what, t - last, t - t0); last = t; }
+};
+
 int run_mut(const Options& options)
 {
   if (!options.count("mut") || !options.count("output")) {  // coal.cpp:3077-3086
@@ -115,9 +125,19 @@ int run_mut(const Options& options)
   if (R < 0) R = 0;
   const std::string out = options.get("output");
 
+  Phases ph;
+  // the CUDA context comes up (about a second) while the main thread reads the input files
   colate_handle* h = nullptr;
-  if (colate_create(options.count("device") ? atoi(options.get("device").c_str()) : 0, &h)) return die("colate_create");
-
+  int create_rc = 0;
+  std::string create_err;
+  const int device = options.count("device") ? atoi(options.get("device").c_str()) : 0;
+  std::thread init([&] { create_rc = colate_create(device, &h); if (create_rc) create_err = colate_last_error(); });
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{init};
+  auto wait_for_device = [&]() -> bool {
+    if (init.joinable()) init.join();
+    if (create_rc) std::cerr << "colate_create: " << create_err << std::endl;
+    return create_rc == 0;
+  };
   std::vector<double> counts((size_t)std::max(R, 1) * 2 * COLATE_NUM_AGE_BINS, 0.0);
   uint32_t mt[COLATE_MT_WORDS];
   colate_mt_seed((uint32_t)seed, mt);
@@ -173,6 +193,23 @@ int run_mut(const Options& options)
       if (sz > 0 && fread(texts[c].data(), 1, (size_t)sz, f) != (size_t)sz) all_plain = false;
       fclose(f);
     }
+    // the two .colate.in files: decoded on the host in one pass each (at least 19 bytes per record)
+    std::vector<const char*> names;
+    for (auto& s : name_chr) names.push_back(s.c_str());
+    const std::string files[2] = {options.get("target_tmp"), options.get("reference_tmp")};
+    struct GenomeHost { int64_t n = 0; std::vector<int32_t> rc, bp, aaf, daf; std::vector<uint16_t> al; } gh[2];
+    for (int g = 0; g < 2; g++) {
+      struct stat st;
+      const int64_t cap = stat(files[g].c_str(), &st) == 0 ? (int64_t)st.st_size / 19 + 16 : 16;
+      gh[g].rc.resize(cap); gh[g].bp.resize(cap); gh[g].aaf.resize(cap); gh[g].daf.resize(cap); gh[g].al.resize(cap);
+      int64_t n = colate_read_colate_in(files[g].c_str(), n_chr, names.data(), cap, gh[g].rc.data(), gh[g].bp.data(), gh[g].aaf.data(),
+                                        gh[g].daf.data(), gh[g].al.data());
+      if (n < 0) { std::cerr << colate_last_error() << std::endl; n = 0; }  // the reference only warns (coal.cpp:2093-2098)
+      gh[g].n = n;
+    }
+    ph.tick("read input files");
+    if (!wait_for_device()) return 1;
+    ph.tick("wait for the CUDA context");
     if (all_plain) {
       int64_t cap = 0;
       for (auto& t : texts) cap += (int64_t)std::count(t.begin(), t.end(), '\n') + 1;
@@ -206,20 +243,15 @@ int run_mut(const Options& options)
       }
       if (colate_set_sites(h, n_chr, site_off.data(), pos.data(), ab.data(), ae.data(), meta.data(), 0)) return die("colate_set_sites");
     }
-    std::vector<const char*> names;
-    for (auto& s : name_chr) names.push_back(s.c_str());
-    const std::string files[2] = {options.get("target_tmp"), options.get("reference_tmp")};
+    ph.tick("parse .mut -> device sites");
     for (int g = 0; g < 2; g++) {
-      int64_t n = colate_read_colate_in(files[g].c_str(), n_chr, names.data(), 0, nullptr, nullptr, nullptr, nullptr, nullptr);
-      if (n < 0) { std::cerr << colate_last_error() << std::endl; n = 0; }  // the reference only warns (coal.cpp:2093-2098)
-      std::vector<int32_t> rc(n + 1), bp(n + 1), aaf(n + 1), daf(n + 1);
-      std::vector<uint16_t> al(n + 1);
-      if (n > 0 && colate_read_colate_in(files[g].c_str(), n_chr, names.data(), n, rc.data(), bp.data(), aaf.data(), daf.data(), al.data()) < 0)
-        return die("colate_read_colate_in");
       std::vector<int64_t> first(n_chr), end(n_chr);
-      colate_chr_ranges(n_chr, n, rc.data(), first.data(), end.data());
-      if (colate_set_genome(h, g, n, first.data(), end.data(), bp.data(), aaf.data(), daf.data(), al.data(), 0)) return die("colate_set_genome");
+      colate_chr_ranges(n_chr, gh[g].n, gh[g].rc.data(), first.data(), end.data());
+      if (colate_set_genome(h, g, gh[g].n, first.data(), end.data(), gh[g].bp.data(), gh[g].aaf.data(), gh[g].daf.data(), gh[g].al.data(), 0))
+        return die("colate_set_genome");
+      gh[g] = GenomeHost();
     }
+    ph.tick("upload .colate.in x2");
     const std::vector<std::string>* masks[2] = {&f_tmask, &f_rmask};
     for (int g = 0; g < 2; g++) {
       if (masks[g]->empty()) continue;
@@ -232,12 +264,14 @@ int run_mut(const Options& options)
       }
       if (colate_set_mask(h, g, bits.data(), 0)) return die("colate_set_mask");
     }
+    ph.tick("masks");
     // stage i
     int num_blocks = 0;
     int64_t n_used = 0;
     std::vector<double> block_stats((size_t)COLATE_MAX_BLOCKS * 4 * COLATE_NUM_AGE_BINS);
     if (colate_stage1(h, 0, 1, mt, &num_blocks, block_stats.data(), nullptr, &n_used, mt)) return die("colate_stage1");
     std::cerr << "Number of blocks: " << num_blocks << std::endl;
+    ph.tick("stage i");
     // stage ii
     if (R > 0) {
       std::vector<int32_t> w((size_t)R * num_blocks);
@@ -259,6 +293,7 @@ int run_mut(const Options& options)
     E = colate_epochs_from_bins(options.get("bins").c_str(), age, ypg, epochs.data(), 4096, &ep_null);
     if (E < 0) { std::cerr << colate_last_error() << std::endl; exit(1); }
   }
+  if (!wait_for_device()) return 1;   // (the .colate_mat cache path gets here without having touched the device)
   std::cerr << "Maximising likelihood using EM.. " << std::endl;
   std::vector<double> rates((size_t)std::max(R, 1) * E, 0.0), ll(std::max(R, 1));
   std::vector<int32_t> iters(std::max(R, 1), 0);
@@ -269,6 +304,7 @@ int run_mut(const Options& options)
   }
   // .coal first: for ancient samples it zeroes rates[0..ep_null] (coal.cpp:3832-3834); the fp64 side
   // output then holds exactly the values the text was printed from
+  ph.tick("stage ii + iii");
   if (colate_write_coal((out + ".coal").c_str(), R, E, epochs.data(), rates.data(), is_ancient, ep_null)) return die("write .coal");
   if (colate_write_bin((out + ".bin").c_str(), R, E, epochs.data(), rates.data(), iters.data())) return die("write .bin");
   colate_destroy(h);

@@ -94,6 +94,8 @@ struct colate_handle {
   double ing_ms = 0.0;
   std::vector<int64_t> ing_off;
   colate::DevBuf ing_text, ing_tile_cnt, ing_tile_off, ing_nl, ing_status, ing_fb;
+  void* ing_bounce[2] = {nullptr, nullptr};       // pinned staging for pageable callers
+  cudaEvent_t ing_bounce_ev[2] = {nullptr, nullptr};
 };
 
 namespace colate {

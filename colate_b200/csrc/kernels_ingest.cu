@@ -264,8 +264,27 @@ int64_t colate_ingest_mut_text(colate_handle* h, const char* text, int64_t n_byt
   const char* d_text = text;
   if (!location) {
     CK(h->ing_text.ensure((size_t)n_bytes + 64));
-    CK(cudaMemcpyAsync(h->ing_text.p, text, (size_t)n_bytes, cudaMemcpyHostToDevice, s));
     d_text = h->ing_text.as<char>();
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, text) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+      CK(cudaMemcpyAsync(h->ing_text.p, text, (size_t)n_bytes, cudaMemcpyHostToDevice, s));
+    } else {
+      // pageable caller memory: stage through two pinned bounce buffers so the copies run at PCIe speed
+      // while the host fills the other buffer
+      const size_t CH = (size_t)32 << 20;
+      for (int k = 0; k < 2; k++)
+        if (!h->ing_bounce[k]) { CK(cudaHostAlloc(&h->ing_bounce[k], CH, cudaHostAllocDefault)); CK(cudaEventCreateWithFlags(&h->ing_bounce_ev[k], cudaEventDisableTiming)); }
+      int k = 0;
+      for (size_t o = 0; o < (size_t)n_bytes; o += CH, k ^= 1) {
+        const size_t m = std::min(CH, (size_t)n_bytes - o);
+        CK(cudaEventSynchronize(h->ing_bounce_ev[k]));
+        memcpy(h->ing_bounce[k], text + o, m);
+        CK(cudaMemcpyAsync(h->ing_text.as<char>() + o, h->ing_bounce[k], m, cudaMemcpyHostToDevice, s));
+        CK(cudaEventRecord(h->ing_bounce_ev[k], s));
+      }
+    }
   }
   const int64_t n_tiles = (n_bytes + ING_TILE - 1) / ING_TILE;
   CK(h->ing_tile_cnt.ensure(n_tiles * 4)); CK(h->ing_tile_off.ensure((n_tiles + 1) * 8)); CK(h->ing_status.ensure(64));
