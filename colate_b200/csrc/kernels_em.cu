@@ -769,10 +769,12 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
       Lam[e] = l;
     }
     __syncthreads();
-    // what the folds need: A_ep (threads 0..E-1) and the not-shared tasks' own first term (one thread per bin, from warp 2 on)
+    // what the folds need: A_ep (threads 0..E-1) and the not-shared tasks' own first term (one thread per bin,
+    // on the warps after those)
+    const int ft0 = (E + 31) & ~31;
     if (tid < E) em_A(E, ep, rate, Lam, tid, A, c.T);
-    else if (tid >= 64 && tid < 64 + nbl && h_cnt[2 * (tid - 64) + 1] > 0) {   // EM_notshared, coal_EM.cpp:327-357, num part
-      const int l = 2 * (tid - 64) + 1, et = h_et[l], k = et + 1;
+    else if (tid >= ft0 && tid < ft0 + nbl && h_cnt[2 * (tid - ft0) + 1] > 0) {   // EM_notshared, coal_EM.cpp:327-357, num part
+      const int l = 2 * (tid - ft0) + 1, et = h_et[l], k = et + 1;
       const double t = h_t[l], r = rate[et];
       const double c1 = Lam[et] + r * (t - ep[et]);
       const double c2 = c1 + r * (t - t);
@@ -1073,10 +1075,16 @@ int run_em(colate_handle* h, int R, int E, int max_iter)
     if (csize == 8 && R * 16 * 2 <= 148) csize = 16;   // non-portable cluster size: one GPC (16-20 SMs) per replicate
   }
   if (csize != 1 && csize != 2 && csize != 4 && csize != 8 && csize != 16) csize = 1;
-  // latency mode: one replicate over a cluster of 8 (k_em_split) when its per-CTA tables fit
-  const int nbl = (NBINS + csize - 1) / csize, ntl = 2 * nbl, CW = (2 * E + 1 + csize - 1) / csize;
-  const size_t smem_split = sizeof(double) * ((size_t)10 * E + 1 + (size_t)ntl * E * 3 + (size_t)2 * NBINS * CW) + 512 * 8;
-  const bool split = csize >= 8 && ntl <= EMS_TLMAX && E + 2 * nbl <= EMS_THREADS - (EMS_FOLD_WARPS + 1) * 32 && smem_split <= 200 * 1024 && !getenv("COLATE_EM_NOSPLIT");
+  // latency mode: one replicate over a cluster of 8 or 16 (k_em_split) when its per-CTA tables fit
+  auto split_fits = [&](int cs, size_t* bytes) {
+    const int nbl = (NBINS + cs - 1) / cs, ntl = 2 * nbl, CW = (2 * E + 1 + cs - 1) / cs;
+    *bytes = sizeof(double) * ((size_t)10 * E + 1 + (size_t)ntl * E * 3 + (size_t)2 * NBINS * CW) + 512 * 8;
+    return cs >= 8 && ntl <= EMS_TLMAX && *bytes <= 200 * 1024 && !getenv("COLATE_EM_NOSPLIT") &&
+           E + 2 * nbl <= EMS_THREADS - (EMS_FOLD_WARPS + 1) * 32 && ((E + 31) & ~31) + nbl <= EMS_THREADS;
+  };
+  size_t smem_split = 0;
+  bool split = split_fits(csize, &smem_split);
+  if (!split && csize > 8) { csize = 8; split = split_fits(csize, &smem_split); }   // k_em itself runs on portable cluster sizes only
   const size_t smem = split ? smem_split : sizeof(double) * ((size_t)10 * E + 1 + 2 * EM_STAGE_DOUBLES) + 512 * 8;
   if (split) {
     CK(cudaFuncSetAttribute(k_em_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -94,7 +94,7 @@ def test_stage2_bit_exact(handle, R, age):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("bins,age,R", [("3,7,0.2", 0.0, 3), ("3,7,0.1", 0.0, 2), ("3,7,0.2", 250.0, 2)])
+@pytest.mark.parametrize("bins,age,R", [("3,7,0.2", 0.0, 3), ("3,7,0.1", 0.0, 2), ("3,7,0.2", 250.0, 2), ("3,7,0.05", 0.0, 1), ("2,8,0.3", 100.0, 5), ("4,6,0.5", 0.0, 2), ("1,8,0.02", 0.0, 1)])
 def test_em_rates_and_iterations(handle, bins, age, R):
     o = _block_stats()
     nb = o["num_blocks"]
