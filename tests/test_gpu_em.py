@@ -134,3 +134,18 @@ def test_em_short_run_tight(handle):
     ro, it, llo = po.em_run(ep, init, counts[0], max_iter=5)
     assert iters[0] == it == 5
     assert _same(rates[0], ro)
+
+
+def test_em_throughput_mode_many_replicates(handle):
+    """Enough replicates to fill the GPU: one CTA per replicate (k_em), no cluster; spot-checked against the oracle."""
+    o = _block_stats()
+    R = 80
+    w = api.draw_block_weights(api.mt_seed(11), R, o["num_blocks"])
+    counts = po.stage2(w, o, 0.0)
+    ep, _ = po.epochs_from_bins("3,7,0.2", 0.0, 28.0)
+    init = np.full(len(ep), 1 / 20000.)
+    rates, iters, ll = handle.stage3_em(R, ep, init, counts)
+    for r in (0, 41, 79):
+        ro, it, llo = po.em_run(ep, init, counts[r])
+        assert iters[r] == it and _same(rates[r], ro) and _same(ll[r], llo)
+    assert len({tuple(x) for x in rates}) > R // 2      # the replicates really differ
