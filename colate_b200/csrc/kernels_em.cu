@@ -290,109 +290,19 @@ __device__ double task_notshared(const EmCtx& c, double t, int k, bool active, E
   return good ? nc : 0.0;
 }
 
-// ---- split form of a task (latency mode: one replicate spread over a cluster) ----------------
-// head   = special epoch + the sequential logsumexp fold -> log normaliser (one thread per task)
-// raw    = the two exp() per epoch, independent of each other -> spread over all threads
-// finish = the serial `integ` recursion over the epochs (cheap) -> scratch row
-// Same operations and operand order as task_shared / task_notshared, just scheduled differently.
-__device__ __forceinline__ void notshared_head(const EmCtx& c, double t, int k, double& num_t, double& den_t, double& nc)
-{
-  const int E = c.E, et = k - 1;
-  const double r = c.rate[et], inv = 1.0 / r;
-  const double c1 = c.Lam[et] + r * (t - c.ep[et]);
-  const double c2 = c1 + r * (t - t);
-  if (et != E - 1) {
-    const double c3 = c2 + r * (c.ep[k] - t);
-    if (r > 0) {
-      num_t = lme(-c2, -c3, c.T);
-      den_t = glm::log((t + inv) - (c.ep[k] + inv) * glm::exp(-c3 + c2, c.T), c.T) - c2;
-      nc = num_t;
-    } else { num_t = neg_inf(); den_t = neg_inf(); nc = neg_inf(); }
-    for (int e = et + 1; e < E; e++) nc = lse(nc, c.A[e], c.T);
-  } else {
-    num_t = -c2;
-    den_t = glm::log(t + inv, c.T) - c2;
-    nc = num_t;
-  }
-}
-
-// arguments of the two exp() of epoch e; false if the epoch needs none
-__device__ __forceinline__ bool task_raw_args(bool is_shared, const EmCtx& c, int et, int e, double num_t, double den_t, double nc,
-                                              double& xn, double& xd)
-{
-  const int E = c.E;
-  double ln, ld;
-  if (is_shared) {
-    const int lim = (E - 1 < et + 1) ? E - 1 : et + 1;
-    if (!(e < lim || (e == E - 1 && et == E - 1))) return false;
-    ln = (e < et) ? c.A[e] : num_t;
-    ld = (e < et) ? c.B[e] : den_t;
-  } else {
-    if (e < et) return false;
-    ln = (e == et) ? num_t : c.A[e];
-    ld = (e == et) ? den_t : c.B[e];
-  }
-  xn = ln - nc;
-  xd = ld - nc;
-  return true;
-}
-
-__device__ __forceinline__ void task_finish(bool is_shared, const EmCtx& c, int et, bool good, const double* raw /*[E][2]*/,
-                                            double cnt, double* Mt)
-{
-  const int E = c.E;
-  double integ = 1.0;
-  const int lim = (E - 1 < et + 1) ? E - 1 : et + 1;
-  for (int e = 0; e < E; e++) {
-    double ne = 0.0, de = 0.0;
-    if (good) {
-      if (is_shared) {
-        if (e < lim) {
-          ne = raw[2 * e];
-          if (integ > 0.0) integ -= ne; else integ = 0.0;
-          de = raw[2 * e + 1];
-          de += -c.ep[e] * ne + (c.ep[e + 1] - c.ep[e]) * integ;
-          if (de < 0.0) de = 0.0;
-        } else if (e == E - 1 && et == E - 1) {
-          ne = raw[2 * e];
-          de = raw[2 * e + 1];
-          de -= c.ep[e] * ne;
-          if (de < 0.0) de = 0.0;
-        }
-      } else {
-        if (e < et) {
-          de = c.ep[e + 1] - c.ep[e];
-        } else {
-          ne = raw[2 * e];
-          if (e < E - 1) {
-            if (integ > 0.0) integ -= ne; else integ = 0.0;
-            de = raw[2 * e + 1];
-            de += -c.ep[e] * ne + (c.ep[e + 1] - c.ep[e]) * integ;
-          } else {
-            de = raw[2 * e + 1];
-            de -= c.ep[e] * ne;
-          }
-          if (de < 0.0) de = 0.0;
-        }
-      }
-    }
-    Mt[e] = cnt * ne;
-    Mt[E + e] = cnt * de;
-  }
-}
-
-// ---- stage iii: EM to convergence ----------------------------------------------------------
-// One thread-block cluster per bootstrap replicate (cluster size 1 when there are enough
-// replicates to fill the GPU, up to 8 SMs per replicate when there are few).  Per iteration:
+// ---- stage iii: EM to convergence, throughput mode --------------------------------------------
+// One CTA per bootstrap replicate, 2 CTAs per SM (used when there are enough replicates to fill the
+// GPU; small portable clusters of 2 / 4 CTAs per replicate in between).  Few replicates run on
+// k_em_split below.  Per iteration:
 //   A  cumulative hazard (every thread sums the per-epoch products in order), A_ep / B_ep
 //   B  the sequential logsumexp folds: one prefix chain for all "shared" tasks (its own warp,
-//      published entry by entry), one suffix chain per bin for the "not shared" tasks -- these
-//      folds bound the iteration latency; shared tasks start as soon as their prefix is ready
+//      published entry by entry), one suffix chain per bin for the "not shared" tasks; shared tasks
+//      start as soon as their prefix is ready
 //   C  per (bin, type) task: posterior mass / exposure per epoch -> scratch M[task][column]
 //      (tasks are dealt round-robin to the CTAs of the cluster)
-//   D  cluster barrier; every CTA then sums M over the tasks IN THE REFERENCE'S ORDER
-//      (coal.cpp:3704-3733; chunks staged through shared memory) and applies the M-step
-//      redundantly, so no broadcast is needed.
+//   D  (cluster barrier;) the CTA sums its columns of M over the tasks IN THE REFERENCE'S ORDER
+//      (coal.cpp:3704-3733; chunks staged through shared memory), totals reach every CTA through
+//      DSMEM, and the M-step runs redundantly.
 constexpr int EM_STAGE_DOUBLES = 3328;  // per staging buffer of the column sums (26 KB)
 
 __global__ void __launch_bounds__(EM_THREADS, 2)
@@ -422,9 +332,6 @@ k_em(int E, const double* __restrict__ epochs, const double* __restrict__ rates_
   __shared__ int stop_flag;
   __shared__ volatile int pl_ready;
   __shared__ double ll_s, prev_s, ll_new;
-  constexpr int TLMAX = 96;  // tasks of one CTA in split mode
-  __shared__ double h_nc[TLMAX], h_numt[TLMAX], h_dent[TLMAX], h_cnt[TLMAX];
-  __shared__ int h_et[TLMAX], h_good[TLMAX];
 
   const int tid = threadIdx.x;
   for (int e = tid; e < E; e += blockDim.x) { ep[e] = epochs[e]; rate[e] = rates_init[e]; }
@@ -446,12 +353,6 @@ k_em(int E, const double* __restrict__ epochs, const double* __restrict__ rates_
   const int k = is_task ? tint_k(E, ep, t) : 1;
   const int et = k - 1;
   const bool mine = active && ((task % csize) == crank);  // tasks dealt round-robin over the cluster
-  const int ntl = (2 * NBINS + csize - 1) / csize;        // local task slots
-  const int tl = task / csize;                            // this thread's slot (when mine)
-  const bool split = csize > 1 && ntl <= TLMAX && (size_t)ntl * E * 2 <= 2 * (size_t)EM_STAGE_DOUBLES;
-  for (int i = tid; i < TLMAX; i += blockDim.x) { h_good[i] = 0; h_cnt[i] = 0.0; h_et[i] = 0; }
-  __syncthreads();
-  if (mine && split) { h_cnt[tl] = cnt; h_et[tl] = et; }
   EmCtx c{E, ep, rate, A, B, Lam, glm::Tables{etab, ltab}};
   // scratch of this replicate: [buf][task][RS], row = {count*num[e] (E), count*denom[e] (E), count*logl}
   const int RS = 2 * E + 2;
@@ -497,21 +398,6 @@ k_em(int E, const double* __restrict__ epochs, const double* __restrict__ rates_
         __threadfence_block();
         pl_ready = e + 1;
       }
-    } else if (split) {
-      if (mine) {  // heads: special epoch + fold -> log normaliser
-        double num_t, den_t, nc;
-        if (is_shared) {
-          shared_special(c, t, et, num_t, den_t);
-          while (pl_ready < et) { }
-          const double pl = ((volatile double*)PL)[et];
-          nc = (pl == 1.0) ? num_t : lse(pl, num_t, c.T);
-        } else {
-          notshared_head(c, t, k, num_t, den_t, nc);
-        }
-        const bool good = !bad(nc);
-        h_nc[tl] = nc; h_numt[tl] = num_t; h_dent[tl] = den_t; h_good[tl] = good ? 1 : 0;
-        my_logl = cnt * (good ? nc : 0.0);
-      }
     } else if (mine && !is_shared) {
       my_logl = cnt * task_notshared(c, t, k, true, emit);
     } else if (mine && is_shared) {
@@ -520,24 +406,6 @@ k_em(int E, const double* __restrict__ epochs, const double* __restrict__ rates_
       while (pl_ready < et) { }
       const double pl = ((volatile double*)PL)[et];
       my_logl = cnt * task_shared(c, et, true, pl, num_t, den_t, emit);
-    }
-    if (split) {
-      __syncthreads();
-      // raw exps of all (local task, epoch) pairs, spread over the whole CTA
-      for (int i = tid; i < ntl * E; i += blockDim.x) {
-        const int l = i / E, e = i - l * E;
-        double xn, xd;
-        if (h_good[l] && task_raw_args(((l * csize + crank) & 1) == 0, c, h_et[l], e, h_numt[l], h_dent[l], h_nc[l], xn, xd)) {
-          stage[2 * i] = glm::exp(xn, c.T);
-          stage[2 * i + 1] = glm::exp(xd, c.T);
-        }
-      }
-      __syncthreads();
-      // serial recursion per task -> scratch row
-      if (tid < ntl && h_cnt[tid] > 0) {
-        const int tk = tid * csize + crank;
-        task_finish((tk & 1) == 0, c, h_et[tid], h_good[tid] != 0, stage + (size_t)tid * E * 2, h_cnt[tid], M + (size_t)tk * RS);
-      }
     }
     if (mine) Mt[2 * E] = my_logl;
     __threadfence();
