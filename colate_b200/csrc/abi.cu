@@ -348,9 +348,13 @@ int colate_stage3_em(colate_handle* h, int R, int E, const double* epochs, const
   }
   if ((rc = run_em(h, R, E, max_iter))) return rc;
   if (rates) CK(cudaMemcpyAsync(rates, h->d_rates.as<double>() + E, (size_t)R * E * 8, cudaMemcpyDeviceToHost, s));
-  if (iters) CK(cudaMemcpyAsync(iters, h->d_iters.p, (size_t)R * 4, cudaMemcpyDeviceToHost, s));
+  std::vector<int32_t> it_host((size_t)R);
+  CK(cudaMemcpyAsync(it_host.data(), h->d_iters.p, (size_t)R * 4, cudaMemcpyDeviceToHost, s));
   if (final_ll) CK(cudaMemcpyAsync(final_ll, h->d_ll.p, (size_t)R * 8, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  for (int r = 0; r < R; r++)
+    if (it_host[r] < 0) return fail(COLATE_ERR_CUDA, "EM kernel: the cluster handshake timed out (replicate " + std::to_string(r) + ")");
+  if (iters) memcpy(iters, it_host.data(), (size_t)R * 4);
   return 0;
 }
 

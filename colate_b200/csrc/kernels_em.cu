@@ -545,15 +545,20 @@ __device__ __forceinline__ void em_mbar_arm(uint64_t* bar, uint32_t bytes)   // 
 {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(em_smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void em_mbar_wait(uint64_t* bar, uint32_t parity)
+// false: the bytes did not arrive within ~2 s (a peer is gone or the byte accounting is off): the caller gives up
+// instead of hanging the GPU
+__device__ __forceinline__ bool em_mbar_wait(uint64_t* bar, uint32_t parity)
 {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(em_smem_u32(bar)), "r"(parity) : "memory");
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(em_smem_u32(bar)), "r"(parity) : "memory");
+    if (done) return true;
+    if (clock64() - t0 > 4000000000ll) return false;
+  }
 }
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -595,6 +600,10 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
   __shared__ int h_et[EMS_TLMAX], h_good[EMS_TLMAX];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // exact i / E and c / CW for the small indices used below (i < 2^15): one multiply-high instead of a division
+  const uint32_t magicE = E > 1 ? 0xffffffffu / (uint32_t)E + 1u : 0u, magicCW = CW > 1 ? 0xffffffffu / (uint32_t)CW + 1u : 0u;
+  auto divE = [&](int i) { return magicE ? (int)__umulhi((uint32_t)i, magicE) : i; };
+  auto divCW = [&](int c) { return magicCW ? (int)__umulhi((uint32_t)c, magicCW) : c; };
   for (int e = tid; e < E; e += blockDim.x) { ep[e] = epochs[e]; rate[e] = rates_init[e]; }
   for (int i = tid; i < 256; i += blockDim.x) { etab[i] = exp_tab_g[i]; ltab[i] = log_tab_g[i]; }
   if (tid == 0) {
@@ -728,7 +737,7 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
     // exp() of the two log-domain terms of every (slot, epoch) pair: first the numerator terms (the
     // integ recursion needs them), then the denominator terms while the first warp(s) run the recursion
     auto raw_term = [&](int i, int which) {
-      const int l = i / E, e = i - l * E, et = h_et[l];
+      const int l = divE(i), e = i - l * E, et = h_et[l];
       const bool sh = (l & 1) == 0;
       const int lim = (E - 1 < et + 1) ? E - 1 : et + 1;
       const bool need = h_good[l] && (sh ? (e < lim || (e == E - 1 && et == E - 1)) : (e >= et));
@@ -770,7 +779,7 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
     // rows {count*num[e] (E), count*denom[e] (E), count*logl} -> pushed through distributed shared
     // memory into the column buffers of the CTAs that sum them
     for (int i = tid; i < ntl * E; i += blockDim.x) {
-      const int l = i / E, e = i - l * E;
+      const int l = divE(i), e = i - l * E;
       const double cnt = h_cnt[l];
       if (cnt > 0) {
         const int et = h_et[l];
@@ -807,7 +816,7 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
           }
         }
         const int tk = 2 * ((l >> 1) * csize + crank) + (l & 1);   // row of the task
-        const int r1 = e / CW, r2 = (E + e) / CW;
+        const int r1 = divCW(e), r2 = divCW(E + e);
         em_st_async(em_mapa(colbuf_s, r1) + 8u * (tk * CW + (e - r1 * CW)), cnt * ne, em_mapa(bar_rows_s, r1));
         em_st_async(em_mapa(colbuf_s, r2) + 8u * (tk * CW + (E + e - r2 * CW)), cnt * de, em_mapa(bar_rows_s, r2));
       }
@@ -817,7 +826,7 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
       em_st_async(em_mapa(colbuf_s, r) + 8u * (tk * CW + (2 * E - r * CW)), h_logl[tid], em_mapa(bar_rows_s, r));
     }
     if (prof) { t1 = clock64(); tp[6] += t1 - t0; t0 = t1; }
-    if (warp == 0) em_mbar_wait(&bar_rows, iter & 1);        // all rows of this iteration have landed in colbuf
+    if (warp == 0 && !em_mbar_wait(&bar_rows, iter & 1)) stop_flag = 2;   // all rows of this iteration have landed in colbuf
     __syncthreads();
     if (prof) { t1 = clock64(); tp[3] += t1 - t0; t0 = t1; }
     // sums over the tasks in the reference's order (bin ascending, shared before not shared)
@@ -837,7 +846,7 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
         const uint32_t dst = col < E ? tn_s + 8u * col : col < 2 * E ? td_s + 8u * (col - E) : ll_sa;
         em_st_async(em_mapa(dst, r), acc, em_mapa(bar_tot_s, r));
       }
-      if (warp == 0) em_mbar_wait(&bar_tot, iter & 1);       // the totals of all columns have landed here
+      if (warp == 0 && !em_mbar_wait(&bar_tot, iter & 1)) stop_flag = 2;    // the totals of all columns have landed here
       __syncthreads();
       if (tid == 0) { prev_s = ll_s; ll_s = ll_new; }
     }
@@ -857,7 +866,7 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
       while (s >= 0 && tn[s] == 0) s--;          // nearest epoch at or below e with a non-zero numerator
       rate[e] = (s >= 0) ? cand[s] : 0.0;
     }
-    if (tid == 0 && (ll_s / prev_s > 1.0 - 1e-7) && (iter > 1000)) stop_flag = 1;  // coal.cpp:3822
+    if (tid == 0 && stop_flag == 0 && (ll_s / prev_s > 1.0 - 1e-7) && (iter > 1000)) stop_flag = 1;  // coal.cpp:3822
     __syncthreads();
     if (prof) { t1 = clock64(); tp[5] += t1 - t0; t0 = t1; }
     if (stop_flag) break;
@@ -868,6 +877,7 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
     for (int e = tid; e < E; e += blockDim.x) rates_out[(size_t)rep * E + e] = rate[e];
     if (tid == 0) { iters_out[rep] = iter; ll_out[rep] = ll_s; }
   }
+  if (stop_flag == 2 && tid == 0) iters_out[rep] = -1;   // handshake timed out: reported as an error by the host
 }
 
 // E-step probe: one thread per age, plain stores
