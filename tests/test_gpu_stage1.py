@@ -171,3 +171,30 @@ def test_config5_all_pairs_small(handle):
     # asymmetric in target / reference: the swapped pair is a different estimate
     swapped = pairs_mod.all_pairs(handle, len(genomes), seed=3, bins="3,7,0.2", pairs=[(1, 0)], max_iter=60)
     assert not np.array_equal(swapped["rates"][0], res["rates"][0])
+
+
+def test_stage1_fuzz_shapes(handle):
+    """Random shapes: chromosome counts, empty chromosomes, tiny and mid-size row counts, coverages from
+    almost nothing to every site, odd rows, masks on either / both genomes -- bit-exact every time."""
+    rng = np.random.default_rng(2024)
+    for case in range(40):
+        n_chr = int(rng.integers(1, 6))
+        rows = [int(rng.choice([0, 1, 2, 37, 500, 4000, 20000], p=[.08, .05, .05, .12, .3, .3, .1])) for _ in range(n_chr)]
+        lens = [float(rng.choice([3e7, 9e7, 2.4e8])) for _ in range(n_chr)]
+        seed = int(rng.integers(1, 1 << 30))
+        sites = synth.make_sites(seed % 1000 + 7, rows, lens, weird=float(rng.choice([0.0, 0.1, 0.3])))
+        cov_t, cov_r = float(rng.choice([0.05, 0.5, 1.0])), float(rng.choice([0.05, 0.7, 1.0]))
+        gt = synth.make_genome(seed % 977 + 1, sites, cov_t, mean_extra_reads=float(rng.choice([0.0, 1.0, 4.0])), weird=0.1)
+        gr = synth.make_genome(seed % 991 + 2, sites, cov_r, weird=0.1)
+        tm = rm = None
+        if rng.random() < 0.4:
+            tm = [synth.make_mask(case * 10 + c, int(L), float(rng.choice([0.1, 0.6])), run_lo=100, run_hi=200000) for c, L in enumerate(lens)]
+        if rng.random() < 0.4:
+            rm = [synth.make_mask(case * 10 + 5 + c, int(L), 0.3, run_lo=100, run_hi=200000) for c, L in enumerate(lens)]
+        o = po.stage1(sites, gt, gr, seed=seed, tmask=tm, rmask=rm)
+        handle.load(sites, gt, gr, tm, rm)
+        if o["num_blocks"] < 0:
+            with pytest.raises(api._lib.ColateError):
+                handle.stage1(api.mt_seed(seed))
+            continue
+        _compare_stage1(o, handle.stage1(api.mt_seed(seed)))
