@@ -24,6 +24,8 @@ for slot, g in ((0, gt), (1, gr)):
                                           api.ptr(g.bp), api.ptr(g.aaf), api.ptr(g.daf), api.ptr(al), 0))
 torch.cuda.synchronize(); dist.barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+res = cdist.mut_sharded(cdist.CudaBackend(h), seed=1, bins="3,7,0.1", num_bootstraps=R, device="cuda")   # cold: allocations, NCCL connections
+torch.cuda.synchronize(); dist.barrier()
 e0.record()
 res = cdist.mut_sharded(cdist.CudaBackend(h), seed=1, bins="3,7,0.1", num_bootstraps=R, device="cuda")
 e1.record(); torch.cuda.synchronize()
@@ -33,5 +35,5 @@ if rank == 0:
     one = api.mut(h1, seed=1, bins="3,7,0.1", num_bootstraps=R)
     ok = (res.num_blocks == one["num_blocks"] and np.array_equal(res.block_stats, one["stage1"].block_stats)
           and np.array_equal(res.rates, one["rates"]) and np.array_equal(res.iters, one["iters"]))
-    print(f"dist_check world={world} rows={rows} R={R}: {'PASS' if ok else 'FAIL'} (bit-identical to 1 GPU), sharded pass {ms.item():.1f} ms", flush=True)
+    print(f"dist_check world={world} rows={rows} R={R}: {'PASS' if ok else 'FAIL'} (bit-identical to 1 GPU), sharded pass (second, warm) {ms.item():.1f} ms", flush=True)
 dist.barrier(); dist.destroy_process_group()
