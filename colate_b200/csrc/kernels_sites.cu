@@ -8,6 +8,8 @@
 //               uniform stream in HBM, exact bin index, warp-aggregated histogram updates in
 //               per-warp shared-memory histograms (no atomics), one partial per tile
 //   k_reduce    fixed-order sum of the tile partials of each genomic block
+#include <cuda.h>
+
 #include "device.cuh"
 #include "exact_sum.cuh"
 
@@ -345,108 +347,133 @@ __device__ __forceinline__ int slot_of_age(double a, const uint16_t* lut, const 
   return p;
 }
 
-constexpr int SW = 8;                 // consumer warps = used rows per pipeline stage
-#ifndef SAMPLE_STAGES_
-#define SAMPLE_STAGES_ 4
+constexpr int TS_ROWS = 32;            // used rows per tile: one per lane
+constexpr int CH_WORDS = 20;           // engine words per chunk and row = 10 samples
+constexpr int N_CHUNK = 200 / CH_WORDS;
+constexpr int ROW_BYTES = 192;         // per-row sample counts, one byte per count slot (188 used)
+constexpr int TILE_BYTES = ROW_BYTES * TS_ROWS;   // count tile of 32 rows: [slot][row] bytes
+#ifndef S2_WARPS_
+#define S2_WARPS_ 4
 #endif
-constexpr int SAMPLE_STAGES = SAMPLE_STAGES_;
-constexpr int ROW_BYTES = 192;        // per-row sample counts, one byte per age bin (185 used)
-#ifndef ROW_COPIES
-#define ROW_COPIES 2
+#ifndef S2_RING_
+#define S2_RING_ 2
 #endif
-#ifndef ROW_STRIDE64_
-#define ROW_STRIDE64_ 24
-#endif
-constexpr int ROW_STRIDE64 = ROW_STRIDE64_;      // 64-bit words between the two shared-memory copies of a row (208 B: staggers the banks)
-struct __align__(16) SampleStage {
-  uint4 words[SW][50];                // 200 engine words per used row
-  double4 hdr[SW];
+constexpr int S2_WARPS = S2_WARPS_;    // warps per CTA, each with its own tile, ring and counters
+constexpr int S2_RING = S2_RING_;      // chunk slots per warp (one being read, one in flight): 11 KB per warp -> 16 warps per SM
+struct __align__(128) SampleWarp {
+  uint32_t chunk[S2_RING][TS_ROWS][CH_WORDS];   // TMA boxes: 32 rows x 80 B of the generator stream
+  uint32_t cnt[ROW_WORDS][TS_ROWS];             // this tile's counts: word w of lane L = slots 4w..4w+3 of row L (bank = lane)
+  uint64_t full[S2_RING];
 };
 
-// THE per-mutation kernel.  Streams the reference's generator output (800 B per used row) and
-// the row headers from HBM through a TMA bulk-copy ring in shared memory; each consumer warp
-// takes one row per stage: 100 uniform ages -> exact bin index -> per-row counts per bin
-// (byte-packed shared-memory counters) -> one 192-byte count row back to HBM.  (MATCH.ANY was
-// measured at ~33 cycles per warp instruction per SM on B200 -- the ADU pipe -- and capped this
-// kernel at 30 % of HBM peak; a shared-memory atomic add costs ~5.)
-__global__ void __launch_bounds__((SW + 1) * 32)
-k_sample(int64_t n_used, const uint32_t* __restrict__ stream, const double4* __restrict__ hdr_g,
-         const double* __restrict__ thrA_g, const uint16_t* __restrict__ lut_g, uint8_t* __restrict__ cnt, int64_t* misc)
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
+// THE per-mutation kernel.  Thread = used row: a warp owns a tile of 32 consecutive used rows and streams
+// their 100 x 2 generator words (800 B per row) from HBM in ten 2-D TMA boxes of 32 rows x 80 B (a tensor
+// map over the stream as a [rows][200 words] matrix), three boxes in flight per warp.  Each lane turns its
+// row's word pairs into uniform ages -> exact bin index (slot_of_age) -> its own column of the tile's
+// count bytes in shared memory: no atomics, no idle lanes, every instruction serves 32 samples.  The tile
+// [188 slots][32 rows] leaves as 6 KB of coalesced stores; k_replay reads it back the same way.
+// (History: MATCH.ANY aggregation 33 cycles per warp instruction on the ADU pipe -> 12 % of HBM peak;
+// warp-per-row with shared-memory atomics -> 47 %, bound by issue slots and atomic conflicts.)
+__global__ void __launch_bounds__(S2_WARPS * 32)
+k_sample(const __grid_constant__ CUtensorMap tmap, int64_t n_used, const double4* __restrict__ hdr_g,
+         const double* __restrict__ thrA_g, const uint16_t* __restrict__ lut_g, uint8_t* __restrict__ cnt_tiles)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  SampleStage* st = (SampleStage*)smem_raw;
-  uint64_t* full = (uint64_t*)(smem_raw + sizeof(SampleStage) * SAMPLE_STAGES);
-  uint64_t* empty = full + SAMPLE_STAGES;
-  double* thrA = (double*)(empty + SAMPLE_STAGES);                 // [192] thresholds by count slot
-  uint16_t* lut = (uint16_t*)(thrA + 192);                     // [LUT_N]
-  uint64_t* rows = (uint64_t*)(lut + ((LUT_N + 15) & ~15));         // [SW][ROW_COPIES][ROW_STRIDE64]: per-warp count rows
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t n_stage = (n_used + SW - 1) / SW;
+  SampleWarp& sw = ((SampleWarp*)smem_raw)[warp];
+  double* thrA = (double*)(smem_raw + sizeof(SampleWarp) * S2_WARPS);   // [192] thresholds by count slot
+  uint16_t* lut = (uint16_t*)(thrA + 192);                                // [LUT_N]
   for (int i = threadIdx.x; i < 192; i += blockDim.x) thrA[i] = thrA_g[i];
   for (int i = threadIdx.x; i < LUT_N; i += blockDim.x) lut[i] = lut_g[i];
-  for (int i = threadIdx.x; i < SW * ROW_COPIES * ROW_STRIDE64; i += blockDim.x) rows[i] = 0;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < SAMPLE_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], SW); }
+  for (int w = 0; w < ROW_WORDS; w++) sw.cnt[w][lane] = 0;
+  if (lane == 0) {
+    for (int i = 0; i < S2_RING; i++) mbar_init(&sw.full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  if (warp == SW) {  // producer warp: one lane drives the TMA ring
-    if (lane == 0) {
-      int it = 0;
-      for (int64_t sid = blockIdx.x; sid < n_stage; sid += gridDim.x, it++) {
-        const int slot = it % SAMPLE_STAGES;
-        mbar_wait(&empty[slot], ((it / SAMPLE_STAGES) & 1) ^ 1);
-        const int64_t r0 = sid * SW;
-        const int nrow = (int)min((int64_t)SW, n_used - r0);
-        mbar_expect_tx(&full[slot], (uint32_t)nrow * (800 + 32));
-        bulk_g2s(&st[slot].words[0][0], stream + 200 * r0, (uint32_t)nrow * 800, &full[slot]);
-        bulk_g2s(&st[slot].hdr[0], hdr_g + r0, (uint32_t)nrow * 32, &full[slot]);
-      }
+  const int64_t n_tile = (n_used + TS_ROWS - 1) / TS_ROWS;
+  const int64_t w0 = (int64_t)blockIdx.x * S2_WARPS + warp, nw = (int64_t)gridDim.x * S2_WARPS;
+  const int64_t my_tiles = w0 < n_tile ? (n_tile - w0 + nw - 1) / nw : 0;
+  const int64_t G = my_tiles * N_CHUNK;                        // chunks this warp consumes, in order
+  auto issue = [&](int64_t g) {                                // chunk g of this warp -> its ring slot
+    const int64_t tile = w0 + (g / N_CHUNK) * nw;
+    const int slot = (int)(g % S2_RING);
+    mbar_expect_tx(&sw.full[slot], TS_ROWS * CH_WORDS * 4);
+    tma_load_2d(&sw.chunk[slot][0][0], &tmap, (int)(g % N_CHUNK) * CH_WORDS, (int)(tile * TS_ROWS), &sw.full[slot]);
+  };
+  if (lane == 0)
+    for (int64_t g = 0; g < G && g < S2_RING - 1; g++) issue(g);
+  double lenp = 0.0, abd = 0.0;
+  bool have = false;
+  for (int64_t g = 0; g < G; g++) {
+    const int ch = (int)(g % N_CHUNK);
+    const int64_t tile = w0 + (g / N_CHUNK) * nw;
+    if (ch == 0) {
+      const int64_t r = tile * TS_ROWS + lane;
+      have = r < n_used;
+      if (have) { const double2 h = *(const double2*)&hdr_g[r]; lenp = h.x; abd = h.y; }
     }
-    return;
-  }
-
-  uint64_t* myrows = rows + (size_t)warp * ROW_COPIES * ROW_STRIDE64;           // two copies (odd / even lanes), bank-staggered
-  uint32_t* myrow = (uint32_t*)(myrows + (size_t)(lane & (ROW_COPIES - 1)) * ROW_STRIDE64);
-  int it = 0;
-  for (int64_t sid = blockIdx.x; sid < n_stage; sid += gridDim.x, it++) {
-    const int slot = it % SAMPLE_STAGES;
-    mbar_wait(&full[slot], (it / SAMPLE_STAGES) & 1);
-    const int64_t r = sid * SW + warp;
-    if (r < n_used) {
-      const double4 h = st[slot].hdr[warp];
-      const double lenp = h.x, abd = h.y;
-      const uint4 q0 = st[slot].words[warp][lane];
-      const bool has1 = lane < 18;
-      uint4 q1 = q0;
-      if (has1) q1 = st[slot].words[warp][32 + lane];
-      // sampled_age = U * (age_end - age_begin) + age_begin, product and sum rounded separately
-      const int b0 = slot_of_age(__dadd_rn(__dmul_rn(u64_scaled(q0.x, q0.y), lenp), abd), lut, thrA);
-      const int b1 = slot_of_age(__dadd_rn(__dmul_rn(u64_scaled(q0.z, q0.w), lenp), abd), lut, thrA);
-      // per-row counts: one byte per age bin at its count slot (neighbouring bins in different words);
-      // shared-memory atomics resolve lanes that hit the same word (at most 100 per byte: no carry).
-      // Bin 185 (age out of range) is counted like any other and reported by k_replay.
-      atomicAdd(&myrow[b0 >> 2], 1u << (8 * (b0 & 3)));
-      atomicAdd(&myrow[b1 >> 2], 1u << (8 * (b1 & 3)));
-      if (has1) {
-        const int b2 = slot_of_age(__dadd_rn(__dmul_rn(u64_scaled(q1.x, q1.y), lenp), abd), lut, thrA);
-        const int b3 = slot_of_age(__dadd_rn(__dmul_rn(u64_scaled(q1.z, q1.w), lenp), abd), lut, thrA);
-        atomicAdd(&myrow[b2 >> 2], 1u << (8 * (b2 & 3)));
-        atomicAdd(&myrow[b3 >> 2], 1u << (8 * (b3 & 3)));
-      }
-      __syncwarp();
-      if (lane < ROW_BYTES / 8) {
-        uint64_t* rw = myrows;
-        uint64_t v = 0;                                          // byte-wise sum of the copies
+    __syncwarp();                                              // every lane is done with the slot of chunk g - 1
+    if (lane == 0 && g + S2_RING - 1 < G) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of that slot before the async write
+      issue(g + S2_RING - 1);
+    }
+    const int slot = (int)(g % S2_RING);
+    mbar_wait(&sw.full[slot], (uint32_t)((g / S2_RING) & 1));
+    if (have) {
+      // Ten samples as straight-line, branch-free code (the steps of different samples interleave):
+      // ages, LUT cells, the threshold compare (cells without a threshold compare against +inf in the
+      // spare slot 191: one broadcast address), then fire-and-forget shared-memory adds into the lane's
+      // own counter words.
+      const uint4* wq = (const uint4*)&sw.chunk[slot][lane][0];
+      double a[CH_WORDS / 2];
 #pragma unroll
-        for (int c = 0; c < ROW_COPIES; c++) { v += rw[c * ROW_STRIDE64 + lane]; rw[c * ROW_STRIDE64 + lane] = 0; }
-        ((uint64_t*)(cnt + (size_t)r * ROW_BYTES))[lane] = v;
+      for (int q = 0; q < CH_WORDS / 4; q++) {
+        const uint4 w = wq[q];
+        // sampled_age = U * (age_end - age_begin) + age_begin, product and sum rounded separately
+        a[2 * q] = __dadd_rn(__dmul_rn(u64_scaled(w.x, w.y), lenp), abd);
+        a[2 * q + 1] = __dadd_rn(__dmul_rn(u64_scaled(w.z, w.w), lenp), abd);
       }
+      int e[CH_WORDS / 2];
+#pragma unroll
+      for (int i = 0; i < CH_WORDS / 2; i++) {
+        const int cell = (__double2hiint(a[i]) >> LUT_SHIFT) - LUT_BASE;
+        e[i] = lut[max(0, min(cell, LUT_N - 1))];            // slot at the cell's lower edge | 0x8000: a threshold inside
+      }
+#pragma unroll
+      for (int i = 0; i < CH_WORDS / 2; i++) {
+        int p = e[i] & 0xff;
+        const double thr = thrA[(e[i] & 0x8000) ? p : 191];
+        const int pn = p + 4 >= ROW_SLOTS ? p + 4 - (ROW_SLOTS - 1) : p + 4;   // slot of the next bin
+        p = a[i] >= thr ? pn : p;
+        atomicAdd(&sw.cnt[p >> 2][lane], 1u << (8 * (p & 3)));   // own word, own bank: never a conflict, never waited for
+      }                                                          // (slot 185, age out of range, is reported by k_replay)
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[slot]);
+    if (ch == N_CHUNK - 1) {
+      // Tile done.  Lane L holds row L as 47 words of 4 slots; the tile leaves as [slot][row] bytes, so
+      // every quad of lanes transposes its 4 x 4 bytes (two shuffles + two byte permutes per word) and
+      // each lane stores "one slot, four rows": 32-byte runs per slot, full sectors.  Counters back to 0.
+      __syncwarp();
+      uint32_t* gt = (uint32_t*)(cnt_tiles + (size_t)tile * TILE_BYTES);
+      const uint32_t sel1 = (lane & 1) ? 0x3715u : 0x6240u, sel2 = (lane & 2) ? 0x3276u : 0x5410u;
+      const int j = lane & 3, rg = lane >> 2;
+#pragma unroll 4
+      for (int w = 0; w < ROW_WORDS; w++) {
+        const uint32_t x = sw.cnt[w][lane];
+        sw.cnt[w][lane] = 0;
+        const uint32_t t = __byte_perm(x, __shfl_xor_sync(0xffffffffu, x, 1), sel1);
+        const uint32_t z = __byte_perm(t, __shfl_xor_sync(0xffffffffu, t, 2), sel2);
+        gt[(4 * w + j) * (TS_ROWS / 4) + rg] = z;
+      }
+      gt[ROW_SLOTS * (TS_ROWS / 4) + lane] = 0;                 // slots 188..191 do not exist
+    }
   }
 }
 
@@ -456,7 +483,7 @@ constexpr int RP_ROWS = 8;      // rows collapsed into one exact update
 constexpr int RP_RANGES = 6;    // consumer warps: 32-bin ranges (192 >= 185 bins)
 constexpr int RP_THREADS = (RP_RANGES + 1) * 32;   // + 1 producer warp
 struct __align__(16) ReplayStage {
-  uint8_t cnt[RP_SITES][ROW_BYTES];
+  uint8_t cnt[ROW_BYTES][RP_SITES];   // one count tile of k_sample: [slot][row]
   double4 hdr[RP_SITES];
 };
 
@@ -492,7 +519,8 @@ __device__ __forceinline__ void replay_body(ReplayStage* st, uint64_t* full, uin
 {
   const int blk = blockIdx.x;
   const int64_t r0 = blk_rank_start[blk], r1 = blk_rank_start[blk + 1];
-  const int n_stage = (int)((r1 - r0 + RP_SITES - 1) / RP_SITES);
+  const int64_t t0 = r0 / RP_SITES;                               // the block's rows live in count tiles t0 .. t1
+  const int n_stage = r1 > r0 ? (int)((r1 - 1) / RP_SITES - t0 + 1) : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < RP_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], RP_RANGES); }
@@ -504,11 +532,10 @@ __device__ __forceinline__ void replay_body(ReplayStage* st, uint64_t* full, uin
       for (int it = 0; it < n_stage; it++) {
         const int slot = it % RP_STAGES;
         mbar_wait(&empty[slot], ((it / RP_STAGES) & 1) ^ 1);
-        const int64_t s0 = r0 + (int64_t)it * RP_SITES;
-        const int nrow = (int)min((int64_t)RP_SITES, r1 - s0);
-        mbar_expect_tx(&full[slot], (uint32_t)nrow * (ROW_BYTES + 32));
-        bulk_g2s(&st[slot].cnt[0][0], cnt + (size_t)s0 * ROW_BYTES, (uint32_t)nrow * ROW_BYTES, &full[slot]);
-        bulk_g2s(&st[slot].hdr[0], hdr_g + s0, (uint32_t)nrow * 32, &full[slot]);
+        const int64_t t = t0 + it;
+        mbar_expect_tx(&full[slot], (uint32_t)(TILE_BYTES + RP_SITES * 32));
+        bulk_g2s(&st[slot].cnt[0][0], cnt + (size_t)t * TILE_BYTES, TILE_BYTES, &full[slot]);
+        bulk_g2s(&st[slot].hdr[0], hdr_g + t * RP_SITES, RP_SITES * 32, &full[slot]);
       }
     }
     return;
@@ -521,21 +548,21 @@ __device__ __forceinline__ void replay_body(ReplayStage* st, uint64_t* full, uin
   for (int it = 0; it < n_stage; it++) {
     const int slot = it % RP_STAGES;
     mbar_wait(&full[slot], (it / RP_STAGES) & 1);
-    const int nrow = (int)min((int64_t)RP_SITES, r1 - (r0 + (int64_t)it * RP_SITES));
-    const uint8_t* cp = &st[slot].cnt[0][0] + cslot;
+    // rows of this tile that belong to the block ...
+    const int64_t g0r = (t0 + it) * RP_SITES;
+    const int lo = (int)max((int64_t)0, r0 - g0r), hi = (int)min((int64_t)RP_SITES, r1 - g0r);
+    uint32_t live = (hi >= 32 ? 0xffffffffu : (1u << hi) - 1u) & ~((1u << lo) - 1u);
+    const uint4* cw = (const uint4*)&st[slot].cnt[cslot][0];      // this bin's counts in the tile's 32 rows
     const double* hp = (const double*)&st[slot].hdr[0] + 2 + WHICH;
-    // rows that exist and add to this histogram (-0.0 weight: nothing to add), one bit per row
-    uint32_t live = nrow >= 32 ? 0xffffffffu : (1u << nrow) - 1u;
+    // ... and add to this histogram (-0.0 weight: nothing to add), one bit per row
     if (WHICH == 0) live &= __ballot_sync(0xffffffffu, ((const int*)(hp + 4 * lane))[1] >= 0);
-#pragma unroll 1
-    for (int g0 = 0; g0 < nrow; g0 += RP_ROWS) {
-      // this bin's counts in the run's rows, one byte each (<= 100)
-      uint32_t cs_lo = 0, cs_hi = 0;
+    const uint4 ca = cw[0], cb = cw[1];
+    const uint32_t cw8[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
 #pragma unroll
-      for (int i = 0; i < RP_ROWS; i++) {
-        const uint32_t c = cp[(g0 + i) * ROW_BYTES];
-        if (i < 4) cs_lo |= c << (8 * i); else cs_hi |= c << (8 * (i - 4));
-      }
+    for (int run = 0; run < RP_SITES / RP_ROWS; run++) {
+      const int g0 = run * RP_ROWS;
+      // this bin's counts in the run's rows, one byte each (<= 100)
+      uint32_t cs_lo = cw8[2 * run], cs_hi = cw8[2 * run + 1];
       const uint32_t lv = live >> g0;
       cs_lo &= (((lv & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu;        // bit i -> byte i
       cs_hi &= ((((lv >> 4) & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu;
@@ -548,25 +575,26 @@ __device__ __forceinline__ void replay_body(ReplayStage* st, uint64_t* full, uin
       const double hu = __hiloint2double((E - 53) << 20, 0);           // ulp(acc) / 2
       const int wmax_hi = (E - 1) << 20;                               // w must stay below 2^(E-1)
       bool bad = (E <= 54) | (E >= 0x7fe);
-      double t0 = 0.0, t1 = 0.0;                                       // exact sums: any order
+      double t0s = 0.0, t1s = 0.0;                                     // exact sums: any order
 #pragma unroll
       for (int i = 0; i < RP_ROWS; i++) {
         const int c = ((i < 4 ? cs_lo : cs_hi) >> (8 * (i & 3))) & 0xff;
-        const double w = hp[4 * (g0 + i)];
+        const double w = ((lv >> i) & 1u) ? hp[4 * (g0 + i)] : 0.0;    // rows of other blocks / past the end: not ours
         const double d = __dsub_rn(__dadd_rn(w, M), M);
         const double err = __dsub_rn(w, d);
         bad |= (c != 0) & ((fabs(err) == hu) | (__double2hiint(w) >= wmax_hi));
-        if (i & 1) t1 = __fma_rn((double)c, d, t1); else t0 = __fma_rn((double)c, d, t0);
+        if (i & 1) t1s = __fma_rn((double)c, d, t1s); else t0s = __fma_rn((double)c, d, t0s);
       }
-      const double accn = __dadd_rn(acc, __dadd_rn(t0, t1));
+      const double accn = __dadd_rn(acc, __dadd_rn(t0s, t1s));
       bad |= (__double2hiint(accn) >> 20) != E;
       bad &= any;
       if (__any_sync(0xffffffffu, bad)) {
         if (bad) {
 #pragma unroll 1
-          for (int r = g0; r < min(nrow, g0 + RP_ROWS); r++) {
+          for (int r = g0; r < g0 + RP_ROWS; r++) {
+            if (!((live >> r) & 1u)) continue;
             const double w = hp[4 * r];
-            const int c = cp[r * ROW_BYTES];
+            const int c = st[slot].cnt[cslot][r];
             if (c != 0 && (__double_as_longlong(w) << 1) != 0 && __double2hiint(w) >= 0)   // x + 0.0 == x
               acc = replay_row(acc, w, c);
           }
@@ -696,8 +724,9 @@ int run_sample(colate_handle* h, const uint32_t* stream_local, int)
   GenomeDev& R = h->genomes[h->ref_slot];
   cudaStream_t s = h->stream;
   const size_t un = (size_t)std::max<int64_t>(nu, 1);
-  CK(h->u_hdr.ensure(un * 32 + 64)); CK(h->u_eb2.ensure(un + 64)); CK(h->u_ews.ensure(un * 8 + 64)); CK(h->u_ewn.ensure(un * 8 + 64));
-  CK(h->u_blk.ensure(un * 4 + 64)); CK(h->u_cnt.ensure(un * ROW_BYTES + 64));
+  const size_t un32 = (un + TS_ROWS - 1) / TS_ROWS * TS_ROWS;   // headers and counts are read / written in tiles of 32 rows
+  CK(h->u_hdr.ensure(un32 * 32 + 64)); CK(h->u_eb2.ensure(un + 64)); CK(h->u_ews.ensure(un * 8 + 64)); CK(h->u_ewn.ensure(un * 8 + 64));
+  CK(h->u_blk.ensure(un * 4 + 64)); CK(h->u_cnt.ensure(un32 * ROW_BYTES + 64));
   CK(h->blk_rank_start.ensure((MAX_BLOCKS + 2) * 8));
   CK(h->out_f.ensure((size_t)MAX_BLOCKS * 4 * NBINS * 8)); CK(h->out_n.ensure((size_t)MAX_BLOCKS * 3 * NBINS * 8));
   CK(cudaEventRecord(h->ev[2], s));
@@ -714,15 +743,34 @@ int run_sample(colate_handle* h, const uint32_t* stream_local, int)
   h->launches += 1;
   CK(cudaEventRecord(h->ev[3], s));
   if (nu > 0) {
-    const size_t smem = sizeof(SampleStage) * SAMPLE_STAGES + 2 * SAMPLE_STAGES * 8 + 192 * 8 + 2 * ((LUT_N + 15) & ~15) +
-                        (size_t)SW * ROW_COPIES * ROW_STRIDE64 * 8;
+    // tensor map over the generator stream as a [nu rows][200 words] matrix, boxes of 32 rows x 20 words
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+      if (!fn || qres != cudaDriverEntryPointSuccess) return fail(COLATE_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+      encode = (EncodeFn)fn;
+    }
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {200, (cuuint64_t)nu};
+    const cuuint64_t gstride[1] = {800};
+    const cuuint32_t box[2] = {CH_WORDS, TS_ROWS}, estr[2] = {1, 1};
+    const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)stream_local, gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(COLATE_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")");
+    const size_t smem = sizeof(SampleWarp) * S2_WARPS + 192 * 8 + 2 * ((LUT_N + 15) & ~15);
     CK(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t n_stage = (nu + SW - 1) / SW;
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / (smem + 1024)));
+    const int64_t n_tile = (nu + TS_ROWS - 1) / TS_ROWS;
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (224 * 1024) / (smem + 1024)));
     if (const char* e = getenv("COLATE_SAMPLE_CTAS_PER_SM")) per_sm = std::max(1, atoi(e));
-    const int grid = (int)std::min<int64_t>(n_stage, (int64_t)h->sm_count * per_sm);
-    k_sample<<<grid, (SW + 1) * 32, smem, s>>>(nu, stream_local, h->u_hdr.as<double4>(), h->thrA.as<double>(), h->lut.as<uint16_t>(),
-                                                h->u_cnt.as<uint8_t>(), h->misc.as<int64_t>());
+    const int grid = (int)std::min<int64_t>((n_tile + S2_WARPS - 1) / S2_WARPS, (int64_t)h->sm_count * per_sm);
+    k_sample<<<grid, S2_WARPS * 32, smem, s>>>(tmap, nu, h->u_hdr.as<double4>(), h->thrA.as<double>(), h->lut.as<uint16_t>(),
+                                               h->u_cnt.as<uint8_t>());
     h->launches += 1;
   }
   CK(cudaEventRecord(h->ev[4], s));
