@@ -579,7 +579,7 @@ __device__ __forceinline__ void replay_body(ReplayStage* st, uint64_t* full, uin
 #pragma unroll
       for (int i = 0; i < RP_ROWS; i++) {
         const int c = ((i < 4 ? cs_lo : cs_hi) >> (8 * (i & 3))) & 0xff;
-        const double w = ((lv >> i) & 1u) ? hp[4 * (g0 + i)] : 0.0;    // rows of other blocks / past the end: not ours
+        const double w = hp[4 * (g0 + i)];                             // (rows of other blocks carry count 0 here; the padding rows are zeroed)
         const double d = __dsub_rn(__dadd_rn(w, M), M);
         const double err = __dsub_rn(w, d);
         bad |= (c != 0) & ((fabs(err) == hu) | (__double2hiint(w) >= wmax_hi));
@@ -729,6 +729,8 @@ int run_sample(colate_handle* h, const uint32_t* stream_local, int)
   CK(h->u_blk.ensure(un * 4 + 64)); CK(h->u_cnt.ensure(un32 * ROW_BYTES + 64));
   CK(h->blk_rank_start.ensure((MAX_BLOCKS + 2) * 8));
   CK(h->out_f.ensure((size_t)MAX_BLOCKS * 4 * NBINS * 8)); CK(h->out_n.ensure((size_t)MAX_BLOCKS * 3 * NBINS * 8));
+  if (un32 > (size_t)nu)   // header rows between the last used row and the end of its tile: read by k_replay, never written
+    CK(cudaMemsetAsync(h->u_hdr.as<double4>() + nu, 0, (un32 - (size_t)nu) * 32, s));
   CK(cudaEventRecord(h->ev[2], s));
   if (n > 0) {
     k_compact<<<grid_for(n, 256), 256, 0, s>>>(n, h->n_chr, h->site_off.as<int64_t>(), h->pos.as<int32_t>(), h->ab.as<float>(),
