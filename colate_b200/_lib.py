@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcolate_b200.so")
+# COLATE_B200_LIB: another build of the same library (kernel tuning variants, tools/sample_variants.py)
+LIB_PATH = os.environ.get("COLATE_B200_LIB") or os.path.join(HERE, "libcolate_b200.so")
 
 NBINS = 185
 MAX_BLOCKS = 500
@@ -88,6 +89,8 @@ TEST_HOOKS = {
     "colate_test_bin_thresholds": (C.c_int, [f64]),
     "colate_test_add_repeated": (C.c_double, [C.c_double, C.c_double, C.c_int]),
     "colate_test_libm": (C.c_int, [VP, C.c_int, C.c_int, f64, f64]),
+    "colate_test_bin_fast": (C.c_int, [VP, C.c_int, f64, i32, i32]),
+    "colate_test_bin_sweep": (C.c_int, [VP, C.c_uint32, C.c_uint32, _p(dtype=np.uint64, flags="C_CONTIGUOUS")]),
     "colate_test_mt_stream": (C.c_int, [VP, u32, C.c_int64, C.c_int64, C.c_int, u32]),
 }
 

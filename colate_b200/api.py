@@ -282,6 +282,20 @@ class Handle:
         check(lib().colate_test_libm(self._h, {"exp": 0, "log": 1, "log1p": 2}[which], x.shape[0], x, y))
         return y
 
+    def bin_fast(self, ages):
+        """Test hook: k_sample's table-free age-bin index (-1 = sample flagged for the exact table) and the exact one."""
+        a = np.ascontiguousarray(ages, dtype=np.float64)
+        fast, exact = np.zeros(a.shape[0], dtype=np.int32), np.zeros(a.shape[0], dtype=np.int32)
+        check(lib().colate_test_bin_fast(self._h, a.shape[0], a, fast, exact))
+        return fast, exact
+
+    def bin_sweep(self, lo_bits, hi_bits):
+        """Test hook: every float with bit pattern in [lo, hi) through both bin indices on the device:
+        (flagged, unflagged mismatches, max |t_fast - t| in 1e-9)."""
+        out = np.zeros(3, dtype=np.uint64)
+        check(lib().colate_test_bin_sweep(self._h, lo_bits, hi_bits, out))
+        return int(out[0]), int(out[1]), int(out[2]) * 1e-9
+
     def mt_stream(self, mt_state, word0, n_words, log2_chunk_sites=3):
         """Test hook: engine words [word0, word0+n) generated by the device path (+ window after)."""
         out = np.zeros(n_words + MT_WORDS, dtype=np.uint32)

@@ -390,6 +390,21 @@ int colate_test_libm(colate_handle* h, int which, int n, const double* x, double
   return run_libm(h, which, n, x, y);
 }
 
+// test hooks: k_sample's table-free age-bin index (fast[i] = -1 where the kernel would consult the exact
+// table) next to the exact index, on given ages / swept over all floats with bit patterns in [lo, hi)
+int colate_test_bin_fast(colate_handle* h, int n, const double* ages, int32_t* fast, int32_t* exact)
+{
+  if (!h || n <= 0 || !ages || !fast || !exact) return fail(COLATE_ERR_ARG, "colate_test_bin_fast: bad arguments");
+  CK(cudaSetDevice(h->device));
+  return run_test_bin_fast(h, n, ages, fast, exact);
+}
+int colate_test_bin_sweep(colate_handle* h, uint32_t lo_bits, uint32_t hi_bits, uint64_t* out3)
+{
+  if (!h || !out3 || hi_bits < lo_bits || hi_bits > 0x7f800000u) return fail(COLATE_ERR_ARG, "colate_test_bin_sweep: bad arguments");
+  CK(cudaSetDevice(h->device));
+  return run_test_bin_sweep(h, lo_bits, hi_bits, out3);
+}
+
 // test hook: raw engine words [word0, word0+n) of the stream behind `mt_state`, via the device path
 int colate_test_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int64_t n_words, int log2_chunk_sites,
                           uint32_t* out)

@@ -103,6 +103,8 @@ namespace colate {
 int run_join(colate_handle* h, int slot);
 int run_flags(colate_handle* h, int tslot, int rslot);
 int run_sample(colate_handle* h, const uint32_t* stream_local, int block_base_unused);
+int run_test_bin_fast(colate_handle* h, int n, const double* a_host, int32_t* fast_host, int32_t* exact_host);
+int run_test_bin_sweep(colate_handle* h, uint32_t lo_bits, uint32_t hi_bits, uint64_t* out3_host);
 // kernels_mt.cu
 int run_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int64_t n_words, int log2_chunk_sites,
                   uint32_t** stream_at_word0, uint32_t* window_after /* host, may be null */);

@@ -17,15 +17,15 @@ constexpr int NTHR = NBINS + 1;  // thr10[1..185]; index 0 unused
 constexpr int LUT_SHIFT = 15;
 constexpr int LUT_BASE = 0x3FB00000 >> LUT_SHIFT;
 constexpr int LUT_N = (0x41700000 >> LUT_SHIFT) - LUT_BASE;
-// Per-row sample counts travel as one byte per age bin, bins interleaved over 47 32-bit words:
-// bin k lives in byte k / 47 of word k % 47, so the neighbouring bins one row's samples fall into
-// hit different words (shared-memory atomics on one word serialise).  slot = byte offset in the row.
+// Per-row sample counts travel as one byte per age bin: 47 32-bit words per row, bin k in byte k & 3 of
+// word k >> 2 (k_sample keeps one row per lane, so a row's samples never meet another row's in a word).
+// slot = byte offset in the row.
 constexpr int ROW_WORDS = 47;
 constexpr int ROW_SLOTS = 4 * ROW_WORDS;  // 188 >= NBINS + 1 (bin 185 = "age out of range")
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-constexpr int slot_of_bin(int k) { return 4 * (k % ROW_WORDS) + k / ROW_WORDS; }
+constexpr int slot_of_bin(int k) { return k; }
 
 // error plumbing (thread-local message behind colate_last_error())
 void set_error(const std::string& msg);
@@ -61,6 +61,8 @@ int colate_test_jump_window_host(const uint32_t* w, int q, uint32_t* out);
 int colate_test_bin_thresholds(double* thr10);
 double colate_test_add_repeated(double acc, double w, int c);
 int colate_test_libm(colate_handle* h, int which, int n, const double* x, double* y);
+int colate_test_bin_fast(colate_handle* h, int n, const double* ages, int32_t* fast, int32_t* exact);
+int colate_test_bin_sweep(colate_handle* h, uint32_t lo_bits, uint32_t hi_bits, uint64_t* out3);
 int colate_test_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int64_t n_words,
                           int log2_chunk_sites, uint32_t* out);
 }

@@ -342,7 +342,7 @@ __device__ __forceinline__ int slot_of_age(double a, const uint16_t* lut, const 
   int p = lut[cell];           // bit 15: an age-bin threshold lies inside this cell (about 1 cell in 5)
   if (p & 0x8000) {
     p &= 0xff;
-    if (a >= thrP[p]) { p += 4; if (p >= ROW_SLOTS) p -= ROW_SLOTS - 1; }   // slot of the next bin
+    if (a >= thrP[p]) p += 1;   // slot of the next bin
   }
   return p;
 }
@@ -358,10 +358,16 @@ constexpr int TILE_BYTES = ROW_BYTES * TS_ROWS;   // count tile of 32 rows: [slo
 #ifndef S2_RING_
 #define S2_RING_ 2
 #endif
+#ifndef S2_BOXES_
+#define S2_BOXES_ 1
+#endif
 constexpr int S2_WARPS = S2_WARPS_;    // warps per CTA, each with its own tile, ring and counters
-constexpr int S2_RING = S2_RING_;      // chunk slots per warp (one being read, one in flight): 11 KB per warp -> 16 warps per SM
+constexpr int S2_RING = S2_RING_;      // ring slots per warp (one being read, the others in flight)
+constexpr int S2_BOXES = S2_BOXES_;    // TMA boxes (32 rows x 80 B) per ring slot = chunks handled per loop iteration
+constexpr int N_STEP = N_CHUNK / S2_BOXES;
+static_assert(N_CHUNK % S2_BOXES == 0, "boxes per slot must divide the 10 chunks of a row");
 struct __align__(128) SampleWarp {
-  uint32_t chunk[S2_RING][TS_ROWS][CH_WORDS];   // TMA boxes: 32 rows x 80 B of the generator stream
+  uint32_t chunk[S2_RING][S2_BOXES][TS_ROWS][CH_WORDS];   // TMA boxes: 32 rows x 80 B of the generator stream (row stride 20 words: conflict-free LDS.128)
   uint32_t cnt[ROW_WORDS][TS_ROWS];             // this tile's counts: word w of lane L = slots 4w..4w+3 of row L (bank = lane)
   uint64_t full[S2_RING];
 };
@@ -374,12 +380,75 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, 
 
 // THE per-mutation kernel.  Thread = used row: a warp owns a tile of 32 consecutive used rows and streams
 // their 100 x 2 generator words (800 B per row) from HBM in ten 2-D TMA boxes of 32 rows x 80 B (a tensor
-// map over the stream as a [rows][200 words] matrix), three boxes in flight per warp.  Each lane turns its
-// row's word pairs into uniform ages -> exact bin index (slot_of_age) -> its own column of the tile's
-// count bytes in shared memory: no atomics, no idle lanes, every instruction serves 32 samples.  The tile
+// map over the stream as a [rows][200 words] matrix), S2_RING - 1 boxes in flight per warp.  Each lane turns
+// its row's word pairs into uniform ages -> exact bin index -> its own column of the tile's count bytes in
+// shared memory: no conflicts, no idle lanes, every instruction serves 32 samples.  The tile
 // [188 slots][32 rows] leaves as 6 KB of coalesced stores; k_replay reads it back the same way.
+//
+// Bin index (coal.cpp:2265/2284: max(0,(int)round(log(10 a)*10)+1)) in the common case WITHOUT a table:
+//   r = fmaf(lg2.approx(float(a)), 10 ln 2, 10 ln 10 + 1.5 + 320)
+// is t + 320 with t = 10 ln(10 a) + 1.5, and the reference's bin is floor(t) wherever t is not within the
+// error of r of an integer.  For t in [-64, 192) r lies in the binade [256, 512): its float bit pattern IS a
+// fixed-point number with 15 fraction bits (bin = (bits >> 15) - KB, fraction = bits & 0x7fff), values
+// outside the binade compare below / above as integers and clamp to bin 0 / bin 185.  Error of r against
+// the reference's own boundary: lg2.approx 2 ulp at |lg| < 32 (2.6e-5 after the factor 6.93; swept over
+// every float by tests/test_gpu_stage1.py::test_lg2_error_bound), one rounding of the FMA to 2^-15
+// (1.5e-5), the rounded constants (2.5e-6 + 4.4e-7), float(a) and the reference's two float roundings
+// (coal.cpp:2253; 2e-6): < 4.7e-5.  A sample whose fraction is within [-4, +3] units of 2^-15 (1.2e-4 /
+// 9.2e-5) of an integer -- 1 in 4096 -- takes the exact threshold table (slot_of_age) instead, as does the
+// one generator pair in 2^32 whose uniform needs the "< 1" clamp of generate_canonical.
 // (History: MATCH.ANY aggregation 33 cycles per warp instruction on the ADU pipe -> 12 % of HBM peak;
-// warp-per-row with shared-memory atomics -> 47 %, bound by issue slots and atomic conflicts.)
+// warp-per-row with shared-memory atomics -> 47 %; lane-per-row with 64-bit chunk indexing and the LUT in
+// the main path -> 58 %, 470 instructions per 10 samples.)
+constexpr float S2_C1 = 6.931471805599453f;        // 10 ln 2
+constexpr float S2_C0 = 344.5258509299405f;        // 10 ln 10 + 1.5 + 320
+constexpr int S2_KB = (0x43800000 >> 15) + 64;     // (bits(r) >> 15) of t = 0
+static_assert(S2_KB % 4 == 0, "count words are addressed from the raw bits");
+__device__ __forceinline__ bool s2_unsure(uint32_t rbits) { return ((rbits + 4u) & 0x7ff8u) == 0u; }
+__device__ __forceinline__ uint32_t s2_rbits(double a)
+{
+  float lg;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(__double2float_rn(a)));
+  return __float_as_uint(__fmaf_rn(lg, S2_C1, S2_C0));
+}
+// raw bits (clamped as signed integers into the binade of bins 0 .. 185) -> bin
+__device__ __forceinline__ int s2_clamp(uint32_t rbits) { return min(max((int)rbits, S2_KB << 15), ((S2_KB + NBINS) << 15) | 0x7fff); }
+
+// test hooks: the table-free bin index against the exact one (threshold table), on given ages and swept
+// over every float in a range of bit patterns
+__global__ void k_test_bin_fast(int n, const double* __restrict__ a, const double* __restrict__ thrA, const uint16_t* __restrict__ lut,
+                                int32_t* __restrict__ fast, int32_t* __restrict__ exact)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t rb = s2_rbits(a[i]);
+  fast[i] = s2_unsure(rb) ? -1 : (s2_clamp(rb) >> 15) - S2_KB;
+  exact[i] = slot_of_age(a[i], lut, thrA);
+}
+__global__ void k_test_bin_sweep(uint32_t lo, uint32_t hi, const double* __restrict__ thrA, const uint16_t* __restrict__ lut,
+                                 unsigned long long* __restrict__ out /* flagged, unflagged mismatches, max |t_fast - t| * 1e9 */)
+{
+  unsigned long long flagged = 0, bad = 0, worst = 0;
+  for (uint64_t b = (uint64_t)lo + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b < hi; b += (uint64_t)gridDim.x * blockDim.x) {
+    const double a = (double)__uint_as_float((uint32_t)b);
+    const uint32_t rb = s2_rbits(a);
+    const int ex = slot_of_age(a, lut, thrA);
+    if (s2_unsure(rb)) flagged++;
+    else if ((s2_clamp(rb) >> 15) - S2_KB != ex) bad++;
+    const double t = 10.0 * log(10.0 * a) + 1.5 + 320.0;
+    if (t >= 256.0 && t < 512.0) {
+      const double e = fabs((double)__uint_as_float(rb) - t) * 1e9;
+      worst = max(worst, (unsigned long long)e);
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    flagged += __shfl_xor_sync(0xffffffffu, flagged, o);
+    bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    worst = max(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], flagged); atomicAdd(&out[1], bad); atomicMax(&out[2], worst); }
+}
+
 __global__ void __launch_bounds__(S2_WARPS * 32)
 k_sample(const __grid_constant__ CUtensorMap tmap, int64_t n_used, const double4* __restrict__ hdr_g,
          const double* __restrict__ thrA_g, const uint16_t* __restrict__ lut_g, uint8_t* __restrict__ cnt_tiles)
@@ -387,76 +456,98 @@ k_sample(const __grid_constant__ CUtensorMap tmap, int64_t n_used, const double4
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   SampleWarp& sw = ((SampleWarp*)smem_raw)[warp];
-  double* thrA = (double*)(smem_raw + sizeof(SampleWarp) * S2_WARPS);   // [192] thresholds by count slot
-  uint16_t* lut = (uint16_t*)(thrA + 192);                                // [LUT_N]
-  for (int i = threadIdx.x; i < 192; i += blockDim.x) thrA[i] = thrA_g[i];
-  for (int i = threadIdx.x; i < LUT_N; i += blockDim.x) lut[i] = lut_g[i];
   for (int w = 0; w < ROW_WORDS; w++) sw.cnt[w][lane] = 0;
   if (lane == 0) {
     for (int i = 0; i < S2_RING; i++) mbar_init(&sw.full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
+  __syncwarp();
 
-  const int64_t n_tile = (n_used + TS_ROWS - 1) / TS_ROWS;
-  const int64_t w0 = (int64_t)blockIdx.x * S2_WARPS + warp, nw = (int64_t)gridDim.x * S2_WARPS;
-  const int64_t my_tiles = w0 < n_tile ? (n_tile - w0 + nw - 1) / nw : 0;
-  const int64_t G = my_tiles * N_CHUNK;                        // chunks this warp consumes, in order
-  auto issue = [&](int64_t g) {                                // chunk g of this warp -> its ring slot
-    const int64_t tile = w0 + (g / N_CHUNK) * nw;
-    const int slot = (int)(g % S2_RING);
-    mbar_expect_tx(&sw.full[slot], TS_ROWS * CH_WORDS * 4);
-    tma_load_2d(&sw.chunk[slot][0][0], &tmap, (int)(g % N_CHUNK) * CH_WORDS, (int)(tile * TS_ROWS), &sw.full[slot]);
+  // 32-bit bookkeeping throughout (800 B of generator stream per used row keep n_used far below 2^36): tiles, chunk counters, ring phases
+  const uint32_t n_tile = (uint32_t)((n_used + TS_ROWS - 1) / TS_ROWS);
+  const uint32_t w0 = blockIdx.x * S2_WARPS + warp, nw = gridDim.x * S2_WARPS;
+  if (w0 >= n_tile) return;
+  const uint32_t my_tiles = (n_tile - w0 + nw - 1) / nw;
+  // producer side (lane 0): next ring slot to request = chunks pch .. pch + S2_BOXES - 1 of tile ptile
+  uint32_t ptile = w0, pch = 0, pslot = 0, pleft = my_tiles * N_STEP;
+  auto issue = [&]() {
+    mbar_expect_tx(&sw.full[pslot], S2_BOXES * TS_ROWS * CH_WORDS * 4);
+#pragma unroll
+    for (int b = 0; b < S2_BOXES; b++)
+      tma_load_2d(&sw.chunk[pslot][b][0][0], &tmap, (int)(pch + b) * CH_WORDS, (int)(ptile * TS_ROWS), &sw.full[pslot]);
+    pslot = pslot + 1 == S2_RING ? 0 : pslot + 1;
+    pch += S2_BOXES;
+    if (pch == N_CHUNK) { pch = 0; ptile += nw; }
+    pleft--;
   };
   if (lane == 0)
-    for (int64_t g = 0; g < G && g < S2_RING - 1; g++) issue(g);
-  double lenp = 0.0, abd = 0.0;
-  bool have = false;
-  for (int64_t g = 0; g < G; g++) {
-    const int ch = (int)(g % N_CHUNK);
-    const int64_t tile = w0 + (g / N_CHUNK) * nw;
-    if (ch == 0) {
-      const int64_t r = tile * TS_ROWS + lane;
-      have = r < n_used;
-      if (have) { const double2 h = *(const double2*)&hdr_g[r]; lenp = h.x; abd = h.y; }
-    }
-    __syncwarp();                                              // every lane is done with the slot of chunk g - 1
-    if (lane == 0 && g + S2_RING - 1 < G) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of that slot before the async write
-      issue(g + S2_RING - 1);
-    }
-    const int slot = (int)(g % S2_RING);
-    mbar_wait(&sw.full[slot], (uint32_t)((g / S2_RING) & 1));
-    if (have) {
-      // Ten samples as straight-line, branch-free code (the steps of different samples interleave):
-      // ages, LUT cells, the threshold compare (cells without a threshold compare against +inf in the
-      // spare slot 191: one broadcast address), then fire-and-forget shared-memory adds into the lane's
-      // own counter words.
-      const uint4* wq = (const uint4*)&sw.chunk[slot][lane][0];
-      double a[CH_WORDS / 2];
+    for (int i = 0; i < S2_RING - 1 && pleft; i++) issue();
+
+  // rows past the end of the last tile: length 0 at age 1 (a valid bin), increment 0
+  auto header = [&](uint32_t tile, double& lenp, double& abd, uint32_t& one) {
+    const int64_t r = (int64_t)tile * TS_ROWS + lane;
+    lenp = 0.0; abd = 1.0; one = 0;
+    if (r < n_used) { const double2 h = *(const double2*)&hdr_g[r]; lenp = h.x; abd = h.y; one = 1; }
+  };
+  double lenp_n, abd_n;
+  uint32_t one_n;
+  header(w0, lenp_n, abd_n, one_n);
+  uint32_t cslot = 0, cphase = 0;
+  const uint32_t cnt_base = smem_u32(&sw.cnt[0][lane]) - (uint32_t)(S2_KB >> 2) * (TS_ROWS * 4);
+  constexpr int NS = S2_BOXES * CH_WORDS / 2;                      // samples per loop iteration and lane
+
+  for (uint32_t ti = 0, tile = w0; ti < my_tiles; ti++, tile += nw) {
+    const double lenp = lenp_n, abd = abd_n;
+    const uint32_t one = one_n;
+    if (ti + 1 < my_tiles) header(tile + nw, lenp_n, abd_n, one_n);   // next tile's header: in flight during this tile
+#pragma unroll 1
+    for (int st = 0; st < N_STEP; st++) {
+      __syncwarp();                                              // every lane is done with the slot of the previous step
+      if (lane == 0 && pleft) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of that slot before the async write
+        issue();
+      }
+      mbar_wait(&sw.full[cslot], cphase);
+      const uint32_t* wbase = &sw.chunk[cslot][0][lane][0];
+      cslot = cslot + 1 == S2_RING ? 0 : cslot + 1;
+      cphase ^= cslot == 0;
+      auto words = [&](int i) { return *(const uint2*)(wbase + (i / (CH_WORDS / 2)) * (TS_ROWS * CH_WORDS) + 2 * (i % (CH_WORDS / 2))); };
+      // NS samples as straight-line code (the steps of different samples interleave)
+      uint32_t rb[NS];
+      bool rare = false;
 #pragma unroll
-      for (int q = 0; q < CH_WORDS / 4; q++) {
-        const uint4 w = wq[q];
+      for (int i = 0; i < NS; i++) {
+        const uint2 w = words(i);
+        // generate_canonical: (x1 + x2 2^32) / 2^64 with one rounding (I2F.F64.U64, the 2^-64 sits in lenp);
         // sampled_age = U * (age_end - age_begin) + age_begin, product and sum rounded separately
-        a[2 * q] = __dadd_rn(__dmul_rn(u64_scaled(w.x, w.y), lenp), abd);
-        a[2 * q + 1] = __dadd_rn(__dmul_rn(u64_scaled(w.z, w.w), lenp), abd);
+        const double v = __ull2double_rn(((unsigned long long)w.y << 32) | w.x);
+        rare |= w.y == 0xffffffffu;                              // v may round to 2^64: needs the clamp below 1
+        const double a = __dadd_rn(__dmul_rn(v, lenp), abd);
+        rb[i] = s2_rbits(a);
+        rare |= s2_unsure(rb[i]);
       }
-      int e[CH_WORDS / 2];
+      if (__any_sync(0xffffffffu, rare)) {
+        // exact path for the flagged samples: clamped uniform, threshold table (global memory, L1-resident)
 #pragma unroll
-      for (int i = 0; i < CH_WORDS / 2; i++) {
-        const int cell = (__double2hiint(a[i]) >> LUT_SHIFT) - LUT_BASE;
-        e[i] = lut[max(0, min(cell, LUT_N - 1))];            // slot at the cell's lower edge | 0x8000: a threshold inside
+        for (int i = 0; i < NS; i++) {
+          const uint2 w = words(i);
+          if (w.y == 0xffffffffu || s2_unsure(rb[i])) {
+            const double ax = __dadd_rn(__dmul_rn(u64_scaled(w.x, w.y), lenp), abd);
+            rb[i] = (uint32_t)(slot_of_age(ax, lut_g, thrA_g) + S2_KB) << 15;
+          }
+        }
       }
 #pragma unroll
-      for (int i = 0; i < CH_WORDS / 2; i++) {
-        int p = e[i] & 0xff;
-        const double thr = thrA[(e[i] & 0x8000) ? p : 191];
-        const int pn = p + 4 >= ROW_SLOTS ? p + 4 - (ROW_SLOTS - 1) : p + 4;   // slot of the next bin
-        p = a[i] >= thr ? pn : p;
-        atomicAdd(&sw.cnt[p >> 2][lane], 1u << (8 * (p & 3)));   // own word, own bank: never a conflict, never waited for
-      }                                                          // (slot 185, age out of range, is reported by k_replay)
+      for (int i = 0; i < NS; i++) {
+        // bin = clamp((bits >> 15) - KB, 0, 185) (as signed integers: r below the binade or negative -> 0,
+        // above -> 185 = age out of range, reported by k_replay); count byte bin & 3 of the lane's word bin >> 2
+        const int B = s2_clamp(rb[i]);
+        const uint32_t addr = cnt_base + ((uint32_t)B >> 17) * (TS_ROWS * 4);
+        const uint32_t inc = __funnelshift_l(0u, one, ((uint32_t)B >> 12) & 0x18u);   // 1 << 8 (bin & 3); KB % 4 == 0
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(inc) : "memory");   // own word, own bank: never a conflict, never waited for
+      }
     }
-    if (ch == N_CHUNK - 1) {
+    {
       // Tile done.  Lane L holds row L as 47 words of 4 slots; the tile leaves as [slot][row] bytes, so
       // every quad of lanes transposes its 4 x 4 bytes (two shuffles + two byte permutes per word) and
       // each lane stores "one slot, four rows": 32-byte runs per slot, full sectors.  Counters back to 0.
@@ -765,7 +856,7 @@ int run_sample(colate_handle* h, const uint32_t* stream_local, int)
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(COLATE_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")");
-    const size_t smem = sizeof(SampleWarp) * S2_WARPS + 192 * 8 + 2 * ((LUT_N + 15) & ~15);
+    const size_t smem = sizeof(SampleWarp) * S2_WARPS;
     CK(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_tile = (nu + TS_ROWS - 1) / TS_ROWS;
     int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (224 * 1024) / (smem + 1024)));
@@ -783,6 +874,33 @@ int run_sample(colate_handle* h, const uint32_t* stream_local, int)
     h->launches += 1;
   }
   CK(cudaEventRecord(h->ev[5], s));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int run_test_bin_fast(colate_handle* h, int n, const double* a_host, int32_t* fast_host, int32_t* exact_host)
+{
+  cudaStream_t s = h->stream;
+  CK(h->d_scratch.ensure((size_t)n * 16));
+  double* a = h->d_scratch.as<double>();
+  int32_t* f = (int32_t*)(a + n);
+  CK(cudaMemcpyAsync(a, a_host, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+  k_test_bin_fast<<<(n + 255) / 256, 256, 0, s>>>(n, a, h->thrA.as<double>(), h->lut.as<uint16_t>(), f, f + n);
+  CK(cudaMemcpyAsync(fast_host, f, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(exact_host, f + n, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  return 0;
+}
+int run_test_bin_sweep(colate_handle* h, uint32_t lo_bits, uint32_t hi_bits, uint64_t* out3_host)
+{
+  cudaStream_t s = h->stream;
+  CK(h->d_scratch.ensure(64));
+  CK(cudaMemsetAsync(h->d_scratch.p, 0, 24, s));
+  k_test_bin_sweep<<<h->sm_count * 8, 256, 0, s>>>(lo_bits, hi_bits, h->thrA.as<double>(), h->lut.as<uint16_t>(),
+                                                   h->d_scratch.as<unsigned long long>());
+  CK(cudaMemcpyAsync(out3_host, h->d_scratch.p, 24, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
   CK(cudaGetLastError());
   return 0;
 }

@@ -198,3 +198,39 @@ def test_stage1_fuzz_shapes(handle):
                 handle.stage1(api.mt_seed(seed))
             continue
         _compare_stage1(o, handle.stage1(api.mt_seed(seed)))
+
+
+def test_fast_bin_index_near_every_threshold(handle):
+    """k_sample's table-free bin index (lg2.approx + one FMA, fixed-point in the float's mantissa) around every
+    age-bin threshold of coal.cpp:2265: wherever it does not defer to the exact table it IS the exact bin."""
+    thr10 = np.zeros(po_nthr(), dtype=np.float64)
+    assert api.lib().colate_test_bin_thresholds(thr10) == 0
+    j = np.arange(-3000, 3001, dtype=np.float64)
+    ages = (thr10[1:, None] / 10.0) * (1.0 + j[None, :] * 1e-7)                 # +-3e-4 relative = +-3e-3 in 10 ln(10 a)
+    ulps = np.concatenate([np.nextafter(thr10[1:] / 10.0, np.inf), np.nextafter(thr10[1:] / 10.0, 0), thr10[1:] / 10.0])
+    a = np.concatenate([ages.ravel(), ulps, [0.0, 1e-300, 1e-30, 0.05, 1e9, 1e30]])
+    fast, exact = handle.bin_fast(a)
+    sure = fast >= 0
+    assert np.array_equal(fast[sure], exact[sure])
+    # the deferral window is narrow (< 1.3e-4 in t on either side of a threshold) ...
+    far = np.abs(j) > 200                                                       # |dt| > 2e-4
+    assert sure[: ages.size].reshape(ages.shape)[:, far].all()
+    # ... and contains every age within 4e-5 of a threshold (the documented error bound of the fast index)
+    near = np.abs(j) < 40
+    assert not sure[: ages.size].reshape(ages.shape)[:, near].any()
+    want = np.array([0, 0, 0, 0, 185, 185])                                     # far outside the grid: bin 0 / "out of range"
+    assert np.array_equal(exact[-6:], want) and ((fast[-6:] == want) | (fast[-6:] == -1)).all()
+
+
+def po_nthr():
+    return 186
+
+
+def test_fast_bin_index_every_float(handle):
+    """All 2.7e8 floats from 2^-7 to 2^25 (every age the bins distinguish): no unflagged disagreement with the exact
+    table, and the measured error of the fixed-point t stays inside the documented 4.7e-5."""
+    flagged, bad, worst = handle.bin_sweep(0x3C000000, 0x4C000000)
+    n = 0x4C000000 - 0x3C000000
+    assert bad == 0
+    assert worst < 4.7e-5, worst
+    assert 1e-5 < flagged / n < 1e-3
