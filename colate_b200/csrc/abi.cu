@@ -107,7 +107,7 @@ void colate_destroy(colate_handle* h)
   DevBuf* bufs[] = {&h->site_off, &h->pos, &h->ab, &h->ae, &h->meta, &h->candR, &h->candT, &h->use, &h->word_rank, &h->scan_tmp,
                     &h->chr_used, &h->chr_blocks, &h->chr_block_base, &h->misc, &h->u_hdr, &h->u_eb2, &h->u_ews, &h->u_ewn, &h->u_cnt,
                     &h->u_blk, &h->blk_rank_start, &h->out_f, &h->out_n, &h->thrA, &h->lut, &h->d_scratch, &h->d_prof, &h->libm_tab, &h->ing_text, &h->ing_tile_cnt, &h->ing_tile_off, &h->ing_nl, &h->ing_status, &h->ing_fb,
-                    &h->windows, &h->rng_stream, &h->poly, &h->thr10, &h->d_counts, &h->d_blockstats, &h->d_weights, &h->d_epochs,
+                    &h->windows, &h->rng_stream, &h->mt_tail, &h->poly, &h->thr10, &h->d_counts, &h->d_blockstats, &h->d_weights, &h->d_epochs,
                     &h->d_rates, &h->d_iters, &h->d_ll, &h->d_agebin, &h->d_tmp};
   for (DevBuf* b : bufs) b->release();
   for (auto& g : h->genomes) {
@@ -246,7 +246,7 @@ int colate_stage1_sample(colate_handle* h, const uint32_t* mt_state, int64_t use
   uint32_t* stream_local = nullptr;
   uint32_t win_after[COLATE_MT_WORDS];
   CK(cudaEventRecord(h->ev[6], s));
-  int rc = run_mt_stream(h, mt_state, 200 * used_rank_base, 200 * nu, pick_chunk_log2(nu), &stream_local, nullptr);
+  int rc = run_mt_stream(h, mt_state, 200 * used_rank_base, 200 * nu, pick_chunk_log2(nu), &stream_local, nullptr, true);
   if (rc) return rc;
   CK(cudaEventRecord(h->ev[7], s));
   if ((rc = run_sample(h, stream_local, block_base))) return rc;
@@ -412,7 +412,7 @@ int colate_test_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t wo
   if (!h || !mt_state || word0 < 0 || n_words < 0) return fail(COLATE_ERR_ARG, "colate_test_mt_stream: bad arguments");
   CK(cudaSetDevice(h->device));
   uint32_t* p = nullptr;
-  int rc = run_mt_stream(h, mt_state, word0, n_words, log2_chunk_sites, &p, out ? out + n_words : nullptr);
+  int rc = run_mt_stream(h, mt_state, word0, n_words, log2_chunk_sites, &p, out ? out + n_words : nullptr, false);
   if (rc) return rc;
   if (n_words > 0) CK(cudaMemcpyAsync(out, p, (size_t)n_words * 4, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));

@@ -72,7 +72,7 @@ struct colate_handle {
   colate::DevBuf chr_used, chr_blocks, chr_block_base, misc;  // misc: small device scalars
   colate::DevBuf u_hdr, u_eb2, u_ews, u_ewn, u_blk, u_cnt;   // compacted used rows, per-row sample counts
   colate::DevBuf blk_rank_start, out_f, out_n;
-  colate::DevBuf windows, rng_stream, poly, thr10, thrA, lut;
+  colate::DevBuf windows, rng_stream, mt_tail, poly, thr10, thrA, lut;
   int sm_count = 148;
   std::vector<int64_t> h_chr_used;
   std::vector<int32_t> h_chr_blocks;
@@ -107,7 +107,8 @@ int run_test_bin_fast(colate_handle* h, int n, const double* a_host, int32_t* fa
 int run_test_bin_sweep(colate_handle* h, uint32_t lo_bits, uint32_t hi_bits, uint64_t* out3_host);
 // kernels_mt.cu
 int run_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int64_t n_words, int log2_chunk_sites,
-                  uint32_t** stream_at_word0, uint32_t* window_after /* host, may be null */);
+                  uint32_t** stream_at_word0, uint32_t* window_after /* host, may be null */,
+                  bool tiled /* lay the words out in k_sample's tile order (internal.h: stream_phys) */);
 int mt_window_after(colate_handle* h, uint32_t* window_after);
 // kernels_em.cu
 int run_bootstrap(colate_handle* h, int R, int num_blocks, double age);

@@ -27,6 +27,28 @@ __host__ __device__
 #endif
 constexpr int slot_of_bin(int k) { return k; }
 
+// The generator stream in HBM is laid out in the order k_sample consumes it: used rows in tiles of 32, the
+// 200 words of a row cut into chunks of SAMPLE_CHUNK_WORDS, and tile t / chunk c stored as one contiguous
+// [32 rows][SAMPLE_CHUNK_WORDS] block (k_gen scatters, k_sample fetches each block with one 1-D bulk copy).
+#ifndef S2_CH_WORDS_
+#define S2_CH_WORDS_ 20
+#endif
+constexpr int SAMPLE_TILE_ROWS = 32;
+constexpr int SAMPLE_CHUNK_WORDS = S2_CH_WORDS_;
+constexpr int SAMPLE_TILE_WORDS = SAMPLE_TILE_ROWS * 200;
+static_assert(200 % SAMPLE_CHUNK_WORDS == 0 && SAMPLE_CHUNK_WORDS % 20 == 0, "chunks: whole steps of 10 samples");
+// physical word index of logical word o of the stream buffer; tiling starts at word `off` (a row boundary), off < 0: linear
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline int64_t stream_phys(int64_t o, int64_t off)
+{
+  if (off < 0 || o < off) return o;
+  const uint64_t q = (uint64_t)(o - off), row = q / 200u;
+  const uint32_t w = (uint32_t)(q - row * 200u), c = w / SAMPLE_CHUNK_WORDS, ww = w - c * SAMPLE_CHUNK_WORDS;
+  return off + (int64_t)((((row >> 5) * (200 / SAMPLE_CHUNK_WORDS) + c) * 32 + (row & 31)) * SAMPLE_CHUNK_WORDS + ww);
+}
+
 // error plumbing (thread-local message behind colate_last_error())
 void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);

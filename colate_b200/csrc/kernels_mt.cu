@@ -90,7 +90,8 @@ k_jump(uint32_t* __restrict__ windows, const uint16_t* __restrict__ taps, int n_
 
 // chunk c: sequential generation from its window, tempered words to stream[c*chunk_words ...)
 __global__ void __launch_bounds__(256)
-k_gen(const uint32_t* __restrict__ windows, int64_t chunk_words, int64_t total_words, uint32_t* __restrict__ stream)
+k_gen(const uint32_t* __restrict__ windows, int64_t chunk_words, int64_t total_words, uint32_t* __restrict__ stream,
+      int64_t tile_off, uint32_t* __restrict__ tail, int64_t tail_from)
 {
   __shared__ uint32_t bufA[MT_N + 1], bufB[MT_N + 1];
   const int tid = threadIdx.x;
@@ -103,18 +104,23 @@ k_gen(const uint32_t* __restrict__ windows, int64_t chunk_words, int64_t total_w
   uint32_t* nxt = bufB;
   for (int64_t o = start; o < end; o += MT_N) {
     const int64_t rem = end - o;
-    uint32_t* out = stream + o;
+    // word o + k goes to its place in the sampler's tile order; the last words also go to `tail`, linearly
+    auto put = [&](int k, uint32_t v) {
+      const uint32_t y = mt_temper_dev(v);
+      stream[stream_phys(o + k, tile_off)] = y;
+      if (o + k >= tail_from) tail[o + k - tail_from] = y;
+    };
     if (tid < 227) {
       uint32_t v = mt_mix_dev(cur[tid], cur[tid + 1], cur[tid + 397]);
       nxt[tid] = v;
-      if (tid < rem) out[tid] = mt_temper_dev(v);
+      if (tid < rem) put(tid, v);
     }
     __syncthreads();
     if (tid < 227) {
       int k = tid + 227;
       uint32_t v = mt_mix_dev(cur[k], cur[k + 1], nxt[tid]);
       nxt[k] = v;
-      if (k < rem) out[k] = mt_temper_dev(v);
+      if (k < rem) put(k, v);
     }
     __syncthreads();
     if (tid < 170) {
@@ -122,7 +128,7 @@ k_gen(const uint32_t* __restrict__ windows, int64_t chunk_words, int64_t total_w
       uint32_t b = (k == 623) ? nxt[0] : cur[k + 1];
       uint32_t v = mt_mix_dev(cur[k], b, nxt[k - 227]);
       nxt[k] = v;
-      if (k < rem) out[k] = mt_temper_dev(v);
+      if (k < rem) put(k, v);
     }
     __syncthreads();
     uint32_t* t = cur; cur = nxt; nxt = t;
@@ -176,7 +182,7 @@ static int launch_jump(colate_handle* h, int q, int level, int n_chunks, int n_j
 // aligned when word0 is a multiple of 4).  window_after (host, optional) = state window after
 // word0+n_words outputs.
 int run_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int64_t n_words, int k,
-                  uint32_t** stream_at_word0, uint32_t* window_after)
+                  uint32_t** stream_at_word0, uint32_t* window_after, bool tiled)
 {
   if (k < 0 || k > 40) return fail(COLATE_ERR_ARG, "bad chunk size");
   const int64_t S = (int64_t)200 << k;
@@ -188,7 +194,9 @@ int run_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int
   const int64_t total_local = word0 + n_words - c0 * S;  // words from the start of chunk c0
   cudaStream_t s = h->stream;
   CK(h->windows.ensure((size_t)(M + 1) * MT_N * 4));  // + one scratch window for the offset jumps
-  CK(h->rng_stream.ensure((size_t)std::max<int64_t>(total_local, 4) * 4 + 64));
+  const int64_t off = word0 - c0 * S;                    // the caller's first word inside chunk c0
+  CK(h->rng_stream.ensure((size_t)(std::max<int64_t>(total_local, 4) + (tiled ? SAMPLE_TILE_WORDS : 0)) * 4 + 64));   // tiled: whole last tile
+  CK(h->mt_tail.ensure(MT_N * 4));
   CK(cudaMemcpyAsync(h->windows.p, mt_state, MT_N * 4, cudaMemcpyHostToDevice, s));
   // reach chunk c0: one jump per set bit of c0, ping-ponging between window 0 and the scratch window
   int cur = 0;
@@ -212,18 +220,20 @@ int run_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int
     if (rc) return rc;
   }
   if (total_local > 0) {
-    k_gen<<<M, 256, 0, s>>>(h->windows.as<uint32_t>(), S, total_local, h->rng_stream.as<uint32_t>());
+    if (tiled && off % 200 != 0) return fail(COLATE_ERR_ARG, "tiled generator stream must start at a row boundary");
+    k_gen<<<M, 256, 0, s>>>(h->windows.as<uint32_t>(), S, total_local, h->rng_stream.as<uint32_t>(), tiled ? off : -1,
+                            h->mt_tail.as<uint32_t>(), total_local - std::min<int64_t>(total_local, MT_N));
     h->launches += 1;
     CK(cudaGetLastError());
   }
-  *stream_at_word0 = h->rng_stream.as<uint32_t>() + (word0 - c0 * S);
+  *stream_at_word0 = h->rng_stream.as<uint32_t>() + off;
   h->mt_total_local = total_local;
   if (window_after) return mt_window_after(h, window_after);
   return 0;
 }
 
 // State window after the last word produced by the latest run_mt_stream() call, composed on
-// the host from the chunk-0 window and the tail of the stream (tempering is invertible):
+// the host from the chunk-0 window and the tail of the stream (kept linearly in mt_tail; tempering is invertible):
 // y[i] = window(c0)[i] for i < 624, y[624+n] = untemper(stream[n]); answer = y[T .. T+624).
 int mt_window_after(colate_handle* h, uint32_t* window_after)
 {
@@ -233,8 +243,7 @@ int mt_window_after(colate_handle* h, uint32_t* window_after)
   std::vector<uint32_t> tail((size_t)std::min<int64_t>(T, MT_N));
   CK(cudaMemcpyAsync(w0, h->windows.p, MT_N * 4, cudaMemcpyDeviceToHost, s));
   if (!tail.empty())
-    CK(cudaMemcpyAsync(tail.data(), h->rng_stream.as<uint32_t>() + (T - (int64_t)tail.size()), tail.size() * 4,
-                       cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(tail.data(), h->mt_tail.p, tail.size() * 4, cudaMemcpyDeviceToHost, s));   // k_gen's linear copy of the last words
   CK(cudaStreamSynchronize(s));
   for (int j = 0; j < MT_N; j++) {
     int64_t i = T + j;  // index into y

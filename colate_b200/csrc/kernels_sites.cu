@@ -348,7 +348,8 @@ __device__ __forceinline__ int slot_of_age(double a, const uint16_t* lut, const 
 }
 
 constexpr int TS_ROWS = 32;            // used rows per tile: one per lane
-constexpr int CH_WORDS = 20;           // engine words per chunk and row = 10 samples
+constexpr int CH_WORDS = SAMPLE_CHUNK_WORDS;  // engine words per chunk and row: a ring slot holds 32 rows x CH_WORDS, one contiguous block of the stream
+constexpr int SUB_WORDS = 20;                 // words per unrolled step = 10 samples
 constexpr int N_CHUNK = 200 / CH_WORDS;
 constexpr int ROW_BYTES = 192;         // per-row sample counts, one byte per count slot (188 used)
 constexpr int TILE_BYTES = ROW_BYTES * TS_ROWS;   // count tile of 32 rows: [slot][row] bytes
@@ -358,31 +359,23 @@ constexpr int TILE_BYTES = ROW_BYTES * TS_ROWS;   // count tile of 32 rows: [slo
 #ifndef S2_RING_
 #define S2_RING_ 2
 #endif
-#ifndef S2_BOXES_
-#define S2_BOXES_ 1
-#endif
 constexpr int S2_WARPS = S2_WARPS_;    // warps per CTA, each with its own tile, ring and counters
 constexpr int S2_RING = S2_RING_;      // ring slots per warp (one being read, the others in flight)
-constexpr int S2_BOXES = S2_BOXES_;    // TMA boxes (32 rows x 80 B) per ring slot = chunks handled per loop iteration
-constexpr int N_STEP = N_CHUNK / S2_BOXES;
-static_assert(N_CHUNK % S2_BOXES == 0, "boxes per slot must divide the 10 chunks of a row");
+constexpr int N_STEP = N_CHUNK;
 struct __align__(128) SampleWarp {
-  uint32_t chunk[S2_RING][S2_BOXES][TS_ROWS][CH_WORDS];   // TMA boxes: 32 rows x 80 B of the generator stream (row stride 20 words: conflict-free LDS.128)
+  uint32_t chunk[S2_RING][TS_ROWS][CH_WORDS];   // one block of the stream per slot: 32 rows x CH_WORDS (row stride of 20 words: conflict-free LDS.128)
   uint32_t cnt[ROW_WORDS][TS_ROWS];             // this tile's counts: word w of lane L = slots 4w..4w+3 of row L (bank = lane)
   uint64_t full[S2_RING];
 };
 
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar)
-{
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-                   smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
-}
-
 // THE per-mutation kernel.  Thread = used row: a warp owns a tile of 32 consecutive used rows and streams
-// their 100 x 2 generator words (800 B per row) from HBM in ten 2-D TMA boxes of 32 rows x 80 B (a tensor
-// map over the stream as a [rows][200 words] matrix), S2_RING - 1 boxes in flight per warp.  Each lane turns
-// its row's word pairs into uniform ages -> exact bin index -> its own column of the tile's count bytes in
-// shared memory: no conflicts, no idle lanes, every instruction serves 32 samples.  The tile
+// their 100 x 2 generator words (800 B per row) from HBM.  k_gen has laid the stream out in exactly this
+// order (internal.h: stream_phys): tile t / chunk c is ONE contiguous block of 32 rows x 20 words, fetched
+// with one 1-D bulk copy (cp.async.bulk + mbarrier) into a per-warp ring, S2_RING - 1 blocks in flight per
+// warp.  (Measured, memory pipeline alone: 2-D TMA boxes of 32 x 80 B over the row-major stream 0.223 ms,
+// 32 x 160 B 0.201 ms, 32 x 400 B 0.195 ms, contiguous blocks 0.181 ms: the TMA unit pays per box row.)
+// Each lane turns its row's word pairs into uniform ages -> exact bin index -> its own column of the tile's
+// count bytes in shared memory: no conflicts, no idle lanes, every instruction serves 32 samples.  The tile
 // [188 slots][32 rows] leaves as 6 KB of coalesced stores; k_replay reads it back the same way.
 //
 // Bin index (coal.cpp:2265/2284: max(0,(int)round(log(10 a)*10)+1)) in the common case WITHOUT a table:
@@ -399,7 +392,8 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, 
 // one generator pair in 2^32 whose uniform needs the "< 1" clamp of generate_canonical.
 // (History: MATCH.ANY aggregation 33 cycles per warp instruction on the ADU pipe -> 12 % of HBM peak;
 // warp-per-row with shared-memory atomics -> 47 %; lane-per-row with 64-bit chunk indexing and the LUT in
-// the main path -> 58 %, 470 instructions per 10 samples.)
+// the main path -> 58 %, 470 instructions per 10 samples; table-free index, 270 instructions -> 70 %, then
+// bound by the TMA unit's per-row cost until the stream was re-laid in tile order.)
 constexpr float S2_C1 = 6.931471805599453f;        // 10 ln 2
 constexpr float S2_C0 = 344.5258509299405f;        // 10 ln 10 + 1.5 + 320
 constexpr int S2_KB = (0x43800000 >> 15) + 64;     // (bits(r) >> 15) of t = 0
@@ -450,7 +444,7 @@ __global__ void k_test_bin_sweep(uint32_t lo, uint32_t hi, const double* __restr
 }
 
 __global__ void __launch_bounds__(S2_WARPS * 32)
-k_sample(const __grid_constant__ CUtensorMap tmap, int64_t n_used, const double4* __restrict__ hdr_g,
+k_sample(const uint32_t* __restrict__ stream, int64_t n_used, const double4* __restrict__ hdr_g,
          const double* __restrict__ thrA_g, const uint16_t* __restrict__ lut_g, uint8_t* __restrict__ cnt_tiles)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -468,16 +462,16 @@ k_sample(const __grid_constant__ CUtensorMap tmap, int64_t n_used, const double4
   const uint32_t w0 = blockIdx.x * S2_WARPS + warp, nw = gridDim.x * S2_WARPS;
   if (w0 >= n_tile) return;
   const uint32_t my_tiles = (n_tile - w0 + nw - 1) / nw;
-  // producer side (lane 0): next ring slot to request = chunks pch .. pch + S2_BOXES - 1 of tile ptile
-  uint32_t ptile = w0, pch = 0, pslot = 0, pleft = my_tiles * N_STEP;
+  // producer side (lane 0): next block to request = chunk pch of tile ptile, CH_BYTES contiguous bytes of the stream
+  constexpr uint32_t CH_BYTES = TS_ROWS * CH_WORDS * 4;
+  const uint32_t* pblk = stream + (size_t)w0 * SAMPLE_TILE_WORDS;
+  uint32_t pch = 0, pslot = 0, pleft = my_tiles * N_STEP;
   auto issue = [&]() {
-    mbar_expect_tx(&sw.full[pslot], S2_BOXES * TS_ROWS * CH_WORDS * 4);
-#pragma unroll
-    for (int b = 0; b < S2_BOXES; b++)
-      tma_load_2d(&sw.chunk[pslot][b][0][0], &tmap, (int)(pch + b) * CH_WORDS, (int)(ptile * TS_ROWS), &sw.full[pslot]);
+    mbar_expect_tx(&sw.full[pslot], CH_BYTES);
+    bulk_g2s(&sw.chunk[pslot][0][0], pblk, CH_BYTES, &sw.full[pslot]);
     pslot = pslot + 1 == S2_RING ? 0 : pslot + 1;
-    pch += S2_BOXES;
-    if (pch == N_CHUNK) { pch = 0; ptile += nw; }
+    pblk += TS_ROWS * CH_WORDS;
+    if (++pch == N_CHUNK) { pch = 0; pblk += (size_t)(nw - 1) * SAMPLE_TILE_WORDS; }
     pleft--;
   };
   if (lane == 0)
@@ -494,7 +488,7 @@ k_sample(const __grid_constant__ CUtensorMap tmap, int64_t n_used, const double4
   header(w0, lenp_n, abd_n, one_n);
   uint32_t cslot = 0, cphase = 0;
   const uint32_t cnt_base = smem_u32(&sw.cnt[0][lane]) - (uint32_t)(S2_KB >> 2) * (TS_ROWS * 4);
-  constexpr int NS = S2_BOXES * CH_WORDS / 2;                      // samples per loop iteration and lane
+  constexpr int NS = SUB_WORDS / 2;                      // samples per loop iteration and lane
 
   for (uint32_t ti = 0, tile = w0; ti < my_tiles; ti++, tile += nw) {
     const double lenp = lenp_n, abd = abd_n;
@@ -508,13 +502,19 @@ k_sample(const __grid_constant__ CUtensorMap tmap, int64_t n_used, const double4
         issue();
       }
       mbar_wait(&sw.full[cslot], cphase);
-      const uint32_t* wbase = &sw.chunk[cslot][0][lane][0];
+      const uint32_t* wslot = &sw.chunk[cslot][lane][0];
       cslot = cslot + 1 == S2_RING ? 0 : cslot + 1;
       cphase ^= cslot == 0;
-      auto words = [&](int i) { return *(const uint2*)(wbase + (i / (CH_WORDS / 2)) * (TS_ROWS * CH_WORDS) + 2 * (i % (CH_WORDS / 2))); };
+#pragma unroll 1
+      for (int sub = 0; sub < CH_WORDS / SUB_WORDS; sub++) {
+      const uint32_t* wbase = wslot + sub * SUB_WORDS;
+      auto words = [&](int i) { return *(const uint2*)(wbase + 2 * i); };
       // NS samples as straight-line code (the steps of different samples interleave)
       uint32_t rb[NS];
       bool rare = false;
+#ifdef S2_EXP_NOCOMPUTE
+      if (lenp != 12345.0) continue;                             // experiment: memory pipeline only
+#endif
 #pragma unroll
       for (int i = 0; i < NS; i++) {
         const uint2 w = words(i);
@@ -545,6 +545,7 @@ k_sample(const __grid_constant__ CUtensorMap tmap, int64_t n_used, const double4
         const uint32_t addr = cnt_base + ((uint32_t)B >> 17) * (TS_ROWS * 4);
         const uint32_t inc = __funnelshift_l(0u, one, ((uint32_t)B >> 12) & 0x18u);   // 1 << 8 (bin & 3); KB % 4 == 0
         asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(inc) : "memory");   // own word, own bank: never a conflict, never waited for
+      }
       }
     }
     {
@@ -836,33 +837,18 @@ int run_sample(colate_handle* h, const uint32_t* stream_local, int)
   h->launches += 1;
   CK(cudaEventRecord(h->ev[3], s));
   if (nu > 0) {
-    // tensor map over the generator stream as a [nu rows][200 words] matrix, boxes of 32 rows x 20 words
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn encode = nullptr;
-    if (!encode) {
-      void* fn = nullptr;
-      cudaDriverEntryPointQueryResult qres;
-      CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-      if (!fn || qres != cudaDriverEntryPointSuccess) return fail(COLATE_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
-      encode = (EncodeFn)fn;
-    }
-    CUtensorMap tmap;
-    const cuuint64_t gdim[2] = {200, (cuuint64_t)nu};
-    const cuuint64_t gstride[1] = {800};
-    const cuuint32_t box[2] = {CH_WORDS, TS_ROWS}, estr[2] = {1, 1};
-    const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)stream_local, gdim, gstride, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) return fail(COLATE_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")");
     const size_t smem = sizeof(SampleWarp) * S2_WARPS;
+    // all of the SM's 228 KB as shared memory (the kernel's only L1 traffic is one 16 B header per row): the
+    // resident warps, and with them the bytes in flight, are bounded by the rings and count tiles
     CK(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_sample, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const int64_t n_tile = (nu + TS_ROWS - 1) / TS_ROWS;
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (224 * 1024) / (smem + 1024)));
+    int per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sample, S2_WARPS * 32, smem));
+    per_sm = std::max(1, per_sm);
     if (const char* e = getenv("COLATE_SAMPLE_CTAS_PER_SM")) per_sm = std::max(1, atoi(e));
     const int grid = (int)std::min<int64_t>((n_tile + S2_WARPS - 1) / S2_WARPS, (int64_t)h->sm_count * per_sm);
-    k_sample<<<grid, S2_WARPS * 32, smem, s>>>(tmap, nu, h->u_hdr.as<double4>(), h->thrA.as<double>(), h->lut.as<uint16_t>(),
+    k_sample<<<grid, S2_WARPS * 32, smem, s>>>(stream_local, nu, h->u_hdr.as<double4>(), h->thrA.as<double>(), h->lut.as<uint16_t>(),
                                                h->u_cnt.as<uint8_t>());
     h->launches += 1;
   }

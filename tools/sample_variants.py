@@ -1,9 +1,9 @@
 #!/usr/bin/env python3
-"""k_sample tuning: build kernels_sites.cu with different (warps per CTA, ring slots, boxes per slot) into
+"""k_sample tuning: build kernels_sites.cu with different (warps per CTA, ring slots, words per chunk) into
 build/variants/ (here, no GPU needed) and time each on the GPU box at config-2 size, with a checksum of the
 stage-i result so that every variant is seen to be bit-identical.
 
-  python tools/sample_variants.py build 4,2,1 4,3,1 4,2,2 ...
+  python tools/sample_variants.py build 4,2,20 4,3,20 4,2,40 ...
   python tools/sample_variants.py run [rows]          (on the GPU box)
 """
 import glob, hashlib, os, subprocess, sys
@@ -17,13 +17,17 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 def build(tags):
     os.makedirs(OUT, exist_ok=True)
     subprocess.run(["make", "-s", "-j8", "-C", CSRC, "all"], check=True)
-    others = [os.path.join(CSRC, o) for o in ("abi.o", "kernels_mt.o", "kernels_em.o", "kernels_ingest.o", "host_mt.o", "host_misc.o")]
+    others = [os.path.join(CSRC, o) for o in ("abi.o", "kernels_em.o", "kernels_ingest.o", "host_mt.o", "host_misc.o")]
     for t in tags:
-        w, r, b = t.split(",")
-        obj = os.path.join(OUT, f"sites_{w}_{r}_{b}.o")
-        subprocess.run(["nvcc", *ARCH, "-O3", "-lineinfo", "-std=c++17", "--fmad=false", "-Xcompiler", "-fPIC,-O2",
-                        f"-DS2_WARPS_={w}", f"-DS2_RING_={r}", f"-DS2_BOXES_={b}", "-c", os.path.join(CSRC, "kernels_sites.cu"), "-o", obj], check=True)
-        subprocess.run(["nvcc", *ARCH, "-shared", "-o", os.path.join(OUT, f"lib_{w}_{r}_{b}.so"), obj, *others, "-lz"], check=True)
+        w, r, c, *extra = t.split(",")
+        tag = f"{w}_{r}_{c}" + "".join("_" + e for e in extra)
+        objs = []
+        for src in ("kernels_sites", "kernels_mt"):       # both see the chunk width (internal.h: stream layout)
+            objs.append(os.path.join(OUT, f"{src}_{tag}.o"))
+            subprocess.run(["nvcc", *ARCH, "-O3", "-lineinfo", "-std=c++17", "--fmad=false", "-Xcompiler", "-fPIC,-O2",
+                            f"-DS2_WARPS_={w}", f"-DS2_RING_={r}", f"-DS2_CH_WORDS_={c}", *[f"-D{e}" for e in extra], "-c",
+                            os.path.join(CSRC, src + ".cu"), "-o", objs[-1]], check=True)
+        subprocess.run(["nvcc", *ARCH, "-shared", "-o", os.path.join(OUT, f"lib_{tag}.so"), *objs, *others, "-lz"], check=True)
         print("built", t, flush=True)
 
 
