@@ -348,9 +348,9 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     sample_bytes = 800.0 * n_used
     # DRAM traffic of one k_sample launch from the ncu --set full capture of this workload
-    # (profiles/r01_ncu_k_sample_full.md: dram__bytes_read.sum + dram__bytes_write.sum = 1.2273 GB at
+    # (profiles/r01_ncu_k_sample_full.md: dram__bytes_read.sum + dram__bytes_write.sum = 1.0067 GB + 0.2101 GB at
     # 1,209,943 used rows); it scales with the used rows (832 B read + 192 B written each)
-    traffic = 1.2273e9 * n_used / 1209943.0
+    traffic = 1.21688e9 * n_used / 1209943.0
     ach = sample_bytes / (t_stage1["sample_ms"] * 1e-3) / 1e9
     stage_bytes = 40.0 * rows + 800.0 * n_used
     roofline = {"bound": "hbm", "kernel": "k_sample (per-mutation Monte-Carlo age binning)", "achieved": ach, "peak": peak,

@@ -102,25 +102,42 @@ k_gen(const uint32_t* __restrict__ windows, int64_t chunk_words, int64_t total_w
   __syncthreads();
   uint32_t* cur = bufA;
   uint32_t* nxt = bufB;
+  // Where the words go: linear (tile_off < 0), or k_sample's tile order from word tile_off on (internal.h:
+  // stream_phys).  Each thread keeps (row, word in row) of its three words of the round relative to
+  // tile_off and steps them by 624 = 3 rows + 24 words per round: no division in the loop.
+  const bool tiled = tile_off >= 0;
+  int prow[3], pw[3];                                          // rows stay far below 2^31 (800 B of stream each)
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const int64_t q = start + tid + 227 * j - (tiled ? tile_off : 0);
+    int64_t r = q / 200;
+    if (q - r * 200 < 0) r--;                                  // floor: words before tile_off have row < 0
+    prow[j] = (int)r;
+    pw[j] = (int)(q - r * 200);
+  }
+  auto put = [&](int j, int64_t o_k, uint32_t v) {
+    const uint32_t y = mt_temper_dev(v);
+    int64_t idx = o_k;
+    if (tiled && prow[j] >= 0) {
+      const int c = pw[j] / SAMPLE_CHUNK_WORDS;
+      idx = tile_off + (int64_t)(prow[j] >> 5) * SAMPLE_TILE_WORDS + ((prow[j] & 31) * SAMPLE_CHUNK_WORDS + c * (31 * SAMPLE_CHUNK_WORDS) + pw[j]);
+    }
+    stream[idx] = y;
+    if (o_k >= tail_from) tail[o_k - tail_from] = y;            // the last words also linearly, for the state recovery
+  };
   for (int64_t o = start; o < end; o += MT_N) {
     const int64_t rem = end - o;
-    // word o + k goes to its place in the sampler's tile order; the last words also go to `tail`, linearly
-    auto put = [&](int k, uint32_t v) {
-      const uint32_t y = mt_temper_dev(v);
-      stream[stream_phys(o + k, tile_off)] = y;
-      if (o + k >= tail_from) tail[o + k - tail_from] = y;
-    };
     if (tid < 227) {
       uint32_t v = mt_mix_dev(cur[tid], cur[tid + 1], cur[tid + 397]);
       nxt[tid] = v;
-      if (tid < rem) put(tid, v);
+      if (tid < rem) put(0, o + tid, v);
     }
     __syncthreads();
     if (tid < 227) {
       int k = tid + 227;
       uint32_t v = mt_mix_dev(cur[k], cur[k + 1], nxt[tid]);
       nxt[k] = v;
-      if (k < rem) put(k, v);
+      if (k < rem) put(1, o + k, v);
     }
     __syncthreads();
     if (tid < 170) {
@@ -128,9 +145,15 @@ k_gen(const uint32_t* __restrict__ windows, int64_t chunk_words, int64_t total_w
       uint32_t b = (k == 623) ? nxt[0] : cur[k + 1];
       uint32_t v = mt_mix_dev(cur[k], b, nxt[k - 227]);
       nxt[k] = v;
-      if (k < rem) put(k, v);
+      if (k < rem) put(2, o + k, v);
     }
     __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      pw[j] += MT_N - 600;
+      prow[j] += 3;
+      if (pw[j] >= 200) { pw[j] -= 200; prow[j]++; }
+    }
     uint32_t* t = cur; cur = nxt; nxt = t;
   }
 }
