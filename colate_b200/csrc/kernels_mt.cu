@@ -88,10 +88,16 @@ k_jump(uint32_t* __restrict__ windows, const uint16_t* __restrict__ taps, int n_
   }
 }
 
-// chunk c: sequential generation from its window, tempered words to stream[c*chunk_words ...)
+// chunk c: sequential generation from its window, tempered words to the stream.  TILED: from word tile_off
+// on, the words go where k_sample reads them (internal.h: stream_phys: tiles of 32 rows, a tile's chunk of
+// SAMPLE_CHUNK_WORDS words per row stored as one contiguous block); each thread keeps (row, word in row) of its
+// three words of a round relative to tile_off and steps them by 624 = 3 rows + 24 words per round, so the
+// loop has no division and no 64-bit compare.  The CTA that produces the last word also leaves the last
+// min(total, 624) words linearly in `tail` (from the two windows it holds) for the state recovery.
+template <bool TILED>
 __global__ void __launch_bounds__(256)
 k_gen(const uint32_t* __restrict__ windows, int64_t chunk_words, int64_t total_words, uint32_t* __restrict__ stream,
-      int64_t tile_off, uint32_t* __restrict__ tail, int64_t tail_from)
+      int64_t tile_off, uint32_t* __restrict__ tail)
 {
   __shared__ uint32_t bufA[MT_N + 1], bufB[MT_N + 1];
   const int tid = threadIdx.x;
@@ -102,42 +108,49 @@ k_gen(const uint32_t* __restrict__ windows, int64_t chunk_words, int64_t total_w
   __syncthreads();
   uint32_t* cur = bufA;
   uint32_t* nxt = bufB;
-  // Where the words go: linear (tile_off < 0), or k_sample's tile order from word tile_off on (internal.h:
-  // stream_phys).  Each thread keeps (row, word in row) of its three words of the round relative to
-  // tile_off and steps them by 624 = 3 rows + 24 words per round: no division in the loop.
-  const bool tiled = tile_off >= 0;
   int prow[3], pw[3];                                          // rows stay far below 2^31 (800 B of stream each)
+  if (TILED) {
 #pragma unroll
-  for (int j = 0; j < 3; j++) {
-    const int64_t q = start + tid + 227 * j - (tiled ? tile_off : 0);
-    int64_t r = q / 200;
-    if (q - r * 200 < 0) r--;                                  // floor: words before tile_off have row < 0
-    prow[j] = (int)r;
-    pw[j] = (int)(q - r * 200);
-  }
-  auto put = [&](int j, int64_t o_k, uint32_t v) {
-    const uint32_t y = mt_temper_dev(v);
-    int64_t idx = o_k;
-    if (tiled && prow[j] >= 0) {
-      const int c = pw[j] / SAMPLE_CHUNK_WORDS;
-      idx = tile_off + (int64_t)(prow[j] >> 5) * SAMPLE_TILE_WORDS + ((prow[j] & 31) * SAMPLE_CHUNK_WORDS + c * (31 * SAMPLE_CHUNK_WORDS) + pw[j]);
+    for (int j = 0; j < 3; j++) {
+      const int64_t q = start + tid + 227 * j - tile_off;
+      int64_t r = q / 200;
+      if (q - r * 200 < 0) r--;                                // floor: words before tile_off have row < 0 and stay linear
+      prow[j] = (int)r;
+      pw[j] = (int)(q - r * 200);
     }
-    stream[idx] = y;
-    if (o_k >= tail_from) tail[o_k - tail_from] = y;            // the last words also linearly, for the state recovery
+  }
+  uint32_t* const tiled_base = stream + tile_off;
+  // where word k = tid + 227 j of the round at `lin` goes
+  auto place = [&](int j, uint32_t* lin) -> uint32_t* {
+    if (!TILED) return lin;
+    const int c = (pw[j] * 3277) >> 16;                        // pw / 20 for pw < 200
+    const int inner = (prow[j] & 31) * SAMPLE_CHUNK_WORDS + (c / (SAMPLE_CHUNK_WORDS / 20)) * (31 * SAMPLE_CHUNK_WORDS) + pw[j];
+    uint32_t* t = tiled_base + ((int64_t)(prow[j] >> 5) * SAMPLE_TILE_WORDS + inner);
+    return prow[j] >= 0 ? t : lin;
   };
-  for (int64_t o = start; o < end; o += MT_N) {
-    const int64_t rem = end - o;
+  auto advance = [&]() {
+    if (!TILED) return;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      pw[j] += MT_N - 600;
+      prow[j] += 3;
+      if (pw[j] >= 200) { pw[j] -= 200; prow[j]++; }
+    }
+  };
+  // one round = the next 624 words in three dependent steps; `rem` masks the stores of the chunk's last round
+  auto round = [&](int64_t o, int rem) {
+    uint32_t* out = stream + o;
     if (tid < 227) {
       uint32_t v = mt_mix_dev(cur[tid], cur[tid + 1], cur[tid + 397]);
       nxt[tid] = v;
-      if (tid < rem) put(0, o + tid, v);
+      if (tid < rem) *place(0, out + tid) = mt_temper_dev(v);
     }
     __syncthreads();
     if (tid < 227) {
       int k = tid + 227;
       uint32_t v = mt_mix_dev(cur[k], cur[k + 1], nxt[tid]);
       nxt[k] = v;
-      if (k < rem) put(1, o + k, v);
+      if (k < rem) *place(1, out + k) = mt_temper_dev(v);
     }
     __syncthreads();
     if (tid < 170) {
@@ -145,16 +158,22 @@ k_gen(const uint32_t* __restrict__ windows, int64_t chunk_words, int64_t total_w
       uint32_t b = (k == 623) ? nxt[0] : cur[k + 1];
       uint32_t v = mt_mix_dev(cur[k], b, nxt[k - 227]);
       nxt[k] = v;
-      if (k < rem) put(2, o + k, v);
+      if (k < rem) *place(2, out + k) = mt_temper_dev(v);
     }
     __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-      pw[j] += MT_N - 600;
-      prow[j] += 3;
-      if (pw[j] >= 200) { pw[j] -= 200; prow[j]++; }
-    }
     uint32_t* t = cur; cur = nxt; nxt = t;
+  };
+  int64_t o = start;
+  for (; o + MT_N <= end; o += MT_N) { round(o, MT_N); advance(); }
+  if (o < end) { round(o, (int)(end - o)); o += MT_N; }
+  if (end == total_words) {
+    // cur = untempered words [o - 624, o), nxt = the 624 before them (the chunk's start window if only one round ran)
+    const int n_tail = (int)min(total_words, (int64_t)MT_N);
+    for (int i = tid; i < n_tail; i += blockDim.x) {
+      const int64_t g = total_words - n_tail + i;               // >= o - 1248 because o - 624 < total_words
+      const int rel = (int)(g - (o - 2 * MT_N));
+      tail[i] = mt_temper_dev(rel >= MT_N ? cur[rel - MT_N] : nxt[rel]);
+    }
   }
 }
 
@@ -244,8 +263,8 @@ int run_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int
   }
   if (total_local > 0) {
     if (tiled && off % 200 != 0) return fail(COLATE_ERR_ARG, "tiled generator stream must start at a row boundary");
-    k_gen<<<M, 256, 0, s>>>(h->windows.as<uint32_t>(), S, total_local, h->rng_stream.as<uint32_t>(), tiled ? off : -1,
-                            h->mt_tail.as<uint32_t>(), total_local - std::min<int64_t>(total_local, MT_N));
+    if (tiled) k_gen<true><<<M, 256, 0, s>>>(h->windows.as<uint32_t>(), S, total_local, h->rng_stream.as<uint32_t>(), off, h->mt_tail.as<uint32_t>());
+    else k_gen<false><<<M, 256, 0, s>>>(h->windows.as<uint32_t>(), S, total_local, h->rng_stream.as<uint32_t>(), 0, h->mt_tail.as<uint32_t>());
     h->launches += 1;
     CK(cudaGetLastError());
   }
