@@ -234,3 +234,43 @@ def test_fast_bin_index_every_float(handle):
     assert bad == 0
     assert worst < 4.7e-5, worst
     assert 1e-5 < flagged / n < 1e-3
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_stage1_chromosome_shards_on_one_gpu(handle, world):
+    """The multi-GPU decomposition (dist.py) replayed on one GPU: each shard samples at its offset of the reference's
+    generator stream (colate_stage1_sample with used_rank_base > 0: the stream chunk starts before the shard's first
+    row and the tile-ordered layout begins mid-chunk).  Concatenated blocks == the oracle's single run, bit for bit."""
+    from colate_b200 import dist as cdist
+    sites = synth.make_sites(7, [9000, 2500, 7000, 100, 6000], [2.0e8, 0.6e8, 1.5e8, 0.3e8, 1.2e8])
+    gt = synth.make_genome(107, sites, 0.7)
+    gr = synth.make_genome(207, sites, 0.7)
+    o = po.stage1(sites, gt, gr, seed=3)
+    parts = cdist.split_chromosomes(np.diff(sites.site_off), world)
+    seed_state = api.mt_seed(3)
+    used_base = block_base = 0
+    stats, tallies, state = [], [], None
+    for lo, hi in parts:
+        s0, s1 = int(sites.site_off[lo]), int(sites.site_off[hi])
+        handle.set_sites(sites.site_off[lo:hi + 1] - sites.site_off[lo], sites.pos[s0:s1], sites.age_begin[s0:s1],
+                         sites.age_end[s0:s1], sites.meta()[s0:s1])
+        for slot, g in ((0, gt), (1, gr)):
+            first, end = api.chr_ranges(len(sites.chr_names), g.chrom)          # the seek is emulated on the whole file
+            al = g.anc.astype(np.uint16) | (g.der.astype(np.uint16) << 8)
+            api.check(api.lib().colate_set_genome(handle._h, slot, g.n, api.ptr(np.ascontiguousarray(first[lo:hi])),
+                                                  api.ptr(np.ascontiguousarray(end[lo:hi])), api.ptr(g.bp), api.ptr(g.aaf),
+                                                  api.ptr(g.daf), api.ptr(al), 0))
+        handle.set_mask(0, None); handle.set_mask(1, None)
+        used_chr, blocks_chr = handle.stage1_flags()
+        n_local = int(np.sum(blocks_chr))
+        st, tl, state = handle.stage1_sample(seed_state, used_base, block_base, n_local)
+        stats.append(st[:n_local]); tallies.append(tl[:n_local])
+        used_base += int(np.sum(used_chr)); block_base += n_local
+    assert used_base == o["n_used_total"] and block_base == o["num_blocks"]
+    stats, tallies = np.concatenate(stats), np.concatenate(tallies)
+    for v, k in enumerate(("shared", "notshared", "shared_emp", "notshared_emp")):
+        assert np.array_equal(stats[:, v], o[k]), k
+    assert np.array_equal(tallies[:, 1], o["n_notshared"])
+    a = np.zeros(64, np.uint32); b = np.array([po.lib().oracle_mt_next(o["rng"]) for _ in range(64)], np.uint32)
+    api.lib().colate_mt_generate(state.copy(), 64, a)                           # the last shard holds the final generator state
+    assert np.array_equal(a, b)
