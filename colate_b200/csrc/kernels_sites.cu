@@ -5,10 +5,10 @@
 //   k_*rank*    used-row rank = offset into the reference's generator stream
 //   k_compact   used rows -> dense records in rank order, genomic block index
 //   k_sample    THE per-mutation kernel: 100 Monte-Carlo age draws per used row from the
-//               uniform stream in HBM, exact bin index, warp-aggregated histogram updates in
-//               per-warp shared-memory histograms (no atomics), one partial per tile
-//   k_reduce    fixed-order sum of the tile partials of each genomic block
-#include <cuda.h>
+//               uniform stream in HBM (tile-ordered by k_gen, bulk-copied into per-warp rings),
+//               exact bin index, per-lane byte counters in shared memory -> [slot][row] count tiles
+//   k_replay    exact fp64 histograms: the reference's rounded additions replayed in row order
+//               per genomic block, plus the "emp" slice
 
 #include "device.cuh"
 #include "exact_sum.cuh"
