@@ -216,10 +216,17 @@ __global__ void k_compact(int64_t n_site, int n_chr, const int64_t* __restrict__
                           double4* __restrict__ hdr, uint8_t* __restrict__ e_b2, double* __restrict__ e_ws,
                           double* __restrict__ e_wn, int32_t* __restrict__ u_blk, int64_t* __restrict__ misc)
 {
-  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= n_site) return;
-  if (!((use[m >> 5] >> (m & 31)) & 1u)) return;
-  int64_t r = rank_of(use, word_rank, m);
+  // thread = used row (rank r): one row in eight is used, so a thread per site would leave the warps of the
+  // division-heavy part below nearly empty.  Site of rank r: the last bitmap word whose exclusive rank is <= r
+  // (empty words in front of it share its rank, the words behind it start above r), then the bit inside it.
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= misc[0]) return;
+  int64_t lo = 0, hi = (n_site + 31) >> 5;            // invariant: word_rank[lo] <= r, word_rank[hi] > r (hi = one past the end)
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)word_rank[mid] <= r) lo = mid; else hi = mid;
+  }
+  const int64_t m = (lo << 5) + __fns(use[lo], 0, (int)(r - word_rank[lo]) + 1);
   int c = chr_of(site_off, n_chr, m);
   // pseudo-genotype, coal.cpp:2236-2242: float /= double, then round half away
   const int32_t dt = t_daf[m], at = t_aaf[m];
@@ -825,7 +832,7 @@ int run_sample(colate_handle* h, const uint32_t* stream_local, int)
     CK(cudaMemsetAsync(h->u_hdr.as<double4>() + nu, 0, (un32 - (size_t)nu) * 32, s));
   CK(cudaEventRecord(h->ev[2], s));
   if (n > 0) {
-    k_compact<<<grid_for(n, 256), 256, 0, s>>>(n, h->n_chr, h->site_off.as<int64_t>(), h->pos.as<int32_t>(), h->ab.as<float>(),
+    k_compact<<<grid_for(std::max<int64_t>(nu, 1), 256), 256, 0, s>>>(n, h->n_chr, h->site_off.as<int64_t>(), h->pos.as<int32_t>(), h->ab.as<float>(),
                                                h->ae.as<float>(), h->use.as<uint32_t>(), h->word_rank.as<uint32_t>(),
                                                h->chr_block_base.as<int32_t>(), T.j_aaf.as<int32_t>(), T.j_daf.as<int32_t>(),
                                                R.j_aaf.as<int32_t>(), R.j_daf.as<int32_t>(), h->thr10.as<double>(),
