@@ -49,6 +49,7 @@ SIGNATURES = {
     "colate_create": (C.c_int, [C.c_int, C.POINTER(VP)]),
     "colate_destroy": (None, [VP]),
     "colate_stream": (VP, [VP]),
+    "colate_set_stream_cache": (C.c_int, [VP, C.c_int]),
     "colate_set_sites": (C.c_int, [VP, C.c_int, VP, VP, VP, VP, VP, C.c_int]),
     "colate_set_genome": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, C.c_int]),
     "colate_set_mask": (C.c_int, [VP, C.c_int, VP, C.c_int]),

@@ -208,6 +208,10 @@ class Handle:
         check(lib().colate_ingest_stats(self._h, C.byref(ms), C.byref(fb)))
         return dict(kernel_ms=ms.value, host_fallback_rows=fb.value)
 
+    def set_stream_cache(self, enable: bool):
+        """Reuse the generator stream across stage-i calls that start from the same state (all-pairs jobs)."""
+        check(lib().colate_set_stream_cache(self._h, 1 if enable else 0))
+
     # ---- stage i
     def stage1_flags(self, target_slot=0, reference_slot=1):
         used = np.zeros(self.n_chr, dtype=np.int64)

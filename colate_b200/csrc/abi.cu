@@ -122,6 +122,14 @@ void colate_destroy(colate_handle* h)
 
 void* colate_stream(colate_handle* h) { return h ? (void*)h->stream : nullptr; }
 
+int colate_set_stream_cache(colate_handle* h, int enable)
+{
+  if (!h) return fail(COLATE_ERR_ARG, "colate_set_stream_cache: null handle");
+  h->stream_cache_on = enable != 0;
+  h->sc_valid = false;
+  return 0;
+}
+
 int colate_set_sites(colate_handle* h, int n_chr, const int64_t* site_off, const int32_t* pos, const float* age_begin,
                      const float* age_end, const uint32_t* meta, int location)
 {

@@ -79,6 +79,10 @@ struct colate_handle {
   int64_t n_used = 0;
   int n_blocks_local = 0;
   int64_t mt_total_local = 0;
+  // generator-stream cache (colate_set_stream_cache): state, offset and length of the tile-ordered stream in rng_stream
+  bool stream_cache_on = false, sc_valid = false, mt_tail_gather = false;
+  uint32_t sc_state[624] = {};
+  int64_t sc_word0 = -1, sc_nwords = 0, sc_off = 0;
   bool thr_ready = false;
   colate_stage1_timing timing = {};
   // stage 2/3

@@ -9,6 +9,7 @@
 // (the recurrence exposes 227-wide parallelism per step) and written tempered to HBM.
 #include "device.cuh"
 
+#include <cstring>
 #include <map>
 #include <mutex>
 
@@ -177,6 +178,14 @@ k_gen(const uint32_t* __restrict__ windows, int64_t chunk_words, int64_t total_w
   }
 }
 
+// the n words before logical position `from + n` of a tile-ordered stream, linearly (state recovery when the stream in
+// HBM is longer than the caller's request: stream cache)
+__global__ void k_tail_gather(const uint32_t* __restrict__ stream, int64_t tile_off, int64_t from, int n, uint32_t* __restrict__ tail)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tail[i] = stream[stream_phys(from + i, tile_off)];
+}
+
 // ---- tap lists per polynomial, cached per device -------------------------------------------
 struct TapList { uint16_t* d = nullptr; int n = 0; };
 static std::mutex g_mu;
@@ -227,6 +236,21 @@ int run_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int
                   uint32_t** stream_at_word0, uint32_t* window_after, bool tiled)
 {
   if (k < 0 || k > 40) return fail(COLATE_ERR_ARG, "bad chunk size");
+  // Stream cache (colate_set_stream_cache; all-pairs jobs reseed every pair with the same --seed): the words
+  // from `word0` on depend only on the generator state, so a tile-ordered stream left by an earlier call with the
+  // same state and offset serves every request that is not longer.  The state after THIS request's last word is
+  // then gathered from the stream (mt_window_after).
+  if (tiled && h->stream_cache_on && h->sc_valid && word0 == h->sc_word0 && n_words <= h->sc_nwords &&
+      memcmp(mt_state, h->sc_state, sizeof h->sc_state) == 0) {
+    *stream_at_word0 = h->rng_stream.as<uint32_t>() + h->sc_off;
+    h->mt_total_local = h->sc_off + n_words;
+    h->mt_tail_gather = true;
+    if (window_after) return mt_window_after(h, window_after);
+    return 0;
+  }
+  h->sc_valid = false;
+  const int64_t n_req = n_words;
+  if (tiled && h->stream_cache_on) n_words += n_words / 8 + SAMPLE_TILE_WORDS;   // headroom: the next pairs use a few more rows
   const int64_t S = (int64_t)200 << k;
   const int64_t c0 = word0 / S;
   const int64_t last = n_words > 0 ? word0 + n_words - 1 : word0;
@@ -269,7 +293,12 @@ int run_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int
     CK(cudaGetLastError());
   }
   *stream_at_word0 = h->rng_stream.as<uint32_t>() + off;
-  h->mt_total_local = total_local;
+  h->mt_total_local = off + n_req;
+  h->mt_tail_gather = tiled && n_req != n_words;
+  if (tiled && h->stream_cache_on) {
+    memcpy(h->sc_state, mt_state, sizeof h->sc_state);
+    h->sc_word0 = word0; h->sc_nwords = n_words; h->sc_off = off; h->sc_valid = true;
+  }
   if (window_after) return mt_window_after(h, window_after);
   return 0;
 }
@@ -284,8 +313,15 @@ int mt_window_after(colate_handle* h, uint32_t* window_after)
   uint32_t w0[MT_N];
   std::vector<uint32_t> tail((size_t)std::min<int64_t>(T, MT_N));
   CK(cudaMemcpyAsync(w0, h->windows.p, MT_N * 4, cudaMemcpyDeviceToHost, s));
-  if (!tail.empty())
-    CK(cudaMemcpyAsync(tail.data(), h->mt_tail.p, tail.size() * 4, cudaMemcpyDeviceToHost, s));   // k_gen's linear copy of the last words
+  if (!tail.empty()) {
+    if (h->mt_tail_gather) {   // the stream in HBM runs past T: pick the words in front of T out of the tile order
+      k_tail_gather<<<(int)(tail.size() + 255) / 256, 256, 0, s>>>(h->rng_stream.as<uint32_t>(), h->sc_off, T - (int64_t)tail.size(),
+                                                                (int)tail.size(), h->mt_tail.as<uint32_t>());
+      h->launches += 1;
+      CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(tail.data(), h->mt_tail.p, tail.size() * 4, cudaMemcpyDeviceToHost, s));   // the last words, linearly (k_gen's copy or the gather)
+  }
   CK(cudaStreamSynchronize(s));
   for (int j = 0; j < MT_N; j++) {
     int64_t i = T + j;  // index into y

@@ -4,8 +4,9 @@ The reference is run once per pair (`Colate --mode mut --target_tmp i --referenc
 estimator is asymmetric in target / reference (coal.cpp:2198, 2236-2242).  On the device the pairs share
 almost everything:
   * the mutation SoA is uploaded once, every genome is joined against it once (k_join; the joined
-    columns are cached per genome slot) -- only the per-pair passes (flags, generator stream, sampling,
-    exact replay, stage ii) run per pair;
+    columns are cached per genome slot), and because every pair reseeds with the same --seed they all
+    consume prefixes of ONE generator stream, which is generated once (colate_set_stream_cache) --
+    only the per-pair passes (flags, compaction, sampling, exact replay, stage ii) run per pair;
   * the EM of ALL pairs runs as one launch in throughput mode (one CTA per pair, 2 CTAs/SM), ~0.3 ms per
     pair instead of the ~21 ms the latency-mode EM needs for a single pair.
 Results per pair are what `api.mut()` returns for that pair alone (same seed): bit-identical.
@@ -38,11 +39,15 @@ def all_pairs(handle: api.Handle, n_genomes: int, seed: int, bins: str = "3,7,0.
     nb = np.zeros(P, dtype=np.int32)
     nu = np.zeros(P, dtype=np.int64)
     t0 = time.perf_counter()
-    for p, (i, j) in enumerate(pairs):
-        s1 = handle.stage1(api.mt_seed(seed), target_slot=i, reference_slot=j)      # the reference reseeds per run
-        w = api.draw_block_weights(s1.mt_state, 1, s1.num_blocks)
-        counts[p] = handle.stage2_bootstrap(w, s1.block_stats, age)[0]
-        nb[p], nu[p] = s1.num_blocks, s1.n_used
+    handle.set_stream_cache(True)       # every pair reseeds with the same --seed: one generator stream serves them all
+    try:
+        for p, (i, j) in enumerate(pairs):
+            s1 = handle.stage1(api.mt_seed(seed), target_slot=i, reference_slot=j)      # the reference reseeds per run
+            w = api.draw_block_weights(s1.mt_state, 1, s1.num_blocks)
+            counts[p] = handle.stage2_bootstrap(w, s1.block_stats, age)[0]
+            nb[p], nu[p] = s1.num_blocks, s1.n_used
+    finally:
+        handle.set_stream_cache(False)
     t1 = time.perf_counter()
     rates = np.zeros((P, epochs.shape[0]))
     iters = np.zeros(P, dtype=np.int32)

@@ -50,6 +50,12 @@ int colate_create(int device, colate_handle** out);
 void colate_destroy(colate_handle* h);
 /* cudaStream_t the handle launches on (as void*), for event timing by the caller. */
 void* colate_stream(colate_handle* h);
+/* Keep the generator stream (the std::mt19937 words parse_tmptmp consumes, coal.cpp:2262/2282) in device memory
+ * between colate_stage1* calls and reuse it whenever a call starts from the same generator state at the same
+ * offset and needs no more words than are there.  Off by default.  For all-pairs jobs: the reference is run
+ * once per pair with the same --seed (mut(), coal.cpp:3157-3162), so every pair consumes a prefix of one and the
+ * same stream; results are unchanged (the stream is a function of the state alone). */
+int colate_set_stream_cache(colate_handle* h, int enable);
 
 /* ---- inputs: what parse_tmptmp (coal.cpp:2072) obtains from its readers -------------- */
 

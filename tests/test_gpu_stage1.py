@@ -274,3 +274,27 @@ def test_stage1_chromosome_shards_on_one_gpu(handle, world):
     a = np.zeros(64, np.uint32); b = np.array([po.lib().oracle_mt_next(o["rng"]) for _ in range(64)], np.uint32)
     api.lib().colate_mt_generate(state.copy(), 64, a)                           # the last shard holds the final generator state
     assert np.array_equal(a, b)
+
+
+def test_stream_cache_serves_shorter_and_longer_requests(handle):
+    """colate_set_stream_cache: pairs with fewer / more used rows than the stream left in HBM, a different seed and a
+    switch back -- histograms and the generator state after the stage are those of the uncached calls."""
+    sites = synth.make_sites(21, [6000, 5000], [2.0e8, 1.1e8])
+    cover = (0.7, 0.3, 0.9, 0.5, 0.95)                              # used rows differ by far more than the cache's headroom
+    genomes = [synth.make_genome(400 + g, sites, c) for g, c in enumerate(cover)]
+    handle.set_sites(sites.site_off, sites.pos, sites.age_begin, sites.age_end, sites.meta())
+    for g, G in enumerate(genomes):
+        handle.set_genome(g, G.chrom, G.bp, G.aaf, G.daf, G.anc.astype(np.uint16) | (G.der.astype(np.uint16) << 8))
+        handle.set_mask(g, None)
+    calls = [(0, 1, 5), (1, 2, 5), (2, 4, 5), (3, 1, 5), (0, 2, 6), (2, 4, 5), (1, 3, 5)]
+    plain = [handle.stage1(api.mt_seed(s), target_slot=i, reference_slot=j) for i, j, s in calls]
+    assert len({p.n_used for p in plain}) > 3
+    handle.set_stream_cache(True)
+    try:
+        cached = [handle.stage1(api.mt_seed(s), target_slot=i, reference_slot=j) for i, j, s in calls]
+    finally:
+        handle.set_stream_cache(False)
+    for a, b in zip(plain, cached):
+        assert a.n_used == b.n_used and a.num_blocks == b.num_blocks
+        assert np.array_equal(a.block_stats, b.block_stats) and np.array_equal(a.block_tallies, b.block_tallies)
+        assert np.array_equal(a.mt_state, b.mt_state)
