@@ -89,6 +89,7 @@ TEST_HOOKS = {
     "colate_test_jump_window_host": (C.c_int, [u32, C.c_int, u32]),
     "colate_test_bin_thresholds": (C.c_int, [f64]),
     "colate_test_add_repeated": (C.c_double, [C.c_double, C.c_double, C.c_int]),
+    "colate_test_stream_phys": (C.c_int64, [C.c_int64, C.c_int64]),
     "colate_test_libm": (C.c_int, [VP, C.c_int, C.c_int, f64, f64]),
     "colate_test_bin_fast": (C.c_int, [VP, C.c_int, f64, i32, i32]),
     "colate_test_bin_sweep": (C.c_int, [VP, C.c_uint32, C.c_uint32, _p(dtype=np.uint64, flags="C_CONTIGUOUS")]),

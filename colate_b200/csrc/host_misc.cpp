@@ -167,6 +167,7 @@ void colate_age_bins(double* age_bin)
 
 int colate_test_bin_thresholds(double* thr10) { return bin_thresholds(thr10) ? 0 : 1; }
 double colate_test_add_repeated(double acc, double w, int c) { return exsum::add_repeated(acc, w, c); }
+int64_t colate_test_stream_phys(int64_t o, int64_t off) { return stream_phys(o, off); }
 
 uint32_t colate_site_meta(int flipped, int n_branch, float age_begin, float age_end, const char* mutation_type)
 {

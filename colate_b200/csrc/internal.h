@@ -82,6 +82,7 @@ int colate_test_charpoly_terms(int* out, int cap);
 int colate_test_jump_window_host(const uint32_t* w, int q, uint32_t* out);
 int colate_test_bin_thresholds(double* thr10);
 double colate_test_add_repeated(double acc, double w, int c);
+int64_t colate_test_stream_phys(int64_t o, int64_t off);
 int colate_test_libm(colate_handle* h, int which, int n, const double* x, double* y);
 int colate_test_bin_fast(colate_handle* h, int n, const double* ages, int32_t* fast, int32_t* exact);
 int colate_test_bin_sweep(colate_handle* h, uint32_t lo_bits, uint32_t hi_bits, uint64_t* out3);

@@ -256,3 +256,21 @@ def test_cli_surface(built):
             r = subprocess.run([cli, "--mode", "mut", "--mut", d + "/x", "--target_tmp", "a", "--reference_tmp", "b", "--bins", "3,7,0.2",
                                 "--num_bootstrap", "2", "-o", d + "/o"], capture_output=True, text=True)
             assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def test_generator_stream_tile_order(built):
+    """internal.h: stream_phys -- where k_gen puts word o of the generator stream so that k_sample can fetch tile t /
+    chunk c of 32 used rows as one contiguous block: a bijection onto whole tiles, linear in front of the tiling origin,
+    rows of a block 20 words apart, blocks of a tile back to back."""
+    from colate_b200 import _lib
+    phys = _lib.lib().colate_test_stream_phys
+    assert [phys(o, -1) for o in (0, 5, 12345)] == [0, 5, 12345]              # linear mode (test hook / plain stream)
+    for off in (0, 200 * 7, 200 * 1000):
+        assert all(phys(o, off) == o for o in range(max(0, off - 300), off))  # words before the origin stay in place
+        n_rows = 32 * 3                                                         # three whole tiles
+        got = np.array([phys(off + q, off) for q in range(200 * n_rows)], dtype=np.int64) - off
+        assert np.array_equal(np.sort(got), np.arange(200 * n_rows))           # a permutation of the tiles' words
+        q = np.arange(200 * n_rows)
+        row, w = q // 200, q % 200
+        want = ((row // 32) * 10 + w // 20) * 640 + (row % 32) * 20 + w % 20    # [tile][chunk][row][20 words]
+        assert np.array_equal(got, want)
