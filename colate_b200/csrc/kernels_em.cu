@@ -951,6 +951,9 @@ int run_em(colate_handle* h, int R, int E, int max_iter)
   else {
     while (csize < 8 && R * csize * 2 <= 148) csize *= 2;
     if (csize == 8 && R * 16 * 2 <= 148) csize = 16;   // non-portable cluster size: one GPC (16-20 SMs) per replicate
+    // 19..37 replicates: clusters of 8 on k_em_split (two CTAs per SM) beat k_em's clusters of 4 (measured at R = 30:
+    // 59 ms against 73.5 ms, and 80 ms at one CTA per replicate; profiles/r01_em_phase_profile.md)
+    if (csize == 4 && R * 8 <= 2 * 148) csize = 8;
   }
   if (csize != 1 && csize != 2 && csize != 4 && csize != 8 && csize != 16) csize = 1;
   // latency mode: one replicate over a cluster of 8 or 16 (k_em_split) when its per-CTA tables fit

@@ -149,3 +149,18 @@ def test_em_throughput_mode_many_replicates(handle):
         ro, it, llo = po.em_run(ep, init, counts[r])
         assert iters[r] == it and _same(rates[r], ro) and _same(ll[r], llo)
     assert len({tuple(x) for x in rates}) > R // 2      # the replicates really differ
+
+
+def test_em_mid_range_replicates_on_split_clusters(handle):
+    """19..37 replicates run as clusters of 8 on k_em_split, two CTAs per SM; spot-checked against the oracle."""
+    o = _block_stats()
+    R = 24
+    w = api.draw_block_weights(api.mt_seed(12), R, o["num_blocks"])
+    counts = po.stage2(w, o, 0.0)
+    ep, _ = po.epochs_from_bins("3,7,0.2", 0.0, 28.0)
+    init = np.full(len(ep), 1 / 20000.)
+    rates, iters, ll = handle.stage3_em(R, ep, init, counts, max_iter=300)
+    for r in (0, 13, 23):
+        ro, it, llo = po.em_run(ep, init, counts[r], max_iter=300)
+        assert iters[r] == it and _same(rates[r], ro) and _same(ll[r], llo)
+    assert len({tuple(x) for x in rates}) > R // 2
