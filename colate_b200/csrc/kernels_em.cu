@@ -954,6 +954,7 @@ int run_em(colate_handle* h, int R, int E, int max_iter)
     // 19..37 replicates: clusters of 8 on k_em_split (two CTAs per SM) beat k_em's clusters of 4 (measured at R = 30:
     // 59 ms against 73.5 ms, and 80 ms at one CTA per replicate; profiles/r01_em_phase_profile.md)
     if (csize == 4 && R * 8 <= 2 * 148) csize = 8;
+    if (csize == 2) csize = 1;                         // 38..74 replicates: pairs of CTAs are slower than single CTAs (R = 60: 66.4 against 61.3 ms)
   }
   if (csize != 1 && csize != 2 && csize != 4 && csize != 8 && csize != 16) csize = 1;
   // latency mode: one replicate over a cluster of 8 or 16 (k_em_split) when its per-CTA tables fit
