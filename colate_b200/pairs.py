@@ -10,6 +10,9 @@ almost everything:
   * the EM of ALL pairs runs as one launch in throughput mode (one CTA per pair, 2 CTAs/SM), ~0.3 ms per
     pair instead of the ~21 ms the latency-mode EM needs for a single pair.
 Results per pair are what `api.mut()` returns for that pair alone (same seed): bit-identical.
+
+Across GPUs (`all_pairs_sharded`): pair p -> rank p mod world, every rank holds the mutation SoA and
+all genomes, no collective on the data path; the result tables are combined by one all-reduce at the end.
 """
 from __future__ import annotations
 
@@ -58,3 +61,39 @@ def all_pairs(handle: api.Handle, n_genomes: int, seed: int, bins: str = "3,7,0.
     t2 = time.perf_counter()
     return dict(pairs=np.array(pairs, dtype=np.int32).reshape(P, 2), epochs=epochs, ep_null=ep_null, rates=rates, iters=iters,
                 ll=ll, num_blocks=nb, n_used=nu, counts=counts, seconds=dict(stage12=t1 - t0, em=t2 - t1))
+
+
+def all_pairs_sharded(handle, n_genomes: int, seed: int, bins: str = "3,7,0.1", pairs=None, device="cuda", **kw):
+    """`all_pairs` across the ranks of the default torch.distributed process group (NCCL on GPUs, gloo in the CPU
+    tests).  Pair p of the list goes to rank p mod world; each rank runs its pairs exactly as `all_pairs` does (its own
+    generator-stream cache, its own batched EM launch).  Every rank returns the full tables: the per-rank rows are
+    placed into zero tables and summed as 64-bit integers (bit patterns; disjoint supports), so the combined result is
+    bit-identical to a single-process run.  `seconds` holds the maximum over the ranks."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if pairs is None:
+        pairs = list(itertools.combinations(range(n_genomes), 2))
+    pairs = [(int(i), int(j)) for i, j in pairs]
+    P = len(pairs)
+    mine = np.arange(rank, P, world)
+    res = all_pairs(handle, n_genomes, seed, bins, pairs=[pairs[k] for k in mine], **kw)
+    E = res["epochs"].shape[0]
+
+    def combine(rows, shape, dtype):
+        full = np.zeros((P,) + shape, dtype=dtype)
+        if mine.shape[0]:
+            full[mine] = rows
+        t = torch.from_numpy(full.view(np.int64) if dtype == np.float64 else full.astype(np.int64)).to(device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        out = t.cpu().numpy()
+        return out.view(np.float64) if dtype == np.float64 else out.astype(dtype)
+
+    out = dict(pairs=np.array(pairs, dtype=np.int32).reshape(P, 2), epochs=res["epochs"], ep_null=res["ep_null"],
+               rates=combine(res["rates"], (E,), np.float64), iters=combine(res["iters"], (), np.int32),
+               ll=combine(res["ll"], (), np.float64), num_blocks=combine(res["num_blocks"], (), np.int32),
+               n_used=combine(res["n_used"], (), np.int64), counts=combine(res["counts"], (2, api.NBINS), np.float64))
+    sec = torch.tensor([res["seconds"]["stage12"], res["seconds"]["em"]], dtype=torch.float64, device=device)
+    dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+    out["seconds"] = dict(stage12=float(sec[0]), em=float(sec[1]))
+    return out

@@ -141,3 +141,81 @@ def test_split_chromosomes():
     for w in (1, 2, 3, 8):
         parts = split_chromosomes([249, 243, 198, 191, 180, 171, 159, 146, 141, 135, 135, 133, 115, 107, 102, 90, 81, 78, 59, 63, 48, 51], w)
         assert parts[0][0] == 0 and parts[-1][1] == 22 and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+
+
+class OracleHandle:
+    """Stand-in for api.Handle with genomes in slots (the contract pairs.all_pairs uses), computed by the CPU oracle."""
+
+    def __init__(self, sites, genomes):
+        self.sites, self.genomes = sites, genomes
+
+    def set_stream_cache(self, enable):
+        pass
+
+    def stage1(self, mt_state, target_slot=0, reference_slot=1):
+        from types import SimpleNamespace
+        from colate_b200 import api
+        from oracle import pyoracle as po
+        o = po.stage1(self.sites, self.genomes[target_slot], self.genomes[reference_slot], seed=self.seed)
+        after = api.mt_seed(self.seed)
+        burn = np.zeros(max(1, 200 * o["n_used_total"]), np.uint32)
+        api.lib().colate_mt_generate(after, 200 * o["n_used_total"], burn)
+        stats = np.stack([o["shared"], o["notshared"], o["shared_emp"], o["notshared_emp"]], axis=1)
+        return SimpleNamespace(num_blocks=o["num_blocks"], n_used=o["n_used_total"], block_stats=stats, mt_state=after)
+
+    def stage2_bootstrap(self, w, block_stats, age):
+        from oracle import pyoracle as po
+        blk = {k: np.ascontiguousarray(block_stats[:, i]) for i, k in enumerate(("shared", "notshared", "shared_emp", "notshared_emp"))}
+        return po.stage2(np.ascontiguousarray(w), blk, age)
+
+    def stage3_em(self, R, epochs, init, counts, max_iter):
+        from oracle import pyoracle as po
+        out = [po.em_run(epochs, init, counts[r], max_iter) for r in range(R)]
+        return np.stack([o[0] for o in out]), np.array([o[1] for o in out], np.int32), np.array([o[2] for o in out])
+
+
+def _pairs_inputs(seed):
+    from colate_b200 import synth
+    sites = synth.make_sites(seed, [700, 500], [2.4e8, 1.3e8])
+    return sites, [synth.make_genome(seed + 50 + g, sites, 0.8) for g in range(4)]
+
+
+def _pairs_worker(rank, world, port, seed, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from colate_b200 import pairs as pairs_mod
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sites, genomes = _pairs_inputs(seed)
+    h = OracleHandle(sites, genomes)
+    h.seed = seed
+    res = pairs_mod.all_pairs_sharded(h, len(genomes), seed, bins="3,7,0.2", device="cpu", max_iter=20)
+    q.put((rank, res["pairs"], res["rates"], res["iters"], res["ll"], res["num_blocks"], res["n_used"], res["counts"]))
+    dist.destroy_process_group()
+
+
+def test_all_pairs_sharded_world2(built):
+    """configs[4] host logic: pairs dealt round-robin to two ranks, tables combined -- identical to one process."""
+    from colate_b200 import pairs as pairs_mod
+    seed, world = 6, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pairs_worker, args=(r, world, port, seed, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=150) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    sites, genomes = _pairs_inputs(seed)
+    h = OracleHandle(sites, genomes)
+    h.seed = seed
+    one = pairs_mod.all_pairs(h, len(genomes), seed, bins="3,7,0.2", max_iter=20)
+    assert one["pairs"].shape == (6, 2) and len({int(x) for x in one["n_used"]}) > 1
+    for rank, prs, rates, iters, ll, nb, nu, counts in outs:
+        assert np.array_equal(prs, one["pairs"])
+        assert np.array_equal(rates.view(np.int64), one["rates"].view(np.int64))       # bit patterns
+        assert np.array_equal(ll.view(np.int64), one["ll"].view(np.int64))
+        assert np.array_equal(iters, one["iters"]) and np.array_equal(nb, one["num_blocks"]) and np.array_equal(nu, one["n_used"])
+        assert np.array_equal(counts, one["counts"])
