@@ -74,7 +74,9 @@ SIGNATURES = {
     "colate_epochs_from_coal_file": (C.c_int, [C.c_char_p, C.c_double, f64, f64, C.c_int]),
     "colate_ingest_begin": (C.c_int, [VP, C.c_int, C.c_int64]),
     "colate_ingest_mut_text": (C.c_int64, [VP, VP, C.c_int64, C.c_int]),
+    "colate_ingest_mut_texts": (C.c_int, [VP, C.c_int, C.POINTER(VP), i64, C.c_int, VP]),
     "colate_ingest_end": (C.c_int, [VP]),
+    "colate_ingest_colate_in": (C.c_int64, [VP, C.c_int, VP, C.c_int64, C.c_int, C.POINTER(C.c_char_p), C.c_int]),
     "colate_ingest_fetch": (C.c_int, [VP, C.c_int64, C.c_int64, VP, VP, VP, VP]),
     "colate_ingest_stats": (C.c_int, [VP, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "colate_read_mut": (C.c_int64, [C.c_char_p, C.c_int64, VP, VP, VP, VP]),
@@ -90,6 +92,7 @@ TEST_HOOKS = {
     "colate_test_bin_thresholds": (C.c_int, [f64]),
     "colate_test_add_repeated": (C.c_double, [C.c_double, C.c_double, C.c_int]),
     "colate_test_stream_phys": (C.c_int64, [C.c_int64, C.c_int64]),
+    "colate_test_colate_in_runs": (C.c_int64, [VP, C.c_int64, C.c_int, C.POINTER(C.c_char_p), C.c_int, i64, i64, i64]),
     "colate_test_libm": (C.c_int, [VP, C.c_int, C.c_int, f64, f64]),
     "colate_test_bin_fast": (C.c_int, [VP, C.c_int, f64, i32, i32]),
     "colate_test_bin_sweep": (C.c_int, [VP, C.c_uint32, C.c_uint32, _p(dtype=np.uint64, flags="C_CONTIGUOUS")]),

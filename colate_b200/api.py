@@ -75,6 +75,17 @@ def chr_ranges(n_chr: int, rec_chrom: np.ndarray):
     return first, end
 
 
+def colate_in_runs(image: bytes, chr_names, cap_runs=4096):
+    """Test hook: the host run finder of .colate.in images -> (n_rec, runs[n,4] = byte_off/width/chr_id/n_rec, first, end)."""
+    buf = np.frombuffer(image, dtype=np.uint8) if len(image) else np.zeros(1, np.uint8)
+    names = (C.c_char_p * len(chr_names))(*[s.encode() for s in chr_names])
+    runs = np.zeros((cap_runs, 4), dtype=np.int64)
+    first = np.zeros(max(1, len(chr_names)), dtype=np.int64); end = np.zeros(max(1, len(chr_names)), dtype=np.int64)
+    r = check(lib().colate_test_colate_in_runs(C.c_void_p(buf.ctypes.data), len(image), len(chr_names), names, cap_runs, runs, first, end))
+    n_rec, n_runs = r & ((1 << 40) - 1), r >> 40
+    return n_rec, runs[:n_runs].copy(), first[:len(chr_names)], end[:len(chr_names)]
+
+
 def read_mut(path: str):
     """Relate .mut[.gz] -> (pos, age_begin, age_end, meta) (mutations.cpp:56-283)."""
     n = check(lib().colate_read_mut(path.encode(), 0, None, None, None, None))
@@ -197,6 +208,30 @@ class Handle:
         self.n_site = int(sum(rows))
         return rows
 
+    def ingest_mut_bytes(self, bufs, row_capacity=None):
+        """Same as ingest_mut for uint8 arrays (pinned host memory: torch.Tensor.pin_memory().numpy()): ONE call for all
+        chromosomes, the copies run on the handle's copy stream under the parse kernels of the chromosomes before."""
+        n = len(bufs)
+        if row_capacity is None:
+            row_capacity = sum(int(b.shape[0]) for b in bufs) // 20 + n     # a data row has at least 10 fields
+        check(lib().colate_ingest_begin(self._h, n, row_capacity))
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        sizes = np.array([b.shape[0] for b in bufs], dtype=np.int64)
+        rows = np.zeros(n, dtype=np.int64)
+        check(lib().colate_ingest_mut_texts(self._h, n, ptrs, sizes, 0, ptr(rows)))
+        check(lib().colate_ingest_end(self._h))
+        self.n_chr = n
+        self.n_site = int(rows.sum())
+        return rows
+
+    def ingest_colate_in(self, slot, image, chr_names):
+        """.colate.in image (bytes or a uint8 array, e.g. pinned) -> genome slot, decoded on the device.
+        Replaces read_colate_in() + set_genome().  Returns the number of records."""
+        buf = np.frombuffer(image, dtype=np.uint8) if isinstance(image, (bytes, bytearray, memoryview)) else image
+        names = (C.c_char_p * len(chr_names))(*[s.encode() for s in chr_names])
+        return check(lib().colate_ingest_colate_in(self._h, slot, C.c_void_p(buf.ctypes.data if buf.shape[0] else None), int(buf.shape[0]),
+                                                   len(chr_names), names, 0))
+
     def ingest_fetch(self, row0=0, n_rows=None):
         n = self.n_site - row0 if n_rows is None else n_rows
         pos = np.zeros(n, np.int32); ab = np.zeros(n, np.float32); ae = np.zeros(n, np.float32); meta = np.zeros(n, np.uint32)
@@ -229,8 +264,31 @@ class Handle:
                                          ptr(out_state)))
         return stats, tallies, out_state
 
-    def stage1(self, mt_state, target_slot=0, reference_slot=1) -> Stage1Result:
-        """parse_tmptmp (coal.cpp:2072) on one GPU."""
+    def stage1_sample_dev(self, mt_state, used_rank_base, block_base, stats_ptr, tallies_ptr, want_state=True):
+        """stage1_sample with DEVICE destinations (e.g. rows of a torch tensor: tensor.data_ptr() + offset)."""
+        mt_state = np.ascontiguousarray(mt_state, dtype=np.uint32)
+        out_state = np.zeros(MT_WORDS, dtype=np.uint32) if want_state else None
+        check(lib().colate_stage1_sample(self._h, ptr(mt_state), used_rank_base, block_base,
+                                         C.c_void_p(stats_ptr) if stats_ptr else None, C.c_void_p(tallies_ptr) if tallies_ptr else None,
+                                         ptr(out_state)))
+        return out_state
+
+    def stage2_bootstrap_dev(self, block_weights, stats_ptr, num_blocks, age=0.0):
+        """stage2_bootstrap on block histograms that already sit on the device: stats_ptr = device pointer to
+        [num_blocks][4][185] fp64, or None for what the last stage1 call left in the handle.  Counts stay on the device."""
+        w = np.ascontiguousarray(block_weights, dtype=np.int32)
+        assert w.shape[1] == num_blocks
+        check(lib().colate_stage2_bootstrap(self._h, w.shape[0], num_blocks, ptr(w), C.c_void_p(stats_ptr) if stats_ptr else None, age, None))
+
+    def stage1(self, mt_state, target_slot=0, reference_slot=1, fetch=True) -> Stage1Result:
+        """parse_tmptmp (coal.cpp:2072) on one GPU.  fetch=False: the histograms stay on the device
+        (stage2_bootstrap_dev(w, None, num_blocks)); block_stats / block_tallies of the result are None."""
+        if not fetch:
+            nb, nu = C.c_int(0), C.c_int64(0)
+            mt_state = np.ascontiguousarray(mt_state, dtype=np.uint32)
+            out_state = np.zeros(MT_WORDS, dtype=np.uint32)
+            check(lib().colate_stage1(self._h, target_slot, reference_slot, ptr(mt_state), C.byref(nb), None, None, C.byref(nu), ptr(out_state)))
+            return Stage1Result(nb.value, None, None, nu.value, out_state)
         stats = np.zeros((MAX_BLOCKS, 4, NBINS))
         tallies = np.zeros((MAX_BLOCKS, 3, NBINS), dtype=np.int64)
         nb, nu = C.c_int(0), C.c_int64(0)

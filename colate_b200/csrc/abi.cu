@@ -63,18 +63,45 @@ int libm_self_check()
   return ok;
 }
 
+// New site arrays are in place (colate_set_sites / colate_ingest_end): every genome's chromosome ranges, join and mask
+// refer to the previous site axis and --chr list, so all slots go back to "not set"; the order check of the
+// sites is queued (its verdict is read by colate_stage1_flags: COLATE_ERR_ORDER).
+int sites_replaced(colate_handle* h)
+{
+  h->sites_set = true;
+  h->flags_done = false;
+  for (auto& g : h->genomes) { g.set = false; g.joined = false; g.has_mask = false; }
+  CK(h->order_flag.ensure((1 + COLATE_MAX_GENOMES) * 4));
+  CK(cudaMemsetAsync(h->order_flag.p, 0, (1 + COLATE_MAX_GENOMES) * 4, h->stream));
+  return run_check_sites(h);
+}
+int genome_replaced(colate_handle* h, int slot)
+{
+  GenomeDev& g = h->genomes[slot];
+  g.set = true;
+  g.joined = false;
+  h->flags_done = false;
+  CK(cudaMemsetAsync(h->order_flag.as<int>() + 1 + slot, 0, 4, h->stream));
+  return run_check_genome(h, slot);
+}
+
 int pick_chunk_log2(int64_t n_used)
 {
   if (const char* e = getenv("COLATE_CHUNK_LOG2")) return std::max(0, std::min(30, atoi(e)));
   // ~2 generator chunks per SM: a jump costs as much shared-memory traffic as generating ~1 M words,
   // while fewer than ~300 sequential chunks leave the generator latency-bound (measured optimum on B200)
-  int64_t per = (n_used + 295) / 296;
+  int64_t per = (n_used + 295) / 296;   // (296 = 2 x 148 SMs; the optimum is flat around it)
   int k = 0;
   while ((int64_t(1) << k) < per) k++;
   return std::max(3, std::min(k, 24));
 }
 
 }  // namespace
+
+namespace colate {
+int sites_replaced_ext(colate_handle* h) { return sites_replaced(h); }
+int genome_replaced_ext(colate_handle* h, int slot) { return genome_replaced(h, slot); }
+}
 
 extern "C" {
 
@@ -93,8 +120,14 @@ int colate_create(int device, colate_handle** out)
   colate_handle* h = new colate_handle();
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
-  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
+  cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  for (auto& ev : h->ev) if (ce == cudaSuccess) ce = cudaEventCreate(&ev);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->copy_done, cudaEventDisableTiming);
+  if (ce != cudaSuccess) {   // nothing half-built leaves this function
+    colate_destroy(h);
+    return fail(COLATE_ERR_CUDA, std::string("colate_create: ") + cudaGetErrorString(ce));
+  }
   *out = h;
   return 0;
 }
@@ -103,20 +136,24 @@ void colate_destroy(colate_handle* h)
 {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   DevBuf* bufs[] = {&h->site_off, &h->pos, &h->ab, &h->ae, &h->meta, &h->candR, &h->candT, &h->use, &h->word_rank, &h->scan_tmp,
                     &h->chr_used, &h->chr_blocks, &h->chr_block_base, &h->misc, &h->u_hdr, &h->u_eb2, &h->u_ews, &h->u_ewn, &h->u_cnt,
                     &h->u_blk, &h->blk_rank_start, &h->out_f, &h->out_n, &h->thrA, &h->lut, &h->d_scratch, &h->d_prof, &h->libm_tab, &h->ing_text, &h->ing_tile_cnt, &h->ing_tile_off, &h->ing_nl, &h->ing_status, &h->ing_fb,
                     &h->windows, &h->rng_stream, &h->mt_tail, &h->poly, &h->thr10, &h->d_counts, &h->d_blockstats, &h->d_weights, &h->d_epochs,
-                    &h->d_rates, &h->d_iters, &h->d_ll, &h->d_agebin, &h->d_tmp};
+                    &h->d_rates, &h->d_iters, &h->d_ll, &h->d_agebin, &h->d_tmp, &h->order_flag, &h->ing_raw};
   for (DevBuf* b : bufs) b->release();
   for (auto& g : h->genomes) {
     DevBuf* gb[] = {&g.bp, &g.aaf, &g.daf, &g.alleles, &g.chr_first, &g.chr_end, &g.mask_bits, &g.j_aaf, &g.j_daf, &g.j_prevbp, &g.j_flag};
     for (DevBuf* b : gb) b->release();
   }
   for (int k = 0; k < 2; k++) if (h->ing_bounce[k]) { cudaFreeHost(h->ing_bounce[k]); cudaEventDestroy(h->ing_bounce_ev[k]); }
-  for (auto& ev : h->ev) cudaEventDestroy(ev);
-  cudaStreamDestroy(h->stream);
+  for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : h->ing_evs) cudaEventDestroy(ev);
+  if (h->copy_done) cudaEventDestroy(h->copy_done);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
 
@@ -133,7 +170,9 @@ int colate_set_stream_cache(colate_handle* h, int enable)
 int colate_set_sites(colate_handle* h, int n_chr, const int64_t* site_off, const int32_t* pos, const float* age_begin,
                      const float* age_end, const uint32_t* meta, int location)
 {
-  if (!h || n_chr <= 0 || !site_off) return fail(COLATE_ERR_ARG, "colate_set_sites: bad arguments");
+  // n_chr == 0 (site_off = {0}) is legal: a rank of a chromosome-sharded job that owns no chromosome still takes
+  // part in every exchange with zero used rows and zero blocks
+  if (!h || n_chr < 0 || !site_off) return fail(COLATE_ERR_ARG, "colate_set_sites: bad arguments");
   CK(cudaSetDevice(h->device));
   std::vector<int64_t> off(n_chr + 1);
   if (location) CK(cudaMemcpy(off.data(), site_off, (n_chr + 1) * 8, cudaMemcpyDeviceToHost));
@@ -144,19 +183,17 @@ int colate_set_sites(colate_handle* h, int n_chr, const int64_t* site_off, const
   if (n >= (int64_t(1) << 31)) return fail(COLATE_ERR_ARG, "more than 2^31 rows per handle");
   CK(h->site_off.ensure((n_chr + 1) * 8)); CK(h->pos.ensure(n * 4 + 4)); CK(h->ab.ensure(n * 4 + 4));
   CK(h->ae.ensure(n * 4 + 4)); CK(h->meta.ensure(n * 4 + 4));
-  CK(cudaMemcpyAsync(h->site_off.p, off.data(), (n_chr + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+  h->h_site_off = off;   // (the async copy below reads the handle's copy, not the local)
+  CK(cudaMemcpyAsync(h->site_off.p, h->h_site_off.data(), (n_chr + 1) * 8, cudaMemcpyHostToDevice, h->stream));
   int rc;
   if ((rc = copy_in(h->pos.p, pos, n * 4, location, h->stream))) return rc;
   if ((rc = copy_in(h->ab.p, age_begin, n * 4, location, h->stream))) return rc;
   if ((rc = copy_in(h->ae.p, age_end, n * 4, location, h->stream))) return rc;
   if ((rc = copy_in(h->meta.p, meta, n * 4, location, h->stream))) return rc;
-  CK(cudaStreamSynchronize(h->stream));
   h->n_chr = n_chr;
   h->n_site = n;
-  h->h_site_off = off;
-  h->sites_set = true;
-  h->flags_done = false;
-  for (auto& g : h->genomes) { g.joined = false; g.has_mask = false; }
+  if ((rc = sites_replaced(h))) return rc;
+  if (!h->opt_async_uploads) CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
@@ -177,11 +214,9 @@ int colate_set_genome(colate_handle* h, int slot, int64_t n_rec, const int64_t* 
   if ((rc = copy_in(g.aaf.p, aaf, n_rec * 4, location, h->stream))) return rc;
   if ((rc = copy_in(g.daf.p, daf, n_rec * 4, location, h->stream))) return rc;
   if ((rc = copy_in(g.alleles.p, alleles, n_rec * 2, location, h->stream))) return rc;
-  CK(cudaStreamSynchronize(h->stream));
   g.n_rec = n_rec;
-  g.set = true;
-  g.joined = false;
-  h->flags_done = false;
+  if ((rc = genome_replaced(h, slot))) return rc;
+  if (!h->opt_async_uploads) CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
@@ -197,7 +232,7 @@ int colate_set_mask(colate_handle* h, int slot, const uint32_t* pass_bits, int l
   CK(g.mask_bits.ensure(nw * 4 + 4));
   int rc;
   if ((rc = copy_in(g.mask_bits.p, pass_bits, nw * 4, location, h->stream))) return rc;
-  CK(cudaStreamSynchronize(h->stream));
+  if (!h->opt_async_uploads) CK(cudaStreamSynchronize(h->stream));
   g.has_mask = true;
   return 0;
 }
@@ -222,15 +257,23 @@ int colate_stage1_flags(colate_handle* h, int target_slot, int reference_slot, i
   h->h_chr_used.resize(h->n_chr);
   h->h_chr_blocks.resize(h->n_chr);
   int64_t misc[8];
-  CK(cudaMemcpyAsync(h->h_chr_used.data(), h->chr_used.p, h->n_chr * 8, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(h->h_chr_blocks.data(), h->chr_blocks.p, h->n_chr * 4, cudaMemcpyDeviceToHost, s));
+  int order[1 + COLATE_MAX_GENOMES];
+  if (h->n_chr > 0) {
+    CK(cudaMemcpyAsync(h->h_chr_used.data(), h->chr_used.p, h->n_chr * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->h_chr_blocks.data(), h->chr_blocks.p, h->n_chr * 4, cudaMemcpyDeviceToHost, s));
+  }
   CK(cudaMemcpyAsync(misc, h->misc.p, 64, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(order, h->order_flag.p, sizeof order, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  if (order[0]) return fail(COLATE_ERR_ORDER, "positions of a .mut file are not ascending (the reference's sequential reader needs sorted input)");
+  if (order[1 + target_slot] || order[1 + reference_slot])
+    return fail(COLATE_ERR_ORDER, "positions of a .colate.in file are not ascending within a chromosome");
   h->n_used = misc[0];
   h->n_blocks_local = (int)misc[1];
   h->tgt_slot = target_slot;
   h->ref_slot = reference_slot;
   h->flags_done = true;
+  h->sampled = false;
   if (n_used_chr) memcpy(n_used_chr, h->h_chr_used.data(), h->n_chr * 8);
   if (n_blocks_chr) memcpy(n_blocks_chr, h->h_chr_blocks.data(), h->n_chr * 4);
   float ms = 0;
@@ -260,9 +303,11 @@ int colate_stage1_sample(colate_handle* h, const uint32_t* mt_state, int64_t use
   if ((rc = run_sample(h, stream_local, block_base))) return rc;
   int64_t misc[8];
   CK(cudaMemcpyAsync(misc, h->misc.p, 64, cudaMemcpyDeviceToHost, s));
-  if (block_stats && nb > 0) CK(cudaMemcpyAsync(block_stats, h->out_f.p, (size_t)nb * 4 * NBINS * 8, cudaMemcpyDeviceToHost, s));
-  if (block_tallies && nb > 0) CK(cudaMemcpyAsync(block_tallies, h->out_n.p, (size_t)nb * 3 * NBINS * 8, cudaMemcpyDeviceToHost, s));
+  // (host or device destinations: unified addressing resolves the direction)
+  if (block_stats && nb > 0) CK(cudaMemcpyAsync(block_stats, h->out_f.p, (size_t)nb * 4 * NBINS * 8, cudaMemcpyDefault, s));
+  if (block_tallies && nb > 0) CK(cudaMemcpyAsync(block_tallies, h->out_n.p, (size_t)nb * 3 * NBINS * 8, cudaMemcpyDefault, s));
   CK(cudaStreamSynchronize(s));
+  h->sampled = true;
   if (misc[3]) return fail(COLATE_ERR_AGE_RANGE, "a used row has an age bin >= 185 (age_end beyond ~9.3e6 generations)");
   if (mt_state_out) {
     if ((rc = mt_window_after(h, win_after))) return rc;
@@ -297,6 +342,9 @@ int colate_set_option(colate_handle* h, const char* key, int64_t value)
 {
   if (!h || !key) return fail(COLATE_ERR_ARG, "null");
   if (!strcmp(key, "rejoin")) { h->opt_rejoin = value != 0; return 0; }
+  // async_uploads = 1: colate_set_sites / colate_set_genome / colate_set_mask queue their copies and return; the
+  // caller keeps the (pinned) host buffers unchanged until the next colate_stage1_flags() has returned
+  if (!strcmp(key, "async_uploads")) { h->opt_async_uploads = value != 0; return 0; }
   return fail(COLATE_ERR_ARG, std::string("unknown option ") + key);
 }
 
@@ -312,8 +360,10 @@ int colate_last_stage1_timing(colate_handle* h, colate_stage1_timing* out)
 int colate_stage2_bootstrap(colate_handle* h, int R, int num_blocks, const int32_t* block_weights,
                             const double* block_stats, double age, double* counts)
 {
-  if (!h || R <= 0 || num_blocks <= 0 || num_blocks > MAX_BLOCKS || !block_weights || !block_stats)
+  if (!h || R <= 0 || num_blocks <= 0 || num_blocks > MAX_BLOCKS || !block_weights)
     return fail(COLATE_ERR_ARG, "colate_stage2_bootstrap: bad arguments");
+  if (!block_stats && (!h->flags_done || !h->sampled || num_blocks != h->n_blocks_local))
+    return fail(COLATE_ERR_STATE, "colate_stage2_bootstrap: no device-resident block histograms of this size (run colate_stage1 first)");
   CK(cudaSetDevice(h->device));
   int rc = ensure_tables(h);
   if (rc) return rc;
@@ -324,10 +374,14 @@ int colate_stage2_bootstrap(colate_handle* h, int R, int num_blocks, const int32
   CK(h->d_weights.ensure((size_t)R * num_blocks * 4));
   CK(h->d_blockstats.ensure((size_t)num_blocks * 4 * NBINS * 8));
   CK(h->d_counts.ensure((size_t)R * 2 * NBINS * 8));
-  CK(cudaMemcpyAsync(h->d_weights.p, block_weights, (size_t)R * num_blocks * 4, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(h->d_blockstats.p, block_stats, (size_t)num_blocks * 4 * NBINS * 8, cudaMemcpyHostToDevice, s));
-  if ((rc = run_bootstrap(h, R, num_blocks, age))) return rc;
-  if (counts) CK(cudaMemcpyAsync(counts, h->d_counts.p, (size_t)R * 2 * NBINS * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h->d_weights.p, block_weights, (size_t)R * num_blocks * 4, cudaMemcpyDefault, s));
+  const double* blk = h->out_f.as<double>();   // NULL: what the last colate_stage1_sample left on the device (no bounce through the host)
+  if (block_stats) {
+    CK(cudaMemcpyAsync(h->d_blockstats.p, block_stats, (size_t)num_blocks * 4 * NBINS * 8, cudaMemcpyDefault, s));
+    blk = h->d_blockstats.as<double>();
+  }
+  if ((rc = run_bootstrap(h, R, num_blocks, blk, age))) return rc;
+  if (counts) CK(cudaMemcpyAsync(counts, h->d_counts.p, (size_t)R * 2 * NBINS * 8, cudaMemcpyDefault, s));
   CK(cudaStreamSynchronize(s));
   h->counts_R = R;
   return 0;
@@ -351,18 +405,18 @@ int colate_stage3_em(colate_handle* h, int R, int E, const double* epochs, const
   CK(cudaMemcpyAsync(h->d_rates.p, rates_init, (size_t)E * 8, cudaMemcpyHostToDevice, s));
   if (counts) {
     CK(h->d_counts.ensure((size_t)R * 2 * NBINS * 8));
-    CK(cudaMemcpyAsync(h->d_counts.p, counts, (size_t)R * 2 * NBINS * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_counts.p, counts, (size_t)R * 2 * NBINS * 8, cudaMemcpyDefault, s));
     h->counts_R = R;
   }
   if ((rc = run_em(h, R, E, max_iter))) return rc;
-  if (rates) CK(cudaMemcpyAsync(rates, h->d_rates.as<double>() + E, (size_t)R * E * 8, cudaMemcpyDeviceToHost, s));
+  if (rates) CK(cudaMemcpyAsync(rates, h->d_rates.as<double>() + E, (size_t)R * E * 8, cudaMemcpyDefault, s));
   std::vector<int32_t> it_host((size_t)R);
   CK(cudaMemcpyAsync(it_host.data(), h->d_iters.p, (size_t)R * 4, cudaMemcpyDeviceToHost, s));
-  if (final_ll) CK(cudaMemcpyAsync(final_ll, h->d_ll.p, (size_t)R * 8, cudaMemcpyDeviceToHost, s));
+  if (iters) CK(cudaMemcpyAsync(iters, h->d_iters.p, (size_t)R * 4, cudaMemcpyDefault, s));
+  if (final_ll) CK(cudaMemcpyAsync(final_ll, h->d_ll.p, (size_t)R * 8, cudaMemcpyDefault, s));
   CK(cudaStreamSynchronize(s));
   for (int r = 0; r < R; r++)
     if (it_host[r] < 0) return fail(COLATE_ERR_CUDA, "EM kernel: the cluster handshake timed out (replicate " + std::to_string(r) + ")");
-  if (iters) memcpy(iters, it_host.data(), (size_t)R * 4);
   return 0;
 }
 

@@ -57,6 +57,8 @@ struct Stage1Dims {
 struct colate_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // host -> device copies that run under the kernels of `stream`
+  cudaEvent_t copy_done = nullptr;
   cudaEvent_t ev[8] = {};
   // sites
   bool sites_set = false;
@@ -66,7 +68,7 @@ struct colate_handle {
   colate::DevBuf site_off, pos, ab, ae, meta;
   colate::GenomeDev genomes[COLATE_MAX_GENOMES];
   // stage-1 scratch
-  bool flags_done = false;
+  bool flags_done = false, sampled = false;
   int tgt_slot = -1, ref_slot = -1;
   colate::DevBuf candR, candT, use, word_rank, scan_tmp;
   colate::DevBuf chr_used, chr_blocks, chr_block_base, misc;  // misc: small device scalars
@@ -90,14 +92,16 @@ struct colate_handle {
   int libm_exact = -1;  // host libm == glibc_math.cuh port on the self-check sample (1/0), -1 unknown
   int counts_R = 0;
   int64_t launches = 0;
-  bool opt_rejoin = false;
+  bool opt_rejoin = false, opt_async_uploads = false;
   // GPU-side .mut ingest (kernels_ingest.cu)
   bool ing_active = false;
   int ing_nchr = 0;
-  int64_t ing_cap = 0, ing_fallback_rows = 0;
+  int64_t ing_cap = 0, ing_fallback_rows = 0, ing_genome_fallbacks = 0;
   double ing_ms = 0.0;
   std::vector<int64_t> ing_off;
-  colate::DevBuf ing_text, ing_tile_cnt, ing_tile_off, ing_nl, ing_status, ing_fb;
+  colate::DevBuf ing_text, ing_tile_cnt, ing_tile_off, ing_nl, ing_status, ing_fb, ing_raw;
+  colate::DevBuf order_flag;   // device int[4]: unsorted input seen by the order checks (COLATE_ERR_ORDER)
+  std::vector<cudaEvent_t> ing_evs;               // one per chromosome text in flight on the copy stream
   void* ing_bounce[2] = {nullptr, nullptr};       // pinned staging for pageable callers
   cudaEvent_t ing_bounce_ev[2] = {nullptr, nullptr};
 };
@@ -106,6 +110,11 @@ namespace colate {
 // kernels_sites.cu
 int run_join(colate_handle* h, int slot);
 int run_flags(colate_handle* h, int tslot, int rslot);
+int run_check_sites(colate_handle* h);
+int run_check_genome(colate_handle* h, int slot);
+// abi.cu
+int sites_replaced_ext(colate_handle* h);
+int genome_replaced_ext(colate_handle* h, int slot);
 int run_sample(colate_handle* h, const uint32_t* stream_local, int block_base_unused);
 int run_test_bin_fast(colate_handle* h, int n, const double* a_host, int32_t* fast_host, int32_t* exact_host);
 int run_test_bin_sweep(colate_handle* h, uint32_t lo_bits, uint32_t hi_bits, uint64_t* out3_host);
@@ -115,7 +124,7 @@ int run_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int
                   bool tiled /* lay the words out in k_sample's tile order (internal.h: stream_phys) */);
 int mt_window_after(colate_handle* h, uint32_t* window_after);
 // kernels_em.cu
-int run_bootstrap(colate_handle* h, int R, int num_blocks, double age);
+int run_bootstrap(colate_handle* h, int R, int num_blocks, const double* block_stats_dev, double age);
 int run_em(colate_handle* h, int R, int E, int max_iter);
 int run_estep(colate_handle* h, int shared, int E, int n_t);
 int run_libm(colate_handle* h, int which, int n, const double* x_host, double* y_host);

@@ -6,6 +6,7 @@
 
 #include <zlib.h>
 
+#include <algorithm>
 #include <cmath>
 #include <climits>
 #include <cstdio>
@@ -114,6 +115,120 @@ static bool slurp_or_gz(const std::string& path, std::vector<char>& buf)
   FILE* probe = fopen(path.c_str(), "rb");
   if (probe) { fclose(probe); return slurp(path, buf); }
   return slurp(path + ".gz", buf);
+}
+
+
+// ---- .colate.in images in memory -------------------------------------------------------------
+// Sequential decode of a record stream {i32 lchrom, chrom, i32 bp, anc, der, i32 AAF, i32 DAF} (coal.cpp:2505-2514),
+// the way the reference freads it (coal.cpp:2126-2133): a truncated last record ends the stream.
+// bp == nullptr: count only.
+int64_t decode_colate_in_host(const char* buf, int64_t sz, const std::vector<std::string>& names, int64_t cap,
+                              int32_t* rec_chrom, int32_t* bp, int32_t* aaf, int32_t* daf, uint16_t* alleles)
+{
+  const int n_chr = (int)names.size();
+  int64_t n = 0;
+  size_t o = 0;
+  int last_id = -1;
+  std::string last_name;
+  while (o + 4 <= (size_t)sz) {
+    int32_t l;
+    memcpy(&l, buf + o, 4);
+    if (l < 0 || l >= 1024 || o + 4 + (size_t)l + 14 > (size_t)sz) break;  // truncated tail
+    if (bp) {
+      if (n >= cap) return fail(COLATE_ERR_ARG, "colate_read_colate_in: capacity too small");
+      const char* nm = buf + o + 4;
+      int id;
+      if (last_id >= 0 && last_name.size() == (size_t)l && memcmp(last_name.data(), nm, l) == 0) id = last_id;
+      else {
+        id = n_chr;
+        for (int c = 0; c < n_chr; c++)
+          if (names[c].size() == (size_t)l && memcmp(names[c].data(), nm, l) == 0) { id = c; break; }
+        last_id = id;
+        last_name.assign(nm, l);
+      }
+      const char* r = nm + l;
+      rec_chrom[n] = id;
+      memcpy(&bp[n], r, 4);
+      alleles[n] = (uint16_t)((unsigned char)r[4] | ((unsigned char)r[5] << 8));
+      memcpy(&aaf[n], r + 6, 4);
+      memcpy(&daf[n], r + 10, 4);
+    }
+    n++;
+    o += 4 + (size_t)l + 14;
+  }
+  return n;
+}
+
+// Run structure of an image WITHOUT walking it record by record: a run = consecutive records with the same
+// {lchrom, chrom} header, hence the same width.  From a record at a known boundary the run's end is located by
+// galloping + bisection over "does the header at boundary + j * width equal this run's header".  The probes only
+// look at O(log n) records per run, so the result is a HYPOTHESIS: it is exactly the sequential reader's
+// segmentation iff every record inside every run carries its run's header (by induction each record then starts
+// where the previous one ends) -- which the device decoder checks for all records in parallel (k_decode_colate_in);
+// if the check fails the caller falls back to decode_colate_in_host.
+int64_t colate_in_runs(const char* buf, int64_t sz, const std::vector<std::string>& names, std::vector<ColateInRun>& runs)
+{
+  const int n_chr = (int)names.size();
+  runs.clear();
+  int64_t o = 0, n = 0;
+  while (o + 4 <= sz) {
+    int32_t l;
+    memcpy(&l, buf + o, 4);
+    if (l < 0 || l >= 1024 || o + 4 + (int64_t)l + 14 > sz) break;  // truncated tail
+    const int64_t w = 18 + (int64_t)l;
+    const int hl = 4 + l;
+    const int64_t bound = (sz - o) / w;                             // complete records of this width that fit
+    auto same = [&](int64_t j) { return memcmp(buf + o + j * w, buf + o, hl) == 0; };
+    int64_t good = 0, badj = bound;                                 // header(good) matches; badj: first known mismatch (or the bound)
+    for (int64_t j = 1; j < bound; j *= 2) {
+      if (same(j)) good = j; else { badj = j; break; }
+    }
+    while (badj - good > 1) {
+      const int64_t mid = good + (badj - good) / 2;
+      if (same(mid)) good = mid; else badj = mid;
+    }
+    int id = n_chr;
+    for (int c = 0; c < n_chr; c++)
+      if (names[c].size() == (size_t)l && memcmp(names[c].data(), buf + o + 4, l) == 0) { id = c; break; }
+    runs.push_back(ColateInRun{o, (int32_t)w, id, good + 1, n});
+    n += good + 1;
+    o += (good + 1) * w;
+  }
+  return n;
+}
+
+// colate_chr_ranges() on the run-length form
+void chr_ranges_runs(int n_chr, const std::vector<ColateInRun>& runs, int64_t* chr_first, int64_t* chr_end)
+{
+  const int64_t n_rec = runs.empty() ? 0 : runs.back().rec_base + runs.back().n_rec;
+  auto chrom_of = [&](int64_t k) {   // run index holding record k
+    size_t lo = 0, hi = runs.size();
+    while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (runs[mid].rec_base <= k) lo = mid; else hi = mid; }
+    return lo;
+  };
+  int64_t cur = -1, next = 0;
+  for (int c = 0; c < n_chr; c++) {
+    bool have = cur >= 0 && runs[chrom_of(cur)].chr_id == c;
+    if (!have) {
+      // the reader advances record by record until it holds one of chromosome c (or hits the end of the file)
+      size_t r = next < n_rec ? chrom_of(next) : runs.size();
+      while (r < runs.size() && runs[r].chr_id != c) r++;
+      if (r < runs.size()) { cur = std::max(next, runs[r].rec_base); next = cur + 1; have = true; }
+      else if (n_rec > 0) { cur = n_rec - 1; next = n_rec; }          // fread failed: it keeps its last record
+    }
+    if (have) {
+      size_t r = chrom_of(cur);
+      int64_t e = runs[r].rec_base + runs[r].n_rec;
+      while (r + 1 < runs.size() && runs[r + 1].chr_id == c) { r++; e = runs[r].rec_base + runs[r].n_rec; }
+      chr_first[c] = cur;
+      chr_end[c] = e;
+      cur = e - 1;
+      next = e;
+    } else {
+      chr_first[c] = -1;
+      chr_end[c] = -1;
+    }
+  }
 }
 
 // one data line of a .mut file, [p, nl) with *nl == '\n' (mutations.cpp:70-250; the columns the path uses)
@@ -350,37 +465,7 @@ int64_t colate_read_colate_in(const char* path, int n_chr, const char* const* ch
   if (sz > 0 && fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); return fail(COLATE_ERR_IO, "short read"); }
   fclose(f);
   std::vector<std::string> names(chr_names, chr_names + n_chr);
-  int64_t n = 0;
-  size_t o = 0;
-  int last_id = -1;
-  std::string last_name;
-  while (o + 4 <= (size_t)sz) {
-    int32_t l;
-    memcpy(&l, buf.data() + o, 4);
-    if (l < 0 || l >= 1024 || o + 4 + (size_t)l + 14 > (size_t)sz) break;  // truncated tail
-    if (bp) {
-      if (n >= cap) return fail(COLATE_ERR_ARG, "colate_read_colate_in: capacity too small");
-      const char* nm = buf.data() + o + 4;
-      int id;
-      if (last_id >= 0 && last_name.size() == (size_t)l && memcmp(last_name.data(), nm, l) == 0) id = last_id;
-      else {
-        id = n_chr;
-        for (int c = 0; c < n_chr; c++)
-          if (names[c].size() == (size_t)l && memcmp(names[c].data(), nm, l) == 0) { id = c; break; }
-        last_id = id;
-        last_name.assign(nm, l);
-      }
-      const char* r = nm + l;
-      rec_chrom[n] = id;
-      memcpy(&bp[n], r, 4);
-      alleles[n] = (uint16_t)((unsigned char)r[4] | ((unsigned char)r[5] << 8));
-      memcpy(&aaf[n], r + 6, 4);
-      memcpy(&daf[n], r + 10, 4);
-    }
-    n++;
-    o += 4 + (size_t)l + 14;
-  }
-  return n;
+  return colate::decode_colate_in_host(buf.data(), sz, names, cap, rec_chrom, bp, aaf, daf, alleles);
 }
 
 int colate_mask_bits_from_fasta(const char* path, int64_t n, const int32_t* pos, int64_t row0, uint32_t* pass_bits)
@@ -456,3 +541,17 @@ int colate_write_bin(const char* path, int R, int E, const double* epochs, const
 }
 
 }  // extern "C"
+
+extern "C" int64_t colate_test_colate_in_runs(const char* buf, int64_t sz, int n_chr, const char* const* chr_names, int cap_runs,
+                                              int64_t* runs4, int64_t* chr_first, int64_t* chr_end)
+{
+  std::vector<std::string> names(chr_names, chr_names + n_chr);
+  std::vector<colate::ColateInRun> runs;
+  const int64_t n = colate::colate_in_runs(buf, sz, names, runs);
+  if ((int)runs.size() > cap_runs) return -1;
+  for (size_t i = 0; i < runs.size(); i++) {
+    runs4[4 * i] = runs[i].byte_off; runs4[4 * i + 1] = runs[i].width; runs4[4 * i + 2] = runs[i].chr_id; runs4[4 * i + 3] = runs[i].n_rec;
+  }
+  colate::chr_ranges_runs(n_chr, runs, chr_first, chr_end);
+  return n | ((int64_t)runs.size() << 40);
+}

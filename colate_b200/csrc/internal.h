@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <cstddef>
 #include <string>
+#include <vector>
 
 #include "../../include/colate_b200.h"
 
@@ -72,6 +73,11 @@ bool bin_thresholds(double* thr10 /*[NTHR]*/);
 // lut[cell] = slot_of_bin(bin at the lower edge of the cell) | 0x8000 if a threshold lies inside the cell
 bool age_thresholds(double* thrA /*[NBINS+2]*/, double* thrP /*[192]*/, uint16_t* lut /*[LUT_N]*/);
 int bin_of_x10_host(double x10);
+struct ColateInRun { int64_t byte_off; int32_t width; int32_t chr_id; int64_t n_rec; int64_t rec_base; };
+int64_t decode_colate_in_host(const char* buf, int64_t sz, const std::vector<std::string>& names, int64_t cap,
+                              int32_t* rec_chrom, int32_t* bp, int32_t* aaf, int32_t* daf, uint16_t* alleles);
+int64_t colate_in_runs(const char* buf, int64_t sz, const std::vector<std::string>& names, std::vector<ColateInRun>& runs);
+void chr_ranges_runs(int n_chr, const std::vector<ColateInRun>& runs, int64_t* chr_first, int64_t* chr_end);
 bool parse_mut_line_host(const char* p, const char* nl, int32_t* pos, float* age_begin, float* age_end, uint32_t* meta);
 
 }  // namespace colate
@@ -83,6 +89,9 @@ int colate_test_jump_window_host(const uint32_t* w, int q, uint32_t* out);
 int colate_test_bin_thresholds(double* thr10);
 double colate_test_add_repeated(double acc, double w, int c);
 int64_t colate_test_stream_phys(int64_t o, int64_t off);
+// host run finder of .colate.in images: runs[n][4] = {byte_off, width, chr_id, n_rec}; chr ranges from the runs
+int64_t colate_test_colate_in_runs(const char* buf, int64_t sz, int n_chr, const char* const* chr_names, int cap_runs,
+                                   int64_t* runs4, int64_t* chr_first, int64_t* chr_end);
 int colate_test_libm(colate_handle* h, int which, int n, const double* x, double* y);
 int colate_test_bin_fast(colate_handle* h, int n, const double* ages, int32_t* fast, int32_t* exact);
 int colate_test_bin_sweep(colate_handle* h, uint32_t lo_bits, uint32_t hi_bits, uint64_t* out3);

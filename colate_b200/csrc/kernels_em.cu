@@ -933,9 +933,9 @@ int ensure_libm_tables(colate_handle* h)
   return 0;
 }
 
-int run_bootstrap(colate_handle* h, int R, int num_blocks, double age)
+int run_bootstrap(colate_handle* h, int R, int num_blocks, const double* block_stats_dev, double age)
 {
-  k_bootstrap<<<R, 256, 0, h->stream>>>(num_blocks, h->d_weights.as<int32_t>(), h->d_blockstats.as<double>(), age,
+  k_bootstrap<<<R, 256, 0, h->stream>>>(num_blocks, h->d_weights.as<int32_t>(), block_stats_dev, age,
                                         h->d_agebin.as<double>(), h->d_counts.as<double>());
   h->launches += 1;
   CK(cudaGetLastError());
@@ -949,11 +949,12 @@ int run_em(colate_handle* h, int R, int E, int max_iter)
   int csize = 1;
   if (const char* e = getenv("COLATE_EM_CLUSTER")) csize = atoi(e);
   else {
-    while (csize < 8 && R * csize * 2 <= 148) csize *= 2;
-    if (csize == 8 && R * 16 * 2 <= 148) csize = 16;   // non-portable cluster size: one GPC (16-20 SMs) per replicate
+    const int sms = h->sm_count;
+    while (csize < 8 && R * csize * 2 <= sms) csize *= 2;
+    if (csize == 8 && R * 16 * 2 <= sms) csize = 16;   // non-portable cluster size: one GPC (16-20 SMs) per replicate
     // 19..37 replicates: clusters of 8 on k_em_split (two CTAs per SM) beat k_em's clusters of 4 (measured at R = 30:
     // 59 ms against 73.5 ms, and 80 ms at one CTA per replicate; profiles/r01_em_phase_profile.md)
-    if (csize == 4 && R * 8 <= 2 * 148) csize = 8;
+    if (csize == 4 && R * 8 <= 2 * sms) csize = 8;
     if (csize == 2) csize = 1;                         // 38..74 replicates: pairs of CTAs are slower than single CTAs (R = 60: 66.4 against 61.3 ms)
   }
   if (csize != 1 && csize != 2 && csize != 4 && csize != 8 && csize != 16) csize = 1;

@@ -225,6 +225,52 @@ k_parse_mut(const char* __restrict__ text, int64_t n_bytes, const int64_t* __res
   }
 }
 
+// ---- .colate.in records (coal.cpp:2505-2514) decoded on the device ----------------------------------
+// The host has cut the image into runs of equal-width records by galloping (host_misc.cpp: colate_in_runs);
+// thread = record: locate its run, CHECK that its {lchrom, chrom} header equals the run's (all records passing
+// this check is what makes the host's segmentation the sequential reader's, see colate_in_runs) and split the
+// 14 payload bytes into the genome's structure of arrays.  Records sit at arbitrary byte offsets: byte loads.
+struct DevRun { long long byte_off; int width; int chr_id; long long n_rec; long long rec_base; };
+
+__device__ __forceinline__ uint32_t ld_u32_unaligned(const unsigned char* p)
+{
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+__global__ void __launch_bounds__(256)
+k_decode_colate_in(const unsigned char* __restrict__ img, const DevRun* __restrict__ runs, int n_runs, int64_t n_rec,
+                   int32_t* __restrict__ bp, int32_t* __restrict__ aaf, int32_t* __restrict__ daf, uint16_t* __restrict__ alleles,
+                   int* __restrict__ bad)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_rec) return;
+  int lo = 0, hi = n_runs;                      // last run with rec_base <= k
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (runs[mid].rec_base <= k) lo = mid; else hi = mid; }
+  const DevRun r = runs[lo];
+  const unsigned char* first = img + r.byte_off;
+  const unsigned char* rec = first + (k - r.rec_base) * r.width;
+  const int hl = r.width - 14;                  // 4 + lchrom
+  bool same = true;
+  for (int i = 0; i < hl; i++) same &= rec[i] == first[i];
+  if (!same) *bad = 1;
+  const unsigned char* q = rec + hl;
+  bp[k] = (int32_t)ld_u32_unaligned(q);
+  alleles[k] = (uint16_t)(q[4] | (q[5] << 8));
+  aaf[k] = (int32_t)ld_u32_unaligned(q + 6);
+  daf[k] = (int32_t)ld_u32_unaligned(q + 10);
+}
+
+// rows re-parsed on the host (strtof) -> their places in the site arrays
+__global__ void k_patch_rows(int64_t n, const int64_t* __restrict__ idx, const int32_t* __restrict__ ps, const float* __restrict__ a,
+                             const float* __restrict__ e, const uint32_t* __restrict__ m, int32_t* __restrict__ pos,
+                             float* __restrict__ ab, float* __restrict__ ae, uint32_t* __restrict__ meta)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t r = idx[i];
+  pos[r] = ps[i]; ab[r] = a[i]; ae[r] = e[i]; meta[r] = m[i];
+}
+
 }  // namespace colate
 
 using namespace colate;
@@ -249,43 +295,19 @@ int colate_ingest_begin(colate_handle* h, int n_chr, int64_t row_capacity)
   h->ing_nchr = n_chr;
   h->ing_off.assign(1, 0);
   h->ing_ms = 0.0;
+  h->ing_fallback_rows = 0;
   return 0;
 }
 
-int64_t colate_ingest_mut_text(colate_handle* h, const char* text, int64_t n_bytes, int location)
+// One .mut text already on its way to the device (d_text, ordered before h->stream's next work): line index,
+// one thread per row, host re-parse of the rows the device flags.  host_text: the same bytes on the host (or
+// nullptr: fetched back from the device if a row needs the host).  Returns the data rows.
+static int64_t ingest_one(colate_handle* h, const char* d_text, int64_t n_bytes, const char* host_text)
 {
-  if (!h || !text || n_bytes < 0) return fail(COLATE_ERR_ARG, "colate_ingest_mut_text: bad arguments");
-  if (!h->ing_active) return fail(COLATE_ERR_STATE, "colate_ingest_mut_text: call colate_ingest_begin first");
-  if ((int)h->ing_off.size() > h->ing_nchr) return fail(COLATE_ERR_STATE, "colate_ingest_mut_text: more chromosomes than announced");
-  CK(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
   const int64_t row0 = h->ing_off.back();
-  if (n_bytes == 0) { h->ing_off.push_back(row0); return 0; }
-  const char* d_text = text;
-  if (!location) {
-    CK(h->ing_text.ensure((size_t)n_bytes + 64));
-    d_text = h->ing_text.as<char>();
-    cudaPointerAttributes attr;
-    const bool pinned = cudaPointerGetAttributes(&attr, text) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-    cudaGetLastError();
-    if (pinned) {
-      CK(cudaMemcpyAsync(h->ing_text.p, text, (size_t)n_bytes, cudaMemcpyHostToDevice, s));
-    } else {
-      // pageable caller memory: stage through two pinned bounce buffers so the copies run at PCIe speed
-      // while the host fills the other buffer
-      const size_t CH = (size_t)32 << 20;
-      for (int k = 0; k < 2; k++)
-        if (!h->ing_bounce[k]) { CK(cudaHostAlloc(&h->ing_bounce[k], CH, cudaHostAllocDefault)); CK(cudaEventCreateWithFlags(&h->ing_bounce_ev[k], cudaEventDisableTiming)); }
-      int k = 0;
-      for (size_t o = 0; o < (size_t)n_bytes; o += CH, k ^= 1) {
-        const size_t m = std::min(CH, (size_t)n_bytes - o);
-        CK(cudaEventSynchronize(h->ing_bounce_ev[k]));
-        memcpy(h->ing_bounce[k], text + o, m);
-        CK(cudaMemcpyAsync(h->ing_text.as<char>() + o, h->ing_bounce[k], m, cudaMemcpyHostToDevice, s));
-        CK(cudaEventRecord(h->ing_bounce_ev[k], s));
-      }
-    }
-  }
+  const char* text = host_text;
+  const int location = host_text ? 0 : 1;
   const int64_t n_tiles = (n_bytes + ING_TILE - 1) / ING_TILE;
   CK(h->ing_tile_cnt.ensure(n_tiles * 4)); CK(h->ing_tile_off.ensure((n_tiles + 1) * 8)); CK(h->ing_status.ensure(64));
   CK(cudaEventRecord(h->ev[0], s));
@@ -330,6 +352,10 @@ int64_t colate_ingest_mut_text(colate_handle* h, const char* text, int64_t n_byt
       const char* ht = text;
       if (location) { htext.resize(n_bytes); CK(cudaMemcpy(htext.data(), d_text, n_bytes, cudaMemcpyDeviceToHost)); ht = htext.data(); }
       CK(cudaMemcpy(nlp.data(), h->ing_nl.p, n_nl * 8, cudaMemcpyDeviceToHost));
+      // re-parsed rows are collected and scattered by one small kernel on the handle's stream (ordered against the
+      // parse kernel before it and every consumer after it)
+      std::vector<int64_t> pidx; std::vector<int32_t> ppos; std::vector<float> pab, pae; std::vector<uint32_t> pmeta;
+      pidx.reserve(rows.size()); ppos.reserve(rows.size()); pab.reserve(rows.size()); pae.reserve(rows.size()); pmeta.reserve(rows.size());
       for (int64_t r : rows) {
         const char* p = ht + nlp[r] + 1;
         const char* nl = ht + (r + 1 < n_nl ? nlp[r + 1] : n_bytes);
@@ -338,16 +364,127 @@ int64_t colate_ingest_mut_text(colate_handle* h, const char* text, int64_t n_byt
         int32_t ps; float a, e; uint32_t m;
         if (!parse_mut_line_host(line.data(), line.data() + line.size() - 1, &ps, &a, &e, &m))
           return fail(COLATE_ERR_IO, "Error reading following line in mut file: " + std::string(p, nl));
-        CK(cudaMemcpy(h->pos.as<int32_t>() + row0 + r, &ps, 4, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(h->ab.as<float>() + row0 + r, &a, 4, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(h->ae.as<float>() + row0 + r, &e, 4, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(h->meta.as<uint32_t>() + row0 + r, &m, 4, cudaMemcpyHostToDevice));
+        pidx.push_back(row0 + r); ppos.push_back(ps); pab.push_back(a); pae.push_back(e); pmeta.push_back(m);
       }
+      const size_t np = pidx.size();
+      CK(h->d_tmp.ensure(np * 24 + 64));
+      char* base = h->d_tmp.as<char>();
+      int64_t* d_idx = (int64_t*)base;
+      int32_t* d_pos = (int32_t*)(base + np * 8);
+      float* d_ab = (float*)(base + np * 12);
+      float* d_ae = (float*)(base + np * 16);
+      uint32_t* d_meta = (uint32_t*)(base + np * 20);
+      CK(cudaMemcpyAsync(d_idx, pidx.data(), np * 8, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(d_pos, ppos.data(), np * 4, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(d_ab, pab.data(), np * 4, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(d_ae, pae.data(), np * 4, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(d_meta, pmeta.data(), np * 4, cudaMemcpyHostToDevice, s));
+      k_patch_rows<<<(unsigned)((np + 255) / 256), 256, 0, s>>>((int64_t)np, d_idx, d_pos, d_ab, d_ae, d_meta, h->pos.as<int32_t>(),
+                                                                h->ab.as<float>(), h->ae.as<float>(), h->meta.as<uint32_t>());
+      h->launches += 1;
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(s));   // the host vectors are locals
     }
     h->ing_fallback_rows += nfb;
   }
   h->ing_off.push_back(row0 + n_rows);
   return n_rows;
+}
+
+
+int64_t colate_ingest_mut_text(colate_handle* h, const char* text, int64_t n_bytes, int location)
+{
+  if (!h || !text || n_bytes < 0) return fail(COLATE_ERR_ARG, "colate_ingest_mut_text: bad arguments");
+  if (!h->ing_active) return fail(COLATE_ERR_STATE, "colate_ingest_mut_text: call colate_ingest_begin first");
+  if ((int)h->ing_off.size() > h->ing_nchr) return fail(COLATE_ERR_STATE, "colate_ingest_mut_text: more chromosomes than announced");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int64_t row0 = h->ing_off.back();
+  if (n_bytes == 0) { h->ing_off.push_back(row0); return 0; }
+  const char* d_text = text;
+  if (!location) {
+    CK(h->ing_text.ensure((size_t)n_bytes + 64));
+    d_text = h->ing_text.as<char>();
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, text) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+      CK(cudaMemcpyAsync(h->ing_text.p, text, (size_t)n_bytes, cudaMemcpyHostToDevice, s));
+    } else {
+      // pageable caller memory: stage through two pinned bounce buffers so the copies run at PCIe speed
+      // while the host fills the other buffer
+      const size_t CH = (size_t)32 << 20;
+      for (int k = 0; k < 2; k++)
+        if (!h->ing_bounce[k]) { CK(cudaHostAlloc(&h->ing_bounce[k], CH, cudaHostAllocDefault)); CK(cudaEventCreateWithFlags(&h->ing_bounce_ev[k], cudaEventDisableTiming)); }
+      int k = 0;
+      for (size_t o = 0; o < (size_t)n_bytes; o += CH, k ^= 1) {
+        const size_t m = std::min(CH, (size_t)n_bytes - o);
+        CK(cudaEventSynchronize(h->ing_bounce_ev[k]));
+        memcpy(h->ing_bounce[k], text + o, m);
+        CK(cudaMemcpyAsync(h->ing_text.as<char>() + o, h->ing_bounce[k], m, cudaMemcpyHostToDevice, s));
+        CK(cudaEventRecord(h->ing_bounce_ev[k], s));
+      }
+    }
+  }
+  return ingest_one(h, d_text, n_bytes, location ? nullptr : text);
+}
+
+// All chromosomes of a job in one call (texts[c] / n_bytes[c] in --chr order, pinned host memory or device memory):
+// every text is copied on the handle's copy stream, and chromosome c is parsed on the compute stream as soon as
+// its bytes have landed -- the parse kernels and the host's per-chromosome bookkeeping run under the copies of the
+// following chromosomes.  rows_out[c] = data rows of chromosome c.  Equivalent to n calls of colate_ingest_mut_text.
+int colate_ingest_mut_texts(colate_handle* h, int n_texts, const char* const* texts, const int64_t* n_bytes, int location,
+                            int64_t* rows_out)
+{
+  if (!h || n_texts < 0 || (n_texts > 0 && (!texts || !n_bytes))) return fail(COLATE_ERR_ARG, "colate_ingest_mut_texts: bad arguments");
+  if (!h->ing_active) return fail(COLATE_ERR_STATE, "colate_ingest_mut_texts: call colate_ingest_begin first");
+  if ((int)h->ing_off.size() - 1 + n_texts > h->ing_nchr) return fail(COLATE_ERR_STATE, "colate_ingest_mut_texts: more chromosomes than announced");
+  CK(cudaSetDevice(h->device));
+  bool direct = location != 0;
+  if (!direct) {   // pinned host memory copies asynchronously; anything else takes the bounce path text by text
+    direct = true;
+    for (int c = 0; c < n_texts && direct; c++) {
+      if (n_bytes[c] <= 0) continue;
+      cudaPointerAttributes attr;
+      direct = cudaPointerGetAttributes(&attr, texts[c]) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+      cudaGetLastError();
+    }
+  }
+  if (!direct || location != 0) {
+    for (int c = 0; c < n_texts; c++) {
+      const int64_t n = colate_ingest_mut_text(h, texts[c], n_bytes[c], location);
+      if (n < 0) return (int)n;
+      if (rows_out) rows_out[c] = n;
+    }
+    return 0;
+  }
+  std::vector<size_t> off(n_texts + 1, 0);
+  for (int c = 0; c < n_texts; c++) {
+    if (n_bytes[c] < 0 || (n_bytes[c] > 0 && !texts[c])) return fail(COLATE_ERR_ARG, "colate_ingest_mut_texts: bad text");
+    off[c + 1] = off[c] + (((size_t)n_bytes[c] + 255) & ~(size_t)255);
+  }
+  CK(cudaStreamSynchronize(h->stream));                       // nothing may still read the text buffer this call replaces
+  CK(h->ing_text.ensure(off[n_texts] + 64));
+  while ((int)h->ing_evs.size() < n_texts) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->ing_evs.push_back(e);
+  }
+  for (int c = 0; c < n_texts; c++) {
+    if (n_bytes[c] > 0) CK(cudaMemcpyAsync(h->ing_text.as<char>() + off[c], texts[c], (size_t)n_bytes[c], cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaEventRecord(h->ing_evs[c], h->copy_stream));
+  }
+  for (int c = 0; c < n_texts; c++) {
+    int64_t n = 0;
+    if (n_bytes[c] == 0) h->ing_off.push_back(h->ing_off.back());
+    else {
+      CK(cudaStreamWaitEvent(h->stream, h->ing_evs[c], 0));
+      n = ingest_one(h, h->ing_text.as<char>() + off[c], n_bytes[c], texts[c]);
+      if (n < 0) { cudaStreamSynchronize(h->copy_stream); return (int)n; }
+    }
+    if (rows_out) rows_out[c] = n;
+  }
+  return 0;
 }
 
 int colate_ingest_end(colate_handle* h)
@@ -362,11 +499,8 @@ int colate_ingest_end(colate_handle* h)
   h->n_chr = h->ing_nchr;
   h->n_site = h->ing_off.back();
   h->h_site_off = h->ing_off;
-  h->sites_set = true;
-  h->flags_done = false;
   h->ing_active = false;
-  for (auto& g : h->genomes) { g.joined = false; g.has_mask = false; }
-  return 0;
+  return sites_replaced_ext(h);
 }
 
 int colate_ingest_fetch(colate_handle* h, int64_t row0, int64_t n_rows, int32_t* pos, float* age_begin, float* age_end, uint32_t* meta)
@@ -388,6 +522,82 @@ int colate_ingest_stats(colate_handle* h, double* kernel_ms, int64_t* host_fallb
   if (kernel_ms) *kernel_ms = h->ing_ms;
   if (host_fallback_rows) *host_fallback_rows = h->ing_fallback_rows;
   return 0;
+}
+
+// .colate.in image -> genome slot, decoded on the device (replaces colate_read_colate_in + colate_chr_ranges +
+// colate_set_genome; reader being replaced: coal.cpp:2126-2133, 2185-2192, 2205-2212).
+int64_t colate_ingest_colate_in(colate_handle* h, int slot, const char* bytes, int64_t n_bytes, int n_chr,
+                                const char* const* chr_names, int location)
+{
+  if (!h || slot < 0 || slot >= COLATE_MAX_GENOMES || n_bytes < 0 || (n_bytes > 0 && !bytes) || n_chr < 0 || (n_chr > 0 && !chr_names))
+    return fail(COLATE_ERR_ARG, "colate_ingest_colate_in: bad arguments");
+  if (!h->sites_set) return fail(COLATE_ERR_STATE, "colate_ingest_colate_in: call colate_set_sites / colate_ingest_end first");
+  if (n_chr != h->n_chr) return fail(COLATE_ERR_ARG, "colate_ingest_colate_in: n_chr differs from the site set's");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  std::vector<std::string> names(chr_names, chr_names + n_chr);
+  std::vector<char> pulled;
+  const char* host = bytes;
+  if (location) {   // the run finder probes the image on the host
+    pulled.resize((size_t)n_bytes);
+    if (n_bytes) CK(cudaMemcpy(pulled.data(), bytes, (size_t)n_bytes, cudaMemcpyDeviceToHost));
+    host = pulled.data();
+  }
+  GenomeDev& g = h->genomes[slot];
+  const unsigned char* d_img = (const unsigned char*)bytes;
+  if (!location && n_bytes > 0) {
+    CK(h->ing_raw.ensure((size_t)n_bytes + 64));
+    CK(cudaMemcpyAsync(h->ing_raw.p, bytes, (size_t)n_bytes, cudaMemcpyHostToDevice, s));   // under way while the host finds the runs
+    d_img = h->ing_raw.as<unsigned char>();
+  }
+  std::vector<ColateInRun> runs;
+  int64_t n_rec = colate_in_runs(host, n_bytes, names, runs);
+  CK(g.bp.ensure(n_rec * 4 + 4)); CK(g.aaf.ensure(n_rec * 4 + 4)); CK(g.daf.ensure(n_rec * 4 + 4)); CK(g.alleles.ensure(n_rec * 2 + 4));
+  CK(g.chr_first.ensure(n_chr * 8 + 8)); CK(g.chr_end.ensure(n_chr * 8 + 8));
+  bool device_ok = true;
+  if (n_rec > 0) {
+    static_assert(sizeof(DevRun) == sizeof(ColateInRun), "run records are copied as they are");
+    CK(h->d_tmp.ensure(runs.size() * sizeof(DevRun) + 64));
+    int* d_bad = (int*)(h->d_tmp.as<char>() + runs.size() * sizeof(DevRun));
+    CK(cudaMemcpyAsync(h->d_tmp.p, runs.data(), runs.size() * sizeof(DevRun), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(d_bad, 0, 4, s));
+    k_decode_colate_in<<<(unsigned)((n_rec + 255) / 256), 256, 0, s>>>(d_img, h->d_tmp.as<DevRun>(), (int)runs.size(), n_rec,
+                                                                       g.bp.as<int32_t>(), g.aaf.as<int32_t>(), g.daf.as<int32_t>(),
+                                                                       g.alleles.as<uint16_t>(), d_bad);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    device_ok = bad == 0;
+  }
+  std::vector<int64_t> first(n_chr + 1), end(n_chr + 1);
+  if (device_ok) {
+    chr_ranges_runs(n_chr, runs, first.data(), end.data());
+  } else {
+    // a record inside a run carries another header: interleaved chromosomes or mixed name lengths.  The
+    // sequential decode is the definition; take it.
+    const int64_t cap = n_bytes / 18 + 1;
+    std::vector<int32_t> rc(cap), bp(cap), aaf(cap), daf(cap);
+    std::vector<uint16_t> al(cap);
+    n_rec = decode_colate_in_host(host, n_bytes, names, cap, rc.data(), bp.data(), aaf.data(), daf.data(), al.data());
+    if (n_rec < 0) return n_rec;
+    colate_chr_ranges(n_chr, n_rec, rc.data(), first.data(), end.data());
+    CK(g.bp.ensure(n_rec * 4 + 4)); CK(g.aaf.ensure(n_rec * 4 + 4)); CK(g.daf.ensure(n_rec * 4 + 4)); CK(g.alleles.ensure(n_rec * 2 + 4));
+    CK(cudaMemcpyAsync(g.bp.p, bp.data(), n_rec * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(g.aaf.p, aaf.data(), n_rec * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(g.daf.p, daf.data(), n_rec * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(g.alleles.p, al.data(), n_rec * 2, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    h->ing_genome_fallbacks += 1;
+  }
+  CK(cudaMemcpyAsync(g.chr_first.p, first.data(), n_chr * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(g.chr_end.p, end.data(), n_chr * 8, cudaMemcpyHostToDevice, s));
+  g.n_rec = n_rec;
+  const int rc2 = genome_replaced_ext(h, slot);
+  if (rc2) return rc2;
+  CK(cudaStreamSynchronize(s));   // first / end are locals
+  return n_rec;
 }
 
 }  // extern "C"

@@ -90,6 +90,27 @@ __global__ void k_join(int64_t n_site, int n_chr, const int64_t* __restrict__ si
   }
 }
 
+// ---- input order (COLATE_ERR_ORDER) ---------------------------------------------------------
+// k_join's binary search and the find-previous-candidate rule of k_ok equal the reference's sequential reader
+// (coal.cpp:2184-2217) only on ascending positions: .mut rows ascending within a chromosome, .colate.in records
+// ascending within the record range the reader can reach on a chromosome.  One pass each; equal neighbours are fine.
+__global__ void k_check_sites(int64_t n_site, int n_chr, const int64_t* __restrict__ site_off, const int32_t* __restrict__ pos,
+                              int* __restrict__ flag)
+{
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m == 0 || m >= n_site) return;
+  if (pos[m] < pos[m - 1] && site_off[chr_of(site_off, n_chr, m)] != m) *flag = 1;   // a descent is legal only at a chromosome start
+}
+__global__ void k_check_genome(int64_t n_rec, int n_chr, const int64_t* __restrict__ chr_first, const int64_t* __restrict__ chr_end,
+                               const int32_t* __restrict__ bp, int* __restrict__ flag)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0 || k >= n_rec) return;
+  if (bp[k] < bp[k - 1])
+    for (int c = 0; c < n_chr; c++)
+      if (chr_first[c] >= 0 && k > chr_first[c] && k < chr_end[c]) *flag = 1;
+}
+
 // row filter x masks -> candidate bitmap for the reference stream (coal.cpp:2150-2181)
 __global__ void k_cand(int64_t n_site, const uint32_t* __restrict__ meta, const uint32_t* __restrict__ tmask,
                        const uint32_t* __restrict__ rmask, uint32_t* __restrict__ cand)
@@ -763,7 +784,7 @@ int run_join(colate_handle* h, int slot)
   const int64_t n = h->n_site;
   CK(g.j_aaf.ensure(n * 4 + 4)); CK(g.j_daf.ensure(n * 4 + 4)); CK(g.j_prevbp.ensure(n * 4 + 4)); CK(g.j_flag.ensure(n + 4));
   if (n > 0) {
-    int grid = (int)std::min<int64_t>(grid_for(n, 256), 148 * 16);
+    int grid = (int)std::min<int64_t>(grid_for(n, 256), (int64_t)h->sm_count * 16);
     k_join<<<grid, 256, 0, h->stream>>>(n, h->n_chr, h->site_off.as<int64_t>(), h->pos.as<int32_t>(), h->meta.as<uint32_t>(),
                                         g.chr_first.as<int64_t>(), g.chr_end.as<int64_t>(), g.bp.as<int32_t>(),
                                         g.aaf.as<int32_t>(), g.daf.as<int32_t>(), g.alleles.as<uint16_t>(),
@@ -772,6 +793,29 @@ int run_join(colate_handle* h, int slot)
     h->launches += 1;
   }
   g.joined = true;
+  return 0;
+}
+
+int run_check_sites(colate_handle* h)
+{
+  if (h->n_site > 1) {
+    k_check_sites<<<grid_for(h->n_site, 256), 256, 0, h->stream>>>(h->n_site, h->n_chr, h->site_off.as<int64_t>(), h->pos.as<int32_t>(),
+                                                                   h->order_flag.as<int>());
+    h->launches += 1;
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+
+int run_check_genome(colate_handle* h, int slot)
+{
+  GenomeDev& g = h->genomes[slot];
+  if (g.n_rec > 1 && h->n_chr > 0) {
+    k_check_genome<<<grid_for(g.n_rec, 256), 256, 0, h->stream>>>(g.n_rec, h->n_chr, g.chr_first.as<int64_t>(), g.chr_end.as<int64_t>(),
+                                                                  g.bp.as<int32_t>(), h->order_flag.as<int>() + 1 + slot);
+    h->launches += 1;
+    CK(cudaGetLastError());
+  }
   return 0;
 }
 

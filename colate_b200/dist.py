@@ -24,23 +24,29 @@ from ._lib import MAX_BLOCKS, NBINS
 
 
 def split_chromosomes(rows_per_chr, world: int):
-    """Contiguous ranges [lo, hi) of the --chr list per rank, balanced by row count."""
+    """Contiguous ranges [lo, hi) of the --chr list per rank, balanced by row count: boundary r is the cumulative row
+    count nearest to r/world of the total, moved if necessary so that every rank keeps at least one chromosome
+    (world <= n_chr).  With more ranks than chromosomes the first n_chr ranks own one chromosome each and the rest
+    own none: an empty rank still joins every exchange with zero used rows and zero blocks."""
     rows = np.asarray(rows_per_chr, dtype=np.int64)
     n = rows.shape[0]
     cum = np.concatenate([[0], np.cumsum(rows)])
     total = cum[-1]
     bounds = [0]
     for r in range(1, world):
+        lo = min(n, bounds[-1] + 1)                    # at least one chromosome for rank r - 1 ...
+        hi = max(lo, n - (world - r))                  # ... and for each of the ranks r .. world - 1
+        hi = min(hi, n)
         target = total * r / world
-        c = int(np.searchsorted(cum, target, side="left"))
-        c = max(bounds[-1], min(n, c))
+        c = lo + int(np.argmin(np.abs(cum[lo:hi + 1] - target)))
         bounds.append(c)
     bounds.append(n)
     return [(bounds[r], bounds[r + 1]) for r in range(world)]
 
 
 class CudaBackend:
-    """The product path: api.Handle on this rank's GPU."""
+    """The product path: api.Handle on this rank's GPU.  The block histograms stay on the device from the sampling
+    kernels through the all-reduce into the bootstrap kernel (`sample_into` / `bootstrap_dev`)."""
 
     def __init__(self, handle: api.Handle):
         self.h = handle
@@ -48,12 +54,14 @@ class CudaBackend:
     def flags(self):
         return self.h.stage1_flags()
 
-    def sample(self, mt_state, used_rank_base, block_base, n_blocks):
-        return self.h.stage1_sample(mt_state, used_rank_base, block_base, n_blocks)
+    def sample_into(self, mt_state, used_rank_base, block_base, n_blocks, stats_t, tallies_t):
+        """Rows [block_base, block_base + n_blocks) of the zero-padded device tensors receive this rank's blocks."""
+        return self.h.stage1_sample_dev(mt_state, used_rank_base, block_base,
+                                        stats_t.data_ptr() + block_base * 4 * NBINS * 8 if n_blocks else None,
+                                        tallies_t.data_ptr() + block_base * 3 * NBINS * 8 if n_blocks else None)
 
-    def bootstrap(self, weights, block_stats, age):
-        self.h.stage2_bootstrap(weights, block_stats, age, fetch=False)
-        return None
+    def bootstrap_dev(self, weights, stats_t, num_blocks, age):
+        self.h.stage2_bootstrap_dev(weights, stats_t.data_ptr(), num_blocks, age)
 
     def em(self, R, epochs, rates_init, counts, max_iter):
         return self.h.stage3_em(R, epochs, rates_init, counts, max_iter)
@@ -63,13 +71,21 @@ class CudaBackend:
 class DistResult:
     num_blocks: int
     n_used: int
-    block_stats: np.ndarray      # [num_blocks, 4, 185], identical on every rank
-    block_tallies: np.ndarray    # [num_blocks, 3, 185]
+    block_stats: np.ndarray | None     # [num_blocks, 4, 185], identical on every rank (fetched on first use: .stats())
+    block_tallies: np.ndarray | None   # [num_blocks, 3, 185]
     mt_state: np.ndarray         # generator state after stage i, identical on every rank
     rates: np.ndarray | None     # [R, E] on every rank
     iters: np.ndarray | None
     epochs: np.ndarray | None
     ep_null: int = 0
+    stats_dev: object = None     # torch [500, 4, 185] f64 / [500, 3, 185] i64 on the compute device
+    tallies_dev: object = None
+
+    def stats(self):
+        if self.block_stats is None:
+            self.block_stats = self.stats_dev[:self.num_blocks].cpu().numpy()
+            self.block_tallies = self.tallies_dev[:self.num_blocks].cpu().numpy()
+        return self.block_stats, self.block_tallies
 
 
 def _dist():
@@ -93,19 +109,25 @@ def stage1_sharded(backend, seed_state: np.ndarray, device="cuda"):
     if num_blocks > MAX_BLOCKS:
         raise api._lib.ColateError(-3, "more than 500 genomic blocks")
     n_local = int(allv[rank, 1])
-    stats, tallies, state_after = backend.sample(seed_state, used_base, block_base, n_local)
     pad = torch.zeros((MAX_BLOCKS, 4, NBINS), dtype=torch.float64, device=device)
     pad_n = torch.zeros((MAX_BLOCKS, 3, NBINS), dtype=torch.int64, device=device)
-    if n_local:
-        pad[block_base:block_base + n_local] = torch.from_numpy(np.ascontiguousarray(stats[:n_local])).to(device)
-        pad_n[block_base:block_base + n_local] = torch.from_numpy(np.ascontiguousarray(tallies[:n_local])).to(device)
+    if hasattr(backend, "sample_into"):
+        if pad.is_cuda:
+            torch.cuda.current_stream().synchronize()          # the zero fill, before the handle's stream writes into the tensors
+        state_after = backend.sample_into(seed_state, used_base, block_base, n_local, pad, pad_n)
+    else:
+        stats, tallies, state_after = backend.sample(seed_state, used_base, block_base, n_local)
+        if n_local:
+            pad[block_base:block_base + n_local] = torch.from_numpy(np.ascontiguousarray(stats[:n_local])).to(device)
+            pad_n[block_base:block_base + n_local] = torch.from_numpy(np.ascontiguousarray(tallies[:n_local])).to(device)
     dist.all_reduce(pad, op=dist.ReduceOp.SUM)                 # disjoint supports: x + 0.0 == x
     dist.all_reduce(pad_n, op=dist.ReduceOp.SUM)
     # the generator state after the last used row lives on the last rank
     st = torch.from_numpy(state_after.astype(np.int64)).to(device)
     dist.broadcast(st, src=world - 1)
-    return DistResult(num_blocks, n_used, pad[:num_blocks].cpu().numpy(), pad_n[:num_blocks].cpu().numpy(),
-                      st.cpu().numpy().astype(np.uint32), None, None, None)
+    res = DistResult(num_blocks, n_used, None, None, st.cpu().numpy().astype(np.uint32), None, None, None)
+    res.stats_dev, res.tallies_dev = pad, pad_n                # [500, ...] device tensors, identical on every rank
+    return res
 
 
 def em_sharded(backend, res: DistResult, num_bootstraps: int, epochs, rates_init, age=0.0, max_iter=100000, device="cuda"):
@@ -119,7 +141,13 @@ def em_sharded(backend, res: DistResult, num_bootstraps: int, epochs, rates_init
     rates = torch.zeros((num_bootstraps, E), dtype=torch.float64, device=device)
     iters = torch.zeros(num_bootstraps, dtype=torch.int64, device=device)
     if mine.shape[0]:
-        counts = backend.bootstrap(np.ascontiguousarray(w[mine]), res.block_stats, age)
+        if hasattr(backend, "bootstrap_dev"):
+            if res.stats_dev.is_cuda:
+                torch.cuda.current_stream().synchronize()      # the all-reduce, before the handle's stream reads the tensor
+            backend.bootstrap_dev(np.ascontiguousarray(w[mine]), res.stats_dev, res.num_blocks, age)
+            counts = None
+        else:
+            counts = backend.bootstrap(np.ascontiguousarray(w[mine]), res.stats()[0], age)
         r, it, _ = backend.em(mine.shape[0], epochs, rates_init, counts, max_iter)
         idx = torch.from_numpy(mine).to(device)
         rates[idx] = torch.from_numpy(np.ascontiguousarray(r)).to(device)

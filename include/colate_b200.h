@@ -119,8 +119,12 @@ int colate_stage1(colate_handle* h, int target_slot, int reference_slot, const u
 /* ---- stage ii: block bootstrap + F redistribution, coal.cpp:3344-3451 ---------------- */
 /* block_weights[R][num_blocks]: multiplicity of each block per replicate, drawn by the host
  * with the reference's generator (colate_draw_block_weights(), coal.cpp:3350-3357).
- * counts[R][2][185]: age_shared_count / age_notshared_count per replicate (host). The
- * counts also stay resident on the device for colate_stage3_em(). */
+ * counts[R][2][185]: age_shared_count / age_notshared_count per replicate (optional). The
+ * counts also stay resident on the device for colate_stage3_em().
+ * block_stats == NULL: the histograms the last colate_stage1 / colate_stage1_sample call left on the device
+ * (num_blocks must be that call's block count).
+ * Data pointers of stages i-iii outputs and of block_weights / block_stats / counts may be host or device
+ * pointers (unified addressing): a multi-GPU driver all-reduces the histograms on the device. */
 int colate_stage2_bootstrap(colate_handle* h, int R, int num_blocks, const int32_t* block_weights,
                             const double* block_stats, double age, double* counts);
 
@@ -187,17 +191,33 @@ int colate_epochs_from_coal_file(const char* path, double age, double* epochs, d
  * device, one thread per row, straight into the handle's site arrays.  Integers as std::stoi, ages
  * as std::stof (correctly rounded decimal -> float; the rare rows the device cannot convert with
  * that guarantee are re-parsed on the host with strtof).  Result == colate_read_mut() row for row.
- *   colate_ingest_begin(h, n_chr, row_capacity)     row_capacity >= total data rows of all files
+ *   colate_ingest_begin(h, n_chr, row_capacity)     row_capacity >= total data rows of all files (any upper bound,
+ *                                                   e.g. total bytes / 20: a data row has at least 10 fields)
  *   colate_ingest_mut_text(h, text, n_bytes, loc)   once per --chr entry, in order; returns its rows
  *   colate_ingest_end(h)                            == colate_set_sites() on what was ingested
  *   colate_ingest_fetch(...)                        host copies of ingested rows (masks, tests)
  *   colate_ingest_stats(...)                        device time of the parse kernels, host-parsed rows */
 int colate_ingest_begin(colate_handle* h, int n_chr, int64_t row_capacity);
 int64_t colate_ingest_mut_text(colate_handle* h, const char* text, int64_t n_bytes, int location);
+/* All chromosomes at once: texts[c] / n_bytes[c] in --chr order.  From pinned host memory every text is copied on
+ * the handle's copy stream and parsed as soon as it has landed, under the copies of the following chromosomes.
+ * rows_out[c] (optional) = data rows of chromosome c.  Same result as n_texts calls of colate_ingest_mut_text. */
+int colate_ingest_mut_texts(colate_handle* h, int n_texts, const char* const* texts, const int64_t* n_bytes, int location,
+                            int64_t* rows_out);
 int colate_ingest_end(colate_handle* h);
 int colate_ingest_fetch(colate_handle* h, int64_t row0, int64_t n_rows, int32_t* pos, float* age_begin, float* age_end,
                         uint32_t* meta);
 int colate_ingest_stats(colate_handle* h, double* kernel_ms, int64_t* host_fallback_rows);
+
+/* .colate.in image (the file's bytes, host or device) -> genome slot, decoded on the device: replaces
+ * colate_read_colate_in + colate_chr_ranges + colate_set_genome (the reference's inline reader: coal.cpp:2126-2133,
+ * 2185-2192, 2205-2212; record layout coal.cpp:2505-2514).  The host locates the runs of equal-width records
+ * ({lchrom, chrom} headers) by galloping, the device checks every record's header against its run and splits the
+ * payload into the slot's arrays; an image whose runs do not verify (interleaved chromosomes) is decoded
+ * sequentially on the host instead -- the result is the sequential reader's in every case.  chr_names = the --chr
+ * list of the site set in the handle.  Returns the number of records (>= 0) or a negative status. */
+int64_t colate_ingest_colate_in(colate_handle* h, int slot, const char* bytes, int64_t n_bytes, int n_chr,
+                                const char* const* chr_names, int location);
 
 /* ---- readers / writers (host) --------------------------------------------------------- */
 /* Relate .mut[.gz] (mutations.cpp:56-283).  Two-call pattern: n = colate_read_mut(path, 0, ...NULL)

@@ -34,6 +34,8 @@ class OracleBackend:
     def flags(self):
         from oracle import pyoracle as po
         used, blocks = [], []
+        if not self.sites.chr_names:                    # a rank that owns no chromosome (world > n_chr)
+            return np.zeros(0, np.int64), np.zeros(0, np.int32)
         for c in range(len(self.sites.chr_names)):
             o = OracleBackend._one(self, c)
             used.append(o["n_used_total"]); blocks.append(o["num_blocks"])
@@ -55,6 +57,11 @@ class OracleBackend:
     def sample(self, mt_state, used_rank_base, block_base, n_blocks):
         from colate_b200 import api
         from oracle import pyoracle as po
+        if not self.sites.chr_names:
+            after = api.mt_seed(self._seed)
+            api.lib().colate_mt_generate(after, 200 * used_rank_base, np.zeros(max(1, 200 * used_rank_base), np.uint32))
+            assert n_blocks == 0
+            return np.zeros((0, 4, 185)), np.zeros((0, 3, 185), np.int64), after
         # an oracle generator positioned at this rank's offset in the reference's stream
         g = po.mt_seed(self._seed)
         for _ in range(200 * used_rank_base):
@@ -80,20 +87,26 @@ class OracleBackend:
         return np.stack([o[0] for o in out]), np.array([o[1] for o in out]), np.array([o[2] for o in out])
 
 
-def _worker(rank, world, port, seed, R, q):
+ROWS = {"even": ([900, 600, 1400, 700, 1100], [2.4e8, 5e7, 1.3e8, 6.1e7, 9e7]),
+        "skewed": ([40, 40, 2500], [5e7, 5e7, 2.4e8]),          # everything nearest the target sits in the last chromosome
+        "two": ([800, 1200], [9e7, 2.4e8])}                     # fewer chromosomes than ranks at world 3
+
+
+def _worker(rank, world, port, seed, R, q, shape="even"):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
     from colate_b200 import dist as cdist, synth
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    sites = synth.make_sites(seed, [900, 600, 1400, 700, 1100], [2.4e8, 5e7, 1.3e8, 6.1e7, 9e7], weird=0.05)
+    sites = synth.make_sites(seed, *ROWS[shape], weird=0.05)
     gt = synth.make_genome(seed + 100, sites, 0.8)
     gr = synth.make_genome(seed + 200, sites, 0.8)
     parts = cdist.split_chromosomes(np.diff(sites.site_off), world)
     be = OracleBackend(sites, gt, gr, *parts[rank])
     be._seed = seed
     res = cdist.mut_sharded(be, seed, bins="3,7,0.2", num_bootstraps=R, max_iter=30, device="cpu")
-    q.put((rank, res.num_blocks, res.n_used, res.block_stats, res.block_tallies, res.mt_state, res.rates, res.iters))
+    stats, tallies = res.stats()
+    q.put((rank, res.num_blocks, res.n_used, stats, tallies, res.mt_state, res.rates, res.iters))
     dist.destroy_process_group()
 
 
@@ -101,15 +114,23 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-@pytest.mark.parametrize("R", [1, 5])
-def test_chromosome_and_replicate_sharding_world2(built, R):
+@pytest.mark.parametrize("R,world,shape", [(1, 2, "even"), (5, 2, "even"), (3, 2, "skewed"), (2, 3, "two")])
+def test_chromosome_and_replicate_sharding(built, R, world, shape):
+    """world 2 on five chromosomes; a skewed split (no rank may end up empty while world <= n_chr); three
+    ranks on two chromosomes (one rank owns nothing and still joins every exchange)."""
     from colate_b200 import synth
+    from colate_b200.dist import split_chromosomes
     from oracle import pyoracle as po
-    seed, world = 4, 2
+    seed = 4
+    parts = split_chromosomes(ROWS[shape][0], world)
+    if world <= len(ROWS[shape][0]):
+        assert all(hi > lo for lo, hi in parts), parts
+    else:
+        assert sum(hi > lo for lo, hi in parts) == len(ROWS[shape][0])
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, seed, R, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, seed, R, q, shape)) for r in range(world)]
     for p in procs:
         p.start()
     outs = sorted([q.get(timeout=150) for _ in procs], key=lambda t: t[0])
@@ -117,7 +138,7 @@ def test_chromosome_and_replicate_sharding_world2(built, R):
         p.join(60)
         assert p.exitcode == 0
     # single-process run of the whole thing
-    sites = synth.make_sites(seed, [900, 600, 1400, 700, 1100], [2.4e8, 5e7, 1.3e8, 6.1e7, 9e7], weird=0.05)
+    sites = synth.make_sites(seed, *ROWS[shape], weird=0.05)
     gt = synth.make_genome(seed + 100, sites, 0.8)
     gr = synth.make_genome(seed + 200, sites, 0.8)
     o = po.stage1(sites, gt, gr, seed=seed)
@@ -131,13 +152,16 @@ def test_chromosome_and_replicate_sharding_world2(built, R):
         assert np.array_equal(stats, ref_stats)                       # bit-identical to one process
         assert np.array_equal(tallies[:, 1], o["n_notshared"])
         assert np.array_equal(rates, want) and (iters == 30).all()
-    assert np.array_equal(outs[0][5], outs[1][5])                     # same generator state everywhere
+    for o2 in outs[1:]:
+        assert np.array_equal(outs[0][5], o2[5])                      # same generator state everywhere
 
 
 def test_split_chromosomes():
     from colate_b200.dist import split_chromosomes
     assert split_chromosomes([10, 10, 10, 10], 2) == [(0, 2), (2, 4)]
-    assert split_chromosomes([5], 4) == [(0, 0), (0, 0), (0, 0), (0, 1)] or sum(h - l for l, h in split_chromosomes([5], 4)) == 1
+    assert split_chromosomes([5], 4) == [(0, 1), (1, 1), (1, 1), (1, 1)]
+    assert split_chromosomes([1, 1, 100], 2) == [(0, 2), (2, 3)]                       # was [(0, 3), (3, 3)]
+    assert split_chromosomes([10, 10, 10, 1000], 4) == [(0, 1), (1, 2), (2, 3), (3, 4)]
     for w in (1, 2, 3, 8):
         parts = split_chromosomes([249, 243, 198, 191, 180, 171, 159, 146, 141, 135, 135, 133, 115, 107, 102, 90, 81, 78, 59, 63, 48, 51], w)
         assert parts[0][0] == 0 and parts[-1][1] == 22 and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))

@@ -195,6 +195,55 @@ def test_chr_ranges_emulate_the_sequential_seek(built):
         assert same(f, bf) and same(e, be), ch
 
 
+def _colate_in_image(chrom_ids, names, rng):
+    """Record stream with the given chromosome id per record (ids index `names`)."""
+    out = bytearray()
+    for k, c in enumerate(chrom_ids):
+        nm = names[int(c)].encode()
+        out += np.array([len(nm)], dtype="<i4").tobytes() + nm + np.array([1000 + 3 * k], dtype="<i4").tobytes()
+        out += bytes([65 + int(rng.integers(0, 4)), 67]) + np.array([int(rng.integers(0, 5)), int(rng.integers(0, 5))], dtype="<i4").tobytes()
+    return bytes(out)
+
+
+def test_colate_in_run_finder_matches_the_sequential_reader(built, tmp_path):
+    """colate_ingest_colate_in's host half: runs found by galloping + run-level chromosome seek == the record-by-record
+    decode + colate_chr_ranges whenever every record carries its run's header (what the device verifies)."""
+    rng = np.random.default_rng(11)
+    names_all = ["1", "2", "3", "10", "X", "chr22"]          # widths 19, 19, 19, 20, 19, 23
+    chr_list = ["1", "2", "3", "10"]                         # "X" and "chr22" are not in --chr
+    cases = [np.repeat([0, 1, 2, 3], [5, 1, 7, 3]), np.repeat([1, 2], [4, 4]), np.repeat([4, 0, 5, 3], [3, 6, 2, 9]),
+             np.array([], dtype=np.int64), np.array([2]), np.repeat([0, 3, 0], [8, 2, 8]), np.repeat([0, 1, 0, 1], [600, 7, 500, 1])]
+    cases += [np.repeat(rng.integers(0, 6, 6), rng.integers(1, 40, 6)) for _ in range(30)]
+    cases += [rng.integers(0, 6, 40) for _ in range(10)]                     # interleaved: mostly runs of length 1
+    verified = 0
+    for ch in cases:
+        img = _colate_in_image(ch, names_all, rng)
+        for cut in (0, 5):                                                   # a truncated last record ends the stream
+            image = img[:len(img) - cut] if len(img) > cut else img
+            path = str(tmp_path / "x.colate.in")
+            open(path, "wb").write(image)
+            rc, bp, aaf, daf, al = api.read_colate_in(path, chr_list)
+            f0, e0 = api.chr_ranges(len(chr_list), rc)
+            n_rec, runs, f1, e1 = api.colate_in_runs(image, chr_list)
+            # the device's check, here on the host: every record of a run starts with the run's header
+            ok = True
+            for off, w, cid, n in runs:
+                hl = w - 14
+                first = image[off:off + hl]
+                ok &= all(image[off + j * w: off + j * w + hl] == first for j in range(n))
+            if not ok:
+                continue
+            verified += 1
+            assert n_rec == rc.shape[0]
+            assert same(np.repeat(runs[:, 2], runs[:, 3]).astype(np.int32), rc)
+            assert same(f0, f1) and same(e0, e1), (ch, cut)
+    assert verified >= 60
+    # a clean file: one run per chromosome, found with O(log n) probes per run
+    ch = np.repeat([0, 1, 2, 3], [5000, 3000, 1, 4000])
+    n_rec, runs, _, _ = api.colate_in_runs(_colate_in_image(ch, names_all, rng), chr_list)
+    assert n_rec == 12001 and runs.shape[0] == 4 and same(runs[:, 3], np.array([5000, 3000, 1, 4000]))
+
+
 def test_readers_roundtrip_against_written_files(built):
     z = load("stage1_small.npz")
     sites, gt, gr = dataset_from(z)

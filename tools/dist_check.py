@@ -33,7 +33,7 @@ ms = torch.tensor([e0.elapsed_time(e1)], device="cuda"); dist.all_reduce(ms, op=
 if rank == 0:
     h1 = api.Handle(local); h1.load(sites, gt, gr)
     one = api.mut(h1, seed=1, bins="3,7,0.1", num_bootstraps=R)
-    ok = (res.num_blocks == one["num_blocks"] and np.array_equal(res.block_stats, one["stage1"].block_stats)
+    ok = (res.num_blocks == one["num_blocks"] and np.array_equal(res.stats()[0], one["stage1"].block_stats)
           and np.array_equal(res.rates, one["rates"]) and np.array_equal(res.iters, one["iters"]))
     print(f"dist_check world={world} rows={rows} R={R}: {'PASS' if ok else 'FAIL'} (bit-identical to 1 GPU), sharded pass (second, warm) {ms.item():.1f} ms", flush=True)
 dist.barrier(); dist.destroy_process_group()
