@@ -15,12 +15,19 @@ CPU stand-in to exercise this host logic under gloo with world_size 2.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 
 import numpy as np
 
 from . import api
 from ._lib import MAX_BLOCKS, NBINS
+
+
+CALLS: list = []   # collectives issued since the last clear(): (name, shape, dtype) -- bench.py prints them
+
+
+def _log(name, t):
+    CALLS.append([name, list(t.shape), str(t.dtype).replace("torch.", "")])
 
 
 def split_chromosomes(rows_per_chr, world: int):
@@ -42,6 +49,23 @@ def split_chromosomes(rows_per_chr, world: int):
         bounds.append(c)
     bounds.append(n)
     return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+def load_shard(handle: api.Handle, sites, target, reference, world: int, rank: int):
+    """This rank's chromosomes of a dataset (synth.Sites / synth.Genome) into `handle`: the rows of its contiguous
+    range of the --chr list, and both genomes with the record ranges of those chromosomes -- the chromosome seek
+    (coal.cpp:2125-2145) is emulated on the WHOLE record stream, a rank only keeps the ranges of its own names."""
+    lo, hi = split_chromosomes(np.diff(sites.site_off), world)[rank]
+    s0, s1 = int(sites.site_off[lo]), int(sites.site_off[hi])
+    meta = sites.meta()
+    handle.set_sites(sites.site_off[lo:hi + 1] - sites.site_off[lo], sites.pos[s0:s1], sites.age_begin[s0:s1], sites.age_end[s0:s1], meta[s0:s1])
+    for slot, g in ((0, target), (1, reference)):
+        first, end = api.chr_ranges(len(sites.chr_names), g.chrom)
+        al = g.anc.astype(np.uint16) | (g.der.astype(np.uint16) << 8)
+        api.check(api.lib().colate_set_genome(handle._h, slot, g.n, api.ptr(np.ascontiguousarray(first[lo:hi])),
+                                              api.ptr(np.ascontiguousarray(end[lo:hi])), api.ptr(np.ascontiguousarray(g.bp)),
+                                              api.ptr(np.ascontiguousarray(g.aaf)), api.ptr(np.ascontiguousarray(g.daf)), api.ptr(al), 0))
+    return lo, hi
 
 
 class CudaBackend:
@@ -78,6 +102,7 @@ class DistResult:
     iters: np.ndarray | None
     epochs: np.ndarray | None
     ep_null: int = 0
+    seconds: dict = field(default_factory=dict)   # this rank's wall time of the EM launch
     stats_dev: object = None     # torch [500, 4, 185] f64 / [500, 3, 185] i64 on the compute device
     tallies_dev: object = None
 
@@ -102,6 +127,7 @@ def stage1_sharded(backend, seed_state: np.ndarray, device="cuda"):
     mine = torch.tensor([int(np.sum(used_chr)), int(np.sum(blocks_chr))], dtype=torch.int64, device=device)
     allv = [torch.zeros_like(mine) for _ in range(world)]
     dist.all_gather(allv, mine)
+    _log("all_gather", mine)
     allv = np.stack([v.cpu().numpy() for v in allv])           # [world, 2]
     used_base = int(allv[:rank, 0].sum())
     block_base = int(allv[:rank, 1].sum())
@@ -122,9 +148,11 @@ def stage1_sharded(backend, seed_state: np.ndarray, device="cuda"):
             pad_n[block_base:block_base + n_local] = torch.from_numpy(np.ascontiguousarray(tallies[:n_local])).to(device)
     dist.all_reduce(pad, op=dist.ReduceOp.SUM)                 # disjoint supports: x + 0.0 == x
     dist.all_reduce(pad_n, op=dist.ReduceOp.SUM)
+    _log("all_reduce(sum)", pad); _log("all_reduce(sum)", pad_n)
     # the generator state after the last used row lives on the last rank
     st = torch.from_numpy(state_after.astype(np.int64)).to(device)
     dist.broadcast(st, src=world - 1)
+    _log("broadcast(src=last)", st)
     res = DistResult(num_blocks, n_used, None, None, st.cpu().numpy().astype(np.uint32), None, None, None)
     res.stats_dev, res.tallies_dev = pad, pad_n                # [500, ...] device tensors, identical on every rank
     return res
@@ -140,6 +168,8 @@ def em_sharded(backend, res: DistResult, num_bootstraps: int, epochs, rates_init
     E = len(epochs)
     rates = torch.zeros((num_bootstraps, E), dtype=torch.float64, device=device)
     iters = torch.zeros(num_bootstraps, dtype=torch.int64, device=device)
+    import time
+    t_em = 0.0
     if mine.shape[0]:
         if hasattr(backend, "bootstrap_dev"):
             if res.stats_dev.is_cuda:
@@ -148,13 +178,17 @@ def em_sharded(backend, res: DistResult, num_bootstraps: int, epochs, rates_init
             counts = None
         else:
             counts = backend.bootstrap(np.ascontiguousarray(w[mine]), res.stats()[0], age)
-        r, it, _ = backend.em(mine.shape[0], epochs, rates_init, counts, max_iter)
+        t0 = time.perf_counter()
+        r, it, _ = backend.em(mine.shape[0], epochs, rates_init, counts, max_iter)      # synchronous: returns with the rates on the host
+        t_em = time.perf_counter() - t0
         idx = torch.from_numpy(mine).to(device)
         rates[idx] = torch.from_numpy(np.ascontiguousarray(r)).to(device)
         iters[idx] = torch.from_numpy(np.asarray(it, dtype=np.int64)).to(device)
     dist.all_reduce(rates, op=dist.ReduceOp.SUM)               # disjoint supports again
     dist.all_reduce(iters, op=dist.ReduceOp.SUM)
+    _log("all_reduce(sum)", rates); _log("all_reduce(sum)", iters)
     res.rates, res.iters, res.epochs = rates.cpu().numpy(), iters.cpu().numpy().astype(np.int32), np.asarray(epochs)
+    res.seconds["em"] = t_em
     return res
 
 
