@@ -408,7 +408,7 @@ int colate_stage3_em(colate_handle* h, int R, int E, const double* epochs, const
     CK(cudaMemcpyAsync(h->d_counts.p, counts, (size_t)R * 2 * NBINS * 8, cudaMemcpyDefault, s));
     h->counts_R = R;
   }
-  if ((rc = run_em(h, R, E, max_iter))) return rc;
+  if ((rc = run_em(h, R, E, max_iter, epochs))) return rc;
   if (rates) CK(cudaMemcpyAsync(rates, h->d_rates.as<double>() + E, (size_t)R * E * 8, cudaMemcpyDefault, s));
   std::vector<int32_t> it_host((size_t)R);
   CK(cudaMemcpyAsync(it_host.data(), h->d_iters.p, (size_t)R * 4, cudaMemcpyDeviceToHost, s));
@@ -444,6 +444,13 @@ int colate_estep(colate_handle* h, int shared, int E, const double* epochs, cons
 }
 
 int colate_libm_exact(void) { return libm_self_check(); }
+
+// test hook (host): the straight-line log1p of the throughput-mode EM folds and its validity predicate
+int colate_test_log1p_wide(int n, const double* x, double* y, int32_t* ok)
+{
+  for (int i = 0; i < n; i++) { y[i] = glm::log1p_wide(x[i]); ok[i] = glm::log1p_wide_ok(x[i]) ? 1 : 0; }
+  return 0;
+}
 
 int colate_test_libm(colate_handle* h, int which, int n, const double* x, double* y)
 {

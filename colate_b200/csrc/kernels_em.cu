@@ -10,6 +10,8 @@
 #include "device.cuh"
 #include "glibc_math.cuh"
 
+#include <cstring>
+
 namespace cg = cooperative_groups;
 
 namespace colate {
@@ -89,6 +91,21 @@ __device__ __forceinline__ double lse(double a, double b, const glm::Tables& T)
   const double y = glm::log1p_k0(x);
   const double hi = (a > b) ? a : b;
   const bool ok = !bad(a) & !bad(b) & glm::exp_is_main(d) & glm::log1p_is_k0(x);
+  if (ok) return hi + y;
+  return lse_generic(a, b, T);
+}
+// The same for warps that run one fold per LANE (k_em_cta): at any step some lane's term is above 0.414 of its running
+// sum (the first steps of a fold) or below e^-20 of it (the deep epochs), so a fast path that covers only the
+// middle regime would send the whole warp through the generic code at almost every step.  log1p_wide() covers all
+// regimes of 0 < x < 1 without a branch; what is left for lse_generic is rare for every lane at once (non-finite
+// operands, equal operands, terms below e^-512 of the sum, three narrow bands of log1p).
+__device__ __forceinline__ double lse_wide(double a, double b, const glm::Tables& T)
+{
+  const double d = -fabs(a - b);
+  const double x = glm::exp_main(d, T);
+  const double y = glm::log1p_wide(x);
+  const double hi = (a > b) ? a : b;
+  const bool ok = !bad(a) & !bad(b) & glm::exp_is_main(d) & glm::log1p_wide_ok(x);
   if (ok) return hi + y;
   return lse_generic(a, b, T);
 }
@@ -880,6 +897,362 @@ k_em_split(int E, const double* __restrict__ epochs, const double* __restrict__ 
   if (stop_flag == 2 && tid == 0) iters_out[rep] = -1;   // handshake timed out: reported as an error by the host
 }
 
+// ---- stage iii, throughput mode: ONE replicate per CTA, work spread over the whole CTA --------------
+// Used when there are enough replicates to give every SM a CTA (config 3).  Same arithmetic as k_em /
+// k_em_split (same operations in the same order: rates, log-likelihood and iteration counts are bit-identical),
+// organised like k_em_split inside one CTA: the sequential logsumexp folds run one per lane, everything
+// else is spread over all threads, and nothing leaves shared memory.
+//   P0  cumulative hazard, A_ep, the not-shared tasks' own first term
+//   P1  folds: one not-shared fold per lane (warps 0..5), the shared tasks' prefix chain on its own thread,
+//       followed by the 185 shared heads; the other warps fill in B_ep, the denominator terms and the shared
+//       tasks' special epoch meanwhile
+//   P2  exp() of the two log-domain terms of every NEEDED (task, epoch) pair -- a shared task needs epochs
+//       [0, et], a not-shared task [et, E): 185 x (E + 1) pairs instead of 370 x E -- from a static pair
+//       table, written to a compact store (valN / valD, a task's entries contiguous, odd-length blocks)
+//   P3  thread = task: the serial `integ` recursion and the epoch's exposure, in place, times the count
+//   P4  thread = column: the sums over the 370 tasks in the reference's order (coal.cpp:3704-3733) straight
+//       from the compact store; M-step and stop rule.
+constexpr int EMC_THREADS = 640;
+constexpr int EMC_FOLD_WARPS = 6;     // 185 not-shared folds, one per lane
+constexpr int EMC_NT = 384;           // task slots (370 used): slot = 2 * bin + type
+
+struct EmcTask { int lo, hi, off, et; };   // needed epochs [lo, hi), first entry in the compact store, epoch that holds t
+
+// entries task `l` occupies in the compact store: its needed epochs, padded to an odd count for a shared task and to
+// an even count for a not-shared one: the distance between the blocks of two neighbouring bins' tasks of the same
+// type is then odd, and a half-warp of P3 threads (one task each) walks 16 different 8-byte banks
+__host__ __device__ inline int emc_block(int type, int et, int E)
+{
+  const int n = type ? E - et : ((E - 1 < et + 1 ? E - 1 : et + 1) + (et == E - 1 ? 1 : 0));
+  return type ? (n + 1) & ~1 : n | 1;
+}
+
+__global__ void __launch_bounds__(EMC_THREADS, 1)
+k_em_cta(int E, int n_pairs_cap, const double* __restrict__ epochs, const double* __restrict__ rates_init,
+         const double* __restrict__ age_bin_g, const double* __restrict__ counts, int max_iter,
+         const uint64_t* __restrict__ exp_tab_g, const uint64_t* __restrict__ log_tab_g,
+         double* __restrict__ rates_out, int32_t* __restrict__ iters_out, double* __restrict__ ll_out, long long* prof_g)
+{
+  const int rep = blockIdx.x;
+  extern __shared__ double sm[];
+  double* ep = sm;                  // [E]
+  double* rate = ep + E;            // [E]
+  double* Lam = rate + E;           // [E]
+  double* A = Lam + E;              // [E]
+  double* B = A + E;                // [E]
+  double* PL = B + E;               // [E+1]
+  double* tn = PL + E + 1;          // [E]
+  double* td = tn + E;              // [E]
+  double* cand = td + E;            // [E]
+  double* prod = cand + E;          // [E]
+  double* wz = prod + E;            // [E+1]  wz[0] = 0.0, wz[1 + e] = width of epoch e: what a task adds outside its block
+  double* h_t = sm + ((11 * E + 2 + 1) & ~1);   // [192]  age of the bin (even offset: h_cg and binrec are read as 16-byte words)
+  double* h_cnt = h_t + 192;        // [EMC_NT] count of the task (0: inactive, coal.cpp:3706 / 3719)
+  double* h_cg = h_cnt + EMC_NT;    // count while the task's normaliser is finite, else 0.0 (set every iteration)
+  double* h_nc = h_cg + EMC_NT;     // log normaliser
+  double* h_numt = h_nc + EMC_NT;   // the task's own log-domain terms (epoch that holds t)
+  double* h_dent = h_numt + EMC_NT;
+  double* h_logl = h_dent + EMC_NT; // count * log normaliser
+  double* valN = h_logl + EMC_NT;   // [n_pairs_cap] compact store: num[e] of every needed (task, epoch) pair
+  double* valD = valN + n_pairs_cap;  // [n_pairs_cap]                exp(den term), then denom[e]
+  uint64_t* etab = (uint64_t*)(valD + n_pairs_cap);  // [256]
+  uint64_t* ltab = etab + 256;                        // [256]
+  EmcTask* task = (EmcTask*)(ltab + 256);             // [EMC_NT]
+  int4* binrec = (int4*)(task + EMC_NT);              // [192] column sums: {off_s, hi_s, off_n - lo_n, lo_n} of the bin's two tasks
+  int* h_good = (int*)(binrec + 192);                 // [EMC_NT]
+  uint16_t* pair_task = (uint16_t*)(h_good + EMC_NT); // [n_pairs_cap] task of every store entry (0xffff: padding)
+  __shared__ int stop_flag, n_pairs_s;
+  __shared__ double ll_s, prev_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_task = 2 * NBINS;
+  for (int e = tid; e < E; e += blockDim.x) { ep[e] = epochs[e]; rate[e] = rates_init[e]; }
+  for (int i = tid; i < 256; i += blockDim.x) { etab[i] = exp_tab_g[i]; ltab[i] = log_tab_g[i]; }
+  if (tid == 0) { stop_flag = 0; ll_s = neg_inf(); }
+  __syncthreads();
+  for (int e = tid; e <= E; e += blockDim.x) wz[e] = (e >= 1 && e < E) ? ep[e] - ep[e - 1] : 0.0;   // wz[1 + e] = ep[e + 1] - ep[e]
+  if (tid < EMC_NT) {
+    const int b = tid >> 1, type = tid & 1;
+    double t = 0.0, cnt = 0.0;
+    int et = 0;
+    if (b < NBINS) {
+      t = age_bin_g[b];
+      cnt = counts[(size_t)rep * 2 * NBINS + (type ? NBINS : 0) + b];
+      et = tint_k(E, ep, t) - 1;
+      if (type == 0) h_t[b] = t;
+    }
+    h_cnt[tid] = cnt > 0 ? cnt : 0.0;
+    h_cg[tid] = 0.0;
+    h_good[tid] = 0; h_nc[tid] = 0.0; h_numt[tid] = 0.0; h_dent[tid] = 0.0; h_logl[tid] = 0.0;
+    EmcTask k;
+    k.et = et;
+    k.lo = type ? et : 0;
+    k.hi = type ? E : ((E - 1 < et + 1 ? E - 1 : et + 1) + (et == E - 1 ? 1 : 0));
+    if (b >= NBINS || !(cnt > 0)) { k.lo = 0; k.hi = 0; }     // inactive task (coal.cpp:3706, 3719): no entries, its block stays unused
+    k.off = 0;
+    task[tid] = k;
+  }
+  __syncthreads();
+  if (tid == 0) {   // offsets of the tasks' blocks (static for the whole run)
+    int o = 0;
+    for (int l = 0; l < n_task; l++) { task[l].off = o; o += emc_block(l & 1, task[l].et, E); }
+    n_pairs_s = o;
+  }
+  __syncthreads();
+  const int n_pairs = n_pairs_s;     // <= n_pairs_cap (the host computed the same sum)
+  for (int i = tid; i < n_pairs; i += blockDim.x) pair_task[i] = 0xffff;
+  if (tid < 192) {
+    int4 r = make_int4(0, 0, 0, E + 1);                       // no shared entries; not-shared: never in range (its count is 0.0)
+    if (tid < NBINS) {
+      const EmcTask ks = task[2 * tid], kn = task[2 * tid + 1];
+      r.x = ks.off; r.y = ks.hi;
+      if (kn.hi > kn.lo) { r.z = kn.off - kn.lo; r.w = kn.lo; }
+    }
+    binrec[tid] = r;
+  }
+  __syncthreads();
+  if (tid < n_task) {
+    const EmcTask k = task[tid];
+    for (int j = 0; j < k.hi - k.lo; j++) pair_task[k.off + j] = (uint16_t)tid;
+  }
+  EmCtx c{E, ep, rate, A, B, Lam, glm::Tables{etab, ltab}};
+  long long* prof = prof_g ? prof_g + (size_t)blockIdx.x * 40 : nullptr;
+  long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  __syncthreads();
+
+  int iter = 0;
+  for (; iter < max_iter; iter++) {
+    long long t0 = prof ? clock64() : 0, t1;
+    // P0: cumulative hazard, coal_EM.cpp:100-103 (products in parallel, then every thread that needs Lam[e] adds
+    // them up in index order: the same additions as the serial loop), A_ep, first terms of the not-shared heads
+    for (int e = tid + 1; e < E; e += blockDim.x) prod[e] = rate[e - 1] * (ep[e] - ep[e - 1]);
+    __syncthreads();
+    for (int e = tid; e < E; e += blockDim.x) {
+      double l = 0.0;
+      for (int i = 1; i <= e; i++) l = l + prod[i];
+      Lam[e] = l;
+    }
+    __syncthreads();
+    const int ft0 = (E + 31) & ~31;
+    if (tid < E) em_A(E, ep, rate, Lam, tid, A, c.T);
+    else if (tid >= ft0 && tid < ft0 + NBINS && h_cnt[2 * (tid - ft0) + 1] > 0) {   // EM_notshared, coal_EM.cpp:327-357, num part
+      const int l = 2 * (tid - ft0) + 1, et = task[l].et, k = et + 1;
+      const double t = h_t[l >> 1], r = rate[et];
+      const double c1 = Lam[et] + r * (t - ep[et]);
+      const double c2 = c1 + r * (t - t);
+      double num_t;
+      if (et != E - 1) {
+        const double c3 = c2 + r * (ep[k] - t);
+        num_t = (r > 0) ? lme(-c2, -c3, c.T) : neg_inf();
+      } else num_t = -c2;
+      h_numt[l] = num_t;
+    }
+    __syncthreads();
+    if (prof) { t1 = clock64(); tp[0] += t1 - t0; t0 = t1; }
+    // P1: the folds; the warps without one fill in what only the later phases need
+    if (warp < EMC_FOLD_WARPS) {
+      const int b = tid, l = 2 * b + 1;                        // not-shared fold of bin b
+      if (b < NBINS && h_cnt[l] > 0) {
+        double nc = h_numt[l];
+        const int et = task[l].et;
+        if (et != E - 1) {
+          double v = A[et + 1];
+          for (int e = et + 1; e < E; e++) {                   // next term loaded before the step that hides its latency
+            const double vn = A[min(e + 1, E - 1)];
+            nc = lse_wide(nc, v, c.T);
+            v = vn;
+          }
+        }
+        const bool good = !bad(nc);
+        h_nc[l] = nc; h_good[l] = good ? 1 : 0; h_cg[l] = good ? h_cnt[l] : 0.0; h_logl[l] = h_cnt[l] * (good ? nc : 0.0);
+      }
+    } else if (warp == EMC_FOLD_WARPS) {
+      if (lane == 0) {                                         // shared_prefix_chain with the next term prefetched
+        double nc = A[0], v = A[min(1, E - 1)];
+        PL[0] = 1.0;
+        PL[1] = nc;
+        for (int e = 1; e < E; e++) {
+          const double vn = A[min(e + 1, E - 1)];
+          if (nc == 1.0) nc = v; else nc = lse(nc, v, c.T);
+          PL[e + 1] = nc;
+          v = vn;
+        }
+      }
+    } else {
+      const int nh = EMC_THREADS - (EMC_FOLD_WARPS + 1) * 32;
+      for (int q = tid - (EMC_FOLD_WARPS + 1) * 32; q < E + 2 * NBINS; q += nh) {
+        if (q < E) em_B(E, ep, rate, Lam, q, B, c.T);
+        else if (q < E + NBINS) {                              // EM_notshared, coal_EM.cpp:327-357, denom part
+          const int l = 2 * (q - E) + 1;
+          if (h_cnt[l] > 0) {
+            const int et = task[l].et, k = et + 1;
+            const double t = h_t[l >> 1], r = rate[et], inv = 1.0 / r;
+            const double c1 = Lam[et] + r * (t - ep[et]);
+            const double c2 = c1 + r * (t - t);
+            double den_t;
+            if (et != E - 1) {
+              const double c3 = c2 + r * (ep[k] - t);
+              den_t = (r > 0) ? glm::log((t + inv) - (ep[k] + inv) * glm::exp(-c3 + c2, c.T), c.T) - c2 : neg_inf();
+            } else den_t = glm::log(t + inv, c.T) - c2;
+            h_dent[l] = den_t;
+          }
+        } else {
+          const int l = 2 * (q - E - NBINS);
+          if (h_cnt[l] > 0) {
+            double num_t, den_t;
+            shared_special(c, h_t[l >> 1], task[l].et, num_t, den_t);
+            h_numt[l] = num_t; h_dent[l] = den_t;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (prof) { t1 = clock64(); tp[1] += t1 - t0; t0 = t1; }
+    // the shared heads: one logsumexp each (coal_EM.cpp:254-258 ends at the epoch that holds t)
+    if (tid < NBINS) {
+      const int l = 2 * tid;
+      if (h_cnt[l] > 0) {
+        const double pl = PL[task[l].et], num_t = h_numt[l];
+        const double nc = (pl == 1.0) ? num_t : lse_wide(pl, num_t, c.T);
+        const bool good = !bad(nc);
+        h_nc[l] = nc; h_good[l] = good ? 1 : 0; h_cg[l] = good ? h_cnt[l] : 0.0; h_logl[l] = h_cnt[l] * (good ? nc : 0.0);
+      }
+    }
+    __syncthreads();
+    if (prof) { t1 = clock64(); tp[2] += t1 - t0; t0 = t1; }
+    // P2: exp() of the two log-domain terms of every needed (task, epoch) pair (zeros while the task's normaliser is not finite)
+    for (int i = tid; i < n_pairs; i += blockDim.x) {
+      const int l = pair_task[i];
+      if (l == 0xffff) continue;
+      const EmcTask k = task[l];
+      const int e = k.lo + (i - k.off);
+      const bool own = (l & 1) ? (e == k.et) : !(e < k.et);      // the task's own special-epoch terms instead of A_ep / B_ep
+      const double nc = h_nc[l];
+      const double xn = (own ? h_numt[l] : A[e]) - nc, xd = (own ? h_dent[l] : B[e]) - nc;
+      const bool good = h_good[l] != 0;
+      valN[i] = good ? exp_fast(xn, c.T) : 0.0;
+      valD[i] = good ? exp_fast(xd, c.T) : 0.0;
+    }
+    __syncthreads();
+    if (prof) { t1 = clock64(); tp[3] += t1 - t0; t0 = t1; }
+    // P3: thread = task: the serial `integ` recursion (coal_EM.cpp:266-271, 437-446) and the exposure of every needed
+    // epoch, in place.  Four epochs at a time (groups aligned to multiples of four for every lane, so the epoch
+    // bounds and widths are warp-uniform loads): the loads first, then the four dependent recursion steps, then the
+    // four independent exposure chains -- an in-order pipeline overlaps those, not a step-by-step loop.  Same
+    // operations as task_shared / task_notshared; the multiplication with the count happens in the column sums.
+    // Shared tasks on warps 0..5, not-shared tasks on warps 6..11: neighbouring lanes have similar ranges.
+    if (tid < 12 * 32) {
+      const int type = tid >= 192, bin = type ? tid - 192 : tid;
+      EmcTask k = task[2 * min(bin, NBINS - 1) + type];
+      if (bin >= NBINS || !h_good[2 * bin + type]) k.hi = k.lo = 0;
+      const int w_lo = __reduce_min_sync(0xffffffffu, k.hi > k.lo ? k.lo : E) & ~3, w_hi = __reduce_max_sync(0xffffffffu, k.hi);
+      const double* vn = valN + k.off - k.lo;
+      double* vd = valD + k.off - k.lo;
+      double integ = 1.0;
+      const int n_int = type ? E - 1 : (E - 1 < k.et + 1 ? E - 1 : k.et + 1);   // epochs [lo, n_int) take part in the recursion
+      for (int e0 = w_lo; e0 < w_hi; e0 += 4) {
+        double ne[4], de[4], el[4], ew[4], ig[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int e = e0 + u, ec = min(max(e, k.lo), max(k.hi - 1, k.lo));   // (outside [lo, hi): some entry of the block, not used)
+          ne[u] = vn[ec]; de[u] = vd[ec]; el[u] = ep[min(e, E - 1)]; ew[u] = wz[1 + min(e, E - 1)];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int e = e0 + u;
+          if (e >= k.lo && e < n_int) { if (integ > 0.0) integ -= ne[u]; else integ = 0.0; }
+          ig[u] = integ;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int e = e0 + u;
+          double d_ = de[u];
+          if (e < n_int) d_ += -el[u] * ne[u] + ew[u] * ig[u];
+          else d_ -= el[u] * ne[u];                              // the last epoch (coal_EM.cpp:273-287, 455-460)
+          if (d_ < 0.0) d_ = 0.0;
+          if (e >= k.lo && e < k.hi) vd[e] = d_;
+        }
+      }
+    }
+    __syncthreads();
+    if (prof) { t1 = clock64(); tp[4] += t1 - t0; t0 = t1; }
+    // P4: sums over the tasks in the reference's order (bin ascending, shared before not shared), thread = column;
+    // every term is count * value as the reference forms it (coal.cpp:3709-3731).  Outside a task's block its
+    // entries are exact zeros -- read from wz[0] -- except the not-shared tasks' epochs before the one that holds
+    // t, whose exposure is the whole epoch (coal_EM.cpp:437-441) -- read from wz[1 + e].  (Adding count * 0.0 = +0.0
+    // changes nothing: the sums are >= +0.0, or negative in the log-likelihood column.)  Branch-free body: one
+    // address select per task, loads and products issued ahead of the addition chain.
+    if (tid <= 2 * E) {
+      double acc = 0.0;
+      if (tid == 2 * E) {
+#pragma unroll 8
+        for (int l = 0; l < n_task; l++) acc += h_logl[l];       // (0.0 for inactive tasks)
+      } else {
+        const bool den = tid >= E;
+        const int e = den ? tid - E : tid;
+        const double* val = (den ? valD : valN) + e;
+        const double* before = den ? wz + 1 + e : wz;
+        const double2* cg2 = (const double2*)h_cg;
+        // groups of four bins, software-pipelined by hand: the records, addresses and values of the NEXT group are
+        // loaded before the eight dependent additions of the current one
+        constexpr int G = 4;
+        double vs[G], vn_[G], cs[G], cn[G];
+        auto fetch = [&](int g, double* ps, double* pn, double* qs, double* qn) {
+#pragma unroll
+          for (int j = 0; j < G; j++) {
+            const int bin = min(g * G + j, NBINS);               // bin NBINS: a record without entries and counts of 0.0
+            const int4 r = binrec[bin];
+            const double2 cg = cg2[bin];
+            ps[j] = *(e < r.y ? val + r.x : wz);
+            pn[j] = *(e >= r.w ? val + r.z : before);
+            qs[j] = cg.x; qn[j] = cg.y;
+          }
+        };
+        fetch(0, vs, vn_, cs, cn);
+        for (int g = 0; g < (NBINS + G - 1) / G; g++) {
+          double nvs[G], nvn[G], ncs[G], ncn[G];
+          fetch(g + 1, nvs, nvn, ncs, ncn);
+#pragma unroll
+          for (int j = 0; j < G; j++) {
+            acc += cs[j] * vs[j];
+            acc += cn[j] * vn_[j];
+          }
+#pragma unroll
+          for (int j = 0; j < G; j++) { vs[j] = nvs[j]; vn_[j] = nvn[j]; cs[j] = ncs[j]; cn[j] = ncn[j]; }
+        }
+      }
+      if (tid < E) tn[tid] = acc;
+      else if (tid < 2 * E) td[tid - E] = acc;
+      else { prev_s = ll_s; ll_s = acc; }
+    }
+    __syncthreads();
+    if (prof) { t1 = clock64(); tp[5] += t1 - t0; t0 = t1; }
+    // M-step, coal.cpp:3771-3815 (regularise == 2): rate[e] = num/denom floored at 5e-9; num == 0 ->
+    // copy the (already updated) rate of the previous epoch, or 0 for epoch 0; denom == 0 -> keep
+    for (int e = tid; e < E; e += blockDim.x) {
+      const double n_ = tn[e], d_ = td[e];
+      double r = rate[e];
+      if (n_ != 0 && d_ != 0) { r = n_ / d_; r = (r < 5e-9) ? 5e-9 : r; }
+      cand[e] = r;
+    }
+    __syncthreads();
+    for (int e = tid; e < E; e += blockDim.x) {
+      int s = e;
+      while (s >= 0 && tn[s] == 0) s--;          // nearest epoch at or below e with a non-zero numerator
+      rate[e] = (s >= 0) ? cand[s] : 0.0;
+    }
+    if (tid == 0 && (ll_s / prev_s > 1.0 - 1e-7) && (iter > 1000)) stop_flag = 1;  // coal.cpp:3822
+    __syncthreads();
+    if (prof) { t1 = clock64(); tp[6] += t1 - t0; t0 = t1; }
+    if (stop_flag) break;
+  }
+  // (the clock is read when the thread ARRIVES at a barrier: a thread without work in a phase shows the phase's length
+  // in the NEXT slot; thread 639 has no work in heads / P3 / P4)
+  if (prof && (tid == 0 || tid == 639)) for (int i = 0; i < 8; i++) prof[(tid ? 8 : 0) + i] = tp[i];
+  for (int e = tid; e < E; e += blockDim.x) rates_out[(size_t)rep * E + e] = rate[e];
+  if (tid == 0) { iters_out[rep] = iter; ll_out[rep] = ll_s; }
+}
+
 // E-step probe: one thread per age, plain stores
 __global__ void k_estep(int shared, int E, const double* __restrict__ epochs, const double* __restrict__ rates,
                         int n_t, const double* __restrict__ tt, const uint64_t* __restrict__ exp_tab_g,
@@ -942,7 +1315,7 @@ int run_bootstrap(colate_handle* h, int R, int num_blocks, const double* block_s
   return 0;
 }
 
-int run_em(colate_handle* h, int R, int E, int max_iter)
+int run_em(colate_handle* h, int R, int E, int max_iter, const double* epochs_host)
 {
   int rc = ensure_libm_tables(h);
   if (rc) return rc;
@@ -968,22 +1341,44 @@ int run_em(colate_handle* h, int R, int E, int max_iter)
   size_t smem_split = 0;
   bool split = split_fits(csize, &smem_split);
   if (!split && csize > 8) { csize = 8; split = split_fits(csize, &smem_split); }   // k_em itself runs on portable cluster sizes only
-  const size_t smem = split ? smem_split : sizeof(double) * ((size_t)10 * E + 1 + 2 * EM_STAGE_DOUBLES) + 512 * 8;
-  if (split) {
+  // throughput mode: one replicate per CTA with the work spread over the CTA (k_em_cta) whenever its compact store
+  // fits shared memory; the thread-per-task k_em remains for very fine epoch grids
+  bool cta = false;
+  size_t smem_cta = 0;
+  int n_pairs_cap = 0;
+  const char* force = getenv("COLATE_EM_KERNEL");   // "cta", "task" (k_em), "split": tests and tuning
+  if ((!split && csize == 1 && !(force && !strcmp(force, "task"))) || (force && !strcmp(force, "cta"))) {
+    double ab[NBINS];
+    colate_age_bins(ab);
+    for (int b = 0; b < NBINS; b++) {
+      int k = E;
+      for (int e = 0; e < E; e++) if (ab[b] < epochs_host[e]) { k = e; break; }
+      n_pairs_cap += emc_block(0, k - 1, E) + emc_block(1, k - 1, E);
+    }
+    smem_cta = sizeof(double) * ((size_t)11 * E + 4 + 192 + 6 * EMC_NT + 2 * (size_t)n_pairs_cap) + 512 * 8 + EMC_NT * (sizeof(EmcTask) + 4) + 192 * 16 +
+               (size_t)n_pairs_cap * 2 + 32;
+    cta = smem_cta <= 225 * 1024 && ((E + 31) & ~31) + NBINS <= EMC_THREADS;
+    if (cta) { split = false; csize = 1; }
+  }
+  const size_t smem = cta ? smem_cta : split ? smem_split : sizeof(double) * ((size_t)10 * E + 1 + 2 * EM_STAGE_DOUBLES) + 512 * 8;
+  if (cta) CK(cudaFuncSetAttribute(k_em_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (split) {
     CK(cudaFuncSetAttribute(k_em_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (csize > 8) CK(cudaFuncSetAttribute(k_em_split, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   }
   else CK(cudaFuncSetAttribute(k_em, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
-  CK(h->d_scratch.ensure((size_t)R * 2 * (2 * E + 2) * EM_TASKS * 8 + 1024));
+  if (!cta) CK(h->d_scratch.ensure((size_t)R * 2 * (2 * E + 2) * EM_TASKS * 8 + 1024));
   long long* prof = nullptr;
   if (getenv("COLATE_EM_PROF")) {
-    CK(h->d_prof.ensure((size_t)R * csize * 16 * 8));
-    CK(cudaMemsetAsync(h->d_prof.p, 0, (size_t)R * csize * 16 * 8, h->stream));
+    CK(h->d_prof.ensure((size_t)R * csize * 40 * 8));
+    CK(cudaMemsetAsync(h->d_prof.p, 0, (size_t)R * csize * 40 * 8, h->stream));
     prof = h->d_prof.as<long long>();
   }
+  h->em_kernel = cta ? 2 : split ? 1 : 0;
+  h->em_csize = csize;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(R * csize);
-  cfg.blockDim = dim3(split ? EMS_THREADS : EM_THREADS);
+  cfg.blockDim = dim3(cta ? EMC_THREADS : split ? EMS_THREADS : EM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = h->stream;
   cudaLaunchAttribute at[1];
@@ -992,12 +1387,26 @@ int run_em(colate_handle* h, int R, int E, int max_iter)
   cfg.attrs = at;
   cfg.numAttrs = 1;
   const uint64_t* tabs = h->libm_tab.as<uint64_t>();
+  if (cta)
+    CK(cudaLaunchKernelEx(&cfg, k_em_cta, E, n_pairs_cap, (const double*)h->d_epochs.as<double>(), (const double*)h->d_rates.as<double>(),
+                          (const double*)h->d_agebin.as<double>(), (const double*)h->d_counts.as<double>(), max_iter, tabs, tabs + 256,
+                          h->d_rates.as<double>() + E, h->d_iters.as<int32_t>(), h->d_ll.as<double>(), prof));
+  else
   CK(cudaLaunchKernelEx(&cfg, split ? k_em_split : k_em, E, (const double*)h->d_epochs.as<double>(), (const double*)h->d_rates.as<double>(),
                         (const double*)h->d_agebin.as<double>(), (const double*)h->d_counts.as<double>(), max_iter, tabs, tabs + 256,
                         h->d_scratch.as<double>(), h->d_rates.as<double>() + E, h->d_iters.as<int32_t>(), h->d_ll.as<double>(), prof));
   h->launches += 1;
   CK(cudaGetLastError());
   if (prof) {
+    if (cta) {
+      long long q[16];
+      CK(cudaMemcpyAsync(q, prof, 128, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      for (int w = 0; w < 2; w++)
+        fprintf(stderr, "[k_em_cta prof, replicate 0 thread %d, cycles between its arrivals at the phase barriers] P0 %lld | P1 folds %lld | heads %lld | P2 exps %lld | P3 integ %lld | P4 column sums %lld | M-step %lld\n",
+                w ? 639 : 0, q[8 * w], q[8 * w + 1], q[8 * w + 2], q[8 * w + 3], q[8 * w + 4], q[8 * w + 5], q[8 * w + 6]);
+      return 0;
+    }
     const int ps = split ? 16 : 8;
     std::vector<long long> hp((size_t)ps * csize);
     CK(cudaMemcpyAsync(hp.data(), prof, (size_t)ps * 8 * csize, cudaMemcpyDeviceToHost, h->stream));

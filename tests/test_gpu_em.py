@@ -164,3 +164,50 @@ def test_em_mid_range_replicates_on_split_clusters(handle):
         ro, it, llo = po.em_run(ep, init, counts[r], max_iter=300)
         assert iters[r] == it and _same(rates[r], ro) and _same(ll[r], llo)
     assert len({tuple(x) for x in rates}) > R // 2
+
+
+def test_em_1000_replicates_three_kernels_bitwise(handle, monkeypatch):
+    """BASELINE.json configs[2]'s EM: 1000 block-bootstrap replicates at E = 43 (--bins 3,7,0.1).  Every replicate's
+    iteration count, rates and log-likelihood agree BITWISE between the three EM kernels -- k_em_cta (one CTA per
+    replicate, work spread over the CTA: the default here), k_em (thread per task) and k_em_split (clusters of 8) --
+    and 20 replicates are checked against the oracle (coal.cpp:3675-3827 + coal_EM)."""
+    o = _block_stats()
+    R = 1000
+    w = api.draw_block_weights(api.mt_seed(13), R, o["num_blocks"])
+    counts = po.stage2(w, o, 0.0)
+    ep, _ = po.epochs_from_bins("3,7,0.1", 0.0, 28.0)
+    assert len(ep) == 43
+    init = np.full(len(ep), 1 / 20000.)
+    res = {}
+    for name, env in (("cta", {}), ("task", {"COLATE_EM_KERNEL": "task"}), ("split", {"COLATE_EM_CLUSTER": "8"})):
+        with monkeypatch.context() as m:
+            for k, v in env.items():
+                m.setenv(k, v)
+            res[name] = handle.stage3_em(R, ep, init, counts)
+    for name in ("task", "split"):
+        assert np.array_equal(res["cta"][1], res[name][1]), name                                  # iterations, all 1000
+        assert np.array_equal(res["cta"][0].view(np.int64), res[name][0].view(np.int64)), name    # rates, bit patterns
+        assert np.array_equal(res["cta"][2].view(np.int64), res[name][2].view(np.int64)), name    # log-likelihoods
+    rates, iters, ll = res["cta"]
+    assert iters.min() >= 1001 and len({tuple(x) for x in rates}) > R // 2
+    for r in list(range(0, R, 53)) + [R - 1]:
+        ro, it, llo = po.em_run(ep, init, counts[r])
+        assert iters[r] == it and _same(rates[r], ro) and _same(ll[r], llo), r
+
+
+@pytest.mark.parametrize("kernel", ["cta", "task"])
+@pytest.mark.parametrize("bins,age", [("3,7,0.2", 0.0), ("3,7,0.1", 250.0), ("2,8,0.3", 100.0), ("4,6,0.5", 0.0)])
+def test_em_one_cta_kernels_on_other_grids(handle, monkeypatch, kernel, bins, age):
+    """Both one-CTA-per-replicate kernels on ancient / coarse / wide epoch grids (the last epoch holding ages, epochs
+    without ages, ep_null > 0), 40 replicates each, against the oracle."""
+    monkeypatch.setenv("COLATE_EM_KERNEL", kernel)
+    o = _block_stats()
+    R = 40
+    w = api.draw_block_weights(api.mt_seed(14), R, o["num_blocks"])
+    counts = po.stage2(w, o, age)
+    ep, _ = po.epochs_from_bins(bins, age, 28.0)
+    init = np.full(len(ep), 1 / 20000.)
+    rates, iters, ll = handle.stage3_em(R, ep, init, counts, max_iter=150)
+    for r in (0, 17, 39):
+        ro, it, llo = po.em_run(ep, init, counts[r], max_iter=150)
+        assert iters[r] == it and _same(rates[r], ro) and _same(ll[r], llo), r

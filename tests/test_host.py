@@ -131,6 +131,29 @@ def test_libm_port_is_this_hosts_libm(built):
     assert api.libm_exact()
 
 
+def test_straight_line_log1p_of_the_em_folds(built):
+    """glm::log1p_wide (all branches of fdlibm's log1p for 0 < x < 1 as selects, used by the one-fold-per-lane
+    logsumexp of k_em_cta) == this host's log1p wherever log1p_wide_ok says so, and that is nearly everywhere."""
+    if not api.libm_exact():
+        pytest.skip("this host's libm is not glibc 2.39 / FMA")
+    import math
+    rng = np.random.default_rng(3)
+    xs = [np.exp(-rng.uniform(0, 45, 200000)), rng.uniform(0.40, 0.43, 100000), rng.uniform(0.9999, 1.0, 50000),
+          np.exp(-rng.uniform(0, 700, 50000)), rng.uniform(0, 1, 200000),
+          np.array([2.0 ** -54, 2.0 ** -29, np.nextafter(2.0 ** -54, 0), np.nextafter(2.0 ** -29, 0), math.sqrt(2) - 1, 1.0, 0.5, 0.41421356, 0.41422])]
+    edges = np.array([0x3c8fffff, 0x3c900000, 0x3e1fffff, 0x3e200000, 0x3fda8279, 0x3fda827a], dtype=np.uint64) << np.uint64(32)
+    xs.append(np.concatenate([(edges + np.uint64(k)).view(np.float64) for k in (0, 1, 0xffffffff)]))
+    x = np.concatenate(xs)
+    x = x[(x > 0) & (x <= 1)]
+    y = np.zeros_like(x); ok = np.zeros(x.shape[0], np.int32)
+    api.lib().colate_test_log1p_wide(x.shape[0], np.ascontiguousarray(x), y, ok)
+    want = np.array([math.log1p(float(v)) for v in x])      # libm's log1p (numpy's array log1p is its own SIMD code)
+    good = ok == 1
+    assert np.array_equal(y[good].view(np.int64), want[good].view(np.int64))
+    assert good.mean() > 0.9 and good[x < 0.41].all()
+    assert not ok[x == 1.0].any()
+
+
 def test_ages_epochs_and_age_bins_match_oracle(built):
     assert same(api.age_bins(), po.age_bins())
     for ta, ra, ypg in ((None, None, None), ("7000", "0", 28.0), ("1e4", "23000", 29.5), ("0", "500", None)):
