@@ -1325,10 +1325,10 @@ int run_em(colate_handle* h, int R, int E, int max_iter, const double* epochs_ho
     const int sms = h->sm_count;
     while (csize < 8 && R * csize * 2 <= sms) csize *= 2;
     if (csize == 8 && R * 16 * 2 <= sms) csize = 16;   // non-portable cluster size: one GPC (16-20 SMs) per replicate
-    // 19..37 replicates: clusters of 8 on k_em_split (two CTAs per SM) beat k_em's clusters of 4 (measured at R = 30:
-    // 59 ms against 73.5 ms, and 80 ms at one CTA per replicate; profiles/r01_em_phase_profile.md)
-    if (csize == 4 && R * 8 <= 2 * sms) csize = 8;
-    if (csize == 2) csize = 1;                         // 38..74 replicates: pairs of CTAs are slower than single CTAs (R = 60: 66.4 against 61.3 ms)
+    // up to 4 replicates: one GPC each (20.5 ms for 1001 iterations at E = 43); up to 9: clusters of 8, one CTA per SM
+    // (23 ms); from 10 on one CTA per replicate (k_em_cta: 31 ms for any count up to the number of SMs, against 59 ms
+    // for 30 replicates on clusters of 8 at two CTAs per SM; profiles/r02_em_throughput.md)
+    if (csize < 8) csize = 1;
   }
   if (csize != 1 && csize != 2 && csize != 4 && csize != 8 && csize != 16) csize = 1;
   // latency mode: one replicate over a cluster of 8 or 16 (k_em_split) when its per-CTA tables fit

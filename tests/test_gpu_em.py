@@ -137,7 +137,7 @@ def test_em_short_run_tight(handle):
 
 
 def test_em_throughput_mode_many_replicates(handle):
-    """Enough replicates to fill the GPU: one CTA per replicate (k_em), no cluster; spot-checked against the oracle."""
+    """Enough replicates to fill the GPU: one CTA per replicate (k_em_cta), no cluster; spot-checked against the oracle."""
     o = _block_stats()
     R = 80
     w = api.draw_block_weights(api.mt_seed(11), R, o["num_blocks"])
@@ -151,16 +151,16 @@ def test_em_throughput_mode_many_replicates(handle):
     assert len({tuple(x) for x in rates}) > R // 2      # the replicates really differ
 
 
-def test_em_mid_range_replicates_on_split_clusters(handle):
-    """19..37 replicates run as clusters of 8 on k_em_split, two CTAs per SM; spot-checked against the oracle."""
+@pytest.mark.parametrize("R", [7, 24])
+def test_em_mid_range_replicates(handle, R):
+    """5..9 replicates run as clusters of 8 on k_em_split, 10 and more one CTA each on k_em_cta; spot-checked against the oracle."""
     o = _block_stats()
-    R = 24
     w = api.draw_block_weights(api.mt_seed(12), R, o["num_blocks"])
     counts = po.stage2(w, o, 0.0)
     ep, _ = po.epochs_from_bins("3,7,0.2", 0.0, 28.0)
     init = np.full(len(ep), 1 / 20000.)
     rates, iters, ll = handle.stage3_em(R, ep, init, counts, max_iter=300)
-    for r in (0, 13, 23):
+    for r in (0, R // 2, R - 1):
         ro, it, llo = po.em_run(ep, init, counts[r], max_iter=300)
         assert iters[r] == it and _same(rates[r], ro) and _same(ll[r], llo)
     assert len({tuple(x) for x in rates}) > R // 2
