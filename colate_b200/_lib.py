@@ -63,6 +63,7 @@ SIGNATURES = {
     "colate_last_stage1_timing": (C.c_int, [VP, C.POINTER(Stage1Timing)]),
     "colate_set_option": (C.c_int, [VP, C.c_char_p, C.c_int64]),
     "colate_launch_count": (C.c_int64, [VP]),
+    "colate_last_stage1_extra_words": (C.c_int64, [VP]),
     "colate_mt_seed": (None, [C.c_uint32, u32]),
     "colate_mt_generate": (None, [u32, C.c_int64, u32]),
     "colate_draw_block_weights": (None, [u32, C.c_int, C.c_int, i32]),

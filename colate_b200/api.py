@@ -301,6 +301,10 @@ class Handle:
     def set_option(self, key: str, value: int):
         check(lib().colate_set_option(self._h, key.encode(), value))
 
+    def extra_words(self) -> int:
+        """Generator words the last stage-i call consumed beyond 200 per used row (redraws, coal.cpp:2279-2294)."""
+        return lib().colate_last_stage1_extra_words(self._h)
+
     def launch_count(self) -> int:
         return lib().colate_launch_count(self._h)
 

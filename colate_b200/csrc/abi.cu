@@ -35,6 +35,7 @@ int ensure_tables(colate_handle* h)
   CK(cudaMemcpyAsync(h->thrA.p, thrP, sizeof thrP, cudaMemcpyHostToDevice, h->stream));  // slot-indexed thresholds
   CK(cudaMemcpyAsync(h->lut.p, lut, sizeof lut, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->thr10.p, thr, sizeof thr, cudaMemcpyHostToDevice, h->stream));
+  h->thr185 = thr[NBINS];
   CK(cudaMemcpyAsync(h->d_agebin.p, ab, sizeof ab, cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->thr_ready = true;
@@ -68,6 +69,8 @@ int libm_self_check()
 // sites is queued (its verdict is read by colate_stage1_flags: COLATE_ERR_ORDER).
 int sites_replaced(colate_handle* h)
 {
+  int rc0 = ensure_tables(h);
+  if (rc0) return rc0;
   h->sites_set = true;
   h->flags_done = false;
   for (auto& g : h->genomes) { g.set = false; g.joined = false; g.has_mask = false; }
@@ -142,7 +145,7 @@ void colate_destroy(colate_handle* h)
                     &h->chr_used, &h->chr_blocks, &h->chr_block_base, &h->misc, &h->u_hdr, &h->u_eb2, &h->u_ews, &h->u_ewn, &h->u_cnt,
                     &h->u_blk, &h->blk_rank_start, &h->out_f, &h->out_n, &h->thrA, &h->lut, &h->d_scratch, &h->d_prof, &h->libm_tab, &h->ing_text, &h->ing_tile_cnt, &h->ing_tile_off, &h->ing_nl, &h->ing_status, &h->ing_fb,
                     &h->windows, &h->rng_stream, &h->mt_tail, &h->poly, &h->thr10, &h->d_counts, &h->d_blockstats, &h->d_weights, &h->d_epochs,
-                    &h->d_rates, &h->d_iters, &h->d_ll, &h->d_agebin, &h->d_tmp, &h->order_flag, &h->ing_raw};
+                    &h->d_rates, &h->d_iters, &h->d_ll, &h->d_agebin, &h->d_tmp, &h->order_flag, &h->ing_raw, &h->deep_rows};
   for (DevBuf* b : bufs) b->release();
   for (auto& g : h->genomes) {
     DevBuf* gb[] = {&g.bp, &g.aaf, &g.daf, &g.alleles, &g.chr_first, &g.chr_end, &g.mask_bits, &g.j_aaf, &g.j_daf, &g.j_prevbp, &g.j_flag};
@@ -270,6 +273,11 @@ int colate_stage1_flags(colate_handle* h, int target_slot, int reference_slot, i
     return fail(COLATE_ERR_ORDER, "positions of a .colate.in file are not ascending within a chromosome");
   h->n_used = misc[0];
   h->n_blocks_local = (int)misc[1];
+  h->n_deep = misc[4];
+  if (misc[3])
+    return fail(COLATE_ERR_AGE_RANGE, "a used row cannot be processed by the reference either: age_begin <= 0 with an age interval beyond "
+                                      "the age grid (~9.3e6 generations; out-of-bounds write at coal.cpp:2269), or age_begin itself beyond it "
+                                      "(the rejection loop of coal.cpp:2279-2294 never ends)");
   h->tgt_slot = target_slot;
   h->ref_slot = reference_slot;
   h->flags_done = true;
@@ -284,6 +292,54 @@ int colate_stage1_flags(colate_handle* h, int target_slot, int reference_slot, i
   return 0;
 }
 
+// Rows with age_begin > 0 whose age interval reaches past the age grid (h->n_deep of them, coal.cpp:2279-2294): every draw
+// whose bin reaches 185 is redrawn, so such a row consumes 200 + 2 * redraws engine words and every later row starts that
+// much later in the stream.  The redraw count depends on the stream itself, hence strictly in row order: the used rows are
+// cut into the runs BETWEEN deep rows; a run is sampled by the normal kernels from the generator state in front of it (no
+// long jump: the state is carried along), the deep row in between is walked on the host (it is one row: ~100 + redraws draws).
+// The exact replay then sees ordinary count rows.  win: state window in front of the first row, advanced to behind the last.
+static int sample_segmented(colate_handle* h, uint32_t* win)
+{
+  cudaStream_t s = h->stream;
+  const int64_t nu = h->n_used, nd = h->n_deep;
+  std::vector<int64_t> deep((size_t)nd);
+  int64_t misc[8];
+  CK(cudaMemcpyAsync(misc, h->misc.p, 64, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(deep.data(), h->deep_rows.p, (size_t)nd * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (misc[5] != nd) return fail(COLATE_ERR_STATE, "rejection-sampling rows: the flag pass and the compaction disagree");
+  std::sort(deep.begin(), deep.end());
+  CK(cudaMemsetAsync(h->u_cnt.p, 0, (size_t)((nu + 31) / 32) * 32 * 192, s));
+  h->extra_words = 0;
+  int64_t r = 0;
+  for (int64_t k = 0; k <= nd; k++) {
+    const int64_t f = k < nd ? deep[(size_t)k] : nu;
+    const int64_t len = f - r;
+    if (len > 0) {
+      uint32_t* stream_local = nullptr;
+      uint32_t after[COLATE_MT_WORDS];
+      int rc = run_mt_stream(h, win, 0, 200 * len, pick_chunk_log2(len), &stream_local, after, true);
+      if (rc) return rc;
+      if ((rc = run_sample_rows(h, stream_local, r, len))) return rc;
+      CK(cudaStreamSynchronize(s));     // the stream buffer and the scratch tiles are reused by the next run
+      memcpy(win, after, sizeof after);
+    }
+    if (f < nu) {
+      double hdr[4];
+      CK(cudaMemcpy(hdr, h->u_hdr.as<double>() + 4 * f, 32, cudaMemcpyDeviceToHost));
+      uint8_t cnt[192];
+      const int64_t redraws = sample_deep_row_host(win, hdr[1], hdr[0] * 0x1p64, cnt, (int64_t)1 << 26);
+      if (redraws < 0)
+        return fail(COLATE_ERR_AGE_RANGE, "a row's age interval lies almost entirely beyond the age grid: more than 2^26 redraws (coal.cpp:2279-2294)");
+      h->extra_words += 2 * redraws;
+      int rc = run_put_count_row(h, f, cnt);
+      if (rc) return rc;
+    }
+    r = f + 1;
+  }
+  return 0;
+}
+
 int colate_stage1_sample(colate_handle* h, const uint32_t* mt_state, int64_t used_rank_base, int block_base,
                          double* block_stats, int64_t* block_tallies, uint32_t* mt_state_out)
 {
@@ -294,13 +350,26 @@ int colate_stage1_sample(colate_handle* h, const uint32_t* mt_state, int64_t use
   cudaStream_t s = h->stream;
   const int64_t nu = h->n_used;
   const int nb = h->n_blocks_local;
-  uint32_t* stream_local = nullptr;
   uint32_t win_after[COLATE_MT_WORDS];
-  CK(cudaEventRecord(h->ev[6], s));
-  int rc = run_mt_stream(h, mt_state, 200 * used_rank_base, 200 * nu, pick_chunk_log2(nu), &stream_local, nullptr, true);
-  if (rc) return rc;
-  CK(cudaEventRecord(h->ev[7], s));
-  if ((rc = run_sample(h, stream_local, block_base))) return rc;
+  int rc;
+  h->extra_words = 0;
+  if (h->n_deep == 0) {
+    uint32_t* stream_local = nullptr;
+    CK(cudaEventRecord(h->ev[6], s));
+    if ((rc = run_mt_stream(h, mt_state, 200 * used_rank_base, 200 * nu, pick_chunk_log2(nu), &stream_local, nullptr, true))) return rc;
+    CK(cudaEventRecord(h->ev[7], s));
+    if ((rc = run_compact(h))) return rc;
+    if ((rc = run_sample_rows(h, stream_local, 0, nu))) return rc;
+  } else {
+    // rejection-sampling rows present: runs between them in row order (sample_segmented)
+    CK(cudaEventRecord(h->ev[6], s));
+    uint32_t* dummy = nullptr;
+    if ((rc = run_mt_stream(h, mt_state, 200 * used_rank_base, 0, 3, &dummy, win_after, true))) return rc;   // state in front of this handle's rows
+    CK(cudaEventRecord(h->ev[7], s));
+    if ((rc = run_compact(h))) return rc;
+    if ((rc = sample_segmented(h, win_after))) return rc;
+  }
+  if ((rc = run_replay(h))) return rc;
   int64_t misc[8];
   CK(cudaMemcpyAsync(misc, h->misc.p, 64, cudaMemcpyDeviceToHost, s));
   // (host or device destinations: unified addressing resolves the direction)
@@ -310,15 +379,15 @@ int colate_stage1_sample(colate_handle* h, const uint32_t* mt_state, int64_t use
   h->sampled = true;
   if (misc[3]) return fail(COLATE_ERR_AGE_RANGE, "a used row has an age bin >= 185 (age_end beyond ~9.3e6 generations)");
   if (mt_state_out) {
-    if ((rc = mt_window_after(h, win_after))) return rc;
+    if (h->n_deep == 0) { if ((rc = mt_window_after(h, win_after))) return rc; }
     memcpy(mt_state_out, win_after, sizeof win_after);
   }
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]); h->timing.rng_ms = ms;
   cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->timing.compact_ms = ms;
-  cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); h->timing.sample_ms = ms;   // k_sample alone
+  cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); h->timing.sample_ms = ms;   // k_sample alone (with rejection-sampling rows: all the runs)
   cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->timing.replay_ms = ms;
-  h->timing.rng_words = 200 * nu;
+  h->timing.rng_words = 200 * nu + h->extra_words;
   h->timing.total_ms = h->timing.join_ms + h->timing.flags_ms + h->timing.rng_ms + h->timing.compact_ms + h->timing.sample_ms +
                        h->timing.replay_ms;
   return 0;
@@ -349,6 +418,8 @@ int colate_set_option(colate_handle* h, const char* key, int64_t value)
 }
 
 int64_t colate_launch_count(colate_handle* h) { return h ? h->launches : 0; }
+
+int64_t colate_last_stage1_extra_words(colate_handle* h) { return h ? h->extra_words : 0; }
 
 int colate_last_stage1_timing(colate_handle* h, colate_stage1_timing* out)
 {

@@ -73,7 +73,10 @@ struct colate_handle {
   colate::DevBuf candR, candT, use, word_rank, scan_tmp;
   colate::DevBuf chr_used, chr_blocks, chr_block_base, misc;  // misc: small device scalars
   colate::DevBuf u_hdr, u_eb2, u_ews, u_ewn, u_blk, u_cnt;   // compacted used rows, per-row sample counts
-  colate::DevBuf blk_rank_start, out_f, out_n;
+  colate::DevBuf blk_rank_start, out_f, out_n, deep_rows;
+  int64_t n_deep = 0;           // used rows of the current pair that take the rejection-sampling path (coal.cpp:2279-2294)
+  int64_t extra_words = 0;      // generator words the last stage-i call consumed beyond 200 per used row (redraws)
+  double thr185 = 0.0;          // 10 * age from which the age bin is 185 (thr10[185])
   colate::DevBuf windows, rng_stream, mt_tail, poly, thr10, thrA, lut;
   int sm_count = 148;
   std::vector<int64_t> h_chr_used;
@@ -116,7 +119,10 @@ int run_check_genome(colate_handle* h, int slot);
 // abi.cu
 int sites_replaced_ext(colate_handle* h);
 int genome_replaced_ext(colate_handle* h, int slot);
-int run_sample(colate_handle* h, const uint32_t* stream_local, int block_base_unused);
+int run_compact(colate_handle* h);
+int run_sample_rows(colate_handle* h, const uint32_t* stream_local, int64_t row0, int64_t n_rows);
+int run_put_count_row(colate_handle* h, int64_t row, const uint8_t* cnt192_host);
+int run_replay(colate_handle* h);
 int run_test_bin_fast(colate_handle* h, int n, const double* a_host, int32_t* fast_host, int32_t* exact_host);
 int run_test_bin_sweep(colate_handle* h, uint32_t lo_bits, uint32_t hi_bits, uint64_t* out3_host);
 // kernels_mt.cu

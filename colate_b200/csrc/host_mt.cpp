@@ -132,6 +132,35 @@ void draw_block_weights(uint32_t* w, int R, int num_blocks, int32_t* weights)
   g.finish(consumed, before);
 }
 
+// One used row with age_begin > 0 whose age interval reaches past the age grid, exactly as the reference's loop
+// at coal.cpp:2279-2294 walks it: draw (std::uniform_real_distribution<double>(0,1) = generate_canonical: two
+// engine words, (x1 + x2 * 2^32) / 2^64 with one rounding, clamped below 1), sampled_age = U * len + age_begin, bin
+// = max(0,(int)round(log(10 * age) * 10) + 1); a draw whose bin reaches 185 is redrawn and does not count.
+// cnt[slot] = accepted samples per bin (slot = bin), 100 in total.  Advances the state window by the words consumed
+// and returns the number of redraws; -1: more than `max_redraws` (the interval barely touches the grid).
+int64_t sample_deep_row_host(uint32_t* w, double age_begin, double len, uint8_t* cnt /*[192]*/, int64_t max_redraws)
+{
+  uint32_t before[624];
+  memcpy(before, w, sizeof before);
+  WindowGen g(w);
+  int64_t consumed = 0, redraws = 0;
+  memset(cnt, 0, 192);
+  int j = 0;
+  while (j < COLATE_NUM_SAMPLES) {
+    const uint32_t x1 = g.next(), x2 = g.next();
+    consumed += 2;
+    double u = ((double)x1 + (double)x2 * 4294967296.0) / 18446744073709551616.0;
+    if (u >= 1.0) u = 0x1.fffffffffffffp-1;
+    const double a = u * len + age_begin;
+    const int b = bin_of_x10_host(10.0 * a);
+    if (b >= NBINS) { if (++redraws > max_redraws) return -1; continue; }
+    cnt[b]++;
+    j++;
+  }
+  g.finish(consumed, before);
+  return redraws;
+}
+
 // ---- GF(2)[t] ------------------------------------------------------------------------
 static const int DEG = 19937;
 static const int NW64 = 312;  // 19968 bits

@@ -512,7 +512,10 @@ int colate_ingest_fetch(colate_handle* h, int64_t row0, int64_t n_rows, int32_t*
   if (pos) CK(cudaMemcpy(pos, h->pos.as<int32_t>() + row0, n_rows * 4, cudaMemcpyDeviceToHost));
   if (age_begin) CK(cudaMemcpy(age_begin, h->ab.as<float>() + row0, n_rows * 4, cudaMemcpyDeviceToHost));
   if (age_end) CK(cudaMemcpy(age_end, h->ae.as<float>() + row0, n_rows * 4, cudaMemcpyDeviceToHost));
-  if (meta) CK(cudaMemcpy(meta, h->meta.as<uint32_t>() + row0, n_rows * 4, cudaMemcpyDeviceToHost));
+  if (meta) {
+    CK(cudaMemcpy(meta, h->meta.as<uint32_t>() + row0, n_rows * 4, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n_rows; i++) meta[i] &= ~6u;   // bits 1-2 are the handle's own age-range marks (k_check_sites), not part of colate_site_meta()
+  }
   return 0;
 }
 

@@ -16,6 +16,8 @@
 namespace colate {
 
 constexpr int SCAN_ITEMS = 8;     // bitmap words per thread in the rank scan
+constexpr int TS_ROWS_C = 32;      // used rows per count tile (== TS_ROWS below)
+constexpr int ROW_BYTES_C = 192;
 constexpr int SCAN_THREADS = 256;
 
 // ------------------------------------------------------------------------------------------
@@ -95,11 +97,26 @@ __global__ void k_join(int64_t n_site, int n_chr, const int64_t* __restrict__ si
 // (coal.cpp:2184-2217) only on ascending positions: .mut rows ascending within a chromosome, .colate.in records
 // ascending within the record range the reader can reach on a chromosome.  One pass each; equal neighbours are fine.
 __global__ void k_check_sites(int64_t n_site, int n_chr, const int64_t* __restrict__ site_off, const int32_t* __restrict__ pos,
+                              const float* __restrict__ ab, const float* __restrict__ ae, uint32_t* __restrict__ meta, double thr185,
                               int* __restrict__ flag)
 {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m == 0 || m >= n_site) return;
-  if (pos[m] < pos[m - 1] && site_off[chr_of(site_off, n_chr, m)] != m) *flag = 1;   // a descent is legal only at a chromosome start
+  if (m >= n_site) return;
+  if (m > 0 && pos[m] < pos[m - 1] && site_off[chr_of(site_off, n_chr, m)] != m) *flag = 1;   // a descent is legal only at a chromosome start
+  // Age interval against the end of the age grid (bin 185 starts where 10 * age reaches thr185), from the row alone:
+  //   bit 1  age_begin > 0 and the interval reaches past the grid: the reference redraws every sample beyond it
+  //          (coal.cpp:2279-2294) -- the row takes the rejection-sampling path (abi.cu: sample_segmented)
+  //   bit 2  the reference cannot process the row: age_begin <= 0 with the interval past the grid (it writes past the
+  //          end of the histogram, coal.cpp:2269) or age_begin itself past the grid (its loop never ends)
+  uint32_t mt = meta[m] & ~6u;
+  if (mt & 1u) {
+    const double b = fmax((double)ab[m], 0.0), e = (double)ae[m];   // coal.cpp:2225 with ref_age == 0 (coal.cpp:2075)
+    const bool past = __dmul_rn(10.0, e) >= thr185;
+    if (b > 0.0) {
+      if (__dmul_rn(10.0, b) >= thr185) mt |= 4u; else if (past) mt |= 2u;
+    } else if (past) mt |= 4u;
+  }
+  meta[m] = mt;
 }
 __global__ void k_check_genome(int64_t n_rec, int n_chr, const int64_t* __restrict__ chr_first, const int64_t* __restrict__ chr_end,
                                const int32_t* __restrict__ bp, int* __restrict__ flag)
@@ -134,7 +151,8 @@ template <bool IS_REF>
 __global__ void k_ok(int64_t n_site, int n_chr, const int64_t* __restrict__ site_off, const int32_t* __restrict__ pos,
                      const uint32_t* __restrict__ in_bits, const int32_t* __restrict__ j_aaf,
                      const int32_t* __restrict__ j_daf, const int32_t* __restrict__ j_prevbp,
-                     const uint8_t* __restrict__ j_flag, uint32_t* __restrict__ out_bits)
+                     const uint8_t* __restrict__ j_flag, uint32_t* __restrict__ out_bits, const uint32_t* __restrict__ meta,
+                     int64_t* __restrict__ misc)
 {
   int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool ok = false;
@@ -148,6 +166,11 @@ __global__ void k_ok(int64_t n_site, int n_chr, const int64_t* __restrict__ site
         ok = prev_cand_pos <= j_prevbp[m];
       }
     }
+  }
+  if (!IS_REF && ok) {   // a USED row: does it need the rejection path, or is it one the reference cannot process?
+    const uint32_t mt = meta[m];
+    if (mt & 4u) misc[3] = 1;
+    if (mt & 2u) atomicAdd((unsigned long long*)&misc[4], 1ull);
   }
   uint32_t b = __ballot_sync(0xffffffffu, ok);
   if ((threadIdx.x & 31) == 0 && m < n_site) out_bits[m >> 5] = b;
@@ -235,7 +258,8 @@ __global__ void k_compact(int64_t n_site, int n_chr, const int64_t* __restrict__
                           const int32_t* __restrict__ r_aaf, const int32_t* __restrict__ r_daf,
                           const double* __restrict__ thr10,
                           double4* __restrict__ hdr, uint8_t* __restrict__ e_b2, double* __restrict__ e_ws,
-                          double* __restrict__ e_wn, int32_t* __restrict__ u_blk, int64_t* __restrict__ misc)
+                          double* __restrict__ e_wn, int32_t* __restrict__ u_blk, int64_t* __restrict__ misc,
+                          const uint32_t* __restrict__ meta, int64_t* __restrict__ deep_rows, int64_t deep_cap)
 {
   // thread = used row (rank r): one row in eight is used, so a thread per site would leave the warps of the
   // division-heavy part below nearly empty.  Site of rank r: the last bitmap word whose exclusive rank is <= r
@@ -280,8 +304,29 @@ __global__ void k_compact(int64_t n_site, int n_chr, const int64_t* __restrict__
   }
   e_b2[r] = b2; e_ws[r] = ws; e_wn[r] = wn;
   u_blk[r] = chr_block_base[c] + (pos[m] - 1) / COLATE_BLOCK_BASES;
-  // the reference writes out of bounds / rejection-samples once a bin index reaches 185
-  if (__dmul_rn(10.0, (double)e) >= thr10[NBINS]) misc[3] = 1;
+  // rows whose samples the reference redraws when they fall past the age grid (meta bit 1, k_check_sites): listed
+  // (in any order; the host sorts the few of them) for the rejection-sampling path
+  if (meta[m] & 2u) {
+    const unsigned long long k = atomicAdd((unsigned long long*)&misc[5], 1ull);
+    if ((int64_t)k < deep_cap) deep_rows[k] = r;
+  }
+}
+
+// rejection-sampling path: the count rows of a segment sampled into scratch tiles -> their places in the tile array of all
+// used rows ([tile][slot][row % 32] bytes); and one count row computed on the host
+__global__ void k_scatter_count_rows(const uint8_t* __restrict__ seg_tiles, int64_t n_rows, int64_t row0, uint8_t* __restrict__ cnt_tiles)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (row of the segment, slot)
+  if (i >= n_rows * ROW_BYTES_C) return;
+  const int64_t j = i / ROW_BYTES_C, r = row0 + j;
+  const int slot = (int)(i - j * ROW_BYTES_C);
+  cnt_tiles[(r / TS_ROWS_C) * (ROW_BYTES_C * TS_ROWS_C) + slot * TS_ROWS_C + (r % TS_ROWS_C)] =
+      seg_tiles[(j / TS_ROWS_C) * (ROW_BYTES_C * TS_ROWS_C) + slot * TS_ROWS_C + (j % TS_ROWS_C)];
+}
+__global__ void k_put_count_row(const uint8_t* __restrict__ row_cnt /*[192]*/, int64_t r, uint8_t* __restrict__ cnt_tiles)
+{
+  const int slot = threadIdx.x;
+  if (slot < ROW_BYTES_C) cnt_tiles[(r / TS_ROWS_C) * (ROW_BYTES_C * TS_ROWS_C) + slot * TS_ROWS_C + (r % TS_ROWS_C)] = row_cnt[slot];
 }
 
 // rank range of every genomic block
@@ -381,6 +426,7 @@ constexpr int SUB_WORDS = 20;                 // words per unrolled step = 10 sa
 constexpr int N_CHUNK = 200 / CH_WORDS;
 constexpr int ROW_BYTES = 192;         // per-row sample counts, one byte per count slot (188 used)
 constexpr int TILE_BYTES = ROW_BYTES * TS_ROWS;   // count tile of 32 rows: [slot][row] bytes
+static_assert(TS_ROWS == TS_ROWS_C && ROW_BYTES == ROW_BYTES_C, "count-tile geometry");
 #ifndef S2_WARPS_
 #define S2_WARPS_ 4
 #endif
@@ -798,8 +844,9 @@ int run_join(colate_handle* h, int slot)
 
 int run_check_sites(colate_handle* h)
 {
-  if (h->n_site > 1) {
+  if (h->n_site > 0) {
     k_check_sites<<<grid_for(h->n_site, 256), 256, 0, h->stream>>>(h->n_site, h->n_chr, h->site_off.as<int64_t>(), h->pos.as<int32_t>(),
+                                                                   h->ab.as<float>(), h->ae.as<float>(), h->meta.as<uint32_t>(), h->thr185,
                                                                    h->order_flag.as<int>());
     h->launches += 1;
     CK(cudaGetLastError());
@@ -840,10 +887,10 @@ int run_flags(colate_handle* h, int tslot, int rslot)
                                 R.has_mask ? R.mask_bits.as<uint32_t>() : nullptr, h->candR.as<uint32_t>());
     k_ok<true><<<grid, 256, 0, s>>>(n, h->n_chr, h->site_off.as<int64_t>(), h->pos.as<int32_t>(), h->candR.as<uint32_t>(),
                                     R.j_aaf.as<int32_t>(), R.j_daf.as<int32_t>(), R.j_prevbp.as<int32_t>(), R.j_flag.as<uint8_t>(),
-                                    h->candT.as<uint32_t>());
+                                    h->candT.as<uint32_t>(), h->meta.as<uint32_t>(), h->misc.as<int64_t>());
     k_ok<false><<<grid, 256, 0, s>>>(n, h->n_chr, h->site_off.as<int64_t>(), h->pos.as<int32_t>(), h->candT.as<uint32_t>(),
                                      T.j_aaf.as<int32_t>(), T.j_daf.as<int32_t>(), T.j_prevbp.as<int32_t>(), T.j_flag.as<uint8_t>(),
-                                     h->use.as<uint32_t>());
+                                     h->use.as<uint32_t>(), h->meta.as<uint32_t>(), h->misc.as<int64_t>());
     k_popc_blocksum<<<nsb, SCAN_THREADS, 0, s>>>(h->use.as<uint32_t>(), nw, h->scan_tmp.as<uint32_t>());
     k_scan_sums<<<1, 32, 0, s>>>(h->scan_tmp.as<uint32_t>(), nsb, total);
     k_word_rank<<<nsb, SCAN_THREADS, 0, s>>>(h->use.as<uint32_t>(), nw, h->scan_tmp.as<uint32_t>(), total, h->word_rank.as<uint32_t>());
@@ -858,11 +905,10 @@ int run_flags(colate_handle* h, int tslot, int rslot)
   return 0;
 }
 
-// compaction + sampling + exact per-block replay; needs h->n_used / n_blocks_local
-int run_sample(colate_handle* h, const uint32_t* stream_local, int)
+// used rows -> dense records in rank order, block ranges; needs h->n_used / n_blocks_local
+int run_compact(colate_handle* h)
 {
   const int64_t n = h->n_site, nu = h->n_used;
-  const int nb = h->n_blocks_local;
   GenomeDev& T = h->genomes[h->tgt_slot];
   GenomeDev& R = h->genomes[h->ref_slot];
   cudaStream_t s = h->stream;
@@ -872,6 +918,7 @@ int run_sample(colate_handle* h, const uint32_t* stream_local, int)
   CK(h->u_blk.ensure(un * 4 + 64)); CK(h->u_cnt.ensure(un32 * ROW_BYTES + 64));
   CK(h->blk_rank_start.ensure((MAX_BLOCKS + 2) * 8));
   CK(h->out_f.ensure((size_t)MAX_BLOCKS * 4 * NBINS * 8)); CK(h->out_n.ensure((size_t)MAX_BLOCKS * 3 * NBINS * 8));
+  CK(h->deep_rows.ensure((size_t)std::max<int64_t>(h->n_deep, 1) * 8));
   if (un32 > (size_t)nu)   // header rows between the last used row and the end of its tile: read by k_replay, never written
     CK(cudaMemsetAsync(h->u_hdr.as<double4>() + nu, 0, (un32 - (size_t)nu) * 32, s));
   CK(cudaEventRecord(h->ev[2], s));
@@ -881,28 +928,69 @@ int run_sample(colate_handle* h, const uint32_t* stream_local, int)
                                                h->chr_block_base.as<int32_t>(), T.j_aaf.as<int32_t>(), T.j_daf.as<int32_t>(),
                                                R.j_aaf.as<int32_t>(), R.j_daf.as<int32_t>(), h->thr10.as<double>(),
                                                h->u_hdr.as<double4>(), h->u_eb2.as<uint8_t>(), h->u_ews.as<double>(),
-                                               h->u_ewn.as<double>(), h->u_blk.as<int32_t>(), h->misc.as<int64_t>());
+                                               h->u_ewn.as<double>(), h->u_blk.as<int32_t>(), h->misc.as<int64_t>(),
+                                               h->meta.as<uint32_t>(), h->deep_rows.as<int64_t>(), h->n_deep);
     h->launches += 1;
   }
   k_block_ranges<<<1, 512, 0, s>>>(h->u_blk.as<int32_t>(), h->misc.as<int64_t>(), h->blk_rank_start.as<int64_t>());
   h->launches += 1;
   CK(cudaEventRecord(h->ev[3], s));
-  if (nu > 0) {
-    const size_t smem = sizeof(SampleWarp) * S2_WARPS;
-    // all of the SM's 228 KB as shared memory (the kernel's only L1 traffic is one 16 B header per row): the
-    // resident warps, and with them the bytes in flight, are bounded by the rings and count tiles
-    CK(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(k_sample, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    const int64_t n_tile = (nu + TS_ROWS - 1) / TS_ROWS;
-    int per_sm = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sample, S2_WARPS * 32, smem));
-    per_sm = std::max(1, per_sm);
-    if (const char* e = getenv("COLATE_SAMPLE_CTAS_PER_SM")) per_sm = std::max(1, atoi(e));
-    const int grid = (int)std::min<int64_t>((n_tile + S2_WARPS - 1) / S2_WARPS, (int64_t)h->sm_count * per_sm);
-    k_sample<<<grid, S2_WARPS * 32, smem, s>>>(stream_local, nu, h->u_hdr.as<double4>(), h->thrA.as<double>(), h->lut.as<uint16_t>(),
-                                               h->u_cnt.as<uint8_t>());
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// k_sample over used rows [row0, row0 + n_rows) whose generator words start at `stream_local` (tile order relative to
+// row0).  row0 == 0 and n_rows == n_used: straight into the count tiles; otherwise (rejection-sampling path) into scratch
+// tiles and from there to the rows' places.
+int run_sample_rows(colate_handle* h, const uint32_t* stream_local, int64_t row0, int64_t n_rows)
+{
+  cudaStream_t s = h->stream;
+  if (n_rows <= 0) return 0;
+  const bool whole = row0 == 0 && n_rows == h->n_used;
+  uint8_t* tiles = h->u_cnt.as<uint8_t>();
+  if (!whole) {
+    CK(h->d_tmp.ensure((size_t)((n_rows + TS_ROWS - 1) / TS_ROWS) * TILE_BYTES + 64));
+    tiles = h->d_tmp.as<uint8_t>();
+  }
+  const size_t smem = sizeof(SampleWarp) * S2_WARPS;
+  // all of the SM's 228 KB as shared memory (the kernel's only L1 traffic is one 16 B header per row): the
+  // resident warps, and with them the bytes in flight, are bounded by the rings and count tiles
+  CK(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(k_sample, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  const int64_t n_tile = (n_rows + TS_ROWS - 1) / TS_ROWS;
+  int per_sm = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sample, S2_WARPS * 32, smem));
+  per_sm = std::max(1, per_sm);
+  if (const char* e = getenv("COLATE_SAMPLE_CTAS_PER_SM")) per_sm = std::max(1, atoi(e));
+  const int grid = (int)std::min<int64_t>((n_tile + S2_WARPS - 1) / S2_WARPS, (int64_t)h->sm_count * per_sm);
+  k_sample<<<grid, S2_WARPS * 32, smem, s>>>(stream_local, n_rows, h->u_hdr.as<double4>() + row0, h->thrA.as<double>(), h->lut.as<uint16_t>(), tiles);
+  h->launches += 1;
+  if (!whole) {
+    k_scatter_count_rows<<<grid_for(n_rows * ROW_BYTES, 256), 256, 0, s>>>(tiles, n_rows, row0, h->u_cnt.as<uint8_t>());
     h->launches += 1;
   }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// one count row computed on the host (a rejection-sampled row) -> its place in the count tiles
+int run_put_count_row(colate_handle* h, int64_t row, const uint8_t* cnt192_host)
+{
+  cudaStream_t s = h->stream;
+  CK(h->d_scratch.ensure(256));
+  CK(cudaMemcpyAsync(h->d_scratch.p, cnt192_host, ROW_BYTES, cudaMemcpyHostToDevice, s));
+  k_put_count_row<<<1, ROW_BYTES, 0, s>>>(h->d_scratch.as<uint8_t>(), row, h->u_cnt.as<uint8_t>());
+  h->launches += 1;
+  CK(cudaStreamSynchronize(s));   // the host row buffer is the caller's local; d_scratch is reused by the next row
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// exact per-block replay of the count rows
+int run_replay(colate_handle* h)
+{
+  cudaStream_t s = h->stream;
+  const int nb = h->n_blocks_local;
   CK(cudaEventRecord(h->ev[4], s));
   if (nb > 0) {
     k_replay<<<dim3(nb, 3), RP_THREADS, 0, s>>>(h->blk_rank_start.as<int64_t>(), h->u_cnt.as<uint8_t>(), h->u_hdr.as<double4>(),

@@ -84,6 +84,9 @@ class CudaBackend:
                                         stats_t.data_ptr() + block_base * 4 * NBINS * 8 if n_blocks else None,
                                         tallies_t.data_ptr() + block_base * 3 * NBINS * 8 if n_blocks else None)
 
+    def extra_words(self):
+        return self.h.extra_words()
+
     def bootstrap_dev(self, weights, stats_t, num_blocks, age):
         self.h.stage2_bootstrap_dev(weights, stats_t.data_ptr(), num_blocks, age)
 
@@ -146,6 +149,15 @@ def stage1_sharded(backend, seed_state: np.ndarray, device="cuda"):
         if n_local:
             pad[block_base:block_base + n_local] = torch.from_numpy(np.ascontiguousarray(stats[:n_local])).to(device)
             pad_n[block_base:block_base + n_local] = torch.from_numpy(np.ascontiguousarray(tallies[:n_local])).to(device)
+    if hasattr(backend, "extra_words"):
+        # rows the reference rejection-samples (coal.cpp:2279-2294) consume extra generator words: the stream offsets of
+        # the ranks behind would depend on them -- such inputs run on one GPU
+        ex = torch.tensor([backend.extra_words()], dtype=torch.int64, device=device)
+        dist.all_reduce(ex, op=dist.ReduceOp.MAX)
+        _log("all_reduce(max)", ex)
+        if int(ex.item()) != 0:
+            raise api._lib.ColateError(-2, "rows with redrawn samples (age interval beyond the age grid, coal.cpp:2279-2294) "
+                                           "cannot be sharded by chromosome: run this input on one GPU")
     dist.all_reduce(pad, op=dist.ReduceOp.SUM)                 # disjoint supports: x + 0.0 == x
     dist.all_reduce(pad_n, op=dist.ReduceOp.SUM)
     _log("all_reduce(sum)", pad); _log("all_reduce(sum)", pad_n)

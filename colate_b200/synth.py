@@ -117,6 +117,18 @@ def make_sites(seed: int, rows_per_chr, chrom_len, chr_names=None, weird: float 
     return Sites(chr_names, off, pos, ab, ae, flipped, n_branch, anc, der, odd, list(chrom_len))
 
 
+def add_deep_rows(sites: Sites, seed: int, frac: float = 0.02) -> np.ndarray:
+    """Gives a fraction of the rows age intervals that reach past the age grid (bin 185 starts at ~9.3e6 generations)
+    with age_begin > 0: for such rows the reference redraws every sample that falls beyond the grid (coal.cpp:2279-2294),
+    consuming two more engine words per redraw.  Returns the indices of the modified rows."""
+    rng = np.random.default_rng(seed)
+    idx = np.nonzero(rng.random(sites.n) < frac)[0]
+    ab = rng.uniform(2e6, 8.5e6, idx.shape[0])
+    sites.age_begin[idx] = ab.astype(np.float32)
+    sites.age_end[idx] = (ab + _loguniform(rng, 5e5, 4e7, idx.shape[0])).astype(np.float32)
+    return idx
+
+
 def make_genome(seed: int, sites: Sites, p_present: float = 0.7, mean_extra_reads: float = 1.0,
                 p_derived: float = 0.3, weird: float = 0.0) -> Genome:
     """Record present w.p. ``p_present``; N = 1 + floor(Exp(mean_extra_reads)) reads, each derived

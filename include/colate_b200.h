@@ -31,8 +31,9 @@ extern "C" {
 typedef enum {
   COLATE_OK = 0,
   COLATE_ERR_ARG = -1,        /* bad argument / inconsistent sizes                        */
-  COLATE_ERR_AGE_RANGE = -2,  /* a used row has age bin >= 185: the reference writes out of */
-                              /* bounds there (coal.cpp:2269) / rejection-samples (2289)   */
+  COLATE_ERR_AGE_RANGE = -2,  /* a used row the reference cannot process: age_begin <= 0 and  */
+                              /* age bin >= 185 (it writes out of bounds, coal.cpp:2269), or */
+                              /* age_begin itself in bin >= 185 (its loop 2279-2294 never ends) */
   COLATE_ERR_BLOCKS = -3,     /* more than 500 genomic blocks (reference overruns, 3140)   */
   COLATE_ERR_CUDA = -4,       /* CUDA runtime error or no usable device                    */
   COLATE_ERR_IO = -5,         /* unreadable / malformed input file                         */
@@ -106,7 +107,8 @@ int colate_stage1_flags(colate_handle* h, int target_slot, int reference_slot,
  *       age_shared_emp / age_notshared_emp, for blocks block_base .. block_base+n_blocks-1
  *   block_tallies[n_blocks][3][185] int64: samples added to shared / notshared, rows added to emp
  *   mt_state_out[624]  state window after 200*(used_rank_base+n_used) words (may alias mt_state)
- * Returns COLATE_ERR_AGE_RANGE if a used row's age bin reaches 185. */
+ * Rows with age_begin > 0 whose age interval reaches past the age grid are rejection-sampled as the reference does
+ * (coal.cpp:2279-2294: 200 + 2 * redraws engine words), in row order with the redraws walked on the host. */
 int colate_stage1_sample(colate_handle* h, const uint32_t* mt_state, int64_t used_rank_base,
                          int block_base, double* block_stats, int64_t* block_tallies,
                          uint32_t* mt_state_out);
@@ -163,6 +165,10 @@ int colate_last_stage1_timing(colate_handle* h, colate_stage1_timing* out);
 int colate_set_option(colate_handle* h, const char* key, int64_t value);
 /* Kernels launched on this handle since creation (for launch accounting). */
 int64_t colate_launch_count(colate_handle* h);
+/* Generator words the last colate_stage1 / colate_stage1_sample call consumed beyond 200 per used row: the redraws of
+ * the reference's rejection sampling (coal.cpp:2279-2294; rows with age_begin > 0 whose interval reaches past the age
+ * grid).  A chromosome-sharded job must see 0 on every rank (a later rank's stream offset would depend on it). */
+int64_t colate_last_stage1_extra_words(colate_handle* h);
 
 /* ---- host-side pieces of the path (no GPU needed) ------------------------------------ */
 /* std::mt19937::seed(seed) -> state window (coal.cpp:3157-3162). */

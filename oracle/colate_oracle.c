@@ -208,8 +208,10 @@ static int stream_on_chr(const stream_state* s, int chr) { return s->loaded && s
  *   n_shared, n_notshared, n_emp : [500][185] int64 sample / site tallies
  *   n_used : [500] int64 used rows per block
  * Returns num_blocks (coal.cpp:2319), or a negative error:
- *   -2 a used row has bin(age_end) >= 185 (reference writes out of bounds /
- *      rejection-samples, coal.cpp:2269, 2289) -- rejected, see DESIGN.md
+ *   -2 a used row with age_begin <= 0 has bin(age_end) >= 185 (the reference writes out of bounds,
+ *      coal.cpp:2269) or a used row has bin(age_begin) >= 185 (the rejection loop of coal.cpp:2279-2294
+ *      never ends) -- rejected, see DESIGN.md.  Rows with age_begin > 0 and bin(age_end) >= 185 are
+ *      rejection-sampled exactly as the reference does.
  *   -3 more than 500 blocks (reference overruns its 500 vectors, coal.cpp:3140)
  */
 int oracle_stage1(int n_chr, const int64_t* site_off /*[n_chr+1]*/,
@@ -289,7 +291,11 @@ int oracle_stage1(int n_chr, const int64_t* site_off /*[n_chr+1]*/,
       fA /= N_target / 2.0;
       fD = roundf(fD);
       fA = roundf(fA);
-      if (oracle_bin_of_double_age((double)age_end[m]) >= NBINS) return -2;
+      /* Rows the reference cannot process: with age_begin <= 0 a draw whose bin reaches 185 is written past the end of
+       * the 185-long histogram (coal.cpp:2269: undefined behaviour), and with age_begin itself in bin >= 185 the
+       * rejection loop of coal.cpp:2279-2294 never accepts a draw (the reference does not terminate). */
+      if (ab <= age && oracle_bin_of_double_age((double)age_end[m]) >= NBINS) return -2;
+      if (ab > age && oracle_bin_of_double_age(ab) >= NBINS) return -2;
       n_used[blk]++; (*n_used_total)++;
 
       if (ab <= age) {
@@ -310,15 +316,21 @@ int oracle_stage1(int n_chr, const int64_t* site_off /*[n_chr+1]*/,
           n_notshared[blk * NBINS + b]++;
         }
       } else {
-        /* coal.cpp:2279-2295 (no rejection can occur once -2 is excluded) */
-        for (int j = 0; j < NSAMPLES; j++) {
+        /* coal.cpp:2279-2295: a draw whose bin reaches 185 (or that falls below `age`) is REDRAWN: it consumes its
+         * uniform (two engine words) and does not count towards the 100 samples */
+        int j = 0;
+        while (j < NSAMPLES) {
           double a = oracle_uniform_real(rng) * (age_end[m] - ab) + ab;
+          int skip = a < age;
           int b = oracle_bin_of_double_age(a);
-          if (b >= NBINS) return -2;
-          shared[blk * NBINS + b] += fD * sr.daf / ((double)N_ref * num_samples);
-          notshared[blk * NBINS + b] += fA * sr.daf / ((double)N_ref * num_samples);
-          n_shared[blk * NBINS + b]++;
-          n_notshared[blk * NBINS + b]++;
+          if (b >= NBINS) skip = 1;
+          if (!skip) {
+            shared[blk * NBINS + b] += fD * sr.daf / ((double)N_ref * num_samples);
+            notshared[blk * NBINS + b] += fA * sr.daf / ((double)N_ref * num_samples);
+            n_shared[blk * NBINS + b]++;
+            n_notshared[blk * NBINS + b]++;
+            j++;
+          }
         }
       }
     }

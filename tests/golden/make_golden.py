@@ -39,8 +39,30 @@ def pack(sites, gt, gr):
     return d
 
 
+def reject_fixture():
+    """parse_tmptmp on rows whose age interval reaches past the age grid (rejection sampling, coal.cpp:2279-2294)."""
+    seed = 17
+    sites = synth.make_sites(seed, [1400, 1000], [2.4e8, 1.3e8], weird=0.05)
+    deep = synth.add_deep_rows(sites, seed + 1, 0.03)
+    gt = synth.make_genome(seed + 100, sites, 0.8)
+    gr = synth.make_genome(seed + 200, sites, 0.8)
+    d = tempfile.mkdtemp()
+    synth.write_dataset(d, sites, {"t": gt, "r": gr})
+    r = po.ref_parse_tmptmp(d, sites.chr_names, "syn", "t", "r", seed=seed)
+    out = pack(sites, gt, gr)
+    for k in ("num_blocks", "shared", "notshared", "shared_emp", "notshared_emp", "mt", "next_words"):
+        out[f"ref_{k}"] = np.asarray(r[k])
+    out["seed"] = seed
+    out["deep_rows"] = deep
+    np.savez_compressed(os.path.join(OUT, "stage1_reject.npz"), **out)
+    print("stage1_reject.npz:", len(deep), "deep rows, blocks", r["num_blocks"])
+
+
 def main():
     assert po.ref_available() and po.ref_cli(), "build oracle/_ref first (make -C oracle ref)"
+    if len(sys.argv) > 1 and sys.argv[1] == "reject":
+        return reject_fixture()
+    reject_fixture()
     # ---- stage i: parse_tmptmp on weird rows, with and without masks
     seed = 11
     sites, gt, gr = dataset(seed, [1500, 900, 1200], [2.4e8, 6.1e7, 1.3e8], weird=0.12)

@@ -298,3 +298,59 @@ def test_stream_cache_serves_shorter_and_longer_requests(handle):
         assert a.n_used == b.n_used and a.num_blocks == b.num_blocks
         assert np.array_equal(a.block_stats, b.block_stats) and np.array_equal(a.block_tallies, b.block_tallies)
         assert np.array_equal(a.mt_state, b.mt_state)
+
+
+def test_rejection_sampling_rows_match_the_reference(handle):
+    """Rows with age_begin > 0 whose interval reaches past the age grid: every sample beyond it is redrawn (coal.cpp:2279-2294),
+    two more engine words each.  Device == compiled reference (fixture) == oracle: histograms, tallies and the generator
+    state after the stage."""
+    from helpers import load, dataset_from
+    z = load("stage1_reject.npz")
+    sites, gt, gr = dataset_from(z)
+    handle.load(sites, gt, gr)
+    s1 = handle.stage1(api.mt_seed(int(z["seed"])))
+    assert s1.num_blocks == int(z["ref_num_blocks"])
+    for v, k in enumerate(("shared", "notshared", "shared_emp", "notshared_emp")):
+        assert np.array_equal(s1.block_stats[:, v], z[f"ref_{k}"]), k
+    o = po.stage1(sites, gt, gr, seed=int(z["seed"]))
+    _compare_stage1(o, s1)
+    assert handle.extra_words() > 0 and handle.extra_words() % 2 == 0
+    want = api.mt_seed(int(z["seed"]))
+    n = 200 * s1.n_used + handle.extra_words()
+    api.lib().colate_mt_generate(want, n, np.zeros(n, np.uint32))
+    assert np.array_equal(want, s1.mt_state)
+    assert (s1.block_tallies[:, 1].sum(), s1.block_tallies[:, 0].sum() <= 100 * s1.n_used) == (100 * s1.n_used, True)
+
+
+@pytest.mark.parametrize("seed", [41, 42])
+def test_rejection_sampling_random(handle, seed):
+    sites = synth.make_sites(seed, [30000, 20000, 9000], [2.4e8, 1.3e8, 6e7], weird=0.05)
+    deep = synth.add_deep_rows(sites, seed + 7, 0.004)
+    gt = synth.make_genome(seed + 100, sites, 0.7)
+    gr = synth.make_genome(seed + 200, sites, 0.7)
+    o = po.stage1(sites, gt, gr, seed=seed)
+    handle.load(sites, gt, gr)
+    s1 = handle.stage1(api.mt_seed(seed))
+    _compare_stage1(o, s1)
+    assert handle.extra_words() > 0
+    # without such rows the call consumes exactly 200 words per used row
+    sites2 = synth.make_sites(seed, [30000, 20000, 9000], [2.4e8, 1.3e8, 6e7], weird=0.05)
+    handle.load(sites2, gt, gr)
+    handle.stage1(api.mt_seed(seed))
+    assert handle.extra_words() == 0
+
+
+def test_rows_the_reference_cannot_process_are_refused(handle):
+    """age_begin <= 0 with an interval past the grid (the reference writes out of bounds, coal.cpp:2269); age_begin itself
+    past the grid (its rejection loop never ends): COLATE_ERR_AGE_RANGE from the flag pass, as in the oracle."""
+    for ab, ae in ((0.0, 2e7), (1e7, 3e7), (-5.0, 1.2e7)):
+        sites = synth.make_sites(5, [3000], [2.4e8])
+        gt = synth.make_genome(105, sites, 0.9)
+        gr = synth.make_genome(205, sites, 0.9)
+        k = np.nonzero(sites.meta() & 1)[0]
+        sites.age_begin[k[::7]] = ab; sites.age_end[k[::7]] = ae
+        assert po.stage1(sites, gt, gr, seed=1)["num_blocks"] == -2
+        handle.load(sites, gt, gr)
+        with pytest.raises(api._lib.ColateError) as e:
+            handle.stage1(api.mt_seed(1))
+        assert e.value.code == -2

@@ -124,6 +124,31 @@ def test_bin_index():
             assert L.oracle_bin_of_float_age(np.float32(a)) == po.ref().ref_bin_of_float_age(np.float32(a))
 
 
+def test_stage1_rejection_sampling_matches_reference():
+    """Rows with age_begin > 0 whose interval reaches past the age grid: the reference redraws every sample whose bin
+    reaches 185 (coal.cpp:2279-2294), two more engine words per redraw.  Histograms AND generator state after the
+    stage equal the compiled reference's (fixture from tests/golden/make_golden.py reject)."""
+    z = load("stage1_reject.npz")
+    sites, gt, gr = dataset_from(z)
+    o = po.stage1(sites, gt, gr, seed=int(z["seed"]))
+    assert o["num_blocks"] == int(z["ref_num_blocks"])
+    for k in ("shared", "notshared", "shared_emp", "notshared_emp"):
+        assert same(o[k], z[f"ref_{k}"]), k
+    assert same(o["rng"].words(), z["ref_mt"])
+    # the stage consumed more than 200 words per used row: redraws happened
+    plain = po.mt_seed(int(z["seed"]))
+    for _ in range(200 * o["n_used_total"]):
+        po.lib().oracle_mt_next(plain)
+    assert not same(plain.words(), z["ref_mt"])
+    # rows the reference cannot process stay errors: age_begin <= 0 with an interval past the grid (out-of-bounds write,
+    # coal.cpp:2269), age_begin itself past the grid (the rejection loop never ends)
+    for ab, ae in ((0.0, 2e7), (1e7, 3e7)):
+        s2, g2t, g2r = dataset_from(z)
+        used = np.nonzero(s2.meta() & 1)[0]
+        s2.age_begin[used] = ab; s2.age_end[used] = ae
+        assert po.stage1(s2, g2t, g2r, seed=1)["num_blocks"] == -2
+
+
 @pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref not built (needs /root/reference)")
 @pytest.mark.parametrize("seed", [21, 22])
 def test_stage1_random_vs_live_reference(seed):
