@@ -58,6 +58,7 @@ SIGNATURES = {
     "colate_stage1": (C.c_int, [VP, C.c_int, C.c_int, VP, C.POINTER(C.c_int), VP, VP, C.POINTER(C.c_int64), VP]),
     "colate_stage2_bootstrap": (C.c_int, [VP, C.c_int, C.c_int, VP, VP, C.c_double, VP]),
     "colate_stage3_em": (C.c_int, [VP, C.c_int, C.c_int, VP, VP, VP, C.c_int, VP, VP, VP]),
+    "colate_set_age_bins": (C.c_int, [VP, VP]),
     "colate_estep": (C.c_int, [VP, C.c_int, C.c_int, VP, VP, C.c_int, VP, VP, VP, VP]),
     "colate_libm_exact": (C.c_int, []),
     "colate_last_stage1_timing": (C.c_int, [VP, C.POINTER(Stage1Timing)]),

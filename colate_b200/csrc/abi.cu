@@ -38,6 +38,7 @@ int ensure_tables(colate_handle* h)
   h->thr185 = thr[NBINS];
   CK(cudaMemcpyAsync(h->d_agebin.p, ab, sizeof ab, cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  memcpy(h->h_agebin, ab, sizeof ab);
   h->thr_ready = true;
   return 0;
 }
@@ -511,6 +512,21 @@ int colate_estep(colate_handle* h, int shared, int E, const double* epochs, cons
   if (denom) CK(cudaMemcpyAsync(denom, base + n_t + (size_t)n_t * E, (size_t)n_t * E * 8, cudaMemcpyDeviceToHost, s));
   if (logl) CK(cudaMemcpyAsync(logl, base + n_t + 2 * (size_t)n_t * E, (size_t)n_t * 8, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int colate_set_age_bins(colate_handle* h, const double* age_bin)
+{
+  if (!h) return fail(COLATE_ERR_ARG, "colate_set_age_bins: null handle");
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_tables(h);
+  if (rc) return rc;
+  double ab[NBINS];
+  if (age_bin) memcpy(ab, age_bin, sizeof ab); else colate_age_bins(ab);
+  for (int b = 0; b < NBINS; b++) if (!(ab[b] >= 0) || (b > 0 && !(ab[b] >= ab[b - 1]))) return fail(COLATE_ERR_ARG, "colate_set_age_bins: the grid must be non-negative and ascending");
+  memcpy(h->h_agebin, ab, sizeof ab);
+  CK(cudaMemcpyAsync(h->d_agebin.p, h->h_agebin, sizeof ab, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 

@@ -76,6 +76,7 @@ struct colate_handle {
   colate::DevBuf blk_rank_start, out_f, out_n, deep_rows;
   int64_t n_deep = 0;           // used rows of the current pair that take the rejection-sampling path (coal.cpp:2279-2294)
   int64_t extra_words = 0;      // generator words the last stage-i call consumed beyond 200 per used row (redraws)
+  double h_agebin[COLATE_NUM_AGE_BINS] = {};   // the age grid the EM evaluates (default: colate_age_bins(); colate_set_age_bins())
   double thr185 = 0.0;          // 10 * age from which the age bin is 185 (thr10[185])
   colate::DevBuf windows, rng_stream, mt_tail, poly, thr10, thrA, lut;
   int sm_count = 148;

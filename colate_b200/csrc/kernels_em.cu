@@ -1348,8 +1348,7 @@ int run_em(colate_handle* h, int R, int E, int max_iter, const double* epochs_ho
   int n_pairs_cap = 0;
   const char* force = getenv("COLATE_EM_KERNEL");   // "cta", "task" (k_em), "split": tests and tuning
   if ((!split && csize == 1 && !(force && !strcmp(force, "task"))) || (force && !strcmp(force, "cta"))) {
-    double ab[NBINS];
-    colate_age_bins(ab);
+    const double* ab = h->h_agebin;
     for (int b = 0; b < NBINS; b++) {
       int k = E;
       for (int e = 0; e < E; e++) if (ab[b] < epochs_host[e]) { k = e; break; }

@@ -137,6 +137,12 @@ int colate_stage2_bootstrap(colate_handle* h, int R, int num_blocks, const int32
 int colate_stage3_em(colate_handle* h, int R, int E, const double* epochs, const double* rates_init,
                      const double* counts, int max_iter, double* rates, int32_t* iters, double* final_ll);
 
+/* The age grid colate_stage3_em() evaluates (the point ages t = age_bin[b], coal.cpp:3708, 3721).  Default: colate_age_bins().
+ * mut() started from a <out>.colate_mat cache reads the grid back from that file's first line, i.e. rounded to six
+ * significant digits (coal.cpp:3481-3483), and runs the EM on THOSE ages: the host passes them here.  NULL restores the
+ * default.  (Stage ii keeps the exact grid: the cache path never runs it.) */
+int colate_set_age_bins(colate_handle* h, const double* age_bin);
+
 /* One E-step call: coal_EM(epochs, rates).EM_shared / EM_notshared(t, t, num, denom)
  * (coal_EM.cpp:153, 297) evaluated on the device for n_t ages.  num/denom: [n_t][E]. */
 int colate_estep(colate_handle* h, int shared, int E, const double* epochs, const double* rates,

@@ -186,12 +186,15 @@ def estep(shared: bool, epochs, rates, t: float):
     return ll, num, den
 
 
-def em_run(epochs, rates_init, counts, max_iter=100000):
+def em_run(epochs, rates_init, counts, max_iter=100000, age_bin=None):
+    """age_bin: the point ages of the 185 bins (default: the exact grid; mut() started from a .colate_mat cache uses the
+    grid read back from the file, coal.cpp:3481-3483)."""
     E = len(epochs)
     out = np.zeros(E)
     ll = C.c_double(0)
     it = lib().oracle_em_run(E, np.ascontiguousarray(epochs, dtype=np.float64),
-                             np.ascontiguousarray(rates_init, dtype=np.float64), age_bins(),
+                             np.ascontiguousarray(rates_init, dtype=np.float64),
+                             age_bins() if age_bin is None else np.ascontiguousarray(age_bin, dtype=np.float64),
                              np.ascontiguousarray(counts, dtype=np.float64), max_iter, out, C.byref(ll))
     return out, it, ll.value
 

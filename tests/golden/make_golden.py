@@ -58,10 +58,49 @@ def reject_fixture():
     print("stage1_reject.npz:", len(deep), "deep rows, blocks", r["num_blocks"])
 
 
+def n2_fixture():
+    """the reference CLI (a) started from a <out>.colate_mat cache (coal.cpp:3169-3170, 3471-3499: parsing is
+    skipped, the counts are read back from 6-digit text) and (b) warm-started from a .coal file (--coal, coal.cpp:3508-3549,
+    3638-3646) on the cli_small dataset."""
+    z = np.load(os.path.join(OUT, "cli_small.npz"), allow_pickle=False)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import dataset_from
+    sites, gt, gr = dataset_from(z)
+    seed = int(z["seed"])
+    d = tempfile.mkdtemp()
+    synth.write_dataset(d, sites, {"t": gt, "r": gr})
+    # (a) a cache in the reference's own format (coal.cpp:3336-3343, 3453-3465): age grid line, then per replicate the shared
+    # and the not-shared line, operator<< with default precision (== %g)
+    o = po.stage1(sites, gt, gr, seed=seed)
+    w = po.draw_block_weights(o["rng"], 3, o["num_blocks"])
+    counts = po.stage2(w, o, 0.0)
+    lines = [" ".join("%g" % v for v in po.age_bins()) + " "]
+    for r in range(3):
+        lines += [" ".join("%g" % v for v in counts[r, 0]) + " ", " ".join("%g" % v for v in counts[r, 1]) + " "]
+    mat = "\n".join(lines) + "\n"
+    open(os.path.join(OUT, "n2_cache.colate_mat"), "w").write(mat)
+    open(d + "/cached.colate_mat", "w").write(mat)
+    base = [po.ref_cli(), "--mode", "mut", "--mut", d + "/syn", "--chr", d + "/chr.txt", "--target_tmp", d + "/t.colate.in",
+            "--reference_tmp", d + "/r.colate.in", "--seed", str(seed)]
+    pr = subprocess.run(base + ["--bins", "3,7,0.2", "--num_bootstraps", "3", "-o", d + "/cached"], capture_output=True, text=True)
+    assert pr.returncode == 0 and "Loading precomputed file" in pr.stderr, pr.stderr
+    open(os.path.join(OUT, "n2_cache.coal"), "w").write(open(d + "/cached.coal").read())
+    # (b) warm start from the golden .coal of the ancient run (a non-ancient .coal starts "0 0 ..." and trips the
+    # reference's own assert(epochs[e] > epochs[e-1]) at coal.cpp:3548)
+    pr = subprocess.run(base + ["--coal", os.path.join(OUT, "cli_ancient.coal"), "--target_age", "7000", "--reference_age", "0",
+                                "--years_per_gen", "28", "-o", d + "/warm"], capture_output=True, text=True)
+    assert pr.returncode == 0, pr.stderr
+    open(os.path.join(OUT, "n2_warm.coal"), "w").write(open(d + "/warm.coal").read())
+    print("n2 fixtures written")
+
+
 def main():
     assert po.ref_available() and po.ref_cli(), "build oracle/_ref first (make -C oracle ref)"
     if len(sys.argv) > 1 and sys.argv[1] == "reject":
         return reject_fixture()
+    if len(sys.argv) > 1 and sys.argv[1] == "n2":
+        return n2_fixture()
+    n2_fixture()
     reject_fixture()
     # ---- stage i: parse_tmptmp on weird rows, with and without masks
     seed = 11

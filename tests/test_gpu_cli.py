@@ -80,3 +80,68 @@ def test_cli_masks_and_cache(dataset_dir):
     E = int(np.frombuffer(raw[12:16], np.int32)[0])
     assert np.array_equal(np.frombuffer(raw[16 + 8 * E:16 + 16 * E], np.float64), ro)
     assert f"Number of blocks: {o['num_blocks']}" in r.stderr
+
+
+def _run(args):
+    r = subprocess.run([CLI, "--mode", "mut"] + args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return r
+
+
+def test_cli_devices_sharding_is_byte_identical(dataset_dir):
+    """--devices: chromosomes dealt to the devices for stage i (generator offsets and block bases exchanged in the process),
+    replicates round-robin for stages ii-iii.  .coal and .bin do not depend on the device list -- two, three (more devices
+    than chromosomes: one owns nothing) or, on a multi-GPU box, distinct GPUs."""
+    import torch
+    d, z, sites, gt, gr = dataset_dir
+    base = ["--mut", d + "/syn", "--chr", d + "/chr.txt", "--target_tmp", d + "/t.colate.in", "--reference_tmp", d + "/r.colate.in",
+            "--bins", "3,7,0.2", "--seed", "1", "--num_bootstraps", "23"]
+    lists = ["0", "0,0", "0,0,0"] + (["0,1"] if torch.cuda.device_count() > 1 else [])
+    outs = []
+    for i, devs in enumerate(lists):
+        out = os.path.join(d, f"gpu_dev{i}")
+        r = _run(base + ["--devices", devs, "-o", out] + (["--host_parse"] if i == 1 else []))
+        assert "Number of blocks: 13" in r.stderr
+        outs.append((open(out + ".coal", "rb").read(), open(out + ".bin", "rb").read()))
+    for o in outs[1:]:
+        assert o == outs[0]
+    # ... and equal the oracle: replicate 22 of 23
+    raw = outs[0][1]
+    R, E = np.frombuffer(raw[8:16], np.int32)
+    rates = np.frombuffer(raw[16 + 8 * E:16 + 8 * E + 8 * R * E], np.float64).reshape(R, E)
+    o = po.stage1(sites, gt, gr, seed=1)
+    w = po.draw_block_weights(o["rng"], 23, o["num_blocks"])
+    ep, _ = po.epochs_from_bins("3,7,0.2")
+    ro, it, _ = po.em_run(ep, np.full(len(ep), 1 / 20000.), po.stage2(w, o, 0.0)[22])
+    assert np.array_equal(rates[22], ro)
+
+
+def test_cli_colate_mat_cache_and_coal_warm_start(dataset_dir):
+    """SURVEY.md 8(f) N2.  (a) <out>.colate_mat present: parsing is skipped and the counts come from the 6-digit text
+    (coal.cpp:3169-3170, 3471-3499); (b) --coal: epochs and initial rates from a .coal file (coal.cpp:3508-3549, 3638-3646).
+    Both against .coal files the reference CLI wrote from the same inputs (tests/golden/make_golden.py n2), (a) also bitwise
+    against the oracle's EM on the read-back counts."""
+    import shutil
+    d, z, sites, gt, gr = dataset_dir
+    common = ["--mut", d + "/syn", "--chr", d + "/chr.txt", "--target_tmp", d + "/t.colate.in", "--reference_tmp", d + "/r.colate.in", "--seed", "1"]
+    out = os.path.join(d, "gpu_cached")
+    shutil.copy(os.path.join(GOLDEN, "n2_cache.colate_mat"), out + ".colate_mat")
+    r = _run(common + ["--bins", "3,7,0.2", "--num_bootstraps", "3", "-o", out])
+    assert "Loading precomputed file" in r.stderr and "Number of blocks" not in r.stderr
+    assert open(out + ".coal").read() == open(os.path.join(GOLDEN, "n2_cache.coal")).read()
+    vals = np.array(open(out + ".colate_mat").read().split(), dtype=np.float64)
+    counts = vals[185:].reshape(3, 2, 185)
+    raw = open(out + ".bin", "rb").read()
+    R, E = np.frombuffer(raw[8:16], np.int32)
+    rates = np.frombuffer(raw[16 + 8 * E:16 + 8 * E + 8 * R * E], np.float64).reshape(R, E)
+    ep, _ = po.epochs_from_bins("3,7,0.2")
+    for i in range(3):
+        ro, it, _ = po.em_run(ep, np.full(len(ep), 1 / 20000.), counts[i], age_bin=vals[:185])   # the EM runs on the grid read back from the file
+        assert np.array_equal(rates[i], ro)
+    os.remove(out + ".colate_mat")
+    out = os.path.join(d, "gpu_warm")
+    r = _run(common + ["--coal", os.path.join(GOLDEN, "cli_ancient.coal"), "--target_age", "7000", "--reference_age", "0", "--years_per_gen", "28", "-o", out])
+    assert open(out + ".coal").read() == open(os.path.join(GOLDEN, "n2_warm.coal")).read()
+    # a non-ancient .coal starts "0 0 ...": the reference trips its own assert (coal.cpp:3548); this host reports it
+    bad = subprocess.run([CLI, "--mode", "mut"] + common + ["--coal", os.path.join(GOLDEN, "cli_bins02_R1.coal"), "-o", out], capture_output=True, text=True)
+    assert bad.returncode != 0 and "epochs must increase" in bad.stderr
