@@ -261,21 +261,6 @@ int run_mut(const Options& options)
       fclose(f);
     }
     struct SitesHost { std::vector<int64_t> off; std::vector<int32_t> pos; std::vector<float> ab, ae; std::vector<uint32_t> meta; } sh;
-    if (!all_plain) {
-      sh.off.assign(n_chr + 1, 0);
-      for (int c = 0; c < n_chr; c++) {
-        std::cerr << "parsing CHR: " << c + 1 << " / " << n_chr << std::endl;
-        int64_t n = colate_read_mut(f_mut[c].c_str(), 0, nullptr, nullptr, nullptr, nullptr);
-        if (n < 0) { std::cerr << colate_last_error() << std::endl; exit(1); }
-        size_t o = sh.pos.size();
-        sh.pos.resize(o + n); sh.ab.resize(o + n); sh.ae.resize(o + n); sh.meta.resize(o + n);
-        if (colate_read_mut(f_mut[c].c_str(), n, sh.pos.data() + o, sh.ab.data() + o, sh.ae.data() + o, sh.meta.data() + o) < 0) {
-          std::cerr << colate_last_error() << std::endl;
-          exit(1);
-        }
-        sh.off[c + 1] = (int64_t)sh.pos.size();
-      }
-    }
     // the two .colate.in files.  One device: the file image goes to the GPU and is decoded there (colate_ingest_colate_in).
     // Several devices: decoded once on the host, the chromosome seek (coal.cpp:2125-2145) emulated on the WHOLE record
     // stream, and every device receives the records and ranges of its own chromosomes.
@@ -307,6 +292,21 @@ int run_mut(const Options& options)
     ph.tick("read input files");
     if (!wait_for_devices()) return 1;
     ph.tick("wait for the CUDA context");
+    if (!all_plain) {
+      sh.off.assign(n_chr + 1, 0);
+      for (int c = 0; c < n_chr; c++) {
+        std::cerr << "parsing CHR: " << c + 1 << " / " << n_chr << std::endl;
+        int64_t n = colate_read_mut(f_mut[c].c_str(), 0, nullptr, nullptr, nullptr, nullptr);
+        if (n < 0) { std::cerr << colate_last_error() << std::endl; exit(1); }
+        size_t o = sh.pos.size();
+        sh.pos.resize(o + n); sh.ab.resize(o + n); sh.ae.resize(o + n); sh.meta.resize(o + n);
+        if (colate_read_mut(f_mut[c].c_str(), n, sh.pos.data() + o, sh.ab.data() + o, sh.ae.data() + o, sh.meta.data() + o) < 0) {
+          std::cerr << colate_last_error() << std::endl;
+          exit(1);
+        }
+        sh.off[c + 1] = (int64_t)sh.pos.size();
+      }
+    }
 
     // chromosomes -> devices, balanced by text bytes / rows
     std::vector<int64_t> w(n_chr);

@@ -7,6 +7,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <cerrno>
 #include <cmath>
 #include <climits>
 #include <cstdio>
@@ -232,23 +233,59 @@ void chr_ranges_runs(int n_chr, const std::vector<ColateInRun>& runs, int64_t* c
 }
 
 // one data line of a .mut file, [p, nl) with *nl == '\n' (mutations.cpp:70-250; the columns the path uses)
+// std::stoi / std::stof as libstdc++ implements them (__gnu_cxx::__stoa over strtol / strtof): false where they throw
+// -- no conversion (invalid_argument), ERANGE or a value outside int (out_of_range).  The text is NUL-terminated
+// somewhere behind the field; conversion stops at the field's ';' (or ' ') by itself.
+static bool stoi_like(const char* s, int* v)
+{
+  char* end = nullptr;
+  errno = 0;
+  const long x = strtol(s, &end, 10);
+  if (end == s || errno == ERANGE || x < INT_MIN || x > INT_MAX) return false;
+  *v = (int)x;
+  return true;
+}
+static bool stof_like(const char* s, float* v)
+{
+  char* end = nullptr;
+  errno = 0;
+  const float x = strtof(s, &end);
+  if (end == s || errno == ERANGE) return false;
+  *v = x;
+  return true;
+}
+
+// One data line of a .mut file, [p, nl) with *nl == '\n' and a NUL somewhere behind it, field by field as
+// Mutations::Read walks it (mutations.cpp:70-250).  false = the reference does not survive the line: a field it
+// converts with std::stoi (snp, pos, dist, tree, every branch index, is_flipped, every frequency column: it prints
+// "Error reading following line in mut file" and exits, mutations.cpp:84-88 ...) or std::stof (the two ages: the
+// exception is not caught) cannot be converted, or fields are missing (it reads past the end of the line).
 bool parse_mut_line_host(const char* p, const char* nl, int32_t* pos, float* age_begin, float* age_end, uint32_t* meta)
 {
-  // snp;pos;dist;rs-id;tree;branches;is_not_mapping;is_flipped;age_begin;age_end;type;...
+  // snp;pos;dist;rs-id;tree;branches;is_not_mapping;is_flipped;age_begin;age_end;type;upstream;downstream;freq...
   const char* f[11];
   const char* q = p;
   int nf = 0;
   f[nf++] = q;
   while (q < nl && nf < 11) { if (*q == ';') f[nf++] = q + 1; q++; }
   if (nf < 10) return false;
-  *pos = (int32_t)strtol(f[1], nullptr, 10);
+  int v = 0, ps = 0, fl = 0;
+  if (!stoi_like(f[0], &v) || !stoi_like(f[1], &ps) || !stoi_like(f[2], &v) || !stoi_like(f[4], &v)) return false;
+  *pos = ps;
   int nb = 0;
-  for (const char* b = f[5]; b < f[6] - 1;) {
+  for (const char* b = f[5]; b < f[6] - 1;) {          // tokens between single spaces (mutations.cpp:144-160)
     while (b < f[6] - 1 && *b == ' ') b++;
-    if (b < f[6] - 1) { nb++; while (b < f[6] - 1 && *b != ' ') b++; }
+    if (b < f[6] - 1) {
+      if (!stoi_like(b, &v)) return false;
+      nb++;
+      while (b < f[6] - 1 && *b != ' ') b++;
+    }
   }
-  int flipped = strtol(f[7], nullptr, 10) != 0;
-  float ab = strtof(f[8], nullptr), ae = strtof(f[9], nullptr);
+  if (!stoi_like(f[7], &fl)) return false;
+  const int flipped = fl != 0;
+  float ab, ae;
+  if (nf < 11 && memchr(f[9], ';', nl - f[9]) == nullptr) return false;   // age_end must end with ';' (mutations.cpp:207-210)
+  if (!stof_like(f[8], &ab) || !stof_like(f[9], &ae)) return false;
   *age_begin = ab;
   *age_end = ae;
   char mt[16] = "NA";
@@ -259,6 +296,21 @@ bool parse_mut_line_host(const char* p, const char* nl, int32_t* pos, float* age
     while (e < nl && *e != ';' && k + 1 < sizeof mt) mt[k++] = *e++;
     mt[k] = 0;
     if (e < nl && *e != ';') { mt[0] = 'N'; mt[1] = 'N'; mt[2] = 0; }  // longer than any valid code
+    while (e < nl && *e != ';') e++;
+    // upstream; downstream; then frequency columns, each converted with std::stoi (mutations.cpp:224-250)
+    if (e < nl && e + 1 < nl) {
+      const char* g = e + 1;
+      for (int k2 = 0; k2 < 2; k2++) {                 // both must end with ';'
+        const char* sc = (const char*)memchr(g, ';', nl - g);
+        if (!sc) return false;
+        g = sc + 1;
+      }
+      while (g < nl) {
+        if (!stoi_like(g, &v)) return false;
+        const char* sc = (const char*)memchr(g, ';', nl - g);
+        g = sc ? sc + 1 : nl;
+      }
+    }
   }
   *meta = colate_site_meta(flipped, nb, ab, ae, mt);
   return true;

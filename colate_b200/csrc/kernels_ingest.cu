@@ -116,7 +116,8 @@ __constant__ double c_p10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e
 
 __device__ __forceinline__ bool is_space(char ch) { return ch == ' ' || (ch >= '\t' && ch <= '\r'); }
 
-// strtol(s, 0, 10) on [s, e); false: more digits than fit without overflow handling -> host
+// std::stoi on [s, e) (strtol base 10 + range check); false: the host decides -- no digits (the reference's std::stoi
+// throws and the run ends, mutations.cpp:84-88) or more than 9 digits (may leave the int range)
 __device__ bool dev_strtol(const char* s, const char* e, long long& v)
 {
   while (s < e && is_space(*s)) s++;
@@ -124,9 +125,9 @@ __device__ bool dev_strtol(const char* s, const char* e, long long& v)
   if (s < e && (*s == '+' || *s == '-')) { neg = *s == '-'; s++; }
   long long x = 0;
   int nd = 0;
-  while (s < e && *s >= '0' && *s <= '9') { x = x * 10 + (*s - '0'); s++; if (++nd > 18) return false; }
+  while (s < e && *s >= '0' && *s <= '9') { x = x * 10 + (*s - '0'); s++; if (++nd > 9) return false; }
   v = neg ? -x : x;
-  return true;
+  return nd > 0;
 }
 
 // strtof(s, 0) on [s, e); false: not convertible here with a correct-rounding guarantee -> host
@@ -150,7 +151,7 @@ __device__ bool dev_strtof(const char* s, const char* e, float& out)
     } else if (ch == '.' && !seen_point) seen_point = true;
     else break;
   }
-  if (ndig == 0) { out = 0.0f; return true; }                                // no conversion: strtof returns 0
+  if (ndig == 0) return false;                                               // no conversion: std::stof throws, the host reports the line
   int ex = 0;
   if (s < e && (*s == 'e' || *s == 'E')) {
     const char* q = s + 1;
@@ -193,18 +194,31 @@ k_parse_mut(const char* __restrict__ text, int64_t n_bytes, const int64_t* __res
   if (nf < 10) { atomicMin(status, (unsigned long long)row + 1); return; }
   bool ok = true;
   long long v = 0;
+  // every field Mutations::Read converts with std::stoi must convert (snp, pos, dist, tree, branch indices, is_flipped,
+  // frequency columns): anything doubtful goes to the host, which applies std::stoi's rules to the letter
+  ok &= dev_strtol(f[0], f[1] - 1, v);
+  ok &= dev_strtol(f[2], f[3] - 1, v);
+  ok &= dev_strtol(f[4], f[5] - 1, v);
   ok &= dev_strtol(f[1], f[2] - 1, v);
   const int32_t ps = (int32_t)v;
   int nb = 0;
   for (const char* b = f[5]; b < f[6] - 1;) {
     while (b < f[6] - 1 && *b == ' ') b++;
-    if (b < f[6] - 1) { nb++; while (b < f[6] - 1 && *b != ' ') b++; }
+    if (b < f[6] - 1) {
+      const char* te = b;
+      while (te < f[6] - 1 && *te != ' ') te++;
+      long long bv;
+      ok &= dev_strtol(b, te, bv);
+      nb++;
+      b = te;
+    }
   }
   ok &= dev_strtol(f[7], f[8] - 1, v);
   const int flipped = v != 0;
   float ab = 0.0f, ae = 0.0f;
   ok &= dev_strtof(f[8], f[9] - 1, ab);
   ok &= dev_strtof(f[9], nf >= 11 ? f[10] - 1 : nl, ae);
+  ok &= nf >= 11;                                                  // age_end without its ';': the reference reads past the line
   // mutation type runs to the next ';' or the end of the line (mutations.cpp:216-223); "NA" if absent
   uint32_t m = 0;
   if (flipped == 0 && nb == 1 && ab < ae && ae >= 0 && nf >= 11) {
@@ -216,6 +230,23 @@ k_parse_mut(const char* __restrict__ text, int64_t n_bytes, const int64_t* __res
       const bool oka = a == 'A' || a == 'C' || a == 'G' || a == 'T' || a == '0';
       const bool okd = d == 'A' || d == 'C' || d == 'G' || d == 'T' || d == '1';
       if (oka && okd) m = 1u | ((uint32_t)(unsigned char)a << 8) | ((uint32_t)(unsigned char)d << 16);
+    }
+  }
+  if (nf >= 11) {   // upstream; downstream; frequency columns (std::stoi each, mutations.cpp:224-250)
+    const char* g = f[10];
+    while (g < nl && *g != ';') g++;
+    if (g < nl && g + 1 < nl) {
+      g++;
+      int semis = 0;
+      while (g < nl && semis < 2) { if (*g == ';') semis++; g++; }
+      if (semis < 2) ok = false;
+      while (g < nl) {
+        const char* fe = g;
+        while (fe < nl && *fe != ';') fe++;
+        long long fv;
+        ok &= dev_strtol(g, fe, fv);
+        g = fe < nl ? fe + 1 : nl;
+      }
     }
   }
   pos[row] = ps; age_begin[row] = ab; age_end[row] = ae; meta[row] = m;

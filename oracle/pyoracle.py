@@ -218,6 +218,7 @@ def write_coal(path, epochs, rates, is_ancient=False, ep_null=0):
 
 # ---------------------------------------------------------------- compiled reference
 _ref = None
+REF_LIB = os.path.join(HERE, "_ref", "libcolate_ref.so")
 
 
 def ref_available() -> bool:
@@ -251,6 +252,50 @@ def ref():
         L.ref_bin_of_double_age.argtypes = [C.c_double]
         _ref = L
     return _ref
+
+
+_REF_READ_MUT = r"""
+import ctypes as C, sys, numpy as np
+L = C.CDLL(sys.argv[1])
+cap = int(sys.argv[3])
+pos = np.zeros(cap, np.int32); ab = np.zeros(cap, np.float32); ae = np.zeros(cap, np.float32)
+fl = np.zeros(cap, np.int32); nb = np.zeros(cap, np.int32); ty = np.zeros((cap, 16), np.uint8); tl = np.zeros(cap, np.int32)
+L.ref_read_mut.restype = C.c_long
+p = lambda a: a.ctypes.data_as(C.c_void_p)
+n = L.ref_read_mut(sys.argv[2].encode(), C.c_long(cap), p(pos), p(ab), p(ae), p(fl), p(nb), p(ty), p(tl))
+if n < 0:
+    sys.exit(3)
+np.savez(sys.argv[4], n=n, pos=pos[:n], age_begin=ab[:n], age_end=ae[:n], flipped=fl[:n], n_branch=nb[:n], type15=ty[:n], type_len=tl[:n])
+"""
+
+
+def ref_read_mut(path, cap=1 << 20):
+    """The reference's own Mutations::Read (mutations.cpp:56-283) on one .mut file, in a child process (it calls exit(1) on a
+    field std::stoi cannot convert and dies of an uncaught exception on one std::stof cannot).  Returns the fields the
+    tmp/tmp path uses, or None when the reference did not survive the file."""
+    import subprocess
+    import sys
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "rows.npz")
+        r = subprocess.run([sys.executable, "-c", _REF_READ_MUT, REF_LIB, path, str(cap), out], capture_output=True)
+        if r.returncode != 0 or not os.path.exists(out):
+            return None
+        z = np.load(out)
+        return {k: z[k] for k in z.files}
+
+
+def ref_meta(rows):
+    """Packed site word (colate_site_meta) from the reference reader's rows: coal.cpp:2150-2176 minus the masks."""
+    n = int(rows["n"])
+    meta = np.zeros(n, np.uint32)
+    for i in range(n):
+        t = bytes(rows["type15"][i]).split(b"\0")[0]
+        ok = rows["flipped"][i] == 0 and rows["n_branch"][i] == 1 and rows["age_begin"][i] < rows["age_end"][i] and rows["age_end"][i] >= 0
+        ok = ok and rows["type_len"][i] == 3 and len(t) == 3 and t[1:2] == b"/" and t[0:1] in b"ACGT0" and t[2:3] in b"ACGT1"
+        if ok:
+            meta[i] = 1 | (t[0] << 8) | (t[2] << 16)
+    return meta
 
 
 def ref_parse_tmptmp(dirname, chr_names, prefix, target, reference, seed=1, tmask=None, rmask=None):

@@ -165,4 +165,33 @@ int ref_bin_of_double_age(double a)
   return std::max(0, (int)std::round(log(10 * a) * C) + 1);
 }
 
+
+// Mutations::Read(filename) (include/src/mutations.cpp:259-283 -> 56-257), the reader parse_tmptmp uses (coal.cpp:2115-2116),
+// on one .mut file; returns the rows it produced (or -1 if it threw: std::stoi / std::stof throw on fields they cannot
+// convert, which ends the reference run) and, per row, the fields the tmp/tmp path looks at (coal.cpp:2150-2176).
+// mutation_type is returned as the first 15 characters + its length.
+long ref_read_mut(const char* filename, long cap, int* pos, float* age_begin, float* age_end, int* flipped, int* n_branch,
+                  char* type15 /*[cap][16]*/, int* type_len)
+{
+  Mutations m;
+  try {
+    m.Read(std::string(filename));
+  } catch (const std::exception& e) {
+    return -1;
+  }
+  long n = (long)m.info.size();
+  for (long i = 0; i < n && i < cap; i++) {
+    const SNPInfo& s = m.info[i];
+    pos[i] = s.pos;
+    age_begin[i] = s.age_begin;
+    age_end[i] = s.age_end;
+    flipped[i] = s.flipped ? 1 : 0;
+    n_branch[i] = (int)s.branch.size();
+    memset(type15 + 16 * i, 0, 16);
+    strncpy(type15 + 16 * i, s.mutation_type.c_str(), 15);
+    type_len[i] = (int)s.mutation_type.size();
+  }
+  return n;
+}
+
 }  // extern "C"

@@ -58,6 +58,58 @@ def reject_fixture():
     print("stage1_reject.npz:", len(deep), "deep rows, blocks", r["num_blocks"])
 
 
+HEADER = b"snp;pos_of_snp;dist;rs-id;tree_index;branch_indices;is_not_mapping;is_flipped;age_begin;age_end;ancestral_allele/alternative_allele;upstream_allele;downstream_allele;\n"
+
+
+def mut_reader_cases():
+    """(valid text, [invalid single data lines]) for the .mut reader: number spellings std::stoi / std::stof accept in every
+    form the device parser has to get right, and lines the reference does not survive."""
+    rng = np.random.default_rng(7)
+    ages = ["0", "-0", "0.0", "+5", ".5", "5.", "1e3", "1E-3", "1.5e+2", "12345.678", "0.000123", "16777217", "16777219",
+            "33554434.000000001", "8388608.5", "8388609.5", "0.1", "0.30000001192092896", "3.4028235e38", "inf", "-inf", "nan",
+            "0x1p3", "1e", "1e+", " 12", "12 ", "1.2.3", "123456789012345678", "1234567890123456789012",
+            "0.00000000000000000000000000001", "1000000000000000000000000", "9007199254740993", "1.17549435e-38", "  7.5", "\t3",
+            "12abc", "1e5x", "4.5e+", "+.5e1", "-1e-3", "00012.5000", "1e0000000002"]
+    for _ in range(200):                      # exact float midpoints printed with all their digits, and their neighbours
+        f = np.float32(np.exp(rng.uniform(-20, 20)))
+        mid = (np.float64(f) + np.float64(np.nextafter(f, np.float32(np.inf)))) / 2
+        ages += [format(mid, ".30g"), format(np.nextafter(mid, 0), ".30g"), format(np.nextafter(mid, np.inf), ".25g")]
+    for _ in range(3000):
+        x = np.exp(rng.uniform(-12, 18))
+        ages.append(format(x, rng.choice([".3f", ".6g", ".9g", ".12g", ".17g", "e", ".1f"])))
+    lines = [HEADER]
+    for i, a in enumerate(ages):
+        b = ages[(i * 7 + 3) % len(ages)]
+        pos = ["17", " 42", "+9", "-3", "007", "2147483647", "12x"][i % 7]
+        flip = ["0", "1", "00", "2", " 0"][i % 5]
+        br = ["17", "17 23", " 5", "", "1 2 3"][i % 5]
+        typ = ["A/C", "G/T", "AT/C", "A/", "/C", "0/1", "N/A", "A/C extra", "ACGTACGTACGTACGTACGT/A", "A/C"][i % 10]
+        tail = ["A;C;\n", "\n", ";;\n", "A;C;10 20 30\n", "A;C;5;6;7;\n"][i % 5]
+        lines.append(f"{i};{pos};10;.;5;{br};0;{flip};{a};{b};{typ};".encode() + tail.encode())
+    good = b"".join(lines)
+    row = lambda **kw: "{snp};{pos};{dist};rs;{tree};{br};0;{fl};{ab};{ae};A/C;A;C;".format(**{**dict(snp=1, pos=5, dist=1, tree=1, br=7, fl=0, ab="1.5", ae="2.5"), **kw})
+    bad = [row(ab="1e39"), row(ae="1e-50"), row(ab=""), row(ae="e5"), row(ab="4.9406564584124654e-324"), row(ae="1e400"), row(ab="7e-46"),
+           row(pos=""), row(pos="99999999999"), row(pos="x1"), row(snp="a"), row(dist=""), row(tree="t"), row(br="1 x"), row(fl=""),
+           row(fl="f"), "1;2;3;.;5;6;0;0;1.0", "9;5;1;.;1;7;0;0;1.5;2.5", row() + "7;;", row() + "x;"]
+    return good, [b.encode() + b"\n" for b in bad]
+
+
+def mut_reader_fixture():
+    """Mutations::Read (include/src/mutations.cpp:56-283) itself, through oracle/ref_probe.cpp, on the reader test cases."""
+    good, bad = mut_reader_cases()
+    d = tempfile.mkdtemp()
+    open(d + "/good.mut", "wb").write(good)
+    rows = po.ref_read_mut(d + "/good.mut")
+    assert rows is not None, "the reference did not survive the valid file"
+    died = []
+    for i, b in enumerate(bad):
+        open(d + f"/bad{i}.mut", "wb").write(HEADER + b)
+        died.append(po.ref_read_mut(d + f"/bad{i}.mut") is None)
+    print("reference reader:", int(rows["n"]), "rows; invalid cases it died on:", sum(died), "of", len(bad))
+    np.savez_compressed(os.path.join(OUT, "mut_reader.npz"), text=np.frombuffer(good, np.uint8), pos=rows["pos"], age_begin=rows["age_begin"],
+                        age_end=rows["age_end"], meta=po.ref_meta(rows), bad=np.array(bad), ref_died=np.array(died))
+
+
 def n2_fixture():
     """the reference CLI (a) started from a <out>.colate_mat cache (coal.cpp:3169-3170, 3471-3499: parsing is
     skipped, the counts are read back from 6-digit text) and (b) warm-started from a .coal file (--coal, coal.cpp:3508-3549,
@@ -100,6 +152,9 @@ def main():
         return reject_fixture()
     if len(sys.argv) > 1 and sys.argv[1] == "n2":
         return n2_fixture()
+    if len(sys.argv) > 1 and sys.argv[1] == "mut_reader":
+        return mut_reader_fixture()
+    mut_reader_fixture()
     n2_fixture()
     reject_fixture()
     # ---- stage i: parse_tmptmp on weird rows, with and without masks

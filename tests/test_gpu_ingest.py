@@ -54,40 +54,24 @@ def test_ingest_matches_host_reader_on_generated_files(handle):
     assert np.array_equal(s1.block_stats[:, 0], o["shared"]) and np.array_equal(s1.block_stats[:, 1], o["notshared"])
 
 
-def test_ingest_number_formats_are_strtof_exact(handle):
-    """Decimal -> float must round exactly like strtof: halfway cases, long mantissas, exponents, signs,
-    leading / trailing zeros, no digits, inf / nan / hex (host fallback), overflow and underflow."""
-    rng = np.random.default_rng(7)
-    ages = ["0", "-0", "0.0", "+5", ".5", "5.", "1e3", "1E-3", "1.5e+2", "12345.678", "0.000123", "16777217", "16777219",
-            "33554434.000000001", "8388608.5", "8388609.5", "0.1", "0.30000001192092896", "3.4028235e38", "3.5e38", "1e39",
-            "1e-39", "1.4e-45", "7e-46", "1e-50", "inf", "-inf", "nan", "0x1p3", "1e", "1e+", "e5", "", " 12", "12 ", "1.2.3",
-            "123456789012345678", "1234567890123456789012", "0.00000000000000000000000000001", "1e400", "4.9406564584124654e-324",
-            "1000000000000000000000000", "9007199254740993", "1.17549435e-38", "1.17549421e-38"]
-    # exact float midpoints printed with all their digits, and their neighbours
-    for _ in range(200):
-        f = np.float32(np.exp(rng.uniform(-20, 20)))
-        mid = (np.float64(f) + np.float64(np.nextafter(f, np.float32(np.inf)))) / 2
-        ages += [format(mid, ".30g"), format(np.nextafter(mid, 0), ".30g"), format(np.nextafter(mid, np.inf), ".25g")]
-    for _ in range(3000):
-        x = np.exp(rng.uniform(-12, 18))
-        ages.append(format(x, rng.choice([".3f", ".6g", ".9g", ".12g", ".17g", "e", ".1f"])))
-    lines = [HEADER]
-    for i, a in enumerate(ages):
-        b = ages[(i * 7 + 3) % len(ages)]
-        pos = ["17", " 42", "+9", "-3", "007", "2147483647", "99999999999"][i % 7]
-        flip = ["0", "1", "00", "2", ""][i % 5]
-        br = ["17", "17 23", " 5", "", "1 2 3"][i % 5]
-        typ = ["A/C", "G/T", "AT/C", "A/", "/C", "0/1", "N/A", "A/C extra", "ACGTACGTACGTACGTACGT/A", "A/C"][i % 10]
-        tail = ["A;C;\n", "\n", ";\n", "A;C;10 20 30\n"][i % 4]
-        lines.append(f"{i};{pos};10;.;5;{br};0;{flip};{a};{b};{typ};".encode() + tail.encode())
-    lines.append(b"9;5;1;.;1;7;0;0;1.5;2.5")              # last line: no type field, no newline
-    text = b"".join(lines)
-    want = _host(text)
+def test_ingest_pinned_to_the_reference_reader(handle):
+    """The device parser against Mutations::Read itself (fixture tests/golden/mut_reader.npz, written from the compiled
+    reference by make_golden.py mut_reader): decimal -> float rounds exactly like std::stof on halfway cases, long mantissas,
+    exponents, signs, leading / trailing zeros, inf / nan / hex; integers like std::stoi.  Lines the reference dies on
+    (std::stoi / std::stof throw: no digits, out of range, overflow, underflow; missing fields) are refused."""
+    from helpers import load
+    z = load("mut_reader.npz")
+    text = z["text"].tobytes()
     rows = handle.ingest_mut([text])
-    assert rows == [len(want[0])]
-    _same_rows(handle.ingest_fetch(), want)
+    assert rows == [len(z["pos"])]
+    got = handle.ingest_fetch()
+    _same_rows(got, (z["pos"], z["age_begin"], z["age_end"], z["meta"]))
     st = handle.ingest_stats()
-    assert 0 < st["host_fallback_rows"] < len(ages)       # the exotic spellings went to the host, the bulk did not
+    assert 0 < st["host_fallback_rows"] < len(z["pos"]) * 3 // 5   # the exotic spellings (10-digit positions, 17-digit mantissas, midpoints ...) went to the host, plain rows did not
+    for line in z["bad"]:
+        with pytest.raises(api._lib.ColateError) as e:
+            handle.ingest_mut([HEADER + bytes(line)])
+        assert e.value.code == -5, line
 
 
 def test_ingest_errors(handle):

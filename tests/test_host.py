@@ -296,6 +296,33 @@ def test_readers_roundtrip_against_written_files(built):
             assert a == b == metas[i]
 
 
+def test_mut_reader_pinned_to_the_reference_reader(built, tmp_path):
+    """colate_read_mut against Mutations::Read ITSELF (include/src/mutations.cpp:56-283, run through oracle/ref_probe.cpp;
+    fixture tests/golden/mut_reader.npz from make_golden.py mut_reader): 3643 rows of number spellings std::stoi / std::stof
+    accept (signs, blanks, leading zeros, trailing garbage, exponents, inf / nan / hex, float midpoints with all their digits)
+    give the same positions, age bit patterns and row filter; every line the reference dies on -- a field std::stoi or
+    std::stof throws on (no digits, out of range, ERANGE overflow AND underflow), missing fields -- is refused here too."""
+    z = load("mut_reader.npz")
+    p = str(tmp_path / "good.mut")
+    open(p, "wb").write(z["text"].tobytes())
+    pos, ab, ae, meta = api.read_mut(p)
+    assert same(pos, z["pos"]) and same(meta, z["meta"])
+    assert same(ab.view(np.uint32), z["age_begin"].view(np.uint32)) and same(ae.view(np.uint32), z["age_end"].view(np.uint32))
+    assert int((meta & 1).sum()) > 300
+    head = z["text"].tobytes().split(b"\n")[0] + b"\n"
+    for line, died in zip(z["bad"], z["ref_died"]):
+        open(p, "wb").write(head + bytes(line))
+        with pytest.raises(_lib.ColateError) as e:
+            api.read_mut(p)
+        assert e.value.code == -5
+        # (one case the reference survives by reading past the end of the line -- age_end without its ';' -- is refused as well)
+        assert died or bytes(line).count(b";") == 9
+    if po.ref_available():      # live: the fixture is what the compiled reference says today
+        open(p, "wb").write(z["text"].tobytes())
+        rows = po.ref_read_mut(p)
+        assert same(rows["pos"], pos) and same(rows["age_begin"].view(np.uint32), ab.view(np.uint32)) and same(po.ref_meta(rows), meta)
+
+
 def test_mask_bits_from_fasta(built):
     sites = synth.make_sites(3, [400, 300], [3e5, 2e5])
     masks = [synth.make_mask(1, 300000, 0.4, 50, 500), synth.make_mask(2, 100000, 0.3, 50, 500, lower=True)]   # 2nd: short + lower case
