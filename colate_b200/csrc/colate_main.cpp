@@ -488,6 +488,69 @@ int run_mut(const Options& options)
   return 0;
 }
 
+// --mode make_tmp with --target_table (make_tmp(), coal.cpp:2923-3069 -> maketmp_table, 2682-2808): host-only
+int run_make_tmp(const Options& options)
+{
+  if (!options.count("mut") || !options.count("output")) {
+    std::cout << "Not enough arguments supplied." << std::endl;
+    std::cout << "Needed: mut, ref_genome, output, either of target_bcf or target_bam. Optional: filters, target_mask, strandfilter, anc_genome." << std::endl;
+    help();
+    std::cout << "Calculate coalescence rates for sample." << std::endl;
+    exit(0);
+  }
+  std::cerr << "---------------------------------------------------------" << std::endl;
+  std::cerr << "Calculating Colate tmp input file for ";
+  if (options.count("target_bcf") || options.count("target_bam")) {
+    std::cerr << std::endl << "This build writes .colate.in files from a --target_table only; bcf / bam inputs need htslib and are out of scope." << std::endl;
+    return 1;
+  }
+  if (!options.count("target_table")) { std::cerr << std::endl; return 0; }   // the reference does nothing without an input either
+  if (!options.count("ref_genome")) { std::cerr << std::endl << "Option 'ref_genome' has no value" << std::endl; return 1; }   // cxxopts throws in the reference
+  std::cerr << options.get("target_table") << ".." << std::endl;
+  std::vector<std::string> name_chr, f_mut, f_ref, f_mask;
+  if (options.count("chr")) {
+    std::ifstream is(options.get("chr"));
+    if (is.fail()) std::cerr << "Error while opening file " << options.get("chr") << std::endl;
+    std::string line;
+    while (std::getline(is, line)) {
+      name_chr.push_back(line);
+      f_mut.push_back(options.get("mut") + "_chr" + line + ".mut");
+      f_ref.push_back(options.get("ref_genome") + "_chr" + line + ".fa");
+      if (options.count("target_mask")) f_mask.push_back(options.get("target_mask") + "_chr" + line + ".fa");
+    }
+  } else {
+    name_chr.push_back("");
+    f_mut.push_back(options.get("mut"));
+    f_ref.push_back(options.get("ref_genome"));
+    if (options.count("target_mask")) f_mask.push_back(options.get("target_mask"));
+  }
+  for (size_t c = 0; c < name_chr.size(); c++) {
+    std::cerr << "parsing CHR: " << c + 1 << " / " << name_chr.size() << std::endl;
+    if (!file_exists(f_ref[c]) && !file_exists(f_ref[c] + ".gz")) {   // fasta::Read exits (data.cpp:220-223); only its presence matters here
+      std::cerr << "Error while opening file " << f_ref[c] << "." << std::endl;
+      exit(1);
+    }
+  }
+  std::vector<const char*> names, muts, masks;
+  for (size_t c = 0; c < name_chr.size(); c++) {
+    names.push_back(name_chr[c].c_str());
+    muts.push_back(f_mut[c].c_str());
+    if (!f_mask.empty()) masks.push_back(f_mask[c].c_str());
+  }
+  const std::string out = options.get("output") + ".colate.in";
+  if (colate_maketmp_table((int)names.size(), names.data(), muts.data(), options.get("target_table").c_str(), masks.empty() ? nullptr : masks.data(), 1,
+                           out.c_str()) < 0) {
+    std::cerr << colate_last_error() << std::endl;
+    exit(1);
+  }
+  rusage usage;
+  getrusage(RUSAGE_SELF, &usage);
+  std::cerr << "CPU Time spent: " << usage.ru_utime.tv_sec << "." << std::setfill('0') << std::setw(6) << usage.ru_utime.tv_usec
+            << "s; Max Memory usage: " << usage.ru_maxrss / 1000.0 << "Mb." << std::endl;
+  std::cerr << "---------------------------------------------------------" << std::endl << std::endl;
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char* argv[])
@@ -502,11 +565,12 @@ int main(int argc, char* argv[])
   const std::string mode = options.get("mode");
   int rc = 0;
   if (mode == "mut") rc = run_mut(options);
+  else if (mode == "make_tmp") rc = run_make_tmp(options);
   else {
     std::cout << "####### error #######" << std::endl;
     std::cout << "Invalid or missing mode." << std::endl;
-    std::cout << "This build implements --mode mut (tmp/tmp inputs). The reference's other modes "
-                 "(preprocess_mut, make_tmp, calc_depth, print_tmp, CondCoalRates) are out of scope." << std::endl;
+    std::cout << "This build implements --mode mut (tmp/tmp inputs) and --mode make_tmp from a --target_table. The reference's other "
+                 "modes (preprocess_mut, make_tmp from bcf / bam, calc_depth, print_tmp, CondCoalRates) are out of scope." << std::endl;
   }
   if (options.count("help")) help();
   return rc;

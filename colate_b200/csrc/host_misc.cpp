@@ -89,7 +89,7 @@ bool age_thresholds(double* thrA, double* thrP, uint16_t* lut)
 }
 
 // ---- gz/plain file slurp (igzstream semantics: gzopen reads plain files transparently) ----
-static bool slurp(const std::string& path, std::vector<char>& buf)
+bool slurp(const std::string& path, std::vector<char>& buf)
 {
   gzFile f = gzopen(path.c_str(), "rb");
   if (!f) return false;
@@ -110,7 +110,7 @@ static bool slurp(const std::string& path, std::vector<char>& buf)
   return true;
 }
 
-static bool slurp_or_gz(const std::string& path, std::vector<char>& buf)
+bool slurp_or_gz(const std::string& path, std::vector<char>& buf)
 {
   // Mutations::Read(filename) / fasta::Read: try <path>, then <path>.gz
   FILE* probe = fopen(path.c_str(), "rb");
@@ -260,7 +260,8 @@ static bool stof_like(const char* s, float* v)
 // converts with std::stoi (snp, pos, dist, tree, every branch index, is_flipped, every frequency column: it prints
 // "Error reading following line in mut file" and exits, mutations.cpp:84-88 ...) or std::stof (the two ages: the
 // exception is not caught) cannot be converted, or fields are missing (it reads past the end of the line).
-bool parse_mut_line_host(const char* p, const char* nl, int32_t* pos, float* age_begin, float* age_end, uint32_t* meta)
+bool parse_mut_line_fields(const char* p, const char* nl, int32_t* pos, float* age_begin, float* age_end, uint32_t* meta, int* flipped_out,
+                           int* n_branch_out, char* type16 /*[16], may be null*/)
 {
   // snp;pos;dist;rs-id;tree;branches;is_not_mapping;is_flipped;age_begin;age_end;type;upstream;downstream;freq...
   const char* f[11];
@@ -313,7 +314,15 @@ bool parse_mut_line_host(const char* p, const char* nl, int32_t* pos, float* age
     }
   }
   *meta = colate_site_meta(flipped, nb, ab, ae, mt);
+  if (flipped_out) *flipped_out = flipped;
+  if (n_branch_out) *n_branch_out = nb;
+  if (type16) memcpy(type16, mt, 16);
   return true;
+}
+
+bool parse_mut_line_host(const char* p, const char* nl, int32_t* pos, float* age_begin, float* age_end, uint32_t* meta)
+{
+  return parse_mut_line_fields(p, nl, pos, age_begin, age_end, meta, nullptr, nullptr, nullptr);
 }
 
 }  // namespace colate
@@ -606,4 +615,126 @@ extern "C" int64_t colate_test_colate_in_runs(const char* buf, int64_t sz, int n
   }
   colate::chr_ranges_runs(n_chr, runs, chr_first, chr_end);
   return n | ((int64_t)runs.size() << 40);
+}
+
+// ---- make_tmp from a table ------------------------------------------------------
+// fasta::Read (data.cpp:213-237): header line dropped, the rest upper-cased and concatenated
+static bool read_fasta_seq(const std::string& path, std::vector<char>& seq)
+{
+  if (!slurp_or_gz(path, seq)) return false;
+  size_t i = 0;
+  while (i < seq.size() && seq[i] != '\n') i++;
+  i++;
+  size_t len = 0;
+  for (; i < seq.size(); i++) {
+    char c = seq[i];
+    if (c == '\n') continue;
+    if (c >= 'a' && c <= 'z') c -= 32;
+    seq[len++] = c;
+  }
+  seq.resize(len);
+  return true;
+}
+
+// maketmp_table (coal.cpp:2682-2808): a .colate.in record stream for a haploid target given as a whitespace-separated
+// table of (chromosome, position, allele) triples in --chr order.  For every row of the .mut files that is not
+// flipped, maps to one branch and has single-letter allele codes (no age condition here), passes the optional mask
+// (positions at or beyond the mask end are DROPPED here, unlike in mode mut) and has a table entry at its position,
+// one record {lchrom, chrom, bp, anc, der, AAF = 1 - DAF, DAF} is written; with a reference genome (always the case
+// through the CLI) the entry must carry the ancestral or the derived allele.  The table cursor is the reference's
+// `is >> chr >> bp >> allele` stream: it persists across chromosomes, and once it runs dry nothing matches any more.
+extern "C" int64_t colate_maketmp_table(int n_chr, const char* const* chr_names, const char* const* mut_files, const char* table_file,
+                                        const char* const* target_masks, int has_ref_genome, const char* out_file)
+{
+  using colate::fail;
+  if (n_chr <= 0 || !chr_names || !mut_files || !table_file || !out_file) return fail(COLATE_ERR_ARG, "colate_maketmp_table: bad arguments");
+  std::vector<char> tab;
+  if (!colate::slurp(table_file, tab)) return fail(COLATE_ERR_IO, std::string("Error while opening file ") + table_file);
+  FILE* fp = fopen(out_file, "wb");
+  if (!fp) return fail(COLATE_ERR_IO, std::string("cannot write ") + out_file);
+  // token cursor over the table with the semantics of three chained formatted extractions
+  size_t tp = 0;
+  bool dry = false;                                   // a past extraction failed: the stream stays failed
+  std::string chr_table, allele;
+  long bp_target = -1;
+  auto token = [&](std::string& out) -> bool {
+    while (tp < tab.size() && isspace((unsigned char)tab[tp])) tp++;
+    out.clear();                                      // operator>>(string) erases first
+    if (tp >= tab.size()) return false;
+    size_t b = tp;
+    while (tp < tab.size() && !isspace((unsigned char)tab[tp])) tp++;
+    out.assign(tab.data() + b, tp - b);
+    return true;
+  };
+  auto next_triple = [&]() -> bool {
+    if (dry) return false;
+    std::string t;
+    if (!token(chr_table)) { dry = true; return false; }
+    if (!token(t)) { dry = true; return false; }
+    char* end = nullptr;
+    const long v = strtol(t.c_str(), &end, 10);
+    if (end == t.c_str()) { bp_target = 0; dry = true; return false; }     // failed int extraction stores 0
+    bp_target = v;
+    if (!token(allele)) { dry = true; return false; }
+    return true;
+  };
+  int64_t n_written = 0;
+  for (int chr = 0; chr < n_chr; chr++) {
+    const std::string name = chr_names[chr];
+    std::vector<char> mask;
+    const bool has_mask = target_masks && target_masks[chr];
+    if (has_mask && !read_fasta_seq(target_masks[chr], mask)) { fclose(fp); return fail(COLATE_ERR_IO, std::string("Error while opening file ") + target_masks[chr] + "."); }
+    std::vector<char> buf;
+    if (!colate::slurp_or_gz(mut_files[chr], buf)) { fclose(fp); return fail(COLATE_ERR_IO, std::string("Error while reading ") + mut_files[chr] + "(.gz)."); }
+    buf.push_back('\n');
+    buf.push_back('\0');
+    if (bp_target == -1) next_triple();
+    while (chr_table != name) { if (!next_triple()) break; }
+    const char* p = buf.data();
+    const char* endp = buf.data() + buf.size() - 1;
+    const char* nl = (const char*)memchr(p, '\n', endp - p);   // header line
+    p = nl ? nl + 1 : endp;
+    while (p < endp) {
+      nl = (const char*)memchr(p, '\n', endp - p);
+      if (!nl) break;
+      if (nl == p) { if (nl + 1 >= endp) break; fclose(fp); return fail(COLATE_ERR_IO, std::string("empty line in ") + mut_files[chr]); }
+      int32_t bp_mut; float ab, ae; uint32_t meta; int flipped, nb; char type[16];
+      if (!colate::parse_mut_line_fields(p, nl, &bp_mut, &ab, &ae, &meta, &flipped, &nb, type)) {
+        fclose(fp);
+        return fail(COLATE_ERR_IO, std::string("Error reading following line in mut file: ") + std::string(p, nl));
+      }
+      p = nl + 1;
+      if (!(flipped == 0 && nb == 1)) continue;
+      // single-letter codes: ancestral in {A,C,G,T,0}, derived in {A,C,G,T,1} (type[] holds at most 15 characters: anything longer is not a code)
+      const char* slash = strchr(type, '/');
+      if (!slash || slash - type != 1 || strlen(slash + 1) != 1) continue;
+      const char a = type[0], d = type[2];
+      if (!(a == 'A' || a == 'C' || a == 'G' || a == 'T' || a == '0')) continue;
+      if (!(d == 'A' || d == 'C' || d == 'G' || d == 'T' || d == '1')) continue;
+      if (has_mask) {
+        if ((uint64_t)(int64_t)bp_mut >= (uint64_t)mask.size()) continue;
+        if (bp_mut >= 1 && mask[bp_mut - 1] != 'P') continue;
+      }
+      if (chr_table == name && bp_target < bp_mut)
+        while (!dry && chr_table == name && bp_target < bp_mut) next_triple();
+      if (!(chr_table == name && bp_target == bp_mut)) continue;
+      int32_t daf = 0;
+      const bool is_anc = allele.size() == 1 && allele[0] == a, is_der = allele.size() == 1 && allele[0] == d;
+      if (has_ref_genome) {
+        if (!(is_anc || is_der)) continue;
+        if (is_der) daf = 1;
+      } else if (!is_anc) daf = 1;
+      const int32_t lchrom = (int32_t)name.size(), aaf = 1 - daf;
+      fwrite(&lchrom, 4, 1, fp);
+      fwrite(name.data(), 1, name.size(), fp);
+      fwrite(&bp_mut, 4, 1, fp);
+      fwrite(&a, 1, 1, fp);
+      fwrite(&d, 1, 1, fp);
+      fwrite(&aaf, 4, 1, fp);
+      fwrite(&daf, 4, 1, fp);
+      n_written++;
+    }
+  }
+  fclose(fp);
+  return n_written;
 }

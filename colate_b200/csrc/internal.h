@@ -79,6 +79,10 @@ int64_t decode_colate_in_host(const char* buf, int64_t sz, const std::vector<std
                               int32_t* rec_chrom, int32_t* bp, int32_t* aaf, int32_t* daf, uint16_t* alleles);
 int64_t colate_in_runs(const char* buf, int64_t sz, const std::vector<std::string>& names, std::vector<ColateInRun>& runs);
 void chr_ranges_runs(int n_chr, const std::vector<ColateInRun>& runs, int64_t* chr_first, int64_t* chr_end);
+bool slurp(const std::string& path, std::vector<char>& buf);
+bool slurp_or_gz(const std::string& path, std::vector<char>& buf);
+bool parse_mut_line_fields(const char* p, const char* nl, int32_t* pos, float* age_begin, float* age_end, uint32_t* meta, int* flipped_out,
+                           int* n_branch_out, char* type16);
 bool parse_mut_line_host(const char* p, const char* nl, int32_t* pos, float* age_begin, float* age_end, uint32_t* meta);
 
 }  // namespace colate

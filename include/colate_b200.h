@@ -240,6 +240,11 @@ int64_t colate_read_colate_in(const char* path, int n_chr, const char* const* ch
                               int32_t* rec_chrom, int32_t* bp, int32_t* aaf, int32_t* daf, uint16_t* alleles);
 /* fasta mask (data.cpp:213-237) evaluated at positions -> pass bits for rows [row0, row0+n). */
 int colate_mask_bits_from_fasta(const char* path, int64_t n, const int32_t* pos, int64_t row0, uint32_t* pass_bits);
+/* make_tmp from a table (maketmp_table, coal.cpp:2682-2808; README.md:86-127): writes the .colate.in record stream of a
+ * haploid target given as whitespace-separated (chromosome, position, allele) triples in --chr order, for the rows of the
+ * per-chromosome .mut files.  target_masks may be NULL (or hold NULL entries).  Returns the records written or < 0. */
+int64_t colate_maketmp_table(int n_chr, const char* const* chr_names, const char* const* mut_files, const char* table_file,
+                             const char* const* target_masks, int has_ref_genome, const char* out_file);
 /* <out>.coal (coal.cpp:3660-3672, 3830-3844) and the raw fp64 side output <out>.bin. */
 int colate_write_coal(const char* path, int R, int E, const double* epochs, double* rates, int is_ancient, int ep_null);
 int colate_write_bin(const char* path, int R, int E, const double* epochs, const double* rates, const int32_t* iters);

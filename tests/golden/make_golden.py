@@ -110,6 +110,52 @@ def mut_reader_fixture():
                         age_end=rows["age_end"], meta=po.ref_meta(rows), bad=np.array(bad), ref_died=np.array(died))
 
 
+def maketmp_inputs(d):
+    """Dataset + haploid table for --mode make_tmp --target_table: entries at most row positions (ancestral / derived / a third
+    allele), some at positions that are not rows, a chromosome without entries, the table ending before the last chromosome."""
+    z = np.load(os.path.join(OUT, "stage1_small.npz"), allow_pickle=False)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import dataset_from
+    sites, gt, gr = dataset_from(z)
+    rng = np.random.default_rng(5)
+    synth.write_dataset(d, sites, {"t": gt, "r": gr})
+    masks = [synth.make_mask(90 + c, int(L) if c != 0 else int(L) // 2, 0.25, lower=(c == 1)) for c, L in enumerate(sites.chrom_len)]
+    for c, nm in enumerate(sites.chr_names):
+        synth.write_mask(os.path.join(d, f"tm_chr{nm}.fa"), masks[c])
+        open(os.path.join(d, f"refg_chr{nm}.fa"), "w").write(">ref\nACGT\n")
+    lines = []
+    for c, nm in enumerate(sites.chr_names):
+        if c == 1:
+            continue                                   # no entry at all for the second chromosome
+        lo, hi = int(sites.site_off[c]), int(sites.site_off[c + 1])
+        if c == 2:
+            hi = lo + (hi - lo) * 2 // 3               # the table runs dry inside the last chromosome
+        for m in range(lo, hi):
+            u = rng.random()
+            if u < 0.25:
+                continue
+            al = chr(sites.anc[m]) if u < 0.55 else chr(sites.der[m]) if u < 0.9 else "ACGT"[int(rng.integers(0, 4))]
+            lines.append(f"{nm} {int(sites.pos[m])} {al}")
+            if u > 0.97:
+                lines.append(f"{nm} {int(sites.pos[m]) + 1} A")      # a position that is not a row (ascending order kept)
+    open(os.path.join(d, "table.txt"), "w").write("\n".join(lines) + "\n")
+    return sites
+
+
+def maketmp_fixture():
+    """`Colate --mode make_tmp --target_table` (maketmp_table, coal.cpp:2682-2808) by the reference CLI."""
+    d = tempfile.mkdtemp()
+    maketmp_inputs(d)
+    out = {}
+    for tag, extra in (("nomask", []), ("mask", ["--target_mask", d + "/tm"])):
+        pr = subprocess.run([po.ref_cli(), "--mode", "make_tmp", "--mut", d + "/syn", "--chr", d + "/chr.txt", "--target_table", d + "/table.txt",
+                             "--ref_genome", d + "/refg", "-o", d + "/" + tag] + extra, capture_output=True, text=True)
+        assert pr.returncode == 0, pr.stderr
+        out[tag] = np.frombuffer(open(d + "/" + tag + ".colate.in", "rb").read(), np.uint8)
+        print("make_tmp", tag, out[tag].shape[0], "bytes")
+    np.savez_compressed(os.path.join(OUT, "maketmp_table.npz"), **out)
+
+
 def n2_fixture():
     """the reference CLI (a) started from a <out>.colate_mat cache (coal.cpp:3169-3170, 3471-3499: parsing is
     skipped, the counts are read back from 6-digit text) and (b) warm-started from a .coal file (--coal, coal.cpp:3508-3549,
@@ -154,6 +200,9 @@ def main():
         return n2_fixture()
     if len(sys.argv) > 1 and sys.argv[1] == "mut_reader":
         return mut_reader_fixture()
+    if len(sys.argv) > 1 and sys.argv[1] == "maketmp":
+        return maketmp_fixture()
+    maketmp_fixture()
     mut_reader_fixture()
     n2_fixture()
     reject_fixture()

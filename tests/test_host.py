@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 import subprocess
+import sys
 import tempfile
 
 import numpy as np
@@ -321,6 +322,30 @@ def test_mut_reader_pinned_to_the_reference_reader(built, tmp_path):
         open(p, "wb").write(z["text"].tobytes())
         rows = po.ref_read_mut(p)
         assert same(rows["pos"], pos) and same(rows["age_begin"].view(np.uint32), ab.view(np.uint32)) and same(po.ref_meta(rows), meta)
+
+
+def test_make_tmp_from_a_table_matches_the_reference_cli(built, tmp_path):
+    """`Colate --mode make_tmp --target_table` (maketmp_table, coal.cpp:2682-2808) -- the .colate.in the host
+    writes is byte-identical to the file the reference CLI wrote from the same inputs (fixture maketmp_table.npz from
+    make_golden.py maketmp), with and without a target mask; the records then read back through colate_read_colate_in."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden
+    z = load("maketmp_table.npz")
+    d = str(tmp_path)
+    sites = make_golden.maketmp_inputs(d)
+    cli = os.path.join(ROOT, "colate_b200", "bin", "Colate")
+    for tag, extra in (("nomask", []), ("mask", ["--target_mask", d + "/tm"])):
+        r = subprocess.run([cli, "--mode", "make_tmp", "--mut", d + "/syn", "--chr", d + "/chr.txt", "--target_table", d + "/table.txt",
+                            "--ref_genome", d + "/refg", "-o", d + "/" + tag] + extra, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        got = open(d + "/" + tag + ".colate.in", "rb").read()
+        assert got == z[tag].tobytes(), tag
+        rc, bp, aaf, daf, al = api.read_colate_in(d + "/" + tag + ".colate.in", sites.chr_names)
+        assert len(bp) > 100 and set(np.unique(aaf + daf)) == {1} and 1 not in set(rc)     # haploid; nothing for the second chromosome
+    if po.ref_cli():
+        r = subprocess.run([po.ref_cli(), "--mode", "make_tmp", "--mut", d + "/syn", "--chr", d + "/chr.txt", "--target_table", d + "/table.txt",
+                            "--ref_genome", d + "/refg", "-o", d + "/live"], capture_output=True, text=True)
+        assert r.returncode == 0 and open(d + "/live.colate.in", "rb").read() == z["nomask"].tobytes()
 
 
 def test_mask_bits_from_fasta(built):
