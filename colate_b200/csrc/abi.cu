@@ -74,6 +74,7 @@ int sites_replaced(colate_handle* h)
   if (rc0) return rc0;
   h->sites_set = true;
   h->flags_done = false;
+  h->tiles_valid = false;
   for (auto& g : h->genomes) { g.set = false; g.joined = false; g.has_mask = false; }
   CK(h->order_flag.ensure((1 + COLATE_MAX_GENOMES) * 4));
   CK(cudaMemsetAsync(h->order_flag.p, 0, (1 + COLATE_MAX_GENOMES) * 4, h->stream));
@@ -146,7 +147,7 @@ void colate_destroy(colate_handle* h)
                     &h->chr_used, &h->chr_blocks, &h->chr_block_base, &h->misc, &h->u_hdr, &h->u_eb2, &h->u_ews, &h->u_ewn, &h->u_cnt,
                     &h->u_blk, &h->blk_rank_start, &h->out_f, &h->out_n, &h->thrA, &h->lut, &h->d_scratch, &h->d_prof, &h->libm_tab, &h->ing_text, &h->ing_tile_cnt, &h->ing_tile_off, &h->ing_nl, &h->ing_status, &h->ing_fb,
                     &h->windows, &h->rng_stream, &h->mt_tail, &h->poly, &h->thr10, &h->d_counts, &h->d_blockstats, &h->d_weights, &h->d_epochs,
-                    &h->d_rates, &h->d_iters, &h->d_ll, &h->d_agebin, &h->d_tmp, &h->order_flag, &h->ing_raw, &h->deep_rows};
+                    &h->d_rates, &h->d_iters, &h->d_ll, &h->d_agebin, &h->d_tmp, &h->order_flag, &h->ing_raw, &h->deep_rows, &h->tile_start, &h->tile_rlo};
   for (DevBuf* b : bufs) b->release();
   for (auto& g : h->genomes) {
     DevBuf* gb[] = {&g.bp, &g.aaf, &g.daf, &g.alleles, &g.chr_first, &g.chr_end, &g.mask_bits, &g.j_aaf, &g.j_daf, &g.j_prevbp, &g.j_flag};

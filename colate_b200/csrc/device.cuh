@@ -65,7 +65,9 @@ struct colate_handle {
   int n_chr = 0;
   int64_t n_site = 0;
   std::vector<int64_t> h_site_off;
-  colate::DevBuf site_off, pos, ab, ae, meta;
+  colate::DevBuf site_off, pos, ab, ae, meta, tile_start, tile_rlo;   // tile_*: k_join's tiles of 256 sites
+  std::vector<int32_t> h_tile_start;
+  bool tiles_valid = false;
   colate::GenomeDev genomes[COLATE_MAX_GENOMES];
   // stage-1 scratch
   bool flags_done = false, sampled = false;

@@ -7,6 +7,7 @@
 #include "internal.h"
 
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -282,6 +283,35 @@ const uint32_t* jump_poly(int q)
   if (q < 0 || q > 48) return nullptr;
   if (!gf2_init_locked(q)) return nullptr;
   return G.g[q].data();
+}
+
+// t^(3 * 200 * 2^q) mod p = g[q] * g[q + 1] mod p: the third polynomial of a radix-4 level of the jump tree
+// (kernels_mt.cu).  Schoolbook product over GF(2), then the reduction; cached.
+const uint32_t* jump_poly3(int q)
+{
+  std::lock_guard<std::mutex> lk(G_mu);
+  if (q < 0 || q > 47) return nullptr;
+  if (!gf2_init_locked(q + 1)) return nullptr;
+  static std::map<int, std::vector<uint32_t>> cache;
+  auto it = cache.find(q);
+  if (it != cache.end()) return it->second.data();
+  std::vector<uint64_t> a(NW64, 0), b(NW64, 0), prod(2 * NW64 + 2, 0);
+  for (int k = 0; k < NW64; k++) {
+    a[k] = (uint64_t)G.g[q][2 * k] | ((uint64_t)G.g[q][2 * k + 1] << 32);
+    b[k] = (uint64_t)G.g[q + 1][2 * k] | ((uint64_t)G.g[q + 1][2 * k + 1] << 32);
+  }
+  for (int i = 0; i < DEG; i++) {
+    if (!getbit(a.data(), i)) continue;
+    const int ws = i >> 6, bs = i & 63;
+    for (int k = 0; k < NW64; k++) {
+      prod[k + ws] ^= b[k] << bs;
+      if (bs) prod[k + ws + 1] ^= b[k] >> (64 - bs);
+    }
+  }
+  reduce_mod_p(prod, G.p_terms);
+  std::vector<uint32_t> g32(624);
+  for (int k = 0; k < NW64; k++) { g32[2 * k] = (uint32_t)prod[k]; g32[2 * k + 1] = (uint32_t)(prod[k] >> 32); }
+  return cache.emplace(q, std::move(g32)).first->second.data();
 }
 
 int charpoly_terms(int* out, int cap)

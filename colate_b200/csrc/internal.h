@@ -62,6 +62,7 @@ void mt_generate_window(uint32_t* w, int64_t n, uint32_t* out);
 void draw_block_weights(uint32_t* w, int R, int num_blocks, int32_t* weights);
 int64_t sample_deep_row_host(uint32_t* w, double age_begin, double len, uint8_t* cnt /*[192]*/, int64_t max_redraws);
 const uint32_t* jump_poly(int q);  // t^(200*2^q) mod p(t), 624 x u32
+const uint32_t* jump_poly3(int q); // t^(3*200*2^q) mod p(t)
 void jump_window_host(const uint32_t* w, int q, uint32_t* out);
 
 // host_misc.cpp

@@ -35,27 +35,38 @@ __device__ __forceinline__ uint32_t mt_temper_dev(uint32_t z)
   return z;
 }
 
-// windows[d] <- jump(windows[src]) for d = (2*j+1) << level, src = d - (1<<level), j = blockIdx.x / P;
-// level < 0: single jump windows[aux_dst] <- jump(windows[aux_src]).
+// windows[d] <- jump(windows[src]).  Binary level (radix 2): d = (2*j+1) << level, src = d - (1<<level).  Radix-4 level:
+// d = (4*j + r) << level for r = 1, 2, 3 from src = (4*j) << level, with the polynomials t^(r * S * 2^level) (tap list r - 1):
+// two bits of the chunk index per launch, so the latency-bound top of the tree (a handful of jumps per level) is half
+// as deep.  j / r from blockIdx.x / P;  level < 0: single jump windows[aux_dst] <- jump(windows[aux_src]).
 // A jump is split over P CTAs (P = 1, 2, 4, 8): CTA p computes outputs [p*624/P, (p+1)*624/P); inside
 // the CTA the taps are split over T = P groups of threads whose partial XORs are combined in shared
 // memory.  (One CTA per jump is bound by a single SM's shared-memory bandwidth: 624 x ~10^4 loads.)
 __global__ void __launch_bounds__(JUMP_THREADS)
-k_jump(uint32_t* __restrict__ windows, const uint16_t* __restrict__ taps, int n_taps, int level, int n_chunks, int P,
-       int aux_src, int aux_dst)
+k_jump(uint32_t* __restrict__ windows, const uint16_t* __restrict__ taps0, int n_taps0, const uint16_t* __restrict__ taps1, int n_taps1,
+       const uint16_t* __restrict__ taps2, int n_taps2, int level, int n_chunks, int P, int radix, int aux_src, int aux_dst)
 {
   extern __shared__ __align__(16) uint32_t sm[];
   uint32_t* X = sm;                                   // XLEN words (+ pad)
   uint16_t* T = (uint16_t*)(sm + ((XLEN + 3) & ~3));  // tap offsets
   uint32_t* red = (uint32_t*)(T + ((MAX_TAPS + 15) & ~15));  // [8][78] partial results
   const int tid = threadIdx.x;
-  const int j = blockIdx.x / P, p = blockIdx.x % P;
+  const int jr = blockIdx.x / P, p = blockIdx.x % P;
   int d, src;
+  const uint16_t* taps = taps0;
+  int n_taps = n_taps0;
   if (level < 0) { d = aux_dst; src = aux_src; }
-  else {
-    d = (2 * j + 1) << level;
+  else if (radix == 2) {
+    d = (2 * jr + 1) << level;
     if (d >= n_chunks) return;
     src = d - (1 << level);
+  } else {
+    const int j = jr / 3, r = jr - 3 * j + 1;
+    d = (4 * j + r) << level;
+    if (d >= n_chunks) return;
+    src = (4 * j) << level;
+    if (r == 2) { taps = taps1; n_taps = n_taps1; }
+    if (r == 3) { taps = taps2; n_taps = n_taps2; }
   }
   for (int i = tid; i < MT_N; i += blockDim.x) X[i] = windows[(size_t)src * MT_N + i];
   for (int i = tid; i < n_taps; i += blockDim.x) T[i] = taps[i];
@@ -189,14 +200,15 @@ __global__ void k_tail_gather(const uint32_t* __restrict__ stream, int64_t tile_
 // ---- tap lists per polynomial, cached per device -------------------------------------------
 struct TapList { uint16_t* d = nullptr; int n = 0; };
 static std::mutex g_mu;
-static std::map<std::pair<int, int>, TapList> g_taps;  // (device, q) -> taps
+static std::map<std::pair<int, int>, TapList> g_taps;  // (device, q or 1000 + q for the 3x polynomial) -> taps
 
-static int get_taps(int device, int q, cudaStream_t s, TapList* out)
+static int get_taps(int device, int q, cudaStream_t s, TapList* out, bool triple = false)
 {
   std::lock_guard<std::mutex> lk(g_mu);
-  auto it = g_taps.find({device, q});
+  const int key = triple ? 1000 + q : q;
+  auto it = g_taps.find({device, key});
   if (it != g_taps.end()) { *out = it->second; return 0; }
-  const uint32_t* g = jump_poly(q);
+  const uint32_t* g = triple ? jump_poly3(q) : jump_poly(q);
   if (!g) return fail(COLATE_ERR_ARG, "jump polynomial unavailable");
   std::vector<uint16_t> taps;
   taps.reserve(10500);
@@ -208,21 +220,35 @@ static int get_taps(int device, int q, cudaStream_t s, TapList* out)
   CK(cudaMemsetAsync(tl.d, 0, bytes, s));
   CK(cudaMemcpyAsync(tl.d, taps.data(), taps.size() * 2, cudaMemcpyHostToDevice, s));
   CK(cudaStreamSynchronize(s));  // taps is a local
-  g_taps[{device, q}] = tl;
+  g_taps[{device, key}] = tl;
   *out = tl;
   return 0;
 }
 
-static int launch_jump(colate_handle* h, int q, int level, int n_chunks, int n_jumps, int aux_src, int aux_dst)
+static int launch_jump(colate_handle* h, int q, int level, int n_chunks, int n_jumps, int aux_src, int aux_dst, int radix = 2)
 {
-  TapList tl;
+  TapList tl, tl2, tl3;
   int rc = get_taps(h->device, q, h->stream, &tl);
   if (rc) return rc;
-  int P = 8;
-  while (P > 1 && n_jumps * P > 2 * h->sm_count) P >>= 1;   // fill the GPU, then stop splitting
+  tl2 = tl; tl3 = tl;
+  if (radix == 4) {
+    if ((rc = get_taps(h->device, q + 1, h->stream, &tl2))) return rc;
+    if ((rc = get_taps(h->device, q, h->stream, &tl3, true))) return rc;
+  }
+  // Split factor: one CTA per SM (the base sequence alone takes 82 KB of shared memory), so a launch runs in
+  // ceil(n_jumps * P / SMs) waves of (tap work / P + the base sequence every CTA regenerates): take the cheapest
+  // (measured on B200: ~130 us of taps per jump, ~10 us for the base sequence)
+  int P = 1;
+  double best = 1e30;
+  for (int cand = 1; cand <= 8; cand *= 2) {
+    const double waves = (double)((n_jumps * cand + h->sm_count - 1) / h->sm_count);
+    const double cost = waves * (130.0 / cand + 10.0);
+    if (cost < best) { best = cost; P = cand; }
+  }
   const size_t smem = (size_t)((XLEN + 3) & ~3) * 4 + (size_t)((MAX_TAPS + 15) & ~15) * 2 + (size_t)7 * 312 * 4 + 64;
   CK(cudaFuncSetAttribute(k_jump, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_jump<<<n_jumps * P, JUMP_THREADS, smem, h->stream>>>(h->windows.as<uint32_t>(), tl.d, tl.n, level, n_chunks, P, aux_src, aux_dst);
+  k_jump<<<n_jumps * P, JUMP_THREADS, smem, h->stream>>>(h->windows.as<uint32_t>(), tl.d, tl.n, tl2.d, tl2.n, tl3.d, tl3.n, level, n_chunks, P, radix,
+                                                         aux_src, aux_dst);
   h->launches += 1;
   CK(cudaGetLastError());
   return 0;
@@ -279,10 +305,18 @@ int run_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int
   // tree over the chunks of this call
   int K = 0;
   while ((1 << K) < M) K++;
-  for (int l = K - 1; l >= 0; l--) {
-    if (M <= (1 << l)) continue;
-    int n_jumps = (M - (1 << l) + (2 << l) - 1) / (2 << l);
-    int rc = launch_jump(h, k + l, l, M, n_jumps, 0, 0);
+  int l = K - 1;
+  if (K & 1) {                                              // an odd number of index bits: the top one on its own
+    if (M > (1 << l)) {
+      int n_jumps = (M - (1 << l) + (2 << l) - 1) / (2 << l);
+      int rc = launch_jump(h, k + l, l, M, n_jumps, 0, 0);
+      if (rc) return rc;
+    }
+    l--;
+  }
+  for (l -= 1; l >= 0; l -= 2) {                            // then two bits per level: sources at multiples of 4 << l
+    const int n_src = (M + (4 << l) - 1) / (4 << l);
+    int rc = launch_jump(h, k + l, l, M, 3 * n_src, 0, 0, 4);
     if (rc) return rc;
   }
   if (total_local > 0) {

@@ -56,40 +56,103 @@ __device__ __forceinline__ int64_t rank_of(const uint32_t* __restrict__ use, con
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void k_join(int64_t n_site, int n_chr, const int64_t* __restrict__ site_off,
-                       const int32_t* __restrict__ pos, const uint32_t* __restrict__ meta,
-                       const int64_t* __restrict__ chr_first, const int64_t* __restrict__ chr_end,
-                       const int32_t* __restrict__ bp, const int32_t* __restrict__ aaf,
-                       const int32_t* __restrict__ daf, const uint16_t* __restrict__ alleles,
-                       int32_t* __restrict__ j_aaf, int32_t* __restrict__ j_daf,
-                       int32_t* __restrict__ j_prevbp, uint8_t* __restrict__ j_flag)
+// Record -> row join of one genome (coal.cpp:2181-2219 looks the row's position up in the record stream): sites and
+// records are both ascending inside a chromosome, so a TILE of 256 consecutive sites of one chromosome only ever meets
+// the records between the tile's first and last position.  k_join_bounds finds, per tile, the first record at or
+// behind the tile's first position (one global binary search per 256 sites instead of one per site); k_join stages the
+// tile's record positions in shared memory (coalesced), every site searches there, and a hit fetches the record's counts
+// and alleles from a window of a few hundred records.  Tiles whose window does not fit (records much denser than sites)
+// search in global memory as before.
+constexpr int JOIN_TILE = 256;
+constexpr int JOIN_CAP = 1024;     // record positions staged per tile
+
+__device__ __forceinline__ void join_tile_of(int n_chr, const int32_t* __restrict__ tile_start, int t, const int64_t* __restrict__ site_off,
+                                             int& c, int64_t& m0, int64_t& m1)
 {
-  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < n_site; m += (int64_t)gridDim.x * blockDim.x) {
-    int32_t a = 0, d = 0, pb = -1;
-    uint8_t fl = 0;
-    uint32_t mt = meta[m];
-    if (mt & 1u) {
-      int c = chr_of(site_off, n_chr, m);
-      int64_t first = chr_first[c], end = chr_end[c];
-      if (first >= 0) {
-        int32_t p = pos[m];
-        int64_t lo = first, hi = end;
-        while (lo < hi) {
-          int64_t mid = (lo + hi) >> 1;
-          if (bp[mid] < p) lo = mid + 1; else hi = mid;
-        }
-        if (lo < end && bp[lo] == p) {
-          fl = 1;
-          a = aaf[lo];
-          d = daf[lo];
-          pb = lo > first ? bp[lo - 1] : -1;
-          uint32_t al = alleles[lo];
-          if ((al & 0xffu) == ((mt >> 8) & 0xffu) && (al >> 8) == ((mt >> 16) & 0xffu)) fl |= 2;
-        }
-      }
+  int lo = 0, hi = n_chr;            // largest c with tile_start[c] <= t
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tile_start[mid] <= t) lo = mid; else hi = mid; }
+  c = lo;
+  m0 = site_off[c] + (int64_t)(t - tile_start[c]) * JOIN_TILE;
+  m1 = min(m0 + JOIN_TILE, site_off[c + 1]);
+}
+
+__global__ void k_join_bounds(int n_tiles, int n_chr, const int32_t* __restrict__ tile_start, const int64_t* __restrict__ site_off,
+                              const int32_t* __restrict__ pos, const int64_t* __restrict__ chr_first, const int64_t* __restrict__ chr_end,
+                              const int32_t* __restrict__ bp, int64_t* __restrict__ tile_rlo)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  int c; int64_t m0, m1;
+  join_tile_of(n_chr, tile_start, t, site_off, c, m0, m1);
+  const int64_t first = chr_first[c], end = chr_end[c];
+  int64_t lo = first, hi = end, lo2 = first, hi2 = end;
+  if (first >= 0) {
+    const int32_t p = pos[m0], q = pos[m1 - 1];      // first record at or behind the first position; first record behind the last one
+    while (lo < hi || lo2 < hi2) {                   // (the two searches side by side: their loads overlap)
+      if (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (bp[mid] < p) lo = mid + 1; else hi = mid; }
+      if (lo2 < hi2) { const int64_t mid = (lo2 + hi2) >> 1; if (bp[mid] <= q) lo2 = mid + 1; else hi2 = mid; }
     }
-    j_aaf[m] = a; j_daf[m] = d; j_prevbp[m] = pb; j_flag[m] = fl;
   }
+  tile_rlo[2 * t] = lo;
+  tile_rlo[2 * t + 1] = lo2;
+}
+
+__global__ void __launch_bounds__(JOIN_TILE)
+k_join(int n_chr, const int32_t* __restrict__ tile_start, const int64_t* __restrict__ site_off,
+       const int32_t* __restrict__ pos, const uint32_t* __restrict__ meta,
+       const int64_t* __restrict__ chr_first, const int64_t* __restrict__ chr_end, const int64_t* __restrict__ tile_rlo,
+       const int32_t* __restrict__ bp, const int32_t* __restrict__ aaf,
+       const int32_t* __restrict__ daf, const uint16_t* __restrict__ alleles,
+       int32_t* __restrict__ j_aaf, int32_t* __restrict__ j_daf,
+       int32_t* __restrict__ j_prevbp, uint8_t* __restrict__ j_flag)
+{
+  __shared__ int32_t sbp[JOIN_CAP + 1];     // bp[w0 - 1 .. w1): the window and the record in front of it
+  const int t = blockIdx.x;
+  int c; int64_t m0, m1;
+  join_tile_of(n_chr, tile_start, t, site_off, c, m0, m1);
+  const int64_t first = chr_first[c], end = chr_end[c];
+  const int64_t m = m0 + threadIdx.x;
+  if (first < 0) {                           // the reader never reaches this chromosome in this file
+    if (m < m1) { j_aaf[m] = 0; j_daf[m] = 0; j_prevbp[m] = -1; j_flag[m] = 0; }
+    return;
+  }
+  const int64_t w0 = tile_rlo[2 * t], w1 = tile_rlo[2 * t + 1];      // records with a position inside [first, last position of the tile]
+  const int64_t base = w0 > first ? w0 - 1 : w0;                       // also the record in front of the window (for j_prevbp)
+  const int n_w = (int)(w1 - base);
+  const bool staged = n_w <= JOIN_CAP + 1;
+  if (staged) for (int i = threadIdx.x; i < n_w; i += JOIN_TILE) sbp[i] = bp[base + i];
+  __syncthreads();
+  if (m >= m1) return;
+  int32_t a = 0, d = 0, pb = -1;
+  uint8_t fl = 0;
+  const uint32_t mt = meta[m];
+  if (mt & 1u) {
+    const int32_t p = pos[m];
+    int64_t k;
+    int32_t hit_bp, prev_bp = -1;
+    if (staged) {
+      int lo = (int)(w0 - base), hi = n_w;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (sbp[mid] < p) lo = mid + 1; else hi = mid; }
+      k = base + lo;
+      hit_bp = lo < n_w ? sbp[lo] : -1;
+      if (lo > 0) prev_bp = sbp[lo - 1];
+    } else {
+      int64_t lo = w0, hi = w1;
+      while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (bp[mid] < p) lo = mid + 1; else hi = mid; }
+      k = lo;
+      hit_bp = lo < w1 ? bp[lo] : -1;
+      if (lo > first) prev_bp = bp[lo - 1];
+    }
+    if (k < w1 && hit_bp == p) {
+      fl = 1;
+      a = aaf[k];
+      d = daf[k];
+      pb = k > first ? prev_bp : -1;
+      const uint32_t al = alleles[k];
+      if ((al & 0xffu) == ((mt >> 8) & 0xffu) && (al >> 8) == ((mt >> 16) & 0xffu)) fl |= 2;
+    }
+  }
+  j_aaf[m] = a; j_daf[m] = d; j_prevbp[m] = pb; j_flag[m] = fl;
 }
 
 // ---- input order (COLATE_ERR_ORDER) ---------------------------------------------------------
@@ -128,40 +191,40 @@ __global__ void k_check_genome(int64_t n_rec, int n_chr, const int64_t* __restri
       if (chr_first[c] >= 0 && k > chr_first[c] && k < chr_end[c]) *flag = 1;
 }
 
-// row filter x masks -> candidate bitmap for the reference stream (coal.cpp:2150-2181)
-__global__ void k_cand(int64_t n_site, const uint32_t* __restrict__ meta, const uint32_t* __restrict__ tmask,
-                       const uint32_t* __restrict__ rmask, uint32_t* __restrict__ cand)
-{
-  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool c = false;
-  if (m < n_site) {
-    c = meta[m] & 1u;
-    if (tmask) c = c && ((tmask[m >> 5] >> (m & 31)) & 1u);
-    if (rmask) c = c && ((rmask[m >> 5] >> (m & 31)) & 1u);
-  }
-  uint32_t b = __ballot_sync(0xffffffffu, c);
-  if ((threadIdx.x & 31) == 0 && m < n_site) cand[m >> 5] = b;
-}
-
 // one stream lookup for every candidate row (coal.cpp:2181-2199 / 2201-2219): the row keeps
 // `use` iff a record sits at its position with the same alleles, that record had not already
 // been pulled in by the look-ahead of an earlier candidate (or by the chromosome seek), and
 // DAF_ref != 0 (reference stream) / AAF+DAF != 0 (target stream).
+// candidate for the reference stream = row filter x masks (coal.cpp:2150-2181), straight from the site word and the mask bits
+__device__ __forceinline__ bool is_cand(int64_t m, const uint32_t* __restrict__ meta, const uint32_t* __restrict__ tmask,
+                                        const uint32_t* __restrict__ rmask)
+{
+  bool c = meta[m] & 1u;
+  if (tmask) c = c && ((tmask[m >> 5] >> (m & 31)) & 1u);
+  if (rmask) c = c && ((rmask[m >> 5] >> (m & 31)) & 1u);
+  return c;
+}
+
 template <bool IS_REF>
 __global__ void k_ok(int64_t n_site, int n_chr, const int64_t* __restrict__ site_off, const int32_t* __restrict__ pos,
-                     const uint32_t* __restrict__ in_bits, const int32_t* __restrict__ j_aaf,
+                     const uint32_t* __restrict__ in_bits, const uint32_t* __restrict__ tmask, const uint32_t* __restrict__ rmask,
+                     const int32_t* __restrict__ j_aaf,
                      const int32_t* __restrict__ j_daf, const int32_t* __restrict__ j_prevbp,
                      const uint8_t* __restrict__ j_flag, uint32_t* __restrict__ out_bits, const uint32_t* __restrict__ meta,
                      int64_t* __restrict__ misc)
 {
   int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool ok = false;
-  if (m < n_site && ((in_bits[m >> 5] >> (m & 31)) & 1u)) {
+  // the reference stream's candidates come straight from the site words (no bitmap pass in front of this kernel), the
+  // target stream's from the bitmap the reference pass wrote
+  if (m < n_site && (IS_REF ? is_cand(m, meta, tmask, rmask) : ((in_bits[m >> 5] >> (m & 31)) & 1u) != 0)) {
     if ((j_flag[m] & 3) == 3) {
       bool cnt = IS_REF ? (j_daf[m] != 0) : ((j_aaf[m] + j_daf[m]) != 0);
       if (cnt) {
         int64_t lo = site_off[chr_of(site_off, n_chr, m)];
-        int64_t p = prev_set(in_bits, m, lo);
+        int64_t p;
+        if (IS_REF) { p = m - 1; while (p >= lo && !is_cand(p, meta, tmask, rmask)) p--; if (p < lo) p = -1; }   // 93 % of the rows are candidates: one step
+        else p = prev_set(in_bits, m, lo);
         int32_t prev_cand_pos = p >= 0 ? pos[p] : 0;
         ok = prev_cand_pos <= j_prevbp[m];
       }
@@ -228,22 +291,35 @@ __global__ void k_chr(int n_chr, const int64_t* __restrict__ site_off, const int
                       int64_t* __restrict__ chr_used, int32_t* __restrict__ chr_blocks, int32_t* __restrict__ chr_block_base,
                       int64_t* __restrict__ misc)
 {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  int base = 0;
-  int64_t tot = 0;
-  for (int c = 0; c < n_chr; c++) {
-    int64_t lo = site_off[c], hi = site_off[c + 1];
-    int64_t used = rank_of(use, word_rank, hi) - rank_of(use, word_rank, lo);
-    int64_t p = hi > lo ? prev_set(use, hi, lo) : -1;
-    int nb = p >= 0 ? (pos[p] - 1) / COLATE_BLOCK_BASES + 1 : 1;
-    chr_used[c] = used;
-    chr_blocks[c] = nb;
-    chr_block_base[c] = base;
-    base += nb;
-    tot += used;
+  // thread = chromosome for the lookups (dependent loads), then one thread strings the block bases together
+  __shared__ int s_nb[1024];
+  __shared__ long long s_used[1024];
+  for (int c0 = 0; c0 < n_chr; c0 += 1024) {                  // (more than 1024 chromosomes: in rounds; the running sums live in misc)
+    const int c = c0 + threadIdx.x;
+    if (c < n_chr) {
+      const int64_t lo = site_off[c], hi = site_off[c + 1];
+      const int64_t used = rank_of(use, word_rank, hi) - rank_of(use, word_rank, lo);
+      const int64_t p = hi > lo ? prev_set(use, hi, lo) : -1;
+      s_nb[threadIdx.x] = p >= 0 ? (pos[p] - 1) / COLATE_BLOCK_BASES + 1 : 1;
+      s_used[threadIdx.x] = used;
+      chr_used[c] = used;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int base = c0 ? (int)misc[1] : 0;
+      int64_t tot = c0 ? misc[0] : 0;
+      for (int i = 0; i < min(1024, n_chr - c0); i++) {
+        chr_blocks[c0 + i] = s_nb[i];
+        chr_block_base[c0 + i] = base;
+        base += s_nb[i];
+        tot += s_used[i];
+      }
+      misc[0] = tot;
+      misc[1] = base;
+    }
+    __syncthreads();
   }
-  misc[0] = tot;
-  misc[1] = base;
+  if (n_chr == 0 && threadIdx.x == 0) { misc[0] = 0; misc[1] = 0; }
 }
 
 // used rows -> dense records in rank order:
@@ -830,13 +906,26 @@ int run_join(colate_handle* h, int slot)
   const int64_t n = h->n_site;
   CK(g.j_aaf.ensure(n * 4 + 4)); CK(g.j_daf.ensure(n * 4 + 4)); CK(g.j_prevbp.ensure(n * 4 + 4)); CK(g.j_flag.ensure(n + 4));
   if (n > 0) {
-    int grid = (int)std::min<int64_t>(grid_for(n, 256), (int64_t)h->sm_count * 16);
-    k_join<<<grid, 256, 0, h->stream>>>(n, h->n_chr, h->site_off.as<int64_t>(), h->pos.as<int32_t>(), h->meta.as<uint32_t>(),
-                                        g.chr_first.as<int64_t>(), g.chr_end.as<int64_t>(), g.bp.as<int32_t>(),
-                                        g.aaf.as<int32_t>(), g.daf.as<int32_t>(), g.alleles.as<uint16_t>(),
-                                        g.j_aaf.as<int32_t>(), g.j_daf.as<int32_t>(), g.j_prevbp.as<int32_t>(), g.j_flag.as<uint8_t>());
+    // tiles of JOIN_TILE sites, never across a chromosome boundary
+    if ((int)h->h_tile_start.size() != h->n_chr + 1 || !h->tiles_valid) {
+      h->h_tile_start.assign(h->n_chr + 1, 0);
+      for (int c = 0; c < h->n_chr; c++)
+        h->h_tile_start[c + 1] = h->h_tile_start[c] + (int32_t)((h->h_site_off[c + 1] - h->h_site_off[c] + JOIN_TILE - 1) / JOIN_TILE);
+      CK(h->tile_start.ensure((h->n_chr + 1) * 4));
+      CK(cudaMemcpyAsync(h->tile_start.p, h->h_tile_start.data(), (h->n_chr + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+      h->tiles_valid = true;
+    }
+    const int n_tiles = h->h_tile_start[h->n_chr];
+    CK(h->tile_rlo.ensure((size_t)(n_tiles + 1) * 16));
+    k_join_bounds<<<grid_for(n_tiles, 256), 256, 0, h->stream>>>(n_tiles, h->n_chr, h->tile_start.as<int32_t>(), h->site_off.as<int64_t>(),
+                                                                h->pos.as<int32_t>(), g.chr_first.as<int64_t>(), g.chr_end.as<int64_t>(),
+                                                                g.bp.as<int32_t>(), h->tile_rlo.as<int64_t>());
+    k_join<<<n_tiles, JOIN_TILE, 0, h->stream>>>(h->n_chr, h->tile_start.as<int32_t>(), h->site_off.as<int64_t>(), h->pos.as<int32_t>(),
+                                                 h->meta.as<uint32_t>(), g.chr_first.as<int64_t>(), g.chr_end.as<int64_t>(), h->tile_rlo.as<int64_t>(),
+                                                 g.bp.as<int32_t>(), g.aaf.as<int32_t>(), g.daf.as<int32_t>(), g.alleles.as<uint16_t>(),
+                                                 g.j_aaf.as<int32_t>(), g.j_daf.as<int32_t>(), g.j_prevbp.as<int32_t>(), g.j_flag.as<uint8_t>());
     CK(cudaGetLastError());
-    h->launches += 1;
+    h->launches += 2;
   }
   g.joined = true;
   return 0;
@@ -883,22 +972,21 @@ int run_flags(colate_handle* h, int tslot, int rslot)
   uint32_t* total = (uint32_t*)((char*)h->misc.p + 56);
   if (n > 0) {
     int grid = grid_for(n, 256);
-    k_cand<<<grid, 256, 0, s>>>(n, h->meta.as<uint32_t>(), T.has_mask ? T.mask_bits.as<uint32_t>() : nullptr,
-                                R.has_mask ? R.mask_bits.as<uint32_t>() : nullptr, h->candR.as<uint32_t>());
-    k_ok<true><<<grid, 256, 0, s>>>(n, h->n_chr, h->site_off.as<int64_t>(), h->pos.as<int32_t>(), h->candR.as<uint32_t>(),
+    k_ok<true><<<grid, 256, 0, s>>>(n, h->n_chr, h->site_off.as<int64_t>(), h->pos.as<int32_t>(), nullptr,
+                                    T.has_mask ? T.mask_bits.as<uint32_t>() : nullptr, R.has_mask ? R.mask_bits.as<uint32_t>() : nullptr,
                                     R.j_aaf.as<int32_t>(), R.j_daf.as<int32_t>(), R.j_prevbp.as<int32_t>(), R.j_flag.as<uint8_t>(),
                                     h->candT.as<uint32_t>(), h->meta.as<uint32_t>(), h->misc.as<int64_t>());
-    k_ok<false><<<grid, 256, 0, s>>>(n, h->n_chr, h->site_off.as<int64_t>(), h->pos.as<int32_t>(), h->candT.as<uint32_t>(),
+    k_ok<false><<<grid, 256, 0, s>>>(n, h->n_chr, h->site_off.as<int64_t>(), h->pos.as<int32_t>(), h->candT.as<uint32_t>(), nullptr, nullptr,
                                      T.j_aaf.as<int32_t>(), T.j_daf.as<int32_t>(), T.j_prevbp.as<int32_t>(), T.j_flag.as<uint8_t>(),
                                      h->use.as<uint32_t>(), h->meta.as<uint32_t>(), h->misc.as<int64_t>());
     k_popc_blocksum<<<nsb, SCAN_THREADS, 0, s>>>(h->use.as<uint32_t>(), nw, h->scan_tmp.as<uint32_t>());
     k_scan_sums<<<1, 32, 0, s>>>(h->scan_tmp.as<uint32_t>(), nsb, total);
     k_word_rank<<<nsb, SCAN_THREADS, 0, s>>>(h->use.as<uint32_t>(), nw, h->scan_tmp.as<uint32_t>(), total, h->word_rank.as<uint32_t>());
-    h->launches += 6;
+    h->launches += 5;
   } else {
     CK(cudaMemsetAsync(h->word_rank.p, 0, 8, s));
   }
-  k_chr<<<1, 32, 0, s>>>(h->n_chr, h->site_off.as<int64_t>(), h->pos.as<int32_t>(), h->use.as<uint32_t>(), h->word_rank.as<uint32_t>(),
+  k_chr<<<1, 1024, 0, s>>>(h->n_chr, h->site_off.as<int64_t>(), h->pos.as<int32_t>(), h->use.as<uint32_t>(), h->word_rank.as<uint32_t>(),
                          h->chr_used.as<int64_t>(), h->chr_blocks.as<int32_t>(), h->chr_block_base.as<int32_t>(), h->misc.as<int64_t>());
   h->launches += 1;
   CK(cudaGetLastError());
