@@ -52,6 +52,7 @@ SIGNATURES = {
     "colate_set_stream_cache": (C.c_int, [VP, C.c_int]),
     "colate_set_sites": (C.c_int, [VP, C.c_int, VP, VP, VP, VP, VP, C.c_int]),
     "colate_set_genome": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, C.c_int]),
+    "colate_set_pileup": (C.c_int, [VP, C.c_int, VP, C.c_int]),
     "colate_set_mask": (C.c_int, [VP, C.c_int, VP, C.c_int]),
     "colate_stage1_flags": (C.c_int, [VP, C.c_int, C.c_int, VP, VP]),
     "colate_stage1_sample": (C.c_int, [VP, VP, C.c_int64, C.c_int, VP, VP, VP]),
@@ -85,6 +86,7 @@ SIGNATURES = {
     "colate_read_colate_in": (C.c_int64, [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.c_int64, VP, VP, VP, VP, VP]),
     "colate_mask_bits_from_fasta": (C.c_int, [C.c_char_p, C.c_int64, VP, C.c_int64, VP]),
     "colate_maketmp_table": (C.c_int64, [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_char_p]),
+    "colate_write_colate_mat": (C.c_int, [C.c_char_p, C.c_int, f64, f64]),
     "colate_write_coal": (C.c_int, [C.c_char_p, C.c_int, C.c_int, f64, f64, C.c_int, C.c_int]),
     "colate_write_bin": (C.c_int, [C.c_char_p, C.c_int, C.c_int, f64, f64, i32]),
 }

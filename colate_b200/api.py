@@ -185,6 +185,13 @@ class Handle:
         check(lib().colate_set_genome(self._h, slot, n_rec, C.c_void_p(first_ptr), C.c_void_p(end_ptr), C.c_void_p(bp_ptr),
                                       C.c_void_p(aaf_ptr), C.c_void_p(daf_ptr), C.c_void_p(alleles_ptr), 1))
 
+    def set_pileup(self, slot, counts):
+        """N3 (bam / bcf front-ends from pre-decoded arrays): counts[n_site][4] = reads showing A, C, G, T at every .mut row's
+        position (zeros: not covered) instead of a .colate.in record stream.  Use with set_option("front_end", 1)."""
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        assert counts.shape == (self.n_site, 4)
+        check(lib().colate_set_pileup(self._h, slot, ptr(counts), 0))
+
     def set_mask(self, slot, pass_bits):
         if pass_bits is None:
             check(lib().colate_set_mask(self._h, slot, None, 0))
@@ -409,3 +416,10 @@ def write_bin(path: str, epochs, rates, iters):
     r = np.ascontiguousarray(rates, dtype=np.float64)
     check(lib().colate_write_bin(path.encode(), r.shape[0], r.shape[1], np.ascontiguousarray(epochs, dtype=np.float64), r,
                                  np.ascontiguousarray(iters, dtype=np.int32)))
+
+
+def write_colate_mat(path: str, counts, age_bin=None):
+    """<out>.colate_mat (coal.cpp:3336-3343, 3453-3465): counts[R][2][185], already normalised."""
+    c = np.ascontiguousarray(counts, dtype=np.float64)
+    ab = age_bins() if age_bin is None else np.ascontiguousarray(age_bin, dtype=np.float64)
+    check(lib().colate_write_colate_mat(path.encode(), c.shape[0], ab, c))

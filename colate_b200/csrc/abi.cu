@@ -150,7 +150,7 @@ void colate_destroy(colate_handle* h)
                     &h->d_rates, &h->d_iters, &h->d_ll, &h->d_agebin, &h->d_tmp, &h->order_flag, &h->ing_raw, &h->deep_rows, &h->tile_start, &h->tile_rlo};
   for (DevBuf* b : bufs) b->release();
   for (auto& g : h->genomes) {
-    DevBuf* gb[] = {&g.bp, &g.aaf, &g.daf, &g.alleles, &g.chr_first, &g.chr_end, &g.mask_bits, &g.j_aaf, &g.j_daf, &g.j_prevbp, &g.j_flag};
+    DevBuf* gb[] = {&g.bp, &g.aaf, &g.daf, &g.alleles, &g.chr_first, &g.chr_end, &g.mask_bits, &g.j_aaf, &g.j_daf, &g.j_prevbp, &g.j_flag, &g.pile};
     for (DevBuf* b : gb) b->release();
   }
   for (int k = 0; k < 2; k++) if (h->ing_bounce[k]) { cudaFreeHost(h->ing_bounce[k]); cudaEventDestroy(h->ing_bounce_ev[k]); }
@@ -220,7 +220,27 @@ int colate_set_genome(colate_handle* h, int slot, int64_t n_rec, const int64_t* 
   if ((rc = copy_in(g.daf.p, daf, n_rec * 4, location, h->stream))) return rc;
   if ((rc = copy_in(g.alleles.p, alleles, n_rec * 2, location, h->stream))) return rc;
   g.n_rec = n_rec;
+  g.pileup = false;
   if ((rc = genome_replaced(h, slot))) return rc;
+  if (!h->opt_async_uploads) CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int colate_set_pileup(colate_handle* h, int slot, const int32_t* counts, int location)
+{
+  if (!h || slot < 0 || slot >= COLATE_MAX_GENOMES || !counts) return fail(COLATE_ERR_ARG, "colate_set_pileup: bad arguments");
+  if (!h->sites_set) return fail(COLATE_ERR_STATE, "colate_set_pileup: call colate_set_sites first");
+  CK(cudaSetDevice(h->device));
+  GenomeDev& g = h->genomes[slot];
+  CK(g.pile.ensure((size_t)h->n_site * 16 + 16));
+  int rc;
+  if ((rc = copy_in(g.pile.p, counts, (size_t)h->n_site * 16, location, h->stream))) return rc;
+  g.n_rec = 0;
+  g.pileup = true;
+  g.set = true;
+  g.joined = false;
+  h->flags_done = false;
+  CK(cudaMemsetAsync(h->order_flag.as<int>() + 1 + slot, 0, 4, h->stream));   // no record stream, nothing to be out of order
   if (!h->opt_async_uploads) CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -276,6 +296,9 @@ int colate_stage1_flags(colate_handle* h, int target_slot, int reference_slot, i
   h->n_used = misc[0];
   h->n_blocks_local = (int)misc[1];
   h->n_deep = misc[4];
+  if (h->opt_raw_weights && h->n_deep > 0)
+    return fail(COLATE_ERR_AGE_RANGE, "a used row with age_begin > 0 has an age interval beyond the age grid: the bcf / bam front-ends write past the end "
+                                      "of the histogram there (coal.cpp:2034-2039 has no bound check, unlike the tmp/tmp path's coal.cpp:2289)");
   if (misc[3])
     return fail(COLATE_ERR_AGE_RANGE, "a used row cannot be processed by the reference either: age_begin <= 0 with an age interval beyond "
                                       "the age grid (~9.3e6 generations; out-of-bounds write at coal.cpp:2269), or age_begin itself beyond it "
@@ -416,6 +439,15 @@ int colate_set_option(colate_handle* h, const char* key, int64_t value)
   // async_uploads = 1: colate_set_sites / colate_set_genome / colate_set_mask queue their copies and return; the
   // caller keeps the (pinned) host buffers unchanged until the next colate_stage1_flags() has returned
   if (!strcmp(key, "async_uploads")) { h->opt_async_uploads = value != 0; return 0; }
+  // front_end: which of mut()'s input branches the handle reproduces (coal.cpp:3175-3319).  0 = tmp/tmp (parse_tmptmp: pseudo-
+  // genotype weights, no normalisation).  1 = the bcf / bam front-ends fed from pre-decoded per-row counts:
+  // raw count weights (coal.cpp:2005-2039, 1164-1197) and both count vectors of stage ii divided by 1e3 (coal.cpp:3453-3463).
+  if (!strcmp(key, "front_end")) {
+    if (value != 0 && value != 1) return fail(COLATE_ERR_ARG, "front_end: 0 (tmp/tmp) or 1 (pre-decoded bcf / bam counts)");
+    h->opt_raw_weights = h->opt_norm_1e3 = value == 1;
+    h->flags_done = false;
+    return 0;
+  }
   return fail(COLATE_ERR_ARG, std::string("unknown option ") + key);
 }
 

@@ -39,6 +39,8 @@ struct DevBuf {
 // one .colate.in file on the device, plus its join onto the site axis
 struct GenomeDev {
   bool set = false, joined = false, has_mask = false;
+  bool pileup = false;        // slot filled by colate_set_pileup: `pile` = int32[n_site][4] reads showing A, C, G, T per row
+  DevBuf pile;
   int64_t n_rec = 0;
   DevBuf bp, aaf, daf, alleles, chr_first, chr_end, mask_bits;
   // join (site-aligned): counts of the record at the row's position, position of the record
@@ -100,6 +102,8 @@ struct colate_handle {
   int em_kernel = -1, em_csize = 0;   // last EM launch: 0 k_em, 1 k_em_split, 2 k_em_cta; CTAs per replicate
   int64_t launches = 0;
   bool opt_rejoin = false, opt_async_uploads = false;
+  bool opt_raw_weights = false;   // N3: weights of the bcf / bam front-ends (raw counts) instead of tmp/tmp's pseudo-genotype
+  bool opt_norm_1e3 = false;      // N3: stage ii divides both count vectors by 1e3 (coal.cpp:3453-3463, every front-end but tmp/tmp)
   // GPU-side .mut ingest (kernels_ingest.cu)
   bool ing_active = false;
   int ing_nchr = 0;

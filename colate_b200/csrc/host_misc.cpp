@@ -586,6 +586,22 @@ int colate_write_coal(const char* path, int R, int E, const double* epochs, doub
   return 0;
 }
 
+int colate_write_colate_mat(const char* path, int R, const double* age_bin, const double* counts)
+{
+  // coal.cpp:3336-3343 (grid line) and 3453-3465 (two lines per replicate), operator<<(double) with default flags == "%g"
+  if (!path || R <= 0 || !age_bin || !counts) return fail(COLATE_ERR_ARG, "colate_write_colate_mat: bad arguments");
+  FILE* f = fopen(path, "w");
+  if (!f) return fail(COLATE_ERR_IO, std::string("cannot write ") + path);
+  for (int b = 0; b < colate::NBINS; b++) fprintf(f, "%g ", age_bin[b]);
+  fprintf(f, "\n");
+  for (int i = 0; i < 2 * R; i++) {
+    for (int b = 0; b < colate::NBINS; b++) fprintf(f, "%g ", counts[(size_t)i * colate::NBINS + b]);
+    fprintf(f, "\n");
+  }
+  fclose(f);
+  return 0;
+}
+
 int colate_write_bin(const char* path, int R, int E, const double* epochs, const double* rates, const int32_t* iters)
 {
   FILE* f = fopen(path, "wb");

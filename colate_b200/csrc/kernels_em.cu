@@ -20,13 +20,21 @@ constexpr int EM_THREADS = 416;  // 12 task warps + 1 warp for the prefix chain
 constexpr int EM_TASKS = 384;  // 2 x 185 (bin, shared / not shared) padded; task = 2*bin + type
 
 // ---- stage ii ------------------------------------------------------------------------------
+// One CTA per replicate.  Block sums per bin in block order (thread = bin), then the F redistribution of
+// coal.cpp:3392-3441: its two running sums (fcount, normf) are 185 dependent additions each and stay on one thread in bin
+// order; the divisions and products around them are independent per bin and run one bin per thread (a serial version
+// of the whole redistribution took 120 us per launch: 370 dependent fp64 divisions).
+// norm_1e3: the front-ends other than tmp/tmp divide both vectors by 1e3 afterwards (coal.cpp:3453-3463, tmp_file == true).
 __global__ void __launch_bounds__(256)
 k_bootstrap(int num_blocks, const int32_t* __restrict__ weights, const double* __restrict__ blk,
-            double age, const double* __restrict__ age_bin, double* __restrict__ counts)
+            double age, const double* __restrict__ age_bin, double* __restrict__ counts, int norm_1e3)
 {
   __shared__ double S[NBINS], N[NBINS], SE[NBINS], NE[NBINS], F[NBINS];
+  __shared__ double s_fcount, s_normf;
   const int r = blockIdx.x;
   const int32_t* w = weights + (size_t)r * num_blocks;
+  int bin_start = 0;
+  while (bin_start < NBINS - 1 && age_bin[bin_start] <= age) bin_start++;      // coal.cpp:3394-3396
   for (int b = threadIdx.x; b < NBINS; b += blockDim.x) {
     double s = 0.0, n = 0.0, se = 0.0, ne = 0.0;
     for (int j = 0; j < num_blocks; j++) {  // coal.cpp:3358-3390, block order kept
@@ -39,33 +47,34 @@ k_bootstrap(int num_blocks, const int32_t* __restrict__ weights, const double* _
         ne = __dadd_rn(ne, __dmul_rn(bw, v[3 * NBINS]));
       }
     }
-    S[b] = s; N[b] = n; SE[b] = se; NE[b] = ne; F[b] = 0.0;
+    S[b] = s; N[b] = n; SE[b] = se; NE[b] = ne;
+    // coal.cpp:3406-3417: F[bin] = emp share of bin, bins from bin_start on
+    F[b] = (b >= bin_start && se > 0) ? __ddiv_rn(se, __dadd_rn(se, ne)) : 0.0;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {  // serial sums in bin order, coal.cpp:3392-3441
-    int bin = 0;
-    while (bin < NBINS - 1 && age_bin[bin] <= age) bin++;
-    const int bin_start = bin;
-    double lower_age = age_bin[bin_start - 1];
+  // coal.cpp:3420-3425: F[bin - 1] *= age_bin[bin] - lower_age for bin = bin_start .. 184, lower_age = age_bin[bin - 1] (the first
+  // one age_bin[bin_start - 1] as well): slot k = bin - 1 is scaled by the width of the bin above it
+  for (int k = threadIdx.x; k < NBINS - 1; k += blockDim.x)
+    if (k >= bin_start - 1) F[k] = __dmul_rn(F[k], __dsub_rn(age_bin[k + 1], age_bin[k]));
+  __syncthreads();
+  if (threadIdx.x == 0) {         // the two running sums in bin order
     double fcount = 0.0;
-    for (bin = bin_start; bin < NBINS; bin++) {
-      fcount = __dadd_rn(fcount, SE[bin]);
-      if (SE[bin] > 0) F[bin] = __ddiv_rn(SE[bin], __dadd_rn(SE[bin], NE[bin]));
-    }
-    for (bin = bin_start; bin < NBINS; bin++) {
-      F[bin - 1] = __dmul_rn(F[bin - 1], __dsub_rn(age_bin[bin], lower_age));
-      lower_age = age_bin[bin];
-    }
+    for (int bin = bin_start; bin < NBINS; bin++) fcount = __dadd_rn(fcount, SE[bin]);
+    s_fcount = fcount;
+  } else if (threadIdx.x == 32) {
     double normf = 0.0;
-    for (bin = 0; bin < NBINS; bin++) normf = __dadd_rn(normf, F[bin]);
-    for (bin = 0; bin < NBINS; bin++) {
-      double f = __dmul_rn(__ddiv_rn(F[bin], normf), fcount);
-      S[bin] = __dadd_rn(S[bin], (0.0 < f) ? f : 0.0);  // std::max(0.0, f): NaN -> 0.0
-    }
+    for (int bin = 0; bin < NBINS; bin++) normf = __dadd_rn(normf, F[bin]);
+    s_normf = normf;
   }
   __syncthreads();
   double* out = counts + (size_t)r * 2 * NBINS;
-  for (int b = threadIdx.x; b < NBINS; b += blockDim.x) { out[b] = S[b]; out[NBINS + b] = N[b]; }
+  for (int b = threadIdx.x; b < NBINS; b += blockDim.x) {
+    const double f = __dmul_rn(__ddiv_rn(F[b], s_normf), s_fcount);   // coal.cpp:3435-3441
+    double s = __dadd_rn(S[b], (0.0 < f) ? f : 0.0);                  // std::max(0.0, f): NaN -> 0.0
+    double n = N[b];
+    if (norm_1e3) { s = __ddiv_rn(s, 1e3); n = __ddiv_rn(n, 1e3); }
+    out[b] = s; out[NBINS + b] = n;
+  }
 }
 
 // ---- E-step pieces (coal_EM.cpp) -----------------------------------------------------------
@@ -1309,7 +1318,7 @@ int ensure_libm_tables(colate_handle* h)
 int run_bootstrap(colate_handle* h, int R, int num_blocks, const double* block_stats_dev, double age)
 {
   k_bootstrap<<<R, 256, 0, h->stream>>>(num_blocks, h->d_weights.as<int32_t>(), block_stats_dev, age,
-                                        h->d_agebin.as<double>(), h->d_counts.as<double>());
+                                        h->d_agebin.as<double>(), h->d_counts.as<double>(), h->opt_norm_1e3 ? 1 : 0);
   h->launches += 1;
   CK(cudaGetLastError());
   return 0;

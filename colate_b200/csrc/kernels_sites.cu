@@ -155,6 +155,35 @@ k_join(int n_chr, const int32_t* __restrict__ tile_start, const int64_t* __restr
   j_aaf[m] = a; j_daf[m] = d; j_prevbp[m] = pb; j_flag[m] = fl;
 }
 
+// Pileup genome (the bam front-ends, coal.cpp:1884-1929 reference / 1935-1980 target): the decoder hands
+// over, per .mut row, the reads showing A, C, G, T at the row's position (bam_parser::count_alleles at bp_mut - 1; all zero =
+// not covered).  The row's own alleles pick AAF / DAF out of the four counts ('0' / '1' pick nothing: 0); the row is usable iff
+// reads > 0, (AAF > 0 || DAF > 0) and at most two alleles were seen (coal.cpp:1916-1917, 1967-1968).  The pileup ring is
+// random access, so there is no look-ahead rule: j_prevbp = INT_MAX lets every candidate pass k_ok's stream test.
+__device__ __forceinline__ int acgt_index(uint32_t c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
+__global__ void k_pileup_join(int64_t n_site, const uint32_t* __restrict__ meta, const int4* __restrict__ counts,
+                              int32_t* __restrict__ j_aaf, int32_t* __restrict__ j_daf, int32_t* __restrict__ j_prevbp, uint8_t* __restrict__ j_flag)
+{
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_site) return;
+  const uint32_t mt = meta[m];
+  int32_t a = 0, d = 0;
+  uint8_t fl = 0;
+  if (mt & 1u) {
+    const int4 c = counts[m];
+    const int cc[4] = {c.x, c.y, c.z, c.w};
+    const int reads = c.x + c.y + c.z + c.w;
+    const int n_alleles = (c.x > 0) + (c.y > 0) + (c.z > 0) + (c.w > 0);
+    const int ia = acgt_index((mt >> 8) & 0xffu), id = acgt_index((mt >> 16) & 0xffu);
+    if (reads > 0) {                               // (the counts stay 0 otherwise: coal.cpp:1879-1882)
+      if (ia >= 0) a = cc[ia];
+      if (id >= 0) d = cc[id];
+      if ((a > 0 || d > 0) && n_alleles <= 2) fl = 3;
+    }
+  }
+  j_aaf[m] = a; j_daf[m] = d; j_prevbp[m] = 0x7fffffff; j_flag[m] = fl;
+}
+
 // ---- input order (COLATE_ERR_ORDER) ---------------------------------------------------------
 // k_join's binary search and the find-previous-candidate rule of k_ok equal the reference's sequential reader
 // (coal.cpp:2184-2217) only on ascending positions: .mut rows ascending within a chromosome, .colate.in records
@@ -335,7 +364,7 @@ __global__ void k_compact(int64_t n_site, int n_chr, const int64_t* __restrict__
                           const double* __restrict__ thr10,
                           double4* __restrict__ hdr, uint8_t* __restrict__ e_b2, double* __restrict__ e_ws,
                           double* __restrict__ e_wn, int32_t* __restrict__ u_blk, int64_t* __restrict__ misc,
-                          const uint32_t* __restrict__ meta, int64_t* __restrict__ deep_rows, int64_t deep_cap)
+                          const uint32_t* __restrict__ meta, int64_t* __restrict__ deep_rows, int64_t deep_cap, int raw_weights)
 {
   // thread = used row (rank r): one row in eight is used, so a thread per site would leave the warps of the
   // division-heavy part below nearly empty.  Site of rank r: the last bitmap word whose exclusive rank is <= r
@@ -362,8 +391,10 @@ __global__ void k_compact(int64_t n_site, int n_chr, const int64_t* __restrict__
   const int32_t dafr = r_daf[m], nr = r_daf[m] + r_aaf[m];
   const double abd = (double)b;
   // float * int -> float, then / double (coal.cpp:2255-2256, 2269, 2291-2292)
-  const double num_s = (double)__fmul_rn(fd, __int2float_rn(dafr));
-  const double num_n = (double)__fmul_rn(fa, __int2float_rn(dafr));
+  // raw_weights (the bcf / bam front-ends): the counts themselves, int * int -> double
+  // (coal.cpp:2005-2006, 2019, 2038-2039; 1164-1165, 1179, 1196-1197 with AAF_target = N_target - DAF_target)
+  const double num_s = raw_weights ? (double)(dt * dafr) : (double)__fmul_rn(fd, __int2float_rn(dafr));
+  const double num_n = raw_weights ? (double)(at * dafr) : (double)__fmul_rn(fa, __int2float_rn(dafr));
   const double den = __dmul_rn((double)nr, 100.0);
   // .x = (age_end - age_begin) * 2^-64: the sampling kernel multiplies it with the 64-bit integer
   // x2:x1 converted once (exact power-of-two scaling, same rounding as U * (age_end - age_begin))
@@ -905,6 +936,16 @@ int run_join(colate_handle* h, int slot)
   if (g.joined) return 0;
   const int64_t n = h->n_site;
   CK(g.j_aaf.ensure(n * 4 + 4)); CK(g.j_daf.ensure(n * 4 + 4)); CK(g.j_prevbp.ensure(n * 4 + 4)); CK(g.j_flag.ensure(n + 4));
+  if (g.pileup) {                            // the decoder's per-row counts: no record stream to search
+    if (n > 0) {
+      k_pileup_join<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->meta.as<uint32_t>(), g.pile.as<int4>(), g.j_aaf.as<int32_t>(), g.j_daf.as<int32_t>(),
+                                                             g.j_prevbp.as<int32_t>(), g.j_flag.as<uint8_t>());
+      CK(cudaGetLastError());
+      h->launches += 1;
+    }
+    g.joined = true;
+    return 0;
+  }
   if (n > 0) {
     // tiles of JOIN_TILE sites, never across a chromosome boundary
     if ((int)h->h_tile_start.size() != h->n_chr + 1 || !h->tiles_valid) {
@@ -1017,7 +1058,7 @@ int run_compact(colate_handle* h)
                                                R.j_aaf.as<int32_t>(), R.j_daf.as<int32_t>(), h->thr10.as<double>(),
                                                h->u_hdr.as<double4>(), h->u_eb2.as<uint8_t>(), h->u_ews.as<double>(),
                                                h->u_ewn.as<double>(), h->u_blk.as<int32_t>(), h->misc.as<int64_t>(),
-                                               h->meta.as<uint32_t>(), h->deep_rows.as<int64_t>(), h->n_deep);
+                                               h->meta.as<uint32_t>(), h->deep_rows.as<int64_t>(), h->n_deep, h->opt_raw_weights ? 1 : 0);
     h->launches += 1;
   }
   k_block_ranges<<<1, 512, 0, s>>>(h->u_blk.as<int32_t>(), h->misc.as<int64_t>(), h->blk_rank_start.as<int64_t>());

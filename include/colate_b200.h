@@ -81,6 +81,17 @@ int colate_set_genome(colate_handle* h, int slot, int64_t n_rec, const int64_t* 
                       const int64_t* chr_end, const int32_t* bp, const int32_t* aaf, const int32_t* daf,
                       const uint16_t* alleles, int location);
 
+/* SURVEY.md 8(f) N3 -- the bam front-ends' inputs, pre-decoded: the pileup of genome `slot` at the .mut rows, i.e. what
+ * bam_parser::count_alleles (include/vcf/htslib.cpp:60-168) holds at bp_mut - 1 when parse_onebambam looks it up
+ * (coal.cpp:1885-1929 reference, 1936-1980 target): counts[n_site][4] = reads showing A, C, G, T, all zero where the position is
+ * not covered.  Replaces colate_set_genome for that slot: AAF / DAF are picked by the row's own alleles, a row is usable iff
+ * reads > 0, (AAF > 0 || DAF > 0) and at most two alleles were seen (coal.cpp:1916-1917, 1967-1968); the pileup ring is random
+ * access, so the look-ahead rule of the .colate.in reader does not apply.  A bcf genome resolved by its decoder (parse_vcfvcf,
+ * coal.cpp:1000-1137) fits the same call: counts of the row's ancestral / derived allele in their A/C/G/T columns
+ * (AAF = N - DAF), zeros for rows the decoder rejects.  Use with colate_set_option(h, "front_end", 1): raw count weights
+ * (coal.cpp:2005-2039) and the 1e3 normalisation of stage ii (coal.cpp:3453-3463). */
+int colate_set_pileup(colate_handle* h, int slot, const int32_t* counts, int location);
+
 /* P/N mask of genome `slot` evaluated at the site positions (fasta::Read,
  * include/src/data.cpp:213-237; test at coal.cpp:2169-2174): bit m of pass_bits = row m is
  * NOT rejected by the mask (positions at or beyond the mask end pass).  NULL clears it. */
@@ -245,6 +256,9 @@ int colate_mask_bits_from_fasta(const char* path, int64_t n, const int32_t* pos,
  * per-chromosome .mut files.  target_masks may be NULL (or hold NULL entries).  Returns the records written or < 0. */
 int64_t colate_maketmp_table(int n_chr, const char* const* chr_names, const char* const* mut_files, const char* table_file,
                              const char* const* target_masks, int has_ref_genome, const char* out_file);
+/* <out>.colate_mat as mut() writes it for every front-end but tmp/tmp (coal.cpp:3336-3343, 3453-3465): the age grid, then per
+ * replicate the shared and the not-shared count vector (already divided by 1e3), default ostream formatting. */
+int colate_write_colate_mat(const char* path, int R, const double* age_bin, const double* counts);
 /* <out>.coal (coal.cpp:3660-3672, 3830-3844) and the raw fp64 side output <out>.bin. */
 int colate_write_coal(const char* path, int R, int E, const double* epochs, double* rates, int is_ancient, int ep_null);
 int colate_write_bin(const char* path, int R, int E, const double* epochs, const double* rates, const int32_t* iters);

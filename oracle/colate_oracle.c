@@ -341,6 +341,113 @@ int oracle_stage1(int n_chr, const int64_t* site_off /*[n_chr+1]*/,
 }
 
 /* ------------------------------------------------------------------------------------
+ * the bam/bam front-end parse_onebambam (coal.cpp:1799-2069) on pre-decoded pileups.
+ * t_counts / r_counts: [n_site][4] reads showing A, C, G, T at each row's position, i.e. what
+ * bam_parser::count_alleles holds at bp_mut - 1 when coal.cpp:1888 / 1939 look (all zero: ring entry absent or empty).
+ * Pinned against the reference's own parse_onebambam run on synthetic reads through oracle/hts_stubs.c
+ * (tests/golden/stage1_bambam.npz).  Outputs and error codes as oracle_stage1; -2 also for a row with age_begin > 0
+ * whose draw reaches bin 185: this front-end has no bound check there (coal.cpp:2034-2039).
+ * ---------------------------------------------------------------------------------- */
+static int acgt_index(uint8_t c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
+
+int oracle_stage1_pileup(int n_chr, const int64_t* site_off, const int32_t* pos, const float* age_begin, const float* age_end,
+                         const uint32_t* meta,
+                         const char* const* tmask_seq, const int64_t* tmask_len,
+                         const char* const* rmask_seq, const int64_t* rmask_len,
+                         const int32_t* t_counts, const int32_t* r_counts, oracle_mt* rng,
+                         double* shared, double* notshared, double* shared_emp, double* notshared_emp,
+                         int64_t* n_shared, int64_t* n_notshared, int64_t* n_emp, int64_t* n_used, int64_t* n_used_total)
+{
+  const double age = 0, ref_age = 0;      /* coal.cpp:1801-1802 */
+  const float num_samples = NSAMPLES;     /* coal.cpp:1811 */
+  memset(shared, 0, sizeof(double) * MAX_BLOCKS * NBINS);
+  memset(notshared, 0, sizeof(double) * MAX_BLOCKS * NBINS);
+  memset(shared_emp, 0, sizeof(double) * MAX_BLOCKS * NBINS);
+  memset(notshared_emp, 0, sizeof(double) * MAX_BLOCKS * NBINS);
+  memset(n_shared, 0, sizeof(int64_t) * MAX_BLOCKS * NBINS);
+  memset(n_notshared, 0, sizeof(int64_t) * MAX_BLOCKS * NBINS);
+  memset(n_emp, 0, sizeof(int64_t) * MAX_BLOCKS * NBINS);
+  memset(n_used, 0, sizeof(int64_t) * MAX_BLOCKS);
+  *n_used_total = 0;
+  int num_blocks = 0;
+  for (int chr = 0; chr < n_chr; chr++) {
+    int current_block_base = 0;           /* coal.cpp:1845 */
+    for (int64_t m = site_off[chr]; m < site_off[chr + 1]; m++) {
+      if (!(meta[m] & 1u)) continue;      /* coal.cpp:1849, 1865, 1874-1875: the same row filter as parse_tmptmp */
+      int bp_mut = pos[m];
+      uint8_t anc = (uint8_t)(meta[m] >> 8), der = (uint8_t)(meta[m] >> 16);
+      int use = 1;
+      if (tmask_seq && (uint64_t)(int64_t)bp_mut < (uint64_t)tmask_len[chr]) {   /* coal.cpp:1868-1873 */
+        if (tmask_seq[chr][bp_mut - 1] != 'P') use = 0;
+      }
+      if (rmask_seq && (uint64_t)(int64_t)bp_mut < (uint64_t)rmask_len[chr]) {
+        if (rmask_seq[chr][bp_mut - 1] != 'P') use = 0;
+      }
+      int DAF_ref = 0, AAF_ref = 0, DAF_target = 0, AAF_target = 0;
+      const int ia = acgt_index(anc), id = acgt_index(der);
+      for (int side = 0; side < 2 && use; side++) {      /* coal.cpp:1884-1929 (reference), then 1930-1931, then 1935-1980 (target) */
+        const int32_t* c = (side == 0 ? r_counts : t_counts) + 4 * m;
+        int num_reads = 0, num_alleles = 0;
+        for (int i = 0; i < 4; i++) { num_reads += c[i]; num_alleles += (c[i] > 0); }
+        int A = 0, D = 0;
+        if (num_reads > 0) {
+          if (ia >= 0) A = c[ia];
+          if (id >= 0) D = c[id];
+          if (A > 0 || D > 0) { if (!(num_alleles <= 2)) use = 0; }
+          else use = 0;
+        } else use = 0;
+        if (side == 0) { AAF_ref = A; DAF_ref = D; if (DAF_ref == 0) use = 0; }
+        else { AAF_target = A; DAF_target = D; }
+      }
+      if (!use) continue;
+      int N_ref = DAF_ref + AAF_ref;
+      double ab = age_begin[m];
+      if (ab < ref_age) ab = ref_age;
+      while (current_block_base + BLOCK_BASES < bp_mut) { current_block_base += BLOCK_BASES; num_blocks++; }   /* coal.cpp:1987-1994 */
+      if (num_blocks >= MAX_BLOCKS) return -3;
+      int blk = num_blocks;
+      if (ab <= age && oracle_bin_of_double_age((double)age_end[m]) >= NBINS) return -2;
+      if (ab > age && oracle_bin_of_double_age((double)age_end[m]) >= NBINS) return -2;   /* no bound check at coal.cpp:2034-2039 */
+      n_used[blk]++; (*n_used_total)++;
+      if (ab <= age) {
+        int b2 = oracle_bin_of_float_age(age_end[m]);      /* coal.cpp:2002-2006: int * int / double */
+        if (b2 < NBINS) {
+          shared_emp[blk * NBINS + b2] += DAF_target * DAF_ref / ((double)N_ref);
+          notshared_emp[blk * NBINS + b2] += AAF_target * DAF_ref / ((double)N_ref);
+          n_emp[blk * NBINS + b2]++;
+        }
+        for (int j = 0; j < NSAMPLES; j++) {               /* coal.cpp:2009-2023 */
+          double a = oracle_uniform_real(rng) * (age_end[m] - ab) + ab;
+          if (a < age) a = age;
+          int b = oracle_bin_of_double_age(a);
+          if (b >= NBINS) return -2;
+          notshared[blk * NBINS + b] += AAF_target * DAF_ref / ((double)N_ref * num_samples);
+          n_notshared[blk * NBINS + b]++;
+        }
+      } else {
+        int j = 0;                                         /* coal.cpp:2029-2042 */
+        while (j < NSAMPLES) {
+          double a = oracle_uniform_real(rng) * (age_end[m] - ab) + ab;
+          int skip = a < age;
+          int b = oracle_bin_of_double_age(a);
+          if (!skip) {
+            if (b >= NBINS) return -2;
+            shared[blk * NBINS + b] += DAF_target * DAF_ref / ((double)N_ref * num_samples);
+            notshared[blk * NBINS + b] += AAF_target * DAF_ref / ((double)N_ref * num_samples);
+            n_shared[blk * NBINS + b]++;
+            n_notshared[blk * NBINS + b]++;
+            j++;
+          }
+        }
+      }
+    }
+    num_blocks++;                         /* coal.cpp:2053-2057 */
+    if (num_blocks > MAX_BLOCKS) return -3;
+  }
+  return num_blocks;
+}
+
+/* ------------------------------------------------------------------------------------
  * Stage ii: block bootstrap + F-redistribution, coal.cpp:3344-3451 (tmp inputs: no /1e3)
  * ---------------------------------------------------------------------------------- */
 /* Block multiplicities for all replicates, drawn exactly as coal.cpp:3350-3357.
@@ -400,6 +507,13 @@ void oracle_stage2(int R, int num_blocks, const int32_t* weights,
       S[bin] += (0.0 < F[bin]) ? F[bin] : 0.0;
     }
   }
+}
+
+/* every front-end but tmp/tmp: both vectors divided by 1e3 afterwards (coal.cpp:3453-3463, tmp_file == true) */
+void oracle_stage2_norm(int R, double* counts)
+{
+  const double norm = 1e3;
+  for (size_t i = 0; i < (size_t)R * 2 * NBINS; i++) counts[i] /= norm;
 }
 
 /* ------------------------------------------------------------------------------------

@@ -66,6 +66,10 @@ def lib():
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(GenomeC), C.POINTER(GenomeC), C.POINTER(MT),
                                     _f64, _f64, _f64, _f64, _i64, _i64, _i64, _i64, C.POINTER(C.c_int64)]
+        L.oracle_stage1_pileup.argtypes = [C.c_int, _i64, _i32, _f32, _f32, _u32,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32, _i32, C.POINTER(MT),
+                                           _f64, _f64, _f64, _f64, _i64, _i64, _i64, _i64, C.POINTER(C.c_int64)]
+        L.oracle_stage2_norm.argtypes = [C.c_int, _f64]
         L.oracle_draw_block_weights.argtypes = [C.POINTER(MT), C.c_int, C.c_int, _i32]
         L.oracle_stage2.argtypes = [C.c_int, C.c_int, _i32, _f64, _f64, _f64, _f64, C.c_double, _f64, _f64]
         L.oracle_age_generations.argtypes = [C.c_char_p, C.c_char_p, C.c_float, C.c_int, C.POINTER(C.c_double)]
@@ -137,18 +141,56 @@ def stage1(sites, target, reference, seed=1, tmask=None, rmask=None, rng: MT | N
             "n_emp": nE[:nb].copy(), "n_used": nU[:nb].copy(), "n_used_total": tot.value, "rng": rng}
 
 
+def stage1_pileup(sites, t_counts, r_counts, seed=1, tmask=None, rmask=None, rng: MT | None = None):
+    """Oracle stage i of the bam/bam front-end (parse_onebambam, coal.cpp:1799-2069) on pre-decoded pileups:
+    t_counts / r_counts [n_site][4] = reads showing A, C, G, T at each row.  Returns as stage1()."""
+    L = lib()
+    rng = rng or mt_seed(seed)
+    n_chr = len(sites.chr_names)
+    z = lambda dt=np.float64: np.zeros((MAX_BLOCKS, NBINS), dtype=dt)
+    S, N, SE, NE = z(), z(), z(), z()
+    nS, nN, nE = z(np.int64), z(np.int64), z(np.int64)
+    nU = np.zeros(MAX_BLOCKS, dtype=np.int64)
+    tot = C.c_int64(0)
+
+    def mk(mask):
+        if mask is None:
+            return None, None, None
+        bufs = [C.create_string_buffer(m, len(m)) for m in mask]
+        ptrs = (C.c_char_p * n_chr)(*[C.cast(b, C.c_char_p) for b in bufs])
+        lens = (C.c_int64 * n_chr)(*[len(m) for m in mask])
+        return bufs, ptrs, lens
+
+    tb, tp, tl = mk(tmask)
+    rb, rp, rl = mk(rmask)
+    nb = L.oracle_stage1_pileup(n_chr, np.ascontiguousarray(sites.site_off, dtype=np.int64), np.ascontiguousarray(sites.pos),
+                                np.ascontiguousarray(sites.age_begin), np.ascontiguousarray(sites.age_end), np.ascontiguousarray(sites.meta()),
+                                C.cast(tp, C.c_void_p) if tp else None, C.cast(tl, C.c_void_p) if tl else None,
+                                C.cast(rp, C.c_void_p) if rp else None, C.cast(rl, C.c_void_p) if rl else None,
+                                np.ascontiguousarray(t_counts, dtype=np.int32), np.ascontiguousarray(r_counts, dtype=np.int32),
+                                C.byref(rng), S, N, SE, NE, nS, nN, nE, nU, C.byref(tot))
+    if nb < 0:
+        return {"num_blocks": nb}
+    return {"num_blocks": nb, "shared": S[:nb].copy(), "notshared": N[:nb].copy(), "shared_emp": SE[:nb].copy(),
+            "notshared_emp": NE[:nb].copy(), "n_shared": nS[:nb].copy(), "n_notshared": nN[:nb].copy(),
+            "n_emp": nE[:nb].copy(), "n_used": nU[:nb].copy(), "n_used_total": tot.value, "rng": rng}
+
+
 def draw_block_weights(rng: MT, R: int, num_blocks: int):
     w = np.zeros((R, num_blocks), dtype=np.int32)
     lib().oracle_draw_block_weights(C.byref(rng), R, num_blocks, w)
     return w
 
 
-def stage2(weights, blk, age: float = 0.0):
+def stage2(weights, blk, age: float = 0.0, norm_1e3: bool = False):
+    """norm_1e3: every front-end but tmp/tmp divides both vectors by 1e3 afterwards (coal.cpp:3453-3463)."""
     R, nb = weights.shape
     counts = np.zeros((R, 2, NBINS))
     lib().oracle_stage2(R, nb, np.ascontiguousarray(weights), np.ascontiguousarray(blk["shared"]),
                         np.ascontiguousarray(blk["notshared"]), np.ascontiguousarray(blk["shared_emp"]),
                         np.ascontiguousarray(blk["notshared_emp"]), age, age_bins(), counts)
+    if norm_1e3:
+        lib().oracle_stage2_norm(R, counts)
     return counts
 
 
@@ -250,6 +292,10 @@ def ref():
         L.ref_mt_words.argtypes = [C.c_int, C.c_long, C.c_int, _u32]
         L.ref_bin_of_float_age.argtypes = [C.c_float]
         L.ref_bin_of_double_age.argtypes = [C.c_double]
+        L.ref_parse_onebambam.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_char_p, C.c_char_p,
+                                          C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int,
+                                          _f64, _f64, _f64, _f64, _f64, _u32]
+        L.ref_bam_pileup.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_long, _i32, _i32, _u8]
         _ref = L
     return _ref
 
@@ -333,3 +379,47 @@ def ref_estep_simplified(shared: bool, epochs, rates, t: float):
     f = ref().ref_em_simplified_shared if shared else ref().ref_em_simplified_notshared
     ll = f(E, np.ascontiguousarray(epochs, dtype=np.float64), np.ascontiguousarray(rates, dtype=np.float64), t, num, den)
     return ll, num, den
+
+
+# ---- the bam/bam front-end on synthetic reads (oracle/hts_stubs.c serves the reference's bam_parser) ----
+def write_fake_bam(path, chr_names, reads):
+    """reads: iterable of (tid, pos0, mapq, reverse, seq bytes, qual uint8 array), sorted by (tid, pos0).
+    Format: oracle/hts_stubs.c."""
+    import struct
+    with open(path, "wb") as f:
+        f.write(b"FBAM" + struct.pack("<i", len(chr_names)))
+        for nm in chr_names:
+            b = nm.encode()
+            f.write(struct.pack("<i", len(b)) + b)
+        for tid, pos0, mapq, rev, seq, qual in reads:
+            f.write(struct.pack("<iiBBi", tid, pos0, mapq, 1 if rev else 0, len(seq)) + bytes(seq) + bytes(bytearray(qual)))
+
+
+def ref_parse_onebambam(dirname, chr_names, prefix, target_bam, ref_bam, ref_genome, seed=1, params="20,30,10", tmask=None, rmask=None):
+    """The reference's parse_onebambam (coal.cpp:1799-2069) on <dirname>/<prefix>_chr<c>.mut, two fake BAMs and the
+    per-chromosome reference genome <ref_genome>_chr<c>.fa."""
+    L = ref()
+    n = len(chr_names)
+    arr = lambda xs: (C.c_char_p * n)(*[x.encode() for x in xs])
+    names = arr(chr_names)
+    muts = arr([os.path.join(dirname, f"{prefix}_chr{c}.mut") for c in chr_names])
+    gen = arr([os.path.join(dirname, f"{ref_genome}_chr{c}.fa") for c in chr_names])
+    tm = arr([os.path.join(dirname, f"{tmask}_chr{c}.fa") for c in chr_names]) if tmask else None
+    rm = arr([os.path.join(dirname, f"{rmask}_chr{c}.fa") for c in chr_names]) if rmask else None
+    z = lambda: np.zeros((MAX_BLOCKS, NBINS))
+    S, N, SE, NE = z(), z(), z(), z()
+    rest = np.zeros(2)
+    mt = np.zeros(625, dtype=np.uint32)
+    nb = L.ref_parse_onebambam(params.encode(), n, names, muts, os.path.join(dirname, target_bam).encode(),
+                               os.path.join(dirname, ref_bam).encode(), tm, rm, gen, seed, S, N, SE, NE, rest, mt)
+    return {"num_blocks": nb, "shared": S[:nb].copy(), "notshared": N[:nb].copy(), "shared_emp": SE[:nb].copy(),
+            "notshared_emp": NE[:nb].copy(), "emp_rest": rest, "mt": mt}
+
+
+def ref_bam_pileup(bam_path, contig, ref_genome_path, bp, params="20,30,10"):
+    """What the reference's bam_parser holds at the 1-based positions bp (ascending) of one contig: counts [n][4] (A, C, G, T)."""
+    bp = np.ascontiguousarray(bp, dtype=np.int32)
+    counts = np.zeros((bp.shape[0], 4), dtype=np.int32)
+    cov = np.zeros(bp.shape[0], dtype=np.uint8)
+    ref().ref_bam_pileup(params.encode(), bam_path.encode(), contig.encode(), ref_genome_path.encode(), bp.shape[0], bp, counts, cov)
+    return counts, cov

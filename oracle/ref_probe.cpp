@@ -195,3 +195,82 @@ long ref_read_mut(const char* filename, long cap, int* pos, float* age_begin, fl
 }
 
 }  // extern "C"
+
+extern "C" {
+
+// parse_onebambam (coal.cpp:1799-2069) exactly as mut() calls it (coal.cpp:3288): the bam/bam front-end whose weighting
+// variant is row N3 of SURVEY.md 8(f).  The two "BAM" files are oracle/hts_stubs.c fake BAMs (synthetic reads); everything
+// above the htslib calls -- bam_parser's pileup ring, the filters, the weights -- is the reference's own code.
+// Outputs as ref_parse_tmptmp.
+int ref_parse_onebambam(const char* params, int n_chr, const char** chr_names, const char** mut_files,
+                        const char* target_bam, const char* ref_bam, const char** target_masks, const char** ref_masks,
+                        const char** ref_genomes, int seed,
+                        double* out_shared, double* out_notshared, double* out_shared_emp, double* out_notshared_emp,
+                        double* emp_rest, unsigned int* mt_out /*[625]*/)
+{
+  double C = 10;
+  int num_age_bins = ((int)(log(1e8) * C)) + 1;
+  int num_bases_per_block = 30e6;
+  int num_blocks = 500;
+  std::vector<std::vector<double>> a(num_blocks), b(num_blocks), c(num_blocks), d(num_blocks);
+  for (int i = 0; i < num_blocks; i++) {
+    a[i].assign(num_age_bins, 0.0);
+    b[i].assign(num_age_bins, 0.0);
+    c[i].assign(num_age_bins * num_age_bins, 0.0);
+    d[i].assign(num_age_bins * num_age_bins, 0.0);
+  }
+  std::vector<std::string> name_chr, filename_mut, tmask, rmask, refg, ft(1, target_bam), fr(1, ref_bam);
+  for (int i = 0; i < n_chr; i++) {
+    name_chr.push_back(chr_names[i]);
+    filename_mut.push_back(mut_files[i]);
+    refg.push_back(ref_genomes[i]);
+    if (target_masks) tmask.push_back(target_masks[i]);
+    if (ref_masks) rmask.push_back(ref_masks[i]);
+  }
+  std::string prm(params);
+  std::mt19937 rng;
+  rng.seed(seed);
+  int nb = parse_onebambam(prm, name_chr, filename_mut, ft, fr, tmask, rmask, refg, 0.0, 0.0, C, rng, num_bases_per_block, a, b, c, d);
+  emp_rest[0] = emp_rest[1] = 0.0;
+  for (int i = 0; i < nb && i < 500; i++) {
+    for (int k = 0; k < num_age_bins; k++) {
+      out_shared[i * num_age_bins + k] = a[i][k];
+      out_notshared[i * num_age_bins + k] = b[i][k];
+      out_shared_emp[i * num_age_bins + k] = c[i][k];
+      out_notshared_emp[i * num_age_bins + k] = d[i][k];
+    }
+    for (int k = num_age_bins; k < num_age_bins * num_age_bins; k++) {
+      emp_rest[0] += c[i][k];
+      emp_rest[1] += d[i][k];
+    }
+  }
+  std::stringstream ss;
+  ss << rng;
+  for (int i = 0; i < 625; i++) {
+    unsigned long v;
+    ss >> v;
+    mt_out[i] = (unsigned int)v;
+  }
+  return nb;
+}
+
+// The pileup bam_parser holds at given positions: for every 1-based position bp[i] of chromosome `contig` (ascending),
+// read_to_pos(bp - 1) as coal.cpp:1885-1888 does, then counts[i][0..3] = count_alleles[(bp-1) % num_entries] if that ring
+// entry belongs to bp - 1, else zeros (and covered[i] = 0).  This is the "pre-decoded array" the N3 entry point takes.
+int ref_bam_pileup(const char* params, const char* bam, const char* contig, const char* ref_genome, long n, const int* bp,
+                   int* counts /*[n][4]*/, unsigned char* covered)
+{
+  std::string prm(params), fb(bam);
+  bam_parser P(fb, prm);
+  P.assign_contig(contig, ref_genome);
+  for (long i = 0; i < n; i++) {
+    const int q = bp[i] - 1;
+    P.read_to_pos(q);
+    const bool hit = P.pos_of_entry[q % P.num_entries] == q;
+    covered[i] = hit ? 1 : 0;
+    for (int k = 0; k < 4; k++) counts[4 * i + k] = hit ? P.count_alleles[q % P.num_entries][k] : 0;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -192,8 +192,113 @@ def n2_fixture():
     print("n2 fixtures written")
 
 
+def bambam_reads(rng, sites, genome, p_cov, mean_extra):
+    """Synthetic aligned reads around the .mut rows of every chromosome, sorted by (contig, start): lengths 24..80 (some under the
+    length filter), mapping qualities some under the filter, base qualities some under 30, up to a dozen mismatches against the
+    reference genome (some reads over the mismatch filter), rows at any offset of a read (the first / last three bases of a read
+    never count, htslib.cpp:66), the row's allele ancestral / derived / a third base."""
+    reads = []
+    for c in range(len(sites.chr_names)):
+        g = genome[c]
+        L = g.shape[0]
+        lo, hi = int(sites.site_off[c]), int(sites.site_off[c + 1])
+        per = []
+        for m in range(lo, hi):
+            if rng.random() >= p_cov:
+                continue
+            p0 = int(sites.pos[m]) - 1
+            anc, der = int(sites.anc[m]), int(sites.der[m])
+            for _ in range(1 + rng.poisson(mean_extra)):
+                ln = int(rng.integers(24, 81))
+                off = int(rng.integers(0, ln))
+                st = p0 - off
+                if st < 0 or st + ln > L:
+                    continue
+                seq = g[st:st + ln].copy()
+                u = rng.random()
+                alt = [b for b in b"ACGT" if b not in (anc, der)]
+                seq[off] = der if u < 0.35 else (anc if u < 0.9 and anc in b"ACGT" else alt[int(rng.integers(0, len(alt)))])
+                nmm = int(rng.choice([0, 0, 0, 1, 2, 4, 9, 12]))
+                for k in rng.integers(0, ln, size=nmm):
+                    if k != off:
+                        seq[k] = b"ACGT"[(b"ACGT".index(bytes([seq[k]])) + 1) % 4] if bytes([seq[k]]) in b"ACGT" else seq[k]
+                qual = np.where(rng.random(ln) < 0.1, 12, 37).astype(np.uint8)
+                mapq = int(rng.choice([0, 10, 19, 20, 37, 60, 60, 60]))
+                per.append((c, st, mapq, bool(rng.random() < 0.5), seq.tobytes(), qual))
+        per.sort(key=lambda r: r[1])
+        reads += per
+    return reads
+
+
+def bambam_fixture():
+    """the bam/bam front-end.  The reference's own parse_onebambam (coal.cpp:1799-2069) and bam_parser
+    (include/vcf/htslib.cpp) run on synthetic reads served by oracle/hts_stubs.c; the fixture keeps the rows, the pileup the
+    reference's bam_parser holds at every row (the pre-decoded arrays colate_set_pileup takes) and parse_onebambam's outputs,
+    with and without masks."""
+    seed = 23
+    rng = np.random.default_rng(seed)
+    lens = [65_000_000, 31_000_000]
+    sites = synth.make_sites(seed, [1300, 700], lens, weird=0.1)
+    d = tempfile.mkdtemp()
+    synth.write_dataset(d, sites, {})
+    genome = []
+    for c, L in enumerate(lens):
+        g = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, L)].copy()
+        lo, hi = int(sites.site_off[c]), int(sites.site_off[c + 1])
+        for m in range(lo, hi):                      # the reference genome mostly carries the ancestral allele at a row
+            a = int(sites.anc[m])
+            if a in b"ACGT" and rng.random() < 0.85:
+                g[int(sites.pos[m]) - 1] = a
+        genome.append(g)
+        with open(os.path.join(d, f"g_chr{sites.chr_names[c]}.fa"), "wb") as f:
+            f.write(b">ref\n")
+            for i in range(0, L, 1 << 20):
+                f.write(g[i:i + (1 << 20)].tobytes() + b"\n")
+    bam_names = ["chr" + sites.chr_names[0], sites.chr_names[1]]      # bam_parser accepts "<name>" and "chr<name>" (htslib.cpp:388)
+    po.write_fake_bam(os.path.join(d, "t.bam"), bam_names, bambam_reads(rng, sites, genome, 0.85, 1.2))
+    po.write_fake_bam(os.path.join(d, "r.bam"), bam_names, bambam_reads(rng, sites, genome, 0.9, 2.0))
+    masks = {"tm": [synth.make_mask(seed * 10 + c, int(L) if c else int(L) // 2, 0.25) for c, L in enumerate(lens)],
+             "rm": [synth.make_mask(seed * 20 + c, int(L), 0.15) for c, L in enumerate(lens)]}
+    for mname, per_chr in masks.items():
+        for c, nm in enumerate(sites.chr_names):
+            synth.write_mask(os.path.join(d, f"{mname}_chr{nm}.fa"), per_chr[c])
+    out = dict(chr_names=np.array(sites.chr_names), site_off=sites.site_off, pos=sites.pos, age_begin=sites.age_begin,
+               age_end=sites.age_end, flipped=sites.flipped, n_branch=sites.n_branch, anc=sites.anc, der=sites.der, odd=sites.odd,
+               chrom_len=np.array(lens, dtype=np.int64), seed=seed)
+    for tag, bam in (("t", "t.bam"), ("r", "r.bam")):
+        cnt = np.zeros((sites.n, 4), np.int32)
+        for c, nm in enumerate(sites.chr_names):
+            lo, hi = int(sites.site_off[c]), int(sites.site_off[c + 1])
+            cnt[lo:hi], _ = po.ref_bam_pileup(os.path.join(d, bam), nm, os.path.join(d, f"g_chr{nm}.fa"), sites.pos[lo:hi])
+        out[f"{tag}_counts"] = cnt
+    for tag, tm, rm in (("plain", None, None), ("masked", "tm", "rm")):
+        r = po.ref_parse_onebambam(d, sites.chr_names, "syn", "t.bam", "r.bam", "g", seed=seed, tmask=tm, rmask=rm)
+        assert r["emp_rest"].sum() == 0
+        for k in ("num_blocks", "shared", "notshared", "shared_emp", "notshared_emp", "mt"):
+            out[f"ref_{tag}_{k}"] = np.asarray(r[k])
+        print("stage1_bambam.npz", tag, "blocks", r["num_blocks"], "sum shared", r["shared"].sum(), "notshared", r["notshared"].sum())
+    # (the masks are regenerated by the tests: synth.make_mask(seed * 10 + c, len or len // 2 for c == 0, 0.25) / (seed * 20 + c, len, 0.15))
+    # the whole CLI on the same inputs: <out>.colate_mat (coal.cpp:3336-3343, 3453-3465: counts / 1e3, six digits) and <out>.coal
+    for tag, extra in (("bambam_R1", []), ("bambam_R3", ["--num_bootstraps", "3"])):
+        o = os.path.join(d, tag)
+        cmd = [po.ref_cli(), "--mode", "mut", "--mut", os.path.join(d, "syn"), "--chr", os.path.join(d, "chr.txt"), "--target_bam", os.path.join(d, "t.bam"),
+               "--reference_bam", os.path.join(d, "r.bam"), "--ref_genome", os.path.join(d, "g"), "--bins", "3,7,0.2", "--seed", str(seed), "-o", o] + extra
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        for ext in (".coal", ".colate_mat"):
+            with open(o + ext) as f, open(os.path.join(OUT, tag + ext), "w") as g:
+                g.write(f.read())
+        print(tag, "written:", [ln for ln in r.stderr.splitlines() if "blocks" in ln or "iterations" in ln][:4])
+    np.savez_compressed(os.path.join(OUT, "stage1_bambam.npz"), **out)
+    print("covered rows: target", int((out["t_counts"].sum(1) > 0).sum()), "reference", int((out["r_counts"].sum(1) > 0).sum()), "of", sites.n)
+    import shutil
+    shutil.rmtree(d, ignore_errors=True)
+
+
 def main():
     assert po.ref_available() and po.ref_cli(), "build oracle/_ref first (make -C oracle ref)"
+    if len(sys.argv) > 1 and sys.argv[1] == "bambam":
+        return bambam_fixture()
     if len(sys.argv) > 1 and sys.argv[1] == "reject":
         return reject_fixture()
     if len(sys.argv) > 1 and sys.argv[1] == "n2":
@@ -202,6 +307,7 @@ def main():
         return mut_reader_fixture()
     if len(sys.argv) > 1 and sys.argv[1] == "maketmp":
         return maketmp_fixture()
+    bambam_fixture()
     maketmp_fixture()
     mut_reader_fixture()
     n2_fixture()

@@ -354,3 +354,112 @@ def test_rows_the_reference_cannot_process_are_refused(handle):
         with pytest.raises(api._lib.ColateError) as e:
             handle.stage1(api.mt_seed(1))
         assert e.value.code == -2
+
+
+# ---- the bcf / bam front-ends' weighting variant from pre-decoded per-row counts -------------------------
+def _load_pileup(handle, sites, t_counts, r_counts, tm=None, rm=None):
+    handle.set_sites(sites.site_off, sites.pos, sites.age_begin, sites.age_end, sites.meta())
+    handle.set_pileup(0, t_counts)
+    handle.set_pileup(1, r_counts)
+    handle.set_mask(0, None if tm is None else api.mask_bits_from_seq(tm, sites.site_off, sites.pos))
+    handle.set_mask(1, None if rm is None else api.mask_bits_from_seq(rm, sites.site_off, sites.pos))
+
+
+@pytest.mark.parametrize("tag", ["plain", "masked"])
+def test_pileup_front_end_matches_reference_parse_onebambam(handle, tag):
+    """colate_set_pileup + front_end = 1 against the REFERENCE's parse_onebambam outputs (coal.cpp:1799-2069 run on synthetic
+    reads, tests/golden/stage1_bambam.npz) and against the oracle's tallies, bit for bit, generator state included."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import bambam_masks, load, sites_from
+    z = load("stage1_bambam.npz")
+    sites = sites_from(z)
+    tm, rm = bambam_masks(z) if tag == "masked" else (None, None)
+    handle.set_option("front_end", 1)
+    try:
+        _load_pileup(handle, sites, z["t_counts"], z["r_counts"], tm, rm)
+        s1 = handle.stage1(api.mt_seed(int(z["seed"])))
+        assert s1.num_blocks == int(z[f"ref_{tag}_num_blocks"])
+        for v, k in enumerate(("shared", "notshared", "shared_emp", "notshared_emp")):
+            assert np.array_equal(s1.block_stats[:, v], z[f"ref_{tag}_{k}"]), k
+        o = po.stage1_pileup(sites, z["t_counts"], z["r_counts"], seed=int(z["seed"]), tmask=tm, rmask=rm)
+        _compare_stage1(o, s1)
+        if tag == "plain":        # stage ii with the 1e3 normalisation + EM: the .colate_mat / .coal the reference CLI wrote
+            import tempfile
+            for R in (1, 3):
+                st = s1.mt_state.copy()
+                w = api.draw_block_weights(st, R, s1.num_blocks)
+                counts = handle.stage2_bootstrap(w, s1.block_stats, 0.0)
+                assert np.array_equal(counts, po.stage2(w, o, 0.0, norm_1e3=True))
+                ep, _ = api.epochs_from_bins("3,7,0.2")
+                rates, iters, _ = handle.stage3_em(R, ep, np.full(len(ep), 1 / 20000.0), None, 100000)
+                with tempfile.TemporaryDirectory() as d:
+                    api.write_colate_mat(d + "/o.colate_mat", counts)
+                    api.write_coal(d + "/o.coal", ep, rates)
+                    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"bambam_R{R}")
+                    assert open(d + "/o.colate_mat").read() == open(g + ".colate_mat").read()
+                    assert open(d + "/o.coal").read() == open(g + ".coal").read()
+    finally:
+        handle.set_option("front_end", 0)
+        handle.set_mask(0, None); handle.set_mask(1, None)
+
+
+def test_pileup_front_end_larger_random(handle):
+    """200 k rows, random pileups (0-6 reads of up to three alleles per row and genome): device == oracle; a pass with rejoin
+    (the join columns recomputed from the stored counts) gives the same bits; tmp/tmp weights on the same counts differ."""
+    rng = np.random.default_rng(5)
+    sites = synth.make_sites(9, [120000, 80000], [2.4e8, 1.3e8], weird=0.05)
+    ai = np.searchsorted(np.frombuffer(b"ACGT", np.uint8), sites.anc.clip(65, 84))
+    di = np.searchsorted(np.frombuffer(b"ACGT", np.uint8), sites.der.clip(65, 84))
+
+    def pile(p_cov):
+        c = np.zeros((sites.n, 4), np.int32)
+        cov = rng.random(sites.n) < p_cov
+        n_reads = rng.integers(1, 7, sites.n)
+        for k in range(6):
+            live = cov & (k < n_reads)
+            u = rng.random(sites.n)
+            col = np.where(u < 0.3, di % 4, np.where(u < 0.93, ai % 4, rng.integers(0, 4, sites.n)))
+            np.add.at(c, (np.nonzero(live)[0], col[live]), 1)
+        return c
+
+    tc, rc = pile(0.6), pile(0.7)
+    o = po.stage1_pileup(sites, tc, rc, seed=3)
+    assert o["n_used_total"] > 10000
+    handle.set_option("front_end", 1)
+    try:
+        _load_pileup(handle, sites, tc, rc)
+        s1 = handle.stage1(api.mt_seed(3))
+        _compare_stage1(o, s1)
+        handle.set_option("rejoin", 1)
+        s2 = handle.stage1(api.mt_seed(3))
+        handle.set_option("rejoin", 0)
+        assert np.array_equal(s1.block_stats, s2.block_stats)
+        handle.set_option("front_end", 0)
+        s3 = handle.stage1(api.mt_seed(3))
+        assert s3.n_used == s1.n_used and not np.array_equal(s3.block_stats[:, 1], s1.block_stats[:, 1])
+    finally:
+        handle.set_option("front_end", 0)
+        handle.set_option("rejoin", 0)
+
+
+def test_pileup_front_end_refuses_rows_the_reference_overruns_on(handle):
+    """age_begin > 0 with an interval past the age grid: parse_onebambam has no bound check (coal.cpp:2034-2039)."""
+    sites = synth.make_sites(4, [3000], [2.4e8])
+    synth.add_deep_rows(sites, 5, 0.05)
+    c = np.zeros((sites.n, 4), np.int32)
+    c[:, :] = 2
+    ai = np.searchsorted(np.frombuffer(b"ACGT", np.uint8), sites.anc.clip(65, 84)) % 4
+    di = np.searchsorted(np.frombuffer(b"ACGT", np.uint8), sites.der.clip(65, 84)) % 4
+    c[:] = 0
+    c[np.arange(sites.n), ai] = 1
+    c[np.arange(sites.n), di] += 1
+    assert po.stage1_pileup(sites, c, c, seed=1)["num_blocks"] == -2
+    handle.set_option("front_end", 1)
+    try:
+        _load_pileup(handle, sites, c, c)
+        with pytest.raises(api._lib.ColateError) as e:
+            handle.stage1(api.mt_seed(1))
+        assert e.value.code == -2
+    finally:
+        handle.set_option("front_end", 0)

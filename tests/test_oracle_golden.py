@@ -8,7 +8,7 @@ import pytest
 
 from colate_b200 import synth
 from oracle import pyoracle as po
-from helpers import GOLDEN, dataset_from, load, same
+from helpers import GOLDEN, bambam_masks, dataset_from, load, same, sites_from
 
 
 def test_random_streams_match_libstdcxx():
@@ -52,6 +52,43 @@ def test_stage1_matches_reference_parse_tmptmp(tag):
     # integer tallies are consistent with the fp64 vectors
     assert o["n_notshared"].sum() == 100 * o["n_used_total"]
     assert (o["n_shared"] <= o["n_notshared"]).all()
+
+
+@pytest.mark.parametrize("tag", ["plain", "masked"])
+def test_stage1_pileup_matches_reference_parse_onebambam(tag):
+    """the oracle's bam/bam front-end on pre-decoded pileups against the reference's own parse_onebambam
+    (coal.cpp:1799-2069) run on synthetic reads (fixture: make_golden.py bambam; the pileups are the reference bam_parser's)."""
+    z = load("stage1_bambam.npz")
+    sites = sites_from(z)
+    tm, rm = bambam_masks(z) if tag == "masked" else (None, None)
+    o = po.stage1_pileup(sites, z["t_counts"], z["r_counts"], seed=int(z["seed"]), tmask=tm, rmask=rm)
+    assert o["num_blocks"] == int(z[f"ref_{tag}_num_blocks"])
+    assert o["n_used_total"] > 100
+    for k in ("shared", "notshared", "shared_emp", "notshared_emp"):
+        assert same(o[k], z[f"ref_{tag}_{k}"]), k
+    assert same(o["rng"].words(), z[f"ref_{tag}_mt"])
+    # the filter cases the fixture is meant to hold: three alleles seen, reads without either allele, uncovered rows
+    for cnt in (z["t_counts"], z["r_counts"]):
+        assert ((cnt > 0).sum(1) >= 3).any() and (cnt.sum(1) == 0).any()
+
+
+@pytest.mark.parametrize("R", [1, 3])
+def test_bambam_cli_chain_matches_reference_cli(R, tmp_path):
+    """The oracle's whole bam/bam chain -- stage i on pileups, block bootstrap, F redistribution, the 1e3 normalisation of
+    coal.cpp:3453-3463, EM -- against the <out>.colate_mat and <out>.coal the reference CLI wrote for the same inputs
+    (--target_bam / --reference_bam on synthetic reads, make_golden.py bambam)."""
+    from colate_b200 import api
+    z = load("stage1_bambam.npz")
+    sites = sites_from(z)
+    o = po.stage1_pileup(sites, z["t_counts"], z["r_counts"], seed=int(z["seed"]))
+    w = po.draw_block_weights(o["rng"], R, o["num_blocks"])
+    counts = po.stage2(w, o, 0.0, norm_1e3=True)
+    api.write_colate_mat(str(tmp_path / "o.colate_mat"), counts)             # the product's host writer (no GPU involved)
+    assert open(tmp_path / "o.colate_mat").read() == open(os.path.join(GOLDEN, f"bambam_R{R}.colate_mat")).read()
+    ep, _ = po.epochs_from_bins("3,7,0.2")
+    rates = np.stack([po.em_run(ep, np.full(len(ep), 1 / 20000.0), counts[r])[0] for r in range(R)])
+    po.write_coal(str(tmp_path / "o.coal"), ep, rates)
+    assert open(tmp_path / "o.coal").read() == open(os.path.join(GOLDEN, f"bambam_R{R}.coal")).read()
 
 
 def test_estep_matches_reference_coal_EM():

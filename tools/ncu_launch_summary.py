@@ -13,8 +13,14 @@ for r in rows:
     v = float(r[vi].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}[r[ui]]
     L.append((name, v))
 em = max(i for i, (n, _) in enumerate(L) if n.startswith("k_em"))
-joins = [i for i, (n, _) in enumerate(L[:em]) if n.startswith("k_join")]
-start = joins[-2] if len(joins) >= 2 and joins[-1] - joins[-2] <= 2 else joins[-1]
+bounds = [i for i, (n, _) in enumerate(L[:em]) if n == "k_join_bounds"]
+joins = [i for i, (n, _) in enumerate(L[:em]) if n == "k_join"]
+if len(bounds) >= 2 and bounds[-1] - bounds[-2] <= 2:       # k_join_bounds, k_join once per genome
+    start = bounds[-2]
+elif bounds:
+    start = bounds[-1]
+else:
+    start = joins[-2] if len(joins) >= 2 and joins[-1] - joins[-2] <= 2 else joins[-1]
 one = L[start:em + 1]
 agg = OrderedDict()
 for n, v in one:
