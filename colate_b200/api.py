@@ -339,6 +339,20 @@ class Handle:
         check(lib().colate_stage3_em(self._h, R, E, ptr(ep), ptr(ri), ptr(cn), max_iter, ptr(rates), ptr(iters), ptr(ll)))
         return rates, iters, ll
 
+    def stage3_em_begin(self, R, epochs, rates_init, max_iter=100000):
+        """Queue the EM of the device-resident counts on the handle's EM stream and return (colate_stage3_em_begin): the next
+        pair can be uploaded and taken through stage i meanwhile.  stage3_em_end() fetches the results."""
+        ep = np.ascontiguousarray(epochs, dtype=np.float64)
+        ri = np.ascontiguousarray(rates_init, dtype=np.float64)
+        self._em_shape = (R, ep.shape[0])
+        check(lib().colate_stage3_em_begin(self._h, R, ep.shape[0], ptr(ep), ptr(ri), max_iter))
+
+    def stage3_em_end(self):
+        R, E = self._em_shape
+        rates = np.zeros((R, E)); iters = np.zeros(R, dtype=np.int32); ll = np.zeros(R)
+        check(lib().colate_stage3_em_end(self._h, ptr(rates), ptr(iters), ptr(ll)))
+        return rates, iters, ll
+
     def estep(self, shared: bool, epochs, rates, t):
         ep = np.ascontiguousarray(epochs, dtype=np.float64)
         r = np.ascontiguousarray(rates, dtype=np.float64)

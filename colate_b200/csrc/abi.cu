@@ -143,11 +143,12 @@ void colate_destroy(colate_handle* h)
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  if (h->em_stream) { cudaStreamSynchronize(h->em_stream); cudaStreamDestroy(h->em_stream); }
   DevBuf* bufs[] = {&h->site_off, &h->pos, &h->ab, &h->ae, &h->meta, &h->candR, &h->candT, &h->use, &h->word_rank, &h->scan_tmp,
                     &h->chr_used, &h->chr_blocks, &h->chr_block_base, &h->misc, &h->u_hdr, &h->u_eb2, &h->u_ews, &h->u_ewn, &h->u_cnt,
                     &h->u_blk, &h->blk_rank_start, &h->out_f, &h->out_n, &h->thrA, &h->lut, &h->d_scratch, &h->d_prof, &h->libm_tab, &h->ing_text, &h->ing_tile_cnt, &h->ing_tile_off, &h->ing_nl, &h->ing_status, &h->ing_fb,
                     &h->windows, &h->rng_stream, &h->mt_tail, &h->poly, &h->thr10, &h->d_counts, &h->d_blockstats, &h->d_weights, &h->d_epochs,
-                    &h->d_rates, &h->d_iters, &h->d_ll, &h->d_agebin, &h->d_tmp, &h->order_flag, &h->ing_raw, &h->deep_rows, &h->tile_start, &h->tile_rlo};
+                    &h->d_rates, &h->d_iters, &h->d_ll, &h->d_agebin, &h->d_tmp, &h->d_em_scratch, &h->order_flag, &h->ing_raw, &h->deep_rows, &h->tile_start, &h->tile_rlo};
   for (DevBuf* b : bufs) b->release();
   for (auto& g : h->genomes) {
     DevBuf* gb[] = {&g.bp, &g.aaf, &g.daf, &g.alleles, &g.chr_first, &g.chr_end, &g.mask_bits, &g.j_aaf, &g.j_daf, &g.j_prevbp, &g.j_flag, &g.pile};
@@ -467,6 +468,7 @@ int colate_stage2_bootstrap(colate_handle* h, int R, int num_blocks, const int32
 {
   if (!h || R <= 0 || num_blocks <= 0 || num_blocks > MAX_BLOCKS || !block_weights)
     return fail(COLATE_ERR_ARG, "colate_stage2_bootstrap: bad arguments");
+  if (h->em_inflight) return fail(COLATE_ERR_STATE, "colate_stage2_bootstrap: an EM is in flight on the counts (call colate_stage3_em_end first)");
   if (!block_stats && (!h->flags_done || !h->sampled || num_blocks != h->n_blocks_local))
     return fail(COLATE_ERR_STATE, "colate_stage2_bootstrap: no device-resident block histograms of this size (run colate_stage1 first)");
   CK(cudaSetDevice(h->device));
@@ -498,6 +500,7 @@ int colate_stage3_em(colate_handle* h, int R, int E, const double* epochs, const
   if (!h || R <= 0 || E < 2 || E > 1024 || !epochs || !rates_init || max_iter < 0)
     return fail(COLATE_ERR_ARG, "colate_stage3_em: bad arguments");
   if (!counts && h->counts_R != R) return fail(COLATE_ERR_STATE, "colate_stage3_em: no device-resident counts for this R");
+  if (h->em_inflight) return fail(COLATE_ERR_STATE, "colate_stage3_em: an EM is in flight (colate_stage3_em_begin): call colate_stage3_em_end first");
   CK(cudaSetDevice(h->device));
   int rc = ensure_tables(h);
   if (rc) return rc;
@@ -513,9 +516,56 @@ int colate_stage3_em(colate_handle* h, int R, int E, const double* epochs, const
     CK(cudaMemcpyAsync(h->d_counts.p, counts, (size_t)R * 2 * NBINS * 8, cudaMemcpyDefault, s));
     h->counts_R = R;
   }
-  if ((rc = run_em(h, R, E, max_iter, epochs))) return rc;
+  if ((rc = run_em(h, R, E, max_iter, epochs, s))) return rc;
   if (rates) CK(cudaMemcpyAsync(rates, h->d_rates.as<double>() + E, (size_t)R * E * 8, cudaMemcpyDefault, s));
   std::vector<int32_t> it_host((size_t)R);
+  CK(cudaMemcpyAsync(it_host.data(), h->d_iters.p, (size_t)R * 4, cudaMemcpyDeviceToHost, s));
+  if (iters) CK(cudaMemcpyAsync(iters, h->d_iters.p, (size_t)R * 4, cudaMemcpyDefault, s));
+  if (final_ll) CK(cudaMemcpyAsync(final_ll, h->d_ll.p, (size_t)R * 8, cudaMemcpyDefault, s));
+  CK(cudaStreamSynchronize(s));
+  for (int r = 0; r < R; r++)
+    if (it_host[r] < 0) return fail(COLATE_ERR_CUDA, "EM kernel: the cluster handshake timed out (replicate " + std::to_string(r) + ")");
+  return 0;
+}
+
+// ---- asynchronous form: one EM in flight per handle ---------------------------------------------------------------------
+int colate_stage3_em_begin(colate_handle* h, int R, int E, const double* epochs, const double* rates_init, int max_iter)
+{
+  if (!h || R <= 0 || E < 2 || E > 1024 || !epochs || !rates_init || max_iter < 0)
+    return fail(COLATE_ERR_ARG, "colate_stage3_em_begin: bad arguments");
+  if (h->counts_R != R) return fail(COLATE_ERR_STATE, "colate_stage3_em_begin: no device-resident counts for this R (run colate_stage2_bootstrap first)");
+  if (h->em_inflight) return fail(COLATE_ERR_STATE, "colate_stage3_em_begin: an EM is already in flight on this handle");
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_tables(h);
+  if (rc) return rc;
+  if (!h->em_stream) CK(cudaStreamCreateWithFlags(&h->em_stream, cudaStreamNonBlocking));
+  cudaStream_t s = h->em_stream;
+  CK(h->d_epochs.ensure((size_t)E * 8));
+  CK(h->d_rates.ensure((size_t)(R + 1) * E * 8));
+  CK(h->d_iters.ensure((size_t)R * 4));
+  CK(h->d_ll.ensure((size_t)R * 8));
+  h->em_host_in.assign(epochs, epochs + E);
+  h->em_host_in.insert(h->em_host_in.end(), rates_init, rates_init + E);
+  CK(cudaMemcpyAsync(h->d_epochs.p, h->em_host_in.data(), (size_t)E * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->d_rates.p, h->em_host_in.data() + E, (size_t)E * 8, cudaMemcpyHostToDevice, s));
+  // (the counts were left by colate_stage2_bootstrap, which returns only after its stream has drained)
+  if ((rc = run_em(h, R, E, max_iter, epochs, s))) return rc;
+  h->em_inflight = true;
+  h->em_R = R;
+  h->em_E = E;
+  return 0;
+}
+
+int colate_stage3_em_end(colate_handle* h, double* rates, int32_t* iters, double* final_ll)
+{
+  if (!h) return fail(COLATE_ERR_ARG, "colate_stage3_em_end: null handle");
+  if (!h->em_inflight) return fail(COLATE_ERR_STATE, "colate_stage3_em_end: no EM in flight");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = h->em_stream;
+  const int R = h->em_R, E = h->em_E;
+  h->em_inflight = false;
+  std::vector<int32_t> it_host((size_t)R);
+  if (rates) CK(cudaMemcpyAsync(rates, h->d_rates.as<double>() + E, (size_t)R * E * 8, cudaMemcpyDefault, s));
   CK(cudaMemcpyAsync(it_host.data(), h->d_iters.p, (size_t)R * 4, cudaMemcpyDeviceToHost, s));
   if (iters) CK(cudaMemcpyAsync(iters, h->d_iters.p, (size_t)R * 4, cudaMemcpyDefault, s));
   if (final_ll) CK(cudaMemcpyAsync(final_ll, h->d_ll.p, (size_t)R * 8, cudaMemcpyDefault, s));

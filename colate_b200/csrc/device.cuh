@@ -99,6 +99,12 @@ struct colate_handle {
   colate::DevBuf d_counts, d_blockstats, d_weights, d_epochs, d_rates, d_iters, d_ll, d_agebin, d_tmp, d_scratch, d_prof, libm_tab;
   int libm_exact = -1;  // host libm == glibc_math.cuh port on the self-check sample (1/0), -1 unknown
   int counts_R = 0;
+  // colate_stage3_em_begin / _end: one EM in flight on its own stream while the next pair is uploaded and taken through stage i
+  cudaStream_t em_stream = nullptr;
+  bool em_inflight = false;
+  int em_R = 0, em_E = 0;
+  std::vector<double> em_host_in;   // epochs + initial rates of the EM in flight (the async copies read the handle's copy)
+  colate::DevBuf d_em_scratch;      // the EM kernels' global scratch (apart from d_scratch: stage i of the next pair may use that)
   int em_kernel = -1, em_csize = 0;   // last EM launch: 0 k_em, 1 k_em_split, 2 k_em_cta; CTAs per replicate
   int64_t launches = 0;
   bool opt_rejoin = false, opt_async_uploads = false;
@@ -139,7 +145,7 @@ int run_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int
 int mt_window_after(colate_handle* h, uint32_t* window_after);
 // kernels_em.cu
 int run_bootstrap(colate_handle* h, int R, int num_blocks, const double* block_stats_dev, double age);
-int run_em(colate_handle* h, int R, int E, int max_iter, const double* epochs_host);
+int run_em(colate_handle* h, int R, int E, int max_iter, const double* epochs_host, cudaStream_t stream);
 int run_estep(colate_handle* h, int shared, int E, int n_t);
 int run_libm(colate_handle* h, int which, int n, const double* x_host, double* y_host);
 }  // namespace colate

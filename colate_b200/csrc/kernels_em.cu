@@ -1324,7 +1324,7 @@ int run_bootstrap(colate_handle* h, int R, int num_blocks, const double* block_s
   return 0;
 }
 
-int run_em(colate_handle* h, int R, int E, int max_iter, const double* epochs_host)
+int run_em(colate_handle* h, int R, int E, int max_iter, const double* epochs_host, cudaStream_t stream)
 {
   int rc = ensure_libm_tables(h);
   if (rc) return rc;
@@ -1375,11 +1375,11 @@ int run_em(colate_handle* h, int R, int E, int max_iter, const double* epochs_ho
     if (csize > 8) CK(cudaFuncSetAttribute(k_em_split, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   }
   else CK(cudaFuncSetAttribute(k_em, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
-  if (!cta) CK(h->d_scratch.ensure((size_t)R * 2 * (2 * E + 2) * EM_TASKS * 8 + 1024));
+  if (!cta) CK(h->d_em_scratch.ensure((size_t)R * 2 * (2 * E + 2) * EM_TASKS * 8 + 1024));
   long long* prof = nullptr;
   if (getenv("COLATE_EM_PROF")) {
     CK(h->d_prof.ensure((size_t)R * csize * 40 * 8));
-    CK(cudaMemsetAsync(h->d_prof.p, 0, (size_t)R * csize * 40 * 8, h->stream));
+    CK(cudaMemsetAsync(h->d_prof.p, 0, (size_t)R * csize * 40 * 8, stream));
     prof = h->d_prof.as<long long>();
   }
   h->em_kernel = cta ? 2 : split ? 1 : 0;
@@ -1388,7 +1388,7 @@ int run_em(colate_handle* h, int R, int E, int max_iter, const double* epochs_ho
   cfg.gridDim = dim3(R * csize);
   cfg.blockDim = dim3(cta ? EMC_THREADS : split ? EMS_THREADS : EM_THREADS);
   cfg.dynamicSmemBytes = smem;
-  cfg.stream = h->stream;
+  cfg.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1402,14 +1402,14 @@ int run_em(colate_handle* h, int R, int E, int max_iter, const double* epochs_ho
   else
   CK(cudaLaunchKernelEx(&cfg, split ? k_em_split : k_em, E, (const double*)h->d_epochs.as<double>(), (const double*)h->d_rates.as<double>(),
                         (const double*)h->d_agebin.as<double>(), (const double*)h->d_counts.as<double>(), max_iter, tabs, tabs + 256,
-                        h->d_scratch.as<double>(), h->d_rates.as<double>() + E, h->d_iters.as<int32_t>(), h->d_ll.as<double>(), prof));
+                        h->d_em_scratch.as<double>(), h->d_rates.as<double>() + E, h->d_iters.as<int32_t>(), h->d_ll.as<double>(), prof));
   h->launches += 1;
   CK(cudaGetLastError());
   if (prof) {
     if (cta) {
       long long q[16];
-      CK(cudaMemcpyAsync(q, prof, 128, cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaStreamSynchronize(h->stream));
+      CK(cudaMemcpyAsync(q, prof, 128, cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
       for (int w = 0; w < 2; w++)
         fprintf(stderr, "[k_em_cta prof, replicate 0 thread %d, cycles between its arrivals at the phase barriers] P0 %lld | P1 folds %lld | heads %lld | P2 exps %lld | P3 integ %lld | P4 column sums %lld | M-step %lld\n",
                 w ? 639 : 0, q[8 * w], q[8 * w + 1], q[8 * w + 2], q[8 * w + 3], q[8 * w + 4], q[8 * w + 5], q[8 * w + 6]);
@@ -1417,8 +1417,8 @@ int run_em(colate_handle* h, int R, int E, int max_iter, const double* epochs_ho
     }
     const int ps = split ? 16 : 8;
     std::vector<long long> hp((size_t)ps * csize);
-    CK(cudaMemcpyAsync(hp.data(), prof, (size_t)ps * 8 * csize, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpyAsync(hp.data(), prof, (size_t)ps * 8 * csize, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
     for (int r = 0; r < csize; r++) {
       const long long* q = hp.data() + (size_t)ps * r;
       if (split)

@@ -148,6 +148,15 @@ int colate_stage2_bootstrap(colate_handle* h, int R, int num_blocks, const int32
 int colate_stage3_em(colate_handle* h, int R, int E, const double* epochs, const double* rates_init,
                      const double* counts, int max_iter, double* rates, int32_t* iters, double* final_ll);
 
+/* Asynchronous form for drivers that run many pairs through one handle (the reference is started once per pair): _begin
+ * queues the EM of the device-resident counts of the last colate_stage2_bootstrap() on the handle's EM stream and returns;
+ * _end waits for it and fetches the results.  In between the caller may upload the NEXT pair and take it through stage i
+ * (colate_ingest_*, colate_set_*, colate_stage1*): the latency-mode EM keeps one GPC busy, stage i runs on the rest of the
+ * device.  colate_stage2_bootstrap / colate_stage3_em are refused with COLATE_ERR_STATE while an EM is in flight (they
+ * would overwrite its counts).  Results are those of colate_stage3_em. */
+int colate_stage3_em_begin(colate_handle* h, int R, int E, const double* epochs, const double* rates_init, int max_iter);
+int colate_stage3_em_end(colate_handle* h, double* rates, int32_t* iters, double* final_ll);
+
 /* The age grid colate_stage3_em() evaluates (the point ages t = age_bin[b], coal.cpp:3708, 3721).  Default: colate_age_bins().
  * mut() started from a <out>.colate_mat cache reads the grid back from that file's first line, i.e. rounded to six
  * significant digits (coal.cpp:3481-3483), and runs the EM on THOSE ages: the host passes them here.  NULL restores the

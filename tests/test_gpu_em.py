@@ -211,3 +211,43 @@ def test_em_one_cta_kernels_on_other_grids(handle, monkeypatch, kernel, bins, ag
     for r in (0, 17, 39):
         ro, it, llo = po.em_run(ep, init, counts[r], max_iter=150)
         assert iters[r] == it and _same(rates[r], ro) and _same(ll[r], llo), r
+
+
+def test_em_begin_end_pipeline_equals_the_blocking_calls(handle):
+    """colate_stage3_em_begin / _end: the EM of pair A runs on the handle's EM stream while pair B is uploaded and taken
+    through stage i; results are those of the blocking calls, bit for bit; the calls that would overwrite the counts of
+    the EM in flight are refused."""
+    ep, _ = api.epochs_from_bins("3,7,0.2")
+    ri = np.full(len(ep), 1 / 20000.0)
+    pairs = []
+    for seed in (1, 2, 3):
+        sites = synth.make_sites(seed, [40000, 25000], [2.5e8, 1.2e8])
+        pairs.append((sites, synth.make_genome(seed + 100, sites, 0.7), synth.make_genome(seed + 200, sites, 0.7)))
+
+    def front(p):
+        handle.load(*p)
+        s1 = handle.stage1(api.mt_seed(7), fetch=False)
+        return s1, api.draw_block_weights(s1.mt_state, 2, s1.num_blocks)
+
+    want = []
+    for p in pairs:                                   # blocking reference run
+        s1, w = front(p)
+        handle.stage2_bootstrap_dev(w, None, s1.num_blocks, 0.0)
+        want.append(handle.stage3_em(2, ep, ri))
+    got = []
+    inflight = False
+    for p in pairs:
+        s1, w = front(p)                              # upload + stage i of this pair under the EM of the previous one
+        if inflight:
+            with pytest.raises(api._lib.ColateError) as e:
+                handle.stage2_bootstrap_dev(w, None, s1.num_blocks, 0.0)
+            assert e.value.code == -7
+            got.append(handle.stage3_em_end())
+        handle.stage2_bootstrap_dev(w, None, s1.num_blocks, 0.0)
+        handle.stage3_em_begin(2, ep, ri)
+        inflight = True
+    got.append(handle.stage3_em_end())
+    with pytest.raises(api._lib.ColateError):
+        handle.stage3_em_end()                        # nothing in flight any more
+    for (r0, i0, l0), (r1, i1, l1) in zip(want, got):
+        assert _same(r0, r1) and _same(i0, i1) and _same(l0, l1)
