@@ -754,3 +754,78 @@ extern "C" int64_t colate_maketmp_table(int n_chr, const char* const* chr_names,
   fclose(fp);
   return n_written;
 }
+
+// ---- make_tmp from a pileup (the bam variant on pre-decoded arrays) ------------------------------
+// maketmp_bam (coal.cpp:2527-2680): a .colate.in record stream from the pileup of one BAM file at the rows of the .mut
+// files.  The BAM decoding (htslib, bam_parser) stays with the caller; `counts` is its output: for every DATA ROW of the
+// .mut files in --chr order, the reads showing A, C, G, T at the row's position (bam_parser::count_alleles at bp_mut - 1, zeros
+// where the position is not covered).  Row filter as the reference: not flipped, one branch, ancestral exactly one of
+// A C G T 0 and a non-empty derived string (no age condition, no condition on the derived code: coal.cpp:2568, 2584-2587);
+// the optional mask drops positions at or beyond its end (2589-2595); AAF / DAF are the counts of the one-letter ancestral /
+// derived alleles (2616-2633), a record is written iff one of them is positive (2641-2646; no limit on the number of alleles).
+extern "C" int64_t colate_maketmp_pileup(int n_chr, const char* const* chr_names, const char* const* mut_files, const int32_t* counts,
+                                         int64_t n_rows, const char* const* target_masks, const char* out_file)
+{
+  using colate::fail;
+  if (n_chr <= 0 || !chr_names || !mut_files || !counts || !out_file) return fail(COLATE_ERR_ARG, "colate_maketmp_pileup: bad arguments");
+  FILE* fp = fopen(out_file, "wb");
+  if (!fp) return fail(COLATE_ERR_IO, std::string("cannot write ") + out_file);
+  auto idx = [](char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; };
+  int64_t n_written = 0, row = 0;
+  for (int chr = 0; chr < n_chr; chr++) {
+    const std::string name = chr_names[chr];
+    std::vector<char> mask;
+    const bool has_mask = target_masks && target_masks[chr];
+    if (has_mask && !read_fasta_seq(target_masks[chr], mask)) { fclose(fp); return fail(COLATE_ERR_IO, std::string("Error while opening file ") + target_masks[chr] + "."); }
+    std::vector<char> buf;
+    if (!colate::slurp_or_gz(mut_files[chr], buf)) { fclose(fp); return fail(COLATE_ERR_IO, std::string("Error while reading ") + mut_files[chr] + "(.gz)."); }
+    buf.push_back('\n');
+    buf.push_back('\0');
+    const char* p = buf.data();
+    const char* endp = buf.data() + buf.size() - 1;
+    const char* nl = (const char*)memchr(p, '\n', endp - p);   // header line
+    p = nl ? nl + 1 : endp;
+    while (p < endp) {
+      nl = (const char*)memchr(p, '\n', endp - p);
+      if (!nl) break;
+      if (nl == p) { if (nl + 1 >= endp) break; fclose(fp); return fail(COLATE_ERR_IO, std::string("empty line in ") + mut_files[chr]); }
+      int32_t bp_mut; float ab, ae; uint32_t meta; int flipped, nb; char type[16];
+      if (!colate::parse_mut_line_fields(p, nl, &bp_mut, &ab, &ae, &meta, &flipped, &nb, type)) {
+        fclose(fp);
+        return fail(COLATE_ERR_IO, std::string("Error reading following line in mut file: ") + std::string(p, nl));
+      }
+      p = nl + 1;
+      if (row >= n_rows) { fclose(fp); return fail(COLATE_ERR_ARG, "colate_maketmp_pileup: fewer count rows than .mut rows"); }
+      const int32_t* c = counts + 4 * row++;
+      if (!(flipped == 0 && nb == 1)) continue;
+      // type[] holds the first 15 characters of the mutation type: enough for "one-letter ancestral, '/', first derived letter,
+      // is the derived string longer than one letter"
+      const char* slash = strchr(type, '/');
+      if (!slash || slash - type != 1 || slash[1] == '\0') continue;       // ancestral one letter, derived non-empty
+      const char a = type[0], d = type[2];
+      if (!(a == 'A' || a == 'C' || a == 'G' || a == 'T' || a == '0')) continue;
+      if (has_mask) {
+        if ((uint64_t)(int64_t)bp_mut >= (uint64_t)mask.size()) continue;
+        if (bp_mut >= 1 && mask[bp_mut - 1] != 'P') continue;
+      }
+      const int reads = c[0] + c[1] + c[2] + c[3];
+      if (reads <= 0) continue;
+      int32_t aaf = 0, daf = 0;
+      if (idx(a) >= 0) aaf = c[idx(a)];
+      if (slash[2] == '\0' && idx(d) >= 0) daf = c[idx(d)];              // the derived string must be the single letter
+      if (!(aaf > 0 || daf > 0)) continue;
+      const int32_t lchrom = (int32_t)name.size();
+      fwrite(&lchrom, 4, 1, fp);
+      fwrite(name.data(), 1, name.size(), fp);
+      fwrite(&bp_mut, 4, 1, fp);
+      fwrite(&a, 1, 1, fp);
+      fwrite(&d, 1, 1, fp);
+      fwrite(&aaf, 4, 1, fp);
+      fwrite(&daf, 4, 1, fp);
+      n_written++;
+    }
+  }
+  fclose(fp);
+  if (row != n_rows) return fail(COLATE_ERR_ARG, "colate_maketmp_pileup: more count rows than .mut rows");
+  return n_written;
+}

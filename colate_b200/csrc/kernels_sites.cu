@@ -753,10 +753,15 @@ k_sample(const uint32_t* __restrict__ stream, int64_t n_used, const double4* __r
 constexpr int RP_SITES = 32;    // rows per replay stage
 constexpr int RP_STAGES = 4;
 constexpr int RP_ROWS = 8;      // rows collapsed into one exact update
-constexpr int RP_RANGES = 6;    // consumer warps: 32-bin ranges (192 >= 185 bins)
+#ifndef RP_RANGES_
+#define RP_RANGES_ 6
+#endif
+constexpr int RP_RANGES = RP_RANGES_;   // consumer warps per CTA: each one 32-bin range; 6 / RP_RANGES CTAs cover a block's 192 >= 185 bins
+constexpr int RP_GROUPS = 6 / RP_RANGES;
+static_assert(RP_GROUPS * RP_RANGES == 6, "bin ranges per CTA must divide 6");
 constexpr int RP_THREADS = (RP_RANGES + 1) * 32;   // + 1 producer warp
 struct __align__(16) ReplayStage {
-  uint8_t cnt[ROW_BYTES][RP_SITES];   // one count tile of k_sample: [slot][row]
+  uint8_t cnt[RP_RANGES * 32][RP_SITES];   // this CTA's slots of one count tile of k_sample: [slot][row]
   double4 hdr[RP_SITES];
 };
 
@@ -785,7 +790,7 @@ __device__ __forceinline__ double replay_row(double acc, double w, int c)
 // shortcut is redone row by row (replay_row / exact_sum.cuh).
 // blockIdx.y: 0 shared, 1 not shared.  hdr.z carries -0.0 for rows that add nothing to shared.
 template <int WHICH>
-__device__ __forceinline__ void replay_body(ReplayStage* st, uint64_t* full, uint64_t* empty,
+__device__ __forceinline__ void replay_body(int group, ReplayStage* st, uint64_t* full, uint64_t* empty,
                                             const int64_t* __restrict__ blk_rank_start, const uint8_t* __restrict__ cnt,
                                             const double4* __restrict__ hdr_g, double* __restrict__ out_f,
                                             int64_t* __restrict__ out_n, int64_t* misc)
@@ -806,15 +811,16 @@ __device__ __forceinline__ void replay_body(ReplayStage* st, uint64_t* full, uin
         const int slot = it % RP_STAGES;
         mbar_wait(&empty[slot], ((it / RP_STAGES) & 1) ^ 1);
         const int64_t t = t0 + it;
-        mbar_expect_tx(&full[slot], (uint32_t)(TILE_BYTES + RP_SITES * 32));
-        bulk_g2s(&st[slot].cnt[0][0], cnt + (size_t)t * TILE_BYTES, TILE_BYTES, &full[slot]);
+        constexpr uint32_t CNT_BYTES = RP_RANGES * 32 * RP_SITES;     // the CTA's 32 * RP_RANGES slots: contiguous in the [slot][row] tile
+        mbar_expect_tx(&full[slot], (uint32_t)(CNT_BYTES + RP_SITES * 32));
+        bulk_g2s(&st[slot].cnt[0][0], cnt + (size_t)t * TILE_BYTES + (size_t)group * CNT_BYTES, CNT_BYTES, &full[slot]);
         bulk_g2s(&st[slot].hdr[0], hdr_g + t * RP_SITES, RP_SITES * 32, &full[slot]);
       }
     }
     return;
   }
-  const int bin = threadIdx.x;                                    // 0..191
-  const int cslot = bin < ROW_SLOTS ? slot_of_bin(bin) : bin;     // interleaved count slots (bytes 188..191 stay 0)
+  const int bin = group * (RP_RANGES * 32) + threadIdx.x;         // 0..191
+  const int cslot = threadIdx.x;                                  // slot inside the CTA's part of the tile (slot == bin; bytes 188..191 stay 0)
   double acc = 0.0;
   uint32_t tally = 0;
   bool overflow = false;
@@ -887,7 +893,7 @@ __device__ __forceinline__ void replay_body(ReplayStage* st, uint64_t* full, uin
 // age_shared_emp / age_notshared_emp row 0 (coal.cpp:2250-2256): one addition per row with
 // age_begin <= 0, in row order, thread = age bin.  Runs as the blockIdx.y == 2 slice of k_replay's
 // grid (same launch, other SMs); `scratch` is the CTA's stage storage.
-__device__ __forceinline__ void emp_body(unsigned char* scratch, const int64_t* __restrict__ blk_rank_start,
+__device__ __forceinline__ void emp_body(int group, unsigned char* scratch, const int64_t* __restrict__ blk_rank_start,
                                          const uint8_t* __restrict__ e_b2, const double* __restrict__ e_ws,
                                          const double* __restrict__ e_wn, double* __restrict__ out_f, int64_t* __restrict__ out_n)
 {
@@ -895,7 +901,8 @@ __device__ __forceinline__ void emp_body(unsigned char* scratch, const int64_t* 
   double* sws = (double*)scratch;
   double* swn = sws + CH;
   uint8_t* sb = (uint8_t*)(swn + CH);
-  const int blk = blockIdx.x, bin = threadIdx.x;
+  const int blk = blockIdx.x;
+  const int bin = threadIdx.x < RP_RANGES * 32 ? group * (RP_RANGES * 32) + threadIdx.x : 255;   // (the producer warp's threads only help loading)
   const int64_t r0 = blk_rank_start[blk], r1 = blk_rank_start[blk + 1];
   double as = 0.0, an = 0.0;
   int64_t n = 0;
@@ -919,12 +926,13 @@ k_replay(const int64_t* __restrict__ blk_rank_start, const uint8_t* __restrict__
          const uint8_t* __restrict__ e_b2, const double* __restrict__ e_ws, const double* __restrict__ e_wn,
          double* __restrict__ out_f, int64_t* __restrict__ out_n, int64_t* misc)
 {
-  __shared__ ReplayStage st[RP_STAGES];
+  constexpr int EMP_CH = 512 * 17 / (int)sizeof(ReplayStage) + 1;
+  __shared__ ReplayStage st[RP_STAGES > EMP_CH ? RP_STAGES : EMP_CH];   // (also emp_body's scratch: 512 x 17 bytes)
   __shared__ __align__(8) uint64_t full[RP_STAGES], empty[RP_STAGES];
-  static_assert(sizeof(ReplayStage) * RP_STAGES >= 512 * 17, "emp_body scratch");
-  if (blockIdx.y == 0) replay_body<0>(st, full, empty, blk_rank_start, cnt, hdr_g, out_f, out_n, misc);
-  else if (blockIdx.y == 1) replay_body<1>(st, full, empty, blk_rank_start, cnt, hdr_g, out_f, out_n, misc);
-  else emp_body((unsigned char*)st, blk_rank_start, e_b2, e_ws, e_wn, out_f, out_n);
+  // blockIdx.y: 2 * group + which for the two histograms, 2 * RP_GROUPS + group for the emp slice
+  if (blockIdx.y >= 2 * RP_GROUPS) emp_body(blockIdx.y - 2 * RP_GROUPS, (unsigned char*)st, blk_rank_start, e_b2, e_ws, e_wn, out_f, out_n);
+  else if (blockIdx.y & 1) replay_body<1>(blockIdx.y >> 1, st, full, empty, blk_rank_start, cnt, hdr_g, out_f, out_n, misc);
+  else replay_body<0>(blockIdx.y >> 1, st, full, empty, blk_rank_start, cnt, hdr_g, out_f, out_n, misc);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1122,7 +1130,7 @@ int run_replay(colate_handle* h)
   const int nb = h->n_blocks_local;
   CK(cudaEventRecord(h->ev[4], s));
   if (nb > 0) {
-    k_replay<<<dim3(nb, 3), RP_THREADS, 0, s>>>(h->blk_rank_start.as<int64_t>(), h->u_cnt.as<uint8_t>(), h->u_hdr.as<double4>(),
+    k_replay<<<dim3(nb, 3 * RP_GROUPS), RP_THREADS, 0, s>>>(h->blk_rank_start.as<int64_t>(), h->u_cnt.as<uint8_t>(), h->u_hdr.as<double4>(),
                                                 h->u_eb2.as<uint8_t>(), h->u_ews.as<double>(), h->u_ewn.as<double>(),
                                                 h->out_f.as<double>(), h->out_n.as<int64_t>(), h->misc.as<int64_t>());
     h->launches += 1;

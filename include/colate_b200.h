@@ -265,6 +265,11 @@ int colate_mask_bits_from_fasta(const char* path, int64_t n, const int32_t* pos,
  * per-chromosome .mut files.  target_masks may be NULL (or hold NULL entries).  Returns the records written or < 0. */
 int64_t colate_maketmp_table(int n_chr, const char* const* chr_names, const char* const* mut_files, const char* table_file,
                              const char* const* target_masks, int has_ref_genome, const char* out_file);
+/* make_tmp from a BAM pileup (maketmp_bam, coal.cpp:2527-2680) on pre-decoded arrays: counts[n_rows][4] = reads showing A, C, G, T
+ * at the position of every data row of the .mut files in --chr order (what bam_parser::count_alleles holds at bp_mut - 1; the BAM
+ * decoding stays with the caller).  Returns the records written or < 0. */
+int64_t colate_maketmp_pileup(int n_chr, const char* const* chr_names, const char* const* mut_files, const int32_t* counts,
+                              int64_t n_rows, const char* const* target_masks, const char* out_file);
 /* <out>.colate_mat as mut() writes it for every front-end but tmp/tmp (coal.cpp:3336-3343, 3453-3465): the age grid, then per
  * replicate the shared and the not-shared count vector (already divided by 1e3), default ostream formatting. */
 int colate_write_colate_mat(const char* path, int R, const double* age_bin, const double* counts);

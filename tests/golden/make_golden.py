@@ -289,6 +289,14 @@ def bambam_fixture():
             with open(o + ext) as f, open(os.path.join(OUT, tag + ext), "w") as g:
                 g.write(f.read())
         print(tag, "written:", [ln for ln in r.stderr.splitlines() if "blocks" in ln or "iterations" in ln][:4])
+    # --mode make_tmp --target_bam (maketmp_bam, coal.cpp:2527-2680) on the target's reads: the .colate.in bytes
+    for tag, extra in (("plain", []), ("masked", ["--target_mask", os.path.join(d, "tm")])):
+        o = os.path.join(d, "mk_" + tag)
+        r = subprocess.run([po.ref_cli(), "--mode", "make_tmp", "--mut", os.path.join(d, "syn"), "--chr", os.path.join(d, "chr.txt"),
+                            "--target_bam", os.path.join(d, "t.bam"), "--ref_genome", os.path.join(d, "g"), "-o", o] + extra, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out["maketmp_bam_" + tag] = np.frombuffer(open(o + ".colate.in", "rb").read(), np.uint8)
+        print("make_tmp --target_bam", tag, out["maketmp_bam_" + tag].shape[0], "bytes")
     np.savez_compressed(os.path.join(OUT, "stage1_bambam.npz"), **out)
     print("covered rows: target", int((out["t_counts"].sum(1) > 0).sum()), "reference", int((out["r_counts"].sum(1) > 0).sum()), "of", sites.n)
     import shutil

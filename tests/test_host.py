@@ -348,6 +348,30 @@ def test_make_tmp_from_a_table_matches_the_reference_cli(built, tmp_path):
         assert r.returncode == 0 and open(d + "/live.colate.in", "rb").read() == z["nomask"].tobytes()
 
 
+def test_make_tmp_from_a_pileup_matches_the_reference_cli(built, tmp_path):
+    """SURVEY.md 8(f) N4, the bam variant on pre-decoded arrays: colate_maketmp_pileup against the .colate.in the reference CLI
+    wrote with `--mode make_tmp --target_bam` (maketmp_bam, coal.cpp:2527-2680) from synthetic reads; the pileup handed over is
+    the one the reference's own bam_parser held at every row (fixture stage1_bambam.npz, make_golden.py bambam)."""
+    from helpers import bambam_masks, sites_from
+    z = load("stage1_bambam.npz")
+    sites = sites_from(z)
+    d = str(tmp_path)
+    synth.write_dataset(d, sites, {})
+    tm, _ = bambam_masks(z)
+    for c, nm in enumerate(sites.chr_names):
+        synth.write_mask(os.path.join(d, f"tm_chr{nm}.fa"), tm[c])
+    n = len(sites.chr_names)
+    arr = lambda xs: (C.c_char_p * n)(*[x.encode() for x in xs])
+    names, muts = arr(sites.chr_names), arr([os.path.join(d, f"syn_chr{c}.mut") for c in sites.chr_names])
+    cnt = np.ascontiguousarray(z["t_counts"], dtype=np.int32)
+    for tag, masks in (("plain", None), ("masked", arr([os.path.join(d, f"tm_chr{c}.fa") for c in sites.chr_names]))):
+        out = os.path.join(d, tag + ".colate.in")
+        nrec = api.lib().colate_maketmp_pileup(n, names, muts, api.ptr(cnt), cnt.shape[0], masks, out.encode())
+        assert nrec > 200, api.lib().colate_last_error()
+        assert open(out, "rb").read() == z["maketmp_bam_" + tag].tobytes(), tag
+    assert api.lib().colate_maketmp_pileup(n, names, muts, api.ptr(cnt), cnt.shape[0] - 1, None, (d + "/x").encode()) < 0   # row count must match
+
+
 def test_mask_bits_from_fasta(built):
     sites = synth.make_sites(3, [400, 300], [3e5, 2e5])
     masks = [synth.make_mask(1, 300000, 0.4, 50, 500), synth.make_mask(2, 100000, 0.3, 50, 500, lower=True)]   # 2nd: short + lower case
