@@ -114,6 +114,30 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads (and with them its pinned staging buffers: first touch) to the NUMA node its GPU hangs
+    off.  With one rank per GPU and ~1 GB of file bytes copied in per pass, buffers left on the other socket cross the
+    inter-socket link and every rank's copies slow down.  No-op where the topology is not exposed."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        cpus = sorted(set(cpus) & os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        pass
+    return None
+
+
 def make_dataset(rows, pair=0):
     """Sites are the same for every pair (one Relate .mut set); genomes differ per pair."""
     from colate_b200 import synth
@@ -305,6 +329,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: colate_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -345,8 +370,20 @@ def main():
             api.check(api.lib().colate_set_genome(h._h, slot, d["bp"].shape[0], api.ptr(d["first"]), api.ptr(d["end"]),
                                                   api.ptr(d["bp"]), api.ptr(d["aaf"]), api.ptr(d["daf"]), api.ptr(d["al"]), 0))
 
+    # N > 1: the cohort's .mut files are the same for every pair (make_dataset), i.e. for every rank: each rank copies 1/N of
+    # their bytes from its pinned memory and the ranks all-gather the text over NVLink (pairs.SharedMutText) -- the bytes
+    # cross PCIe once per node and pass instead of once per GPU; every rank still parses the whole text on its own GPU
+    shared_text = None
+    if world > 1:
+        from colate_b200 import pairs as cpairs
+        shared_text = cpairs.SharedMutText(text_pin, torch.device("cuda", local), world, rank)
+        file_bytes = shared_text.h2d_bytes + sum(t.nbytes for t in img_pin)
+
     def upload_files():
-        h.ingest_mut_bytes(text_pin)                                     # text -> site arrays on the GPU
+        if shared_text is not None:
+            h.ingest_mut_device(shared_text.exchange())                  # own slice H2D + NVLink all-gather, then text -> site arrays
+        else:
+            h.ingest_mut_bytes(text_pin)                                 # text -> site arrays on the GPU
         for slot, img in enumerate(img_pin):
             h.ingest_colate_in(slot, img, sites.chr_names)               # records -> genome arrays on the GPU
 
@@ -464,7 +501,10 @@ def main():
         d2h = int(rates.nbytes + iters.nbytes + 8 + 624 * 4 + 64 * (len(text_pin) + 4))
         e2e = {"value": world * sites.n / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(file_bytes),
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
-               "from": "file bytes in pinned host memory: 22 .mut texts (colate_ingest_mut_texts) + 2 .colate.in images (colate_ingest_colate_in)",
+               "from": "file bytes in pinned host memory: 22 .mut texts (colate_ingest_mut_texts) + 2 .colate.in images (colate_ingest_colate_in)" +
+                       ("; the .mut text is the cohort's (the same for every pair / rank): each rank copies 1/N of it and the ranks all-gather it "
+                        "over NVLink (pairs.SharedMutText, one NCCL all_gather of %d bytes per pass); h2d_bytes_per_step is per rank" % (shared_text.per * world)
+                        if shared_text is not None else ""),
                "mut_parse_kernel_ms": ing["kernel_ms"], "rows_reparsed_on_host": ing["host_fallback_rows"],
                "rates_equal_device_resident_pass": True, "serial_ms_per_step": ms_e2e_serial,
                "pipeline": "EM of pass i on the handle's EM stream (colate_stage3_em_begin/_end) under the copies, parse and stage i of pass i+1; "
@@ -586,6 +626,7 @@ def main():
                                     "l2": "inputs (~0.5 GB SoA + 0.2-1 GB generator stream per pass) exceed the 126 MB L2; no flush needed"},
                 "value_pipelined": {"value": world * rows / (ms_pipe / args.steps * 1e-3), "ms_per_step": ms_pipe / args.steps,
                                     "what": "device-resident passes with the EM of pass i overlapped with stage i of pass i+1 (two streams of one handle)"},
+                "host_binding": numa,
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "em": em,
                 "stage_ms": {**t_stage, "pass_total_ms": per_step}}
         if e2e:

@@ -231,6 +231,21 @@ class Handle:
         self.n_site = int(rows.sum())
         return rows
 
+    def ingest_mut_device(self, ptr_sizes, row_capacity=None):
+        """ingest_mut for texts that already sit in device memory: [(device pointer, bytes)] per --chr entry."""
+        n = len(ptr_sizes)
+        if row_capacity is None:
+            row_capacity = sum(int(b) for _, b in ptr_sizes) // 20 + n
+        check(lib().colate_ingest_begin(self._h, n, row_capacity))
+        ptrs = (C.c_void_p * n)(*[int(p) for p, _ in ptr_sizes])
+        sizes = np.array([int(b) for _, b in ptr_sizes], dtype=np.int64)
+        rows = np.zeros(n, dtype=np.int64)
+        check(lib().colate_ingest_mut_texts(self._h, n, ptrs, sizes, 1, ptr(rows)))
+        check(lib().colate_ingest_end(self._h))
+        self.n_chr = n
+        self.n_site = int(rows.sum())
+        return rows
+
     def ingest_colate_in(self, slot, image, chr_names):
         """.colate.in image (bytes or a uint8 array, e.g. pinned) -> genome slot, decoded on the device.
         Replaces read_colate_in() + set_genome().  Returns the number of records."""

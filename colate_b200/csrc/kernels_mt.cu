@@ -106,7 +106,10 @@ k_jump(uint32_t* __restrict__ windows, const uint16_t* __restrict__ taps0, int n
 // three words of a round relative to tile_off and steps them by 624 = 3 rows + 24 words per round, so the
 // loop has no division and no 64-bit compare.  The CTA that produces the last word also leaves the last
 // min(total, 624) words linearly in `tail` (from the two windows it holds) for the state recovery.
-template <bool TILED>
+// PRE: the chunk range starts before tile_off (a sharded job whose first row does not sit on a chunk boundary): words in
+// front of tile_off stay linear.  W32: the whole buffer is below 2^31 words, addresses as 32-bit word offsets.  (The
+// address arithmetic was 14 of the 37 instructions of a step; without the linear fallback and in 32 bits it is 8.)
+template <bool TILED, bool PRE, bool W32>
 __global__ void __launch_bounds__(256)
 k_gen(const uint32_t* __restrict__ windows, int64_t chunk_words, int64_t total_words, uint32_t* __restrict__ stream,
       int64_t tile_off, uint32_t* __restrict__ tail)
@@ -137,7 +140,10 @@ k_gen(const uint32_t* __restrict__ windows, int64_t chunk_words, int64_t total_w
     if (!TILED) return lin;
     const int c = (pw[j] * 3277) >> 16;                        // pw / 20 for pw < 200
     const int inner = (prow[j] & 31) * SAMPLE_CHUNK_WORDS + (c / (SAMPLE_CHUNK_WORDS / 20)) * (31 * SAMPLE_CHUNK_WORDS) + pw[j];
-    uint32_t* t = tiled_base + ((int64_t)(prow[j] >> 5) * SAMPLE_TILE_WORDS + inner);
+    uint32_t* t;
+    if (W32) t = tiled_base + (uint32_t)((prow[j] >> 5) * SAMPLE_TILE_WORDS + inner);
+    else t = tiled_base + ((int64_t)(prow[j] >> 5) * SAMPLE_TILE_WORDS + inner);
+    if (!PRE) return t;
     return prow[j] >= 0 ? t : lin;
   };
   auto advance = [&]() {
@@ -321,8 +327,15 @@ int run_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int
   }
   if (total_local > 0) {
     if (tiled && off % 200 != 0) return fail(COLATE_ERR_ARG, "tiled generator stream must start at a row boundary");
-    if (tiled) k_gen<true><<<M, 256, 0, s>>>(h->windows.as<uint32_t>(), S, total_local, h->rng_stream.as<uint32_t>(), off, h->mt_tail.as<uint32_t>());
-    else k_gen<false><<<M, 256, 0, s>>>(h->windows.as<uint32_t>(), S, total_local, h->rng_stream.as<uint32_t>(), 0, h->mt_tail.as<uint32_t>());
+    const bool w32 = total_local + SAMPLE_TILE_WORDS < ((int64_t)1 << 31);
+    uint32_t* win = h->windows.as<uint32_t>();
+    uint32_t* st = h->rng_stream.as<uint32_t>();
+    uint32_t* tl = h->mt_tail.as<uint32_t>();
+    if (!tiled) k_gen<false, false, false><<<M, 256, 0, s>>>(win, S, total_local, st, 0, tl);
+    else if (off == 0 && w32) k_gen<true, false, true><<<M, 256, 0, s>>>(win, S, total_local, st, off, tl);
+    else if (off == 0) k_gen<true, false, false><<<M, 256, 0, s>>>(win, S, total_local, st, off, tl);
+    else if (w32) k_gen<true, true, true><<<M, 256, 0, s>>>(win, S, total_local, st, off, tl);
+    else k_gen<true, true, false><<<M, 256, 0, s>>>(win, S, total_local, st, off, tl);
     h->launches += 1;
     CK(cudaGetLastError());
   }

@@ -824,9 +824,19 @@ __device__ __forceinline__ void replay_body(int group, ReplayStage* st, uint64_t
   double acc = 0.0;
   uint32_t tally = 0;
   bool overflow = false;
+#ifdef REPLAY_PROF
+  long long pf_t0 = clock64(), pf_wait = 0, pf_slow = 0;
+  int pf_runs = 0, pf_skipped = 0, pf_slowruns = 0, pf_rel = 0, pf_slowlanes = 0;
+#endif
   for (int it = 0; it < n_stage; it++) {
     const int slot = it % RP_STAGES;
+#ifdef REPLAY_PROF
+    long long pf_a = clock64();
+#endif
     mbar_wait(&full[slot], (it / RP_STAGES) & 1);
+#ifdef REPLAY_PROF
+    pf_wait += clock64() - pf_a;
+#endif
     // rows of this tile that belong to the block ...
     const int64_t g0r = (t0 + it) * RP_SITES;
     const int lo = (int)max((int64_t)0, r0 - g0r), hi = (int)min((int64_t)RP_SITES, r1 - g0r);
@@ -848,7 +858,17 @@ __device__ __forceinline__ void replay_body(int group, ReplayStage* st, uint64_t
       if (WHICH == 1) overflow |= (bin == NBINS) & ((cs_lo | cs_hi) != 0);   // a sample in bin 185: out of bounds in the reference
       tally += __dp4a(cs_lo, 0x01010101u, __dp4a(cs_hi, 0x01010101u, 0u));
       const bool any = (cs_lo | cs_hi) != 0;
+#ifdef REPLAY_PROF
+      pf_runs++;
+      {  // rows of the run in which any lane of the warp has a count
+        uint32_t nzb = 0;
+        for (int i = 0; i < 8; i++) nzb |= ((((i < 4 ? cs_lo : cs_hi) >> (8 * (i & 3))) & 0xff) != 0) << i;
+        pf_rel += __popc(__reduce_or_sync(0xffffffffu, nzb));
+      }
+      if (!__any_sync(0xffffffffu, any)) { pf_skipped++; continue; }
+#else
       if (!__any_sync(0xffffffffu, any)) continue;
+#endif
       const int E = __double2hiint(acc) >> 20;                         // biased exponent (acc >= 0)
       const double M = __hiloint2double((E << 20) | 0x80000, 0);       // 1.5 * 2^E: ulp(M) == ulp(acc)
       const double hu = __hiloint2double((E - 53) << 20, 0);           // ulp(acc) / 2
@@ -868,7 +888,15 @@ __device__ __forceinline__ void replay_body(int group, ReplayStage* st, uint64_t
       bad |= (__double2hiint(accn) >> 20) != E;
       bad &= any;
       if (__any_sync(0xffffffffu, bad)) {
+#ifdef REPLAY_PROF
+        pf_slowruns++;
+        pf_slowlanes += __popc(__ballot_sync(0xffffffffu, bad));
+        long long pf_b = clock64();
+#endif
         if (bad) {
+          // (a lane's count is zero in ~85 % of the rows: the serial path only pays for the one or two rows of the run that carry
+          // a count.  A variant that located the crossing row from prefix sums of collapsed steps and committed the rows on
+          // either side at once was measured SLOWER, 1.36 ms against 0.76: its passes touch all eight rows.)
 #pragma unroll 1
           for (int r = g0; r < g0 + RP_ROWS; r++) {
             if (!((live >> r) & 1u)) continue;
@@ -878,11 +906,20 @@ __device__ __forceinline__ void replay_body(int group, ReplayStage* st, uint64_t
               acc = replay_row(acc, w, c);
           }
         } else if (any) acc = accn;
+#ifdef REPLAY_PROF
+        __syncwarp();
+        pf_slow += clock64() - pf_b;
+#endif
       } else if (any) acc = accn;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[slot]);
   }
+#ifdef REPLAY_PROF
+  if (lane == 0 && (blk == 3 || blk == 50))
+    printf("[replay prof] blk %d which %d warp %d stages %d: cycles %lld wait %lld slow %lld | runs %d skipped %d slow %d (lanes %d) | relevant rows %d of %d\n",
+           blk, WHICH, warp, n_stage, clock64() - pf_t0, pf_wait, pf_slow, pf_runs, pf_skipped, pf_slowruns, pf_slowlanes, pf_rel, pf_runs * 8);
+#endif
   if (overflow) misc[3] = 1;
   if (bin < NBINS) {
     out_f[((size_t)blk * 4 + WHICH) * NBINS + bin] = acc;

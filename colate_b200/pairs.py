@@ -13,6 +13,12 @@ Results per pair are what `api.mut()` returns for that pair alone (same seed): b
 
 Across GPUs (`all_pairs_sharded`): pair p -> rank p mod world, every rank holds the mutation SoA and
 all genomes, no collective on the data path; the result tables are combined by one all-reduce at the end.
+
+The cohort's `.mut` files are the same for every pair, hence for every rank.  `SharedMutText` brings their bytes to all
+GPUs of a node with ONE crossing of PCIe: every rank copies 1/world of the bytes from its pinned host memory and the ranks
+all-gather the text over NVLink (687 MB for the whole-genome set: ~86 MB of host-to-device copy per rank at 8 GPUs instead
+of 687 MB each through PCIe uplinks that pairs of GPUs share); each rank then parses the text on its own GPU
+(`Handle.ingest_mut_device`).  This is the one real exchange step of the pair-sharded path.
 """
 from __future__ import annotations
 
@@ -97,3 +103,40 @@ def all_pairs_sharded(handle, n_genomes: int, seed: int, bins: str = "3,7,0.1", 
     dist.all_reduce(sec, op=dist.ReduceOp.MAX)
     out["seconds"] = dict(stage12=float(sec[0]), em=float(sec[1]))
     return out
+
+
+class SharedMutText:
+    """The `.mut` texts of a cohort (one uint8 array per --chr entry, the SAME bytes on every rank, in pinned host memory) on
+    every GPU of the job: rank r copies byte range [r, r+1) * per of their concatenation, `dist.all_gather_into_tensor`
+    completes the text on every GPU.  exchange() returns per-chromosome (device pointer, bytes) for ingest_mut_device()."""
+
+    def __init__(self, texts, device, world: int, rank: int):
+        import torch
+        self.torch = torch
+        self.world, self.rank = world, rank
+        sizes = [int(t.shape[0]) for t in texts]
+        self.sizes = sizes
+        self.offs = np.concatenate([[0], np.cumsum([(n + 255) & ~255 for n in sizes])]).astype(np.int64)   # 256-byte aligned starts
+        total = int(self.offs[-1])
+        self.per = ((total + world - 1) // world + 255) & ~255
+        host = torch.zeros(self.per, dtype=torch.uint8).pin_memory()      # this rank's slice of the concatenation
+        lo, hi = rank * self.per, (rank + 1) * self.per
+        hv = host.numpy()
+        for c, t in enumerate(texts):
+            a, b = int(self.offs[c]), int(self.offs[c]) + sizes[c]
+            x, y = max(a, lo), min(b, hi)
+            if x < y:
+                hv[x - lo:y - lo] = t[x - a:y - a]
+        self.host = host
+        self.dev = torch.empty(world * self.per, dtype=torch.uint8, device=device)
+        self.h2d_bytes = self.per
+
+    def exchange(self):
+        import torch.distributed as dist
+        mine = self.dev[self.rank * self.per:(self.rank + 1) * self.per]
+        mine.copy_(self.host, non_blocking=True)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.dev, mine)
+        self.torch.cuda.current_stream().synchronize()          # the handle parses on its own stream
+        base = self.dev.data_ptr()
+        return [(base + int(self.offs[c]), self.sizes[c]) for c in range(len(self.sizes))]
