@@ -147,6 +147,52 @@ def test_config4_adna_masks(handle):
         assert iters[r] == it and np.array_equal(rates[r], ro) and ll[r] == llo
 
 
+def test_config4_adna_masks_whole_genome(handle):
+    """BASELINE.json configs[3] at FULL size: 22 autosomes, 10 M rows, ~0.5x genomes of mostly single reads, P/N masks with
+    40 % (target) / 20 % (reference) N in runs of 1-50 kb over every chromosome: stage i bit for bit (histograms, tallies,
+    generator state), stage ii at age 250 generations."""
+    lens = synth.AUTOSOME_LEN
+    sites = synth.make_sites(4, synth.rows_for_genome(10_000_000), lens)
+    gt = synth.make_genome(104, sites, 0.35, mean_extra_reads=0.1)
+    gr = synth.make_genome(204, sites, 0.35, mean_extra_reads=0.1)
+    tm = [synth.make_mask(40 + c, int(L), 0.4) for c, L in enumerate(lens)]
+    rm = [synth.make_mask(50 + c, int(L), 0.2) for c, L in enumerate(lens)]
+    o = po.stage1(sites, gt, gr, seed=1, tmask=tm, rmask=rm)
+    handle.load(sites, gt, gr, tm, rm)
+    del tm, rm
+    s1 = handle.stage1(api.mt_seed(1))
+    _compare_stage1(o, s1)
+    assert s1.n_used > 30_000 and s1.num_blocks > 100
+    age = 7000.0 / 28.0
+    w = api.draw_block_weights(s1.mt_state, 3, s1.num_blocks)
+    assert np.array_equal(handle.stage2_bootstrap(w, s1.block_stats, age), po.stage2(w, o, age))
+    handle.set_mask(0, None); handle.set_mask(1, None)
+
+
+def test_config5_all_pairs_eight_genomes(handle):
+    """BASELINE.json configs[4] at 1 M rows x 8 genomes: all 28 ordered pairs through the batched driver (joins cached per
+    genome, one generator stream for all pairs, one EM launch); a third of the pairs against the oracle, bit for bit."""
+    from colate_b200 import pairs as pairs_mod
+    sites = synth.make_sites(12, synth.rows_for_genome(1_000_000), synth.AUTOSOME_LEN)
+    genomes = [synth.make_genome(400 + g, sites, 0.7) for g in range(8)]
+    handle.set_sites(sites.site_off, sites.pos, sites.age_begin, sites.age_end, sites.meta())
+    for g, G in enumerate(genomes):
+        handle.set_genome(g, G.chrom, G.bp, G.aaf, G.daf, G.anc.astype(np.uint16) | (G.der.astype(np.uint16) << 8))
+        handle.set_mask(g, None)
+    res = pairs_mod.all_pairs(handle, len(genomes), seed=5, bins="3,7,0.1", max_iter=40)
+    assert res["pairs"].shape == (28, 2)
+    ep, _ = po.epochs_from_bins("3,7,0.1", 0.0, 28.0)
+    init = np.full(len(ep), 1 / 20000.)
+    for p in range(0, 28, 3):
+        i, j = res["pairs"][p]
+        o = po.stage1(sites, genomes[i], genomes[j], seed=5)
+        assert res["num_blocks"][p] == o["num_blocks"] and res["n_used"][p] == o["n_used_total"]
+        w = po.draw_block_weights(o["rng"], 1, o["num_blocks"])
+        assert np.array_equal(res["counts"][p], po.stage2(w, o, 0.0)[0]), (i, j)
+        ro, it, llo = po.em_run(ep, init, res["counts"][p], max_iter=40)
+        assert res["iters"][p] == it and np.array_equal(res["rates"][p], ro) and res["ll"][p] == llo, (i, j)
+
+
 def test_config5_all_pairs_small(handle):
     """BASELINE.json configs[4] (all pairs of N genomes over one mutation set) at small scale: every
     ordered pair (target=i, reference=j), i<j, through the batched driver == that pair run alone == oracle."""
