@@ -53,6 +53,9 @@ SIGNATURES = {
     "colate_set_sites": (C.c_int, [VP, C.c_int, VP, VP, VP, VP, VP, C.c_int]),
     "colate_set_genome": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, C.c_int]),
     "colate_set_pileup": (C.c_int, [VP, C.c_int, VP, C.c_int]),
+    "colate_pileup_begin": (C.c_int, [VP, C.c_int]),
+    "colate_pileup_reads": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, VP, C.c_int64, C.c_int, C.c_int, C.c_int]),
+    "colate_pileup_end": (C.c_int, [VP, C.c_int, VP]),
     "colate_set_mask": (C.c_int, [VP, C.c_int, VP, C.c_int]),
     "colate_stage1_flags": (C.c_int, [VP, C.c_int, C.c_int, VP, VP]),
     "colate_stage1_sample": (C.c_int, [VP, VP, C.c_int64, C.c_int, VP, VP, VP]),

@@ -192,6 +192,22 @@ class Handle:
         assert counts.shape == (self.n_site, 4)
         check(lib().colate_set_pileup(self._h, slot, ptr(counts), 0))
 
+    def pileup_from_reads(self, slot, per_chr_reads, ref_genomes, filters=(20, 30, 10), fetch=False):
+        """N3, the decoder's counting loop on the device: per_chr_reads[c] = (pos int32[n], mapq uint8[n], len int32[n],
+        seq_off int64[n], seq uint8[bytes], qual uint8[bytes]) of contig c (or None), ref_genomes[c] = uint8 sequence of the
+        contig.  Makes `slot` a pileup genome; fetch=True returns counts[n_site][4]."""
+        check(lib().colate_pileup_begin(self._h, slot))
+        for c, rd in enumerate(per_chr_reads):
+            if rd is None or len(rd[0]) == 0:
+                continue
+            pos, mapq, ln, off, seq, qual = [np.ascontiguousarray(a, dtype=dt) for a, dt in zip(rd, (np.int32, np.uint8, np.int32, np.int64, np.uint8, np.uint8))]
+            ref = np.ascontiguousarray(ref_genomes[c], dtype=np.uint8)
+            check(lib().colate_pileup_reads(self._h, slot, c, pos.shape[0], ptr(pos), ptr(mapq), ptr(ln), ptr(off), ptr(seq), ptr(qual), ptr(ref),
+                                            ref.shape[0], *filters))
+        out = np.zeros((self.n_site, 4), dtype=np.int32) if fetch else None
+        check(lib().colate_pileup_end(self._h, slot, ptr(out) if fetch else None))
+        return out
+
     def set_mask(self, slot, pass_bits):
         if pass_bits is None:
             check(lib().colate_set_mask(self._h, slot, None, 0))

@@ -246,6 +246,80 @@ int colate_set_pileup(colate_handle* h, int slot, const int32_t* counts, int loc
   return 0;
 }
 
+// ---- pileup from decoded reads (the counting loop of bam_parser, include/vcf/htslib.cpp:60-168, on the device) -----------------
+int colate_pileup_begin(colate_handle* h, int slot)
+{
+  if (!h || slot < 0 || slot >= COLATE_MAX_GENOMES) return fail(COLATE_ERR_ARG, "colate_pileup_begin: bad arguments");
+  if (!h->sites_set) return fail(COLATE_ERR_STATE, "colate_pileup_begin: call colate_set_sites first");
+  CK(cudaSetDevice(h->device));
+  GenomeDev& g = h->genomes[slot];
+  CK(g.pile.ensure((size_t)h->n_site * 16 + 16));
+  CK(cudaMemsetAsync(g.pile.p, 0, (size_t)h->n_site * 16, h->stream));
+  g.set = false;
+  g.pileup = false;
+  g.joined = false;
+  h->flags_done = false;
+  return 0;
+}
+
+int colate_pileup_reads(colate_handle* h, int slot, int chr_index, int64_t n_reads, const int32_t* pos, const uint8_t* mapq, const int32_t* len,
+                        const int64_t* seq_off, const uint8_t* seq, const uint8_t* qual, const uint8_t* ref_seq, int64_t ref_len,
+                        int mapq_th, int len_th, int mismatch_th)
+{
+  if (!h || slot < 0 || slot >= COLATE_MAX_GENOMES || n_reads < 0 || (n_reads > 0 && (!pos || !mapq || !len || !seq_off || !seq || !qual || !ref_seq)))
+    return fail(COLATE_ERR_ARG, "colate_pileup_reads: bad arguments");
+  if (!h->sites_set || chr_index < 0 || chr_index >= h->n_chr) return fail(COLATE_ERR_ARG, "colate_pileup_reads: no such chromosome in the site set");
+  if (h->genomes[slot].pile.cap < (size_t)h->n_site * 16) return fail(COLATE_ERR_STATE, "colate_pileup_reads: call colate_pileup_begin first");
+  if (n_reads == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  int max_len = 0;
+  int64_t n_bytes = 0;
+  for (int64_t k = 0; k < n_reads; k++) {
+    if (len[k] < 0 || seq_off[k] < 0) return fail(COLATE_ERR_ARG, "colate_pileup_reads: negative read length / offset");
+    if (k > 0 && pos[k] < pos[k - 1]) return fail(COLATE_ERR_ORDER, "Error: BAM file not sorted by position.");   // htslib.cpp:411-414
+    max_len = std::max(max_len, len[k]);
+    n_bytes = std::max<int64_t>(n_bytes, seq_off[k] + len[k]);
+  }
+  cudaStream_t s = h->stream;
+  // one staging buffer: pos | len | off | mapq | seq | qual | ref | pass
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t o_pos = 0, o_len = o_pos + up(n_reads * 4), o_off = o_len + up(n_reads * 4), o_mq = o_off + up(n_reads * 8),
+               o_seq = o_mq + up(n_reads), o_q = o_seq + up(n_bytes), o_ref = o_q + up(n_bytes), o_pass = o_ref + up(ref_len),
+               total = o_pass + up(n_reads);
+  CK(h->d_tmp.ensure(total));
+  char* d = h->d_tmp.as<char>();
+  CK(cudaMemcpyAsync(d + o_pos, pos, n_reads * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d + o_len, len, n_reads * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d + o_off, seq_off, n_reads * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d + o_mq, mapq, n_reads, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d + o_seq, seq, n_bytes, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d + o_q, qual, n_bytes, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d + o_ref, ref_seq, ref_len, cudaMemcpyHostToDevice, s));
+  int rc = run_pileup_reads(h, slot, chr_index, n_reads, (const int32_t*)(d + o_pos), (const uint8_t*)(d + o_mq), (const int32_t*)(d + o_len),
+                            (const int64_t*)(d + o_off), (const uint8_t*)(d + o_seq), (const uint8_t*)(d + o_q), (const uint8_t*)(d + o_ref), ref_len,
+                            max_len, mapq_th, len_th, mismatch_th, (uint8_t*)(d + o_pass));
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(s));      // the caller's buffers and the staging buffer are free again
+  return 0;
+}
+
+int colate_pileup_end(colate_handle* h, int slot, int32_t* counts_out)
+{
+  if (!h || slot < 0 || slot >= COLATE_MAX_GENOMES) return fail(COLATE_ERR_ARG, "colate_pileup_end: bad arguments");
+  GenomeDev& g = h->genomes[slot];
+  if (!h->sites_set || g.pile.cap < (size_t)h->n_site * 16) return fail(COLATE_ERR_STATE, "colate_pileup_end: call colate_pileup_begin first");
+  CK(cudaSetDevice(h->device));
+  if (counts_out) CK(cudaMemcpyAsync(counts_out, g.pile.p, (size_t)h->n_site * 16, cudaMemcpyDeviceToHost, h->stream));
+  g.n_rec = 0;
+  g.pileup = true;
+  g.set = true;
+  g.joined = false;
+  h->flags_done = false;
+  CK(cudaMemsetAsync(h->order_flag.as<int>() + 1 + slot, 0, 4, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int colate_set_mask(colate_handle* h, int slot, const uint32_t* pass_bits, int location)
 {
   if (!h || slot < 0 || slot >= COLATE_MAX_GENOMES) return fail(COLATE_ERR_ARG, "colate_set_mask: bad arguments");

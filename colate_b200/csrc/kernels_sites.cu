@@ -184,6 +184,77 @@ __global__ void k_pileup_join(int64_t n_site, const uint32_t* __restrict__ meta,
   j_aaf[m] = a; j_daf[m] = d; j_prevbp[m] = 0x7fffffff; j_flag[m] = fl;
 }
 
+// ---- pileup of decoded alignment records (the decoder's counting loop) ----------------------------------------
+// bam_parser (include/vcf/htslib.cpp) keeps, for the positions around the one parse_onebambam / maketmp_bam look up, how many
+// reads show A, C, G, T: count_alleles_for_read (htslib.cpp:60-168) per read, read_to_pos (426-437) to stay ahead of the
+// lookups.  At lookup time a position's counts are those of ALL reads of the contig that cover it (reads are sorted by start
+// and far shorter than half the ring), so the ring reduces to a function of the reads:
+//   a read counts iff mapq >= mapq_th, len >= len_th and, over its bases i in [3, len - 3) with quality >= 30 that lie inside the
+//   reference genome, total > 0 and total - matching <= mismatch_th (htslib.cpp:63-99, 143);
+//   it then adds one to column A/C/G/T of every position pos + i, i in [3, len - 3), whose base quality is >= 30 (145-161).
+// k_read_filter: thread = read -> pass flag.  k_pileup_rows: thread = .mut row of the contig: the reads that can cover its
+// position start in (p - max_len, p]: binary search in the sorted starts, then a short scan.  No atomics, no ring.
+// One quirk of the reference is reproduced: the FIRST read of every contig is counted by assign_contig (htslib.cpp:535-566), which
+// leaves `q` pointing at the record's packed 4-bit sequence (bam_get_seq, line 549) instead of its qualities (read_entry
+// re-points it, line 406).  For that one read "quality i" is byte i of {packed sequence, then the qualities}: found by the
+// golden test (one row of the fixture differed), pinned by it.
+__device__ __forceinline__ int nt16_code(uint8_t c)
+{
+  const char* t = "=ACMGRSVTWYHKDBN";          // seq_nt16_str: bam_parser::seq holds these letters
+  int k = 15;
+#pragma unroll
+  for (int i = 0; i < 16; i++) k = (c == (uint8_t)t[i]) ? i : k;
+  return k;
+}
+__device__ __forceinline__ int read_base_quality(int64_t k, int64_t i, int l, int64_t o, const uint8_t* __restrict__ seq, const uint8_t* __restrict__ qual)
+{
+  if (k != 0) return qual[o + i];
+  const int64_t nb = ((int64_t)l + 1) >> 1;
+  if (i >= nb) return qual[o + i - nb];
+  const int hi = nt16_code(seq[o + 2 * i]), lo = 2 * i + 1 < l ? nt16_code(seq[o + 2 * i + 1]) : 0;
+  return (hi << 4) | lo;
+}
+__global__ void k_read_filter(int64_t n_reads, const int32_t* __restrict__ pos, const uint8_t* __restrict__ mapq, const int32_t* __restrict__ len,
+                              const int64_t* __restrict__ off, const uint8_t* __restrict__ seq, const uint8_t* __restrict__ qual,
+                              const uint8_t* __restrict__ ref, int64_t ref_len, int mapq_th, int len_th, int mismatch_th, uint8_t* __restrict__ pass)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_reads) return;
+  const int l = len[k];
+  bool ok = false;
+  if ((int)mapq[k] >= mapq_th && l >= len_th) {
+    const int64_t p = pos[k], o = off[k];
+    int total = 0, matching = 0;
+    for (int i = 3; i < l - 3; i++) {
+      if (p + i >= ref_len) break;
+      if (read_base_quality(k, i, l, o, seq, qual) >= 30) { total++; matching += ref[p + i] == seq[o + i]; }
+    }
+    ok = total > 0 && total - matching <= mismatch_th;
+  }
+  pass[k] = ok ? 1 : 0;
+}
+
+__global__ void k_pileup_rows(int64_t row0, int64_t n_rows, const int32_t* __restrict__ site_pos, int64_t n_reads, const int32_t* __restrict__ pos,
+                              const int32_t* __restrict__ len, const int64_t* __restrict__ off, const uint8_t* __restrict__ seq,
+                              const uint8_t* __restrict__ qual, const uint8_t* __restrict__ pass, int max_len, int4* __restrict__ pile)
+{
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_rows) return;
+  const int64_t p = (int64_t)site_pos[row0 + m] - 1;          // 0-based position of the row (coal.cpp:1885)
+  int64_t lo = 0, hi = n_reads;                                // first read with start > p - max_len
+  while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if ((int64_t)pos[mid] <= p - max_len) lo = mid + 1; else hi = mid; }
+  int4 c = pile[row0 + m];
+  for (int64_t k = lo; k < n_reads && (int64_t)pos[k] <= p; k++) {
+    if (!pass[k]) continue;
+    const int64_t i = p - pos[k];
+    if (i < 3 || i >= (int64_t)len[k] - 3) continue;
+    if (read_base_quality(k, i, len[k], off[k], seq, qual) < 30) continue;
+    const uint8_t b = seq[off[k] + i];
+    c.x += b == 'A'; c.y += b == 'C'; c.z += b == 'G'; c.w += b == 'T';
+  }
+  pile[row0 + m] = c;
+}
+
 // ---- input order (COLATE_ERR_ORDER) ---------------------------------------------------------
 // k_join's binary search and the find-previous-candidate rule of k_ok equal the reference's sequential reader
 // (coal.cpp:2184-2217) only on ascending positions: .mut rows ascending within a chromosome, .colate.in records
@@ -1195,6 +1266,23 @@ int run_replay(colate_handle* h)
     h->launches += 1;
   }
   CK(cudaEventRecord(h->ev[5], s));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// pileup of one contig's decoded reads at the rows of chromosome chr (device pointers throughout)
+int run_pileup_reads(colate_handle* h, int slot, int chr, int64_t n_reads, const int32_t* pos, const uint8_t* mapq, const int32_t* len,
+                     const int64_t* off, const uint8_t* seq, const uint8_t* qual, const uint8_t* ref, int64_t ref_len, int max_len,
+                     int mapq_th, int len_th, int mismatch_th, uint8_t* pass_scratch)
+{
+  GenomeDev& g = h->genomes[slot];
+  const int64_t row0 = h->h_site_off[chr], n_rows = h->h_site_off[chr + 1] - row0;
+  if (n_reads <= 0 || n_rows <= 0) return 0;
+  cudaStream_t s = h->stream;
+  k_read_filter<<<grid_for(n_reads, 256), 256, 0, s>>>(n_reads, pos, mapq, len, off, seq, qual, ref, ref_len, mapq_th, len_th, mismatch_th, pass_scratch);
+  k_pileup_rows<<<grid_for(n_rows, 128), 128, 0, s>>>(row0, n_rows, h->pos.as<int32_t>(), n_reads, pos, len, off, seq, qual, pass_scratch, max_len,
+                                                     g.pile.as<int4>());
+  h->launches += 2;
   CK(cudaGetLastError());
   return 0;
 }

@@ -92,6 +92,24 @@ int colate_set_genome(colate_handle* h, int slot, int64_t n_rec, const int64_t* 
  * (coal.cpp:2005-2039) and the 1e3 normalisation of stage ii (coal.cpp:3453-3463). */
 int colate_set_pileup(colate_handle* h, int slot, const int32_t* counts, int location);
 
+/* The decoder's counting loop on the device: the pileup of genome `slot` from DECODED alignment records instead of finished counts.
+ * Replaces bam_parser::count_alleles_for_read / read_to_pos (include/vcf/htslib.cpp:60-168, 426-437) for the positions the bam
+ * front-ends look up; what stays with the caller is BAM decompression (sam_read1).  Per contig of the --chr list, its reads in file
+ * order (sorted by start, as the reference requires: htslib.cpp:411-414):
+ *   pos[k] 0-based leftmost position, mapq[k], len[k] (l_qseq), seq_off[k] offset of the read's bases / qualities in seq / qual,
+ *   seq: one ASCII letter per base (seq_nt16_str of the 4-bit code, htslib.cpp:403), qual: phred bytes;
+ *   ref_seq / ref_len: the contig of --ref_genome as fasta::Read leaves it (upper-cased, data.cpp:213-237);
+ *   mapq_th, len_th, mismatch_th: --filters (default "20,30,10", coal.cpp:3096); the base-quality threshold is 30 (htslib.hpp:66).
+ * One call takes ALL reads of a contig: its first record is the one the reference counts from assign_contig with the record's packed
+ * sequence bytes in place of its qualities (htslib.cpp:549 against 406) -- reproduced.
+ * colate_pileup_begin zeroes the slot's counts, colate_pileup_reads adds one contig, colate_pileup_end makes the slot a pileup
+ * genome (as colate_set_pileup would) and optionally returns counts[n_site][4] (e.g. for colate_maketmp_pileup).  Host pointers. */
+int colate_pileup_begin(colate_handle* h, int slot);
+int colate_pileup_reads(colate_handle* h, int slot, int chr_index, int64_t n_reads, const int32_t* pos, const uint8_t* mapq, const int32_t* len,
+                        const int64_t* seq_off, const uint8_t* seq, const uint8_t* qual, const uint8_t* ref_seq, int64_t ref_len,
+                        int mapq_th, int len_th, int mismatch_th);
+int colate_pileup_end(colate_handle* h, int slot, int32_t* counts_out);
+
 /* P/N mask of genome `slot` evaluated at the site positions (fasta::Read,
  * include/src/data.cpp:213-237; test at coal.cpp:2169-2174): bit m of pass_bits = row m is
  * NOT rejected by the mask (positions at or beyond the mask end pass).  NULL clears it. */

@@ -423,3 +423,37 @@ def ref_bam_pileup(bam_path, contig, ref_genome_path, bp, params="20,30,10"):
     cov = np.zeros(bp.shape[0], dtype=np.uint8)
     ref().ref_bam_pileup(params.encode(), bam_path.encode(), contig.encode(), ref_genome_path.encode(), bp.shape[0], bp, counts, cov)
     return counts, cov
+
+
+def pileup_from_reads(pos_rows, reads, ref_seq, filters=(20, 30, 10)):
+    """Restatement of what bam_parser (include/vcf/htslib.cpp:60-168, 379-437, 490-573) holds at the 1-based positions `pos_rows`
+    of ONE contig after reading its `reads` [(pos0, mapq, seq bytes, qual uint8 array)] in file order: counts [n][4] (A, C, G, T).
+    Pure Python (small cases).  The first read of the contig is counted by assign_contig, which leaves `q` pointing at the record's
+    packed 4-bit sequence instead of its qualities (htslib.cpp:549 against 406): "quality i" of that read is byte i of
+    {packed sequence, qualities}."""
+    code = {c: i for i, c in enumerate(b"=ACMGRSVTWYHKDBN")}
+    rows = {int(p) - 1: i for i, p in enumerate(pos_rows)}
+    out = np.zeros((len(pos_rows), 4), dtype=np.int32)
+    for k, (p, mq, seq, q) in enumerate(reads):
+        l = len(seq)
+        if k == 0:
+            nb = (l + 1) // 2
+            packed = [(code.get(seq[2 * i], 15) << 4) | (code.get(seq[2 * i + 1], 15) if 2 * i + 1 < l else 0) for i in range(nb)]
+            q = np.array(packed + [int(x) for x in q[:l - nb]], dtype=np.int64)
+        if mq < filters[0] or l < filters[1]:
+            continue
+        tot = mat = 0
+        for i in range(3, l - 3):
+            if p + i >= len(ref_seq):
+                break
+            if q[i] >= 30:
+                tot += 1
+                mat += int(ref_seq[p + i] == seq[i])
+        if not (tot > 0 and tot - mat <= filters[2]):
+            continue
+        for i in range(3, l - 3):
+            if q[i] >= 30 and (p + i) in rows:
+                col = b"ACGT".find(bytes([seq[i]]))
+                if col >= 0:
+                    out[rows[p + i], col] += 1
+    return out

@@ -230,17 +230,13 @@ def bambam_reads(rng, sites, genome, p_cov, mean_extra):
     return reads
 
 
-def bambam_fixture():
-    """SURVEY.md 8(f) N3: the bam/bam front-end.  The reference's own parse_onebambam (coal.cpp:1799-2069) and bam_parser
-    (include/vcf/htslib.cpp) run on synthetic reads served by oracle/hts_stubs.c; the fixture keeps the rows, the pileup the
-    reference's bam_parser holds at every row (the pre-decoded arrays colate_set_pileup takes) and parse_onebambam's outputs,
-    with and without masks."""
-    seed = 23
+def bambam_inputs(seed=23):
+    """The synthetic bam/bam dataset of the fixture, deterministically from its seed: rows, chromosome lengths, the reference
+    genome per chromosome (uint8 ACGT) and the aligned reads of the target and the reference sample (tests regenerate them to
+    drive the device pileup with the very reads the reference's bam_parser saw)."""
     rng = np.random.default_rng(seed)
     lens = [65_000_000, 31_000_000]
     sites = synth.make_sites(seed, [1300, 700], lens, weird=0.1)
-    d = tempfile.mkdtemp()
-    synth.write_dataset(d, sites, {})
     genome = []
     for c, L in enumerate(lens):
         g = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, L)].copy()
@@ -250,13 +246,29 @@ def bambam_fixture():
             if a in b"ACGT" and rng.random() < 0.85:
                 g[int(sites.pos[m]) - 1] = a
         genome.append(g)
+    reads_t = bambam_reads(rng, sites, genome, 0.85, 1.2)
+    reads_r = bambam_reads(rng, sites, genome, 0.9, 2.0)
+    return sites, lens, genome, reads_t, reads_r
+
+
+def bambam_fixture():
+    """SURVEY.md 8(f) N3: the bam/bam front-end.  The reference's own parse_onebambam (coal.cpp:1799-2069) and bam_parser
+    (include/vcf/htslib.cpp) run on synthetic reads served by oracle/hts_stubs.c; the fixture keeps the rows, the pileup the
+    reference's bam_parser holds at every row (the pre-decoded arrays colate_set_pileup takes) and parse_onebambam's outputs,
+    with and without masks."""
+    seed = 23
+    sites, lens, genome, reads_t, reads_r = bambam_inputs(seed)
+    d = tempfile.mkdtemp()
+    synth.write_dataset(d, sites, {})
+    for c, L in enumerate(lens):
+        g = genome[c]
         with open(os.path.join(d, f"g_chr{sites.chr_names[c]}.fa"), "wb") as f:
             f.write(b">ref\n")
             for i in range(0, L, 1 << 20):
                 f.write(g[i:i + (1 << 20)].tobytes() + b"\n")
     bam_names = ["chr" + sites.chr_names[0], sites.chr_names[1]]      # bam_parser accepts "<name>" and "chr<name>" (htslib.cpp:388)
-    po.write_fake_bam(os.path.join(d, "t.bam"), bam_names, bambam_reads(rng, sites, genome, 0.85, 1.2))
-    po.write_fake_bam(os.path.join(d, "r.bam"), bam_names, bambam_reads(rng, sites, genome, 0.9, 2.0))
+    po.write_fake_bam(os.path.join(d, "t.bam"), bam_names, reads_t)
+    po.write_fake_bam(os.path.join(d, "r.bam"), bam_names, reads_r)
     masks = {"tm": [synth.make_mask(seed * 10 + c, int(L) if c else int(L) // 2, 0.25) for c, L in enumerate(lens)],
              "rm": [synth.make_mask(seed * 20 + c, int(L), 0.15) for c, L in enumerate(lens)]}
     for mname, per_chr in masks.items():

@@ -509,3 +509,50 @@ def test_pileup_front_end_refuses_rows_the_reference_overruns_on(handle):
         assert e.value.code == -2
     finally:
         handle.set_option("front_end", 0)
+
+
+def test_device_pileup_from_reads_matches_reference_bam_parser(handle):
+    """The decoder's counting loop on the device (colate_pileup_*): the synthetic reads of the bam/bam fixture, regenerated from
+    their seed, piled up at the .mut rows == the pileup the REFERENCE's bam_parser held at every row (fixture t_counts / r_counts:
+    length / mapping-quality / base-quality / mismatch filters, the three bases at either end of a read that never count), and
+    stage i on those slots == the reference's parse_onebambam."""
+    import os, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here); sys.path.insert(0, os.path.join(here, "golden"))
+    import make_golden
+    from helpers import load
+    z = load("stage1_bambam.npz")
+    sites, lens, genome, reads_t, reads_r = make_golden.bambam_inputs(int(z["seed"]))
+    assert np.array_equal(sites.pos, z["pos"])
+
+    def soa(reads):
+        per = []
+        for c in range(len(lens)):
+            rd = [r for r in reads if r[0] == c]
+            ln = np.array([len(r[4]) for r in rd], np.int32)
+            off = np.concatenate([[0], np.cumsum(ln)[:-1]]).astype(np.int64) if len(rd) else np.zeros(0, np.int64)
+            per.append((np.array([r[1] for r in rd], np.int32), np.array([r[2] for r in rd], np.uint8), ln, off,
+                        np.frombuffer(b"".join(r[4] for r in rd), np.uint8), np.concatenate([r[5] for r in rd]) if rd else np.zeros(0, np.uint8)))
+        return per
+
+    handle.set_sites(sites.site_off, sites.pos, sites.age_begin, sites.age_end, sites.meta())
+    handle.set_mask(0, None); handle.set_mask(1, None)
+    handle.set_option("front_end", 1)
+    try:
+        got_t = handle.pileup_from_reads(0, soa(reads_t), genome, fetch=True)
+        got_r = handle.pileup_from_reads(1, soa(reads_r), genome, fetch=True)
+        assert np.array_equal(got_t, z["t_counts"]) and np.array_equal(got_r, z["r_counts"])
+        assert (got_t.sum(1) > 0).sum() > 1000
+        s1 = handle.stage1(api.mt_seed(int(z["seed"])))
+        assert s1.num_blocks == int(z["ref_plain_num_blocks"])
+        for v, k in enumerate(("shared", "notshared", "shared_emp", "notshared_emp")):
+            assert np.array_equal(s1.block_stats[:, v], z[f"ref_plain_{k}"]), k
+        # unsorted reads are refused like the reference does (htslib.cpp:411-414)
+        bad = soa(reads_t)
+        p = bad[0][0].copy(); p[5], p[6] = p[6] + 1000, p[5]
+        bad[0] = (p,) + bad[0][1:]
+        with pytest.raises(api._lib.ColateError) as e:
+            handle.pileup_from_reads(0, bad, genome)
+        assert e.value.code == -6
+    finally:
+        handle.set_option("front_end", 0)

@@ -91,6 +91,21 @@ def test_bambam_cli_chain_matches_reference_cli(R, tmp_path):
     assert open(tmp_path / "o.coal").read() == open(os.path.join(GOLDEN, f"bambam_R{R}.coal")).read()
 
 
+def test_pileup_restatement_matches_reference_bam_parser():
+    """The oracle's pileup of decoded reads (incl. the reference's first-read quirk) against the counts the reference's own
+    bam_parser held at every row (fixture, make_golden.py bambam); the reads are regenerated from the fixture's seed."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    import make_golden
+    z = load("stage1_bambam.npz")
+    sites, lens, genome, reads_t, reads_r = make_golden.bambam_inputs(int(z["seed"]))
+    for reads, key in ((reads_t, "t_counts"), (reads_r, "r_counts")):
+        for c in range(len(lens)):
+            lo, hi = int(sites.site_off[c]), int(sites.site_off[c + 1])
+            got = po.pileup_from_reads(sites.pos[lo:hi], [(r[1], r[2], r[4], r[5]) for r in reads if r[0] == c], genome[c])
+            assert same(got, z[key][lo:hi]), (key, c)
+
+
 def test_estep_matches_reference_coal_EM():
     z = load("estep_ref.npz")
     ab = po.age_bins()
