@@ -549,6 +549,7 @@ def main():
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "traffic_source": tr.get("source") if tr else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": stage_bytes, "launch_ms": st_ms,
+                "stage1_pair_site_evals_per_s": rows / (st_ms * 1e-3),
                 "formula": "(40 B x rows + 800 B x used rows) / sum of the stage's kernel times",
                 "per_phase_ms": {k: t_stage[k] for k in ("join_ms", "flags_ms", "rng_ms", "compact_ms", "sample_ms", "replay_ms")},
                 "k_sample": {"algorithmic_bytes_per_launch": sample_bytes, "launch_ms": t_stage["sample_ms"], "achieved": sample_gbs,

@@ -1,6 +1,7 @@
 """Whole CLI runs at BASELINE sizes on the GPU box: generated files -> `colate_b200/bin/Colate` vs the unmodified
 reference CLI (`oracle/_ref/Colate`) on the same files: wall clocks and byte-for-byte comparison of the .coal files.
-usage: cli_wall.py [rows] [n_chr] [num_bootstraps] [--skip-reference]"""
+usage: cli_wall.py [rows] [n_chr] [num_bootstraps] [--skip-reference] [--devices=0,1,...]
+--devices: also run the CLI with chromosomes and replicates dealt to several GPUs and compare its .coal byte for byte."""
 import os, subprocess, sys, tempfile, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from colate_b200 import synth
@@ -35,6 +36,13 @@ t_gpu = min(run(ours, d + "/gpu") for _ in range(2))
 t_gpu_host = run(ours, d + "/gpu_hostparse", ["--host_parse"])
 print("colate_b200 CLI: %.2f s wall (GPU ingest); %.2f s with --host_parse" % (t_gpu, t_gpu_host), flush=True)
 assert open(d + "/gpu.coal").read() == open(d + "/gpu_hostparse.coal").read()
+for a in sys.argv:
+    if a.startswith("--devices="):
+        run(ours, d + "/multi_warm", ["--devices", a.split("=", 1)[1]])
+        t_multi = min(run(ours, d + "/multi", ["--devices", a.split("=", 1)[1]]) for _ in range(2))
+        same = open(d + "/gpu.coal").read() == open(d + "/multi.coal").read()
+        os.environ["COLATE_TIMING"] = "1"; r = subprocess.run([ours] + common + ["--devices", a.split("=", 1)[1], "-o", d + "/tm"], capture_output=True, text=True); print("".join(l + "\n" for l in r.stderr.splitlines() if l.startswith("[timing]"))); del os.environ["COLATE_TIMING"]
+        print("colate_b200 CLI --devices %s: %.2f s wall; .coal byte-identical to one device: %s" % (a.split("=", 1)[1], t_multi, same), flush=True)
 if not skip_ref:
     ref = os.path.join(ROOT, "oracle", "_ref", "Colate")
     t_ref = run(ref, d + "/ref")
