@@ -53,6 +53,7 @@ SIGNATURES = {
     "colate_set_sites": (C.c_int, [VP, C.c_int, VP, VP, VP, VP, VP, C.c_int]),
     "colate_set_genome": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, C.c_int]),
     "colate_set_pileup": (C.c_int, [VP, C.c_int, VP, C.c_int]),
+    "colate_set_row_counts": (C.c_int, [VP, C.c_int, VP, VP, C.c_int]),
     "colate_pileup_begin": (C.c_int, [VP, C.c_int]),
     "colate_pileup_reads": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, VP, C.c_int64, C.c_int, C.c_int, C.c_int]),
     "colate_pileup_end": (C.c_int, [VP, C.c_int, VP]),

@@ -192,6 +192,13 @@ class Handle:
         assert counts.shape == (self.n_site, 4)
         check(lib().colate_set_pileup(self._h, slot, ptr(counts), 0))
 
+    def set_row_counts(self, slot, aaf, daf):
+        """N3, bcf front-ends: per-row counts of the row's ancestral / derived allele as a bcf decoder resolved them (zeros: row
+        not usable for this genome).  Use with set_option("front_end", 1)."""
+        a = np.ascontiguousarray(aaf, dtype=np.int32); d = np.ascontiguousarray(daf, dtype=np.int32)
+        assert a.shape == (self.n_site,) and d.shape == (self.n_site,)
+        check(lib().colate_set_row_counts(self._h, slot, ptr(a), ptr(d), 0))
+
     def pileup_from_reads(self, slot, per_chr_reads, ref_genomes, filters=(20, 30, 10), fetch=False):
         """N3, the decoder's counting loop on the device: per_chr_reads[c] = (pos int32[n], mapq uint8[n], len int32[n],
         seq_off int64[n], seq uint8[bytes], qual uint8[bytes]) of contig c (or None), ref_genomes[c] = uint8 sequence of the

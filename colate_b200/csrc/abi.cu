@@ -246,6 +246,34 @@ int colate_set_pileup(colate_handle* h, int slot, const int32_t* counts, int loc
   return 0;
 }
 
+int colate_set_row_counts(colate_handle* h, int slot, const int32_t* aaf, const int32_t* daf, int location)
+{
+  if (!h || slot < 0 || slot >= COLATE_MAX_GENOMES || !aaf || !daf) return fail(COLATE_ERR_ARG, "colate_set_row_counts: bad arguments");
+  if (!h->sites_set) return fail(COLATE_ERR_STATE, "colate_set_row_counts: call colate_set_sites first");
+  CK(cudaSetDevice(h->device));
+  GenomeDev& g = h->genomes[slot];
+  const size_t n = (size_t)h->n_site;
+  CK(g.pile.ensure(n * 16 + 16));
+  const int32_t *da = aaf, *dd = daf;
+  if (!location) {
+    CK(h->d_tmp.ensure(n * 8 + 16));
+    CK(cudaMemcpyAsync(h->d_tmp.p, aaf, n * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_tmp.as<int32_t>() + n, daf, n * 4, cudaMemcpyHostToDevice, h->stream));
+    da = h->d_tmp.as<int32_t>();
+    dd = da + n;
+  }
+  int rc = run_pack_row_counts(h, slot, da, dd);
+  if (rc) return rc;
+  g.n_rec = 0;
+  g.pileup = true;
+  g.set = true;
+  g.joined = false;
+  h->flags_done = false;
+  CK(cudaMemsetAsync(h->order_flag.as<int>() + 1 + slot, 0, 4, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 // ---- pileup from decoded reads (the counting loop of bam_parser, include/vcf/htslib.cpp:60-168, on the device) -----------------
 int colate_pileup_begin(colate_handle* h, int slot)
 {

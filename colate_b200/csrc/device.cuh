@@ -136,6 +136,7 @@ int run_compact(colate_handle* h);
 int run_sample_rows(colate_handle* h, const uint32_t* stream_local, int64_t row0, int64_t n_rows);
 int run_put_count_row(colate_handle* h, int64_t row, const uint8_t* cnt192_host);
 int run_replay(colate_handle* h);
+int run_pack_row_counts(colate_handle* h, int slot, const int32_t* aaf_dev, const int32_t* daf_dev);
 int run_pileup_reads(colate_handle* h, int slot, int chr, int64_t n_reads, const int32_t* pos, const uint8_t* mapq, const int32_t* len,
                      const int64_t* off, const uint8_t* seq, const uint8_t* qual, const uint8_t* ref, int64_t ref_len, int max_len,
                      int mapq_th, int len_th, int mismatch_th, uint8_t* pass_scratch);

@@ -171,6 +171,12 @@ __global__ void k_pileup_join(int64_t n_site, const uint32_t* __restrict__ meta,
   uint8_t fl = 0;
   if (mt & 1u) {
     const int4 c = counts[m];
+    if (c.w < 0) {                                 // colate_set_row_counts: (AAF, DAF) already resolved by a bcf decoder
+      a = c.x; d = c.y;
+      if (a > 0 || d > 0) fl = 3;
+      j_aaf[m] = a; j_daf[m] = d; j_prevbp[m] = 0x7fffffff; j_flag[m] = fl;
+      return;
+    }
     const int cc[4] = {c.x, c.y, c.z, c.w};
     const int reads = c.x + c.y + c.z + c.w;
     const int n_alleles = (c.x > 0) + (c.y > 0) + (c.z > 0) + (c.w > 0);
@@ -253,6 +259,12 @@ __global__ void k_pileup_rows(int64_t row0, int64_t n_rows, const int32_t* __res
     c.x += b == 'A'; c.y += b == 'C'; c.z += b == 'G'; c.w += b == 'T';
   }
   pile[row0 + m] = c;
+}
+
+__global__ void k_pack_row_counts(int64_t n_site, const int32_t* __restrict__ aaf, const int32_t* __restrict__ daf, int4* __restrict__ pile)
+{
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < n_site) pile[m] = make_int4(aaf[m], daf[m], 0, -1);       // .w = -1: "counts of the row's two alleles", not an A/C/G/T pileup
 }
 
 // ---- input order (COLATE_ERR_ORDER) ---------------------------------------------------------
@@ -1267,6 +1279,17 @@ int run_replay(colate_handle* h)
   }
   CK(cudaEventRecord(h->ev[5], s));
   CK(cudaGetLastError());
+  return 0;
+}
+
+int run_pack_row_counts(colate_handle* h, int slot, const int32_t* aaf_dev, const int32_t* daf_dev)
+{
+  GenomeDev& g = h->genomes[slot];
+  if (h->n_site > 0) {
+    k_pack_row_counts<<<grid_for(h->n_site, 256), 256, 0, h->stream>>>(h->n_site, aaf_dev, daf_dev, g.pile.as<int4>());
+    h->launches += 1;
+    CK(cudaGetLastError());
+  }
   return 0;
 }
 

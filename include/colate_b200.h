@@ -92,6 +92,12 @@ int colate_set_genome(colate_handle* h, int slot, int64_t n_rec, const int64_t* 
  * (coal.cpp:2005-2039) and the 1e3 normalisation of stage ii (coal.cpp:3453-3463). */
 int colate_set_pileup(colate_handle* h, int slot, const int32_t* counts, int location);
 
+/* The bcf front-ends' inputs, pre-decoded (parse_vcfvcf, coal.cpp:997-1137; parse_vcf, parse_bamvcf, parse_onebamvcf alike): per .mut
+ * row the counts of the row's ancestral / derived allele among the genome's haplotypes as the decoder resolved them -- allele match and
+ * flip, biallelic test, "alt not reported" records, the --ref_genome fall-back; AAF = N - DAF -- zeros where the row is not usable for
+ * this genome.  Like colate_set_pileup without the A/C/G/T detour (rows with the allele codes 0 / 1 fit too).  Use with front_end = 1. */
+int colate_set_row_counts(colate_handle* h, int slot, const int32_t* aaf, const int32_t* daf, int location);
+
 /* The decoder's counting loop on the device: the pileup of genome `slot` from DECODED alignment records instead of finished counts.
  * Replaces bam_parser::count_alleles_for_read / read_to_pos (include/vcf/htslib.cpp:60-168, 426-437) for the positions the bam
  * front-ends look up; what stays with the caller is BAM decompression (sam_read1).  Per contig of the --chr list, its reads in file

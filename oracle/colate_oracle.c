@@ -350,7 +350,9 @@ int oracle_stage1(int n_chr, const int64_t* site_off /*[n_chr+1]*/,
  * ---------------------------------------------------------------------------------- */
 static int acgt_index(uint8_t c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
 
-int oracle_stage1_pileup(int n_chr, const int64_t* site_off, const int32_t* pos, const float* age_begin, const float* age_end,
+/* width 4: [n_site][4] A, C, G, T pileups (the bam front-ends); width 2: [n_site][2] = (AAF, DAF) of the row's two alleles as a bcf
+ * decoder resolved them (parse_vcfvcf, coal.cpp:997-1137: N_ref = AAF + DAF, AAF_target = N_target - DAF_target) */
+int oracle_stage1_counts(int width, int n_chr, const int64_t* site_off, const int32_t* pos, const float* age_begin, const float* age_end,
                          const uint32_t* meta,
                          const char* const* tmask_seq, const int64_t* tmask_len,
                          const char* const* rmask_seq, const int64_t* rmask_len,
@@ -386,16 +388,21 @@ int oracle_stage1_pileup(int n_chr, const int64_t* site_off, const int32_t* pos,
       int DAF_ref = 0, AAF_ref = 0, DAF_target = 0, AAF_target = 0;
       const int ia = acgt_index(anc), id = acgt_index(der);
       for (int side = 0; side < 2 && use; side++) {      /* coal.cpp:1884-1929 (reference), then 1930-1931, then 1935-1980 (target) */
-        const int32_t* c = (side == 0 ? r_counts : t_counts) + 4 * m;
-        int num_reads = 0, num_alleles = 0;
-        for (int i = 0; i < 4; i++) { num_reads += c[i]; num_alleles += (c[i] > 0); }
+        const int32_t* c = (side == 0 ? r_counts : t_counts) + width * m;
         int A = 0, D = 0;
-        if (num_reads > 0) {
-          if (ia >= 0) A = c[ia];
-          if (id >= 0) D = c[id];
-          if (A > 0 || D > 0) { if (!(num_alleles <= 2)) use = 0; }
-          else use = 0;
-        } else use = 0;
+        if (width == 2) {
+          A = c[0]; D = c[1];
+          if (!(A > 0 || D > 0)) use = 0;
+        } else {
+          int num_reads = 0, num_alleles = 0;
+          for (int i = 0; i < 4; i++) { num_reads += c[i]; num_alleles += (c[i] > 0); }
+          if (num_reads > 0) {
+            if (ia >= 0) A = c[ia];
+            if (id >= 0) D = c[id];
+            if (A > 0 || D > 0) { if (!(num_alleles <= 2)) use = 0; }
+            else use = 0;
+          } else use = 0;
+        }
         if (side == 0) { AAF_ref = A; DAF_ref = D; if (DAF_ref == 0) use = 0; }
         else { AAF_target = A; DAF_target = D; }
       }
@@ -445,6 +452,18 @@ int oracle_stage1_pileup(int n_chr, const int64_t* site_off, const int32_t* pos,
     if (num_blocks > MAX_BLOCKS) return -3;
   }
   return num_blocks;
+}
+
+int oracle_stage1_pileup(int n_chr, const int64_t* site_off, const int32_t* pos, const float* age_begin, const float* age_end,
+                         const uint32_t* meta,
+                         const char* const* tmask_seq, const int64_t* tmask_len,
+                         const char* const* rmask_seq, const int64_t* rmask_len,
+                         const int32_t* t_counts, const int32_t* r_counts, oracle_mt* rng,
+                         double* shared, double* notshared, double* shared_emp, double* notshared_emp,
+                         int64_t* n_shared, int64_t* n_notshared, int64_t* n_emp, int64_t* n_used, int64_t* n_used_total)
+{
+  return oracle_stage1_counts(4, n_chr, site_off, pos, age_begin, age_end, meta, tmask_seq, tmask_len, rmask_seq, rmask_len, t_counts, r_counts, rng,
+                              shared, notshared, shared_emp, notshared_emp, n_shared, n_notshared, n_emp, n_used, n_used_total);
 }
 
 /* ------------------------------------------------------------------------------------

@@ -69,6 +69,7 @@ def lib():
         L.oracle_stage1_pileup.argtypes = [C.c_int, _i64, _i32, _f32, _f32, _u32,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32, _i32, C.POINTER(MT),
                                            _f64, _f64, _f64, _f64, _i64, _i64, _i64, _i64, C.POINTER(C.c_int64)]
+        L.oracle_stage1_counts.argtypes = [C.c_int] + list(L.oracle_stage1_pileup.argtypes)
         L.oracle_stage2_norm.argtypes = [C.c_int, _f64]
         L.oracle_draw_block_weights.argtypes = [C.POINTER(MT), C.c_int, C.c_int, _i32]
         L.oracle_stage2.argtypes = [C.c_int, C.c_int, _i32, _f64, _f64, _f64, _f64, C.c_double, _f64, _f64]
@@ -163,7 +164,8 @@ def stage1_pileup(sites, t_counts, r_counts, seed=1, tmask=None, rmask=None, rng
 
     tb, tp, tl = mk(tmask)
     rb, rp, rl = mk(rmask)
-    nb = L.oracle_stage1_pileup(n_chr, np.ascontiguousarray(sites.site_off, dtype=np.int64), np.ascontiguousarray(sites.pos),
+    width = np.asarray(t_counts).shape[1]         # 4: A, C, G, T pileups; 2: (AAF, DAF) per row from a bcf decoder
+    nb = L.oracle_stage1_counts(width, n_chr, np.ascontiguousarray(sites.site_off, dtype=np.int64), np.ascontiguousarray(sites.pos),
                                 np.ascontiguousarray(sites.age_begin), np.ascontiguousarray(sites.age_end), np.ascontiguousarray(sites.meta()),
                                 C.cast(tp, C.c_void_p) if tp else None, C.cast(tl, C.c_void_p) if tl else None,
                                 C.cast(rp, C.c_void_p) if rp else None, C.cast(rl, C.c_void_p) if rl else None,
@@ -457,3 +459,146 @@ def pileup_from_reads(pos_rows, reads, ref_seq, filters=(20, 30, 10)):
                 if col >= 0:
                     out[rows[p + i], col] += 1
     return out
+
+
+# ---- the bcf/bcf front-end on synthetic genotype records (oracle/hts_stubs.c serves the reference's vcf_parser) ----
+def write_fake_bcf(path, n_samples, ploidy, records):
+    """records: iterable of (pos0, [allele bytes, ...], [allele index per haplotype] of length n_samples * ploidy), ascending pos0."""
+    import struct
+    with open(path, "wb") as f:
+        f.write(b"FBCF" + struct.pack("<ii", n_samples, ploidy))
+        for pos0, alleles, gt in records:
+            f.write(struct.pack("<ii", pos0, len(alleles)))
+            for a in alleles:
+                f.write(struct.pack("<i", len(a)) + bytes(a))
+            f.write(struct.pack("<%di" % (n_samples * ploidy), *[int(x) for x in gt]))
+
+
+def ref_parse_vcfvcf(dirname, chr_names, prefix, target_bcf, ref_bcf, seed=1, ref_genome=None, tmask=None, rmask=None):
+    """The reference's parse_vcfvcf (coal.cpp:907-1228) on <dirname>/<prefix>_chr<c>.mut and the fake BCFs <target_bcf>_chr<c>.bcf /
+    <ref_bcf>_chr<c>.bcf (+ <ref_genome>_chr<c>.fa, masks)."""
+    L = ref()
+    L.ref_parse_vcfvcf.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_char_p),
+                                   C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int, _f64, _f64, _f64, _f64, _f64, _u32]
+    n = len(chr_names)
+    arr = lambda xs: (C.c_char_p * n)(*[x.encode() for x in xs])
+    per = lambda stem, ext: arr([os.path.join(dirname, f"{stem}_chr{c}.{ext}") for c in chr_names])
+    z = lambda: np.zeros((MAX_BLOCKS, NBINS))
+    S, N, SE, NE = z(), z(), z(), z()
+    rest = np.zeros(2)
+    mt = np.zeros(625, dtype=np.uint32)
+    nb = L.ref_parse_vcfvcf(n, per(prefix, "mut"), per(target_bcf, "bcf"), per(ref_bcf, "bcf"), per(tmask, "fa") if tmask else None,
+                            per(rmask, "fa") if rmask else None, per(ref_genome, "fa") if ref_genome else None, seed, S, N, SE, NE, rest, mt)
+    return {"num_blocks": nb, "shared": S[:nb].copy(), "notshared": N[:nb].copy(), "shared_emp": SE[:nb].copy(),
+            "notshared_emp": NE[:nb].copy(), "emp_rest": rest, "mt": mt}
+
+
+def decode_vcfvcf(pos_rows, anc_rows, der_rows, usable_rows, recs_target, recs_ref, n_target, n_ref, refg_at_rows=None):
+    """The DECODER half of parse_vcfvcf (coal.cpp:997-1137) for ONE chromosome, restated: what the two genotype streams say about
+    every .mut row, as the per-row counts colate_set_row_counts / stage1_pileup (width 2) take: (AAF, DAF) of the row's two
+    alleles per genome, AAF = N - DAF; zeros = the row is not usable for this genome.
+      pos_rows / anc_rows / der_rows: the rows (1-based positions, allele codes); usable_rows: the row passes the filter in front
+      of the lookups (coal.cpp:966-995: meta bit 0 and ancestral != derived) -- the cursors only move for such rows;
+      recs_*: [(pos0, [alleles], [gt])] ascending; n_*: haplotypes per record (samples x ploidy); refg_at_rows: base of the
+      reference genome at every row (--ref_genome given) or None.
+    Masks are not the decoder's business (they gate `use` before the lookups; the cursors lose nothing by not moving)."""
+    n = len(pos_rows)
+    tc = np.zeros((n, 2), np.int32)
+    rc = np.zeros((n, 2), np.int32)
+
+    class Cur:                       # vcf_parser + the bp_* variable of parse_vcfvcf: read_snp() keeps the last record at end of file
+        def __init__(self, recs):
+            self.recs, self.k, self.rec = recs, 0, None
+            self.read()
+            self.bp = self.rec[0] + 1 if self.rec else 0       # coal.cpp:953-954 / 958-959
+
+        def read(self):
+            if self.k < len(self.recs):
+                self.rec = self.recs[self.k]; self.k += 1
+                return 0
+            return -1
+
+        def seek(self, bp_mut):      # coal.cpp:1001-1006
+            if self.bp < bp_mut:
+                while self.read() == 0:
+                    self.bp = self.rec[0] + 1
+                    if self.bp >= bp_mut:
+                        break
+
+    cr, ct = Cur(recs_ref), Cur(recs_target)
+    for m in range(n):
+        if not usable_rows[m]:
+            continue
+        bp, anc, der = int(pos_rows[m]), bytes([anc_rows[m]]), bytes([der_rows[m]])
+        use = True
+        cr.seek(bp)
+        daf_r = 0
+        if cr.bp == bp and cr.rec is not None:
+            al = cr.rec[1]
+            a0, a1 = bytes(al[0]), bytes(al[1]) if len(al) > 1 else None      # (the synthetic reference records always carry two alleles)
+            if (a0 == anc and a1 == der) or (a0 == der and a1 == anc):
+                flip = a0 == der and a1 == anc
+                gt = cr.rec[2]
+                daf_r = int(sum(gt))
+                if all(g <= 1 for g in gt):
+                    if flip:
+                        daf_r = n_ref - daf_r
+                else:
+                    use = False
+            else:
+                use = False
+        else:
+            if refg_at_rows is not None:
+                if der == bytes([refg_at_rows[m]]):
+                    daf_r = n_ref
+                else:
+                    use = False
+            else:
+                use = False
+        if daf_r == 0:
+            use = False
+        if not use:
+            continue
+        ct.seek(bp)
+        daf_t = 0
+        if ct.bp == bp and ct.rec is not None:
+            al = ct.rec[1]
+            a0 = bytes(al[0]) if len(al) > 0 else b""
+            a1 = bytes(al[1]) if len(al) > 1 else b""
+            accept = fixed = tflip = False
+            if a0 != b"" and a1 == b"":
+                if a0 == anc or a0 == der:
+                    accept = True
+                if a0 == der:
+                    tflip = True
+                fixed = True
+            elif (a0 == der and a1 == anc) or (a0 == anc and a1 == der):
+                accept = True
+                tflip = a0 == der and a1 == anc
+            if accept:
+                gt = ct.rec[2]
+                daf_t = int(sum(gt))
+                if not all(g <= 1 for g in gt):
+                    accept = False
+                if fixed and daf_t != 0:
+                    accept = False
+            if not accept:
+                use = False
+            if tflip:
+                daf_t = n_target - daf_t
+        else:
+            if refg_at_rows is not None:
+                b = bytes([refg_at_rows[m]])
+                if der == b:
+                    daf_t = n_target
+                elif anc == b:
+                    daf_t = 0
+                else:
+                    use = False
+            else:
+                use = False
+        if not use:
+            continue
+        rc[m] = (n_ref - daf_r, daf_r)
+        tc[m] = (n_target - daf_t, daf_t)
+    return tc, rc

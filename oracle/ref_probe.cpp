@@ -254,6 +254,59 @@ int ref_parse_onebambam(const char* params, int n_chr, const char** chr_names, c
   return nb;
 }
 
+// parse_vcfvcf (coal.cpp:907-1228) as mut() calls it (coal.cpp:3200): per-chromosome target / reference "bcf" files (fake BCFs of
+// oracle/hts_stubs.c), optional masks and reference genome.  Outputs as ref_parse_tmptmp.
+int ref_parse_vcfvcf(int n_chr, const char** mut_files, const char** target_bcf, const char** ref_bcf, const char** target_masks,
+                     const char** ref_masks, const char** ref_genomes, int seed,
+                     double* out_shared, double* out_notshared, double* out_shared_emp, double* out_notshared_emp,
+                     double* emp_rest, unsigned int* mt_out /*[625]*/)
+{
+  double C = 10;
+  int num_age_bins = ((int)(log(1e8) * C)) + 1;
+  int num_bases_per_block = 30e6;
+  int num_blocks = 500;
+  std::vector<std::vector<double>> a(num_blocks), b(num_blocks), c(num_blocks), d(num_blocks);
+  for (int i = 0; i < num_blocks; i++) {
+    a[i].assign(num_age_bins, 0.0);
+    b[i].assign(num_age_bins, 0.0);
+    c[i].assign(num_age_bins * num_age_bins, 0.0);
+    d[i].assign(num_age_bins * num_age_bins, 0.0);
+  }
+  std::vector<std::string> filename_mut, ft, fr, tmask, rmask, refg;
+  for (int i = 0; i < n_chr; i++) {
+    filename_mut.push_back(mut_files[i]);
+    ft.push_back(target_bcf[i]);
+    fr.push_back(ref_bcf[i]);
+    if (target_masks) tmask.push_back(target_masks[i]);
+    if (ref_masks) rmask.push_back(ref_masks[i]);
+    if (ref_genomes) refg.push_back(ref_genomes[i]);
+  }
+  std::mt19937 rng;
+  rng.seed(seed);
+  int nb = parse_vcfvcf(filename_mut, ft, fr, tmask, rmask, refg, 0.0, 0.0, C, rng, num_bases_per_block, a, b, c, d);
+  emp_rest[0] = emp_rest[1] = 0.0;
+  for (int i = 0; i < nb && i < 500; i++) {
+    for (int k = 0; k < num_age_bins; k++) {
+      out_shared[i * num_age_bins + k] = a[i][k];
+      out_notshared[i * num_age_bins + k] = b[i][k];
+      out_shared_emp[i * num_age_bins + k] = c[i][k];
+      out_notshared_emp[i * num_age_bins + k] = d[i][k];
+    }
+    for (int k = num_age_bins; k < num_age_bins * num_age_bins; k++) {
+      emp_rest[0] += c[i][k];
+      emp_rest[1] += d[i][k];
+    }
+  }
+  std::stringstream ss;
+  ss << rng;
+  for (int i = 0; i < 625; i++) {
+    unsigned long v;
+    ss >> v;
+    mt_out[i] = (unsigned int)v;
+  }
+  return nb;
+}
+
 // The pileup bam_parser holds at given positions: for every 1-based position bp[i] of chromosome `contig` (ascending),
 // read_to_pos(bp - 1) as coal.cpp:1885-1888 does, then counts[i][0..3] = count_alleles[(bp-1) % num_entries] if that ring
 // entry belongs to bp - 1, else zeros (and covered[i] = 0).  This is the "pre-decoded array" the N3 entry point takes.

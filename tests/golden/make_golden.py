@@ -315,10 +315,106 @@ def bambam_fixture():
     shutil.rmtree(d, ignore_errors=True)
 
 
+def vcf_records(rng, sites, c, n_hap, p_rec, ref_side):
+    """Synthetic genotype records of one sample set on chromosome c: at most row positions (alleles as the row has them, flipped,
+    a third allele in the record or in a genotype, unrelated alleles, multi-letter alleles; for the target also records that
+    report a single allele) and at positions that are not rows."""
+    lo, hi = int(sites.site_off[c]), int(sites.site_off[c + 1])
+    recs = {}
+    for m in range(lo, hi):
+        if rng.random() >= p_rec:
+            continue
+        anc, der = bytes([int(sites.anc[m])]), bytes([int(sites.der[m])])
+        third = bytes([[b for b in b"ACGT" if bytes([b]) not in (anc, der)][0]])
+        u = rng.random()
+        if u < 0.55:
+            al = [anc, der]
+        elif u < 0.75:
+            al = [der, anc]
+        elif u < 0.80:
+            al = [anc, third]
+        elif u < 0.85:
+            al = [anc, der, third]
+        elif u < 0.90:
+            al = [anc + b"T", der]
+        elif u < 0.95 and not ref_side:
+            al = [anc] if rng.random() < 0.5 else [der]
+        else:
+            al = [third, anc]
+        if len(al) == 1:
+            gt = [0] * n_hap if rng.random() < 0.8 else [1] + [0] * (n_hap - 1)      # "alt not reported": only sensible if all-reference
+        else:
+            gt = list((rng.random(n_hap) < 0.4).astype(int))
+            if len(al) == 3 and rng.random() < 0.6:
+                gt[int(rng.integers(0, n_hap))] = 2
+        recs[int(sites.pos[m]) - 1] = (al, gt)
+    L = int(sites.chrom_len[c])
+    for p in rng.integers(0, L, size=max(4, (hi - lo) // 5)):            # records between the rows
+        recs.setdefault(int(p), ([b"A", b"G"], list((rng.random(n_hap) < 0.5).astype(int))))
+    return [(p, recs[p][0], recs[p][1]) for p in sorted(recs)]
+
+
+def vcfvcf_fixture():
+    """SURVEY.md 8(f) N3, the bcf/bcf front-end: the reference's own parse_vcfvcf (coal.cpp:907-1228) and vcf_parser run on
+    synthetic genotype records served by oracle/hts_stubs.c, without and with --ref_genome (+ masks).  The fixture keeps the
+    rows, the records, the reference genome's base at every row and parse_vcfvcf's outputs."""
+    seed = 29
+    rng = np.random.default_rng(seed)
+    lens = [65_000_000, 31_000_000]
+    sites = synth.make_sites(seed, [1500, 900], lens, weird=0.08)
+    d = tempfile.mkdtemp()
+    synth.write_dataset(d, sites, {})
+    n_t, pl_t, n_r, pl_r = 1, 2, 3, 2
+    out = dict(chr_names=np.array(sites.chr_names), site_off=sites.site_off, pos=sites.pos, age_begin=sites.age_begin,
+               age_end=sites.age_end, flipped=sites.flipped, n_branch=sites.n_branch, anc=sites.anc, der=sites.der, odd=sites.odd,
+               chrom_len=np.array(lens, dtype=np.int64), seed=seed, n_hap_target=n_t * pl_t, n_hap_ref=n_r * pl_r)
+    refg_rows = np.zeros(sites.n, np.uint8)
+    for c, nm in enumerate(sites.chr_names):
+        for tag, ns, pl, p_rec in (("t", n_t, pl_t, 0.75), ("r", n_r, pl_r, 0.85)):
+            recs = vcf_records(rng, sites, c, ns * pl, p_rec, tag == "r")
+            po.write_fake_bcf(os.path.join(d, f"{tag}_chr{nm}.bcf"), ns, pl, recs)
+            out[f"{tag}{c}_pos"] = np.array([r[0] for r in recs], np.int32)
+            out[f"{tag}{c}_nal"] = np.array([len(r[1]) for r in recs], np.int32)
+            out[f"{tag}{c}_al"] = np.array([[a.ljust(3, b"\0") for a in (r[1] + [b""] * 3)[:3]] for r in recs], dtype="S3")
+            out[f"{tag}{c}_gt"] = np.array([r[2] for r in recs], np.int8)
+        # reference genome: derived / ancestral / another base at the rows
+        L = lens[c]
+        g = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, L)].copy()
+        lo, hi = int(sites.site_off[c]), int(sites.site_off[c + 1])
+        for m in range(lo, hi):
+            u = rng.random()
+            if u < 0.45 and int(sites.der[m]) in b"ACGT":
+                g[int(sites.pos[m]) - 1] = int(sites.der[m])
+            elif u < 0.85 and int(sites.anc[m]) in b"ACGT":
+                g[int(sites.pos[m]) - 1] = int(sites.anc[m])
+        refg_rows[lo:hi] = g[sites.pos[lo:hi] - 1]
+        with open(os.path.join(d, f"g_chr{nm}.fa"), "wb") as f:
+            f.write(b">ref\n")
+            for i in range(0, L, 1 << 20):
+                f.write(g[i:i + (1 << 20)].tobytes() + b"\n")
+    out["refg_at_rows"] = refg_rows
+    masks = {"tm": [synth.make_mask(seed * 10 + c, int(L) if c else int(L) // 2, 0.25) for c, L in enumerate(lens)],
+             "rm": [synth.make_mask(seed * 20 + c, int(L), 0.15) for c, L in enumerate(lens)]}
+    for mname, per_chr in masks.items():
+        for c, nm in enumerate(sites.chr_names):
+            synth.write_mask(os.path.join(d, f"{mname}_chr{nm}.fa"), per_chr[c])
+    for tag, kw in (("plain", {}), ("refg", dict(ref_genome="g")), ("refg_masked", dict(ref_genome="g", tmask="tm", rmask="rm"))):
+        r = po.ref_parse_vcfvcf(d, sites.chr_names, "syn", "t", "r", seed=seed, **kw)
+        assert r["emp_rest"].sum() == 0
+        for k in ("num_blocks", "shared", "notshared", "shared_emp", "notshared_emp", "mt"):
+            out[f"ref_{tag}_{k}"] = np.asarray(r[k])
+        print("stage1_vcfvcf.npz", tag, "blocks", r["num_blocks"], "sum shared", r["shared"].sum(), "notshared", r["notshared"].sum())
+    np.savez_compressed(os.path.join(OUT, "stage1_vcfvcf.npz"), **out)
+    import shutil
+    shutil.rmtree(d, ignore_errors=True)
+
+
 def main():
     assert po.ref_available() and po.ref_cli(), "build oracle/_ref first (make -C oracle ref)"
     if len(sys.argv) > 1 and sys.argv[1] == "bambam":
         return bambam_fixture()
+    if len(sys.argv) > 1 and sys.argv[1] == "vcfvcf":
+        return vcfvcf_fixture()
     if len(sys.argv) > 1 and sys.argv[1] == "reject":
         return reject_fixture()
     if len(sys.argv) > 1 and sys.argv[1] == "n2":
@@ -328,6 +424,7 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "maketmp":
         return maketmp_fixture()
     bambam_fixture()
+    vcfvcf_fixture()
     maketmp_fixture()
     mut_reader_fixture()
     n2_fixture()

@@ -38,3 +38,24 @@ def bambam_masks(z):
     tm = [synth.make_mask(seed * 10 + c, L if c else L // 2, 0.25) for c, L in enumerate(lens)]
     rm = [synth.make_mask(seed * 20 + c, L, 0.15) for c, L in enumerate(lens)]
     return tm, rm
+
+
+def vcfvcf_counts(z, with_refg):
+    """Per-row (AAF, DAF) of the vcfvcf fixture for both genomes: the decoder half of parse_vcfvcf (oracle/pyoracle.py:
+    decode_vcfvcf) on the fixture's genotype records."""
+    from oracle import pyoracle as po
+    sites = sites_from(z)
+    meta = sites.meta()
+    tc = np.zeros((sites.n, 2), np.int32)
+    rc = np.zeros((sites.n, 2), np.int32)
+    for c in range(len(sites.chr_names)):
+        lo, hi = int(sites.site_off[c]), int(sites.site_off[c + 1])
+        recs = {}
+        for tag in ("t", "r"):
+            al = z[f"{tag}{c}_al"]
+            recs[tag] = [(int(p), [bytes(a) for a in al[i][:int(n)]], [int(g) for g in gt])
+                         for i, (p, n, gt) in enumerate(zip(z[f"{tag}{c}_pos"], z[f"{tag}{c}_nal"], z[f"{tag}{c}_gt"]))]
+        usable = ((meta[lo:hi] & 1) != 0) & (sites.anc[lo:hi] != sites.der[lo:hi])          # coal.cpp:966-995
+        tc[lo:hi], rc[lo:hi] = po.decode_vcfvcf(sites.pos[lo:hi], sites.anc[lo:hi], sites.der[lo:hi], usable, recs["t"], recs["r"],
+                                                 int(z["n_hap_target"]), int(z["n_hap_ref"]), z["refg_at_rows"][lo:hi] if with_refg else None)
+    return sites, tc, rc

@@ -556,3 +556,32 @@ def test_device_pileup_from_reads_matches_reference_bam_parser(handle):
         assert e.value.code == -6
     finally:
         handle.set_option("front_end", 0)
+
+
+@pytest.mark.parametrize("tag", ["plain", "refg", "refg_masked"])
+def test_row_counts_front_end_matches_reference_parse_vcfvcf(handle, tag):
+    """colate_set_row_counts + front_end = 1 (the bcf front-ends on pre-decoded per-row (AAF, DAF)) against the REFERENCE's
+    parse_vcfvcf outputs (coal.cpp:907-1228 run on synthetic genotype records, tests/golden/stage1_vcfvcf.npz): histograms and
+    generator state bit for bit; the decoder half is the oracle's restatement (pyoracle.decode_vcfvcf)."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import bambam_masks, load, vcfvcf_counts
+    z = load("stage1_vcfvcf.npz")
+    sites, tc, rc = vcfvcf_counts(z, tag != "plain")
+    tm, rm = bambam_masks(z) if tag == "refg_masked" else (None, None)
+    handle.set_option("front_end", 1)
+    try:
+        handle.set_sites(sites.site_off, sites.pos, sites.age_begin, sites.age_end, sites.meta())
+        handle.set_row_counts(0, tc[:, 0], tc[:, 1])
+        handle.set_row_counts(1, rc[:, 0], rc[:, 1])
+        handle.set_mask(0, None if tm is None else api.mask_bits_from_seq(tm, sites.site_off, sites.pos))
+        handle.set_mask(1, None if rm is None else api.mask_bits_from_seq(rm, sites.site_off, sites.pos))
+        s1 = handle.stage1(api.mt_seed(int(z["seed"])))
+        assert s1.num_blocks == int(z[f"ref_{tag}_num_blocks"])
+        for v, k in enumerate(("shared", "notshared", "shared_emp", "notshared_emp")):
+            assert np.array_equal(s1.block_stats[:, v], z[f"ref_{tag}_{k}"]), k
+        o = po.stage1_pileup(sites, tc, rc, seed=int(z["seed"]), tmask=tm, rmask=rm)
+        _compare_stage1(o, s1)
+    finally:
+        handle.set_option("front_end", 0)
+        handle.set_mask(0, None); handle.set_mask(1, None)

@@ -8,7 +8,7 @@ import pytest
 
 from colate_b200 import synth
 from oracle import pyoracle as po
-from helpers import GOLDEN, bambam_masks, dataset_from, load, same, sites_from
+from helpers import GOLDEN, bambam_masks, dataset_from, load, same, sites_from, vcfvcf_counts
 
 
 def test_random_streams_match_libstdcxx():
@@ -89,6 +89,23 @@ def test_bambam_cli_chain_matches_reference_cli(R, tmp_path):
     rates = np.stack([po.em_run(ep, np.full(len(ep), 1 / 20000.0), counts[r])[0] for r in range(R)])
     po.write_coal(str(tmp_path / "o.coal"), ep, rates)
     assert open(tmp_path / "o.coal").read() == open(os.path.join(GOLDEN, f"bambam_R{R}.coal")).read()
+
+
+@pytest.mark.parametrize("tag", ["plain", "refg", "refg_masked"])
+def test_vcfvcf_front_end_matches_reference_parse_vcfvcf(tag):
+    """SURVEY.md 8(f) N3, the bcf/bcf front-end: the decoder half of parse_vcfvcf restated (cursor over the genotype records, allele
+    match / flip, biallelic test, "alt not reported" records, --ref_genome fall-back: coal.cpp:997-1137) feeding the SAME count-based
+    stage i as the bam front-end (weights (N_target - DAF_target) * DAF_ref / (N_ref * 100), coal.cpp:1164-1197) against the
+    reference's own parse_vcfvcf run on synthetic genotype records (fixture: make_golden.py vcfvcf)."""
+    z = load("stage1_vcfvcf.npz")
+    sites, tc, rc = vcfvcf_counts(z, tag != "plain")
+    tm, rm = bambam_masks(z) if tag == "refg_masked" else (None, None)
+    o = po.stage1_pileup(sites, tc, rc, seed=int(z["seed"]), tmask=tm, rmask=rm)
+    assert o["num_blocks"] == int(z[f"ref_{tag}_num_blocks"])
+    assert o["n_used_total"] > 100
+    for k in ("shared", "notshared", "shared_emp", "notshared_emp"):
+        assert same(o[k], z[f"ref_{tag}_{k}"]), k
+    assert same(o["rng"].words(), z[f"ref_{tag}_mt"])
 
 
 def test_pileup_restatement_matches_reference_bam_parser():
