@@ -18,12 +18,13 @@ def build(specs):
     shutil.rmtree(OUT, ignore_errors=True)
     os.makedirs(OUT, exist_ok=True)
     subprocess.run(["make", "-s", "-j8", "-C", CSRC, "all"], check=True)
-    others = [os.path.join(CSRC, o) for o in ("abi.o", "kernels_em.o", "kernels_ingest.o", "host_mt.o", "host_misc.o")]
+    em = any("EMC_" in sp or "EM_" in sp for sp in specs)          # EM variants rebuild kernels_em.cu too
+    others = [os.path.join(CSRC, o) for o in ("abi.o", "kernels_ingest.o", "host_mt.o", "host_misc.o") + (() if em else ("kernels_em.o",))]
     for spec in specs:
         name, _, flags = spec.partition(":")
         defs = [f for f in flags.split(",") if f]
         objs = []
-        for src in ("kernels_sites", "kernels_mt"):
+        for src in ("kernels_sites", "kernels_mt") + (("kernels_em",) if em else ()):
             objs.append(os.path.join(OUT, f"{src}_{name}.o"))
             subprocess.run(["nvcc", *ARCH, "-O3", "-lineinfo", "-std=c++17", "--fmad=false", "-Xcompiler", "-fPIC,-O2", *defs, "-c",
                             os.path.join(CSRC, src + ".cu"), "-o", objs[-1]], check=True)
