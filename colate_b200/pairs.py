@@ -119,7 +119,9 @@ class SharedMutText:
         self.offs = np.concatenate([[0], np.cumsum([(n + 255) & ~255 for n in sizes])]).astype(np.int64)   # 256-byte aligned starts
         total = int(self.offs[-1])
         self.per = ((total + world - 1) // world + 255) & ~255
-        host = torch.zeros(self.per, dtype=torch.uint8).pin_memory()      # this rank's slice of the concatenation
+        host = torch.zeros(self.per, dtype=torch.uint8)                   # this rank's slice of the concatenation
+        if torch.cuda.is_available():
+            host = host.pin_memory()
         lo, hi = rank * self.per, (rank + 1) * self.per
         hv = host.numpy()
         for c, t in enumerate(texts):
@@ -137,6 +139,7 @@ class SharedMutText:
         mine.copy_(self.host, non_blocking=True)
         if self.world > 1:
             dist.all_gather_into_tensor(self.dev, mine)
-        self.torch.cuda.current_stream().synchronize()          # the handle parses on its own stream
+        if self.dev.is_cuda:
+            self.torch.cuda.current_stream().synchronize()      # the handle parses on its own stream
         base = self.dev.data_ptr()
         return [(base + int(self.offs[c]), self.sizes[c]) for c in range(len(self.sizes))]

@@ -243,3 +243,37 @@ def test_all_pairs_sharded_world2(built):
         assert np.array_equal(ll.view(np.int64), one["ll"].view(np.int64))
         assert np.array_equal(iters, one["iters"]) and np.array_equal(nb, one["num_blocks"]) and np.array_equal(nu, one["n_used"])
         assert np.array_equal(counts, one["counts"])
+
+
+def _shared_text_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from colate_b200 import pairs
+    rng = np.random.default_rng(3)                     # the SAME texts on every rank (the cohort's .mut files)
+    texts = [rng.integers(32, 127, size=n, dtype=np.uint8) for n in (1000, 1, 777, 4096, 255, 256, 257)]
+    st = pairs.SharedMutText(texts, torch.device("cpu"), world, rank)
+    ptr_sizes = st.exchange()
+    got = [st.dev.numpy()[p - st.dev.data_ptr():p - st.dev.data_ptr() + n].copy() for p, n in ptr_sizes]
+    q.put((rank, all(np.array_equal(a, b) for a, b in zip(got, texts)), st.h2d_bytes, [int(p - st.dev.data_ptr()) % 256 for p, _ in ptr_sizes]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_shared_mut_text_exchange(built, world):
+    """pairs.SharedMutText: every rank contributes its 1 / world slice of the concatenated .mut texts, the all-gather leaves the
+    whole text on every rank, every chromosome's text at a 256-byte aligned offset (gloo stand-in for the NVLink all-gather)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shared_text_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs: p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs: p.join(timeout=60)
+    assert sorted(r[0] for r in res) == list(range(world))
+    for rank, ok, h2d, align in res:
+        assert ok, rank
+        assert all(a == 0 for a in align)
+        assert h2d * world >= 1000 + 1 + 777 + 4096 + 255 + 256 + 257 and h2d % 256 == 0
