@@ -74,7 +74,7 @@ struct colate_handle {
   // stage-1 scratch
   bool flags_done = false, sampled = false;
   int tgt_slot = -1, ref_slot = -1;
-  colate::DevBuf candR, candT, use, word_rank, scan_tmp;
+  colate::DevBuf candR, candT, use, word_rank, scan_tmp, row_of_rank;
   colate::DevBuf chr_used, chr_blocks, chr_block_base, misc;  // misc: small device scalars
   colate::DevBuf u_hdr, u_eb2, u_ews, u_ewn, u_blk, u_cnt;   // compacted used rows, per-row sample counts
   colate::DevBuf blk_rank_start, out_f, out_n, deep_rows;

@@ -76,9 +76,13 @@ __device__ __forceinline__ void join_tile_of(int n_chr, const int32_t* __restric
   m1 = min(m0 + JOIN_TILE, site_off[c + 1]);
 }
 
+// everything k_join needs to know about a tile, found once per tile by k_join_bounds (k_join read it through a chain of four
+// dependent lookups per thread before: tile -> chromosome -> rows -> record range -> window)
+struct __align__(16) JoinTileInfo { int64_t m0, first, w0, w1; int32_t n_rows, pad_[3]; };
+
 __global__ void k_join_bounds(int n_tiles, int n_chr, const int32_t* __restrict__ tile_start, const int64_t* __restrict__ site_off,
                               const int32_t* __restrict__ pos, const int64_t* __restrict__ chr_first, const int64_t* __restrict__ chr_end,
-                              const int32_t* __restrict__ bp, int64_t* __restrict__ tile_rlo)
+                              const int32_t* __restrict__ bp, JoinTileInfo* __restrict__ tile_info)
 {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tiles) return;
@@ -93,30 +97,28 @@ __global__ void k_join_bounds(int n_tiles, int n_chr, const int32_t* __restrict_
       if (lo2 < hi2) { const int64_t mid = (lo2 + hi2) >> 1; if (bp[mid] <= q) lo2 = mid + 1; else hi2 = mid; }
     }
   }
-  tile_rlo[2 * t] = lo;
-  tile_rlo[2 * t + 1] = lo2;
+  JoinTileInfo ti;
+  ti.m0 = m0; ti.first = first; ti.w0 = lo; ti.w1 = lo2; ti.n_rows = (int32_t)(m1 - m0); ti.pad_[0] = ti.pad_[1] = ti.pad_[2] = 0;
+  tile_info[t] = ti;
 }
 
 __global__ void __launch_bounds__(JOIN_TILE)
-k_join(int n_chr, const int32_t* __restrict__ tile_start, const int64_t* __restrict__ site_off,
+k_join(const JoinTileInfo* __restrict__ tile_info,
        const int32_t* __restrict__ pos, const uint32_t* __restrict__ meta,
-       const int64_t* __restrict__ chr_first, const int64_t* __restrict__ chr_end, const int64_t* __restrict__ tile_rlo,
        const int32_t* __restrict__ bp, const int32_t* __restrict__ aaf,
        const int32_t* __restrict__ daf, const uint16_t* __restrict__ alleles,
        int32_t* __restrict__ j_aaf, int32_t* __restrict__ j_daf,
        int32_t* __restrict__ j_prevbp, uint8_t* __restrict__ j_flag)
 {
   __shared__ int32_t sbp[JOIN_CAP + 1];     // bp[w0 - 1 .. w1): the window and the record in front of it
-  const int t = blockIdx.x;
-  int c; int64_t m0, m1;
-  join_tile_of(n_chr, tile_start, t, site_off, c, m0, m1);
-  const int64_t first = chr_first[c], end = chr_end[c];
+  const JoinTileInfo ti = tile_info[blockIdx.x];
+  const int64_t m0 = ti.m0, m1 = ti.m0 + ti.n_rows, first = ti.first;
   const int64_t m = m0 + threadIdx.x;
   if (first < 0) {                           // the reader never reaches this chromosome in this file
     if (m < m1) { j_aaf[m] = 0; j_daf[m] = 0; j_prevbp[m] = -1; j_flag[m] = 0; }
     return;
   }
-  const int64_t w0 = tile_rlo[2 * t], w1 = tile_rlo[2 * t + 1];      // records with a position inside [first, last position of the tile]
+  const int64_t w0 = ti.w0, w1 = ti.w1;      // records with a position inside [first, last position of the tile]
   // (the row's own word and position are requested before the window is staged: their latency runs under the staging loads)
   const uint32_t mt = m < m1 ? meta[m] : 0u;
   const int32_t p = m < m1 ? pos[m] : 0;
@@ -398,7 +400,7 @@ __global__ void k_scan_sums(uint32_t* __restrict__ sums, int n, uint32_t* __rest
 }
 
 __global__ void k_word_rank(const uint32_t* __restrict__ words, int64_t n_words, const uint32_t* __restrict__ block_off,
-                            const uint32_t* __restrict__ total, uint32_t* __restrict__ word_rank)
+                            const uint32_t* __restrict__ total, uint32_t* __restrict__ word_rank, int32_t* __restrict__ row_of_rank)
 {
   __shared__ uint32_t s[SCAN_THREADS / 32];
   int64_t base = ((int64_t)blockIdx.x * SCAN_THREADS + threadIdx.x) * SCAN_ITEMS;
@@ -413,7 +415,13 @@ __global__ void k_word_rank(const uint32_t* __restrict__ words, int64_t n_words,
   uint32_t woff = 0;
   for (int i = 0; i < wid; i++) woff += s[i];
   uint32_t excl = block_off[blockIdx.x] + woff + incl - v;
-  for (int i = 0; i < SCAN_ITEMS; i++) if (base + i < n_words) word_rank[base + i] = excl + loc[i];
+  for (int i = 0; i < SCAN_ITEMS; i++)
+    if (base + i < n_words) {
+      word_rank[base + i] = excl + loc[i];
+      // the inverse map for k_compact (thread = used row): which site has rank r (it searched word_rank for it before: 18 dependent loads)
+      uint32_t w = words[base + i], r = excl + loc[i];
+      while (w) { const int b = __ffs(w) - 1; w &= w - 1; row_of_rank[r++] = (int32_t)(((base + i) << 5) + b); }
+    }
   if (blockIdx.x == 0 && threadIdx.x == 0) word_rank[n_words] = *total;
 }
 
@@ -460,7 +468,7 @@ __global__ void k_chr(int n_chr, const int64_t* __restrict__ site_off, const int
 //   u_blk[r] = genomic block (index local to this handle)
 __global__ void k_compact(int64_t n_site, int n_chr, const int64_t* __restrict__ site_off, const int32_t* __restrict__ pos,
                           const float* __restrict__ ab, const float* __restrict__ ae,
-                          const uint32_t* __restrict__ use, const uint32_t* __restrict__ word_rank,
+                          const int32_t* __restrict__ row_of_rank,
                           const int32_t* __restrict__ chr_block_base,
                           const int32_t* __restrict__ t_aaf, const int32_t* __restrict__ t_daf,
                           const int32_t* __restrict__ r_aaf, const int32_t* __restrict__ r_daf,
@@ -470,16 +478,10 @@ __global__ void k_compact(int64_t n_site, int n_chr, const int64_t* __restrict__
                           const uint32_t* __restrict__ meta, int64_t* __restrict__ deep_rows, int64_t deep_cap, int raw_weights)
 {
   // thread = used row (rank r): one row in eight is used, so a thread per site would leave the warps of the
-  // division-heavy part below nearly empty.  Site of rank r: the last bitmap word whose exclusive rank is <= r
-  // (empty words in front of it share its rank, the words behind it start above r), then the bit inside it.
+  // division-heavy part below nearly empty.  Site of rank r: row_of_rank, written by the rank scan (k_word_rank).
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= misc[0]) return;
-  int64_t lo = 0, hi = (n_site + 31) >> 5;            // invariant: word_rank[lo] <= r, word_rank[hi] > r (hi = one past the end)
-  while (hi - lo > 1) {
-    const int64_t mid = (lo + hi) >> 1;
-    if ((int64_t)word_rank[mid] <= r) lo = mid; else hi = mid;
-  }
-  const int64_t m = (lo << 5) + __fns(use[lo], 0, (int)(r - word_rank[lo]) + 1);
+  const int64_t m = row_of_rank[r];
   int c = chr_of(site_off, n_chr, m);
   // pseudo-genotype, coal.cpp:2236-2242: float /= double, then round half away
   const int32_t dt = t_daf[m], at = t_aaf[m];
@@ -1127,12 +1129,11 @@ int run_join(colate_handle* h, int slot)
       h->tiles_valid = true;
     }
     const int n_tiles = h->h_tile_start[h->n_chr];
-    CK(h->tile_rlo.ensure((size_t)(n_tiles + 1) * 16));
+    CK(h->tile_rlo.ensure((size_t)(n_tiles + 1) * sizeof(JoinTileInfo)));
     k_join_bounds<<<grid_for(n_tiles, 256), 256, 0, h->stream>>>(n_tiles, h->n_chr, h->tile_start.as<int32_t>(), h->site_off.as<int64_t>(),
                                                                 h->pos.as<int32_t>(), g.chr_first.as<int64_t>(), g.chr_end.as<int64_t>(),
-                                                                g.bp.as<int32_t>(), h->tile_rlo.as<int64_t>());
-    k_join<<<n_tiles, JOIN_TILE, 0, h->stream>>>(h->n_chr, h->tile_start.as<int32_t>(), h->site_off.as<int64_t>(), h->pos.as<int32_t>(),
-                                                 h->meta.as<uint32_t>(), g.chr_first.as<int64_t>(), g.chr_end.as<int64_t>(), h->tile_rlo.as<int64_t>(),
+                                                                g.bp.as<int32_t>(), h->tile_rlo.as<JoinTileInfo>());
+    k_join<<<n_tiles, JOIN_TILE, 0, h->stream>>>(h->tile_rlo.as<JoinTileInfo>(), h->pos.as<int32_t>(), h->meta.as<uint32_t>(),
                                                  g.bp.as<int32_t>(), g.aaf.as<int32_t>(), g.daf.as<int32_t>(), g.alleles.as<uint16_t>(),
                                                  g.j_aaf.as<int32_t>(), g.j_daf.as<int32_t>(), g.j_prevbp.as<int32_t>(), g.j_flag.as<uint8_t>());
     CK(cudaGetLastError());
@@ -1174,6 +1175,7 @@ int run_flags(colate_handle* h, int tslot, int rslot)
   GenomeDev& R = h->genomes[rslot];
   CK(h->candR.ensure(nw * 4 + 8)); CK(h->candT.ensure(nw * 4 + 8)); CK(h->use.ensure(nw * 4 + 8));
   CK(h->word_rank.ensure((nw + 1) * 4 + 8));
+  CK(h->row_of_rank.ensure((size_t)n * 4 + 8));
   const int nsb = std::max(1, grid_for(nw, SCAN_THREADS * SCAN_ITEMS));
   CK(h->scan_tmp.ensure((size_t)nsb * 4 + 16));
   CK(h->chr_used.ensure(h->n_chr * 8 + 8)); CK(h->chr_blocks.ensure(h->n_chr * 4 + 8)); CK(h->chr_block_base.ensure(h->n_chr * 4 + 8));
@@ -1192,7 +1194,8 @@ int run_flags(colate_handle* h, int tslot, int rslot)
                                      h->use.as<uint32_t>(), h->meta.as<uint32_t>(), h->misc.as<int64_t>());
     k_popc_blocksum<<<nsb, SCAN_THREADS, 0, s>>>(h->use.as<uint32_t>(), nw, h->scan_tmp.as<uint32_t>());
     k_scan_sums<<<1, 32, 0, s>>>(h->scan_tmp.as<uint32_t>(), nsb, total);
-    k_word_rank<<<nsb, SCAN_THREADS, 0, s>>>(h->use.as<uint32_t>(), nw, h->scan_tmp.as<uint32_t>(), total, h->word_rank.as<uint32_t>());
+    k_word_rank<<<nsb, SCAN_THREADS, 0, s>>>(h->use.as<uint32_t>(), nw, h->scan_tmp.as<uint32_t>(), total, h->word_rank.as<uint32_t>(),
+                                             h->row_of_rank.as<int32_t>());
     h->launches += 5;
   } else {
     CK(cudaMemsetAsync(h->word_rank.p, 0, 8, s));
@@ -1223,7 +1226,7 @@ int run_compact(colate_handle* h)
   CK(cudaEventRecord(h->ev[2], s));
   if (n > 0) {
     k_compact<<<grid_for(std::max<int64_t>(nu, 1), 256), 256, 0, s>>>(n, h->n_chr, h->site_off.as<int64_t>(), h->pos.as<int32_t>(), h->ab.as<float>(),
-                                               h->ae.as<float>(), h->use.as<uint32_t>(), h->word_rank.as<uint32_t>(),
+                                               h->ae.as<float>(), h->row_of_rank.as<int32_t>(),
                                                h->chr_block_base.as<int32_t>(), T.j_aaf.as<int32_t>(), T.j_daf.as<int32_t>(),
                                                R.j_aaf.as<int32_t>(), R.j_daf.as<int32_t>(), h->thr10.as<double>(),
                                                h->u_hdr.as<double4>(), h->u_eb2.as<uint8_t>(), h->u_ews.as<double>(),
