@@ -71,9 +71,21 @@ k_jump(uint32_t* __restrict__ windows, const uint16_t* __restrict__ taps0, int n
   for (int i = tid; i < MT_N; i += blockDim.x) X[i] = windows[(size_t)src * MT_N + i];
   for (int i = tid; i < n_taps; i += blockDim.x) T[i] = taps[i];
   __syncthreads();
-  for (int base = MT_N; base < XLEN; base += 227) {
-    int n = base + tid;
-    if (tid < 227 && n < XLEN) X[n] = mt_mix_dev(X[n - 624], X[n - 623], X[n - 227]);
+  // base sequence: 624 words per block barrier (a thread's second and third word of a round depend on its own first and second
+  // one; the last word of a round needs the round's first word, which its thread recomputes: see k_gen)
+  for (int base = MT_N; base < XLEN; base += MT_N) {
+    if (tid < 227) {
+      const int n0 = base + tid;
+      uint32_t v0 = 0, v1 = 0;
+      if (n0 < XLEN) { v0 = mt_mix_dev(X[n0 - 624], X[n0 - 623], X[n0 - 227]); X[n0] = v0; }
+      const int n1 = n0 + 227;
+      if (n1 < XLEN) { v1 = mt_mix_dev(X[n1 - 624], X[n1 - 623], v0); X[n1] = v1; }
+      const int n2 = n0 + 454;
+      if (tid < 170 && n2 < XLEN) {
+        const uint32_t b = (tid == 169) ? mt_mix_dev(X[base - 624], X[base - 623], X[base - 227]) : X[n2 - 623];
+        X[n2] = mt_mix_dev(X[n2 - 624], b, v1);
+      }
+    }
     __syncthreads();
   }
   const int nout = MT_N / P;          // outputs of this CTA
@@ -155,28 +167,27 @@ k_gen(const uint32_t* __restrict__ windows, int64_t chunk_words, int64_t total_w
       if (pw[j] >= 200) { pw[j] -= 200; prow[j]++; }
     }
   };
-  // one round = the next 624 words in three dependent steps; `rem` masks the stores of the chunk's last round
+  // one round = the next 624 words; `rem` masks the stores of the chunk's last round.  Thread tid makes words tid, tid + 227 and
+  // tid + 454: the second needs the first and the third the second (x[n] = f(x[n-624], x[n-623], x[n-227])), i.e. the thread's
+  // own values, and everything else comes from the previous round's window -- except word 623, whose x[n-623] is the new word 0:
+  // its thread recomputes that one word.  So a round needs ONE block barrier (before the windows swap), not one per step.
   auto round = [&](int64_t o, int rem) {
     uint32_t* out = stream + o;
     if (tid < 227) {
-      uint32_t v = mt_mix_dev(cur[tid], cur[tid + 1], cur[tid + 397]);
-      nxt[tid] = v;
-      if (tid < rem) *place(0, out + tid) = mt_temper_dev(v);
-    }
-    __syncthreads();
-    if (tid < 227) {
-      int k = tid + 227;
-      uint32_t v = mt_mix_dev(cur[k], cur[k + 1], nxt[tid]);
-      nxt[k] = v;
-      if (k < rem) *place(1, out + k) = mt_temper_dev(v);
-    }
-    __syncthreads();
-    if (tid < 170) {
-      int k = tid + 454;
-      uint32_t b = (k == 623) ? nxt[0] : cur[k + 1];
-      uint32_t v = mt_mix_dev(cur[k], b, nxt[k - 227]);
-      nxt[k] = v;
-      if (k < rem) *place(2, out + k) = mt_temper_dev(v);
+      const uint32_t v0 = mt_mix_dev(cur[tid], cur[tid + 1], cur[tid + 397]);
+      nxt[tid] = v0;
+      if (tid < rem) *place(0, out + tid) = mt_temper_dev(v0);
+      const int k = tid + 227;
+      const uint32_t v1 = mt_mix_dev(cur[k], cur[k + 1], v0);
+      nxt[k] = v1;
+      if (k < rem) *place(1, out + k) = mt_temper_dev(v1);
+      if (tid < 170) {
+        const int k2 = tid + 454;
+        const uint32_t b = (k2 == 623) ? mt_mix_dev(cur[0], cur[1], cur[397]) : cur[k2 + 1];
+        const uint32_t v2 = mt_mix_dev(cur[k2], b, v1);
+        nxt[k2] = v2;
+        if (k2 < rem) *place(2, out + k2) = mt_temper_dev(v2);
+      }
     }
     __syncthreads();
     uint32_t* t = cur; cur = nxt; nxt = t;
