@@ -407,14 +407,25 @@ def main():
     # through stage i; its result is fetched before this pass's bootstrap overwrites the counts
     pend = {"s1": None, "out": None}
 
+    host_ms = {}                        # host wall clock per phase of the pipelined pass (what the host thread waits for)
+
+    def clk(name, t0):
+        t1 = time.perf_counter()
+        host_ms.setdefault(name, []).append((t1 - t0) * 1e3)
+        return t1
+
     def one_pass_pipelined():
+        t = time.perf_counter()
         s1 = h.stage1(api.mt_seed(SEED), fetch=False)
+        t = clk("stage1", t)
         if pend["s1"] is not None:
             rates, iters, ll = h.stage3_em_end()
             pend["out"] = (pend["s1"], rates, iters)
+        t = clk("wait_for_previous_em", t)
         w = api.draw_block_weights(s1.mt_state, 1, s1.num_blocks)
         h.stage2_bootstrap_dev(w, None, s1.num_blocks, 0.0)
         h.stage3_em_begin(1, ep, rates_init)
+        clk("stage2_and_em_launch", t)
         pend["s1"] = s1
         return pend["out"]
 
@@ -482,7 +493,9 @@ def main():
             return one_pass()
 
         def e2e_pass_pipelined():
+            t = time.perf_counter()
             upload_files()
+            clk("copy_parse_decode", t)
             return one_pass_pipelined()
 
         for _ in range(2):
@@ -494,7 +507,9 @@ def main():
         for _ in range(2):
             e2e_pass_pipelined()
         drain()
+        host_ms.clear()
         ms_e2e, (s1f, rates_f, iters_f) = timed(e2e_pass_pipelined, args.steps, finish=drain)
+        e2e_host_ms = {k: float(np.mean(v)) for k, v in host_ms.items()}
         ing = h.ingest_stats()
         if not (np.array_equal(rates_f, rates_soa) and s1f.n_used == s1.n_used):
             raise SystemExit("bench.py: the pass from the file bytes and the pass from the parsed arrays disagree")
@@ -506,7 +521,7 @@ def main():
                         "over NVLink (pairs.SharedMutText, one NCCL all_gather of %d bytes per pass); h2d_bytes_per_step is per rank" % (shared_text.per * world)
                         if shared_text is not None else ""),
                "mut_parse_kernel_ms": ing["kernel_ms"], "rows_reparsed_on_host": ing["host_fallback_rows"],
-               "rates_equal_device_resident_pass": True, "serial_ms_per_step": ms_e2e_serial,
+               "rates_equal_device_resident_pass": True, "serial_ms_per_step": ms_e2e_serial, "host_phase_ms": e2e_host_ms,
                "pipeline": "EM of pass i on the handle's EM stream (colate_stage3_em_begin/_end) under the copies, parse and stage i of pass i+1; "
                            "every pass's rates are read back inside the timed region"}
         # round 1's leg: parsed SoA in pinned host memory, uploads queued without a sync per call

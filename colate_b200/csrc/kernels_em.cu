@@ -37,15 +37,25 @@ k_bootstrap(int num_blocks, const int32_t* __restrict__ weights, const double* _
   while (bin_start < NBINS - 1 && age_bin[bin_start] <= age) bin_start++;      // coal.cpp:3394-3396
   for (int b = threadIdx.x; b < NBINS; b += blockDim.x) {
     double s = 0.0, n = 0.0, se = 0.0, ne = 0.0;
-    for (int j = 0; j < num_blocks; j++) {  // coal.cpp:3358-3390, block order kept
-      const double bw = (double)w[j];
-      if (bw > 0.0) {
+    // coal.cpp:3358-3390, block order kept.  Four blocks' values are requested before the first of them is added (the loop was a
+    // chain of L2 latencies: the loads sat behind the `weight > 0` test of their own block)
+    for (int j0 = 0; j0 < num_blocks; j0 += 4) {
+      double bw[4], v0[4], v1[4], v2[4], v3[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int j = min(j0 + u, num_blocks - 1);
         const double* v = blk + (size_t)j * 4 * NBINS + b;
-        s = __dadd_rn(s, __dmul_rn(bw, v[0]));
-        n = __dadd_rn(n, __dmul_rn(bw, v[NBINS]));
-        se = __dadd_rn(se, __dmul_rn(bw, v[2 * NBINS]));
-        ne = __dadd_rn(ne, __dmul_rn(bw, v[3 * NBINS]));
+        bw[u] = j0 + u < num_blocks ? (double)w[j] : 0.0;
+        v0[u] = v[0]; v1[u] = v[NBINS]; v2[u] = v[2 * NBINS]; v3[u] = v[3 * NBINS];
       }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (bw[u] > 0.0) {
+          s = __dadd_rn(s, __dmul_rn(bw[u], v0[u]));
+          n = __dadd_rn(n, __dmul_rn(bw[u], v1[u]));
+          se = __dadd_rn(se, __dmul_rn(bw[u], v2[u]));
+          ne = __dadd_rn(ne, __dmul_rn(bw[u], v3[u]));
+        }
     }
     S[b] = s; N[b] = n; SE[b] = se; NE[b] = ne;
     // coal.cpp:3406-3417: F[bin] = emp share of bin, bins from bin_start on
