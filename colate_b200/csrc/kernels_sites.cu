@@ -857,7 +857,12 @@ k_sample(const uint32_t* __restrict__ stream, int64_t n_used, const double4* __r
 
 constexpr int RP_SITES = 32;    // rows per replay stage
 constexpr int RP_STAGES = 4;
-constexpr int RP_ROWS = 8;      // rows collapsed into one exact update
+#ifndef RP_ROWS_
+#define RP_ROWS_ 16
+#endif
+constexpr int RP_ROWS = RP_ROWS_;   // rows collapsed into one exact update (8 or 16)
+constexpr int RP_CW = RP_ROWS / 4;  // count words of a run (4 rows per word)
+static_assert(RP_ROWS == 8 || RP_ROWS == 16 || RP_ROWS == 32, "run width");
 #ifndef RP_RANGES_
 #define RP_RANGES_ 6
 #endif
@@ -956,18 +961,23 @@ __device__ __forceinline__ void replay_body(int group, ReplayStage* st, uint64_t
     for (int run = 0; run < RP_SITES / RP_ROWS; run++) {
       const int g0 = run * RP_ROWS;
       // this bin's counts in the run's rows, one byte each (<= 100)
-      uint32_t cs_lo = cw8[2 * run], cs_hi = cw8[2 * run + 1];
+      uint32_t cs[RP_CW];
       const uint32_t lv = live >> g0;
-      cs_lo &= (((lv & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu;        // bit i -> byte i
-      cs_hi &= ((((lv >> 4) & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu;
-      if (WHICH == 1) overflow |= (bin == NBINS) & ((cs_lo | cs_hi) != 0);   // a sample in bin 185: out of bounds in the reference
-      tally += __dp4a(cs_lo, 0x01010101u, __dp4a(cs_hi, 0x01010101u, 0u));
-      const bool any = (cs_lo | cs_hi) != 0;
+      uint32_t cs_or = 0, cs_sum = 0;
+#pragma unroll
+      for (int k = 0; k < RP_CW; k++) {
+        cs[k] = cw8[RP_CW * run + k] & ((((lv >> (4 * k)) & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu;        // bit i -> byte i
+        cs_or |= cs[k];
+        cs_sum = __dp4a(cs[k], 0x01010101u, cs_sum);
+      }
+      if (WHICH == 1) overflow |= (bin == NBINS) & (cs_or != 0);   // a sample in bin 185: out of bounds in the reference
+      tally += cs_sum;
+      const bool any = cs_or != 0;
 #ifdef REPLAY_PROF
       pf_runs++;
       {  // rows of the run in which any lane of the warp has a count
         uint32_t nzb = 0;
-        for (int i = 0; i < 8; i++) nzb |= ((((i < 4 ? cs_lo : cs_hi) >> (8 * (i & 3))) & 0xff) != 0) << i;
+        for (int i = 0; i < RP_ROWS; i++) nzb |= (((cs[i >> 2] >> (8 * (i & 3))) & 0xff) != 0) << i;
         pf_rel += __popc(__reduce_or_sync(0xffffffffu, nzb));
       }
       if (!__any_sync(0xffffffffu, any)) { pf_skipped++; continue; }
@@ -979,17 +989,18 @@ __device__ __forceinline__ void replay_body(int group, ReplayStage* st, uint64_t
       const double hu = __hiloint2double((E - 53) << 20, 0);           // ulp(acc) / 2
       const int wmax_hi = (E - 1) << 20;                               // w must stay below 2^(E-1)
       bool bad = (E <= 54) | (E >= 0x7fe);
-      double t0s = 0.0, t1s = 0.0;                                     // exact sums: any order
+      double ts[4] = {0.0, 0.0, 0.0, 0.0};                             // exact sums: any order
 #pragma unroll
       for (int i = 0; i < RP_ROWS; i++) {
-        const int c = ((i < 4 ? cs_lo : cs_hi) >> (8 * (i & 3))) & 0xff;
+        const int c = (cs[i >> 2] >> (8 * (i & 3))) & 0xff;
         const double w = hp[4 * (g0 + i)];                             // (rows of other blocks carry count 0 here; the padding rows are zeroed)
         const double d = __dsub_rn(__dadd_rn(w, M), M);
         const double err = __dsub_rn(w, d);
         bad |= (c != 0) & ((fabs(err) == hu) | (__double2hiint(w) >= wmax_hi));
-        if (i & 1) t1s = __fma_rn((double)c, d, t1s); else t0s = __fma_rn((double)c, d, t0s);
+        ts[i & (RP_ROWS == 8 ? 1 : 3)] = __fma_rn((double)c, d, ts[i & (RP_ROWS == 8 ? 1 : 3)]);
       }
-      const double accn = __dadd_rn(acc, __dadd_rn(t0s, t1s));
+      const double accn = RP_ROWS == 8 ? __dadd_rn(acc, __dadd_rn(ts[0], ts[1]))
+                                       : __dadd_rn(acc, __dadd_rn(__dadd_rn(ts[0], ts[1]), __dadd_rn(ts[2], ts[3])));
       bad |= (__double2hiint(accn) >> 20) != E;
       bad &= any;
       if (__any_sync(0xffffffffu, bad)) {
@@ -1002,12 +1013,20 @@ __device__ __forceinline__ void replay_body(int group, ReplayStage* st, uint64_t
           // (a lane's count is zero in ~85 % of the rows: the serial path only pays for the one or two rows of the run that carry
           // a count.  A variant that located the crossing row from prefix sums of collapsed steps and committed the rows on
           // either side at once was measured SLOWER, 1.36 ms against 0.76: its passes touch all eight rows.)
+          // only the rows of the run in which THIS lane has a count (the counts of dead rows are masked to zero above)
+          uint32_t nzr = 0;
+#pragma unroll
+          for (int k = 0; k < RP_CW; k++) {
+            const uint32_t nz = (cs[k] | ((cs[k] & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;      // high bit of every non-zero byte
+            nzr |= ((nz * 0x00204081u) >> 28) << (4 * k);                                         // -> one bit per row
+          }
 #pragma unroll 1
-          for (int r = g0; r < g0 + RP_ROWS; r++) {
-            if (!((live >> r) & 1u)) continue;
+          while (nzr) {
+            const int r = g0 + __ffs(nzr) - 1;
+            nzr &= nzr - 1;
             const double w = hp[4 * r];
             const int c = st[slot].cnt[cslot][r];
-            if (c != 0 && (__double_as_longlong(w) << 1) != 0 && __double2hiint(w) >= 0)   // x + 0.0 == x
+            if ((__double_as_longlong(w) << 1) != 0 && __double2hiint(w) >= 0)   // x + 0.0 == x
               acc = replay_row(acc, w, c);
           }
         } else if (any) acc = accn;
