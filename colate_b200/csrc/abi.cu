@@ -127,8 +127,10 @@ int colate_create(int device, colate_handle** out)
   h->sm_count = prop.multiProcessorCount;
   cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
   for (auto& ev : h->ev) if (ce == cudaSuccess) ce = cudaEventCreate(&ev);
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->copy_done, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->side_done, cudaEventDisableTiming);
   if (ce != cudaSuccess) {   // nothing half-built leaves this function
     colate_destroy(h);
     return fail(COLATE_ERR_CUDA, std::string("colate_create: ") + cudaGetErrorString(ce));
@@ -143,6 +145,7 @@ void colate_destroy(colate_handle* h)
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  if (h->side_stream) cudaStreamSynchronize(h->side_stream);
   if (h->em_stream) { cudaStreamSynchronize(h->em_stream); cudaStreamDestroy(h->em_stream); }
   DevBuf* bufs[] = {&h->site_off, &h->pos, &h->ab, &h->ae, &h->meta, &h->candR, &h->candT, &h->use, &h->word_rank, &h->scan_tmp, &h->row_of_rank,
                     &h->chr_used, &h->chr_blocks, &h->chr_block_base, &h->misc, &h->u_hdr, &h->u_eb2, &h->u_ews, &h->u_ewn, &h->u_cnt,
@@ -159,6 +162,8 @@ void colate_destroy(colate_handle* h)
   for (auto& ev : h->ing_evs) cudaEventDestroy(ev);
   if (h->copy_done) cudaEventDestroy(h->copy_done);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->side_done) cudaEventDestroy(h->side_done);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }

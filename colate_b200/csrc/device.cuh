@@ -61,6 +61,8 @@ struct colate_handle {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // host -> device copies that run under the kernels of `stream`
   cudaEvent_t copy_done = nullptr;
+  cudaStream_t side_stream = nullptr;   // k_emp under the sampler (run_compact forks, run_replay joins)
+  cudaEvent_t side_done = nullptr;
   cudaEvent_t ev[8] = {};
   // sites
   bool sites_set = false;

@@ -856,22 +856,35 @@ k_sample(const uint32_t* __restrict__ stream, int64_t n_used, const double4* __r
 }
 
 constexpr int RP_SITES = 32;    // rows per replay stage
-constexpr int RP_STAGES = 4;
-#ifndef RP_ROWS_
-#define RP_ROWS_ 16
+#ifndef RP_STAGES_
+#define RP_STAGES_ 4
 #endif
-constexpr int RP_ROWS = RP_ROWS_;   // rows collapsed into one exact update (8 or 16)
+constexpr int RP_STAGES = RP_STAGES_;
+#ifndef RP_ROWS_
+#define RP_ROWS_ 32
+#endif
+constexpr int RP_ROWS = RP_ROWS_;   // rows collapsed into one exact update
 constexpr int RP_CW = RP_ROWS / 4;  // count words of a run (4 rows per word)
 static_assert(RP_ROWS == 8 || RP_ROWS == 16 || RP_ROWS == 32, "run width");
-#ifndef RP_RANGES_
-#define RP_RANGES_ 6
+#ifndef RP_Q_
+#define RP_Q_ 4
 #endif
-constexpr int RP_RANGES = RP_RANGES_;   // consumer warps per CTA: each one 32-bin range; 6 / RP_RANGES CTAs cover a block's 192 >= 185 bins
-constexpr int RP_GROUPS = 6 / RP_RANGES;
-static_assert(RP_GROUPS * RP_RANGES == 6, "bin ranges per CTA must divide 6");
-constexpr int RP_THREADS = (RP_RANGES + 1) * 32;   // + 1 producer warp
+constexpr int RP_Q = RP_Q_;               // lanes per bin: each takes RP_ROWS / RP_Q consecutive rows of a run
+constexpr int RP_BPW = 32 / RP_Q;         // bins per warp
+constexpr int RP_RPL = RP_ROWS / RP_Q;    // rows per lane and run
+constexpr int RP_CWL = RP_RPL / 4;        // count words per lane and run
+static_assert(RP_Q == 1 || RP_Q == 2 || RP_Q == 4 || RP_Q == 8, "lanes per bin");
+static_assert(RP_RPL >= 4 && RP_RPL % 4 == 0, "a lane takes whole count words");
+#ifndef RP_WARPS_
+#define RP_WARPS_ (192 / RP_BPW > 12 ? 12 : 192 / RP_BPW)
+#endif
+constexpr int RP_WARPS = RP_WARPS_;       // consumer warps per CTA
+constexpr int RP_BINS_CTA = RP_WARPS * RP_BPW;
+constexpr int RP_GROUPS = 192 / RP_BINS_CTA;   // CTAs that cover a block's 192 >= 185 bins
+static_assert(RP_GROUPS * RP_BINS_CTA == 192, "the bin ranges of the CTAs must tile 192 slots");
+constexpr int RP_THREADS = (RP_WARPS + 1) * 32;   // + 1 producer warp
 struct __align__(16) ReplayStage {
-  uint8_t cnt[RP_RANGES * 32][RP_SITES];   // this CTA's slots of one count tile of k_sample: [slot][row]
+  uint8_t cnt[RP_BINS_CTA][RP_SITES];   // this CTA's slots of one count tile of k_sample: [slot][row]
   double4 hdr[RP_SITES];
 };
 
@@ -888,7 +901,10 @@ __device__ __forceinline__ double replay_row(double acc, double w, int c)
   return ok ? t : exsum::add_repeated(acc, w, c);
 }
 
-// Exact replay: for every genomic block and both histograms, thread = age bin walks the block's
+// bit i of m -> byte i all ones
+__device__ __forceinline__ uint32_t rp_byte_mask(uint32_t m) { return (((m & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu; }
+
+// Exact replay: for every genomic block and both histograms, every age bin walks the block's
 // used rows IN ORDER and adds the row's weight once per sample that fell into the bin, with the
 // reference's rounding, so age_shared_count / age_notshared_count come out bit for bit as the
 // sequential loop of coal.cpp:2259-2295 leaves them.
@@ -896,9 +912,15 @@ __device__ __forceinline__ double replay_row(double acc, double w, int c)
 // While the sum stays inside one binade [2^E, 2^(E+1)) every rounded addition of w moves it by
 // d(w) = w rounded to a multiple of ulp(acc) -- a function of w and E only -- and all these moves
 // are exact, so a run of RP_ROWS rows collapses to acc += sum(count * d(w)): no serial dependency
-// per row.  A run that leaves the binade, meets a rounding tie or a weight too large for the
-// shortcut is redone row by row (replay_row / exact_sum.cuh).
-// blockIdx.y: 0 shared, 1 not shared.  hdr.z carries -0.0 for rows that add nothing to shared.
+// per row, and the sum may be taken in any order (every partial sum is a multiple of ulp(acc) below
+// 2^(E+1), hence exact; a partial sum at or above 2^(E+1) can only round to something that still
+// takes the total out of the binade, which is detected).  So a bin is given to RP_Q lanes, each with
+// RP_ROWS / RP_Q rows of the run, whose partial sums meet in a shuffle butterfly: the walk is a
+// latency chain per tile (the kernel ran at 16 % active warps with one lane per bin), and the chain
+// of a lane is RP_Q times shorter this way while RP_Q times as many warps share the SMs.  A run that
+// leaves the binade, meets a rounding tie or a weight too large for the shortcut is redone row by
+// row (replay_row / exact_sum.cuh) by all RP_Q lanes of the bin alike, over the rows with a count.
+// blockIdx.y: 2 * group + (0 shared, 1 not shared).  hdr.z carries -0.0 for rows that add nothing to shared.
 template <int WHICH>
 __device__ __forceinline__ void replay_body(int group, ReplayStage* st, uint64_t* full, uint64_t* empty,
                                             const int64_t* __restrict__ blk_rank_start, const uint8_t* __restrict__ cnt,
@@ -911,17 +933,17 @@ __device__ __forceinline__ void replay_body(int group, ReplayStage* st, uint64_t
   const int n_stage = r1 > r0 ? (int)((r1 - 1) / RP_SITES - t0 + 1) : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < RP_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], RP_RANGES); }
+    for (int i = 0; i < RP_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], RP_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (warp == RP_RANGES) {
+  if (warp == RP_WARPS) {
     if (lane == 0) {
       for (int it = 0; it < n_stage; it++) {
         const int slot = it % RP_STAGES;
         mbar_wait(&empty[slot], ((it / RP_STAGES) & 1) ^ 1);
         const int64_t t = t0 + it;
-        constexpr uint32_t CNT_BYTES = RP_RANGES * 32 * RP_SITES;     // the CTA's 32 * RP_RANGES slots: contiguous in the [slot][row] tile
+        constexpr uint32_t CNT_BYTES = RP_BINS_CTA * RP_SITES;        // the CTA's slots: contiguous in the [slot][row] tile
         mbar_expect_tx(&full[slot], (uint32_t)(CNT_BYTES + RP_SITES * 32));
         bulk_g2s(&st[slot].cnt[0][0], cnt + (size_t)t * TILE_BYTES + (size_t)group * CNT_BYTES, CNT_BYTES, &full[slot]);
         bulk_g2s(&st[slot].hdr[0], hdr_g + t * RP_SITES, RP_SITES * 32, &full[slot]);
@@ -929,14 +951,17 @@ __device__ __forceinline__ void replay_body(int group, ReplayStage* st, uint64_t
     }
     return;
   }
-  const int bin = group * (RP_RANGES * 32) + threadIdx.x;         // 0..191
-  const int cslot = threadIdx.x;                                  // slot inside the CTA's part of the tile (slot == bin; bytes 188..191 stay 0)
+  const int q = lane & (RP_Q - 1);                                // which part of a run's rows
+  const int cslot = warp * RP_BPW + lane / RP_Q;                  // slot inside the CTA's part of the tile (slot == bin; bytes 188..191 stay 0)
+  const int bin = group * RP_BINS_CTA + cslot;                    // 0..191
+  const unsigned gsh = lane & ~(RP_Q - 1);                        // first lane of this bin
+  constexpr unsigned GMASK = RP_Q == 32 ? 0xffffffffu : (1u << RP_Q) - 1u;
   double acc = 0.0;
   uint32_t tally = 0;
   bool overflow = false;
 #ifdef REPLAY_PROF
   long long pf_t0 = clock64(), pf_wait = 0, pf_slow = 0;
-  int pf_runs = 0, pf_skipped = 0, pf_slowruns = 0, pf_rel = 0, pf_slowlanes = 0;
+  int pf_runs = 0, pf_skipped = 0, pf_slowruns = 0, pf_lanes = 0, pf_tie = 0, pf_big = 0, pf_e54 = 0, pf_exp = 0, pf_rows = 0, pf_csum = 0, pf_cmax = 0;
 #endif
   for (int it = 0; it < n_stage; it++) {
     const int slot = it % RP_STAGES;
@@ -951,74 +976,99 @@ __device__ __forceinline__ void replay_body(int group, ReplayStage* st, uint64_t
     const int64_t g0r = (t0 + it) * RP_SITES;
     const int lo = (int)max((int64_t)0, r0 - g0r), hi = (int)min((int64_t)RP_SITES, r1 - g0r);
     uint32_t live = (hi >= 32 ? 0xffffffffu : (1u << hi) - 1u) & ~((1u << lo) - 1u);
-    const uint4* cw = (const uint4*)&st[slot].cnt[cslot][0];      // this bin's counts in the tile's 32 rows
+    const uint32_t* cwp = (const uint32_t*)&st[slot].cnt[cslot][0];   // this bin's counts in the tile's 32 rows, 4 rows per word
     const double* hp = (const double*)&st[slot].hdr[0] + 2 + WHICH;
     // ... and add to this histogram (-0.0 weight: nothing to add), one bit per row
     if (WHICH == 0) live &= __ballot_sync(0xffffffffu, ((const int*)(hp + 4 * lane))[1] >= 0);
-    const uint4 ca = cw[0], cb = cw[1];
-    const uint32_t cw8[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
 #pragma unroll
     for (int run = 0; run < RP_SITES / RP_ROWS; run++) {
       const int g0 = run * RP_ROWS;
-      // this bin's counts in the run's rows, one byte each (<= 100)
-      uint32_t cs[RP_CW];
-      const uint32_t lv = live >> g0;
+      const int gl = g0 + q * RP_RPL;                                  // this lane's rows of the run: gl .. gl + RP_RPL
+      // this bin's counts in those rows, one byte each (<= 100)
+      uint32_t cs[RP_CWL];
       uint32_t cs_or = 0, cs_sum = 0;
 #pragma unroll
-      for (int k = 0; k < RP_CW; k++) {
-        cs[k] = cw8[RP_CW * run + k] & ((((lv >> (4 * k)) & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu;        // bit i -> byte i
+      for (int k = 0; k < RP_CWL; k++) {
+        cs[k] = cwp[(gl >> 2) + k] & rp_byte_mask(live >> (gl + 4 * k));
         cs_or |= cs[k];
         cs_sum = __dp4a(cs[k], 0x01010101u, cs_sum);
       }
       if (WHICH == 1) overflow |= (bin == NBINS) & (cs_or != 0);   // a sample in bin 185: out of bounds in the reference
       tally += cs_sum;
-      const bool any = cs_or != 0;
+      const unsigned anyb = __ballot_sync(0xffffffffu, cs_or != 0);
 #ifdef REPLAY_PROF
       pf_runs++;
-      {  // rows of the run in which any lane of the warp has a count
-        uint32_t nzb = 0;
-        for (int i = 0; i < RP_ROWS; i++) nzb |= (((cs[i >> 2] >> (8 * (i & 3))) & 0xff) != 0) << i;
-        pf_rel += __popc(__reduce_or_sync(0xffffffffu, nzb));
-      }
-      if (!__any_sync(0xffffffffu, any)) { pf_skipped++; continue; }
+      if (anyb == 0) { pf_skipped++; continue; }
 #else
-      if (!__any_sync(0xffffffffu, any)) continue;
+      if (anyb == 0) continue;
 #endif
+      const bool any = ((anyb >> gsh) & GMASK) != 0;                   // some row of the run counts for this bin
       const int E = __double2hiint(acc) >> 20;                         // biased exponent (acc >= 0)
       const double M = __hiloint2double((E << 20) | 0x80000, 0);       // 1.5 * 2^E: ulp(M) == ulp(acc)
-      const double hu = __hiloint2double((E - 53) << 20, 0);           // ulp(acc) / 2
+      const int hu_hi = (E - 53) << 20;                                // high word of ulp(acc) / 2 (the low word is 0)
       const int wmax_hi = (E - 1) << 20;                               // w must stay below 2^(E-1)
-      bool bad = (E <= 54) | (E >= 0x7fe);
+      bool badl = (E <= 54) | (E >= 0x7fe);
+      constexpr int NTS = RP_RPL >= 8 ? 4 : 2;
       double ts[4] = {0.0, 0.0, 0.0, 0.0};                             // exact sums: any order
+#ifdef REPLAY_PROF
+      bool pf_c_tie = false, pf_c_big = false;
+#endif
 #pragma unroll
-      for (int i = 0; i < RP_ROWS; i++) {
+      for (int i = 0; i < RP_RPL; i++) {
         const int c = (cs[i >> 2] >> (8 * (i & 3))) & 0xff;
-        const double w = hp[4 * (g0 + i)];                             // (rows of other blocks carry count 0 here; the padding rows are zeroed)
+        const double w = hp[4 * (gl + i)];                             // (rows of other blocks carry count 0 here; the padding rows are zeroed)
         const double d = __dsub_rn(__dadd_rn(w, M), M);
         const double err = __dsub_rn(w, d);
-        bad |= (c != 0) & ((fabs(err) == hu) | (__double2hiint(w) >= wmax_hi));
-        ts[i & (RP_ROWS == 8 ? 1 : 3)] = __fma_rn((double)c, d, ts[i & (RP_ROWS == 8 ? 1 : 3)]);
+        // |err| <= ulp / 2, and ulp / 2 itself is the only such value with its exponent field: a tie shows in the exponent alone
+        badl |= (c != 0) & ((((__double2hiint(err) ^ hu_hi) & 0x7ff00000) == 0) | (__double2hiint(w) >= wmax_hi));
+        // (double)c without the quarter-rate I2F.F64: 2^52 + c is a register pair, one DADD takes the 2^52 off
+        ts[i & (NTS - 1)] = __fma_rn(__dsub_rn(__hiloint2double(0x43300000, c), 0x1p52), d, ts[i & (NTS - 1)]);
+#ifdef REPLAY_PROF
+        pf_c_tie |= (c != 0) & (((__double2hiint(err) ^ hu_hi) & 0x7ff00000) == 0);
+        pf_c_big |= (c != 0) & (__double2hiint(w) >= wmax_hi);
+#endif
       }
-      const double accn = RP_ROWS == 8 ? __dadd_rn(acc, __dadd_rn(ts[0], ts[1]))
-                                       : __dadd_rn(acc, __dadd_rn(__dadd_rn(ts[0], ts[1]), __dadd_rn(ts[2], ts[3])));
-      bad |= (__double2hiint(accn) >> 20) != E;
-      bad &= any;
+      double t = NTS == 4 ? __dadd_rn(__dadd_rn(ts[0], ts[1]), __dadd_rn(ts[2], ts[3])) : __dadd_rn(ts[0], ts[1]);
+#pragma unroll
+      for (int o = 1; o < RP_Q; o <<= 1) t = __dadd_rn(t, __shfl_xor_sync(0xffffffffu, t, o));   // the same bits in every lane of the bin
+      const double accn = __dadd_rn(acc, t);
+      badl |= (__double2hiint(accn) >> 20) != E;
+      const unsigned badb = __ballot_sync(0xffffffffu, badl);
+      const bool bad = any & (((badb >> gsh) & GMASK) != 0);
       if (__any_sync(0xffffffffu, bad)) {
 #ifdef REPLAY_PROF
         pf_slowruns++;
-        pf_slowlanes += __popc(__ballot_sync(0xffffffffu, bad));
+        pf_lanes += __popc(__ballot_sync(0xffffffffu, bad));
+        pf_tie += __popc(__ballot_sync(0xffffffffu, bad && pf_c_tie));
+        pf_big += __popc(__ballot_sync(0xffffffffu, bad && pf_c_big));
+        pf_e54 += __popc(__ballot_sync(0xffffffffu, bad && ((E <= 54) | (E >= 0x7fe))));
+        pf_exp += __popc(__ballot_sync(0xffffffffu, bad && (__double2hiint(accn) >> 20) != E));
+        {
+          int rows = 0, csum = 0, cmax = 0;
+          for (int r = g0; r < g0 + RP_ROWS; r++) {
+            const int c = ((live >> r) & 1u) ? st[slot].cnt[cslot][r] : 0;
+            if (bad && c) { rows++; csum += c; cmax = max(cmax, c); }
+          }
+          pf_rows += __reduce_add_sync(0xffffffffu, rows);
+          pf_csum += __reduce_add_sync(0xffffffffu, csum);
+          pf_cmax = max(pf_cmax, __reduce_max_sync(0xffffffffu, cmax));
+        }
         long long pf_b = clock64();
 #endif
+#ifdef RP_EXP_NOSLOW
+        if (false) {   // experiment: what the kernel costs without its serial path (wrong sums)
+#else
         if (bad) {
-          // (a lane's count is zero in ~85 % of the rows: the serial path only pays for the one or two rows of the run that carry
-          // a count.  A variant that located the crossing row from prefix sums of collapsed steps and committed the rows on
-          // either side at once was measured SLOWER, 1.36 ms against 0.76: its passes touch all eight rows.)
-          // only the rows of the run in which THIS lane has a count (the counts of dead rows are masked to zero above)
+#endif
+          // Row by row, but only the rows of the run in which THIS bin has a count (zero in ~85 % of the rows; the counts of dead
+          // rows are masked).  (A variant that located the crossing row from prefix sums of collapsed steps and committed the
+          // rows on either side at once was measured SLOWER, 1.36 ms against 0.76: its passes touch every row.)
           uint32_t nzr = 0;
 #pragma unroll
           for (int k = 0; k < RP_CW; k++) {
-            const uint32_t nz = (cs[k] | ((cs[k] & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;      // high bit of every non-zero byte
-            nzr |= ((nz * 0x00204081u) >> 28) << (4 * k);                                         // -> one bit per row
+            const uint32_t cwk = cwp[(g0 >> 2) + k] & rp_byte_mask(live >> (g0 + 4 * k));
+            const uint32_t nz = (cwk | ((cwk & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;   // high bit of every non-zero byte
+            nzr |= ((nz * 0x00204081u) >> 28) << (4 * k);                                    // -> one bit per row
           }
 #pragma unroll 1
           while (nzr) {
@@ -1026,8 +1076,11 @@ __device__ __forceinline__ void replay_body(int group, ReplayStage* st, uint64_t
             nzr &= nzr - 1;
             const double w = hp[4 * r];
             const int c = st[slot].cnt[cslot][r];
-            if ((__double_as_longlong(w) << 1) != 0 && __double2hiint(w) >= 0)   // x + 0.0 == x
-              acc = replay_row(acc, w, c);
+            if ((__double_as_longlong(w) << 1) != 0 && __double2hiint(w) >= 0) {   // x + 0.0 == x
+              // a handful of samples (the usual case: 100 samples of a row spread over its bins): the reference's own additions
+              if (c <= 4) { for (int j = 0; j < c; j++) acc = __dadd_rn(acc, w); }
+              else acc = replay_row(acc, w, c);
+            }
           }
         } else if (any) acc = accn;
 #ifdef REPLAY_PROF
@@ -1041,31 +1094,45 @@ __device__ __forceinline__ void replay_body(int group, ReplayStage* st, uint64_t
   }
 #ifdef REPLAY_PROF
   if (lane == 0 && (blk == 3 || blk == 50))
-    printf("[replay prof] blk %d which %d warp %d stages %d: cycles %lld wait %lld slow %lld | runs %d skipped %d slow %d (lanes %d) | relevant rows %d of %d\n",
-           blk, WHICH, warp, n_stage, clock64() - pf_t0, pf_wait, pf_slow, pf_runs, pf_skipped, pf_slowruns, pf_slowlanes, pf_rel, pf_runs * 8);
+    printf("[replay prof] blk %d which %d warp %d stages %d: cycles %lld wait %lld slow %lld | runs %d skipped %d slow %d | bad lanes %d: tie %d big %d e54 %d exp %d | rows walked %d counts %d max %d\n",
+           blk, WHICH, warp, n_stage, clock64() - pf_t0, pf_wait, pf_slow, pf_runs, pf_skipped, pf_slowruns, pf_lanes, pf_tie, pf_big, pf_e54, pf_exp,
+           pf_rows, pf_csum, pf_cmax);
 #endif
   if (overflow) misc[3] = 1;
-  if (bin < NBINS) {
+#pragma unroll
+  for (int o = 1; o < RP_Q; o <<= 1) tally += __shfl_xor_sync(0xffffffffu, tally, o);
+  if (bin < NBINS && q == 0) {
     out_f[((size_t)blk * 4 + WHICH) * NBINS + bin] = acc;
     out_n[((size_t)blk * 3 + WHICH) * NBINS + bin] = tally;
   }
 }
 
-// age_shared_emp / age_notshared_emp row 0 (coal.cpp:2250-2256): one addition per row with age_begin <= 0 into the bin of its
-// age_end, in row order.  Runs as one more blockIdx.y slice of k_replay's grid (same launch).  ONE warp per block: lane = row of
-// a group of 32 consecutive used rows; MATCH.ANY groups the rows by bin, the lowest lane of every group adds its members'
-// weights in lane (= row) order to the bin's running sums in shared memory -- different bins in parallel, one bin in order.
-// (The first version gave every bin a thread that scanned ALL rows of the block: 192 x the work, 0.67 ms when run alone --
-// as long as the histogram slices of the same launch, and on the same SMs.)
-__device__ __forceinline__ void emp_body(unsigned char* scratch, const int64_t* __restrict__ blk_rank_start,
-                                         const uint8_t* __restrict__ e_b2, const double* __restrict__ e_ws,
-                                         const double* __restrict__ e_wn, double* __restrict__ out_f, int64_t* __restrict__ out_n)
+#ifndef RP_MINB_
+#define RP_MINB_ (RP_WARPS_ == 12 ? 3 : 1)   // 13 warps: 3 CTAs per SM hold a 107-block genome's 428 CTAs in one wave
+#endif
+__global__ void __launch_bounds__(RP_THREADS, RP_MINB_)
+k_replay(const int64_t* __restrict__ blk_rank_start, const uint8_t* __restrict__ cnt, const double4* __restrict__ hdr_g,
+         double* __restrict__ out_f, int64_t* __restrict__ out_n, int64_t* misc)
 {
-  if (threadIdx.x >= 32) return;
+  __shared__ ReplayStage st[RP_STAGES];
+  __shared__ __align__(8) uint64_t full[RP_STAGES], empty[RP_STAGES];
+  if (blockIdx.y & 1) replay_body<1>(blockIdx.y >> 1, st, full, empty, blk_rank_start, cnt, hdr_g, out_f, out_n, misc);
+  else replay_body<0>(blockIdx.y >> 1, st, full, empty, blk_rank_start, cnt, hdr_g, out_f, out_n, misc);
+}
+
+// age_shared_emp / age_notshared_emp row 0 (coal.cpp:2250-2256): one addition per row with age_begin <= 0 into the bin of its
+// age_end, in row order.  ONE warp per block: lane = row of a group of 32 consecutive used rows; MATCH.ANY groups the rows by
+// bin, the lowest lane of every group adds its members' weights in lane (= row) order to the bin's running sums in shared
+// memory -- different bins in parallel, one bin in order.  Needs only k_compact's output: launched on the side stream right
+// behind the compaction, under the sampler.  (The first version gave every bin a thread that scanned ALL rows of the block:
+// 192 x the work, 0.67 ms when run alone.)
+__global__ void __launch_bounds__(32)
+k_emp(const int64_t* __restrict__ blk_rank_start, const uint8_t* __restrict__ e_b2, const double* __restrict__ e_ws,
+      const double* __restrict__ e_wn, double* __restrict__ out_f, int64_t* __restrict__ out_n)
+{
+  __shared__ double as[192], an[192];
+  __shared__ int cn[192];
   const int lane = threadIdx.x;
-  double* as = (double*)scratch;          // [192]
-  double* an = as + 192;                  // [192]
-  int* cn = (int*)(an + 192);             // [192]
   for (int i = lane; i < 192; i += 32) { as[i] = 0.0; an[i] = 0.0; cn[i] = 0; }
   __syncwarp();
   const int blk = blockIdx.x;
@@ -1102,20 +1169,6 @@ __device__ __forceinline__ void emp_body(unsigned char* scratch, const int64_t* 
     out_f[((size_t)blk * 4 + 3) * NBINS + bin] = an[bin];
     out_n[((size_t)blk * 3 + 2) * NBINS + bin] = cn[bin];
   }
-}
-
-__global__ void __launch_bounds__(RP_THREADS)
-k_replay(const int64_t* __restrict__ blk_rank_start, const uint8_t* __restrict__ cnt, const double4* __restrict__ hdr_g,
-         const uint8_t* __restrict__ e_b2, const double* __restrict__ e_ws, const double* __restrict__ e_wn,
-         double* __restrict__ out_f, int64_t* __restrict__ out_n, int64_t* misc)
-{
-  constexpr int EMP_CH = 192 * 20 / (int)sizeof(ReplayStage) + 1;
-  __shared__ ReplayStage st[RP_STAGES > EMP_CH ? RP_STAGES : EMP_CH];   // (also emp_body's scratch: 192 x 20 bytes)
-  __shared__ __align__(8) uint64_t full[RP_STAGES], empty[RP_STAGES];
-  // blockIdx.y: 2 * group + which for the two histograms, 2 * RP_GROUPS for the emp slice
-  if (blockIdx.y >= 2 * RP_GROUPS) emp_body((unsigned char*)st, blk_rank_start, e_b2, e_ws, e_wn, out_f, out_n);
-  else if (blockIdx.y & 1) replay_body<1>(blockIdx.y >> 1, st, full, empty, blk_rank_start, cnt, hdr_g, out_f, out_n, misc);
-  else replay_body<0>(blockIdx.y >> 1, st, full, empty, blk_rank_start, cnt, hdr_g, out_f, out_n, misc);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1256,6 +1309,14 @@ int run_compact(colate_handle* h)
   k_block_ranges<<<1, 512, 0, s>>>(h->u_blk.as<int32_t>(), h->misc.as<int64_t>(), h->blk_rank_start.as<int64_t>());
   h->launches += 1;
   CK(cudaEventRecord(h->ev[3], s));
+  if (h->n_blocks_local > 0) {
+    // the emp histograms need nothing but the compacted rows: on the side stream, under the sampler; run_replay joins it
+    CK(cudaStreamWaitEvent(h->side_stream, h->ev[3], 0));
+    k_emp<<<h->n_blocks_local, 32, 0, h->side_stream>>>(h->blk_rank_start.as<int64_t>(), h->u_eb2.as<uint8_t>(), h->u_ews.as<double>(),
+                                                        h->u_ewn.as<double>(), h->out_f.as<double>(), h->out_n.as<int64_t>());
+    h->launches += 1;
+    CK(cudaEventRecord(h->side_done, h->side_stream));
+  }
   CK(cudaGetLastError());
   return 0;
 }
@@ -1314,10 +1375,10 @@ int run_replay(colate_handle* h)
   const int nb = h->n_blocks_local;
   CK(cudaEventRecord(h->ev[4], s));
   if (nb > 0) {
-    k_replay<<<dim3(nb, 2 * RP_GROUPS + 1), RP_THREADS, 0, s>>>(h->blk_rank_start.as<int64_t>(), h->u_cnt.as<uint8_t>(), h->u_hdr.as<double4>(),
-                                                h->u_eb2.as<uint8_t>(), h->u_ews.as<double>(), h->u_ewn.as<double>(),
+    k_replay<<<dim3(nb, 2 * RP_GROUPS), RP_THREADS, 0, s>>>(h->blk_rank_start.as<int64_t>(), h->u_cnt.as<uint8_t>(), h->u_hdr.as<double4>(),
                                                 h->out_f.as<double>(), h->out_n.as<int64_t>(), h->misc.as<int64_t>());
     h->launches += 1;
+    CK(cudaStreamWaitEvent(s, h->side_done, 0));   // k_emp's slices of out_f / out_n (run_compact launched it on the side stream)
   }
   CK(cudaEventRecord(h->ev[5], s));
   CK(cudaGetLastError());

@@ -3,7 +3,7 @@
 needed) and time every phase of stage i on the GPU box at config-2 size, with a checksum of the result so that every
 variant is seen to be bit-identical.
 
-  python tools/variants.py build name1:-DRP_RANGES_=1 name2:-DRP_RANGES_=3,-DFOO ...
+  python tools/variants.py build name1:-DRP_Q_=1 name2:-DRP_Q_=2,-DRP_ROWS_=16 ...
   python tools/variants.py run [rows]          (on the GPU box; the in-tree library first)
 """
 import glob, hashlib, os, shutil, subprocess, sys
