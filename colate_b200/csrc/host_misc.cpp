@@ -755,6 +755,108 @@ extern "C" int64_t colate_maketmp_table(int n_chr, const char* const* chr_names,
   return n_written;
 }
 
+// ---- make_tmp from genotype records (the vcf variant on pre-decoded arrays) -----------------------
+// maketmp_vcf (coal.cpp:2325-2525): a .colate.in record stream from the genotype records of one sample set at the rows of the
+// .mut files.  The BCF decoding (htslib, vcf_parser) stays with the caller; its output per record is the 1-based position, the
+// first two alleles (the letter if the allele string is one character, 0 if it is empty, 0xff otherwise), the sum of the allele
+// indices over the n_hap[chr] haplotypes (bcf_gt_allele, coal.cpp:2434, 2467) and whether every index is <= 1.
+// The reference walks the file with a cursor (2397-2403): it reads on only while the record's position is below the row's, so a
+// record is matched iff it is the first one at or after the row's position, and a cursor that has run off the end stays on the
+// last record.  Row filter (2365, 2381-2395): not flipped, one branch, ancestral exactly one of A C G T 0 and derived exactly one
+// of A C G T 1; a mask drops rows at or beyond its end or not 'P'.  A matched record (2406-2487) gives DAF = N when it shows
+// the derived allele alone and nobody carries an alternative, the (flipped) allele sum when its alleles are the row's, and
+// drops the row otherwise; an unmatched row is read off the reference genome (2489-2503).
+extern "C" int64_t colate_maketmp_records(int n_chr, const char* const* chr_names, const char* const* mut_files, const int64_t* rec_off,
+                                          const int32_t* rec_pos, const uint8_t* rec_a0, const uint8_t* rec_a1, const int32_t* rec_alt_sum,
+                                          const uint8_t* rec_biallelic, const int32_t* n_hap, const char* const* ref_genomes,
+                                          const char* const* target_masks, const char* out_file)
+{
+  using colate::fail;
+  if (n_chr <= 0 || !chr_names || !mut_files || !rec_off || !rec_pos || !rec_a0 || !rec_a1 || !rec_alt_sum || !rec_biallelic || !n_hap || !out_file)
+    return fail(COLATE_ERR_ARG, "colate_maketmp_records: bad arguments");
+  for (int chr = 0; chr < n_chr; chr++)
+    if (rec_off[chr + 1] <= rec_off[chr]) return fail(COLATE_ERR_ARG, "colate_maketmp_records: a chromosome without genotype records (the reference reads the first record unconditionally, coal.cpp:2362)");
+  FILE* fp = fopen(out_file, "wb");
+  if (!fp) return fail(COLATE_ERR_IO, std::string("cannot write ") + out_file);
+  int64_t n_written = 0;
+  for (int chr = 0; chr < n_chr; chr++) {
+    const std::string name = chr_names[chr];
+    std::vector<char> mask, refg;
+    const bool has_mask = target_masks && target_masks[chr];
+    const bool has_refg = ref_genomes && ref_genomes[chr];
+    if (has_mask && !read_fasta_seq(target_masks[chr], mask)) { fclose(fp); return fail(COLATE_ERR_IO, std::string("Error while opening file ") + target_masks[chr] + "."); }
+    if (has_refg && !read_fasta_seq(ref_genomes[chr], refg)) { fclose(fp); return fail(COLATE_ERR_IO, std::string("Error while opening file ") + ref_genomes[chr] + "."); }
+    std::vector<char> buf;
+    if (!colate::slurp_or_gz(mut_files[chr], buf)) { fclose(fp); return fail(COLATE_ERR_IO, std::string("Error while reading ") + mut_files[chr] + "(.gz)."); }
+    buf.push_back('\n');
+    buf.push_back('\0');
+    const char* p = buf.data();
+    const char* endp = buf.data() + buf.size() - 1;
+    const char* nl = (const char*)memchr(p, '\n', endp - p);   // header line
+    p = nl ? nl + 1 : endp;
+    int64_t cur = rec_off[chr];                                 // the record the reference's reader holds
+    const int64_t rec_end = rec_off[chr + 1];
+    int32_t bp_target = rec_pos[cur];
+    const int32_t N = n_hap[chr];
+    while (p < endp) {
+      nl = (const char*)memchr(p, '\n', endp - p);
+      if (!nl) break;
+      if (nl == p) { if (nl + 1 >= endp) break; fclose(fp); return fail(COLATE_ERR_IO, std::string("empty line in ") + mut_files[chr]); }
+      int32_t bp_mut; float ab, ae; uint32_t meta; int flipped, nb; char type[16];
+      if (!colate::parse_mut_line_fields(p, nl, &bp_mut, &ab, &ae, &meta, &flipped, &nb, type)) {
+        fclose(fp);
+        return fail(COLATE_ERR_IO, std::string("Error reading following line in mut file: ") + std::string(p, nl));
+      }
+      p = nl + 1;
+      if (!(flipped == 0 && nb == 1)) continue;
+      if (!(type[0] != '\0' && type[1] == '/' && type[2] != '\0' && type[3] == '\0')) continue;   // both alleles one letter
+      const char a = type[0], d = type[2];
+      if (!(a == 'A' || a == 'C' || a == 'G' || a == 'T' || a == '0')) continue;
+      if (!(d == 'A' || d == 'C' || d == 'G' || d == 'T' || d == '1')) continue;
+      if (has_mask) {
+        if ((uint64_t)(int64_t)bp_mut >= (uint64_t)mask.size()) continue;
+        if (bp_mut >= 1 && mask[bp_mut - 1] != 'P') continue;
+      }
+      if (bp_target < bp_mut)
+        while (cur + 1 < rec_end) {
+          bp_target = rec_pos[++cur];
+          if (bp_target >= bp_mut) break;
+        }
+      int32_t daf = 0;
+      if (bp_target == bp_mut) {
+        const uint8_t t0 = rec_a0[cur], t1 = rec_a1[cur];
+        const uint8_t ua = (uint8_t)a, ud = (uint8_t)d;
+        if (t0 == ud && t1 == 0) {                       // the derived allele alone: shared by everybody unless someone carries an alternative
+          if (!rec_biallelic[cur] || rec_alt_sum[cur] != 0) continue;
+          daf = N;
+        } else if ((t0 == ua && t1 == ud) || (t0 == ud && t1 == ua)) {
+          if (!rec_biallelic[cur]) continue;
+          daf = (t0 == ud && t1 == ua) ? N - rec_alt_sum[cur] : rec_alt_sum[cur];
+        } else continue;
+      } else {
+        if (!has_refg || bp_mut < 1 || (uint64_t)(bp_mut - 1) >= (uint64_t)refg.size()) continue;
+        const char g = refg[bp_mut - 1];
+        if (d == g) daf = N;
+        else if (a == g) daf = 0;
+        else continue;
+      }
+      const int32_t aaf = N - daf;
+      if (aaf < 0) { fclose(fp); return fail(COLATE_ERR_ARG, "colate_maketmp_records: allele sum above the number of haplotypes (the reference asserts, coal.cpp:2511)"); }
+      const int32_t lchrom = (int32_t)name.size();
+      fwrite(&lchrom, 4, 1, fp);
+      fwrite(name.data(), 1, name.size(), fp);
+      fwrite(&bp_mut, 4, 1, fp);
+      fwrite(&a, 1, 1, fp);
+      fwrite(&d, 1, 1, fp);
+      fwrite(&aaf, 4, 1, fp);
+      fwrite(&daf, 4, 1, fp);
+      n_written++;
+    }
+  }
+  fclose(fp);
+  return n_written;
+}
+
 // ---- make_tmp from a pileup (the bam variant on pre-decoded arrays) ------------------------------
 // maketmp_bam (coal.cpp:2527-2680): a .colate.in record stream from the pileup of one BAM file at the rows of the .mut
 // files.  The BAM decoding (htslib, bam_parser) stays with the caller; `counts` is its output: for every DATA ROW of the

@@ -294,6 +294,15 @@ int64_t colate_maketmp_table(int n_chr, const char* const* chr_names, const char
  * decoding stays with the caller).  Returns the records written or < 0. */
 int64_t colate_maketmp_pileup(int n_chr, const char* const* chr_names, const char* const* mut_files, const int32_t* counts,
                               int64_t n_rows, const char* const* target_masks, const char* out_file);
+/* make_tmp from genotype records (maketmp_vcf, coal.cpp:2325-2525) on pre-decoded arrays: the records of chromosome c are
+ * [rec_off[c], rec_off[c+1]) in file order, each with its 1-based position, its first two alleles (the letter if the allele is one
+ * character, 0 if it is the empty string, 0xff otherwise), the sum of bcf_gt_allele over the n_hap[c] haplotypes and whether every
+ * allele index is <= 1 (the BCF decoding stays with the caller).  ref_genomes / target_masks: fasta paths per chromosome, may be
+ * NULL.  Returns the records written or < 0. */
+int64_t colate_maketmp_records(int n_chr, const char* const* chr_names, const char* const* mut_files, const int64_t* rec_off,
+                               const int32_t* rec_pos, const uint8_t* rec_a0, const uint8_t* rec_a1, const int32_t* rec_alt_sum,
+                               const uint8_t* rec_biallelic, const int32_t* n_hap, const char* const* ref_genomes,
+                               const char* const* target_masks, const char* out_file);
 /* <out>.colate_mat as mut() writes it for every front-end but tmp/tmp (coal.cpp:3336-3343, 3453-3465): the age grid, then per
  * replicate the shared and the not-shared count vector (already divided by 1e3), default ostream formatting. */
 int colate_write_colate_mat(const char* path, int R, const double* age_bin, const double* counts);

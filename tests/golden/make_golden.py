@@ -409,6 +409,69 @@ def vcfvcf_fixture():
     shutil.rmtree(d, ignore_errors=True)
 
 
+MAKETMP_VCF_LENS = [3_000_000, 2_000_000]
+
+
+def maketmp_vcf_inputs(d):
+    """Dataset, genotype records of a 3-sample diploid target (fake BCFs), reference genome and target mask for
+    `--mode make_tmp --target_bcf`: records as vcf_records makes them, some rewritten to "the derived / ancestral allele alone"
+    (second allele the empty string: coal.cpp:2413), the first chromosome's records ending before its last rows."""
+    seed = 31
+    rng = np.random.default_rng(seed)
+    lens = MAKETMP_VCF_LENS
+    sites = synth.make_sites(seed, [1500, 900], lens, weird=0.08)
+    synth.write_dataset(d, sites, {})
+    ns, pl = 3, 2
+    recs_all = []
+    for c, nm in enumerate(sites.chr_names):
+        recs = vcf_records(rng, sites, c, ns * pl, 0.8, True)
+        lo, hi = int(sites.site_off[c]), int(sites.site_off[c + 1])
+        by_pos = {int(sites.pos[m]) - 1: m for m in range(lo, hi)}
+        out = []
+        for p0, al, gt in recs:
+            if c == 0 and p0 > int(sites.pos[hi - 40]):
+                break                                          # the reader runs off the end before the rows do
+            m = by_pos.get(p0)
+            if m is not None and rng.random() < 0.12:
+                first = bytes([int(sites.der[m])]) if rng.random() < 0.7 else bytes([int(sites.anc[m])])
+                al = [first, b""]
+                gt = [0] * (ns * pl) if rng.random() < 0.75 else [1] + [0] * (ns * pl - 1)
+            out.append((p0, al, gt))
+        po.write_fake_bcf(os.path.join(d, f"t_chr{nm}.bcf"), ns, pl, out)
+        recs_all.append(out)
+        L = lens[c]
+        g = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, L)].copy()
+        for m in range(lo, hi):
+            u = rng.random()
+            if u < 0.45 and int(sites.der[m]) in b"ACGT":
+                g[int(sites.pos[m]) - 1] = int(sites.der[m])
+            elif u < 0.85 and int(sites.anc[m]) in b"ACGT":
+                g[int(sites.pos[m]) - 1] = int(sites.anc[m])
+        with open(os.path.join(d, f"g_chr{nm}.fa"), "wb") as f:
+            f.write(b">ref\n")
+            for i in range(0, L, 60000):
+                f.write(g[i:i + 60000].tobytes() + b"\n")
+        synth.write_mask(os.path.join(d, f"tm_chr{nm}.fa"), synth.make_mask(seed * 10 + c, L if c else L // 2, 0.25, run_lo=200, run_hi=20000))
+    return sites, recs_all, ns * pl
+
+
+def maketmp_vcf_fixture():
+    """SURVEY.md 8(f) N4, the vcf variant: `Colate --mode make_tmp --target_bcf` (maketmp_vcf, coal.cpp:2325-2525) by the reference
+    CLI on synthetic genotype records served by oracle/hts_stubs.c, without and with a target mask."""
+    d = tempfile.mkdtemp()
+    maketmp_vcf_inputs(d)
+    out = {}
+    for tag, extra in (("plain", []), ("masked", ["--target_mask", d + "/tm"])):
+        pr = subprocess.run([po.ref_cli(), "--mode", "make_tmp", "--mut", d + "/syn", "--chr", d + "/chr.txt", "--target_bcf", d + "/t",
+                             "--ref_genome", d + "/g", "-o", d + "/" + tag] + extra, capture_output=True, text=True)
+        assert pr.returncode == 0, pr.stderr[-2000:]
+        out[tag] = np.frombuffer(open(d + "/" + tag + ".colate.in", "rb").read(), np.uint8)
+        print("make_tmp --target_bcf", tag, out[tag].shape[0], "bytes")
+    np.savez_compressed(os.path.join(OUT, "maketmp_vcf.npz"), **out)
+    import shutil
+    shutil.rmtree(d, ignore_errors=True)
+
+
 def main():
     assert po.ref_available() and po.ref_cli(), "build oracle/_ref first (make -C oracle ref)"
     if len(sys.argv) > 1 and sys.argv[1] == "bambam":
@@ -423,9 +486,12 @@ def main():
         return mut_reader_fixture()
     if len(sys.argv) > 1 and sys.argv[1] == "maketmp":
         return maketmp_fixture()
+    if len(sys.argv) > 1 and sys.argv[1] == "maketmp_vcf":
+        return maketmp_vcf_fixture()
     bambam_fixture()
     vcfvcf_fixture()
     maketmp_fixture()
+    maketmp_vcf_fixture()
     mut_reader_fixture()
     n2_fixture()
     reject_fixture()

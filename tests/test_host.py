@@ -372,6 +372,50 @@ def test_make_tmp_from_a_pileup_matches_the_reference_cli(built, tmp_path):
     assert api.lib().colate_maketmp_pileup(n, names, muts, api.ptr(cnt), cnt.shape[0] - 1, None, (d + "/x").encode()) < 0   # row count must match
 
 
+def test_make_tmp_from_genotype_records_matches_the_reference_cli(built, tmp_path):
+    """SURVEY.md 8(f) N4, the vcf variant on pre-decoded arrays: colate_maketmp_records against the .colate.in the reference CLI
+    wrote with `--mode make_tmp --target_bcf` (maketmp_vcf, coal.cpp:2325-2525) from synthetic genotype records (fixture
+    maketmp_vcf.npz, make_golden.py maketmp_vcf): alleles as the row has them, flipped, a third allele in the record or in a
+    genotype, multi-letter alleles, "one allele alone" records, records between rows, a file that ends before the rows do,
+    rows read off the reference genome; without and with a target mask."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden
+    z = load("maketmp_vcf.npz")
+    d = str(tmp_path)
+    sites, recs, n_hap = make_golden.maketmp_vcf_inputs(d)
+    n = len(sites.chr_names)
+    arr = lambda xs: (C.c_char_p * n)(*[x.encode() for x in xs])
+    per = lambda stem, ext: arr([os.path.join(d, f"{stem}_chr{c}.{ext}") for c in sites.chr_names])
+    code = lambda a: 0 if len(a) == 0 else a[0] if len(a) == 1 else 0xff
+    # what a BCF decoder hands over: the arrays of include/colate_b200.h: colate_maketmp_records
+    off = np.zeros(n + 1, np.int64)
+    off[1:] = np.cumsum([len(r) for r in recs])
+    flat = [r for rs in recs for r in rs]
+    pos = np.array([p0 + 1 for p0, _, _ in flat], np.int32)
+    a0 = np.array([code(al[0]) for _, al, _ in flat], np.uint8)
+    a1 = np.array([code(al[1]) for _, al, _ in flat], np.uint8)
+    alt = np.array([sum(gt) for _, _, gt in flat], np.int32)
+    bi = np.array([max(gt) <= 1 for _, _, gt in flat], np.uint8)
+    nh = np.full(n, n_hap, np.int32)
+    L = api.lib()
+    for tag, masks in (("plain", None), ("masked", per("tm", "fa"))):
+        out = os.path.join(d, tag + ".colate.in")
+        nrec = L.colate_maketmp_records(n, arr(sites.chr_names), per("syn", "mut"), api.ptr(off), api.ptr(pos), api.ptr(a0), api.ptr(a1),
+                                        api.ptr(alt), api.ptr(bi), api.ptr(nh), per("g", "fa"), masks, out.encode())
+        assert nrec > 500, L.colate_last_error()
+        assert open(out, "rb").read() == z[tag].tobytes(), tag
+        rc, bp, aaf, daf, al = api.read_colate_in(out, sites.chr_names)
+        assert len(bp) == nrec and set(np.unique(aaf + daf)) == {n_hap} and 0 < (daf > 0).mean() < 1
+    # a chromosome without records: the reference reads its first record unconditionally
+    off2 = off.copy(); off2[1] = off2[0]
+    assert L.colate_maketmp_records(n, arr(sites.chr_names), per("syn", "mut"), api.ptr(off2), api.ptr(pos), api.ptr(a0), api.ptr(a1),
+                                    api.ptr(alt), api.ptr(bi), api.ptr(nh), None, None, (d + "/x").encode()) < 0
+    if po.ref_cli():
+        r = subprocess.run([po.ref_cli(), "--mode", "make_tmp", "--mut", d + "/syn", "--chr", d + "/chr.txt", "--target_bcf", d + "/t",
+                            "--ref_genome", d + "/g", "-o", d + "/live"], capture_output=True, text=True)
+        assert r.returncode == 0 and open(d + "/live.colate.in", "rb").read() == z["plain"].tobytes()
+
+
 def test_mask_bits_from_fasta(built):
     sites = synth.make_sites(3, [400, 300], [3e5, 2e5])
     masks = [synth.make_mask(1, 300000, 0.4, 50, 500), synth.make_mask(2, 100000, 0.3, 50, 500, lower=True)]   # 2nd: short + lower case
