@@ -18,7 +18,10 @@ namespace colate {
 constexpr int MT_N = 624;
 constexpr int XLEN = 19937 + MT_N;       // base sequence needed by one jump
 constexpr int JUMP_THREADS = 640;
-constexpr int MAX_TAPS = 19968;
+#ifndef JUMP_COEF_US_
+#define JUMP_COEF_US_ 35.0
+#endif
+constexpr double JUMP_COEF_US = JUMP_COEF_US_, JUMP_BASE_US = 10.0;   // measured on B200: coefficient work and base sequence of one jump on one SM
 
 __device__ __forceinline__ uint32_t mt_mix_dev(uint32_t a, uint32_t b, uint32_t c)
 {
@@ -36,25 +39,37 @@ __device__ __forceinline__ uint32_t mt_temper_dev(uint32_t z)
 }
 
 // windows[d] <- jump(windows[src]).  Binary level (radix 2): d = (2*j+1) << level, src = d - (1<<level).  Radix-4 level:
-// d = (4*j + r) << level for r = 1, 2, 3 from src = (4*j) << level, with the polynomials t^(r * S * 2^level) (tap list r - 1):
+// d = (4*j + r) << level for r = 1, 2, 3 from src = (4*j) << level, with the polynomials t^(r * S * 2^level) (g0, g1, g2):
 // two bits of the chunk index per launch, so the latency-bound top of the tree (a handful of jumps per level) is half
 // as deep.  j / r from blockIdx.x / P;  level < 0: single jump windows[aux_dst] <- jump(windows[aux_src]).
-// A jump is split over P CTAs (P = 1, 2, 4, 8): CTA p computes outputs [p*624/P, (p+1)*624/P); inside
-// the CTA the taps are split over T = P groups of threads whose partial XORs are combined in shared
-// memory.  (One CTA per jump is bound by a single SM's shared-memory bandwidth: 624 x ~10^4 loads.)
+//
+// The jump itself: out[j] = XOR over the set coefficients i of g of X[i + j], X the base sequence from the source window.
+// The polynomial is walked in blocks of 32 coefficients.  A lane owns JO = 20 consecutive outputs and loads the 51 words
+// X[32 blk + 20 lane .. + 51) of a block ONCE (13 conflict-free LDS.128: the lane stride of 5 x 16 B visits all 8 bank
+// groups); every set coefficient of the block is then 20 register XORs behind a warp-uniform branch.  One warp covers all
+// 624 outputs (lane 31: 4), the CTA's 20 warps take every 20th block and meet in shared-memory atomics.  Shared-memory
+// traffic per jump: 4 MB against 25 MB for one LDS.32 per (coefficient, output) -- the first version, which ran at the
+// shared-memory bandwidth of its SM (~130 us per jump) -- and the tap lists (20 KB per polynomial) are gone: the
+// coefficients travel as the 624-word bit mask.
+// A jump may be split over P CTAs (P = 1, 2, 4, 8): CTA p takes the p-th part of the coefficient blocks and every CTA
+// regenerates the base sequence; the partial results meet in global atomics on the destination window, which the host
+// zeroes beforehand (every window of the tree is the destination of exactly one jump).  level < 0 runs with P = 1.
+constexpr int JO = 20;                      // outputs per lane
+constexpr int JW = 32 + JO - 1;             // words of X a lane needs for one block of 32 coefficients
+constexpr int JBLK = (19937 + 31) / 32;     // 624 coefficient blocks
+constexpr int XPAD = 32 * (JBLK - 1) + JO * 31 + ((JW + 3) & ~3);   // lane 31's window of the last block ends here (its outputs 624.. are discarded)
 __global__ void __launch_bounds__(JUMP_THREADS)
-k_jump(uint32_t* __restrict__ windows, const uint16_t* __restrict__ taps0, int n_taps0, const uint16_t* __restrict__ taps1, int n_taps1,
-       const uint16_t* __restrict__ taps2, int n_taps2, int level, int n_chunks, int P, int radix, int aux_src, int aux_dst)
+k_jump(uint32_t* __restrict__ windows, const uint32_t* __restrict__ g0, const uint32_t* __restrict__ g1, const uint32_t* __restrict__ g2,
+       int level, int n_chunks, int P, int radix, int aux_src, int aux_dst)
 {
   extern __shared__ __align__(16) uint32_t sm[];
-  uint32_t* X = sm;                                   // XLEN words (+ pad)
-  uint16_t* T = (uint16_t*)(sm + ((XLEN + 3) & ~3));  // tap offsets
-  uint32_t* red = (uint32_t*)(T + ((MAX_TAPS + 15) & ~15));  // [8][78] partial results
+  uint32_t* X = sm;                                   // XPAD words
+  uint32_t* G = sm + XPAD;                            // the polynomial's 624 coefficient words
+  uint32_t* out = G + MT_N;                           // 624 result words
   const int tid = threadIdx.x;
   const int jr = blockIdx.x / P, p = blockIdx.x % P;
   int d, src;
-  const uint16_t* taps = taps0;
-  int n_taps = n_taps0;
+  const uint32_t* g = g0;
   if (level < 0) { d = aux_dst; src = aux_src; }
   else if (radix == 2) {
     d = (2 * jr + 1) << level;
@@ -65,11 +80,11 @@ k_jump(uint32_t* __restrict__ windows, const uint16_t* __restrict__ taps0, int n
     d = (4 * j + r) << level;
     if (d >= n_chunks) return;
     src = (4 * j) << level;
-    if (r == 2) { taps = taps1; n_taps = n_taps1; }
-    if (r == 3) { taps = taps2; n_taps = n_taps2; }
+    if (r == 2) g = g1;
+    if (r == 3) g = g2;
   }
-  for (int i = tid; i < MT_N; i += blockDim.x) X[i] = windows[(size_t)src * MT_N + i];
-  for (int i = tid; i < n_taps; i += blockDim.x) T[i] = taps[i];
+  for (int i = tid; i < MT_N; i += blockDim.x) { X[i] = windows[(size_t)src * MT_N + i]; G[i] = g[i]; out[i] = 0; }
+  for (int i = XLEN + tid; i < XPAD; i += blockDim.x) X[i] = 0;
   __syncthreads();
   // base sequence: 624 words per block barrier (a thread's second and third word of a round depend on its own first and second
   // one; the last word of a round needs the round's first word, which its thread recomputes: see k_gen)
@@ -88,27 +103,37 @@ k_jump(uint32_t* __restrict__ windows, const uint16_t* __restrict__ taps0, int n
     }
     __syncthreads();
   }
-  const int nout = MT_N / P;          // outputs of this CTA
-  const int part = tid / nout;        // tap group of this thread (0..P-1); threads >= 624 idle
-  const int jl = tid - part * nout;
-  uint32_t acc = 0;
-  if (tid < MT_N) {
-    const int per = (((n_taps + P - 1) / P) + 7) & ~7;   // taps per group, multiple of 8 (16-byte loads)
-    const int t0 = part * per, t1 = min(n_taps, t0 + per);
-    const uint32_t* Xt = X + p * nout + jl;
-    int i = t0;
-    for (; i + 8 <= t1; i += 8) {
-      uint4 t4 = *(const uint4*)(T + i);  // 8 taps, same address for the whole group
-      acc ^= Xt[t4.x & 0xffff] ^ Xt[t4.x >> 16] ^ Xt[t4.y & 0xffff] ^ Xt[t4.y >> 16] ^
-             Xt[t4.z & 0xffff] ^ Xt[t4.z >> 16] ^ Xt[t4.w & 0xffff] ^ Xt[t4.w >> 16];
+  const int warp = tid >> 5, lane = tid & 31;
+  constexpr int NWARP = JUMP_THREADS / 32;
+  const int b0 = (JBLK * p) / P, b1 = (JBLK * (p + 1)) / P;     // this CTA's coefficient blocks
+  uint32_t acc[JO];
+#pragma unroll
+  for (int o = 0; o < JO; o++) acc[o] = 0;
+#pragma unroll 1
+  for (int blk = b0 + warp; blk < b1; blk += NWARP) {
+    const uint32_t m = G[blk];                                   // the same word in every lane
+    if (m == 0) continue;
+    uint32_t r[(JW + 3) & ~3];
+    const uint4* xs = (const uint4*)(X + 32 * blk + JO * lane);
+#pragma unroll
+    for (int i = 0; i < (JW + 3) / 4; i++) {
+      const uint4 v = xs[i];
+      r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
     }
-    for (; i < t1; i++) acc ^= Xt[T[i]];
-    if (part > 0) red[(part - 1) * nout + jl] = acc;
+#pragma unroll
+    for (int b = 0; b < 32; b++)
+      if (m & (1u << b)) {
+#pragma unroll
+        for (int o = 0; o < JO; o++) acc[o] ^= r[b + o];
+      }
   }
+#pragma unroll
+  for (int o = 0; o < JO; o++)
+    if (JO * lane + o < MT_N) atomicXor(&out[JO * lane + o], acc[o]);
   __syncthreads();
-  if (tid < nout) {
-    for (int q = 1; q < P; q++) acc ^= red[(q - 1) * nout + tid];
-    windows[(size_t)d * MT_N + p * nout + tid] = acc;
+  if (tid < MT_N) {
+    if (P == 1) windows[(size_t)d * MT_N + tid] = out[tid];
+    else atomicXor(&windows[(size_t)d * MT_N + tid], out[tid]);
   }
 }
 
@@ -214,58 +239,55 @@ __global__ void k_tail_gather(const uint32_t* __restrict__ stream, int64_t tile_
   if (i < n) tail[i] = stream[stream_phys(from + i, tile_off)];
 }
 
-// ---- tap lists per polynomial, cached per device -------------------------------------------
-struct TapList { uint16_t* d = nullptr; int n = 0; };
+// ---- coefficient masks per polynomial, cached per device ---------------------------------------
 static std::mutex g_mu;
-static std::map<std::pair<int, int>, TapList> g_taps;  // (device, q or 1000 + q for the 3x polynomial) -> taps
+static std::map<std::pair<int, int>, uint32_t*> g_polys;  // (device, q or 1000 + q for the 3x polynomial) -> 624 words on the device
 
-static int get_taps(int device, int q, cudaStream_t s, TapList* out, bool triple = false)
+static int get_poly(int device, int q, cudaStream_t s, const uint32_t** out, bool triple = false)
 {
   std::lock_guard<std::mutex> lk(g_mu);
   const int key = triple ? 1000 + q : q;
-  auto it = g_taps.find({device, key});
-  if (it != g_taps.end()) { *out = it->second; return 0; }
+  auto it = g_polys.find({device, key});
+  if (it != g_polys.end()) { *out = it->second; return 0; }
   const uint32_t* g = triple ? jump_poly3(q) : jump_poly(q);
   if (!g) return fail(COLATE_ERR_ARG, "jump polynomial unavailable");
-  std::vector<uint16_t> taps;
-  taps.reserve(10500);
-  for (int i = 0; i < 19937; i++) if ((g[i >> 5] >> (i & 31)) & 1u) taps.push_back((uint16_t)i);
-  TapList tl;
-  tl.n = (int)taps.size();
-  size_t bytes = ((taps.size() + 15) & ~(size_t)15) * 2 + 32;
-  CK(cudaMalloc(&tl.d, bytes));
-  CK(cudaMemsetAsync(tl.d, 0, bytes, s));
-  CK(cudaMemcpyAsync(tl.d, taps.data(), taps.size() * 2, cudaMemcpyHostToDevice, s));
-  CK(cudaStreamSynchronize(s));  // taps is a local
-  g_taps[{device, key}] = tl;
-  *out = tl;
+  uint32_t host[MT_N];
+  memcpy(host, g, sizeof host);
+  host[MT_N - 1] &= 1u;                                      // degree < 19937 = 623 * 32 + 1
+  uint32_t* dev = nullptr;
+  CK(cudaMalloc(&dev, sizeof host));
+  CK(cudaMemcpyAsync(dev, host, sizeof host, cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));  // host[] is a local
+  g_polys[{device, key}] = dev;
+  *out = dev;
   return 0;
 }
 
 static int launch_jump(colate_handle* h, int q, int level, int n_chunks, int n_jumps, int aux_src, int aux_dst, int radix = 2)
 {
-  TapList tl, tl2, tl3;
-  int rc = get_taps(h->device, q, h->stream, &tl);
+  const uint32_t *g0, *g1, *g2;
+  int rc = get_poly(h->device, q, h->stream, &g0);
   if (rc) return rc;
-  tl2 = tl; tl3 = tl;
+  g1 = g0; g2 = g0;
   if (radix == 4) {
-    if ((rc = get_taps(h->device, q + 1, h->stream, &tl2))) return rc;
-    if ((rc = get_taps(h->device, q, h->stream, &tl3, true))) return rc;
+    if ((rc = get_poly(h->device, q + 1, h->stream, &g1))) return rc;
+    if ((rc = get_poly(h->device, q, h->stream, &g2, true))) return rc;
   }
   // Split factor: one CTA per SM (the base sequence alone takes 82 KB of shared memory), so a launch runs in
-  // ceil(n_jumps * P / SMs) waves of (tap work / P + the base sequence every CTA regenerates): take the cheapest
-  // (measured on B200: ~130 us of taps per jump, ~10 us for the base sequence)
+  // ceil(n_jumps * P / SMs) waves of (coefficient work / P + the base sequence every CTA regenerates): take the cheapest
   int P = 1;
-  double best = 1e30;
-  for (int cand = 1; cand <= 8; cand *= 2) {
-    const double waves = (double)((n_jumps * cand + h->sm_count - 1) / h->sm_count);
-    const double cost = waves * (130.0 / cand + 10.0);
-    if (cost < best) { best = cost; P = cand; }
+  if (level >= 0) {
+    double best = 1e30;
+    for (int cand = 1; cand <= 8; cand *= 2) {
+      const double waves = (double)((n_jumps * cand + h->sm_count - 1) / h->sm_count);
+      const double cost = waves * (JUMP_COEF_US / cand + JUMP_BASE_US);
+      if (cost < best) { best = cost; P = cand; }
+    }
+    if (const char* e = getenv("COLATE_JUMP_SPLIT")) P = std::max(1, std::min(8, atoi(e)));
   }
-  const size_t smem = (size_t)((XLEN + 3) & ~3) * 4 + (size_t)((MAX_TAPS + 15) & ~15) * 2 + (size_t)7 * 312 * 4 + 64;
+  const size_t smem = (size_t)(XPAD + 2 * MT_N) * 4;
   CK(cudaFuncSetAttribute(k_jump, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_jump<<<n_jumps * P, JUMP_THREADS, smem, h->stream>>>(h->windows.as<uint32_t>(), tl.d, tl.n, tl2.d, tl2.n, tl3.d, tl3.n, level, n_chunks, P, radix,
-                                                         aux_src, aux_dst);
+  k_jump<<<n_jumps * P, JUMP_THREADS, smem, h->stream>>>(h->windows.as<uint32_t>(), g0, g1, g2, level, n_chunks, P, radix, aux_src, aux_dst);
   h->launches += 1;
   CK(cudaGetLastError());
   return 0;
@@ -307,6 +329,7 @@ int run_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int
   CK(h->rng_stream.ensure((size_t)(std::max<int64_t>(total_local, 4) + (tiled ? SAMPLE_TILE_WORDS : 0)) * 4 + 64));   // tiled: whole last tile
   CK(h->mt_tail.ensure(MT_N * 4));
   CK(cudaMemcpyAsync(h->windows.p, mt_state, MT_N * 4, cudaMemcpyHostToDevice, s));
+  if (M > 1) CK(cudaMemsetAsync(h->windows.as<uint32_t>() + MT_N, 0, (size_t)(M - 1) * MT_N * 4, s));   // split jumps meet in atomics on their destination
   // reach chunk c0: one jump per set bit of c0, ping-ponging between window 0 and the scratch window
   int cur = 0;
   for (int b = 62; b >= 0; b--) {
