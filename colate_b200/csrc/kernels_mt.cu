@@ -9,6 +9,9 @@
 // (the recurrence exposes 227-wide parallelism per step) and written tempered to HBM.
 #include "device.cuh"
 
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -231,6 +234,110 @@ k_gen(const uint32_t* __restrict__ windows, int64_t chunk_words, int64_t total_w
   }
 }
 
+// k_gen for the common case (tile order from the first word on).  The address arithmetic of the scatter was a third of
+// k_gen's instructions (49 per word, 11 + 5 of them the place() / advance() above: every thread works out where each of its
+// three words of a round goes).  Here the tempered words go to a ring in shared memory in GENERATOR order and the TMA unit
+// does the permutation: the tile order [tile][chunk c][row r][20 words] is described to it as a 4-d tensor with the dimensions
+// in the order (word 20, chunk 10, row 32, tile) -- strides 4 B, 2560 B, 80 B, 25600 B -- so that a box of 20 x 10 x 4 x 1 is, on
+// the shared-memory side, 4 consecutive rows of the stream exactly as the generator emits them (800 contiguous words), and on
+// the global side their 40 pieces of 80 B.  A ninth warp that takes no part in the recurrence issues one tensor store per
+// finished group of 4 rows (cp.async.bulk.tensor.4d shared -> global, under the next round's recurrence); the ring holds 5
+// groups and the copy warp lets only the two latest rounds' stores be in flight before it joins the next barrier.
+// (Measured before this: one plain bulk copy per 80-byte piece, 33 per round -- 2.0 ms, the copy engine pays per operation.)
+// Chunks are whole multiples of 4 rows (2^k rows, k >= 3); the very last group of the stream may carry up to 3 rows of
+// whatever the ring held beyond the last word: they land inside the last tile, which the buffer always holds whole and
+// whose rows past n_used k_sample does not count.
+constexpr int GEN_GROUP_WORDS = 800;                 // 4 rows
+constexpr int GEN_RING = 5 * GEN_GROUP_WORDS;
+__global__ void __launch_bounds__(288)
+k_gen_tma(const uint32_t* __restrict__ windows, int64_t chunk_words, int64_t total_words, const __grid_constant__ CUtensorMap tmap,
+          uint32_t* __restrict__ tail)
+{
+  static_assert(SAMPLE_CHUNK_WORDS == 20, "the tensor map describes 20-word chunks");
+  __shared__ uint32_t bufA[MT_N + 1], bufB[MT_N + 1];
+  __shared__ __align__(128) uint32_t ring[GEN_RING];
+  const int tid = threadIdx.x;
+  const int64_t start = (int64_t)blockIdx.x * chunk_words;
+  if (start >= total_words) return;
+  const int64_t end = min(start + chunk_words, total_words);
+  for (int i = tid; i < MT_N; i += blockDim.x) bufA[i] = windows[(size_t)blockIdx.x * MT_N + i];
+  __syncthreads();
+  uint32_t* cur = bufA;
+  uint32_t* nxt = bufB;
+  int p0 = tid, p1 = tid + 227, p2 = tid + 454;      // ring positions of this thread's three words of the round
+  const int row_base = (int)(start / 200);           // rows stay far below 2^31 (800 B of stream each); a multiple of 4
+  int groups_issued = 0;
+  int64_t o = start;
+  for (; o < end; o += MT_N) {
+    if (tid < 227) {
+      // (see k_gen: a thread's three words of a round depend on its own, word 623's neighbour is recomputed: one barrier per round)
+      const uint32_t v0 = mt_mix_dev(cur[tid], cur[tid + 1], cur[tid + 397]);
+      nxt[tid] = v0;
+      ring[p0] = mt_temper_dev(v0);
+      const int k = tid + 227;
+      const uint32_t v1 = mt_mix_dev(cur[k], cur[k + 1], v0);
+      nxt[k] = v1;
+      ring[p1] = mt_temper_dev(v1);
+      if (tid < 170) {
+        const int k2 = tid + 454;
+        const uint32_t b = (k2 == 623) ? mt_mix_dev(cur[0], cur[1], cur[397]) : cur[k2 + 1];
+        const uint32_t v2 = mt_mix_dev(cur[k2], b, v1);
+        nxt[k2] = v2;
+        ring[p2] = mt_temper_dev(v2);
+      }
+      p0 += MT_N; p1 += MT_N; p2 += MT_N;
+      if (p0 >= GEN_RING) p0 -= GEN_RING;
+      if (p1 >= GEN_RING) p1 -= GEN_RING;
+      if (p2 >= GEN_RING) p2 -= GEN_RING;
+    }
+    __syncthreads();
+    if (tid >= 256) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the other warps' generic writes of this round before the async reads
+      const int64_t done = min(o + MT_N, end) - start;               // words of the chunk that are in the ring (or have left it)
+      const int g_now = (int)(o + MT_N >= end ? (done + GEN_GROUP_WORDS - 1) / GEN_GROUP_WORDS : done / GEN_GROUP_WORDS);
+      for (int g = groups_issued + (tid - 256); g < g_now; g += 32) {
+        const int row = row_base + 4 * g;
+        const uint32_t src = (uint32_t)__cvta_generic_to_shared(ring + (g % 5) * GEN_GROUP_WORDS);
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(&tmap), "r"(0), "r"(0),
+                     "r"(row & 31), "r"(row >> 5), "r"(src)
+                     : "memory");
+      }
+      groups_issued = g_now;
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");   // a group's place in the ring is written again 3.8 rounds after it left
+    }
+    uint32_t* t = cur; cur = nxt; nxt = t;
+  }
+  if (tid >= 256) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (end == total_words) {
+    // cur = untempered words [o - 624, o), nxt = the 624 before them (the chunk's start window if only one round ran)
+    const int n_tail = (int)min(total_words, (int64_t)MT_N);
+    for (int i = tid; i < n_tail; i += blockDim.x) {
+      const int64_t g = total_words - n_tail + i;               // >= o - 1248 because o - 624 < total_words
+      const int rel = (int)(g - (o - 2 * MT_N));
+      tail[i] = mt_temper_dev(rel >= MT_N ? cur[rel - MT_N] : nxt[rel]);
+    }
+  }
+}
+
+// the tile-ordered stream as the 4-d tensor k_gen_tma stores through (driver entry point fetched once; false: not available)
+static bool encode_stream_map(uint32_t* base, int64_t total_words, CUtensorMap* out)
+{
+  static PFN_cuTensorMapEncodeTiled_v12000 enc = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+    return (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  }();
+  if (!enc) return false;
+  const cuuint64_t tiles = (cuuint64_t)((total_words + SAMPLE_TILE_WORDS - 1) / SAMPLE_TILE_WORDS);
+  const cuuint64_t dims[4] = {20, 10, 32, tiles};
+  const cuuint64_t strides[3] = {20 * 32 * 4, 20 * 4, (cuuint64_t)SAMPLE_TILE_WORDS * 4};
+  const cuuint32_t box[4] = {20, 10, 4, 1}, estr[4] = {1, 1, 1, 1};
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // the n words before logical position `from + n` of a tile-ordered stream, linearly (state recovery when the stream in
 // HBM is longer than the caller's request: stream cache)
 __global__ void k_tail_gather(const uint32_t* __restrict__ stream, int64_t tile_off, int64_t from, int n, uint32_t* __restrict__ tail)
@@ -366,8 +473,13 @@ int run_mt_stream(colate_handle* h, const uint32_t* mt_state, int64_t word0, int
     uint32_t* st = h->rng_stream.as<uint32_t>();
     uint32_t* tl = h->mt_tail.as<uint32_t>();
     if (!tiled) k_gen<false, false, false><<<M, 256, 0, s>>>(win, S, total_local, st, 0, tl);
-    else if (off == 0 && w32) k_gen<true, false, true><<<M, 256, 0, s>>>(win, S, total_local, st, off, tl);
-    else if (off == 0) k_gen<true, false, false><<<M, 256, 0, s>>>(win, S, total_local, st, off, tl);
+    else if (off == 0) {
+      CUtensorMap tm;
+      static const bool no_tma = getenv("COLATE_GEN_NO_TMA") != nullptr;
+      if (k >= 2 && !no_tma && encode_stream_map(st, total_local, &tm)) k_gen_tma<<<M, 288, 0, s>>>(win, S, total_local, tm, tl);
+      else if (w32) k_gen<true, false, true><<<M, 256, 0, s>>>(win, S, total_local, st, off, tl);
+      else k_gen<true, false, false><<<M, 256, 0, s>>>(win, S, total_local, st, off, tl);
+    }
     else if (w32) k_gen<true, true, true><<<M, 256, 0, s>>>(win, S, total_local, st, off, tl);
     else k_gen<true, true, false><<<M, 256, 0, s>>>(win, S, total_local, st, off, tl);
     h->launches += 1;
