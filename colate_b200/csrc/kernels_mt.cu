@@ -20,7 +20,10 @@ namespace colate {
 
 constexpr int MT_N = 624;
 constexpr int XLEN = 19937 + MT_N;       // base sequence needed by one jump
-constexpr int JUMP_THREADS = 640;
+#ifndef JUMP_THREADS_
+#define JUMP_THREADS_ 640
+#endif
+constexpr int JUMP_THREADS = JUMP_THREADS_;
 #ifndef JUMP_COEF_US_
 #define JUMP_COEF_US_ 35.0
 #endif
@@ -61,7 +64,7 @@ constexpr int JO = 20;                      // outputs per lane
 constexpr int JW = 32 + JO - 1;             // words of X a lane needs for one block of 32 coefficients
 constexpr int JBLK = (19937 + 31) / 32;     // 624 coefficient blocks
 constexpr int XPAD = 32 * (JBLK - 1) + JO * 31 + ((JW + 3) & ~3);   // lane 31's window of the last block ends here (its outputs 624.. are discarded)
-__global__ void __launch_bounds__(JUMP_THREADS)
+__global__ void __launch_bounds__(JUMP_THREADS, JUMP_THREADS <= 512 ? 2 : 1)
 k_jump(uint32_t* __restrict__ windows, const uint32_t* __restrict__ g0, const uint32_t* __restrict__ g1, const uint32_t* __restrict__ g2,
        int level, int n_chunks, int P, int radix, int aux_src, int aux_dst)
 {
@@ -134,9 +137,9 @@ k_jump(uint32_t* __restrict__ windows, const uint32_t* __restrict__ g0, const ui
   for (int o = 0; o < JO; o++)
     if (JO * lane + o < MT_N) atomicXor(&out[JO * lane + o], acc[o]);
   __syncthreads();
-  if (tid < MT_N) {
-    if (P == 1) windows[(size_t)d * MT_N + tid] = out[tid];
-    else atomicXor(&windows[(size_t)d * MT_N + tid], out[tid]);
+  for (int i = tid; i < MT_N; i += blockDim.x) {
+    if (P == 1) windows[(size_t)d * MT_N + i] = out[i];
+    else atomicXor(&windows[(size_t)d * MT_N + i], out[i]);
   }
 }
 

@@ -867,7 +867,7 @@ constexpr int RP_ROWS = RP_ROWS_;   // rows collapsed into one exact update
 constexpr int RP_CW = RP_ROWS / 4;  // count words of a run (4 rows per word)
 static_assert(RP_ROWS == 8 || RP_ROWS == 16 || RP_ROWS == 32, "run width");
 #ifndef RP_Q_
-#define RP_Q_ 4
+#define RP_Q_ 2
 #endif
 constexpr int RP_Q = RP_Q_;               // lanes per bin: each takes RP_ROWS / RP_Q consecutive rows of a run
 constexpr int RP_BPW = 32 / RP_Q;         // bins per warp
@@ -876,7 +876,7 @@ constexpr int RP_CWL = RP_RPL / 4;        // count words per lane and run
 static_assert(RP_Q == 1 || RP_Q == 2 || RP_Q == 4 || RP_Q == 8, "lanes per bin");
 static_assert(RP_RPL >= 4 && RP_RPL % 4 == 0, "a lane takes whole count words");
 #ifndef RP_WARPS_
-#define RP_WARPS_ (192 / RP_BPW > 12 ? 12 : 192 / RP_BPW)
+#define RP_WARPS_ 3
 #endif
 constexpr int RP_WARPS = RP_WARPS_;       // consumer warps per CTA
 constexpr int RP_BINS_CTA = RP_WARPS * RP_BPW;
@@ -917,7 +917,11 @@ __device__ __forceinline__ uint32_t rp_byte_mask(uint32_t m) { return (((m & 0xf
 // takes the total out of the binade, which is detected).  So a bin is given to RP_Q lanes, each with
 // RP_ROWS / RP_Q rows of the run, whose partial sums meet in a shuffle butterfly: the walk is a
 // latency chain per tile (the kernel ran at 16 % active warps with one lane per bin), and the chain
-// of a lane is RP_Q times shorter this way while RP_Q times as many warps share the SMs.  A run that
+// of a lane is RP_Q times shorter this way while RP_Q times as many warps share the SMs.  Measured on
+// B200 (10 M rows, bit-identical throughout): 1 lane per bin 0.64 ms, 4 lanes 0.58 - 0.60 (the fixed cost per
+// tile is paid by four times as many warps: issue-bound at 3.45e8 warp instructions), 2 lanes 0.50; and CTAs of
+// 3 bin-warps (48 bins, four CTAs per block and histogram) beat 6 / 12 bin-warps (0.54 / 0.61): the warps of a
+// CTA share the count-tile ring and move at the pace of the slowest.  A run that
 // leaves the binade, meets a rounding tie or a weight too large for the shortcut is redone row by
 // row (replay_row / exact_sum.cuh) by all RP_Q lanes of the bin alike, over the rows with a count.
 // blockIdx.y: 2 * group + (0 shared, 1 not shared).  hdr.z carries -0.0 for rows that add nothing to shared.
@@ -1108,7 +1112,7 @@ __device__ __forceinline__ void replay_body(int group, ReplayStage* st, uint64_t
 }
 
 #ifndef RP_MINB_
-#define RP_MINB_ (RP_WARPS_ == 12 ? 3 : 1)   // 13 warps: 3 CTAs per SM hold a 107-block genome's 428 CTAs in one wave
+#define RP_MINB_ (RP_WARPS_ <= 3 ? 6 : RP_WARPS_ <= 6 ? 3 : RP_WARPS_ <= 12 ? 2 : 1)   // small CTAs (a CTA moves at the pace of its slowest bin-warp); 6 x 148 slots hold a 107-block genome's 856 CTAs in one wave
 #endif
 __global__ void __launch_bounds__(RP_THREADS, RP_MINB_)
 k_replay(const int64_t* __restrict__ blk_rank_start, const uint8_t* __restrict__ cnt, const double4* __restrict__ hdr_g,
