@@ -126,12 +126,21 @@ k_jump(uint32_t* __restrict__ windows, const uint32_t* __restrict__ g0, const ui
       const uint4 v = xs[i];
       r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
     }
+    // two coefficients per (warp-uniform) branch: a set pair is ONE three-input XOR per output
 #pragma unroll
-    for (int b = 0; b < 32; b++)
-      if (m & (1u << b)) {
+    for (int b = 0; b < 32; b += 2) {
+      const uint32_t two = (m >> b) & 3u;
+      if (two == 3u) {
+#pragma unroll
+        for (int o = 0; o < JO; o++) acc[o] ^= r[b + o] ^ r[b + 1 + o];
+      } else if (two == 1u) {
 #pragma unroll
         for (int o = 0; o < JO; o++) acc[o] ^= r[b + o];
+      } else if (two == 2u) {
+#pragma unroll
+        for (int o = 0; o < JO; o++) acc[o] ^= r[b + 1 + o];
       }
+    }
   }
 #pragma unroll
   for (int o = 0; o < JO; o++)
