@@ -57,6 +57,25 @@ def test_cli_coal_identical_to_reference(dataset_dir, name):
         assert np.array_equal(rates[i], ro)
 
 
+def test_cli_generator_fallback_without_tma_is_byte_identical(dataset_dir):
+    """The generator's scatter through the TMA unit (k_gen_tma, kernels_mt.cu) and its fallback that computes every word's place
+    itself (k_gen<true>: COLATE_GEN_NO_TMA=1, also taken when cuTensorMapEncodeTiled is unavailable) write the same stream: the
+    reference CLI's golden .coal either way, and the fp64 side output equal byte for byte."""
+    d, z, sites, gt, gr = dataset_dir
+    name = "bins02_R3"
+    extra = [str(x) for x in z[f"{name}_args"]]
+    outs = []
+    for tag, env in (("tma", {}), ("notma", {"COLATE_GEN_NO_TMA": "1"})):
+        out = os.path.join(d, "gen_" + tag)
+        cmd = [CLI, "--mode", "mut", "--mut", d + "/syn", "--chr", d + "/chr.txt", "--target_tmp", d + "/t.colate.in",
+               "--reference_tmp", d + "/r.colate.in", "--seed", str(int(z["seed"])), "-o", out] + extra
+        r = subprocess.run(cmd, capture_output=True, text=True, env={**os.environ, **env})
+        assert r.returncode == 0, r.stderr
+        assert open(out + ".coal").read() == open(os.path.join(GOLDEN, f"cli_{name}.coal")).read(), tag
+        outs.append(open(out + ".bin", "rb").read())
+    assert outs[0] == outs[1]
+
+
 def test_cli_masks_and_cache(dataset_dir):
     d, z, sites, gt, gr = dataset_dir
     # masks: per-chromosome fasta files; compare stage i through the API with the same masks

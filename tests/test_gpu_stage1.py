@@ -37,6 +37,22 @@ def test_mt_stream_matches_std_mt19937(handle):
         assert np.array_equal(nxt, want[n:]), (word0, n, k)
 
 
+@pytest.mark.parametrize("split", [1, 2, 4, 8])
+def test_mt_stream_jump_split_factors(handle, split, monkeypatch):
+    """A jump split over P CTAs (the parts of the polynomial meet in global atomics on the zeroed destination window,
+    kernels_mt.cu: k_jump) gives the same windows for every P: the stream behind a 5-level jump tree against std::mt19937."""
+    monkeypatch.setenv("COLATE_JUMP_SPLIT", str(split))
+    st = api.mt_seed(7)
+    for word0, n, k in ((0, 200 * 8 * 300, 3), (200 * 777, 200 * 16 * 37, 4)):
+        got, after = handle.mt_stream(st, word0, n, k)
+        want = np.zeros(n + 50, np.uint32)
+        po.lib().oracle_mt_words(7, word0, n + 50, want)
+        assert np.array_equal(got, want[:n]), (split, word0, n, k)
+        nxt = np.zeros(50, np.uint32)
+        api.lib().colate_mt_generate(after, 50, nxt)
+        assert np.array_equal(nxt, want[n:]), (split, word0, n, k)
+
+
 @pytest.mark.parametrize("seed", [1, 2, 3])
 @pytest.mark.parametrize("masks", [False, True])
 def test_stage1_small_weird(handle, seed, masks):
