@@ -318,12 +318,15 @@ class Handle:
                                          ptr(out_state)))
         return out_state
 
-    def stage2_bootstrap_dev(self, block_weights, stats_ptr, num_blocks, age=0.0):
+    def stage2_bootstrap_dev(self, block_weights, stats_ptr, num_blocks, age=0.0, fetch=False):
         """stage2_bootstrap on block histograms that already sit on the device: stats_ptr = device pointer to
-        [num_blocks][4][185] fp64, or None for what the last stage1 call left in the handle.  Counts stay on the device."""
+        [num_blocks][4][185] fp64, or None for what the last stage1 call left in the handle.  Counts stay on the device
+        (fetch=True: also returned, [R][2][185])."""
         w = np.ascontiguousarray(block_weights, dtype=np.int32)
         assert w.shape[1] == num_blocks
-        check(lib().colate_stage2_bootstrap(self._h, w.shape[0], num_blocks, ptr(w), C.c_void_p(stats_ptr) if stats_ptr else None, age, None))
+        counts = np.zeros((w.shape[0], 2, NBINS)) if fetch else None
+        check(lib().colate_stage2_bootstrap(self._h, w.shape[0], num_blocks, ptr(w), C.c_void_p(stats_ptr) if stats_ptr else None, age, ptr(counts)))
+        return counts
 
     def stage1(self, mt_state, target_slot=0, reference_slot=1, fetch=True) -> Stage1Result:
         """parse_tmptmp (coal.cpp:2072) on one GPU.  fetch=False: the histograms stay on the device

@@ -176,7 +176,7 @@ class OracleHandle:
     def set_stream_cache(self, enable):
         pass
 
-    def stage1(self, mt_state, target_slot=0, reference_slot=1):
+    def stage1(self, mt_state, target_slot=0, reference_slot=1, fetch=True):
         from types import SimpleNamespace
         from colate_b200 import api
         from oracle import pyoracle as po
@@ -185,7 +185,12 @@ class OracleHandle:
         burn = np.zeros(max(1, 200 * o["n_used_total"]), np.uint32)
         api.lib().colate_mt_generate(after, 200 * o["n_used_total"], burn)
         stats = np.stack([o["shared"], o["notshared"], o["shared_emp"], o["notshared_emp"]], axis=1)
-        return SimpleNamespace(num_blocks=o["num_blocks"], n_used=o["n_used_total"], block_stats=stats, mt_state=after)
+        self._resident = stats                      # api.Handle keeps the block histograms on the device (fetch=False)
+        return SimpleNamespace(num_blocks=o["num_blocks"], n_used=o["n_used_total"], block_stats=stats if fetch else None, mt_state=after)
+
+    def stage2_bootstrap_dev(self, w, stats_ptr, num_blocks, age=0.0, fetch=False):
+        assert stats_ptr is None and num_blocks == self._resident.shape[0]
+        return self.stage2_bootstrap(w, self._resident, age)
 
     def stage2_bootstrap(self, w, block_stats, age):
         from oracle import pyoracle as po
