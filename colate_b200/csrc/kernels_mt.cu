@@ -31,8 +31,11 @@ constexpr double JUMP_COEF_US = JUMP_COEF_US_, JUMP_BASE_US = 10.0;   // measure
 
 __device__ __forceinline__ uint32_t mt_mix_dev(uint32_t a, uint32_t b, uint32_t c)
 {
-  uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
-  return c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+  // five instructions instead of seven: the upper-bit / lower-bits merge as ONE bit-select LOP3 (two masks would need two),
+  // the conditional constant as a multiply by the low bit
+  uint32_t y;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(y) : "r"(a), "r"(b), "r"(0x80000000u));   // (a & m) | (b & ~m)
+  return c ^ (y >> 1) ^ ((b & 1u) * 0x9908b0dfu);
 }
 
 __device__ __forceinline__ uint32_t mt_temper_dev(uint32_t z)
