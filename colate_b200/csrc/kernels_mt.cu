@@ -276,6 +276,7 @@ k_gen_tma(const uint32_t* __restrict__ windows, int64_t chunk_words, int64_t tot
   if (start >= total_words) return;
   const int64_t end = min(start + chunk_words, total_words);
   for (int i = tid; i < MT_N; i += blockDim.x) bufA[i] = windows[(size_t)blockIdx.x * MT_N + i];
+  for (int i = tid; i < GEN_RING; i += blockDim.x) ring[i] = 0;   // (the stream's last group may reach past its last word: defined bytes)
   __syncthreads();
   uint32_t* cur = bufA;
   uint32_t* nxt = bufB;
