@@ -416,6 +416,37 @@ def test_make_tmp_from_genotype_records_matches_the_reference_cli(built, tmp_pat
         assert r.returncode == 0 and open(d + "/live.colate.in", "rb").read() == z["plain"].tobytes()
 
 
+def test_shipped_objects_use_the_copy_engines(built):
+    """The sm_100a objects the library is linked from carry what DESIGN.md says the kernels are built on (cuobjdump -sass, no
+    GPU needed): 1-D bulk copies + mbarriers in k_sample and k_replay, a TMA tensor store in k_gen_tma, st.async into peer CTAs
+    and cluster barriers in k_em_split, and no tensor-core instruction anywhere (the path has no contraction)."""
+    import re
+    import shutil
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    csrc = os.path.join(ROOT, "colate_b200", "csrc")
+
+    def kernels(obj):
+        out = subprocess.run(["cuobjdump", "-sass", os.path.join(csrc, obj)], capture_output=True, text=True).stdout
+        assert "sm_100a" in out, obj
+        return {f.split("\n", 1)[0].strip(): f for f in re.split(r"\n\s*Function : ", out)[1:]}
+
+    def body(ks, name):
+        hits = [f for m, f in ks.items() if name in m]
+        assert hits, name
+        return "\n".join(hits)
+
+    sites, mt, em = kernels("kernels_sites.o"), kernels("kernels_mt.o"), kernels("kernels_em.o")
+    for k in ("k_sample", "k_replay"):
+        assert "UBLKCP" in body(sites, k) and "SYNCS" in body(sites, k), k
+    assert "UTMASTG" in body(mt, "k_gen_tma")
+    assert "LDS.128" in body(mt, "k_jump")
+    assert "STAS" in body(em, "k_em_split") and "UCGABAR" in body(em, "k_em_split")
+    for ks in (sites, mt, em):
+        for m, f in ks.items():
+            assert not re.search(r"\b(HMMA|IMMA|DMMA|UTCHMMA|UTCIMMA|QGMMA)", f), m
+
+
 def test_mask_bits_from_fasta(built):
     sites = synth.make_sites(3, [400, 300], [3e5, 2e5])
     masks = [synth.make_mask(1, 300000, 0.4, 50, 500), synth.make_mask(2, 100000, 0.3, 50, 500, lower=True)]   # 2nd: short + lower case
