@@ -412,19 +412,17 @@ def vcfvcf_fixture():
 MAKETMP_VCF_LENS = [3_000_000, 2_000_000]
 
 
-def maketmp_vcf_inputs(d):
+def maketmp_vcf_inputs(d, seed=31, ns=3, pl=2, p_rec=0.8, rows=(1500, 900)):
     """Dataset, genotype records of a 3-sample diploid target (fake BCFs), reference genome and target mask for
     `--mode make_tmp --target_bcf`: records as vcf_records makes them, some rewritten to "the derived / ancestral allele alone"
     (second allele the empty string: coal.cpp:2413), the first chromosome's records ending before its last rows."""
-    seed = 31
     rng = np.random.default_rng(seed)
     lens = MAKETMP_VCF_LENS
-    sites = synth.make_sites(seed, [1500, 900], lens, weird=0.08)
+    sites = synth.make_sites(seed, list(rows), lens, weird=0.08)
     synth.write_dataset(d, sites, {})
-    ns, pl = 3, 2
     recs_all = []
     for c, nm in enumerate(sites.chr_names):
-        recs = vcf_records(rng, sites, c, ns * pl, 0.8, True)
+        recs = vcf_records(rng, sites, c, ns * pl, p_rec, True)
         lo, hi = int(sites.site_off[c]), int(sites.site_off[c + 1])
         by_pos = {int(sites.pos[m]) - 1: m for m in range(lo, hi)}
         out = []

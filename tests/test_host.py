@@ -416,6 +416,41 @@ def test_make_tmp_from_genotype_records_matches_the_reference_cli(built, tmp_pat
         assert r.returncode == 0 and open(d + "/live.colate.in", "rb").read() == z["plain"].tobytes()
 
 
+@pytest.mark.parametrize("seed,ns,pl,p_rec,rows", [(41, 1, 2, 0.5, (700, 300)), (42, 5, 2, 0.95, (400, 900)), (43, 2, 1, 0.2, (1000, 50)),
+                                                  (44, 4, 2, 0.7, (60, 60))])
+def test_make_tmp_from_genotype_records_fuzz_against_the_live_reference(built, tmp_path, seed, ns, pl, p_rec, rows):
+    """colate_maketmp_records against the reference CLI run HERE (oracle/_ref, `--mode make_tmp --target_bcf` through the fake BCF
+    reader) on further random datasets: haploid and diploid samples, sparse and dense record files, with and without a mask."""
+    if not po.ref_cli():
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden
+    d = str(tmp_path)
+    sites, recs, n_hap = make_golden.maketmp_vcf_inputs(d, seed=seed, ns=ns, pl=pl, p_rec=p_rec, rows=rows)
+    n = len(sites.chr_names)
+    arr = lambda xs: (C.c_char_p * n)(*[x.encode() for x in xs])
+    per = lambda stem, ext: arr([os.path.join(d, f"{stem}_chr{c}.{ext}") for c in sites.chr_names])
+    code = lambda a: 0 if len(a) == 0 else a[0] if len(a) == 1 else 0xff
+    off = np.zeros(n + 1, np.int64)
+    off[1:] = np.cumsum([len(r) for r in recs])
+    flat = [r for rs in recs for r in rs]
+    pos = np.array([p0 + 1 for p0, _, _ in flat], np.int32)
+    a0 = np.array([code(al[0]) for _, al, _ in flat], np.uint8)
+    a1 = np.array([code(al[1]) for _, al, _ in flat], np.uint8)
+    alt = np.array([sum(gt) for _, _, gt in flat], np.int32)
+    bi = np.array([max(gt) <= 1 for _, _, gt in flat], np.uint8)
+    nh = np.full(n, n_hap, np.int32)
+    for tag, masks, extra in (("plain", None, []), ("masked", per("tm", "fa"), ["--target_mask", d + "/tm"])):
+        r = subprocess.run([po.ref_cli(), "--mode", "make_tmp", "--mut", d + "/syn", "--chr", d + "/chr.txt", "--target_bcf", d + "/t",
+                            "--ref_genome", d + "/g", "-o", d + "/ref_" + tag] + extra, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-1000:]
+        out = os.path.join(d, tag + ".colate.in")
+        nrec = api.lib().colate_maketmp_records(n, arr(sites.chr_names), per("syn", "mut"), api.ptr(off), api.ptr(pos), api.ptr(a0), api.ptr(a1),
+                                                api.ptr(alt), api.ptr(bi), api.ptr(nh), per("g", "fa"), masks, out.encode())
+        assert nrec >= 0, api.lib().colate_last_error()
+        assert open(out, "rb").read() == open(d + "/ref_" + tag + ".colate.in", "rb").read(), (seed, tag)
+
+
 def test_shipped_objects_use_the_copy_engines(built):
     """The sm_100a objects the library is linked from carry what DESIGN.md says the kernels are built on (cuobjdump -sass, no
     GPU needed): 1-D bulk copies + mbarriers in k_sample and k_replay, a TMA tensor store in k_gen_tma, st.async into peer CTAs
